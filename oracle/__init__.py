@@ -1,0 +1,305 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/liborb_oracle.so, the dependency-free CPU restatement of the reference's ORB
+front-end (oracle/orb_oracle.h).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(native=False, force=False, out_dir=None):
+    """Compile the oracle.  native=True -> -march=native copy (bench CPU baseline, built on the box)."""
+    name = "liborb_oracle_native.so" if native else "liborb_oracle.so"
+    out = os.path.join(out_dir or _HERE, name)
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "match_oracle.cpp", "orb_oracle.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "orbb200_pattern.inc"))
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    cmd = [os.environ.get("CXX", "g++"), "-O3", "-march=native" if native else "-march=x86-64-v3", "-std=c++17",
+           "-ffp-contract=off", "-fPIC", "-shared", "-o", out,
+           os.path.join(_HERE, "orb_oracle.cpp"), os.path.join(_HERE, "match_oracle.cpp")]
+    subprocess.run(cmd, check=True, cwd=_HERE)
+    return out
+
+
+_libs = {}
+
+
+def lib(native=False):
+    if native in _libs:
+        return _libs[native]
+    path = build(native=native)
+    L = C.CDLL(path)
+    u8p, i32p, f32p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p
+    sz = C.c_size_t
+    sig = {
+        "oracle_resize_u8": (None, [vp, C.c_int, C.c_int, sz, vp, C.c_int, C.c_int, sz]),
+        "oracle_gauss7_u8": (None, [vp, C.c_int, C.c_int, sz, vp, sz]),
+        "oracle_fast9": (C.c_int, [vp, C.c_int, C.c_int, sz, C.c_int, C.c_int, vp, C.c_int]),
+        "oracle_fast_score_map": (None, [vp, C.c_int, C.c_int, sz, vp]),
+        "oracle_fast_atan2": (C.c_float, [C.c_float, C.c_float]),
+        "oracle_cv_round": (C.c_int, [C.c_float]),
+        "oracle_extractor_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]),
+        "oracle_extractor_destroy": (None, [vp]),
+        "oracle_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, vp, C.c_int]),
+        "oracle_extractor_features_per_level": (C.c_int, [vp, vp]),
+        "oracle_extractor_scale_factors": (C.c_int, [vp, vp]),
+        "oracle_extractor_umax": (C.c_int, [vp, vp]),
+        "oracle_extractor_level_size": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "oracle_extractor_level_image": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
+        "oracle_extractor_level_candidates": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "oracle_extractor_level_keypoints": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "oracle_distribute_octree": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
+        "oracle_descriptor_distance": (C.c_int, [vp, vp]),
+        "oracle_hamming_knn2": (None, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
+        "oracle_frame_create": (vp, [vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
+        "oracle_frame_destroy": (None, [vp]),
+        "oracle_frame_features_in_area": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]),
+        "oracle_search_by_projection": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                  C.c_float, C.c_float, vp, vp, vp]),
+        "oracle_search_by_projection_frame": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                        C.c_float, C.c_float, C.c_int, C.c_int, vp]),
+        "oracle_birdview_match": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp]),
+        "oracle_search_by_match_bird_kf": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_float, C.c_int, vp]),
+        "oracle_search_by_projection_bird": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]),
+        "oracle_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
+                                                      vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
+                                                      vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _libs[native] = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+# ---- primitives --------------------------------------------------------------------------------
+def resize_u8(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def gauss7_u8(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().oracle_gauss7_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast9(img, threshold, nms=True):
+    """-> int32 [n,3] (x, y, response) in cv::FAST output order"""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    cap = max(16, img.shape[0] * img.shape[1])
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_fast9(C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_score_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape, np.int32)
+    lib().oracle_fast_score_map(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out))
+    return out
+
+
+def fast_atan2(y, x):
+    return lib().oracle_fast_atan2(float(y), float(x))
+
+
+def cv_round(v):
+    return lib().oracle_cv_round(float(v))
+
+
+# ---- extractor ---------------------------------------------------------------------------------
+class Extractor:
+    """Mirror of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:44-111)."""
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, native=False):
+        self._L = lib(native)
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = self._L.oracle_extractor_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.oracle_extractor_destroy(self._h)
+            self._h = None
+
+    def __call__(self, img):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = self.nfeatures * 2 + 4096
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = self._L.oracle_extract(self._h, C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError("oracle_extract: capacity too small")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def features_per_level(self):
+        out = np.empty(self.nlevels, np.int32)
+        self._L.oracle_extractor_features_per_level(self._h, _p(out))
+        return out
+
+    def scale_factors(self):
+        out = np.empty(self.nlevels, np.float32)
+        self._L.oracle_extractor_scale_factors(self._h, _p(out))
+        return out
+
+    def umax(self):
+        out = np.empty(16, np.int32)
+        self._L.oracle_extractor_umax(self._h, _p(out))
+        return out
+
+    def level_image(self, level, blurred=False):
+        w, h = C.c_int(), C.c_int()
+        self._L.oracle_extractor_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        if out.size:
+            self._L.oracle_extractor_level_image(self._h, level, int(blurred), _p(out), out.strides[0])
+        return out
+
+    def level_candidates(self, level):
+        n = self._L.oracle_extractor_level_candidates(self._h, level, None, 0)
+        out = np.empty((max(n, 1), 3), np.int32)
+        self._L.oracle_extractor_level_candidates(self._h, level, _p(out), n)
+        return out[:n]
+
+    def level_keypoints(self, level):
+        n = self._L.oracle_extractor_level_keypoints(self._h, level, None, 0)
+        out = np.empty(max(n, 1), KP_DTYPE)
+        self._L.oracle_extractor_level_keypoints(self._h, level, _p(out), n)
+        return out[:n]
+
+
+def distribute_octree(xyr, minX, maxX, minY, maxY, N):
+    xyr = _c(xyr, np.int32).reshape(-1, 3)
+    out = np.empty((max(len(xyr), 1), 3), np.int32)
+    n = lib().oracle_distribute_octree(_p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:n].copy()
+
+
+# ---- matcher -----------------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    a = _c(a, np.uint8)
+    b = _c(b, np.uint8)
+    return lib().oracle_descriptor_distance(_p(a), _p(b))
+
+
+def hamming_knn2(q, m, native=False):
+    q = _c(q, np.uint8)
+    m = _c(m, np.uint8)
+    nq, nm = len(q), len(m)
+    bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
+    lib(native).oracle_hamming_knn2(_p(q), nq, _p(m), nm, _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
+class Frame:
+    """Flattened Frame: keypoints (undistorted), descriptors, 64x48 grid (reference src/Frame.cc:378-412)."""
+
+    def __init__(self, kps, desc, min_x, min_y, inv_w, inv_h, u_right=None, native=False):
+        self._L = lib(native)
+        self.kps = _c(kps, KP_DTYPE)
+        self.desc = _c(desc, np.uint8)
+        self.n = len(self.kps)
+        self.u_right = _c(u_right, np.float32)
+        self._h = self._L.oracle_frame_create(_p(self.kps), _p(self.desc), self.n, min_x, min_y, inv_w, inv_h, _p(self.u_right))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.oracle_frame_destroy(self._h)
+            self._h = None
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = self._L.oracle_frame_features_in_area(self._h, x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def search_by_projection(F, scale_factors, q_valid, q_u, q_v, q_uR, q_level, q_viewcos, q_desc, q_obs_pos=None,
+                         kp_blocked=None, th=1.0, nnratio=0.8):
+    nq = len(q_u)
+    sf = _c(scale_factors, np.float32)
+    a = [_c(q_valid, np.uint8), _c(q_u, np.float32), _c(q_v, np.float32), _c(q_uR, np.float32), _c(q_level, np.int32),
+         _c(q_viewcos, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8)]
+    bi, bd = np.empty(nq, np.int32), np.empty(nq, np.int32)
+    qk = np.empty(F.n, np.int32)
+    n = F._L.oracle_search_by_projection(F._h, _p(sf), nq, *[_p(x) for x in a], th, nnratio, _p(bi), _p(bd), _p(qk))
+    return n, bi, bd, qk
+
+
+def search_by_projection_frame(Cur, scale_factors, q_valid, q_u, q_v, q_invz, q_octave, q_angle, q_desc, q_obs_pos=None,
+                               kp_blocked=None, th=15.0, mbf=0.0, mode=0, check_ori=True):
+    nq = len(q_u)
+    sf = _c(scale_factors, np.float32)
+    a = [_c(q_valid, np.uint8), _c(q_u, np.float32), _c(q_v, np.float32), _c(q_invz, np.float32), _c(q_octave, np.int32),
+         _c(q_angle, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8)]
+    qk = np.empty(Cur.n, np.int32)
+    n = Cur._L.oracle_search_by_projection_frame(Cur._h, _p(sf), nq, *[_p(x) for x in a], th, mbf, mode, int(check_ori), _p(qk))
+    return n, qk
+
+
+def birdview_match(kps1, desc1, F2, prev_xy=None, window=15, nnratio=0.99, check_ori=True):
+    kps1 = _c(kps1, KP_DTYPE)
+    desc1 = _c(desc1, np.uint8)
+    prev = None if prev_xy is None else np.array(prev_xy, np.float32, copy=True).reshape(-1, 2)
+    m12 = np.empty(len(kps1), np.int32)
+    n = F2._L.oracle_birdview_match(_p(kps1), _p(desc1), len(kps1), F2._h, _p(prev), int(window), nnratio, int(check_ori), _p(m12))
+    return n, m12, prev
+
+
+def search_by_match_bird_kf(kf_kps, has_mp, mp_desc, F, r=15.0, nnratio=0.99, check_ori=True):
+    kf_kps = _c(kf_kps, KP_DTYPE)
+    has_mp = _c(has_mp, np.uint8)
+    mp_desc = _c(mp_desc, np.uint8)
+    out = np.empty(F.n, np.int32)
+    n = F._L.oracle_search_by_match_bird_kf(_p(kf_kps), _p(has_mp), _p(mp_desc), len(kf_kps), F._h, r, nnratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_projection_bird(F, q_valid, q_x, q_y, q_desc, q_obs_pos=None, kp_blocked=None, r=4.0, nnratio=0.99):
+    nq = len(q_x)
+    a = [_c(q_valid, np.uint8), _c(q_x, np.float32), _c(q_y, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8),
+         _c(kp_blocked, np.uint8)]
+    out = np.empty(F.n, np.int32)
+    n = F._L.oracle_search_by_projection_bird(F._h, nq, *[_p(x) for x in a], r, nnratio, _p(out))
+    return n, out
+
+
+def search_for_triangulation(kps1, desc1, uR1, has_mp1, kps2, desc2, uR2, has_mp2, fv1, fv2, F12, ex, ey,
+                             scale_factors2, level_sigma2_2, only_stereo=False, check_ori=False):
+    """fv = (node ids ascending int32[nn], ptr int32[nn+1], idx int32[...])"""
+    kps1, kps2 = _c(kps1, KP_DTYPE), _c(kps2, KP_DTYPE)
+    desc1, desc2 = _c(desc1, np.uint8), _c(desc2, np.uint8)
+    uR1, uR2 = _c(uR1, np.float32), _c(uR2, np.float32)
+    has_mp1, has_mp2 = _c(has_mp1, np.uint8), _c(has_mp2, np.uint8)
+    f1 = [_c(x, np.int32) for x in fv1]
+    f2 = [_c(x, np.int32) for x in fv2]
+    F12 = _c(F12, np.float32).reshape(9)
+    sf2, ls2 = _c(scale_factors2, np.float32), _c(level_sigma2_2, np.float32)
+    pairs = np.empty((max(len(kps1), 1), 2), np.int32)
+    n = lib().oracle_search_for_triangulation(
+        _p(kps1), _p(desc1), _p(uR1), _p(has_mp1), len(kps1), _p(kps2), _p(desc2), _p(uR2), _p(has_mp2), len(kps2),
+        _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]), _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
+        _p(F12), ex, ey, _p(sf2), _p(ls2), int(only_stereo), int(check_ori), _p(pairs))
+    return n, pairs[:n].copy()

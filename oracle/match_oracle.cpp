@@ -1,0 +1,502 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see orb_oracle.h).  Matcher half.
+ *
+ * Restates /root/reference/src/ORBmatcher.cc (Hamming scans) and the Frame lookup grid
+ * (/root/reference/src/Frame.cc:378-412,494-559,879-944) on plain arrays.  The object graph
+ * (MapPoint*, KeyFrame*, cv::Mat) the reference walks is flattened by the caller; every loop below keeps
+ * the reference's iteration order, comparison operators and loop-carried state.
+ */
+#include "orb_oracle.h"
+
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int TH_HIGH = 100;      /* src/ORBmatcher.cc:37 */
+const int TH_LOW = 50;        /* :38 */
+const int HISTO_LENGTH = 30;  /* :39 */
+const int FRAME_GRID_ROWS = 48;  /* include/Frame.h:39 */
+const int FRAME_GRID_COLS = 64;  /* include/Frame.h:40 */
+
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1647-1663 */
+inline int DescriptorDistance(const uint8_t* a, const uint8_t* b)
+{
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t wa, wb;
+        memcpy(&wa, a + 4 * i, 4);
+        memcpy(&wb, b + 4 * i, 4);
+        unsigned int v = wa ^ wb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+/* ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:1601-1642 */
+void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2)
+{
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+/* ORBmatcher::RadiusByViewingCos, src/ORBmatcher.cc:131-137 */
+inline float RadiusByViewingCos(float viewCos) { return viewCos > 0.998 ? 2.5f : 4.0f; }
+
+}  // namespace
+
+struct oracle_frame {
+    int N;
+    std::vector<oracle_kp_t> keys;
+    std::vector<uint8_t> desc;
+    std::vector<float> uRight;
+    float minX, minY, invW, invH;
+    std::vector<int> grid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+
+    /* Frame::PosInGrid / PosInGridBirdview (src/Frame.cc:549-559, 879-889); birdview = minX=minY=0 */
+    bool PosInGrid(const oracle_kp_t& kp, int& posX, int& posY) const
+    {
+        posX = (int)round((kp.x - minX) * invW);
+        posY = (int)round((kp.y - minY) * invH);
+        if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) return false;
+        return true;
+    }
+
+    /* Frame::GetFeaturesInArea / GetFeaturesInAreaBirdview (src/Frame.cc:494-547, 891-944) */
+    void GetFeaturesInArea(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& vIndices) const
+    {
+        vIndices.clear();
+        const int nMinCellX = std::max(0, (int)floor((x - minX - r) * invW));
+        if (nMinCellX >= FRAME_GRID_COLS) return;
+        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - minX + r) * invW));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)floor((y - minY - r) * invH));
+        if (nMinCellY >= FRAME_GRID_ROWS) return;
+        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - minY + r) * invH));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const std::vector<int>& vCell = grid[ix][iy];
+                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
+                    const oracle_kp_t& kpUn = keys[vCell[j]];
+                    if (bCheckLevels) {
+                        if (kpUn.octave < minLevel) continue;
+                        if (maxLevel >= 0)
+                            if (kpUn.octave > maxLevel) continue;
+                    }
+                    const float distx = kpUn.x - x;
+                    const float disty = kpUn.y - y;
+                    if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+                }
+            }
+    }
+};
+
+extern "C" {
+
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) { return DescriptorDistance(a, b); }
+
+void oracle_hamming_knn2(const uint8_t* q, int nq, const uint8_t* m, int nm,
+                         int32_t* best_idx, int32_t* best_d, int32_t* second_d)
+{
+    for (int i = 0; i < nq; i++) {
+        int bestDist = 256, bestDist2 = 256, bestIdx = -1;
+        for (int j = 0; j < nm; j++) {
+            const int dist = DescriptorDistance(q + (size_t)i * 32, m + (size_t)j * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = j; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        best_idx[i] = bestIdx; best_d[i] = bestDist; second_d[i] = bestDist2;
+    }
+}
+
+oracle_frame* oracle_frame_create(const oracle_kp_t* kps, const uint8_t* desc, int n,
+                                  float minX, float minY, float invW, float invH, const float* uRight)
+{
+    oracle_frame* F = new oracle_frame;
+    F->N = n;
+    F->keys.assign(kps, kps + n);
+    F->desc.assign(desc, desc + (size_t)n * 32);
+    F->uRight.assign(n, -1.f);
+    if (uRight) F->uRight.assign(uRight, uRight + n);
+    F->minX = minX; F->minY = minY; F->invW = invW; F->invH = invH;
+    /* Frame::AssignFeaturesToGrid, src/Frame.cc:378-412 */
+    for (int i = 0; i < n; i++) {
+        int gx, gy;
+        if (F->PosInGrid(F->keys[i], gx, gy)) F->grid[gx][gy].push_back(i);
+    }
+    return F;
+}
+
+void oracle_frame_destroy(oracle_frame* F) { delete F; }
+
+int oracle_frame_features_in_area(const oracle_frame* F, float x, float y, float r, int minLevel, int maxLevel,
+                                  int32_t* out, int cap)
+{
+    std::vector<int> v;
+    F->GetFeaturesInArea(x, y, r, minLevel, maxLevel, v);
+    for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+/* src/ORBmatcher.cc:45-129 */
+int oracle_search_by_projection(const oracle_frame* F, const float* scaleFactors, int nq,
+                                const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_uR,
+                                const int32_t* q_level, const float* q_viewcos, const uint8_t* q_desc,
+                                const uint8_t* q_obs_pos, const uint8_t* kp_blocked,
+                                float th, float nnratio,
+                                int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp)
+{
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    /* F.mvpMapPoints[idx] && ->Observations()>0, as it evolves through the loop */
+    std::vector<uint8_t> blocked(F->N, 0);
+    if (kp_blocked) blocked.assign(kp_blocked, kp_blocked + F->N);
+    for (int i = 0; i < F->N; i++) out_query_of_kp[i] = -1;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < nq; iMP++) {
+        out_best_idx[iMP] = -1; out_best_dist[iMP] = 256;
+        if (!q_valid[iMP]) continue;
+        const int nPredictedLevel = q_level[iMP];
+        float r = RadiusByViewingCos(q_viewcos[iMP]);
+        if (bFactor) r *= th;
+        F->GetFeaturesInArea(q_u[iMP], q_v[iMP], r * scaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* MPdescriptor = q_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const int idx = vIndices[k];
+            if (blocked[idx]) continue;
+            if (F->uRight[idx] > 0) {
+                const float er = fabs(q_uR[iMP] - F->uRight[idx]);
+                if (er > r * scaleFactors[nPredictedLevel]) continue;
+            }
+            const int dist = DescriptorDistance(MPdescriptor, &F->desc[(size_t)idx * 32]);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F->keys[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            out_query_of_kp[bestIdx] = iMP;
+            blocked[bestIdx] = q_obs_pos ? q_obs_pos[iMP] : 1;
+            out_best_idx[iMP] = bestIdx; out_best_dist[iMP] = bestDist;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+/* src/ORBmatcher.cc:1328-1470 (projection of Last's map points done by the caller) */
+int oracle_search_by_projection_frame(const oracle_frame* Cur, const float* scaleFactors, int nq,
+                                      const uint8_t* q_valid, const float* q_u, const float* q_v,
+                                      const float* q_invz, const int32_t* q_octave, const float* q_angle,
+                                      const uint8_t* q_desc, const uint8_t* q_obs_pos,
+                                      const uint8_t* kp_blocked, float th, float mbf, int mode, int checkOri,
+                                      int32_t* out_query_of_kp)
+{
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<uint8_t> blocked(Cur->N, 0);
+    if (kp_blocked) blocked.assign(kp_blocked, kp_blocked + Cur->N);
+    for (int i = 0; i < Cur->N; i++) out_query_of_kp[i] = -1;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < nq; i++) {
+        if (!q_valid[i]) continue;
+        const float u = q_u[i], v = q_v[i], invzc = q_invz[i];
+        int nLastOctave = q_octave[i];
+        float radius = th * scaleFactors[nLastOctave];
+        if (mode == 1) Cur->GetFeaturesInArea(u, v, radius, nLastOctave, -1, vIndices2);
+        else if (mode == 2) Cur->GetFeaturesInArea(u, v, radius, 0, nLastOctave, vIndices2);
+        else Cur->GetFeaturesInArea(u, v, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = q_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t k = 0; k < vIndices2.size(); k++) {
+            const int i2 = vIndices2[k];
+            if (blocked[i2]) continue;
+            if (Cur->uRight[i2] > 0) {
+                const float ur = u - mbf * invzc;
+                const float er = fabs(ur - Cur->uRight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = DescriptorDistance(dMP, &Cur->desc[(size_t)i2 * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            out_query_of_kp[bestIdx2] = i;
+            blocked[bestIdx2] = q_obs_pos ? q_obs_pos[i] : 1;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(q_angle[i], Cur->keys[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) { out_query_of_kp[rotHist[i][j]] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+/* src/ORBmatcher.cc:1667-1786 (prev_xy != NULL) and :1788-1899 (prev_xy == NULL) */
+int oracle_birdview_match(const oracle_kp_t* kps1, const uint8_t* desc1, int n1, const oracle_frame* F2,
+                          float* prev_xy, int windowSize, float nnratio, int checkOri, int32_t* vnMatches12)
+{
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(F2->N, INT_MAX);
+    std::vector<int> vnMatches21(F2->N, -1);
+    std::vector<int> vIndices2;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const oracle_kp_t& kp1 = kps1[i1];
+        int level1 = kp1.octave;
+        if (prev_xy) {
+            if (level1 > 0) continue;
+            F2->GetFeaturesInArea(prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)windowSize, level1, level1, vIndices2);
+        } else {
+            F2->GetFeaturesInArea(kp1.x, kp1.y, (float)windowSize, level1, level1, vIndices2);
+        }
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = desc1 + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (size_t k = 0; k < vIndices2.size(); k++) {
+            const int i2 = vIndices2[k];
+            int dist = DescriptorDistance(d1, &F2->desc[(size_t)i2 * 32]);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(kp1.angle, F2->keys[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                int idx1 = rotHist[i][j];
+                if (vnMatches12[idx1] >= 0) { vnMatches21[vnMatches12[idx1]] = -1; vnMatches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    if (prev_xy)
+        for (int i1 = 0; i1 < n1; i1++)
+            if (vnMatches12[i1] >= 0) { prev_xy[2 * i1] = F2->keys[vnMatches12[i1]].x; prev_xy[2 * i1 + 1] = F2->keys[vnMatches12[i1]].y; }
+    return nmatches;
+}
+
+/* src/ORBmatcher.cc:2000-2114 */
+int oracle_search_by_match_bird_kf(const oracle_kp_t* kf_kps, const uint8_t* has_mp, const uint8_t* mp_desc, int nk,
+                                   const oracle_frame* F, float r, float nnratio, int checkOri, int32_t* out_mp_of_kp)
+{
+    for (int i = 0; i < F->N; i++) out_mp_of_kp[i] = -1;
+    std::vector<int> vMatchedDistanceBird(F->N, INT_MAX);
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vIndices;
+    for (int k = 0; k < nk; k++) {
+        if (!has_mp[k]) continue;
+        const oracle_kp_t& kp = kf_kps[k];
+        F->GetFeaturesInArea(kp.x, kp.y, r, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* d1 = mp_desc + (size_t)k * 32;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (size_t j = 0; j < vIndices.size(); j++) {
+            const int idx = vIndices[j];
+            const int dist = DescriptorDistance(d1, &F->desc[(size_t)idx * 32]);
+            if (vMatchedDistanceBird[idx] <= dist) continue;
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F->keys[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel != bestLevel2 || bestDist < (float)bestDist2 * nnratio) {
+                out_mp_of_kp[bestIdx] = k;
+                vMatchedDistanceBird[bestIdx] = bestDist;
+                if (checkOri) rotHist[rot_bin(kp.angle, F->keys[bestIdx].angle)].push_back(bestIdx);
+                nmatches++;
+            }
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { out_mp_of_kp[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+/* src/ORBmatcher.cc:1923-1998 (projection through Tbc*Tcw done by the caller) */
+int oracle_search_by_projection_bird(const oracle_frame* F, int nq, const uint8_t* q_valid,
+                                     const float* q_x, const float* q_y, const uint8_t* q_desc,
+                                     const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float r, float nnratio,
+                                     int32_t* out_query_of_kp)
+{
+    int nmatches = 0;
+    std::vector<uint8_t> blocked(F->N, 0);
+    if (kp_blocked) blocked.assign(kp_blocked, kp_blocked + F->N);
+    for (int i = 0; i < F->N; i++) out_query_of_kp[i] = -1;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < nq; iMP++) {
+        if (!q_valid[iMP]) continue;
+        F->GetFeaturesInArea(q_x[iMP], q_y[iMP], r, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* MPdescriptor = q_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const int idx = vIndices[k];
+            if (blocked[idx]) continue;
+            const int dist = DescriptorDistance(MPdescriptor, &F->desc[(size_t)idx * 32]);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F->keys[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            out_query_of_kp[bestIdx] = iMP;
+            blocked[bestIdx] = q_obs_pos ? q_obs_pos[iMP] : 1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+/* ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:140-157 */
+static bool CheckDistEpipolarLine(const oracle_kp_t& kp1, const oracle_kp_t& kp2, const float* F12, const float* levelSigma2_2)
+{
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * levelSigma2_2[kp2.octave];
+}
+
+/* src/ORBmatcher.cc:657-823 */
+int oracle_search_for_triangulation(const oracle_kp_t* kps1, const uint8_t* desc1, const float* uR1, const uint8_t* has_mp1, int n1,
+                                    const oracle_kp_t* kps2, const uint8_t* desc2, const float* uR2, const uint8_t* has_mp2, int n2,
+                                    const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                                    const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                                    const float* F12, float ex, float ey,
+                                    const float* scaleFactors2, const float* levelSigma2_2,
+                                    int onlyStereo, int checkOri, int32_t* pairs)
+{
+    int nmatches = 0;
+    std::vector<bool> vbMatched2(n2, false);
+    std::vector<int> vMatches12(n1, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int f1 = 0, f2 = 0;
+    while (f1 < nn1 && f2 < nn2) {
+        if (fv1_node[f1] == fv2_node[f2]) {
+            for (int i1 = fv1_ptr[f1]; i1 < fv1_ptr[f1 + 1]; i1++) {
+                const int idx1 = fv1_idx[i1];
+                if (has_mp1[idx1]) continue;
+                const bool bStereo1 = uR1 ? uR1[idx1] >= 0 : false;
+                if (onlyStereo)
+                    if (!bStereo1) continue;
+                const oracle_kp_t& kp1 = kps1[idx1];
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist = TH_LOW;
+                int bestIdx2 = -1;
+                for (int i2 = fv2_ptr[f2]; i2 < fv2_ptr[f2 + 1]; i2++) {
+                    const int idx2 = fv2_idx[i2];
+                    if (vbMatched2[idx2] || has_mp2[idx2]) continue;
+                    const bool bStereo2 = uR2 ? uR2[idx2] >= 0 : false;
+                    if (onlyStereo)
+                        if (!bStereo2) continue;
+                    const uint8_t* d2 = desc2 + (size_t)idx2 * 32;
+                    const int dist = DescriptorDistance(d1, d2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const oracle_kp_t& kp2 = kps2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x;
+                        const float distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scaleFactors2[kp2.octave]) continue;
+                    }
+                    if (CheckDistEpipolarLine(kp1, kp2, F12, levelSigma2_2)) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    const oracle_kp_t& kp2 = kps2[bestIdx2];
+                    vMatches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (checkOri) rotHist[rot_bin(kp1.angle, kp2.angle)].push_back(idx1);
+                }
+            }
+            f1++; f2++;
+        } else if (fv1_node[f1] < fv2_node[f2]) {
+            while (f1 < nn1 && fv1_node[f1] < fv2_node[f2]) f1++;   /* lower_bound */
+        } else {
+            while (f2 < nn2 && fv2_node[f2] < fv1_node[f1]) f2++;
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { vMatches12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    int np = 0;
+    for (int i = 0; i < n1; i++) {
+        if (vMatches12[i] < 0) continue;
+        pairs[2 * np] = i; pairs[2 * np + 1] = vMatches12[i];
+        np++;
+    }
+    return nmatches;
+}
+
+}  // extern "C"

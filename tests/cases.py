@@ -1,0 +1,124 @@
+"""Seeded synthetic matcher cases shared by the oracle tests (CPU) and the GPU parity tests.
+
+Everything is generated from numpy PCG64 streams; no reference files are read at run time.
+"""
+import numpy as np
+
+from helpers import KP_DTYPE, synth
+
+QUOTA_FRAC = np.array([217, 181, 151, 126, 105, 87, 73, 60], np.float64) / 1000.0
+SCALE_FACTORS = np.array([np.float32(1.2) ** 0] * 8, np.float32)
+_s = np.float32(1.0)
+for _i in range(8):
+    SCALE_FACTORS[_i] = _s
+    _s = np.float32(np.float64(_s) * np.float64(np.float32(1.2)))
+
+
+def random_keypoints(n, w, h, seed, integer_level_coords=True):
+    """Keypoints shaped like extractor output: octave histogram from the per-level quota, level-integer
+    coordinates scaled by the level's scale factor, random angle/response."""
+    rng = np.random.default_rng(seed)
+    kps = np.zeros(n, KP_DTYPE)
+    octv = rng.choice(8, size=n, p=QUOTA_FRAC / QUOTA_FRAC.sum()).astype(np.int32)
+    octv.sort()
+    sf = SCALE_FACTORS[octv]
+    lx = rng.integers(19, np.maximum(20, (w / sf).astype(np.int64) - 19))
+    ly = rng.integers(19, np.maximum(20, (h / sf).astype(np.int64) - 19))
+    kps["x"] = (lx.astype(np.float32) * sf).astype(np.float32)
+    kps["y"] = (ly.astype(np.float32) * sf).astype(np.float32)
+    kps["size"] = (31 * sf).astype(np.int32).astype(np.float32)
+    kps["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    kps["response"] = rng.integers(7, 120, n).astype(np.float32)
+    kps["octave"] = octv
+    kps["class_id"] = -1
+    return kps
+
+
+def frame_case(n, w, h, seed, stereo_frac=0.0):
+    """(kps, desc, u_right, grid params) of a synthetic frame"""
+    rng = np.random.default_rng(seed + 7)
+    kps = random_keypoints(n, w, h, seed)
+    desc = synth.synth_descriptors(n, seed + 1)
+    u_right = np.full(n, -1, np.float32)
+    if stereo_frac > 0:
+        m = rng.random(n) < stereo_frac
+        u_right[m] = kps["x"][m] - rng.uniform(1, 40, int(m.sum())).astype(np.float32)
+    grid = dict(min_x=np.float32(0), min_y=np.float32(0),
+                inv_w=np.float32(64) / np.float32(w), inv_h=np.float32(48) / np.float32(h))
+    return kps, desc, u_right, grid
+
+
+def projection_queries(kps, desc, u_right, w, h, nq, seed, on_kp_frac=0.7, max_flips=40, jitter=3.0):
+    """Map-point style queries: a fraction sit on (jittered) frame keypoints with a perturbed copy of that
+    keypoint's descriptor (so windows are non-empty and ratio tests bite), the rest are uniform random."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    src = rng.integers(0, n, nq)
+    on = rng.random(nq) < on_kp_frac
+    u = np.where(on, kps["x"][src] + rng.uniform(-jitter, jitter, nq), rng.uniform(0, w, nq)).astype(np.float32)
+    v = np.where(on, kps["y"][src] + rng.uniform(-jitter, jitter, nq), rng.uniform(0, h, nq)).astype(np.float32)
+    lvl = np.where(on, np.clip(kps["octave"][src] + rng.integers(0, 2, nq), 0, 7), rng.integers(0, 8, nq)).astype(np.int32)
+    qd = synth.perturb_descriptors(desc[src], max_flips, seed + 1)
+    rnd = synth.synth_descriptors(nq, seed + 2)
+    qd = np.where(on[:, None], qd, rnd)
+    viewcos = np.where(rng.random(nq) < 0.5, 0.999, 0.9).astype(np.float32)
+    uR = np.where(u_right[src] > 0, u_right[src] + rng.uniform(-2, 2, nq), u - 10).astype(np.float32)
+    valid = (rng.random(nq) < 0.93).astype(np.uint8)
+    obs_pos = (rng.random(nq) < 0.9).astype(np.uint8)
+    angle = np.where(on, kps["angle"][src] + rng.normal(0, 4, nq), rng.uniform(0, 360, nq)) % 360
+    return dict(valid=valid, u=u, v=v, uR=uR, level=lvl, viewcos=viewcos, desc=qd, obs_pos=obs_pos,
+                angle=angle.astype(np.float32), invz=rng.uniform(0.02, 0.5, nq).astype(np.float32), src=src)
+
+
+def bird_pair(n, size, seed, shift=(3, -2), max_flips=25):
+    """Two consecutive birdview frames: frame 2 = frame 1 shifted by <=5 px with perturbed descriptors,
+    some points dropped/added."""
+    rng = np.random.default_rng(seed)
+    k1, d1, _, grid = frame_case(n, size, size, seed)
+    keep = rng.random(n) < 0.85
+    k2 = k1[keep].copy()
+    k2["x"] = k2["x"] + np.float32(shift[0]) + rng.integers(-1, 2, len(k2)).astype(np.float32)
+    k2["y"] = k2["y"] + np.float32(shift[1]) + rng.integers(-1, 2, len(k2)).astype(np.float32)
+    k2["angle"] = (k2["angle"] + rng.normal(0, 3, len(k2)).astype(np.float32)) % np.float32(360)
+    d2 = synth.perturb_descriptors(d1[keep], max_flips, seed + 3)
+    extra = int(0.15 * n)
+    ke, de, _, _ = frame_case(extra, size, size, seed + 11)
+    k2 = np.concatenate([k2, ke])
+    d2 = np.concatenate([d2, de])
+    perm = rng.permutation(len(k2))
+    return (k1, d1), (k2[perm].copy(), d2[perm].copy()), grid
+
+
+def triangulation_case(n1, n2, w, h, seed, n_nodes=60):
+    rng = np.random.default_rng(seed)
+    k1, d1, uR1, _ = frame_case(n1, w, h, seed, stereo_frac=0.3)
+    src = rng.integers(0, n1, n2)
+    k2 = k1[src].copy()
+    k2["x"] += rng.uniform(-25, 25, n2).astype(np.float32)
+    k2["y"] += rng.uniform(-1.5, 1.5, n2).astype(np.float32)
+    k2["angle"] = (k2["angle"] + rng.normal(0, 5, n2).astype(np.float32)) % np.float32(360)
+    d2 = synth.perturb_descriptors(d1[src], 30, seed + 5)
+    uR2 = np.where(rng.random(n2) < 0.3, k2["x"] - 5, -1).astype(np.float32)
+    node1 = rng.integers(0, n_nodes, n1)
+    node2 = np.where(rng.random(n2) < 0.8, node1[src], rng.integers(0, n_nodes, n2))
+    # drop some node ids from each side so that the lower_bound skips are exercised
+    node1 = np.where(node1 % 7 == 3, node1 + n_nodes, node1)
+    node2 = np.where(node2 % 11 == 5, node2 + 2 * n_nodes, node2)
+
+    def csr(nodes):
+        ids = np.unique(nodes)
+        ptr = [0]
+        idx = []
+        for nid in ids:
+            members = np.nonzero(nodes == nid)[0]
+            idx.extend(members.tolist())
+            ptr.append(len(idx))
+        return ids.astype(np.int32), np.array(ptr, np.int32), np.array(idx, np.int32)
+
+    has1 = (rng.random(n1) < 0.3).astype(np.uint8)
+    has2 = (rng.random(n2) < 0.3).astype(np.uint8)
+    # pure horizontal translation: F12 = [t]_x with t=(1,0,0): epipolar lines are image rows
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)
+    sigma2 = (SCALE_FACTORS * SCALE_FACTORS).astype(np.float32)
+    return dict(k1=k1, d1=d1, uR1=uR1, has1=has1, k2=k2, d2=d2, uR2=uR2, has2=has2, fv1=csr(node1), fv2=csr(node2),
+                F12=F12, ex=np.float32(w * 0.5), ey=np.float32(h * 0.5), sf2=SCALE_FACTORS, sigma2=sigma2)

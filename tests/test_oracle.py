@@ -1,0 +1,236 @@
+"""CPU tests: pin the C++ oracle against the committed golden vectors (cv2 4.13 outputs and the two
+independent Python restatements), and against live cv2 where it is importable."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import GOLDEN, oracle, synth
+
+
+def _npz(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+# ---- OpenCV primitives ------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_primitives_vs_cv2_golden(tag):
+    g = _npz("primitives.npz")
+    img = g[f"img_{tag}"]
+    want = g[f"resize_{tag}"]
+    assert np.array_equal(oracle.resize_u8(img, want.shape[1], want.shape[0]), want)
+    assert np.array_equal(oracle.gauss7_u8(img), g[f"gauss_{tag}"])
+    for th in (7, 20):
+        assert np.array_equal(oracle.fast9(img, th), g[f"fast{th}_{tag}"])
+    cell = img[10:46, 20:57]          # strided view == cv::Mat ROI
+    assert np.array_equal(oracle.fast9(cell, 7), g[f"fastcell_{tag}"])
+
+
+def test_fast_atan2_golden():
+    g = _npz("primitives.npz")
+    got = np.array([oracle.fast_atan2(y, x) for y, x in g["atan_yx"]], np.float32)
+    assert np.array_equal(got.view(np.uint32), g["atan_deg"].view(np.uint32))   # bit-exact
+
+
+def test_cv_round_half_even():
+    assert [oracle.cv_round(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 2.4999, 2.5001)] == [0, 2, 2, 0, -2, 2, 3]
+
+
+def test_fast_score_map_consistent_with_fast9():
+    img = synth.synth_frame(80, 90, 5)
+    sc = oracle.fast_score_map(img)
+    for th in (5, 20):
+        k = oracle.fast9(img, th, nms=False)
+        m = np.zeros_like(sc, bool)
+        m[k[:, 1], k[:, 0]] = True
+        assert np.array_equal(m, sc >= th)
+        assert np.array_equal(sc[k[:, 1], k[:, 0]], k[:, 2])
+
+
+def test_primitives_vs_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for (h, w) in [(480, 752), (376, 1241), (41, 53), (7, 9)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        dw, dh = int(round(w / 1.2)), int(round(h / 1.2))
+        assert np.array_equal(oracle.resize_u8(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+        assert np.array_equal(oracle.gauss7_u8(img), cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    img = synth.synth_frame(120, 160, 9)
+    for th in (5, 7, 12, 20):
+        kps = cv2.FastFeatureDetector_create(th, True).detect(img)
+        want = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], np.int32).reshape(-1, 3)
+        assert np.array_equal(oracle.fast9(img, th), want)
+
+
+# ---- extractor --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_752x480", "bird_400x400", "small_320x240"])
+def test_extractor_vs_python_cv2_golden(name):
+    g = _npz(f"extract_{name}.npz")
+    nf, ini, mn, seed = [int(v) for v in g["params"]]
+    img = g["img"]
+    assert np.array_equal(img, synth.synth_frame(img.shape[0], img.shape[1], seed)), "generator drifted"
+    k, d = oracle.Extractor(nf, 1.2, 8, ini, mn)(img)
+    assert len(k) == len(g["kps"])
+    assert k.tobytes() == g["kps"].tobytes()
+    assert np.array_equal(d, g["desc"])
+
+
+def test_extractor_tables():
+    ex = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    assert ex.features_per_level().tolist() == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert ex.umax().tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert oracle.Extractor(2000).features_per_level().tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert oracle.Extractor(4000).features_per_level().tolist() == [869, 724, 603, 503, 419, 349, 291, 242]
+    assert np.array_equal(ex.scale_factors(), cases.SCALE_FACTORS)
+
+
+def test_extractor_edge_cases():
+    ex = oracle.Extractor(500, 1.2, 8, 20, 7)
+    flat = np.full((240, 320), 128, np.uint8)
+    k, d = ex(flat)
+    assert len(k) == 0 and d.shape == (0, 32)
+    # strided input (ROI of a larger buffer) == contiguous copy
+    big = synth.synth_frame(300, 400, 21)
+    roi = big[10:250, 30:350]
+    k1, d1 = ex(roi)
+    k2, d2 = ex(np.ascontiguousarray(roi))
+    assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    # upper levels too small for one FAST cell: defined as "no keypoints there"
+    small = synth.synth_frame(100, 120, 22)
+    k, _ = ex(small)
+    assert len(k) > 0 and k["octave"].max() < 7
+    # keypoints stay >= 19 px inside their level
+    sf = ex.scale_factors()
+    for lvl in range(8):
+        kl = ex.level_keypoints(lvl)
+        im = ex.level_image(lvl)
+        if len(kl):
+            assert kl["x"].min() >= 19 and kl["x"].max() < im.shape[1] - 19
+            assert kl["y"].min() >= 19 and kl["y"].max() < im.shape[0] - 19
+    assert sf[0] == 1.0
+
+
+def test_octree_quota_and_determinism():
+    img = synth.synth_frame(376, 1241, 2000)
+    ex = oracle.Extractor(2000, 1.2, 8, 20, 7)
+    k, d = ex(img)
+    quota = ex.features_per_level()
+    for lvl in range(8):
+        n = int((k["octave"] == lvl).sum())
+        assert quota[lvl] <= n <= quota[lvl] + 3, (lvl, n, quota[lvl])
+    k2, d2 = ex(img)
+    assert k.tobytes() == k2.tobytes() and np.array_equal(d, d2)
+    # standalone octree entry == what the extractor produced, and is independent of candidate order
+    # except through the "first maximum" rule, which keys on (cell row, cell col, y, x) order
+    c = ex.level_candidates(0)
+    im = ex.level_image(0)
+    out = oracle.distribute_octree(c, 16, im.shape[1] - 16, 16, im.shape[0] - 16, int(quota[0]))
+    kl = ex.level_keypoints(0)
+    assert np.array_equal(out[:, 0] + 16, kl["x"].astype(np.int32)) and np.array_equal(out[:, 1] + 16, kl["y"].astype(np.int32))
+
+
+# ---- matcher ----------------------------------------------------------------------------------------
+def test_descriptor_distance_is_popcount():
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    want = np.unpackbits(a ^ b, axis=1).sum(1)
+    got = [oracle.descriptor_distance(a[i], b[i]) for i in range(200)]
+    assert got == want.tolist()
+    assert oracle.descriptor_distance(a[0], a[0]) == 0
+    assert oracle.descriptor_distance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def test_knn2_vs_numpy():
+    q = synth.synth_descriptors(64, 1)
+    m = synth.synth_descriptors(500, 2)
+    m[100] = q[3]
+    m[200] = q[3]          # duplicate best: first index must win, second == best
+    bi, bd, sd = oracle.hamming_knn2(q, m)
+    D = np.unpackbits(q[:, None, :] ^ m[None, :, :], axis=2).sum(2)
+    assert np.array_equal(bi, D.argmin(1))
+    assert np.array_equal(bd, D.min(1))
+    assert np.array_equal(sd, np.sort(D, 1)[:, 1])
+    assert bi[3] == 100 and bd[3] == 0 and sd[3] == 0
+    bi, bd, sd = oracle.hamming_knn2(q[:2], m[:1])
+    assert sd.tolist() == [256, 256]
+    bi, bd, sd = oracle.hamming_knn2(q[:2], m[:0])
+    assert bi.tolist() == [-1, -1] and bd.tolist() == [256, 256]
+
+
+def _golden_frame():
+    w, h = 620, 188
+    kps, desc, uR, grid = cases.frame_case(500, w, h, 11, stereo_frac=0.4)
+    F = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+    q = cases.projection_queries(kps, desc, uR, w, h, 700, 12)
+    blocked = (np.random.default_rng(13).random(len(kps)) < 0.1).astype(np.uint8)
+    return F, q, blocked
+
+
+def test_features_in_area_vs_python():
+    import matcher_py_ref as mref
+    kps, desc, uR, grid = cases.frame_case(300, 400, 400, 5)
+    F = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"])
+    P = mref.PyFrame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"])
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        x, y = rng.uniform(-30, 430, 2)
+        r = float(rng.choice([4.0, 10.0, 15.0, 37.5]))
+        lo, hi = [(-1, -1), (0, 0), (2, 3), (1, -1), (0, 4)][int(rng.integers(0, 5))]
+        assert F.features_in_area(x, y, r, lo, hi).tolist() == P.features_in_area(x, y, r, lo, hi)
+
+
+def test_matchers_vs_python_golden():
+    g = _npz("matcher.npz")
+    F, q, blocked = _golden_frame()
+    for th in (1.0, 3.0):
+        n, bi, bd, qk = oracle.search_by_projection(F, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"],
+                                                    q["viewcos"], q["desc"], q["obs_pos"], blocked, th, 0.8)
+        want = g[f"sbp_th{int(th)}"]
+        assert n == want[0] and np.array_equal(qk, want[1:])
+    for mode in (0, 1, 2):
+        n, qk = oracle.search_by_projection_frame(F, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["invz"], q["level"],
+                                                  q["angle"], q["desc"], q["obs_pos"], blocked, 7.0, 40.0, mode, True)
+        want = g[f"sbpf_mode{mode}"]
+        assert n == want[0] and np.array_equal(qk, want[1:])
+    (k1, d1), (k2, d2), gr = cases.bird_pair(400, 200, 21)
+    F2 = oracle.Frame(k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+    n, m12, _ = oracle.birdview_match(k1, d1, F2, None, 10, 0.99, True)
+    assert n == g["bird_a"][0] and np.array_equal(m12, g["bird_a"][1:])
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n, m12, prev2 = oracle.birdview_match(k1, d1, F2, prev, 15, 0.99, True)
+    assert n == g["bird_b"][0] and np.array_equal(m12, g["bird_b"][1:]) and np.array_equal(prev2, g["bird_b_prev"])
+    has = (np.random.default_rng(22).random(len(k1)) < 0.6).astype(np.uint8)
+    n, mk = oracle.search_by_match_bird_kf(k1, has, d1, F2, 15.0, 0.99, True)
+    assert n == g["bird_kf"][0] and np.array_equal(mk, g["bird_kf"][1:])
+    n, qk = oracle.search_by_projection_bird(F2, has, k1["x"] + 3, k1["y"] - 2, d1, None, None, 4.0, 0.99)
+    assert n == g["bird_proj"][0] and np.array_equal(qk, g["bird_proj"][1:])
+    t = cases.triangulation_case(300, 300, 620, 188, 31)
+    for only_stereo in (0, 1):
+        n, pairs = oracle.search_for_triangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"],
+                                                   t["fv1"], t["fv2"], t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"],
+                                                   bool(only_stereo), True)
+        want = g[f"tri_{only_stereo}"]
+        assert n == want[0, 0] and np.array_equal(pairs, want[1:])
+
+
+def test_matchers_vs_python_live_small():
+    """Fresh seeds (not the committed ones) on small cases, both restatements run here."""
+    import matcher_py_ref as mref
+    for seed in (101, 202):
+        kps, desc, uR, grid = cases.frame_case(200, 300, 200, seed, stereo_frac=0.5)
+        F = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+        P = mref.PyFrame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+        q = cases.projection_queries(kps, desc, uR, 300, 200, 300, seed + 1, jitter=2.0)
+        n, bi, bd, qk = oracle.search_by_projection(F, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"],
+                                                    q["viewcos"], q["desc"], q["obs_pos"], None, 2.0, 0.7)
+        n2, qk2 = mref.search_by_projection(P, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
+                                            q["desc"], q["obs_pos"], None, 2.0, 0.7)
+        assert n == n2 and qk.tolist() == qk2
+        (k1, d1), (k2, d2), gr = cases.bird_pair(150, 120, seed + 2, max_flips=10)
+        F2 = oracle.Frame(k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+        P2 = mref.PyFrame(k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+        n, m12, _ = oracle.birdview_match(k1, d1, F2, None, 20, 0.9, True)
+        n2, m122, _ = mref.birdview_match(k1, d1, P2, None, 20, 0.9, True)
+        assert n == n2 and m12.tolist() == m122
