@@ -1,0 +1,186 @@
+/* orbb200 -- C ABI of the B200-native ORB front-end (extraction + Hamming matching).
+ *
+ * Drop-in boundary for the data-parallel hot path of donglinb/ORB-SLAM-BIRDVIEW.  The reference has no
+ * FFI layer: the boundary is two C++ classes, ORB_SLAM2::ORBextractor (include/ORBextractor.h:44-111) and
+ * ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:38-120).  The host shims in
+ * orb-slam-birdview_b200/cpp/ keep those class signatures and call the functions below; each entry cites
+ * the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; return 0 on success, a negative
+ * orbb200_status otherwise (never throws or aborts); all buffers are caller-owned.  "host" entry points
+ * take host pointers and are synchronous; "_device" entry points take device pointers, enqueue on the
+ * context's stream and return immediately (orbb200_sync waits).  A context is used by one host thread at
+ * a time (the reference uses one ORBextractor per camera/thread: src/Tracking.cc:121-127,
+ * src/Frame.cc:124-127); any number of contexts may exist per process and per GPU.
+ * There is no CPU fallback: without a CUDA device every call fails with ORBB200_ERR_CUDA.
+ */
+#ifndef ORBB200_H
+#define ORBB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ORBB200_OK = 0,
+    ORBB200_ERR_CUDA = -1,        /* CUDA runtime error or no device; see orbb200_last_error */
+    ORBB200_ERR_ARG = -2,         /* bad argument (null pointer, size over the context's limits, ...) */
+    ORBB200_ERR_CAPACITY = -3,    /* caller buffer too small for the result */
+    ORBB200_ERR_UNSUPPORTED = -4  /* geometry outside what the reference defines */
+} orbb200_status;
+
+/* Binary layout of cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orbb200_kp_t;
+
+typedef struct orbb200_ctx orbb200_ctx;
+typedef struct orbb200_frame orbb200_frame;
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (src/ORBextractor.cc:410-470).  max_w/max_h/max_batch size the device buffers (HBM resident pyramid,
+ * blurred pyramid, candidate and keypoint pools for max_batch images). */
+int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFactor, int nlevels,
+                   int iniThFAST, int minThFAST, int max_w, int max_h, int max_batch);
+void orbb200_destroy(orbb200_ctx* ctx);
+const char* orbb200_last_error(const orbb200_ctx* ctx);   /* ctx may be NULL: last create() error */
+int orbb200_sync(orbb200_ctx* ctx);
+/* cudaStream_t of the context, as void* (for callers that enqueue their own work around ours) */
+void* orbb200_stream(orbb200_ctx* ctx);
+
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:63-82); which: 0..3 in that order */
+int orbb200_get_levels(const orbb200_ctx* ctx);
+int orbb200_get_scale_table(const orbb200_ctx* ctx, int which, float* out /*[nlevels]*/);
+int orbb200_get_features_per_level(const orbb200_ctx* ctx, int32_t* out /*[nlevels]*/);
+/* maximum keypoints one image can produce with this context (sum over levels of quota + slack) */
+int orbb200_max_keypoints(const orbb200_ctx* ctx);
+
+/* ---- extraction ---------------------------------------------------------------------------------
+ * Replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (src/ORBextractor.cc:1043-1105;
+ * the mask is ignored by the reference too).  img: CV_8UC1 rows of `stride` bytes.  Writes *n_out
+ * keypoints (reference order: level 0..L-1, each level in octree list order) and n_out*32 descriptor bytes. */
+int orbb200_extract(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride,
+                    orbb200_kp_t* kps, uint8_t* desc, int cap, int* n_out);
+/* n images of one shape in one pass (frame batches, stereo pairs).  Results for image i start at
+ * kps[i*cap_per_img] / desc[i*cap_per_img*32]; n_out[i] keypoints each. */
+int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                          orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out);
+/* Device-resident variant: d_imgs holds n images, image i at d_imgs + i*img_bytes, rows of `stride` bytes.
+ * Results stay in the context's device pools (orbb200_results_device) for the matchers. Asynchronous. */
+int orbb200_extract_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_bytes, int n, int w, int h, size_t stride);
+/* Device pointers of the last extraction: kps [max_batch][cap] , desc [max_batch][cap][32], counts [max_batch] */
+int orbb200_results_device(orbb200_ctx* ctx, const orbb200_kp_t** d_kps, const uint8_t** d_desc,
+                           const int32_t** d_counts, int* cap_per_img);
+/* Copy the results of the last extraction (either variant) to host buffers. */
+int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out);
+/* Lazy download of one pyramid level of image `img_index` of the last extraction: what the reference keeps
+ * in the public member mvImagePyramid (include/ORBextractor.h:85; read by Frame::ComputeStereoMatches,
+ * src/Frame.cc:669-776).  blurred!=0 returns the GaussianBlur'ed copy used for the descriptors. */
+int orbb200_pyramid_level(orbb200_ctx* ctx, int img_index, int level, int blurred,
+                          uint8_t* dst, size_t dst_stride, int* w, int* h);
+/* Debug/inspection: FAST candidates of one level as packed (x,y,response) int32 triples in region
+ * coordinates, unordered.  Returns the count (or a negative status). */
+int orbb200_level_candidates(orbb200_ctx* ctx, int img_index, int level, int32_t* xyr, int cap);
+
+/* ---- brute-force Hamming (C4) -------------------------------------------------------------------
+ * ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1647-1663) over all nq x nm pairs; per query the best
+ * index (first minimum in index order), best distance and second-best distance (256 when absent). */
+int orbb200_hamming_knn2(orbb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* m, int nm,
+                         int32_t* best_idx, int32_t* best_d, int32_t* second_d);
+int orbb200_hamming_knn2_device(orbb200_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm,
+                                int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
+
+/* ---- frames: keypoints + descriptors + 64x48 lookup grid on the device ---------------------------
+ * Replaces Frame::AssignFeaturesToGrid / PosInGrid[Birdview] (src/Frame.cc:378-412,549-559,879-889) and is
+ * what Frame::GetFeaturesInArea[Birdview] (src/Frame.cc:494-547,891-944) scans.  Front camera:
+ * (min_x,min_y,inv_w,inv_h) = (mnMinX,mnMinY,mfGridElementWidthInv,mfGridElementHeightInv); birdview:
+ * (0,0,mfGridElementWidthInvBirdview,mfGridElementHeightInvBirdview).  u_right may be NULL (all -1). */
+int orbb200_frame_upload(orbb200_ctx* ctx, orbb200_frame** f, const orbb200_kp_t* kps, const uint8_t* desc,
+                         const float* u_right, int n, float min_x, float min_y, float inv_w, float inv_h);
+/* Frame over image `img_index` of the last extraction without leaving the device. */
+int orbb200_frame_from_extract(orbb200_ctx* ctx, orbb200_frame** f, int img_index,
+                               float min_x, float min_y, float inv_w, float inv_h);
+void orbb200_frame_free(orbb200_frame* f);
+/* GetFeaturesInArea for one query (testing aid; order = reference scan order).  Returns the count. */
+int orbb200_frame_features_in_area(orbb200_ctx* ctx, const orbb200_frame* f, float x, float y, float r,
+                                   int min_level, int max_level, int32_t* out, int cap);
+
+/* ---- windowed searches ----------------------------------------------------------------------------
+ * All take host arrays of nq flattened queries and write host results.  q_desc is [nq][32].
+ * *_obs_pos / kp_blocked carry the loop-carried "keypoint already holds a map point with
+ * Observations()>0" state of the reference loops (may be NULL: all 1 / all 0). */
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).
+ * out_query_of_kp[n]: query finally assigned to each keypoint (F.mvpMapPoints), -1 none. Returns nmatches
+ * through *nmatches. */
+int orbb200_search_by_projection(orbb200_ctx* ctx, const orbb200_frame* F, int nq,
+                                 const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_uR,
+                                 const int32_t* q_level, const float* q_viewcos, const uint8_t* q_desc,
+                                 const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float th, float nnratio,
+                                 int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp,
+                                 int* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (src/ORBmatcher.cc:1328-1470);
+ * the caller projects Last's map points (u, v, 1/z).  mode 0: levels [oct-1,oct+1]; 1: forward (>=oct);
+ * 2: backward ([0,oct]).  check_ori: rotation-histogram filter (:1431-1467). */
+int orbb200_search_by_projection_frame(orbb200_ctx* ctx, const orbb200_frame* Cur, int nq,
+                                       const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_invz,
+                                       const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                                       const uint8_t* q_obs_pos, const uint8_t* kp_blocked,
+                                       float th, float mbf, int mode, int check_ori,
+                                       int32_t* out_query_of_kp, int* nmatches);
+
+/* ORBmatcher::BirdviewMatch(F1,F2,vnMatches12,vPrevMatched,windowSize) (src/ORBmatcher.cc:1667-1786) when
+ * prev_xy != NULL (octave-0 queries, window around prev_xy[i], prev_xy updated in place), and
+ * ORBmatcher::BirdviewMatch(const F1,const F2,vnMatches12,windowSize) (:1788-1899) when prev_xy == NULL.
+ * F1 is given by its keypoints/descriptors (host), F2 as a device frame. */
+int orbb200_birdview_match(orbb200_ctx* ctx, const orbb200_kp_t* kps1, const uint8_t* desc1, int n1,
+                           const orbb200_frame* F2, float* prev_xy, int window_size, float nnratio, int check_ori,
+                           int32_t* matches12, int* nmatches);
+
+/* ORBmatcher::SearchByMatchBird(KeyFrame*, Frame&, vector<MapPointBird*>&, r) (src/ORBmatcher.cc:2000-2114) */
+int orbb200_search_by_match_bird_kf(orbb200_ctx* ctx, const orbb200_kp_t* kf_kps, const uint8_t* has_mp,
+                                    const uint8_t* mp_desc, int nk, const orbb200_frame* F, float r, float nnratio,
+                                    int check_ori, int32_t* out_mp_of_kp, int* nmatches);
+
+/* ORBmatcher::SearchByProjectionBird(Frame&, const vector<MapPointBird*>&, r) (src/ORBmatcher.cc:1923-1998);
+ * the caller projects the landmarks through Tbc*Tcw and sets q_valid. */
+int orbb200_search_by_projection_bird(orbb200_ctx* ctx, const orbb200_frame* F, int nq, const uint8_t* q_valid,
+                                      const float* q_x, const float* q_y, const uint8_t* q_desc,
+                                      const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float r, float nnratio,
+                                      int32_t* out_query_of_kp, int* nmatches);
+
+/* ORBmatcher::SearchForTriangulation(KF1,KF2,F12,pairs,bOnlyStereo) (src/ORBmatcher.cc:657-823).  Feature
+ * vectors as CSR over ascending vocabulary node ids.  pairs: [n1][2] (idx1, idx2), *npairs written. */
+int orbb200_search_for_triangulation(orbb200_ctx* ctx,
+                                     const orbb200_kp_t* kps1, const uint8_t* desc1, const float* uR1, const uint8_t* has_mp1, int n1,
+                                     const orbb200_kp_t* kps2, const uint8_t* desc2, const float* uR2, const uint8_t* has_mp2, int n2,
+                                     const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                                     const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                                     const float* F12, float ex, float ey,
+                                     const float* scale_factors2, const float* level_sigma2_2,
+                                     int only_stereo, int check_ori, int32_t* pairs, int* npairs);
+
+/* ---- batched front-end step (bench / sequence processing) -----------------------------------------
+ * One pass of the C2 hot path over a batch: extract 2*n_frames images (left,right interleaved: image 2i is
+ * the left image of frame i), build the left frame's grid and run SearchByProjection of nq_per_frame
+ * queries against it, all on the device.  Query arrays are [n_frames][nq_per_frame] device arrays. */
+typedef struct {
+    const uint8_t* q_valid; const float* q_u; const float* q_v; const float* q_uR;
+    const int32_t* q_level; const float* q_viewcos; const uint8_t* q_desc; const uint8_t* q_obs_pos;
+} orbb200_proj_queries;
+int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_bytes, int n_frames, int w, int h,
+                               size_t stride, const orbb200_proj_queries* d_queries, int nq_per_frame,
+                               float th, float nnratio, float min_x, float min_y, float inv_w, float inv_h,
+                               int32_t* d_out_best_idx /*[n_frames][nq]*/, int32_t* d_out_best_dist,
+                               int32_t* d_nmatches /*[n_frames]*/);
+
+/* Number of kernel launches this context has enqueued since creation (bench bookkeeping). */
+long long orbb200_launch_count(const orbb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,374 @@
+"""orb-slam-birdview_b200 -- B200-native ORB front-end (extraction + Hamming matching).
+
+Python host side over the C ABI of liborbb200.so (include/orbb200.h).  The classes mirror the reference's
+C++ interface for the hot path -- ORB_SLAM2::ORBextractor (include/ORBextractor.h:44-111) and
+ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:38-120) -- on numpy arrays: same names, argument meaning and
+error behaviour.  There is no CPU path: importing works anywhere, but every compute call needs the CUDA
+library and a device and raises OrbB200Error otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["ORBextractor", "ORBmatcher", "Frame", "Context", "OrbB200Error", "KP_DTYPE", "load_library", "build"]
+
+_HERE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "orb-slam-birdview_b200") \
+    if os.path.basename(os.path.dirname(os.path.abspath(__file__))) != "orb-slam-birdview_b200" else os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbb200.so")
+
+# == cv::KeyPoint, 28 bytes
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30           # src/ORBmatcher.cc:37-39
+FRAME_GRID_ROWS, FRAME_GRID_COLS = 48, 64             # include/Frame.h:39-40
+
+
+class OrbB200Error(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree (nvcc, sm_100a)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("orbb200_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+_lib = None
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_SIGNATURES = {
+    "orbb200_create": (_i, [C.POINTER(_vp), _i, _i, _f, _i, _i, _i, _i, _i, _i]),
+    "orbb200_destroy": (None, [_vp]),
+    "orbb200_last_error": (C.c_char_p, [_vp]),
+    "orbb200_sync": (_i, [_vp]),
+    "orbb200_stream": (_vp, [_vp]),
+    "orbb200_get_levels": (_i, [_vp]),
+    "orbb200_get_scale_table": (_i, [_vp, _i, _vp]),
+    "orbb200_get_features_per_level": (_i, [_vp, _vp]),
+    "orbb200_max_keypoints": (_i, [_vp]),
+    "orbb200_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbb200_extract_batch": (_i, [_vp, C.POINTER(_vp), _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
+    "orbb200_extract_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz]),
+    "orbb200_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i)]),
+    "orbb200_download_results": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "orbb200_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "orbb200_level_candidates": (_i, [_vp, _i, _i, _vp, _i]),
+    "orbb200_hamming_knn2": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "orbb200_hamming_knn2_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "orbb200_measure_popc_peak": (C.c_double, [_vp]),
+    "orbb200_frame_upload": (_i, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _i, _f, _f, _f, _f]),
+    "orbb200_frame_from_extract": (_i, [_vp, C.POINTER(_vp), _i, _f, _f, _f, _f]),
+    "orbb200_frame_free": (None, [_vp]),
+    "orbb200_frame_features_in_area": (_i, [_vp, _vp, _f, _f, _f, _i, _i, _vp, _i]),
+    "orbb200_search_by_projection": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_search_by_projection_frame": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp, C.POINTER(_i)]),
+    "orbb200_birdview_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _i, _vp, C.POINTER(_i)]),
+    "orbb200_search_by_match_bird_kf": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _f, _f, _i, _vp, C.POINTER(_i)]),
+    "orbb200_search_by_projection_bird": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, C.POINTER(_i)]),
+    "orbb200_search_for_triangulation": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i,
+                                              _vp, _f, _f, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
+    "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "orbb200_launch_count": (C.c_longlong, [_vp]),
+}
+
+
+class ProjQueries(C.Structure):
+    """orbb200_proj_queries: device pointers of [n_frames][nq] query arrays"""
+    _fields_ = [(n, C.c_void_p) for n in ("q_valid", "q_u", "q_v", "q_uR", "q_level", "q_viewcos", "q_desc", "q_obs_pos")]
+
+
+def load_library():
+    """dlopen liborbb200.so; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbB200Error(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                           "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """orbb200_ctx: one per host thread; owns a CUDA stream and the HBM-resident pools."""
+
+    def __init__(self, nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, max_w, max_h, max_batch=1, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.orbb200_create(C.byref(h), device, nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, max_w, max_h, max_batch)
+        if rc != 0:
+            raise OrbB200Error(f"orbb200_create failed ({rc}): {self._L.orbb200_last_error(None).decode()}")
+        self._h = h
+        self.nlevels, self.max_batch, self.device = nlevels, max_batch, device
+        self.max_keypoints = self._L.orbb200_max_keypoints(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def check(self, rc, what=""):
+        if rc < 0:
+            raise OrbB200Error(f"{what} failed ({rc}): {self._L.orbb200_last_error(self._h).decode()}")
+        return rc
+
+    def sync(self):
+        self.check(self._L.orbb200_sync(self._h), "sync")
+
+    @property
+    def launches(self):
+        return self._L.orbb200_launch_count(self._h)
+
+    def scale_table(self, which):
+        out = np.empty(self.nlevels, np.float32)
+        self.check(self._L.orbb200_get_scale_table(self._h, which, _p(out)))
+        return out
+
+    def features_per_level(self):
+        out = np.empty(self.nlevels, np.int32)
+        self.check(self._L.orbb200_get_features_per_level(self._h, _p(out)))
+        return out
+
+    def popc_peak_gops(self):
+        return self._L.orbb200_measure_popc_peak(self._h)
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:44-111).
+
+    `extractor(image, mask=None)` is operator()(image, mask, keypoints, descriptors): returns
+    (keypoints[KP_DTYPE], descriptors[N,32] uint8).  The mask is ignored, as in the reference
+    (include/ORBextractor.h:58).  One instance per camera/thread, as in the reference."""
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_size=(1920, 1080), max_batch=1, device=0):
+        self.ctx = Context(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_size[0], max_size[1], max_batch, device)
+        self._L = self.ctx._L
+        self._scaleFactor = scaleFactor
+        self.last_n = 0
+
+    # -- getters (include/ORBextractor.h:63-82) --
+    def GetLevels(self):
+        return self.ctx.nlevels
+
+    def GetScaleFactor(self):
+        return self._scaleFactor
+
+    def GetScaleFactors(self):
+        return self.ctx.scale_table(0)
+
+    def GetInverseScaleFactors(self):
+        return self.ctx.scale_table(1)
+
+    def GetScaleSigmaSquares(self):
+        return self.ctx.scale_table(2)
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.ctx.scale_table(3)
+
+    def __call__(self, image, mask=None):
+        if image is None or image.size == 0:
+            return np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)     # empty image: silent return (:1046-1047)
+        assert image.dtype == np.uint8 and image.ndim == 2, "image.type() == CV_8UC1"   # (:1050)
+        k, d, n = self.extract_batch([image])
+        return k[0, :n[0]].copy(), d[0, :n[0]].copy()
+
+    def extract_batch(self, images):
+        """n same-shape images -> (kps [n,cap], desc [n,cap,32], counts [n])"""
+        n = len(images)
+        h, w = images[0].shape
+        imgs = []
+        for im in images:
+            assert im.dtype == np.uint8 and im.shape == (h, w)
+            imgs.append(im if im.strides[1] == 1 else np.ascontiguousarray(im))
+        stride = imgs[0].strides[0]
+        imgs = [im if im.strides[0] == stride else np.ascontiguousarray(im) for im in imgs]
+        stride = imgs[0].strides[0] if all(im.strides[0] == imgs[0].strides[0] for im in imgs) else None
+        if stride is None:
+            imgs = [np.ascontiguousarray(im) for im in imgs]
+            stride = w
+        cap = self.ctx.max_keypoints
+        kps = np.empty((n, cap), KP_DTYPE)
+        desc = np.empty((n, cap, 32), np.uint8)
+        counts = np.empty(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        self.ctx.check(self._L.orbb200_extract_batch(self.ctx._h, ptrs, n, w, h, stride, _p(kps), _p(desc), cap, _p(counts)), "extract")
+        self.last_n = n
+        return kps, desc, counts
+
+    def image_pyramid(self, img_index=0, blurred=False):
+        """mvImagePyramid (include/ORBextractor.h:85) of the last extraction, downloaded on demand."""
+        out = []
+        for lvl in range(self.ctx.nlevels):
+            w, h = C.c_int(), C.c_int()
+            self.ctx.check(self._L.orbb200_pyramid_level(self.ctx._h, img_index, lvl, int(blurred), None, 0, C.byref(w), C.byref(h)))
+            a = np.empty((max(h.value, 0), max(w.value, 0)), np.uint8)
+            if a.size:
+                self.ctx.check(self._L.orbb200_pyramid_level(self.ctx._h, img_index, lvl, int(blurred), _p(a), a.strides[0], None, None))
+            out.append(a)
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return self.image_pyramid(0, False)
+
+    def level_candidates(self, img_index, level):
+        n = self.ctx.check(self._L.orbb200_level_candidates(self.ctx._h, img_index, level, None, 0))
+        out = np.empty((max(n, 1), 3), np.int32)
+        self.ctx.check(self._L.orbb200_level_candidates(self.ctx._h, img_index, level, _p(out), n))
+        return out[:n]
+
+
+class Frame:
+    """Device-resident flattened Frame: keypoints, descriptors, 64x48 lookup grid
+    (Frame::AssignFeaturesToGrid, reference src/Frame.cc:378-412)."""
+
+    def __init__(self, ctx, kps=None, desc=None, min_x=0.0, min_y=0.0, inv_w=1.0, inv_h=1.0, u_right=None, from_extract=None):
+        self.ctx = ctx
+        self._L = ctx._L
+        h = C.c_void_p()
+        if from_extract is not None:
+            ctx.check(self._L.orbb200_frame_from_extract(ctx._h, C.byref(h), int(from_extract), min_x, min_y, inv_w, inv_h), "frame_from_extract")
+            self.n = ctx.max_keypoints
+        else:
+            self.kps, self.desc = _c(kps, KP_DTYPE), _c(desc, np.uint8)
+            self.u_right = _c(u_right, np.float32)
+            self.n = len(self.kps)
+            ctx.check(self._L.orbb200_frame_upload(ctx._h, C.byref(h), _p(self.kps), _p(self.desc), _p(self.u_right), self.n,
+                                                   min_x, min_y, inv_w, inv_h), "frame_upload")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbb200_frame_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = self.ctx.check(self._L.orbb200_frame_features_in_area(self.ctx._h, self._h, x, y, r, minLevel, maxLevel, _p(out), len(out)))
+        return out[:n].copy()
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:38-120) on flattened inputs.
+
+    The reference walks MapPoint*/KeyFrame* graphs; here the caller passes the same data as arrays (the
+    C++ shim in cpp/ does that flattening for the real classes).  Method names and arguments follow the
+    reference; results are returned instead of written into Frame members."""
+
+    TH_LOW, TH_HIGH, HISTO_LENGTH = TH_LOW, TH_HIGH, HISTO_LENGTH
+
+    def __init__(self, ctx, nnratio=0.6, checkOri=True):
+        self.ctx = ctx
+        self._L = ctx._L
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        raise OrbB200Error("single-pair DescriptorDistance stays on the host in the reference shim; use knn2/search calls")
+
+    def hamming_knn2(self, q, m):
+        q, m = _c(q, np.uint8), _c(m, np.uint8)
+        nq, nm = len(q), len(m)
+        bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
+        self.ctx.check(self._L.orbb200_hamming_knn2(self.ctx._h, _p(q), nq, _p(m), nm, _p(bi), _p(bd), _p(sd)), "hamming_knn2")
+        return bi, bd, sd
+
+    def SearchByProjection(self, F, q_valid, q_u, q_v, q_uR, q_level, q_viewcos, q_desc, q_obs_pos=None, kp_blocked=None, th=1.0):
+        """SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129)
+        -> (nmatches, best_idx[nq], best_dist[nq], query_of_kp[n])"""
+        nq = len(q_u)
+        a = [_c(q_valid, np.uint8), _c(q_u, np.float32), _c(q_v, np.float32), _c(q_uR, np.float32), _c(q_level, np.int32),
+             _c(q_viewcos, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8)]
+        bi, bd = np.empty(nq, np.int32), np.empty(nq, np.int32)
+        qk = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_by_projection(self.ctx._h, F._h, nq, *[_p(x) for x in a], th, self.mfNNratio,
+                                                            _p(bi), _p(bd), _p(qk), C.byref(nm)), "SearchByProjection")
+        return nm.value, bi, bd, qk[:F.n]
+
+    def SearchByProjectionFrame(self, Cur, q_valid, q_u, q_v, q_invz, q_octave, q_angle, q_desc, q_obs_pos=None, kp_blocked=None,
+                                th=15.0, mbf=0.0, mode=0):
+        """SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (src/ORBmatcher.cc:1328-1470)"""
+        nq = len(q_u)
+        a = [_c(q_valid, np.uint8), _c(q_u, np.float32), _c(q_v, np.float32), _c(q_invz, np.float32), _c(q_octave, np.int32),
+             _c(q_angle, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8)]
+        qk = np.full(max(Cur.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_by_projection_frame(self.ctx._h, Cur._h, nq, *[_p(x) for x in a], th, mbf, mode,
+                                                                  int(self.mbCheckOrientation), _p(qk), C.byref(nm)), "SearchByProjection")
+        return nm.value, qk[:Cur.n]
+
+    def BirdviewMatch(self, kps1, desc1, F2, windowSize, vPrevMatched=None):
+        """BirdviewMatch (src/ORBmatcher.cc:1667-1786 with vPrevMatched, :1788-1899 without)
+        -> (nmatches, vnMatches12, vPrevMatched')"""
+        kps1, desc1 = _c(kps1, KP_DTYPE), _c(desc1, np.uint8)
+        prev = None if vPrevMatched is None else np.array(vPrevMatched, np.float32, copy=True).reshape(-1, 2)
+        m12 = np.full(max(len(kps1), 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_birdview_match(self.ctx._h, _p(kps1), _p(desc1), len(kps1), F2._h, _p(prev), int(windowSize),
+                                                      self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)), "BirdviewMatch")
+        return nm.value, m12[:len(kps1)], prev
+
+    def SearchByMatchBird(self, kf_kps, has_mp, mp_desc, F, r):
+        """SearchByMatchBird(KeyFrame*, Frame&, out, r) (src/ORBmatcher.cc:2000-2114)"""
+        kf_kps, has_mp, mp_desc = _c(kf_kps, KP_DTYPE), _c(has_mp, np.uint8), _c(mp_desc, np.uint8)
+        out = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_by_match_bird_kf(self.ctx._h, _p(kf_kps), _p(has_mp), _p(mp_desc), len(kf_kps), F._h, r,
+                                                               self.mfNNratio, int(self.mbCheckOrientation), _p(out), C.byref(nm)), "SearchByMatchBird")
+        return nm.value, out[:F.n]
+
+    def SearchByProjectionBird(self, F, q_valid, q_x, q_y, q_desc, q_obs_pos=None, kp_blocked=None, r=4.0):
+        """SearchByProjectionBird(Frame&, vector<MapPointBird*>&, r) (src/ORBmatcher.cc:1923-1998)"""
+        nq = len(q_x)
+        a = [_c(q_valid, np.uint8), _c(q_x, np.float32), _c(q_y, np.float32), _c(q_desc, np.uint8), _c(q_obs_pos, np.uint8),
+             _c(kp_blocked, np.uint8)]
+        out = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_by_projection_bird(self.ctx._h, F._h, nq, *[_p(x) for x in a], r, self.mfNNratio,
+                                                                 _p(out), C.byref(nm)), "SearchByProjectionBird")
+        return nm.value, out[:F.n]
+
+    def SearchForTriangulation(self, kps1, desc1, uR1, has_mp1, kps2, desc2, uR2, has_mp2, fv1, fv2, F12, ex, ey,
+                               scale_factors2, level_sigma2_2, bOnlyStereo=False):
+        """SearchForTriangulation(KF1, KF2, F12, pairs, bOnlyStereo) (src/ORBmatcher.cc:657-823)"""
+        kps1, kps2 = _c(kps1, KP_DTYPE), _c(kps2, KP_DTYPE)
+        desc1, desc2 = _c(desc1, np.uint8), _c(desc2, np.uint8)
+        uR1, uR2 = _c(uR1, np.float32), _c(uR2, np.float32)
+        has_mp1, has_mp2 = _c(has_mp1, np.uint8), _c(has_mp2, np.uint8)
+        f1 = [_c(x, np.int32) for x in fv1]
+        f2 = [_c(x, np.int32) for x in fv2]
+        F12 = _c(F12, np.float32).reshape(9)
+        sf2, ls2 = _c(scale_factors2, np.float32), _c(level_sigma2_2, np.float32)
+        pairs = np.empty((max(len(kps1), 1), 2), np.int32)
+        npairs = C.c_int()
+        self.ctx.check(self._L.orbb200_search_for_triangulation(
+            self.ctx._h, _p(kps1), _p(desc1), _p(uR1), _p(has_mp1), len(kps1), _p(kps2), _p(desc2), _p(uR2), _p(has_mp2), len(kps2),
+            _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]), _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
+            _p(F12), ex, ey, _p(sf2), _p(ls2), int(bOnlyStereo), int(self.mbCheckOrientation), _p(pairs), C.byref(npairs)),
+            "SearchForTriangulation")
+        return npairs.value, pairs[:npairs.value].copy()

@@ -1,0 +1,893 @@
+// C ABI of liborbb200.so (include/orbb200.h): context, geometry, host/device entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "match.cuh"
+
+using namespace orbb200;
+
+struct orbb200_ctx { Ctx c; };
+
+struct orbb200_frame {
+    Ctx* ctx = nullptr;
+    FrameDev h{};
+    FrameDev* d_self = nullptr;
+    void* owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cap = 0;
+};
+
+namespace orbb200 {
+
+static std::string g_create_err;
+static std::mutex g_create_mu;
+
+static inline int cvRoundF(float v) { return (int)lrintf(v); }
+static inline int cvFloorF(float v) { int i = (int)v; return i - (i > v); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Geometry of every level for an image shape: level sizes (ComputePyramid, reference
+// src/ORBextractor.cc:1111-1112), FAST grid (:776-787), octree roots (:543-546), pool offsets.
+bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err)
+{
+    memset(&g, 0, sizeof(g));
+    g.nlevels = c.nlevels; g.w = w; g.h = h; g.iniTh = c.iniTh; g.minTh = c.minTh;
+    size_t off = 0, candOff = 0;
+    int kpOff = 0, cellBase = 0, xt = 0, yt = 0;
+    for (int l = 0; l < c.nlevels; l++) {
+        LevelGeom& L = g.lv[l];
+        L.w = std::max(cvRoundF((float)w * c.invScale[l]), 0);
+        L.h = std::max(cvRoundF((float)h * c.invScale[l]), 0);
+        L.pitch = (int)align_up((size_t)std::max(L.w, 1), 128);
+        L.off = (unsigned)off;
+        off += align_up((size_t)L.pitch * std::max(L.h, 1), 256);
+        L.scale = c.scale[l];
+        L.quota = c.quota[l];
+        L.patchSize = (int)(PATCH_SIZE * c.scale[l]);
+        L.maxBX = L.w - EDGE_THRESHOLD + 3;
+        L.maxBY = L.h - EDGE_THRESHOLD + 3;
+        const float width = (float)(L.maxBX - FAST_BORDER), height = (float)(L.maxBY - FAST_BORDER);
+        L.nCols = width > 0 ? (int)(width / 30.f) : 0;
+        L.nRows = height > 0 ? (int)(height / 30.f) : 0;
+        L.cellBase = cellBase;
+        long candCap = 0;
+        if (L.nCols > 0 && L.nRows > 0) {
+            L.wCell = (int)ceilf(width / L.nCols);
+            L.hCell = (int)ceilf(height / L.nRows);
+            if (L.wCell + 6 > 65 || L.hCell + 6 > 65) { err = "FAST cell larger than 59 px: unsupported geometry"; return false; }
+            for (int i = 0; i < L.nRows; i++) {
+                const float iniY = (float)(FAST_BORDER + i * L.hCell);
+                float maxY = iniY + L.hCell + 6;
+                if (iniY >= L.maxBY - 3) continue;
+                if (maxY > L.maxBY) maxY = (float)L.maxBY;
+                for (int j = 0; j < L.nCols; j++) {
+                    const float iniX = (float)(FAST_BORDER + j * L.wCell);
+                    float maxX = iniX + L.wCell + 6;
+                    if (iniX >= L.maxBX - 6) continue;
+                    if (maxX > L.maxBX) maxX = (float)L.maxBX;
+                    const int wi = (int)maxX - (int)iniX - 6, hi = (int)maxY - (int)iniY - 6;
+                    if (wi > 0 && hi > 0) candCap += (long)((wi + 1) / 2) * ((hi + 1) / 2);
+                    L.nCells++;
+                }
+            }
+        } else {
+            L.nCols = L.nRows = 0; L.wCell = L.hCell = 1;
+        }
+        cellBase += L.nCells;
+        L.candCap = (int)candCap;
+        L.candOff = (unsigned)candOff;
+        candOff += align_up((size_t)candCap, 64);
+        const int regW = L.maxBX - FAST_BORDER, regH = L.maxBY - FAST_BORDER;
+        L.nIni = (regW > 0 && regH > 0) ? (int)roundf((float)regW / (float)regH) : 0;
+        L.hX = L.nIni > 0 ? (float)regW / (float)L.nIni : 1.f;
+        if (L.nCells > 0 && L.nIni <= 0) { err = "portrait level with nIni == 0: the reference divides by zero here"; return false; }
+        L.maxNodes = std::max(L.quota + 3, 4 * std::max(L.nIni, 1)) + 1;
+        if (L.maxNodes > 65535 || L.maxBX > 4096 + FAST_BORDER || L.maxBY > 4096 + FAST_BORDER) { err = "image or quota too large (limits: 4096 px, 65535 nodes/level)"; return false; }
+        L.kpCap = L.maxNodes;
+        L.kpOff = kpOff;
+        kpOff += L.kpCap;
+        L.xtabOff = xt; L.ytabOff = yt;
+        if (l > 0) { xt += L.w; yt += L.h; }
+    }
+    g.pyrBytes = (unsigned)off;
+    g.candPerImg = (unsigned)candOff;
+    g.kpPerImg = kpOff;
+    g.totalCells = cellBase;
+    return true;
+}
+
+bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes)
+{
+    if (dev_bytes > c.d_scratch_bytes) {
+        cudaStreamSynchronize(c.stream);
+        if (c.d_scratch) cudaFree(c.d_scratch);
+        c.d_scratch = nullptr; c.d_scratch_bytes = 0;
+        const size_t nb = align_up(dev_bytes + dev_bytes / 4, 1 << 20);
+        if (cudaMalloc(&c.d_scratch, nb) != cudaSuccess) { c.err = "cudaMalloc(scratch) failed"; return false; }
+        c.d_scratch_bytes = nb;
+    }
+    if (host_bytes > c.h_scratch_bytes) {
+        cudaStreamSynchronize(c.stream);
+        if (c.h_scratch) cudaFreeHost(c.h_scratch);
+        c.h_scratch = nullptr; c.h_scratch_bytes = 0;
+        const size_t nb = align_up(host_bytes + host_bytes / 4, 1 << 20);
+        if (cudaMallocHost(&c.h_scratch, nb) != cudaSuccess) { c.err = "cudaMallocHost(scratch) failed"; return false; }
+        c.h_scratch_bytes = nb;
+    }
+    return true;
+}
+
+// Per-shape tables: resize coefficients (OpenCV resize.cpp, INTER_RESIZE_COEF_BITS = 11) and FAST cells.
+const ShapeTables* get_shape(Ctx& c, int w, int h)
+{
+    auto it = c.shapes.find({w, h});
+    if (it != c.shapes.end()) return &it->second;
+    ShapeTables st;
+    if (!build_geom(c, w, h, st.g, c.err)) return nullptr;
+    const Geom& g = st.g;
+    if (g.pyrBytes > c.gmax.pyrBytes || g.candPerImg > c.gmax.candPerImg + c.gmax.candPerImg / 8 || g.kpPerImg > c.gmax.kpPerImg) {
+        c.err = "image shape exceeds the context's max_w/max_h";
+        return nullptr;
+    }
+    std::vector<int2> xtab;
+    std::vector<int4> ytab;
+    for (int l = 1; l < g.nlevels; l++) {
+        const LevelGeom &S = g.lv[l - 1], &D = g.lv[l];
+        if (D.w <= 0 || D.h <= 0) continue;
+        const double sx_ = (double)S.w / D.w, sy_ = (double)S.h / D.h;
+        for (int dx = 0; dx < D.w; dx++) {
+            float fx = (float)((dx + 0.5) * sx_ - 0.5);
+            int sx = cvFloorF(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+            const int a0 = std::min(std::max(cvRoundF((1.f - fx) * 2048), -32768), 32767);
+            const int a1 = std::min(std::max(cvRoundF(fx * 2048), -32768), 32767);
+            xtab.push_back(make_int2(sx, (a0 & 0xffff) | (a1 << 16)));
+        }
+        for (int dy = 0; dy < D.h; dy++) {
+            float fy = (float)((dy + 0.5) * sy_ - 0.5);
+            int sy = cvFloorF(fy);
+            fy -= sy;
+            const int b0 = std::min(std::max(cvRoundF((1.f - fy) * 2048), -32768), 32767);
+            const int b1 = std::min(std::max(cvRoundF(fy * 2048), -32768), 32767);
+            ytab.push_back(make_int4(std::min(std::max(sy, 0), S.h - 1), std::min(std::max(sy + 1, 0), S.h - 1), b0, b1));
+        }
+    }
+    std::vector<int4> cells;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        if (L.nCells == 0) continue;
+        for (int i = 0; i < L.nRows; i++) {
+            const float iniY = (float)(FAST_BORDER + i * L.hCell);
+            float maxY = iniY + L.hCell + 6;
+            if (iniY >= L.maxBY - 3) continue;
+            if (maxY > L.maxBY) maxY = (float)L.maxBY;
+            for (int j = 0; j < L.nCols; j++) {
+                const float iniX = (float)(FAST_BORDER + j * L.wCell);
+                float maxX = iniX + L.wCell + 6;
+                if (iniX >= L.maxBX - 6) continue;
+                if (maxX > L.maxBX) maxX = (float)L.maxBX;
+                cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
+            }
+        }
+    }
+    auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {
+        if (bytes == 0) bytes = 16;
+        if (cudaMalloc(dptr, bytes) != cudaSuccess) return false;
+        if (src && cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
+        return true;
+    };
+    bool ok = up((void**)&st.d_xtab, xtab.data(), xtab.size() * sizeof(int2)) &&
+              up((void**)&st.d_ytab, ytab.data(), ytab.size() * sizeof(int4)) &&
+              up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4));
+    cudaStreamSynchronize(c.stream);   // host vectors go out of scope
+    if (!ok) { c.err = "cudaMalloc(shape tables) failed"; return nullptr; }
+    auto res = c.shapes.emplace(std::make_pair(w, h), st);
+    return &res.first->second;
+}
+
+static int run_extract(Ctx& c, int n)
+{
+    launch_pyramid(c, n);
+    launch_fast(c, n);
+    launch_blur(c, n);
+    launch_octree(c, n);
+    launch_describe(c, n);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+static int check_status(Ctx& c)
+{
+    int32_t st = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&st, c.d_status, sizeof(st), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (st != 0) {
+        cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
+        c.err = "device-side overflow in octree distribution (status " + std::to_string(st) + ")";
+        return ORBB200_ERR_UNSUPPORTED;
+    }
+    return ORBB200_OK;
+}
+
+}  // namespace orbb200
+
+#define CTX_ENTER(ctx)                                             \
+    if (!(ctx)) return ORBB200_ERR_ARG;                            \
+    Ctx& c = (ctx)->c;                                             \
+    ORBB200_CUDA_OK(c, cudaSetDevice(c.device))
+
+extern "C" {
+
+int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFactor, int nlevels,
+                   int iniThFAST, int minThFAST, int max_w, int max_h, int max_batch)
+{
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    if (!out || nfeatures <= 0 || nlevels <= 0 || nlevels > MAX_LEVELS || max_w <= 0 || max_h <= 0 || max_batch <= 0 ||
+        !(scaleFactor > 1.0f) || iniThFAST <= 0 || minThFAST <= 0 || iniThFAST > 254 || minThFAST > iniThFAST) {
+        g_create_err = "orbb200_create: bad argument";
+        return ORBB200_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_err = std::string("orbb200_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad index") + ")";
+        return ORBB200_ERR_CUDA;
+    }
+    orbb200_ctx* h = new orbb200_ctx;
+    Ctx& c = h->c;
+    c.device = device;
+    auto fail = [&](const std::string& m, int code) { g_create_err = m; orbb200_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed", ORBB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
+    // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
+    c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
+    c.scale.resize(nlevels); c.sigma2.resize(nlevels); c.invScale.resize(nlevels); c.invSigma2.resize(nlevels); c.quota.resize(nlevels);
+    c.scale[0] = 1.0f; c.sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        c.scale[i] = (float)(c.scale[i - 1] * c.scaleFactor);
+        c.sigma2[i] = c.scale[i] * c.scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { c.invScale[i] = 1.0f / c.scale[i]; c.invSigma2[i] = 1.0f / c.sigma2[i]; }
+    {
+        float factor = (float)(1.0f / c.scaleFactor);
+        float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; l++) {
+            c.quota[l] = cvRoundF(nDesired);
+            sum += c.quota[l];
+            nDesired *= factor;
+        }
+        c.quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    }
+    c.maxW = max_w; c.maxH = max_h; c.maxBatch = max_batch;
+    std::string err;
+    if (!build_geom(c, max_w, max_h, c.gmax, err)) return fail("orbb200_create: " + err, ORBB200_ERR_UNSUPPORTED);
+    const Geom& g = c.gmax;
+    const size_t candSlots = (size_t)g.candPerImg + g.candPerImg / 8 + 64;   // slack: smaller shapes may tile slightly worse
+    const size_t nb = (size_t)max_batch;
+    bool ok = true;
+    auto alloc = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, std::max<size_t>(bytes, 256)) != cudaSuccess) ok = false; };
+    alloc((void**)&c.d_pyr, nb * g.pyrBytes);
+    alloc((void**)&c.d_blur, nb * g.pyrBytes);
+    alloc((void**)&c.d_cand, nb * candSlots * sizeof(uint32_t));
+    alloc((void**)&c.d_nodeOf, nb * candSlots * sizeof(uint16_t));
+    alloc((void**)&c.d_candCount, nb * MAX_LEVELS * sizeof(int32_t));
+    alloc((void**)&c.d_lvlKp, nb * g.kpPerImg * sizeof(uint32_t));
+    alloc((void**)&c.d_lvlCount, nb * MAX_LEVELS * sizeof(int32_t));
+    alloc((void**)&c.d_kps, nb * g.kpPerImg * sizeof(orbb200_kp_t));
+    alloc((void**)&c.d_desc, nb * g.kpPerImg * 32);
+    alloc((void**)&c.d_counts, nb * sizeof(int32_t));
+    alloc((void**)&c.d_status, 256);
+    if (!ok) return fail("orbb200_create: cudaMalloc of the device pools failed", ORBB200_ERR_CUDA);
+    cudaMemsetAsync(c.d_status, 0, 256, c.stream);
+    cudaMemsetAsync(c.d_counts, 0, nb * sizeof(int32_t), c.stream);
+    cudaMemsetAsync(c.d_lvlCount, 0, nb * MAX_LEVELS * sizeof(int32_t), c.stream);
+    // pyramid pools are read up to the row pitch (never past it): start from defined bytes
+    cudaMemsetAsync(c.d_pyr, 0, nb * g.pyrBytes, c.stream);
+    cudaMemsetAsync(c.d_blur, 0, nb * g.pyrBytes, c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return fail("orbb200_create: device initialisation failed", ORBB200_ERR_CUDA);
+    *out = h;
+    return ORBB200_OK;
+}
+
+void orbb200_destroy(orbb200_ctx* ctx)
+{
+    if (!ctx) return;
+    Ctx& c = ctx->c;
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); }
+    if (c.h_scratch) cudaFreeHost(c.h_scratch);
+    if (c.h_stage) cudaFreeHost(c.h_stage);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    delete ctx;
+}
+
+const char* orbb200_last_error(const orbb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+
+int orbb200_sync(orbb200_ctx* ctx)
+{
+    CTX_ENTER(ctx);
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
+void* orbb200_stream(orbb200_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+int orbb200_get_levels(const orbb200_ctx* ctx) { return ctx ? ctx->c.nlevels : ORBB200_ERR_ARG; }
+
+int orbb200_get_scale_table(const orbb200_ctx* ctx, int which, float* out)
+{
+    if (!ctx || !out || which < 0 || which > 3) return ORBB200_ERR_ARG;
+    const Ctx& c = ctx->c;
+    const std::vector<float>& v = which == 0 ? c.scale : which == 1 ? c.invScale : which == 2 ? c.sigma2 : c.invSigma2;
+    std::copy(v.begin(), v.end(), out);
+    return ORBB200_OK;
+}
+
+int orbb200_get_features_per_level(const orbb200_ctx* ctx, int32_t* out)
+{
+    if (!ctx || !out) return ORBB200_ERR_ARG;
+    std::copy(ctx->c.quota.begin(), ctx->c.quota.end(), out);
+    return ORBB200_OK;
+}
+
+int orbb200_max_keypoints(const orbb200_ctx* ctx) { return ctx ? ctx->c.gmax.kpPerImg : ORBB200_ERR_ARG; }
+long long orbb200_launch_count(const orbb200_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+// ---- extraction -------------------------------------------------------------------------------------
+int orbb200_extract_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_bytes, int n, int w, int h, size_t stride)
+{
+    CTX_ENTER(ctx);
+    if (!d_imgs || n <= 0 || n > c.maxBatch || w <= 0 || h <= 0 || stride < (size_t)w) { c.err = "extract: bad argument"; return ORBB200_ERR_ARG; }
+    const ShapeTables* st = get_shape(c, w, h);
+    if (!st) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
+    c.cur = st; c.curN = n;
+    launch_import(c, d_imgs, img_bytes, stride, n);
+    return run_extract(c, n);
+}
+
+int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out)
+{
+    CTX_ENTER(ctx);
+    if (!c.cur || n <= 0 || n > c.curN || !kps || !desc || !n_out || cap_per_img <= 0) { c.err = "download: bad argument"; return ORBB200_ERR_ARG; }
+    const int kpi = c.cur->g.kpPerImg;
+    const int take = std::min(cap_per_img, kpi);
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(kps, (size_t)cap_per_img * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t),
+                                         (size_t)take * sizeof(orbb200_kp_t), n, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(desc, (size_t)cap_per_img * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, n,
+                                         cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(n_out, c.d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+    int rc = check_status(c);   // synchronises
+    if (rc != ORBB200_OK) return rc;
+    for (int i = 0; i < n; i++)
+        if (n_out[i] > cap_per_img) { c.err = "extract: caller capacity too small"; return ORBB200_ERR_CAPACITY; }
+    return ORBB200_OK;
+}
+
+int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, int w, int h, size_t stride,
+                          orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out)
+{
+    CTX_ENTER(ctx);
+    if (!imgs || n <= 0 || n > c.maxBatch || w <= 0 || h <= 0 || stride < (size_t)w) { c.err = "extract: bad argument"; return ORBB200_ERR_ARG; }
+    const ShapeTables* st = get_shape(c, w, h);
+    if (!st) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
+    c.cur = st; c.curN = n;
+    const Geom& g = st->g;
+    // rows go straight into level 0 of the pyramid pool (row pitch conversion by the copy engine)
+    bool contiguous = true;
+    for (int i = 1; i < n; i++) contiguous &= (imgs[i] == imgs[0] + (size_t)i * h * stride);
+    (void)contiguous;
+    for (int i = 0; i < n; i++) {
+        if (!imgs[i]) { c.err = "extract: null image"; return ORBB200_ERR_ARG; }
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes, g.lv[0].pitch, imgs[i], stride, (size_t)w, (size_t)h,
+                                             cudaMemcpyHostToDevice, c.stream));
+    }
+    int rc = run_extract(c, n);
+    if (rc != ORBB200_OK) return rc;
+    return orbb200_download_results(ctx, n, kps, desc, cap_per_img, n_out);
+}
+
+int orbb200_extract(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride,
+                    orbb200_kp_t* kps, uint8_t* desc, int cap, int* n_out)
+{
+    if (ctx && (!img || w <= 0 || h <= 0)) {   // ORBextractor::operator(): empty image -> return (:1046-1047)
+        if (n_out) *n_out = 0;
+        return ORBB200_OK;
+    }
+    const uint8_t* imgs[1] = {img};
+    return orbb200_extract_batch(ctx, imgs, 1, w, h, stride, kps, desc, cap, n_out);
+}
+
+int orbb200_results_device(orbb200_ctx* ctx, const orbb200_kp_t** d_kps, const uint8_t** d_desc, const int32_t** d_counts, int* cap_per_img)
+{
+    if (!ctx || !ctx->c.cur) return ORBB200_ERR_ARG;
+    Ctx& c = ctx->c;
+    if (d_kps) *d_kps = c.d_kps;
+    if (d_desc) *d_desc = c.d_desc;
+    if (d_counts) *d_counts = c.d_counts;
+    if (cap_per_img) *cap_per_img = c.cur->g.kpPerImg;
+    return ORBB200_OK;
+}
+
+int orbb200_pyramid_level(orbb200_ctx* ctx, int img_index, int level, int blurred, uint8_t* dst, size_t dst_stride, int* w, int* h)
+{
+    CTX_ENTER(ctx);
+    if (!c.cur || img_index < 0 || img_index >= c.curN || level < 0 || level >= c.nlevels) { c.err = "pyramid_level: bad argument"; return ORBB200_ERR_ARG; }
+    const Geom& g = c.cur->g;
+    const LevelGeom& L = g.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return ORBB200_OK;
+    if (dst_stride < (size_t)L.w) { c.err = "pyramid_level: stride too small"; return ORBB200_ERR_ARG; }
+    if (L.w <= 0 || L.h <= 0) return ORBB200_OK;
+    const uint8_t* src = (blurred ? c.d_blur : c.d_pyr) + (size_t)img_index * g.pyrBytes + L.off;
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(dst, dst_stride, src, L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
+int orbb200_level_candidates(orbb200_ctx* ctx, int img_index, int level, int32_t* xyr, int cap)
+{
+    CTX_ENTER(ctx);
+    if (!c.cur || img_index < 0 || img_index >= c.curN || level < 0 || level >= c.nlevels) { c.err = "level_candidates: bad argument"; return ORBB200_ERR_ARG; }
+    const Geom& g = c.cur->g;
+    const LevelGeom& L = g.lv[level];
+    int32_t cnt = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&cnt, c.d_candCount + img_index * MAX_LEVELS + level, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    const int take = std::min(std::min(cnt, L.candCap), cap);
+    if (take > 0 && xyr) {
+        std::vector<uint32_t> tmp(take);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(tmp.data(), c.d_cand + (size_t)img_index * g.candPerImg + L.candOff, sizeof(uint32_t) * take,
+                                           cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        for (int i = 0; i < take; i++) { xyr[3 * i] = tmp[i] & 0xfff; xyr[3 * i + 1] = (tmp[i] >> 12) & 0xfff; xyr[3 * i + 2] = tmp[i] >> 24; }
+    }
+    return cnt;
+}
+
+// ---- brute-force Hamming ----------------------------------------------------------------------------
+static int knn2_splits(int nq, int nm)
+{
+    // enough CTAs for ~2 waves of 148 SMs x 4 resident CTAs, at least 64 map descriptors per split
+    const int qtiles = (nq + 511) / 512;
+    int s = std::max(1, (148 * 8) / std::max(qtiles, 1));
+    s = std::min(s, std::max(1, nm / 64));
+    return s;
+}
+
+int orbb200_hamming_knn2_device(orbb200_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm,
+                                int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d)
+{
+    CTX_ENTER(ctx);
+    if (nq <= 0) return ORBB200_OK;
+    if (!d_q || (!d_m && nm > 0) || nm < 0 || !d_best_idx || !d_best_d || !d_second_d) { c.err = "knn2: bad argument"; return ORBB200_ERR_ARG; }
+    const int ns = knn2_splits(nq, nm);
+    static_assert(sizeof(int4) == 16, "");
+    // partials live at the end of the scratch arena (host wrapper uses the front)
+    const size_t need = (size_t)ns * nq * sizeof(int4);
+    if (!ensure_scratch(c, align_up(need, 256) + 256, 0)) return ORBB200_ERR_CUDA;
+    int4* part = reinterpret_cast<int4*>(c.d_scratch + c.d_scratch_bytes - align_up(need, 256));
+    launch_knn2(c, d_q, nq, d_m, nm, ns, part, d_best_idx, d_best_d, d_second_d);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+int orbb200_hamming_knn2(orbb200_ctx* ctx, const uint8_t* q, int nq, const uint8_t* m, int nm,
+                         int32_t* best_idx, int32_t* best_d, int32_t* second_d)
+{
+    CTX_ENTER(ctx);
+    if (nq <= 0) return ORBB200_OK;
+    if (!q || (!m && nm > 0) || nm < 0 || !best_idx || !best_d || !second_d) { c.err = "knn2: bad argument"; return ORBB200_ERR_ARG; }
+    const int ns = knn2_splits(nq, nm);
+    const size_t qB = align_up((size_t)nq * 32, 256), mB = align_up((size_t)std::max(nm, 1) * 32, 256), oB = align_up((size_t)nq * 4, 256);
+    const size_t need = qB + mB + 3 * oB + align_up((size_t)ns * nq * sizeof(int4), 256) + 4096;
+    if (!ensure_scratch(c, need, 0)) return ORBB200_ERR_CUDA;
+    uint8_t* dq = c.d_scratch;
+    uint8_t* dm = dq + qB;
+    int32_t* bi = reinterpret_cast<int32_t*>(dm + mB);
+    int32_t* bd = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bi) + oB);
+    int32_t* sd = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bd) + oB);
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c.stream));
+    if (nm > 0) ORBB200_CUDA_OK(c, cudaMemcpyAsync(dm, m, (size_t)nm * 32, cudaMemcpyHostToDevice, c.stream));
+    int rc = orbb200_hamming_knn2_device(ctx, dq, nq, dm, nm, bi, bd, sd);
+    if (rc != ORBB200_OK) return rc;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(best_idx, bi, (size_t)nq * 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(best_d, bd, (size_t)nq * 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(second_d, sd, (size_t)nq * 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
+// POPC issue peak in G popc/s measured on this device (roofline denominator for matching)
+double orbb200_measure_popc_peak(orbb200_ctx* ctx)
+{
+    if (!ctx) return -1.0;
+    Ctx& c = ctx->c;
+    if (cudaSetDevice(c.device) != cudaSuccess) return -1.0;
+    if (!ensure_scratch(c, 4096, 0)) return -1.0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, c.device);
+    const int blocks = prop.multiProcessorCount * 8, iters = 2000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch_popc_peak(c, reinterpret_cast<uint32_t*>(c.d_scratch), blocks, 100);
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(e0, c.stream);
+        launch_popc_peak(c, reinterpret_cast<uint32_t*>(c.d_scratch), blocks, iters);
+        cudaEventRecord(e1, c.stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double popc = (double)blocks * 256 * iters * 32;
+    return popc / (best * 1e-3) * 1e-9;
+}
+
+// ---- frames -----------------------------------------------------------------------------------------
+static int frame_finish(Ctx& c, orbb200_frame* f)
+{
+    ORBB200_CUDA_OK(c, cudaMalloc(&f->owned[3], sizeof(int32_t) * (GRID_CELLS + 1)));
+    ORBB200_CUDA_OK(c, cudaMalloc(&f->owned[4], sizeof(int32_t) * std::max(f->cap, 1)));
+    f->h.cellStart = (int32_t*)f->owned[3];
+    f->h.cellItems = (int32_t*)f->owned[4];
+    ORBB200_CUDA_OK(c, cudaMalloc((void**)&f->d_self, sizeof(FrameDev)));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(f->d_self, &f->h, sizeof(FrameDev), cudaMemcpyHostToDevice, c.stream));
+    launch_grid_build(c, f->d_self, 1);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));   // f->h is host memory owned by f: safe, but keep semantics simple
+    return ORBB200_OK;
+}
+
+int orbb200_frame_upload(orbb200_ctx* ctx, orbb200_frame** out, const orbb200_kp_t* kps, const uint8_t* desc,
+                         const float* u_right, int n, float min_x, float min_y, float inv_w, float inv_h)
+{
+    CTX_ENTER(ctx);
+    if (!out || n < 0 || (n > 0 && (!kps || !desc))) { c.err = "frame_upload: bad argument"; return ORBB200_ERR_ARG; }
+    orbb200_frame* f = new orbb200_frame;
+    f->ctx = &c; f->cap = n;
+    auto bail = [&](int rc) { orbb200_frame_free(f); return rc; };
+    if (cudaMalloc(&f->owned[0], sizeof(orbb200_kp_t) * std::max(n, 1)) != cudaSuccess || cudaMalloc(&f->owned[1], 32 * (size_t)std::max(n, 1)) != cudaSuccess) {
+        c.err = "frame_upload: cudaMalloc failed"; return bail(ORBB200_ERR_CUDA);
+    }
+    if (n > 0) {
+        cudaMemcpyAsync(f->owned[0], kps, sizeof(orbb200_kp_t) * n, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(f->owned[1], desc, 32 * (size_t)n, cudaMemcpyHostToDevice, c.stream);
+    }
+    if (u_right && n > 0) {
+        if (cudaMalloc(&f->owned[2], sizeof(float) * n) != cudaSuccess) { c.err = "frame_upload: cudaMalloc failed"; return bail(ORBB200_ERR_CUDA); }
+        cudaMemcpyAsync(f->owned[2], u_right, sizeof(float) * n, cudaMemcpyHostToDevice, c.stream);
+    }
+    f->h.kps = (const orbb200_kp_t*)f->owned[0]; f->h.desc = (const uint8_t*)f->owned[1]; f->h.uRight = (const float*)f->owned[2];
+    f->h.n_ptr = nullptr; f->h.n = n;
+    f->h.minX = min_x; f->h.minY = min_y; f->h.invW = inv_w; f->h.invH = inv_h;
+    int rc = frame_finish(c, f);
+    if (rc != ORBB200_OK) return bail(rc);
+    *out = f;
+    return ORBB200_OK;
+}
+
+int orbb200_frame_from_extract(orbb200_ctx* ctx, orbb200_frame** out, int img_index, float min_x, float min_y, float inv_w, float inv_h)
+{
+    CTX_ENTER(ctx);
+    if (!out || !c.cur || img_index < 0 || img_index >= c.curN) { c.err = "frame_from_extract: bad argument"; return ORBB200_ERR_ARG; }
+    const int kpi = c.cur->g.kpPerImg;
+    orbb200_frame* f = new orbb200_frame;
+    f->ctx = &c; f->cap = kpi;
+    f->h.kps = c.d_kps + (size_t)img_index * kpi;
+    f->h.desc = c.d_desc + (size_t)img_index * kpi * 32;
+    f->h.uRight = nullptr;
+    f->h.n_ptr = c.d_counts + img_index; f->h.n = kpi;
+    f->h.minX = min_x; f->h.minY = min_y; f->h.invW = inv_w; f->h.invH = inv_h;
+    int rc = frame_finish(c, f);
+    if (rc != ORBB200_OK) { orbb200_frame_free(f); return rc; }
+    *out = f;
+    return ORBB200_OK;
+}
+
+void orbb200_frame_free(orbb200_frame* f)
+{
+    if (!f) return;
+    if (f->ctx) { cudaSetDevice(f->ctx->device); cudaStreamSynchronize(f->ctx->stream); }
+    for (void* p : f->owned) if (p) cudaFree(p);
+    if (f->d_self) cudaFree(f->d_self);
+    delete f;
+}
+
+int orbb200_frame_features_in_area(orbb200_ctx* ctx, const orbb200_frame* f, float x, float y, float r,
+                                   int min_level, int max_level, int32_t* out, int cap)
+{
+    CTX_ENTER(ctx);
+    if (!f || cap < 0) { c.err = "features_in_area: bad argument"; return ORBB200_ERR_ARG; }
+    if (!ensure_scratch(c, sizeof(int32_t) * (size_t)(cap + 64), 0)) return ORBB200_ERR_CUDA;
+    int32_t* d_cnt = reinterpret_cast<int32_t*>(c.d_scratch);
+    int32_t* d_out = d_cnt + 64;
+    launch_features_in_area(c, f->d_self, x, y, r, min_level, max_level, d_out, cap, d_cnt);
+    int32_t cnt = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (out && std::min(cnt, cap) > 0) {
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(out, d_out, sizeof(int32_t) * std::min(cnt, cap), cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    }
+    return cnt;
+}
+
+}  // extern "C"
+
+// ---- windowed searches: host wrappers ------------------------------------------------------------------
+namespace {
+
+struct Arena {
+    uint8_t* base;
+    size_t cap, off = 0;
+    Arena(uint8_t* b, size_t c) : base(b), cap(c) {}
+    template <class T> T* take(size_t n) { off = align_up(off, 256); T* p = reinterpret_cast<T*>(base + off); off += n * sizeof(T); return p; }
+};
+
+struct QueryHost {
+    int nq = 0;
+    const uint8_t* valid = nullptr; const float* x = nullptr; const float* y = nullptr; const float* aux = nullptr;
+    const int32_t* level = nullptr; const float* viewcos = nullptr; const float* angle = nullptr;
+    const uint8_t* desc = nullptr; const uint8_t* obs_pos = nullptr; const uint8_t* kp_blocked = nullptr;
+};
+
+// Upload one job's queries, run it, return device pointers of the outputs inside the scratch arena.
+int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode, int levelMode, int checkOri,
+                   float th, float nnratio, float mbf,
+                   int32_t* h_best_idx, int32_t* h_best_dist, int32_t* h_per_kp, int32_t* h_per_query, int* h_nmatches)
+{
+    const int nq = Q.nq, kpCap = std::max(F->cap, 1);
+    const size_t need = (size_t)nq * (32 + 4 * 6 + 2 + 4 * 3) + (size_t)kpCap * (1 + 4) + win_scratch_ints(kpCap, nq) * 4 + 64 * 256 + sizeof(WinJob);
+    if (!ensure_scratch(c, need, 0)) return ORBB200_ERR_CUDA;
+    Arena A(c.d_scratch, c.d_scratch_bytes);
+    WinJob J{};
+    auto upF = [&](const float* src) -> const float* {
+        if (!src) return nullptr;
+        float* d = A.take<float>(nq);
+        cudaMemcpyAsync(d, src, sizeof(float) * nq, cudaMemcpyHostToDevice, c.stream);
+        return d;
+    };
+    auto upB = [&](const uint8_t* src, size_t n) -> const uint8_t* {
+        if (!src) return nullptr;
+        uint8_t* d = A.take<uint8_t>(n);
+        cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, c.stream);
+        return d;
+    };
+    J.frame = F->d_self; J.nq = nq; J.mode = mode; J.levelMode = levelMode; J.checkOri = checkOri; J.kpCap = kpCap;
+    J.th = th; J.nnratio = nnratio; J.mbf = mbf;
+    float* dsf = A.take<float>(MAX_LEVELS);
+    cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream);
+    J.scaleFactors = dsf;
+    J.q_valid = upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
+    if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
+    J.q_viewcos = upF(Q.viewcos); J.q_angle = upF(Q.angle);
+    J.q_desc = upB(Q.desc, (size_t)nq * 32); J.q_obs_pos = upB(Q.obs_pos, nq); J.kp_blocked = upB(Q.kp_blocked, F->cap);
+    J.scratch = A.take<int>(win_scratch_ints(kpCap, nq));
+    J.out_best_idx = A.take<int32_t>(nq); J.out_best_dist = A.take<int32_t>(nq);
+    J.out_per_kp = A.take<int32_t>(kpCap); J.out_per_query = A.take<int32_t>(nq);
+    J.out_nmatches = A.take<int32_t>(1);
+    WinJob* dJ = A.take<WinJob>(1);
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, &J, sizeof(J), cudaMemcpyHostToDevice, c.stream));
+    launch_window_match(c, dJ, 1);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    if (h_best_idx) cudaMemcpyAsync(h_best_idx, J.out_best_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+    if (h_best_dist) cudaMemcpyAsync(h_best_dist, J.out_best_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+    if (h_per_kp && F->cap > 0) cudaMemcpyAsync(h_per_kp, J.out_per_kp, 4 * (size_t)F->cap, cudaMemcpyDeviceToHost, c.stream);
+    if (h_per_query) cudaMemcpyAsync(h_per_query, J.out_per_query, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+    int32_t nm = 0;
+    cudaMemcpyAsync(&nm, J.out_nmatches, 4, cudaMemcpyDeviceToHost, c.stream);
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (h_nmatches) *h_nmatches = nm;
+    return ORBB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbb200_search_by_projection(orbb200_ctx* ctx, const orbb200_frame* F, int nq,
+                                 const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_uR,
+                                 const int32_t* q_level, const float* q_viewcos, const uint8_t* q_desc,
+                                 const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float th, float nnratio,
+                                 int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F || nq < 0 || (nq > 0 && (!q_u || !q_v || !q_uR || !q_level || !q_viewcos || !q_desc))) { c.err = "search_by_projection: bad argument"; return ORBB200_ERR_ARG; }
+    QueryHost Q; Q.nq = nq; Q.valid = q_valid; Q.x = q_u; Q.y = q_v; Q.aux = q_uR; Q.level = q_level; Q.viewcos = q_viewcos;
+    Q.desc = q_desc; Q.obs_pos = q_obs_pos; Q.kp_blocked = kp_blocked;
+    return run_window_job(c, F, Q, WM_PROJ, 0, 0, th, nnratio, 0.f, out_best_idx, out_best_dist, out_query_of_kp, nullptr, nmatches);
+}
+
+int orbb200_search_by_projection_frame(orbb200_ctx* ctx, const orbb200_frame* Cur, int nq,
+                                       const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_invz,
+                                       const int32_t* q_octave, const float* q_angle, const uint8_t* q_desc,
+                                       const uint8_t* q_obs_pos, const uint8_t* kp_blocked,
+                                       float th, float mbf, int mode, int check_ori, int32_t* out_query_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!Cur || nq < 0 || mode < 0 || mode > 2 || (nq > 0 && (!q_u || !q_v || !q_invz || !q_octave || !q_desc || (check_ori && !q_angle)))) {
+        c.err = "search_by_projection_frame: bad argument"; return ORBB200_ERR_ARG;
+    }
+    QueryHost Q; Q.nq = nq; Q.valid = q_valid; Q.x = q_u; Q.y = q_v; Q.aux = q_invz; Q.level = q_octave; Q.angle = q_angle;
+    Q.desc = q_desc; Q.obs_pos = q_obs_pos; Q.kp_blocked = kp_blocked;
+    return run_window_job(c, Cur, Q, WM_PROJ_FRAME, mode, check_ori, th, 0.f, mbf, nullptr, nullptr, out_query_of_kp, nullptr, nmatches);
+}
+
+int orbb200_birdview_match(orbb200_ctx* ctx, const orbb200_kp_t* kps1, const uint8_t* desc1, int n1,
+                           const orbb200_frame* F2, float* prev_xy, int window_size, float nnratio, int check_ori,
+                           int32_t* matches12, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F2 || n1 < 0 || (n1 > 0 && (!kps1 || !desc1 || !matches12))) { c.err = "birdview_match: bad argument"; return ORBB200_ERR_ARG; }
+    std::vector<float> x(n1), y(n1), ang(n1);
+    std::vector<int32_t> lvl(n1);
+    for (int i = 0; i < n1; i++) {
+        x[i] = prev_xy ? prev_xy[2 * i] : kps1[i].x;
+        y[i] = prev_xy ? prev_xy[2 * i + 1] : kps1[i].y;
+        ang[i] = kps1[i].angle; lvl[i] = kps1[i].octave;
+    }
+    QueryHost Q; Q.nq = n1; Q.x = x.data(); Q.y = y.data(); Q.level = lvl.data(); Q.angle = ang.data(); Q.desc = desc1;
+    int rc = run_window_job(c, F2, Q, WM_BIRD, prev_xy ? 1 : 0, check_ori, (float)window_size, nnratio, 0.f, nullptr, nullptr, nullptr, matches12, nmatches);
+    if (rc != ORBB200_OK) return rc;
+    if (prev_xy && n1 > 0) {
+        // vPrevMatched[i1] = F2.mvKeysBird[vnMatches12[i1]].pt (:1777-1779)
+        std::vector<orbb200_kp_t> k2(std::max(F2->cap, 1));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(k2.data(), F2->h.kps, sizeof(orbb200_kp_t) * F2->cap, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        for (int i = 0; i < n1; i++)
+            if (matches12[i] >= 0) { prev_xy[2 * i] = k2[matches12[i]].x; prev_xy[2 * i + 1] = k2[matches12[i]].y; }
+    }
+    return ORBB200_OK;
+}
+
+int orbb200_search_by_match_bird_kf(orbb200_ctx* ctx, const orbb200_kp_t* kf_kps, const uint8_t* has_mp,
+                                    const uint8_t* mp_desc, int nk, const orbb200_frame* F, float r, float nnratio,
+                                    int check_ori, int32_t* out_mp_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F || nk < 0 || (nk > 0 && (!kf_kps || !has_mp || !mp_desc))) { c.err = "search_by_match_bird_kf: bad argument"; return ORBB200_ERR_ARG; }
+    std::vector<float> x(nk), y(nk), ang(nk);
+    for (int i = 0; i < nk; i++) { x[i] = kf_kps[i].x; y[i] = kf_kps[i].y; ang[i] = kf_kps[i].angle; }
+    QueryHost Q; Q.nq = nk; Q.valid = has_mp; Q.x = x.data(); Q.y = y.data(); Q.angle = ang.data(); Q.desc = mp_desc;
+    return run_window_job(c, F, Q, WM_BIRD_KF, 0, check_ori, r, nnratio, 0.f, nullptr, nullptr, out_mp_of_kp, nullptr, nmatches);
+}
+
+int orbb200_search_by_projection_bird(orbb200_ctx* ctx, const orbb200_frame* F, int nq, const uint8_t* q_valid,
+                                      const float* q_x, const float* q_y, const uint8_t* q_desc,
+                                      const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float r, float nnratio,
+                                      int32_t* out_query_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F || nq < 0 || (nq > 0 && (!q_x || !q_y || !q_desc))) { c.err = "search_by_projection_bird: bad argument"; return ORBB200_ERR_ARG; }
+    QueryHost Q; Q.nq = nq; Q.valid = q_valid; Q.x = q_x; Q.y = q_y; Q.desc = q_desc; Q.obs_pos = q_obs_pos; Q.kp_blocked = kp_blocked;
+    return run_window_job(c, F, Q, WM_PROJ_BIRD, 0, 0, r, nnratio, 0.f, nullptr, nullptr, out_query_of_kp, nullptr, nmatches);
+}
+
+int orbb200_search_for_triangulation(orbb200_ctx* ctx,
+                                     const orbb200_kp_t* kps1, const uint8_t* desc1, const float* uR1, const uint8_t* has_mp1, int n1,
+                                     const orbb200_kp_t* kps2, const uint8_t* desc2, const float* uR2, const uint8_t* has_mp2, int n2,
+                                     const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                                     const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                                     const float* F12, float ex, float ey,
+                                     const float* scale_factors2, const float* level_sigma2_2,
+                                     int only_stereo, int check_ori, int32_t* pairs, int* npairs)
+{
+    CTX_ENTER(ctx);
+    if (n1 < 0 || n2 < 0 || !F12 || !scale_factors2 || !level_sigma2_2 || !pairs || !npairs ||
+        (n1 > 0 && (!kps1 || !desc1 || !has_mp1)) || (n2 > 0 && (!kps2 || !desc2 || !has_mp2)) ||
+        (nn1 > 0 && (!fv1_node || !fv1_ptr || !fv1_idx)) || (nn2 > 0 && (!fv2_node || !fv2_ptr || !fv2_idx))) {
+        c.err = "search_for_triangulation: bad argument"; return ORBB200_ERR_ARG;
+    }
+    // shared vocabulary nodes: merge of the two ascending id lists (the f1it/f2it walk, :689-789)
+    std::vector<int32_t> it1, ib2, ie2;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i = fv1_ptr[a]; i < fv1_ptr[a + 1]; i++) { it1.push_back(fv1_idx[i]); ib2.push_back(fv2_ptr[b]); ie2.push_back(fv2_ptr[b + 1]); }
+            a++; b++;
+        } else if (fv1_node[a] < fv2_node[b]) a++;
+        else b++;
+    }
+    const int nItems = (int)it1.size();
+    const int nidx2 = nn2 > 0 ? fv2_ptr[nn2] : 0;
+    const size_t need = (size_t)(n1 + n2) * (28 + 32 + 4 + 1) + (size_t)nidx2 * 4 + (size_t)nItems * 12 + (size_t)n1 * 12 + 64 * 256;
+    if (!ensure_scratch(c, need, 0)) return ORBB200_ERR_CUDA;
+    Arena A(c.d_scratch, c.d_scratch_bytes);
+    auto up = [&](const void* src, size_t bytes) -> void* {
+        if (!src || bytes == 0) return nullptr;
+        uint8_t* d = A.take<uint8_t>(bytes);
+        cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c.stream);
+        return d;
+    };
+    TriJob J{};
+    J.kps1 = (const orbb200_kp_t*)up(kps1, sizeof(orbb200_kp_t) * (size_t)n1); J.desc1 = (const uint8_t*)up(desc1, 32 * (size_t)n1);
+    J.uR1 = (const float*)up(uR1, 4 * (size_t)n1); J.has_mp1 = (const uint8_t*)up(has_mp1, n1); J.n1 = n1;
+    J.kps2 = (const orbb200_kp_t*)up(kps2, sizeof(orbb200_kp_t) * (size_t)n2); J.desc2 = (const uint8_t*)up(desc2, 32 * (size_t)n2);
+    J.uR2 = (const float*)up(uR2, 4 * (size_t)n2); J.has_mp2 = (const uint8_t*)up(has_mp2, n2); J.n2 = n2;
+    J.fv2_idx = (const int32_t*)up(fv2_idx, 4 * (size_t)nidx2);
+    J.item_idx1 = (const int32_t*)up(it1.data(), 4 * (size_t)nItems); J.item_b2 = (const int32_t*)up(ib2.data(), 4 * (size_t)nItems);
+    J.item_e2 = (const int32_t*)up(ie2.data(), 4 * (size_t)nItems); J.nItems = nItems;
+    J.F12 = (const float*)up(F12, 36); J.ex = ex; J.ey = ey;
+    J.scaleFactors2 = (const float*)up(scale_factors2, 4 * (size_t)c.nlevels); J.levelSigma2_2 = (const float*)up(level_sigma2_2, 4 * (size_t)c.nlevels);
+    J.onlyStereo = only_stereo; J.checkOri = check_ori;
+    J.match12 = A.take<int32_t>(std::max(n1, 1)); J.pairs = A.take<int32_t>(2 * (size_t)std::max(n1, 1)); J.npairs = A.take<int32_t>(1);
+    launch_triangulation(c, J);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    int32_t np = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&np, J.npairs, 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));   // also keeps it1/ib2/ie2 alive until uploaded
+    if (np > 0) {
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(pairs, J.pairs, 8 * (size_t)np, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    }
+    *npairs = np;
+    return ORBB200_OK;
+}
+
+// ---- batched C2 step ----------------------------------------------------------------------------------
+int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_bytes, int n_frames, int w, int h,
+                               size_t stride, const orbb200_proj_queries* d_queries, int nq_per_frame,
+                               float th, float nnratio, float min_x, float min_y, float inv_w, float inv_h,
+                               int32_t* d_out_best_idx, int32_t* d_out_best_dist, int32_t* d_nmatches)
+{
+    CTX_ENTER(ctx);
+    if (n_frames <= 0 || 2 * n_frames > c.maxBatch || !d_queries || nq_per_frame < 0 || !d_out_best_idx || !d_out_best_dist || !d_nmatches) {
+        c.err = "stereo_step: bad argument"; return ORBB200_ERR_ARG;
+    }
+    int rc = orbb200_extract_device(ctx, d_imgs, img_bytes, 2 * n_frames, w, h, stride);
+    if (rc != ORBB200_OK) return rc;
+    const int kpi = c.cur->g.kpPerImg, nq = nq_per_frame;
+    // workspace in the scratch arena: frames, grids, jobs, per-job scratch, per-kp outputs
+    const size_t perFrame = align_up(sizeof(FrameDev), 256) + align_up(4 * (size_t)(GRID_CELLS + 1), 256) + align_up(4 * (size_t)kpi, 256) * 2 +
+                            align_up(sizeof(WinJob), 256) + align_up(4 * win_scratch_ints(kpi, nq), 256);
+    const size_t hostNeed = (size_t)n_frames * (sizeof(FrameDev) + sizeof(WinJob)) + 1024;
+    if (!ensure_scratch(c, perFrame * n_frames + 8192, hostNeed)) return ORBB200_ERR_CUDA;
+    Arena A(c.d_scratch, c.d_scratch_bytes);
+    FrameDev* dF = A.take<FrameDev>(n_frames);
+    WinJob* dJ = A.take<WinJob>(n_frames);
+    float* dsf = A.take<float>(MAX_LEVELS);
+    FrameDev* hF = reinterpret_cast<FrameDev*>(c.h_scratch);
+    WinJob* hJ = reinterpret_cast<WinJob*>(c.h_scratch + align_up(sizeof(FrameDev) * n_frames, 256));
+    float* hsf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(hJ) + align_up(sizeof(WinJob) * n_frames, 256));
+    // the pinned staging is reused every call: wait until the previous upload has been consumed
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    for (int l = 0; l < c.nlevels; l++) hsf[l] = c.scale[l];
+    for (int i = 0; i < n_frames; i++) {
+        FrameDev& f = hF[i];
+        const int img = 2 * i;
+        f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32; f.uRight = nullptr;
+        f.n_ptr = c.d_counts + img; f.n = kpi;
+        f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi);
+        f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
+        WinJob& J = hJ[i];
+        memset(&J, 0, sizeof(J));
+        J.frame = dF + i; J.nq = nq; J.mode = WM_PROJ; J.kpCap = kpi; J.th = th; J.nnratio = nnratio; J.scaleFactors = dsf;
+        const size_t o = (size_t)i * nq;
+        J.q_valid = d_queries->q_valid ? d_queries->q_valid + o : nullptr;
+        J.q_x = d_queries->q_u + o; J.q_y = d_queries->q_v + o; J.q_aux = d_queries->q_uR + o; J.q_level = d_queries->q_level + o;
+        J.q_viewcos = d_queries->q_viewcos + o; J.q_desc = d_queries->q_desc + o * 32;
+        J.q_obs_pos = d_queries->q_obs_pos ? d_queries->q_obs_pos + o : nullptr;
+        J.scratch = A.take<int>(win_scratch_ints(kpi, nq));
+        J.out_best_idx = d_out_best_idx + o; J.out_best_dist = d_out_best_dist + o;
+        J.out_per_kp = A.take<int32_t>(kpi);
+        J.out_nmatches = d_nmatches + i;
+    }
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dF, hF, sizeof(FrameDev) * n_frames, cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, hJ, sizeof(WinJob) * n_frames, cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dsf, hsf, sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream));
+    launch_grid_build(c, dF, n_frames);
+    launch_window_match(c, dJ, n_frames);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Context object behind orbb200_ctx: parameters, per-shape geometry cache, HBM-resident pools.
+#pragma once
+#include <map>
+#include <utility>
+
+#include "orbb200_internal.cuh"
+
+namespace orbb200 {
+
+struct ShapeTables {
+    Geom g;
+    int2* d_xtab = nullptr;     // resize: per output x of levels>=1: {sx, a0 | a1<<16}
+    int4* d_ytab = nullptr;     // resize: per output y of levels>=1: {sy0, sy1, b0, b1}
+    int4* d_cells = nullptr;    // FAST cells of all levels: {x0|y0<<16, x1|y1<<16, level, order index}
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)
+    int nfeatures = 0;
+    double scaleFactor = 1.2;
+    int nlevels = 8, iniTh = 20, minTh = 7;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> quota;
+
+    int maxW = 0, maxH = 0, maxBatch = 0;
+    Geom gmax;                               // geometry of the largest shape: sizes the pools
+    std::map<std::pair<int, int>, ShapeTables> shapes;
+    const ShapeTables* cur = nullptr;        // shape of the last extraction
+    int curN = 0;
+
+    // pools (per image blocks, maxBatch images)
+    uint8_t* d_pyr = nullptr;                // [maxBatch][pyrBytes]   pyramid levels (row pitch 128-aligned)
+    uint8_t* d_blur = nullptr;               // [maxBatch][pyrBytes]   GaussianBlur'ed levels
+    uint32_t* d_cand = nullptr;              // [maxBatch][candPerImg] x:12|y:12|response:8, region coords
+    uint16_t* d_nodeOf = nullptr;            // [maxBatch][candPerImg] octree scratch
+    int32_t* d_candCount = nullptr;          // [maxBatch][MAX_LEVELS]
+    uint32_t* d_lvlKp = nullptr;             // [maxBatch][kpPerImg]   octree winners, same packing
+    int32_t* d_lvlCount = nullptr;           // [maxBatch][MAX_LEVELS]
+    orbb200_kp_t* d_kps = nullptr;           // [maxBatch][kpPerImg]
+    uint8_t* d_desc = nullptr;               // [maxBatch][kpPerImg][32]
+    int32_t* d_counts = nullptr;             // [maxBatch]
+    int32_t* d_status = nullptr;             // device-side error flags (octree overflow etc.)
+
+    // staging for host entry points
+    uint8_t* h_stage = nullptr;              // pinned
+    size_t h_stage_bytes = 0;
+    uint8_t* d_scratch = nullptr;            // generic device scratch (matcher uploads)
+    size_t d_scratch_bytes = 0;
+    uint8_t* h_scratch = nullptr;            // pinned generic
+    size_t h_scratch_bytes = 0;
+};
+
+bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes);
+const ShapeTables* get_shape(Ctx& c, int w, int h);   // nullptr + c.err on failure
+bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err);
+
+#define ORBB200_CUDA_OK(c, call)                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            (c).err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            return ORBB200_ERR_CUDA;                                                       \
+        }                                                                                  \
+    } while (0)
+
+}  // namespace orbb200

@@ -1,0 +1,852 @@
+// Extraction kernels: pyramid resize, 7x7 Gaussian blur, per-cell FAST-9 with threshold fallback,
+// octree distribution, intensity-centroid orientation and rBRIEF descriptors.
+//
+// Integer arithmetic follows OpenCV 4.x exactly (DESIGN.md
+// and SURVEY.md Appendix A lists each primitive); float arithmetic uses explicit round-to-nearest intrinsics so that nvcc
+// never contracts it into FMAs.
+#include "ctx.cuh"
+#include "../../include/orbb200_pattern.inc"
+
+namespace orbb200 {
+
+// ---------------------------------------------------------------------------------------------------
+// import: user images (arbitrary stride) -> level 0 of the pyramid pool (pitch 128-aligned)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__ src, size_t img_bytes, size_t stride,
+                                                     uint8_t* __restrict__ pyr, unsigned pyrBytes, int w, int h, int pitch)
+{
+    const int img = blockIdx.z;
+    const int y = blockIdx.y;
+    const uint8_t* s = src + (size_t)img * img_bytes + (size_t)y * stride;
+    uint8_t* d = pyr + (size_t)img * pyrBytes + (size_t)y * pitch;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= w) return;
+    if (((reinterpret_cast<uintptr_t>(s) & 3) == 0) && x4 + 3 < w) {
+        *reinterpret_cast<uint32_t*>(d + x4) = __ldg(reinterpret_cast<const uint32_t*>(s + x4));
+    } else {
+        for (int i = 0; i < 4 && x4 + i < w; i++) d[x4 + i] = __ldg(s + x4 + i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cv::resize INTER_LINEAR u8 (reference src/ORBextractor.cc:1120): level l-1 -> l.
+// 11-bit fixed-point coefficients from host-built tables; vertical pass
+// (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
+                                                     const int2* __restrict__ xtab, const int4* __restrict__ ytab)
+{
+    const int img = blockIdx.z;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (y >= dst.h || x4 >= dst.w) return;
+    const uint8_t* S = pyr + (size_t)img * pyrBytes + src.off;
+    uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off + (size_t)y * dst.pitch;
+    const int4 yt = __ldg(ytab + dst.ytabOff + y);
+    const uint8_t* S0 = S + (size_t)yt.x * src.pitch;
+    const uint8_t* S1 = S + (size_t)yt.y * src.pitch;
+    const int b0 = yt.z, b1 = yt.w;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = min(x4 + i, dst.w - 1);
+        const int2 xt = __ldg(xtab + dst.xtabOff + x);
+        const int sx = xt.x, sx1 = min(sx + 1, src.w - 1);
+        const int a0 = xt.y & 0xffff, a1 = xt.y >> 16;
+        const int r0 = S0[sx] * a0 + S0[sx1] * a1;
+        const int r1 = S1[sx] * a0 + S1[sx1] * a1;
+        const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        out |= (uint32_t)(v & 0xff) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(D + x4) = out;   // pitch padding absorbs the tail
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cv::GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (reference src/ORBextractor.cc:1085-1086).
+// Q8.8 kernel {18,34,48,56,48,34,18}; H in u16, V in u32, (v + 2^15) >> 16.
+// One launch covers all levels: blockIdx.y indexes a flattened (level, tile-row) table.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BL_TW = 128, BL_TH = 16;
+
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * (len - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned pyrBytes,
+                                                   Geom g, int level)
+{
+    __shared__ __align__(16) uint8_t sIn[BL_TH + 6][BL_TW + 8];
+    __shared__ __align__(16) uint16_t sH[BL_TH + 6][BL_TW];
+    const LevelGeom L = g.lv[level];
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+    if (x0 >= L.w || y0 >= L.h) return;
+    const uint8_t* S = pyr + (size_t)img * pyrBytes + L.off;
+    uint8_t* D = blur + (size_t)img * pyrBytes + L.off;
+    const int tid = threadIdx.x;
+    // load (BL_TH+6) x (BL_TW+8) bytes, columns x0-4 .. x0+BL_TW+3, as 32-bit words where fully inside
+    constexpr int WPR = (BL_TW + 8) / 4;
+    for (int i = tid; i < (BL_TH + 6) * WPR; i += 256) {
+        const int r = i / WPR, k = i - r * WPR;
+        int gy = reflect101(y0 - 3 + r, L.h);
+        gy = min(max(gy, 0), L.h - 1);   // tiles past the bottom edge (tiny levels)
+        const int gx = x0 - 4 + 4 * k;
+        const uint8_t* row = S + (size_t)gy * L.pitch;
+        uint32_t v;
+        if (gx >= 0 && gx + 3 < L.w) {
+            v = *reinterpret_cast<const uint32_t*>(row + gx);
+        } else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int xx = reflect101(gx + b, L.w);
+                xx = min(max(xx, 0), L.w - 1);
+                v |= (uint32_t)row[xx] << (8 * b);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(&sIn[r][4 * k]) = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += 256) {
+        const int r = i / BL_TW, x = i - r * BL_TW;
+        const uint8_t* p = &sIn[r][x + 1];   // column x0+x-3
+        sH[r][x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < BL_TH * (BL_TW / 4); i += 256) {
+        const int r = i / (BL_TW / 4), x = (i - r * (BL_TW / 4)) * 4;
+        if (y0 + r >= L.h || x0 + x >= L.w) continue;
+        uint32_t out = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t s = 18u * ((uint32_t)sH[r][x + b] + sH[r + 6][x + b]) + 34u * ((uint32_t)sH[r + 1][x + b] + sH[r + 5][x + b]) +
+                               48u * ((uint32_t)sH[r + 2][x + b] + sH[r + 4][x + b]) + 56u * (uint32_t)sH[r + 3][x + b];
+            out |= ((s + 32768u) >> 16) << (8 * b);
+        }
+        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * L.pitch + x0 + x) = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Grid FAST (reference src/ORBextractor.cc:789-829 + cv::FAST TYPE_9_16 with NMS).
+// One CTA per 30-px cell.  The threshold-independent score S = M-1 (M = best 9-arc contrast) is computed
+// for the cell's inner rectangle with two horizontally adjacent pixels per thread packed as s16x2
+// (VIMNMX3.S16x2); 3x3 strict-greater NMS inside the rectangle; a local maximum is a candidate if
+// S >= iniThFAST, or, when the cell has none, if S >= minThFAST.
+// Candidates are appended unordered to the level's pool: the octree only needs (x, y, response).
+// ---------------------------------------------------------------------------------------------------
+constexpr int FT_PITCH_W = 38;     // u32 words per tile row (2 pixels each): 68 px + bias, padded
+constexpr int FT_MAXH = 66;
+constexpr int FT_SCW = 80;         // score row pitch (bytes)
+constexpr int FT_MAXC = 1024;      // >= ceil(59/2)^2 local maxima per cell
+constexpr int FT_THREADS = 128;
+
+__device__ __forceinline__ uint32_t min3s(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3s(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+
+// score of the two pixels packed in `c` given the 16 ring pairs; lanes hold u8 values
+__device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (&r)[16])
+{
+    uint32_t d[16];
+    const uint32_t cb = c + 0x01000100u;            // bias 256 per lane: no cross-lane borrow below
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = cb - r[k];  // 256 + (v - p_k) in [1,511]
+    uint32_t lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo3[k] = min3s(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        hi3[k] = max3s(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    }
+    uint32_t mn[16], mx[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn[k] = min3s(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);   // min over the 9-arc starting at k
+        mx[k] = max3s(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    }
+    uint32_t a = max3s(mn[0], mn[1], mn[2]);
+    a = max3s(a, mn[3], mn[4]); a = max3s(a, mn[5], mn[6]); a = max3s(a, mn[7], mn[8]);
+    a = max3s(a, mn[9], mn[10]); a = max3s(a, mn[11], mn[12]); a = max3s(a, mn[13], mn[14]);
+    a = __vmaxs2(a, mn[15]);                        // 256 + M_dark
+    uint32_t b = min3s(mx[0], mx[1], mx[2]);
+    b = min3s(b, mx[3], mx[4]); b = min3s(b, mx[5], mx[6]); b = min3s(b, mx[7], mx[8]);
+    b = min3s(b, mx[9], mx[10]); b = min3s(b, mx[11], mx[12]); b = min3s(b, mx[13], mx[14]);
+    b = __vmins2(b, mx[15]);                        // 256 - M_bright
+    // S + 512 = max(M_dark - 1, M_bright - 1, 0) + 512
+    const uint32_t s = max3s(a + 0x00ff00ffu, 0x02ff02ffu - b, 0x02000200u);
+    return s - 0x02000200u;
+}
+
+__global__ void __launch_bounds__(FT_THREADS) fast_cells_kernel(Geom g, const uint8_t* __restrict__ pyr, const int4* __restrict__ cells,
+                                                                uint32_t* __restrict__ cand, int32_t* __restrict__ candCount)
+{
+    __shared__ uint32_t tile[FT_MAXH][FT_PITCH_W];
+    __shared__ __align__(4) uint8_t scr[FT_MAXH - 4][FT_SCW];
+    __shared__ uint32_t clist[FT_MAXC];
+    __shared__ int sN, sNini, sBase, sOut;
+
+    const int img = blockIdx.y;
+    const int4 cell = __ldg(cells + blockIdx.x);
+    const int x0 = cell.x & 0xffff, y0 = cell.x >> 16, x1 = cell.y & 0xffff, y1 = cell.y >> 16;
+    const int level = cell.z;
+    const LevelGeom L = g.lv[level];
+    const int tid = threadIdx.x;
+    const int xa = x0 & ~3;
+    const int tw = x1 - xa, th = y1 - y0;
+    const int wi = x1 - x0 - 6, hi = th - 6;
+    if (wi <= 0 || hi <= 0) return;
+    const int cx0 = x0 - xa + 3, cx1 = cx0 + wi;    // inner columns in tile coordinates
+
+    if (tid == 0) { sN = 0; sNini = 0; sOut = 0; }
+    // zero the score tile (borders must read as 0)
+    for (int i = tid; i < (hi + 2) * (FT_SCW / 4); i += FT_THREADS) reinterpret_cast<uint32_t*>(&scr[0][0])[i] = 0;
+    // load the cell image: 32-bit words, widened to u16 pairs; pixel column tc lives at u16 index tc+2
+    const uint8_t* S = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)y0 * L.pitch + xa;
+    const int nw = (tw + 3) >> 2;
+    for (int i = tid; i < th * nw; i += FT_THREADS) {
+        const int r = __float2int_rz(__fmul_rz((float)i + 0.5f, __frcp_rn((float)nw)));
+        const int k = i - r * nw;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * L.pitch + 4 * k);
+        tile[r][1 + 2 * k] = __byte_perm(v, 0, 0x4140);
+        tile[r][2 + 2 * k] = __byte_perm(v, 0, 0x4342);
+    }
+    __syncthreads();
+
+    // scores: pairs (2m, 2m+1) covering the inner columns
+    const int m0 = cx0 >> 1, m1 = (cx1 - 1) >> 1, npr = m1 - m0 + 1;
+    const float rnpr = __frcp_rn((float)npr);
+    for (int i = tid; i < hi * npr; i += FT_THREADS) {
+        const int rr = __float2int_rz(__fmul_rz((float)i + 0.5f, rnpr));
+        const int m = m0 + (i - rr * npr);
+        const int tr = rr + 3;
+        const uint32_t* t = &tile[tr][m + 1];
+        // ring order k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+        uint32_t r[16];
+        {
+            const uint32_t* p = t + 3 * FT_PITCH_W;                 // dy = +3 : dx -1,0,1
+            const uint32_t wl = p[-1], wc = p[0], wr = p[1];
+            r[15] = __funnelshift_r(wl, wc, 16); r[0] = wc; r[1] = __funnelshift_r(wc, wr, 16);
+        }
+        {
+            const uint32_t* p = t - 3 * FT_PITCH_W;                 // dy = -3
+            const uint32_t wl = p[-1], wc = p[0], wr = p[1];
+            r[9] = __funnelshift_r(wl, wc, 16); r[8] = wc; r[7] = __funnelshift_r(wc, wr, 16);
+        }
+        r[14] = t[2 * FT_PITCH_W - 1]; r[2] = t[2 * FT_PITCH_W + 1];      // dy=+2: dx -2, +2
+        r[10] = t[-2 * FT_PITCH_W - 1]; r[6] = t[-2 * FT_PITCH_W + 1];    // dy=-2
+        {
+            const uint32_t* p = t + FT_PITCH_W;                     // dy = +1 : dx -3, +3
+            r[13] = __funnelshift_r(p[-2], p[-1], 16); r[3] = __funnelshift_r(p[1], p[2], 16);
+        }
+        {
+            const uint32_t* p = t - FT_PITCH_W;                     // dy = -1
+            r[11] = __funnelshift_r(p[-2], p[-1], 16); r[5] = __funnelshift_r(p[1], p[2], 16);
+        }
+        r[12] = __funnelshift_r(t[-2], t[-1], 16); r[4] = __funnelshift_r(t[1], t[2], 16);   // dy = 0
+        const uint32_t s = fast_score_pair(t[0], r);
+        const int c = 2 * m;
+        uint8_t* o = &scr[rr + 1][c];
+        if (c >= cx0 && c < cx1) o[0] = (uint8_t)(s & 0xff);
+        if (c + 1 >= cx0 && c + 1 < cx1) o[1] = (uint8_t)((s >> 16) & 0xff);
+    }
+    __syncthreads();
+
+    // NMS + threshold (raw neighbour scores suffice: a neighbour below the threshold is below S anyway)
+    const float rwi = __frcp_rn((float)wi);
+    const int minTh = g.minTh, iniTh = g.iniTh;
+    for (int i = tid; i < hi * wi; i += FT_THREADS) {
+        const int rr = __float2int_rz(__fmul_rz((float)i + 0.5f, rwi));
+        const int c = cx0 + (i - rr * wi);
+        const uint8_t* p = &scr[rr + 1][c];
+        const int s = p[0];
+        if (s < minTh) continue;
+        if (s > p[-1] && s > p[1] && s > p[-FT_SCW - 1] && s > p[-FT_SCW] && s > p[-FT_SCW + 1] &&
+            s > p[FT_SCW - 1] && s > p[FT_SCW] && s > p[FT_SCW + 1]) {
+            const int slot = atomicAdd(&sN, 1);
+            if (s >= iniTh) atomicAdd(&sNini, 1);
+            const int rx = xa + c - FAST_BORDER, ry = y0 + rr + 3 - FAST_BORDER;   // region coordinates
+            if (slot < FT_MAXC) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)s << 24);
+        }
+    }
+    __syncthreads();
+    const int nAll = min(sN, FT_MAXC), nIni = sNini;
+    const int nEmit = nIni > 0 ? nIni : nAll;
+    if (nEmit == 0) return;
+    if (tid == 0) sBase = atomicAdd(&candCount[img * MAX_LEVELS + level], nEmit);
+    __syncthreads();
+    uint32_t* out = cand + (size_t)img * g.candPerImg + L.candOff;
+    const int base = sBase;
+    for (int i = tid; i < nAll; i += FT_THREADS) {
+        const uint32_t v = clist[i];
+        if (nIni > 0 && (int)(v >> 24) < iniTh) continue;
+        const int o = atomicAdd(&sOut, 1);
+        if (base + o < L.candCap) out[base + o] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DistributeOctTree (reference src/ORBextractor.cc:539-763, DivideNode :481-537) as bulk passes over
+// arrays, one CTA per (image, level).  The std::list is a position-ordered node table; every pass:
+//   1. count the four children of each node that may be split (one sweep over the candidates),
+//   2. choose the split set: all nodes with >1 keys ("full" pass, :598-665) or the size-sorted prefix of
+//      last pass's children up to the first point where |list| >= N (:676-733),
+//   3. new list = reverse(children in processing order) ++ (unsplit nodes in old order),
+//   4. relabel the candidates (second sweep).
+// Size ties in the sorted pass: most recently created node first == smaller list position first
+// (the documented tie rule).  Winner per final node: max response, first in
+// (cell row, cell col, y, x) order on ties (:744-759).
+// ---------------------------------------------------------------------------------------------------
+constexpr int OT_THREADS = 512;
+
+struct OtNode { short x0, y0, x1, y1; };
+
+__device__ __forceinline__ int block_scan_excl(int v, int* warpSums, int& total)
+{
+    // exclusive scan across the block of one value per thread; all threads must call
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < (OT_THREADS / 32) ? warpSums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < (OT_THREADS / 32)) warpSums[lane] = s;
+    }
+    __syncthreads();
+    const int wbase = wid ? warpSums[wid - 1] : 0;
+    total = warpSums[OT_THREADS / 32 - 1];
+    __syncthreads();
+    return wbase + x - v;
+}
+
+size_t octree_smem_bytes(int maxNodes)
+{
+    const int P2 = 1 << (32 - __builtin_clz(std::max(maxNodes, 2) - 1));
+    // nodes A,B (8 B) + cnt A,B (4 B) + cc (16 B) + newPos (4 B) + childPos (16 B) + order (4 B) + sort keys (P2*4)
+    return (size_t)maxNodes * (8 * 2 + 4 * 2 + 16 + 4 + 16 + 4 + 4) + (size_t)P2 * 4 + 256;
+}
+
+__global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
+                                                            uint16_t* __restrict__ nodeOfAll, uint32_t* __restrict__ lvlKp,
+                                                            int32_t* __restrict__ lvlCount, int32_t* __restrict__ status)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int warpSums[OT_THREADS / 32];
+    __shared__ int sFlag;
+
+    const int level = blockIdx.x, img = blockIdx.y;
+    const LevelGeom L = g.lv[level];
+    const int tid = threadIdx.x;
+    const int N = L.quota;
+    const int maxNodes = L.maxNodes;
+    int n = min(candCount[img * MAX_LEVELS + level], L.candCap);
+    const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
+    uint16_t* nodeOf = nodeOfAll + (size_t)img * g.candPerImg + L.candOff;
+    uint32_t* outKp = lvlKp + (size_t)img * g.kpPerImg + L.kpOff;
+
+    // carve shared memory
+    const int P2 = 1 << (32 - __clz(max(maxNodes, 2) - 1));
+    OtNode* nodesA = reinterpret_cast<OtNode*>(smem);
+    OtNode* nodesB = nodesA + maxNodes;
+    int* cntA = reinterpret_cast<int*>(nodesB + maxNodes);
+    int* cntB = cntA + maxNodes;
+    int* cc = cntB + maxNodes;               // [maxNodes][4] child counts
+    int* newPos = cc + 4 * maxNodes;         // [maxNodes] new position of an unsplit node, or -1 if split
+    int* childPos = newPos + maxNodes;       // [maxNodes][4] new position of each child (-1 if empty)
+    int* order = childPos + 4 * maxNodes;    // [maxNodes] processing order -> node position
+    int* aux = order + maxNodes;             // [maxNodes] scratch (split flag / processing rank)
+    uint32_t* keys = reinterpret_cast<uint32_t*>(aux + maxNodes);   // [P2] sort keys
+
+    if (n == 0 || L.nIni <= 0 || L.nIni > maxNodes) {
+        if (tid == 0) lvlCount[img * MAX_LEVELS + level] = 0;
+        return;
+    }
+
+    OtNode* cur = nodesA;
+    OtNode* nxt = nodesB;
+    int* curCnt = cntA;
+    int* nxtCnt = cntB;
+
+    // ---- root nodes (:543-592) ----
+    const int nIni = L.nIni;
+    const float hX = L.hX;
+    const int regH = L.maxBY - FAST_BORDER;
+    for (int i = tid; i < nIni; i += OT_THREADS) {
+        OtNode nd;
+        nd.x0 = (short)(int)__fmul_rn(hX, (float)i);
+        nd.x1 = (short)(int)__fmul_rn(hX, (float)(i + 1));
+        nd.y0 = 0;
+        nd.y1 = (short)regH;
+        cur[i] = nd;
+        curCnt[i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += OT_THREADS) {
+        const uint32_t v = C[i];
+        const int x = v & 0xfff;
+        int r = (int)__fdiv_rn((float)x, hX);
+        r = min(r, nIni - 1);
+        nodeOf[i] = (uint16_t)r;
+        atomicAdd(&curCnt[r], 1);
+    }
+    __syncthreads();
+    // drop empty roots (compaction in order)
+    int listSize;
+    {
+        int total = 0;
+        // nIni is tiny (<= a handful): serial by one thread
+        if (tid == 0) {
+            int k = 0;
+            for (int i = 0; i < nIni; i++) {
+                newPos[i] = curCnt[i] > 0 ? k : -1;
+                if (curCnt[i] > 0) { nxt[k] = cur[i]; nxtCnt[k] = curCnt[i]; k++; }
+            }
+            sFlag = k;
+        }
+        __syncthreads();
+        total = sFlag;
+        for (int i = tid; i < n; i += OT_THREADS) nodeOf[i] = (uint16_t)newPos[nodeOf[i]];
+        __syncthreads();
+        listSize = total;
+        OtNode* t = cur; cur = nxt; nxt = t;
+        int* tc = curCnt; curCnt = nxtCnt; nxtCnt = tc;
+    }
+
+    int frontNew = 0;        // number of nodes at the list front created by the last pass
+    bool sortedMode = false;
+    bool finish = false;
+    int guard = 0;
+    while (!finish && guard++ < 64) {
+        const int prevSize = listSize;
+        // ---- 1. which nodes may be split in this pass, and in which order ----
+        // full pass: every node with cnt>1, list order.  sorted pass: front nodes with cnt>1, by (cnt desc, pos asc).
+        int nProc = 0;
+        if (!sortedMode) {
+            int carry = 0;
+            for (int base = 0; base < listSize; base += OT_THREADS) {
+                const int p = base + tid;
+                const int f = (p < listSize && curCnt[p] > 1) ? 1 : 0;
+                int tot;
+                const int ex = block_scan_excl(f, warpSums, tot);
+                if (f) order[carry + ex] = p;
+                carry += tot;
+            }
+            nProc = carry;
+        } else {
+            int carry = 0;
+            for (int base = 0; base < frontNew; base += OT_THREADS) {
+                const int p = base + tid;
+                const int f = (p < frontNew && curCnt[p] > 1) ? 1 : 0;
+                int tot;
+                const int ex = block_scan_excl(f, warpSums, tot);
+                if (f) keys[carry + ex] = ((uint32_t)min(curCnt[p], 0xffff) << 16) | (uint32_t)(0xffff - p);
+                carry += tot;
+            }
+            nProc = carry;
+            int S2 = 1;
+            while (S2 < nProc) S2 <<= 1;
+            for (int i = nProc + tid; i < S2; i += OT_THREADS) keys[i] = 0;
+            __syncthreads();
+            // bitonic sort, descending
+            for (int k = 2; k <= S2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < S2; i += OT_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint32_t a = keys[i], b = keys[ixj];
+                            const bool desc = (i & k) == 0;
+                            if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < nProc; i += OT_THREADS) order[i] = 0xffff - (int)(keys[i] & 0xffff);
+        }
+        __syncthreads();
+
+        // ---- 2. child counts of the nodes in `order` ----
+        for (int i = tid; i < listSize; i += OT_THREADS) aux[i] = -1;
+        __syncthreads();
+        for (int i = tid; i < nProc; i += OT_THREADS) {
+            const int p = order[i];
+            aux[p] = i;                       // processing rank
+            cc[4 * p + 0] = 0; cc[4 * p + 1] = 0; cc[4 * p + 2] = 0; cc[4 * p + 3] = 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += OT_THREADS) {
+            const int p = nodeOf[i];
+            if (aux[p] < 0) continue;
+            const uint32_t v = C[i];
+            const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+            const OtNode nd = cur[p];
+            const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+            const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
+            atomicAdd(&cc[4 * p + q], 1);
+        }
+        __syncthreads();
+
+        // ---- 3. how many of `order` are actually split (sorted pass stops once |list| >= N) ----
+        // prefix over processing order of (non-empty children - 1)
+        int nSplit = nProc;
+        int nChildrenTotal = 0;
+        {
+            int carryKids = 0;
+            if (tid == 0) sFlag = nProc;      // first processing index at which the list reaches N (sorted mode)
+            __syncthreads();
+            for (int base = 0; base < nProc; base += OT_THREADS) {
+                const int i = base + tid;
+                int kids = 0;
+                if (i < nProc) {
+                    const int p = order[i];
+                    kids = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0);
+                }
+                int tot;
+                const int ex = block_scan_excl(kids, warpSums, tot);
+                if (i < nProc) {
+                    // child sequence start for this node = carryKids + ex; stash in childPos[4p] for now
+                    childPos[4 * order[i]] = carryKids + ex;
+                    if (sortedMode) {
+                        // list size after processing nodes 0..i (inclusive)
+                        const int sizeAfter = prevSize + (carryKids + ex + kids) - (i + 1);
+                        if (sizeAfter >= N) atomicMin(&sFlag, i);
+                    }
+                }
+                carryKids += tot;
+            }
+            __syncthreads();
+            if (sortedMode && sFlag < nProc) nSplit = sFlag + 1;
+            __syncthreads();
+            // total children of the split prefix
+            if (nSplit > 0) {
+                const int pl = order[nSplit - 1];
+                const int kidsLast = (cc[4 * pl] > 0) + (cc[4 * pl + 1] > 0) + (cc[4 * pl + 2] > 0) + (cc[4 * pl + 3] > 0);
+                nChildrenTotal = childPos[4 * pl] + kidsLast;
+            }
+        }
+        __syncthreads();
+        const int newSize = listSize - nSplit + nChildrenTotal;
+        if (newSize > maxNodes) {       // cannot happen for sane geometry; fail loudly rather than corrupt
+            if (tid == 0) { atomicExch(status, 1); lvlCount[img * MAX_LEVELS + level] = 0; }
+            return;
+        }
+
+        // ---- 4. build the new list ----
+        // children: sequence index s (processing order, n1..n4) -> position nChildrenTotal-1-s
+        int nToExpand = 0;
+        for (int i = tid; i < nSplit; i += OT_THREADS) {
+            const int p = order[i];
+            const OtNode nd = cur[p];
+            const int hx = (nd.x1 - nd.x0 + 1) >> 1, hy = (nd.y1 - nd.y0 + 1) >> 1;
+            int s = childPos[4 * p];
+            const int c0 = cc[4 * p], c1 = cc[4 * p + 1], c2 = cc[4 * p + 2], c3 = cc[4 * p + 3];
+            int pos[4] = {-1, -1, -1, -1};
+            if (c0 > 0) { pos[0] = nChildrenTotal - 1 - s; s++; }
+            if (c1 > 0) { pos[1] = nChildrenTotal - 1 - s; s++; }
+            if (c2 > 0) { pos[2] = nChildrenTotal - 1 - s; s++; }
+            if (c3 > 0) { pos[3] = nChildrenTotal - 1 - s; s++; }
+            if (pos[0] >= 0) { OtNode c; c.x0 = nd.x0; c.y0 = nd.y0; c.x1 = nd.x0 + hx; c.y1 = nd.y0 + hy; nxt[pos[0]] = c; nxtCnt[pos[0]] = c0; }
+            if (pos[1] >= 0) { OtNode c; c.x0 = nd.x0 + hx; c.y0 = nd.y0; c.x1 = nd.x1; c.y1 = nd.y0 + hy; nxt[pos[1]] = c; nxtCnt[pos[1]] = c1; }
+            if (pos[2] >= 0) { OtNode c; c.x0 = nd.x0; c.y0 = nd.y0 + hy; c.x1 = nd.x0 + hx; c.y1 = nd.y1; nxt[pos[2]] = c; nxtCnt[pos[2]] = c2; }
+            if (pos[3] >= 0) { OtNode c; c.x0 = nd.x0 + hx; c.y0 = nd.y0 + hy; c.x1 = nd.x1; c.y1 = nd.y1; nxt[pos[3]] = c; nxtCnt[pos[3]] = c3; }
+            childPos[4 * p] = pos[0]; childPos[4 * p + 1] = pos[1]; childPos[4 * p + 2] = pos[2]; childPos[4 * p + 3] = pos[3];
+            nToExpand += (c0 > 1) + (c1 > 1) + (c2 > 1) + (c3 > 1);
+        }
+        // unsplit nodes keep their relative order after the children
+        {
+            int carry = 0;
+            for (int base = 0; base < listSize; base += OT_THREADS) {
+                const int p = base + tid;
+                const int keep = (p < listSize && !(aux[p] >= 0 && aux[p] < nSplit)) ? 1 : 0;
+                int tot;
+                const int ex = block_scan_excl(keep, warpSums, tot);
+                if (p < listSize) {
+                    if (keep) {
+                        const int np = nChildrenTotal + carry + ex;
+                        newPos[p] = np;
+                        nxt[np] = cur[p];
+                        nxtCnt[np] = curCnt[p];
+                    } else {
+                        newPos[p] = -1;
+                    }
+                }
+                carry += tot;
+            }
+        }
+        // nToExpand (block sum) only matters after a full pass
+        int nToExpandTotal;
+        {
+            int tot;
+            block_scan_excl(nToExpand, warpSums, tot);
+            nToExpandTotal = tot;
+        }
+        __syncthreads();
+
+        // ---- 5. relabel candidates ----
+        for (int i = tid; i < n; i += OT_THREADS) {
+            const int p = nodeOf[i];
+            const int np = newPos[p];
+            if (np >= 0) { nodeOf[i] = (uint16_t)np; continue; }
+            const uint32_t v = C[i];
+            const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+            const OtNode nd = cur[p];
+            const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+            const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
+            nodeOf[i] = (uint16_t)childPos[4 * p + q];
+        }
+        __syncthreads();
+        {
+            OtNode* t = cur; cur = nxt; nxt = t;
+            int* tc = curCnt; curCnt = nxtCnt; nxtCnt = tc;
+        }
+        listSize = newSize;
+        frontNew = nChildrenTotal;
+
+        // ---- 6. termination (:667-735) ----
+        if (listSize >= N || listSize == prevSize) {
+            finish = true;
+        } else if (!sortedMode) {
+            if (listSize + nToExpandTotal * 3 > N) sortedMode = true;
+        }
+    }
+
+    // ---- winners (:744-759): max response, first in (cell row, cell col, y, x) order ----
+    uint32_t* best = reinterpret_cast<uint32_t*>(cc);          // [listSize] max response
+    uint32_t* bestKey = reinterpret_cast<uint32_t*>(childPos); // [listSize] min order key among max-response keys
+    uint32_t* bestVal = reinterpret_cast<uint32_t*>(newPos);   // [listSize] packed candidate
+    for (int i = tid; i < listSize; i += OT_THREADS) { best[i] = 0; bestKey[i] = 0xffffffffu; }
+    __syncthreads();
+    for (int i = tid; i < n; i += OT_THREADS) atomicMax(&best[nodeOf[i]], C[i] >> 24);
+    __syncthreads();
+    const int wCell = L.wCell, hCell = L.hCell, nCols = L.nCols;
+    for (int i = tid; i < n; i += OT_THREADS) {
+        const uint32_t v = C[i];
+        const int p = nodeOf[i];
+        if ((v >> 24) != best[p]) continue;
+        const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+        const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
+        const uint32_t key = ((uint32_t)(ci * nCols + cj) << 12) | ((uint32_t)(y - 3 - ci * hCell) << 6) | (uint32_t)(x - 3 - cj * wCell);
+        atomicMin(&bestKey[p], key);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += OT_THREADS) {
+        const uint32_t v = C[i];
+        const int p = nodeOf[i];
+        if ((v >> 24) != best[p]) continue;
+        const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+        const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
+        const uint32_t key = ((uint32_t)(ci * nCols + cj) << 12) | ((uint32_t)(y - 3 - ci * hCell) << 6) | (uint32_t)(x - 3 - cj * wCell);
+        if (key == bestKey[p]) bestVal[p] = v;
+    }
+    __syncthreads();
+    const int nOut = min(listSize, L.kpCap);
+    for (int i = tid; i < nOut; i += OT_THREADS) outKp[i] = bestVal[i];
+    if (tid == 0) {
+        lvlCount[img * MAX_LEVELS + level] = nOut;
+        if (listSize > L.kpCap) atomicExch(status, 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Orientation (IC_Angle, reference src/ORBextractor.cc:77-104 + cv::fastAtan2) and rBRIEF
+// (computeOrbDescriptor :108-147): one warp per keypoint.  Writes the final cv::KeyPoint records
+// (operator() :1095-1103: pt *= scale for level > 0) and descriptors in level-major order.
+// ---------------------------------------------------------------------------------------------------
+__constant__ signed char c_patX[512] = {ORBB200_PATTERN_X_INIT};
+__constant__ signed char c_patY[512] = {ORBB200_PATTERN_Y_INIT};
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // :454-469
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    // cv::fastAtan2, float32 without FMA contraction
+    constexpr float k180pi = (float)(180.0 / 3.14159265358979323846);
+    constexpr float p1 = 0.9997878412794807f * k180pi, p3 = -0.3258083974640975f * k180pi;
+    constexpr float p5 = 0.1555786518463281f * k180pi, p7 = -0.04432655554792128f * k180pi;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    const float eps = 2.22044605e-16f;   // (float)DBL_EPSILON
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+constexpr int DS_WARPS = 8;
+
+__global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                                                                 const uint32_t* __restrict__ lvlKp, const int32_t* __restrict__ lvlCount,
+                                                                 orbb200_kp_t* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                                 int32_t* __restrict__ counts)
+{
+    __shared__ signed char sPX[512], sPY[512];
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { sPX[i] = c_patX[i]; sPY[i] = c_patY[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gk = blockIdx.x * DS_WARPS + (threadIdx.x >> 5);    // keypoint index within the image (output order)
+    // locate level
+    int level = -1, off = 0, total = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        const int c = lvlCount[img * MAX_LEVELS + l];
+        if (level < 0 && gk < total + c) { level = l; off = total; }
+        total += c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = total;
+    if (level < 0) return;
+    const LevelGeom L = g.lv[level];
+    const uint32_t v = lvlKp[(size_t)img * g.kpPerImg + L.kpOff + (gk - off)];
+    const int x = (int)(v & 0xfff) + FAST_BORDER, y = (int)((v >> 12) & 0xfff) + FAST_BORDER;
+    const int resp = (int)(v >> 24);
+
+    // ---- IC_Angle on the un-blurred level ----
+    const uint8_t* center = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)y * L.pitch + x;
+    int m01 = 0, m10 = 0;
+    const int u = lane - HALF_PATCH;      // lanes 0..30 -> u = -15..15
+    if (lane < 31) {
+        m10 = u * center[u];
+#pragma unroll
+        for (int vv = 1; vv <= HALF_PATCH; vv++) {
+            if (abs(u) <= c_umax[vv]) {
+                const int vp = center[u + vv * L.pitch], vm = center[u - vv * L.pitch];
+                m01 += vv * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rBRIEF on the blurred level ----
+    constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);   // (float)(CV_PI/180.f), :106
+    const float ang = __fmul_rn(angle, factorPI);
+    // cosf/sinf of the host libm are correctly rounded for all but ~1e-8 of inputs; round a double
+    // evaluation to float to match them (float parity)
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
+    const uint8_t* bc = blur + (size_t)img * g.pyrBytes + L.off + (size_t)y * L.pitch + x;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int idx = lane * 16 + 2 * k + e;
+            const float px = (float)sPX[idx], py = (float)sPY[idx];
+            const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            t[e] = bc[yy * L.pitch + xx];
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    const size_t o = (size_t)img * g.kpPerImg + gk;
+    desc[o * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        orbb200_kp_t kp;
+        kp.x = (float)x; kp.y = (float)y;
+        if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }
+        kp.size = (float)L.patchSize;
+        kp.angle = angle;
+        kp.response = (float)resp;
+        kp.octave = level;
+        kp.class_id = -1;
+        kps[o] = kp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n)
+{
+    const Geom& g = c.cur->g;
+    dim3 grid((g.w / 4 + 255) / 256 + 1, g.h, n);
+    grid.x = ((g.w + 3) / 4 + 255) / 256;
+    import_kernel<<<grid, 256, 0, c.stream>>>(d_imgs, img_bytes, stride, c.d_pyr, g.pyrBytes, g.w, g.h, g.lv[0].pitch);
+    c.launches++;
+}
+
+void launch_pyramid(Ctx& c, int n)
+{
+    const Geom& g = c.cur->g;
+    for (int l = 1; l < g.nlevels; l++) {
+        const LevelGeom& d = g.lv[l];
+        if (d.w <= 0 || d.h <= 0) break;
+        dim3 block(64, 4);
+        dim3 grid(((d.w + 3) / 4 + 63) / 64, (d.h + 3) / 4, n);
+        resize_kernel<<<grid, block, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, c.cur->d_xtab, c.cur->d_ytab);
+        c.launches++;
+    }
+}
+
+void launch_blur(Ctx& c, int n)
+{
+    const Geom& g = c.cur->g;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        if (L.w <= 0 || L.h <= 0) continue;
+        dim3 grid((L.w + BL_TW - 1) / BL_TW, (L.h + BL_TH - 1) / BL_TH, n);
+        blur_kernel<<<grid, 256, 0, c.stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, l);
+        c.launches++;
+    }
+}
+
+void launch_fast(Ctx& c, int n)
+{
+    const Geom& g = c.cur->g;
+    cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
+    if (g.totalCells > 0) {
+        dim3 grid(g.totalCells, n);
+        fast_cells_kernel<<<grid, FT_THREADS, 0, c.stream>>>(g, c.d_pyr, c.cur->d_cells, c.d_cand, c.d_candCount);
+        c.launches++;
+    }
+}
+
+void launch_octree(Ctx& c, int n)
+{
+    const Geom& g = c.cur->g;
+    int maxNodes = 2;
+    for (int l = 0; l < g.nlevels; l++) maxNodes = std::max(maxNodes, g.lv[l].maxNodes);
+    const size_t smem = octree_smem_bytes(maxNodes);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid(g.nlevels, n);
+    octree_kernel<<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+    c.launches++;
+}
+
+void launch_describe(Ctx& c, int n)
+{
+    const Geom& g = c.cur->g;
+    dim3 grid((g.kpPerImg + DS_WARPS - 1) / DS_WARPS, n);
+    describe_kernel<<<grid, DS_WARPS * 32, 0, c.stream>>>(g, c.d_pyr, c.d_blur, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts);
+    c.launches++;
+}
+
+}  // namespace orbb200

@@ -1,0 +1,587 @@
+// Matching kernels: 256-bit Hamming brute force (best / second best), device lookup grid, and the
+// windowed greedy searches of ORBmatcher restated as parallel fixed-point iterations.
+#include "match.cuh"
+
+namespace orbb200 {
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
+{
+    // ORBmatcher::DescriptorDistance (reference src/ORBmatcher.cc:1647-1663): popcount of the 256-bit XOR
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Brute force knn2: grid = (map splits, query tiles).  Each thread keeps KN_QPT query descriptors in
+// registers; map descriptors are staged in shared memory tiles and read as warp-wide broadcasts.
+// Partial (best_d, best_idx, second_d) per (split, query) are merged by knn2_merge_kernel in split order
+// so that the first minimum in index order wins, exactly like a sequential scan with strict '<'.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KN_THREADS = 128;
+constexpr int KN_QPT = 4;
+constexpr int KN_MT = 128;       // map descriptors per shared-memory tile
+
+__global__ void __launch_bounds__(KN_THREADS) knn2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ m, int nm,
+                                                          int mPerSplit, int4* __restrict__ partial)
+{
+    __shared__ uint4 sM[2][KN_MT][2];
+    const int tid = threadIdx.x;
+    const int split = blockIdx.x;
+    const int mBeg = split * mPerSplit, mEnd = min(nm, mBeg + mPerSplit);
+    const int qBase = blockIdx.y * (KN_THREADS * KN_QPT);
+
+    uint4 qa[KN_QPT], qb[KN_QPT];
+    int best[KN_QPT], second[KN_QPT], bidx[KN_QPT];
+#pragma unroll
+    for (int j = 0; j < KN_QPT; j++) {
+        const int qi = min(qBase + j * KN_THREADS + tid, nq - 1);
+        qa[j] = __ldg(q + 2 * (size_t)qi);
+        qb[j] = __ldg(q + 2 * (size_t)qi + 1);
+        best[j] = 256; second[j] = 256; bidx[j] = -1;
+    }
+    int buf = 0;
+    // prefetch first tile
+    {
+        const int mi = mBeg + tid;
+        if (mi < mEnd) { sM[0][tid][0] = __ldg(m + 2 * (size_t)mi); sM[0][tid][1] = __ldg(m + 2 * (size_t)mi + 1); }
+    }
+    __syncthreads();
+    for (int t0 = mBeg; t0 < mEnd; t0 += KN_MT) {
+        const int cnt = min(KN_MT, mEnd - t0);
+        // prefetch next tile into the other buffer
+        const int nmi = t0 + KN_MT + tid;
+        uint4 n0, n1;
+        const bool havNext = nmi < mEnd;
+        if (havNext) { n0 = __ldg(m + 2 * (size_t)nmi); n1 = __ldg(m + 2 * (size_t)nmi + 1); }
+#pragma unroll 4
+        for (int i = 0; i < cnt; i++) {
+            const uint4 m0 = sM[buf][i][0], m1 = sM[buf][i][1];
+#pragma unroll
+            for (int j = 0; j < KN_QPT; j++) {
+                const int d = hamming256(qa[j], qb[j], m0, m1);
+                if (d < best[j]) { second[j] = best[j]; best[j] = d; bidx[j] = t0 + i; }
+                else second[j] = min(second[j], d);
+            }
+        }
+        if (havNext) { sM[buf ^ 1][tid][0] = n0; sM[buf ^ 1][tid][1] = n1; }
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int j = 0; j < KN_QPT; j++) {
+        const int qi = qBase + j * KN_THREADS + tid;
+        if (qi < nq) partial[(size_t)split * nq + qi] = make_int4(best[j], bidx[j], second[j], 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) knn2_merge_kernel(const int4* __restrict__ partial, int nq, int nsplit,
+                                                         int32_t* __restrict__ bi, int32_t* __restrict__ bd, int32_t* __restrict__ sd)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int best = 256, second = 256, idx = -1;
+    for (int s = 0; s < nsplit; s++) {
+        const int4 p = __ldg(partial + (size_t)s * nq + qi);
+        if (p.x < best) { second = min(best, p.z); best = p.x; idx = p.y; }
+        else second = min(second, p.x);     // p.z >= p.x
+    }
+    bi[qi] = idx; bd[qi] = best; sd[qi] = second;
+}
+
+void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
+                 int32_t* bi, int32_t* bd, int32_t* sd)
+{
+    const int mPerSplit = (nm + nsplit - 1) / nsplit;
+    dim3 grid(nsplit, (nq + KN_THREADS * KN_QPT - 1) / (KN_THREADS * KN_QPT));
+    knn2_kernel<<<grid, KN_THREADS, 0, c.stream>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_m), nm,
+                                                   mPerSplit, d_partial);
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, c.stream>>>(d_partial, nq, nsplit, bi, bd, sd);
+    c.launches += 2;
+}
+
+// POPC issue-rate micro-benchmark: the denominator of the matching roofline.
+__global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t* out, int iters, uint32_t seed)
+{
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x, c0 = a ^ b, d0 = a + b;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s0 += __popc(a); s1 += __popc(b); s2 += __popc(c0); s3 += __popc(d0);
+            a += s3; b += s0; c0 += s1; d0 += s2;     // keep the chain data dependent, 4 independent streams
+        }
+    }
+    if ((s0 ^ s1 ^ s2 ^ s3) == 0x12345678u) out[0] = a;
+}
+
+void launch_popc_peak(Ctx& c, uint32_t* d_out, int blocks, int iters)
+{
+    popc_peak_kernel<<<blocks, 256, 0, c.stream>>>(d_out, iters, 12345u);
+    c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lookup grid: Frame::AssignFeaturesToGrid / PosInGrid[Birdview] (reference src/Frame.cc:378-412,
+// 549-559, 879-889).  CSR over 64x48 cells, column-major cell id = ix*48+iy (the scan order of
+// GetFeaturesInArea), items in ascending keypoint index inside each cell.  One CTA per frame.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int frame_count(const FrameDev& F) { return F.n_ptr ? min(*F.n_ptr, F.n) : F.n; }
+
+__device__ __forceinline__ int grid_cell_of(const FrameDev& F, const orbb200_kp_t& kp)
+{
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, F.minX), F.invW));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, F.minY), F.invH));
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return -1;
+    return px * GRID_ROWS + py;
+}
+
+__global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __restrict__ frames)
+{
+    __shared__ int sCnt[GRID_CELLS];
+    __shared__ int warpTot[32];
+    const FrameDev F = frames[blockIdx.x];
+    const int n = frame_count(F);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < GRID_CELLS; i += 1024) sCnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int cid = grid_cell_of(F, F.kps[i]);
+        if (cid >= 0) atomicAdd(&sCnt[cid], 1);
+    }
+    __syncthreads();
+    // exclusive scan over 3072 cells: 3 per thread
+    int v[3], s = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v[k] = sCnt[tid * 3 + k]; s += v[k]; }
+    int x = s;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warpTot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int t = warpTot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+        warpTot[lane] = t;
+    }
+    __syncthreads();
+    int ex = (wid ? warpTot[wid - 1] : 0) + x - s;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { F.cellStart[tid * 3 + k] = ex; sCnt[tid * 3 + k] = ex; ex += v[k]; }
+    if (tid == 1023) F.cellStart[GRID_CELLS] = ex;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int cid = grid_cell_of(F, F.kps[i]);
+        if (cid >= 0) F.cellItems[atomicAdd(&sCnt[cid], 1)] = i;
+    }
+    __syncthreads();
+    // restore ascending index order inside each cell (lists are a few items long)
+    for (int cidx = tid; cidx < GRID_CELLS; cidx += 1024) {
+        const int b = F.cellStart[cidx], e = sCnt[cidx];
+        for (int i = b + 1; i < e; i++) {
+            const int key = F.cellItems[i];
+            int j = i - 1;
+            while (j >= b && F.cellItems[j] > key) { F.cellItems[j + 1] = F.cellItems[j]; j--; }
+            F.cellItems[j + 1] = key;
+        }
+    }
+}
+
+void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes)
+{
+    grid_build_kernel<<<nframes, 1024, 0, c.stream>>>(d_frames);
+    c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Windowed searches.  A "job" is one reference matcher call: a frame (grid) and nq queries.  One CTA per
+// job.  The reference loops are sequential because later queries see earlier assignments:
+//   BLOCK semantics  (SearchByProjection x2, SearchByProjectionBird): a keypoint that an earlier accepted
+//                    query with Observations()>0 took is skipped;
+//   DIST semantics   (BirdviewMatch x2, SearchByMatchBird(KF,F)): a keypoint is skipped when
+//                    vMatchedDistance[idx] <= dist, i.e. when an earlier accepted query matched it at <= dist.
+// Both make query q a function of the final choices of queries < q only, so iterating "recompute every
+// query from the previous round's choices" reaches the unique fixed point = the sequential result;
+// rounds needed = longest dependency chain + 1 (2-4 in practice).
+// ---------------------------------------------------------------------------------------------------
+struct Sel { int best, second, bestIdx, bestLevel, secondLevel; };
+
+template <class Visit>
+__device__ __forceinline__ void scan_window(const FrameDev& F, float x, float y, float r, int minLevel, int maxLevel, Visit&& visit)
+{
+    // Frame::GetFeaturesInArea[Birdview] (reference src/Frame.cc:494-547, 891-944)
+    const float fx = __fsub_rn(x, F.minX), fy = __fsub_rn(y, F.minY);
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(fx, r), F.invW)));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(fx, r), F.invW)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(fy, r), F.invH)));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(fy, r), F.invH)));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        // cells (ix, nMinCellY..nMaxCellY) are contiguous in the column-major CSR
+        const int b = F.cellStart[ix * GRID_ROWS + nMinCellY], e = F.cellStart[ix * GRID_ROWS + nMaxCellY + 1];
+        for (int k = b; k < e; k++) {
+            const int idx = F.cellItems[k];
+            const orbb200_kp_t kp = F.kps[idx];
+            if (bCheckLevels) {
+                if (kp.octave < minLevel) continue;
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+            }
+            const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+            if (fabsf(dx) < r && fabsf(dy) < r) visit(idx, kp);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) features_in_area_kernel(const FrameDev* frames, float x, float y, float r, int minLevel, int maxLevel,
+                                                               int32_t* out, int cap, int32_t* count)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const FrameDev F = frames[0];
+    int n = 0;
+    scan_window(F, x, y, r, minLevel, maxLevel, [&](int idx, const orbb200_kp_t&) { if (n < cap) out[n] = idx; n++; });
+    *count = n;
+}
+
+void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, float r, int minLevel, int maxLevel,
+                             int32_t* d_out, int cap, int32_t* d_count)
+{
+    features_in_area_kernel<<<1, 32, 0, c.stream>>>(d_frame, x, y, r, minLevel, maxLevel, d_out, cap, d_count);
+    c.launches++;
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2)
+{
+    // rot = a1 - a2 (+360 if <0); bin = round(rot * (1/HISTO_LENGTH)) (reference src/ORBmatcher.cc:236-246)
+    constexpr float factor = 1.0f / HISTO_LENGTH;
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return min(max(bin, 0), HISTO_LENGTH - 1);
+}
+
+// ORBmatcher::ComputeThreeMaxima (reference src/ORBmatcher.cc:1601-1642)
+__device__ void three_maxima(const int* histo, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+
+constexpr int WM_THREADS = 512;
+
+__global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* __restrict__ jobs)
+{
+    __shared__ int sHist[HISTO_LENGTH];
+    __shared__ int sKeep[3];
+    __shared__ int sCount, sRemoved;
+    const WinJob J = jobs[blockIdx.x];
+    const FrameDev F = *J.frame;
+    const int nkp = frame_count(F);
+    const int nq = J.nq;
+    const int tid = threadIdx.x;
+    const int mode = J.mode;
+    const bool distSem = (mode == WM_BIRD || mode == WM_BIRD_KF);
+
+    int* owner = J.scratch;                 // [kpCap] BLOCK: min blocking query; DIST: head of claimant list
+    int* lastOwner = owner + J.kpCap;       // [kpCap] max accepted query per keypoint
+    int* choice = lastOwner + J.kpCap;      // [nq]    published: accepted keypoint or -1
+    int* cdist = choice + nq;               // [nq]    published: its distance
+    int* newChoice = cdist + nq;            // [nq]    staged during a sweep
+    int* newCdist = newChoice + nq;         // [nq]
+    int* nextq = newCdist + nq;             // [nq]    DIST: claimant list link
+    int* qbin = nextq + nq;                 // [nq]    rotation bin of an accepted query
+
+    for (int i = tid; i < nkp; i += WM_THREADS) { owner[i] = distSem ? -1 : 0x7fffffff; lastOwner[i] = -1; }
+    for (int i = tid; i < nq; i += WM_THREADS) { choice[i] = -1; cdist[i] = 0; }
+    __syncthreads();
+
+    for (int round = 0; round <= nq; round++) {
+        int changed = 0;
+        for (int q = tid; q < nq; q += WM_THREADS) {
+            int selIdx = -1, selDist = 0;
+            if (J.q_valid == nullptr || J.q_valid[q]) {
+                // ---- per-mode window ----
+                float x, y, r, urRef = 0.f, urTol = 0.f;
+                int minL = -1, maxL = -1;
+                bool skip = false, urCheck = false;
+                if (mode == WM_PROJ) {
+                    const int lvl = J.q_level[q];
+                    r = J.q_viewcos[q] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
+                    if (J.th != 1.0f) r = __fmul_rn(r, J.th);
+                    r = __fmul_rn(r, J.scaleFactors[lvl]);
+                    x = J.q_x[q]; y = J.q_y[q]; minL = lvl - 1; maxL = lvl;
+                    urCheck = true; urRef = J.q_aux[q]; urTol = r;
+                } else if (mode == WM_PROJ_FRAME) {
+                    const int oct = J.q_level[q];
+                    r = __fmul_rn(J.th, J.scaleFactors[oct]);
+                    x = J.q_x[q]; y = J.q_y[q];
+                    if (J.levelMode == 1) { minL = oct; maxL = -1; }
+                    else if (J.levelMode == 2) { minL = 0; maxL = oct; }
+                    else { minL = oct - 1; maxL = oct + 1; }
+                    urCheck = true; urRef = __fsub_rn(x, __fmul_rn(J.mbf, J.q_aux[q])); urTol = r;
+                } else if (mode == WM_BIRD) {
+                    const int lvl = J.q_level[q];
+                    if (J.levelMode == 1 && lvl > 0) skip = true;             // prevMatched variant: octave 0 only
+                    x = J.q_x[q]; y = J.q_y[q]; r = J.th; minL = lvl; maxL = lvl;
+                } else {   // WM_BIRD_KF, WM_PROJ_BIRD
+                    x = J.q_x[q]; y = J.q_y[q]; r = J.th;
+                }
+                if (!skip) {
+                    const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
+                    const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+                    const int big = distSem ? 0x7fffffff : 256;
+                    int best = big, second = big, bestIdx = -1, bestLevel = -1, secondLevel = -1;
+                    scan_window(F, x, y, r, minL, maxL, [&](int idx, const orbb200_kp_t& kp) {
+                        if (!distSem) {
+                            if (J.kp_blocked && J.kp_blocked[idx]) return;
+                            if (owner[idx] < q) return;
+                            if (urCheck && F.uRight) {
+                                const float ur = F.uRight[idx];
+                                if (ur > 0 && fabsf(__fsub_rn(urRef, ur)) > urTol) return;
+                            }
+                        }
+                        const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
+                        const int d = hamming256(qa, qb, kd[0], kd[1]);
+                        if (distSem) {
+                            // vMatchedDistance[idx] <= d as left by the accepted queries < q
+                            for (int c = owner[idx]; c >= 0; c = nextq[c])
+                                if (c < q && cdist[c] <= d) return;
+                        }
+                        if (d < best) { second = best; best = d; secondLevel = bestLevel; bestLevel = kp.octave; bestIdx = idx; }
+                        else if (d < second) { secondLevel = kp.octave; second = d; }
+                    });
+                    bool acc;
+                    if (mode == WM_PROJ || mode == WM_PROJ_BIRD)
+                        acc = best <= TH_HIGH && !(bestLevel == secondLevel && (float)best > __fmul_rn(J.nnratio, (float)second));
+                    else if (mode == WM_PROJ_FRAME)
+                        acc = best <= TH_HIGH;
+                    else if (mode == WM_BIRD)
+                        acc = best <= TH_LOW && (float)best < __fmul_rn((float)second, J.nnratio);
+                    else
+                        acc = best <= TH_HIGH && (bestLevel != secondLevel || (float)best < __fmul_rn((float)second, J.nnratio));
+                    if (acc) { selIdx = bestIdx; selDist = best; }
+                }
+            }
+            if (selIdx != choice[q] || selDist != cdist[q]) changed = 1;
+            newChoice[q] = selIdx;      // published after the barrier: other threads still read choice/cdist
+            newCdist[q] = selDist;
+        }
+        const int any = __syncthreads_or(changed);
+        if (!any) break;
+        for (int q = tid; q < nq; q += WM_THREADS) { choice[q] = newChoice[q]; cdist[q] = newCdist[q]; }
+        for (int i = tid; i < nkp; i += WM_THREADS) owner[i] = distSem ? -1 : 0x7fffffff;
+        __syncthreads();
+        for (int q = tid; q < nq; q += WM_THREADS) {
+            const int cidx = choice[q];
+            if (cidx < 0) continue;
+            if (distSem) nextq[q] = atomicExch(&owner[cidx], q);
+            else if (J.q_obs_pos == nullptr || J.q_obs_pos[q]) atomicMin(&owner[cidx], q);
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs ----
+    if (tid < HISTO_LENGTH) sHist[tid] = 0;
+    if (tid == 0) { sCount = 0; sRemoved = 0; }
+    __syncthreads();
+    int nAcc = 0;
+    for (int q = tid; q < nq; q += WM_THREADS) {
+        const int cidx = choice[q];
+        qbin[q] = -1;
+        if (cidx < 0) continue;
+        nAcc++;
+        atomicMax(&lastOwner[cidx], q);
+        if (J.checkOri) {
+            const int b = rot_bin(J.q_angle[q], F.kps[cidx].angle);
+            qbin[q] = b;
+            atomicAdd(&sHist[b], 1);
+        }
+    }
+    if (nAcc) atomicAdd(&sCount, nAcc);
+    __syncthreads();
+    if (tid == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (J.checkOri) three_maxima(sHist, i1, i2, i3);
+        sKeep[0] = i1; sKeep[1] = i2; sKeep[2] = i3;
+    }
+    __syncthreads();
+    const int k1 = sKeep[0], k2 = sKeep[1], k3 = sKeep[2];
+    if (J.out_best_idx)
+        for (int q = tid; q < nq; q += WM_THREADS) { J.out_best_idx[q] = choice[q]; if (J.out_best_dist) J.out_best_dist[q] = choice[q] >= 0 ? cdist[q] : 256; }
+    if (mode == WM_BIRD) {
+        // vnMatches12 (:1725-1733): the last accepted claimant owns the keypoint; rotation filter only
+        // un-matches queries that still hold their match (:1758-1768)
+        int removed = 0, owned = 0;
+        for (int q = tid; q < nq; q += WM_THREADS) {
+            const int cidx = choice[q];
+            int m = -1;
+            if (cidx >= 0 && lastOwner[cidx] == q) {
+                owned++;
+                m = cidx;
+                if (J.checkOri) { const int b = qbin[q]; if (b != k1 && b != k2 && b != k3) { m = -1; removed++; } }
+            }
+            J.out_per_query[q] = m;
+        }
+        __syncthreads();              // sCount (accepted) has been read by nobody yet: reuse as "owned"
+        if (tid == 0) sCount = 0;
+        __syncthreads();
+        if (owned) atomicAdd(&sCount, owned);
+        if (removed) atomicAdd(&sRemoved, removed);
+        __syncthreads();
+        if (tid == 0) *J.out_nmatches = sCount - sRemoved;
+        return;
+    }
+    // BLOCK modes and BIRD_KF: per keypoint the last accepted query, unless an accepted query on it sits in a
+    // discarded rotation bin (:1455-1463, :2098-2108); nmatches = accepted - entries in discarded bins
+    for (int i = tid; i < nkp; i += WM_THREADS) J.out_per_kp[i] = lastOwner[i];
+    __syncthreads();
+    if (J.checkOri) {
+        int removed = 0;
+        for (int q = tid; q < nq; q += WM_THREADS) {
+            const int cidx = choice[q];
+            if (cidx < 0) continue;
+            const int b = qbin[q];
+            if (b != k1 && b != k2 && b != k3) { J.out_per_kp[cidx] = -1; removed++; }
+        }
+        if (removed) atomicAdd(&sRemoved, removed);
+    }
+    __syncthreads();
+    if (tid == 0) *J.out_nmatches = sCount - sRemoved;
+}
+
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs)
+{
+    window_match_kernel<<<njobs, WM_THREADS, 0, c.stream>>>(d_jobs);
+    c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SearchForTriangulation (reference src/ORBmatcher.cc:657-823): no loop-carried state (vbMatched2 is never
+// set), so every keypoint of KF1 is independent.  One warp per KF1 keypoint of a shared vocabulary node;
+// lanes stride over the node's KF2 keypoints; the running "dist <= bestDist" rule makes the winner the
+// minimum distance among candidates passing the epipolar tests, last in scan order on ties.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) triangulation_kernel(TriJob J)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= J.nItems) return;
+    const int idx1 = J.item_idx1[w];
+    const int b2 = J.item_b2[w], e2 = J.item_e2[w];
+    J.match12[idx1] = -1;
+    if (J.has_mp1[idx1]) return;
+    const bool st1 = J.uR1 ? J.uR1[idx1] >= 0 : false;
+    if (J.onlyStereo && !st1) return;
+    const orbb200_kp_t kp1 = J.kps1[idx1];
+    const uint4* d1 = reinterpret_cast<const uint4*>(J.desc1) + 2 * (size_t)idx1;
+    const uint4 qa = d1[0], qb = d1[1];
+    // epipolar line of kp1 in image 2 (CheckDistEpipolarLine, :140-157)
+    const float* Fm = J.F12;
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, Fm[0]), __fmul_rn(kp1.y, Fm[3])), Fm[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, Fm[1]), __fmul_rn(kp1.y, Fm[4])), Fm[7]);
+    const float cc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, Fm[2]), __fmul_rn(kp1.y, Fm[5])), Fm[8]);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    int best = 0x7fffffff, bestPos = -1;   // minimise (dist, -pos)
+    for (int p = b2 + lane; p < e2; p += 32) {
+        const int idx2 = J.fv2_idx[p];
+        if (J.has_mp2[idx2]) continue;
+        const bool st2 = J.uR2 ? J.uR2[idx2] >= 0 : false;
+        if (J.onlyStereo && !st2) continue;
+        const uint4* d2 = reinterpret_cast<const uint4*>(J.desc2) + 2 * (size_t)idx2;
+        const int dist = hamming256(qa, qb, d2[0], d2[1]);
+        if (dist > TH_LOW) continue;
+        const orbb200_kp_t kp2 = J.kps2[idx2];
+        if (!st1 && !st2) {
+            const float dx = __fsub_rn(J.ex, kp2.x), dy = __fsub_rn(J.ey, kp2.y);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, J.scaleFactors2[kp2.octave])) continue;
+        }
+        if (den == 0) continue;
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, kp2.x), __fmul_rn(b, kp2.y)), cc);
+        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+        if (!((double)dsqr < 3.84 * (double)J.levelSigma2_2[kp2.octave])) continue;
+        if (dist < best || (dist == best && p > bestPos)) { best = dist; bestPos = p; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, bestPos, o);
+        if (ob < best || (ob == best && op > bestPos)) { best = ob; bestPos = op; }
+    }
+    if (lane == 0 && bestPos >= 0) J.match12[idx1] = J.fv2_idx[bestPos];
+}
+
+// rotation-histogram filter + pair compaction (:791-822); single CTA
+__global__ void __launch_bounds__(1024) triangulation_finish_kernel(TriJob J)
+{
+    __shared__ int sHist[HISTO_LENGTH];
+    __shared__ int sKeep[3];
+    __shared__ int warpTot[32];
+    const int tid = threadIdx.x;
+    if (tid < HISTO_LENGTH) sHist[tid] = 0;
+    __syncthreads();
+    if (J.checkOri) {
+        for (int i = tid; i < J.n1; i += 1024) {
+            const int m = J.match12[i];
+            if (m >= 0) atomicAdd(&sHist[rot_bin(J.kps1[i].angle, J.kps2[m].angle)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) { int a, b, c; three_maxima(sHist, a, b, c); sKeep[0] = a; sKeep[1] = b; sKeep[2] = c; }
+        __syncthreads();
+        for (int i = tid; i < J.n1; i += 1024) {
+            const int m = J.match12[i];
+            if (m < 0) continue;
+            const int bin = rot_bin(J.kps1[i].angle, J.kps2[m].angle);
+            if (bin != sKeep[0] && bin != sKeep[1] && bin != sKeep[2]) J.match12[i] = -1;
+        }
+        __syncthreads();
+    }
+    // ordered compaction over idx1
+    int carry = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < J.n1; base += 1024) {
+        const int i = base + tid;
+        const int f = (i < J.n1 && J.match12[i] >= 0) ? 1 : 0;
+        int x = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warpTot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int t = warpTot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            warpTot[lane] = t;
+        }
+        __syncthreads();
+        const int ex = carry + (wid ? warpTot[wid - 1] : 0) + x - f;
+        if (f) { J.pairs[2 * ex] = i; J.pairs[2 * ex + 1] = J.match12[i]; }
+        carry += warpTot[31];
+        __syncthreads();
+    }
+    if (tid == 0) *J.npairs = carry;
+}
+
+void launch_triangulation(Ctx& c, const TriJob& J)
+{
+    if (J.n1 > 0) cudaMemsetAsync(J.match12, 0xff, sizeof(int32_t) * J.n1, c.stream);
+    if (J.nItems > 0) {
+        triangulation_kernel<<<(J.nItems * 32 + 255) / 256, 256, 0, c.stream>>>(J);
+        c.launches++;
+    }
+    triangulation_finish_kernel<<<1, 1024, 0, c.stream>>>(J);
+    c.launches++;
+}
+
+}  // namespace orbb200

@@ -1,0 +1,57 @@
+// Matcher job descriptors shared by match.cu and api.cu.
+#pragma once
+#include "ctx.cuh"
+
+namespace orbb200 {
+
+enum WinMode { WM_PROJ = 0, WM_PROJ_FRAME = 1, WM_BIRD = 2, WM_BIRD_KF = 3, WM_PROJ_BIRD = 4 };
+
+// One windowed-search call (all pointers are device pointers).
+struct WinJob {
+    const FrameDev* frame;
+    int nq, mode, levelMode, checkOri, kpCap;
+    float th, nnratio, mbf;
+    const float* scaleFactors;
+    const uint8_t* q_valid;     // may be null (all valid)
+    const float* q_x;
+    const float* q_y;
+    const float* q_aux;         // WM_PROJ: projected uR; WM_PROJ_FRAME: 1/z
+    const int32_t* q_level;     // predicted level / octave
+    const float* q_viewcos;     // WM_PROJ
+    const float* q_angle;       // rotation histogram
+    const uint8_t* q_desc;
+    const uint8_t* q_obs_pos;   // may be null (all 1)
+    const uint8_t* kp_blocked;  // may be null (none)
+    int* scratch;               // 2*kpCap + 6*nq ints
+    int32_t* out_best_idx;      // [nq] or null
+    int32_t* out_best_dist;     // [nq] or null
+    int32_t* out_per_kp;        // [n] query assigned to each keypoint (all modes but WM_BIRD)
+    int32_t* out_per_query;     // [nq] WM_BIRD: vnMatches12
+    int32_t* out_nmatches;
+};
+
+static inline size_t win_scratch_ints(int kpCap, int nq) { return (size_t)2 * kpCap + (size_t)6 * nq; }
+
+struct TriJob {
+    const orbb200_kp_t* kps1; const uint8_t* desc1; const float* uR1; const uint8_t* has_mp1; int n1;
+    const orbb200_kp_t* kps2; const uint8_t* desc2; const float* uR2; const uint8_t* has_mp2; int n2;
+    const int32_t* fv2_idx;
+    const int32_t* item_idx1; const int32_t* item_b2; const int32_t* item_e2; int nItems;
+    const float* F12; float ex, ey;
+    const float* scaleFactors2; const float* levelSigma2_2;
+    int onlyStereo, checkOri;
+    int32_t* match12;           // [n1]
+    int32_t* pairs;             // [n1][2]
+    int32_t* npairs;
+};
+
+void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
+                 int32_t* bi, int32_t* bd, int32_t* sd);
+void launch_popc_peak(Ctx& c, uint32_t* d_out, int blocks, int iters);
+void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes);
+void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, float r, int minLevel, int maxLevel,
+                             int32_t* d_out, int cap, int32_t* d_count);
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs);
+void launch_triangulation(Ctx& c, const TriJob& J);
+
+}  // namespace orbb200

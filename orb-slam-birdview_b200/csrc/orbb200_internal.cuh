@@ -1,0 +1,79 @@
+// Internal declarations shared by the CUDA translation units of liborbb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orbb200.h"
+
+namespace orbb200 {
+
+constexpr int MAX_LEVELS = 12;
+constexpr int EDGE_THRESHOLD = 19;      // reference src/ORBextractor.cc:74
+constexpr int HALF_PATCH = 15;          // :73
+constexpr int PATCH_SIZE = 31;          // :72
+constexpr int FAST_BORDER = 16;         // EDGE_THRESHOLD-3, :776
+constexpr int GRID_COLS = 64;           // include/Frame.h:40
+constexpr int GRID_ROWS = 48;           // include/Frame.h:39
+constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // src/ORBmatcher.cc:37-39
+
+// Geometry of one pyramid level for one image shape (host-computed, passed to kernels by value).
+struct LevelGeom {
+    int w, h, pitch;        // level size; row pitch in bytes (multiple of 128)
+    unsigned off;           // byte offset of the level inside one image's pyramid block
+    float scale;            // mvScaleFactor[l]
+    int quota;              // mnFeaturesPerLevel[l]
+    // grid FAST (src/ORBextractor.cc:776-787)
+    int maxBX, maxBY;       // level coords: FAST region is [16,maxBX) x [16,maxBY)
+    int nCols, nRows, wCell, hCell;
+    int cellBase, nCells;   // range in the flattened cell table
+    // octree (src/ORBextractor.cc:543-546)
+    int nIni;
+    float hX;
+    int candCap;            // candidate slots for this level
+    unsigned candOff;       // offset (entries) in one image's candidate block
+    int kpCap;              // keypoint slots (>= quota + slack)
+    int kpOff;              // offset (entries) in one image's level-keypoint block
+    int maxNodes;           // node table size for the octree kernel
+    int xtabOff, ytabOff;   // offsets into the resize tables (level >= 1)
+    int patchSize;          // (int)(PATCH_SIZE*scale)
+};
+
+struct Geom {
+    int nlevels;
+    int w, h;
+    int iniTh, minTh;
+    unsigned pyrBytes;      // bytes of one image's pyramid block
+    unsigned candPerImg;    // candidate entries per image
+    int kpPerImg;           // level-keypoint entries per image (== output capacity per image)
+    int totalCells;
+    LevelGeom lv[MAX_LEVELS];
+};
+
+// Device-side frame (keypoints + descriptors + 64x48 CSR grid).
+struct FrameDev {
+    const orbb200_kp_t* kps;
+    const uint8_t* desc;
+    const float* uRight;        // may be null
+    const int32_t* n_ptr;       // device count (results of an extraction) or null
+    int n;                      // host-known count (uploaded frames) or capacity
+    int32_t* cellStart;         // [GRID_CELLS+1]
+    int32_t* cellItems;         // [cap]
+    float minX, minY, invW, invH;
+};
+
+struct Ctx;
+
+// ---- kernels launchers (extract.cu) ----
+void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);
+void launch_pyramid(Ctx& c, int n);
+void launch_blur(Ctx& c, int n);
+void launch_fast(Ctx& c, int n);
+void launch_octree(Ctx& c, int n);
+void launch_describe(Ctx& c, int n);
+size_t octree_smem_bytes(int maxNodes);
+
+}  // namespace orbb200

@@ -1,0 +1,71 @@
+"""CPU tests of the drop-in boundary: the C ABI library loads, exports every symbol include/orbb200.h
+declares, and fails loudly (no fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "orbb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import orb_slam_birdview_b200 as pkg
+    pkg.build()
+    return pkg
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/orbb200.h but not exported"
+    # and the Python binding table covers the header
+    missing = [n for n in names if n not in pkg._SIGNATURES]
+    assert not missing, missing
+
+
+def test_kp_layout_is_cv_keypoint(pkg):
+    assert pkg.KP_DTYPE.itemsize == 28
+    assert [pkg.KP_DTYPE.fields[f][1] for f in ("x", "y", "size", "angle", "response", "octave", "class_id")] == [0, 4, 8, 12, 16, 20, 24]
+
+
+def test_no_silent_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(pkg.OrbB200Error):
+        pkg.ORBextractor(1000, 1.2, 8, 20, 7)
+    lib = pkg.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.orbb200_create(ctypes.byref(h), 0, 1000, 1.2, 8, 20, 7, 752, 480, 1)
+    assert rc == -1 and b"CUDA" in lib.orbb200_last_error(None)
+    assert lib.orbb200_extract(None, None, 0, 0, 0, None, None, 0, None) == -2     # null context: ERR_ARG, no crash
+
+
+def test_bad_arguments_rejected_before_touching_the_device(pkg):
+    lib = pkg.load_library()
+    h = ctypes.c_void_p()
+    assert lib.orbb200_create(ctypes.byref(h), 0, 0, 1.2, 8, 20, 7, 752, 480, 1) == -2       # nfeatures <= 0
+    assert lib.orbb200_create(ctypes.byref(h), 0, 1000, 1.0, 8, 20, 7, 752, 480, 1) == -2    # scale <= 1
+    assert lib.orbb200_create(ctypes.byref(h), 0, 1000, 1.2, 99, 20, 7, 752, 480, 1) == -2   # too many levels
+    assert lib.orbb200_create(None, 0, 1000, 1.2, 8, 20, 7, 752, 480, 1) == -2
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped path must not import, link or call anything under oracle/."""
+    pk = os.path.join(ROOT, "orb-slam-birdview_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "liborb_oracle" not in txt and "orb_oracle.h" not in txt, os.path.join(dirpath, f)

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bar: bit-exact keypoints (coordinates, octave, response, angle), descriptors, match indices and
+Hamming distances.  Descriptor tolerance per BASELINE.json north_star: bit-exact wherever the angle agrees
+within 1e-4 rad, mismatch rate <= 0.1 % (we expect and assert 0 on these inputs and report the rate)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import GOLDEN, oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import orb_slam_birdview_b200 as pkg
+    pkg.load_library()
+    return pkg
+
+
+def _compare_extract(k_gpu, d_gpu, k_ref, d_ref, tag=""):
+    assert len(k_gpu) == len(k_ref), f"{tag}: keypoint count {len(k_gpu)} vs {len(k_ref)}"
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        bad = np.nonzero(k_gpu[f] != k_ref[f])[0]
+        assert len(bad) == 0, f"{tag}: field {f} differs at {bad[:5]}: {k_gpu[f][bad[:5]]} vs {k_ref[f][bad[:5]]}"
+    dang = np.abs(k_gpu["angle"].astype(np.float64) - k_ref["angle"].astype(np.float64)) * np.pi / 180.0
+    assert np.array_equal(k_gpu["angle"].view(np.uint32), k_ref["angle"].view(np.uint32)), f"{tag}: angles not bit-exact, max diff {dang.max()} rad"
+    agree = dang <= 1e-4
+    rows_bad = (d_gpu != d_ref).any(1)
+    rate = float(rows_bad.mean()) if len(rows_bad) else 0.0
+    assert not (rows_bad & agree).any() or rate <= 1e-3, f"{tag}: descriptor mismatch rate {rate}"
+    assert rate == 0.0, f"{tag}: descriptor mismatch rate {rate} (budget 1e-3)"
+    return rate
+
+
+SHAPES = [
+    ("c1", 480, 752, 1000, 20, 7, 1000),
+    ("bird", 400, 400, 2000, 15, 5, 3001),
+    ("kitti", 376, 1241, 2000, 20, 7, 2000),
+    ("small", 240, 320, 500, 20, 7, 77),
+    ("fisheye", 400, 950, 2000, 15, 5, 4000),
+]
+
+
+@pytest.mark.parametrize("name,h,w,nf,ini,mn,seed", SHAPES)
+def test_extract_vs_oracle(pkg, name, h, w, nf, ini, mn, seed):
+    img = synth.synth_frame(h, w, seed)
+    ex = pkg.ORBextractor(nf, 1.2, 8, ini, mn, max_size=(w, h))
+    k, d = ex(img)
+    orc = oracle.Extractor(nf, 1.2, 8, ini, mn)
+    k0, d0 = orc(img)
+    # stage by stage first, so a failure names the stage
+    pyr, blur = ex.image_pyramid(0, False), ex.image_pyramid(0, True)
+    for lvl in range(8):
+        assert np.array_equal(pyr[lvl], orc.level_image(lvl)), f"{name}: pyramid level {lvl}"
+        assert np.array_equal(blur[lvl], orc.level_image(lvl, blurred=True)), f"{name}: blurred level {lvl}"
+        c_gpu = ex.level_candidates(0, lvl)
+        c_ref = orc.level_candidates(lvl)
+        key = lambda c: np.lexsort((c[:, 2], c[:, 0], c[:, 1]))
+        assert len(c_gpu) == len(c_ref), f"{name}: candidates level {lvl}: {len(c_gpu)} vs {len(c_ref)}"
+        assert np.array_equal(c_gpu[key(c_gpu)], c_ref[key(c_ref)]), f"{name}: candidate set level {lvl}"
+    _compare_extract(k, d, k0, d0, name)
+    # idempotence on a reused context
+    k2, d2 = ex(img)
+    assert k.tobytes() == k2.tobytes() and np.array_equal(d, d2)
+
+
+@pytest.mark.parametrize("name", ["c1_752x480", "bird_400x400", "small_320x240"])
+def test_extract_vs_committed_golden(pkg, name):
+    g = np.load(os.path.join(GOLDEN, f"extract_{name}.npz"))
+    nf, ini, mn, _ = [int(v) for v in g["params"]]
+    img = g["img"]
+    ex = pkg.ORBextractor(nf, 1.2, 8, ini, mn, max_size=(img.shape[1], img.shape[0]))
+    k, d = ex(img)
+    _compare_extract(k, d, g["kps"], g["desc"], name)
+
+
+def test_extract_full_hd_4000(pkg):
+    """BASELINE.json config 5 shape at full size against the oracle."""
+    img = synth.synth_frame(1080, 1920, 5000)
+    ex = pkg.ORBextractor(4000, 1.2, 8, 20, 7, max_size=(1920, 1080))
+    k, d = ex(img)
+    k0, d0 = oracle.Extractor(4000, 1.2, 8, 20, 7)(img)
+    _compare_extract(k, d, k0, d0, "c5")
+
+
+def test_extract_batch_independent_of_batching(pkg):
+    imgs = [synth.synth_frame(376, 1241, 2000 + i) for i in range(5)]
+    ex = pkg.ORBextractor(2000, 1.2, 8, 20, 7, max_size=(1241, 376), max_batch=5)
+    K, D, N = ex.extract_batch(imgs)
+    orc = oracle.Extractor(2000, 1.2, 8, 20, 7)
+    for i, im in enumerate(imgs):
+        k0, d0 = orc(im)
+        _compare_extract(K[i, :N[i]], D[i, :N[i]], k0, d0, f"batch[{i}]")
+    # one at a time on the same context, and in a different order: byte-identical
+    for i in (3, 0):
+        k, d = ex(imgs[i])
+        assert k.tobytes() == K[i, :N[i]].tobytes() and np.array_equal(d, D[i, :N[i]])
+
+
+def test_extract_edge_cases(pkg):
+    ex = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_size=(400, 300))
+    k, d = ex(np.full((240, 320), 128, np.uint8))           # flat image: no keypoints, like the oracle
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = ex(np.empty((0, 0), np.uint8))                    # empty image: silent return
+    assert len(k) == 0
+    big = synth.synth_frame(300, 400, 21)
+    roi = big[10:250, 30:350]                                # strided ROI == contiguous copy
+    k1, d1 = ex(roi)
+    k0, d0 = oracle.Extractor(500, 1.2, 8, 20, 7)(np.ascontiguousarray(roi))
+    _compare_extract(k1, d1, k0, d0, "roi")
+    small = synth.synth_frame(100, 120, 22)                  # top levels too small for one FAST cell
+    k2, d2 = ex(small)
+    k0, d0 = oracle.Extractor(500, 1.2, 8, 20, 7)(small)
+    _compare_extract(k2, d2, k0, d0, "tiny levels")
+    with pytest.raises(pkg.OrbB200Error):
+        ex(synth.synth_frame(500, 700, 1))                   # larger than the context's max size
+
+
+def test_getters_match_oracle(pkg):
+    ex = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_size=(752, 480))
+    orc = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    assert np.array_equal(ex.GetScaleFactors(), orc.scale_factors())
+    assert np.array_equal(ex.ctx.features_per_level(), orc.features_per_level())
+    assert ex.GetLevels() == 8
+    sf = ex.GetScaleFactors()
+    assert np.array_equal(ex.GetInverseScaleFactors(), (np.float32(1) / sf).astype(np.float32))
+    assert np.array_equal(ex.GetScaleSigmaSquares(), (sf * sf).astype(np.float32))
+
+
+# ---- Hamming -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,nm", [(2000, 2000), (2000, 20000), (37, 1), (5, 0), (513, 129), (1, 70000)])
+def test_knn2_vs_oracle(pkg, nq, nm):
+    q = synth.synth_descriptors(nq, 100 + nq)
+    m = synth.synth_descriptors(nm, 200 + nm)
+    if nm > 10:
+        rng = np.random.default_rng(5)
+        plant = rng.integers(0, nm, max(1, nq // 10))
+        m[plant] = synth.perturb_descriptors(q[rng.integers(0, nq, len(plant))], 30, 6)
+        m[nm // 2] = q[0]
+        m[nm // 2 + 3] = q[0]                                # exact duplicates: first index wins, second == best
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    bi, bd, sd = pkg.ORBmatcher(ctx).hamming_knn2(q, m)
+    bi0, bd0, sd0 = oracle.hamming_knn2(q, m)
+    assert np.array_equal(bi, bi0) and np.array_equal(bd, bd0) and np.array_equal(sd, sd0)
+
+
+def test_knn2_full_size_properties(pkg):
+    """C4 at 2k x 200k: checked through size-independent properties + a sampled exact check."""
+    nq, nm = 2000, 200000
+    q = synth.synth_descriptors(nq, 1)
+    m = synth.synth_descriptors(nm, 2)
+    m[12345] = q[7]
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    bi, bd, sd = pkg.ORBmatcher(ctx).hamming_knn2(q, m)
+    assert bi[7] == 12345 and bd[7] == 0
+    assert (bd <= sd).all() and (bi >= 0).all() and (bi < nm).all()
+    d = np.unpackbits(q ^ m[bi], axis=1).sum(1)
+    assert np.array_equal(d, bd)                              # reported distance is the distance to the reported index
+    sub = np.arange(0, nq, 97)
+    bi0, bd0, sd0 = oracle.hamming_knn2(q[sub], m)
+    assert np.array_equal(bi[sub], bi0) and np.array_equal(bd[sub], bd0) and np.array_equal(sd[sub], sd0)
+    # permutation property: reversing the map order keeps best/second distances
+    bi_r, bd_r, sd_r = pkg.ORBmatcher(ctx).hamming_knn2(q, m[::-1].copy())
+    assert np.array_equal(bd_r, bd) and np.array_equal(sd_r, sd)
+
+
+# ---- grid + windowed searches ---------------------------------------------------------------------------
+def _frames(pkg, ctx, kps, desc, grid, uR=None):
+    F = pkg.Frame(ctx, kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+    O = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+    return F, O
+
+
+def test_features_in_area(pkg):
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    kps, desc, uR, grid = cases.frame_case(1500, 1241, 376, 5)
+    F, O = _frames(pkg, ctx, kps, desc, grid)
+    rng = np.random.default_rng(6)
+    for _ in range(60):
+        x, y = rng.uniform(-40, 1280), rng.uniform(-40, 420)
+        r = float(rng.choice([4.0, 10.0, 15.0, 37.5, 120.0]))
+        lo, hi = [(-1, -1), (0, 0), (2, 3), (1, -1), (0, 4)][int(rng.integers(0, 5))]
+        assert F.GetFeaturesInArea(x, y, r, lo, hi).tolist() == O.features_in_area(x, y, r, lo, hi).tolist()
+
+
+@pytest.mark.parametrize("n,nq,w,h,seed,th,ratio", [(2000, 3000, 1241, 376, 11, 1.0, 0.8), (2000, 3000, 1241, 376, 12, 3.0, 0.8),
+                                                     (500, 700, 620, 188, 13, 1.0, 0.8), (300, 2500, 200, 150, 14, 4.0, 0.9)])
+def test_search_by_projection(pkg, n, nq, w, h, seed, th, ratio):
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    kps, desc, uR, grid = cases.frame_case(n, w, h, seed, stereo_frac=0.4)
+    F, O = _frames(pkg, ctx, kps, desc, grid, uR)
+    q = cases.projection_queries(kps, desc, uR, w, h, nq, seed + 1)
+    blocked = (np.random.default_rng(seed).random(n) < 0.1).astype(np.uint8)
+    m = pkg.ORBmatcher(ctx, ratio)
+    nm, bi, bd, qk = m.SearchByProjection(F, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"], q["desc"], q["obs_pos"], blocked, th)
+    nm0, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
+                                                     q["desc"], q["obs_pos"], blocked, th, ratio)
+    assert nm == nm0 and nm > 0
+    assert np.array_equal(bi, bi0)
+    assert np.array_equal(bd[bi >= 0], bd0[bi0 >= 0])
+    assert np.array_equal(qk, qk0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_search_by_projection_frame(pkg, mode):
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    w, h = 1241, 376
+    kps, desc, uR, grid = cases.frame_case(2000, w, h, 31, stereo_frac=0.4)
+    F, O = _frames(pkg, ctx, kps, desc, grid, uR)
+    q = cases.projection_queries(kps, desc, uR, w, h, 2000, 32)
+    for th in (7.0, 15.0, 30.0):
+        nm, qk = pkg.ORBmatcher(ctx, 0.9, True).SearchByProjectionFrame(F, q["valid"], q["u"], q["v"], q["invz"], q["level"], q["angle"],
+                                                                        q["desc"], q["obs_pos"], None, th, 40.0, mode)
+        nm0, qk0 = oracle.search_by_projection_frame(O, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["invz"], q["level"], q["angle"],
+                                                     q["desc"], q["obs_pos"], None, th, 40.0, mode, True)
+        assert nm == nm0 and np.array_equal(qk, qk0), (mode, th)
+
+
+@pytest.mark.parametrize("window,ratio,flips", [(10, 0.99, 25), (15, 0.99, 25), (20, 0.99, 25), (20, 0.7, 8)])
+def test_birdview_match(pkg, window, ratio, flips):
+    ctx = pkg.Context(2000, 1.2, 8, 15, 5, 64, 64)
+    (k1, d1), (k2, d2), grid = cases.bird_pair(2000, 400, 41 + window, max_flips=flips)
+    F2, O2 = _frames(pkg, ctx, k2, d2, grid)
+    m = pkg.ORBmatcher(ctx, ratio, True)
+    nm, m12, _ = m.BirdviewMatch(k1, d1, F2, window)
+    nm0, m120, _ = oracle.birdview_match(k1, d1, O2, None, window, ratio, True)
+    assert nm == nm0 and nm > 0 and np.array_equal(m12, m120)
+    prev = np.stack([k1["x"] + 2, k1["y"] - 1], 1)
+    nm, m12, p1 = m.BirdviewMatch(k1, d1, F2, window, prev)
+    nm0, m120, p0 = oracle.birdview_match(k1, d1, O2, prev, window, ratio, True)
+    assert nm == nm0 and np.array_equal(m12, m120) and np.array_equal(p1, p0)
+
+
+def test_bird_kf_and_projection_bird(pkg):
+    ctx = pkg.Context(2000, 1.2, 8, 15, 5, 64, 64)
+    (k1, d1), (k2, d2), grid = cases.bird_pair(1500, 400, 51)
+    F2, O2 = _frames(pkg, ctx, k2, d2, grid)
+    has = (np.random.default_rng(52).random(len(k1)) < 0.6).astype(np.uint8)
+    m = pkg.ORBmatcher(ctx, 0.99, True)
+    for r in (15.0, 20.0):
+        nm, out = m.SearchByMatchBird(k1, has, d1, F2, r)
+        nm0, out0 = oracle.search_by_match_bird_kf(k1, has, d1, O2, r, 0.99, True)
+        assert nm == nm0 and np.array_equal(out, out0)
+    obs = (np.random.default_rng(53).random(len(k1)) < 0.8).astype(np.uint8)
+    blocked = (np.random.default_rng(54).random(len(k2)) < 0.1).astype(np.uint8)
+    nm, out = m.SearchByProjectionBird(F2, has, k1["x"] + 3, k1["y"] - 2, d1, obs, blocked, 4.0)
+    nm0, out0 = oracle.search_by_projection_bird(O2, has, k1["x"] + 3, k1["y"] - 2, d1, obs, blocked, 4.0, 0.99)
+    assert nm == nm0 and nm > 0 and np.array_equal(out, out0)
+
+
+@pytest.mark.parametrize("only_stereo", [False, True])
+def test_search_for_triangulation(pkg, only_stereo):
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+    t = cases.triangulation_case(2000, 2000, 1241, 376, 61, n_nodes=100)
+    m = pkg.ORBmatcher(ctx, 0.6, True)
+    n, pairs = m.SearchForTriangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], t["fv1"], t["fv2"],
+                                        t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"], only_stereo)
+    n0, pairs0 = oracle.search_for_triangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], t["fv1"], t["fv2"],
+                                                 t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"], only_stereo, True)
+    assert n == n0 and np.array_equal(pairs, pairs0)
+
+
+def test_matchers_vs_committed_golden(pkg):
+    """The Python-transcription golden vectors, through the CUDA path."""
+    g = np.load(os.path.join(GOLDEN, "matcher.npz"))
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    w, h = 620, 188
+    kps, desc, uR, grid = cases.frame_case(500, w, h, 11, stereo_frac=0.4)
+    F = pkg.Frame(ctx, kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+    q = cases.projection_queries(kps, desc, uR, w, h, 700, 12)
+    blocked = (np.random.default_rng(13).random(len(kps)) < 0.1).astype(np.uint8)
+    for th in (1.0, 3.0):
+        nm, bi, bd, qk = pkg.ORBmatcher(ctx, 0.8).SearchByProjection(F, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
+                                                                     q["desc"], q["obs_pos"], blocked, th)
+        want = g[f"sbp_th{int(th)}"]
+        assert nm == want[0] and np.array_equal(qk, want[1:])
+    (k1, d1), (k2, d2), gr = cases.bird_pair(400, 200, 21)
+    F2 = pkg.Frame(ctx, k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+    nm, m12, _ = pkg.ORBmatcher(ctx, 0.99, True).BirdviewMatch(k1, d1, F2, 10)
+    assert nm == g["bird_a"][0] and np.array_equal(m12, g["bird_a"][1:])
+
+
+def test_stereo_step_device_matches_host_calls(pkg):
+    """The batched device path used by bench.py == per-call host API == oracle."""
+    bench = pytest.importorskip("bench")
+    res = bench.parity_check(n_frames=3, nq=600, w=1241, h=376, nfeatures=2000)
+    assert res["ok"], res
