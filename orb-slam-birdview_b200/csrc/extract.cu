@@ -211,6 +211,10 @@ __global__ void __launch_bounds__(FT_THREADS) fast_cells_kernel(Geom g, const ui
         const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * L.pitch + 4 * k);
         tile[r][1 + 2 * k] = __byte_perm(v, 0, 0x4140);
         tile[r][2 + 2 * k] = __byte_perm(v, 0, 0x4342);
+        // words next to the loaded span are read by masked lanes only, but must hold byte-range values:
+        // a lane above 255 would borrow into its neighbour lane in the packed subtraction
+        if (k == 0) tile[r][0] = 0;
+        if (k == nw - 1) { tile[r][2 * nw + 1] = 0; tile[r][2 * nw + 2] = 0; }
     }
     __syncthreads();
 
