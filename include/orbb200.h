@@ -177,6 +177,26 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
                                int32_t* d_out_best_idx /*[n_frames][nq]*/, int32_t* d_out_best_dist,
                                int32_t* d_nmatches /*[n_frames]*/);
 
+/* Same step with HOST buffers (the end-to-end path): copies the 2*n_frames images (contiguous, rows of
+ * `stride` bytes) and the query arrays to the device, runs the step, and copies keypoints, descriptors,
+ * counts and match results back.  Asynchronous on the context's stream: outputs are valid after
+ * orbb200_sync().  Pinned host memory makes the copies overlap with other contexts' work. */
+int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_frames, int w, int h, size_t stride,
+                             const orbb200_proj_queries* h_queries, int nq_per_frame,
+                             float th, float nnratio, float min_x, float min_y, float inv_w, float inv_h,
+                             orbb200_kp_t* h_kps /*[2n][cap]*/, uint8_t* h_desc /*[2n][cap][32]*/, int cap_per_img,
+                             int32_t* h_counts /*[2n]*/, int32_t* h_best_idx /*[n][nq]*/, int32_t* h_best_dist,
+                             int32_t* h_nmatches /*[n]*/);
+
+/* Per-stage device timing (bench): CUDA events on the context's stream around each stage.
+ * stages: 0 import, 1 pyramid, 2 FAST, 3 blur, 4 octree, 5 orientation+descriptors, 6 grid build, 7 windowed match */
+#define ORBB200_NUM_STAGES 8
+int orbb200_stage_timing(orbb200_ctx* ctx, int enable);
+/* Synchronises, then returns accumulated milliseconds and launch-group counts per stage; reset!=0 clears. */
+int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[8]*/, int32_t* groups /*[8]*/, int reset);
+/* Measured POPC issue rate of this device in G popc/s (denominator of the matching roofline). */
+double orbb200_measure_popc_peak(orbb200_ctx* ctx);
+
 /* Number of kernel launches this context has enqueued since creation (bench bookkeeping). */
 long long orbb200_launch_count(const orbb200_ctx* ctx);
 

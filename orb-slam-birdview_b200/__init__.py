@@ -73,6 +73,9 @@ _SIGNATURES = {
     "orbb200_search_for_triangulation": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i,
                                               _vp, _f, _f, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "orbb200_stage_timing": (_i, [_vp, _i]),
+    "orbb200_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orbb200_launch_count": (C.c_longlong, [_vp]),
 }
 

@@ -188,13 +188,46 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     return &res.first->second;
 }
 
+StageTimer::StageTimer(Ctx& c_, int stage) : c(c_), on(c_.timing)
+{
+    if (!on) return;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!c.freeEvents.empty()) { e = c.freeEvents.back(); c.freeEvents.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    p.stage = stage; p.e0 = get(); p.e1 = get();
+    cudaEventRecord(p.e0, c.stream);
+}
+
+StageTimer::~StageTimer()
+{
+    if (!on) return;
+    cudaEventRecord(p.e1, c.stream);
+    c.pending.push_back(p);
+    if (c.pending.size() >= 2048) drain_stage_events(c);
+}
+
+void drain_stage_events(Ctx& c)
+{
+    if (c.pending.empty()) return;
+    cudaStreamSynchronize(c.stream);
+    for (auto& p : c.pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { c.stageMs[p.stage] += ms; c.stageGroups[p.stage]++; }
+        c.freeEvents.push_back(p.e0); c.freeEvents.push_back(p.e1);
+    }
+    c.pending.clear();
+}
+
 static int run_extract(Ctx& c, int n)
 {
-    launch_pyramid(c, n);
-    launch_fast(c, n);
-    launch_blur(c, n);
-    launch_octree(c, n);
-    launch_describe(c, n);
+    { StageTimer t(c, 1); launch_pyramid(c, n); }
+    { StageTimer t(c, 2); launch_fast(c, n); }
+    { StageTimer t(c, 3); launch_blur(c, n); }
+    { StageTimer t(c, 4); launch_octree(c, n); }
+    { StageTimer t(c, 5); launch_describe(c, n); }
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;
 }
@@ -213,6 +246,15 @@ static int check_status(Ctx& c)
 }
 
 }  // namespace orbb200
+
+namespace {
+struct Arena {
+    uint8_t* base;
+    size_t cap, off = 0;
+    Arena(uint8_t* b, size_t c) : base(b), cap(c) {}
+    template <class T> T* take(size_t n) { off = align_up(off, 256); T* p = reinterpret_cast<T*>(base + off); off += n * sizeof(T); return p; }
+};
+}  // namespace
 
 #define CTX_ENTER(ctx)                                             \
     if (!(ctx)) return ORBB200_ERR_ARG;                            \
@@ -299,7 +341,10 @@ void orbb200_destroy(orbb200_ctx* ctx)
     Ctx& c = ctx->c;
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
-    void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch};
+    drain_stage_events(c);
+    for (cudaEvent_t e : c.freeEvents) cudaEventDestroy(e);
+    for (auto& p : c.plans) cudaFree(p.block);
+    void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
@@ -347,7 +392,7 @@ int orbb200_extract_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_b
     const ShapeTables* st = get_shape(c, w, h);
     if (!st) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
     c.cur = st; c.curN = n;
-    launch_import(c, d_imgs, img_bytes, stride, n);
+    { StageTimer t(c, 0); launch_import(c, d_imgs, img_bytes, stride, n); }
     return run_extract(c, n);
 }
 
@@ -626,13 +671,6 @@ int orbb200_frame_features_in_area(orbb200_ctx* ctx, const orbb200_frame* f, flo
 // ---- windowed searches: host wrappers ------------------------------------------------------------------
 namespace {
 
-struct Arena {
-    uint8_t* base;
-    size_t cap, off = 0;
-    Arena(uint8_t* b, size_t c) : base(b), cap(c) {}
-    template <class T> T* take(size_t n) { off = align_up(off, 256); T* p = reinterpret_cast<T*>(base + off); off += n * sizeof(T); return p; }
-};
-
 struct QueryHost {
     int nq = 0;
     const uint8_t* valid = nullptr; const float* x = nullptr; const float* y = nullptr; const float* aux = nullptr;
@@ -846,47 +884,133 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
     int rc = orbb200_extract_device(ctx, d_imgs, img_bytes, 2 * n_frames, w, h, stride);
     if (rc != ORBB200_OK) return rc;
     const int kpi = c.cur->g.kpPerImg, nq = nq_per_frame;
-    // workspace in the scratch arena: frames, grids, jobs, per-job scratch, per-kp outputs
-    const size_t perFrame = align_up(sizeof(FrameDev), 256) + align_up(4 * (size_t)(GRID_CELLS + 1), 256) + align_up(4 * (size_t)kpi, 256) * 2 +
-                            align_up(sizeof(WinJob), 256) + align_up(4 * win_scratch_ints(kpi, nq), 256);
-    const size_t hostNeed = (size_t)n_frames * (sizeof(FrameDev) + sizeof(WinJob)) + 1024;
-    if (!ensure_scratch(c, perFrame * n_frames + 8192, hostNeed)) return ORBB200_ERR_CUDA;
-    Arena A(c.d_scratch, c.d_scratch_bytes);
-    FrameDev* dF = A.take<FrameDev>(n_frames);
-    WinJob* dJ = A.take<WinJob>(n_frames);
-    float* dsf = A.take<float>(MAX_LEVELS);
-    FrameDev* hF = reinterpret_cast<FrameDev*>(c.h_scratch);
-    WinJob* hJ = reinterpret_cast<WinJob*>(c.h_scratch + align_up(sizeof(FrameDev) * n_frames, 256));
-    float* hsf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(hJ) + align_up(sizeof(WinJob) * n_frames, 256));
-    // the pinned staging is reused every call: wait until the previous upload has been consumed
-    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
-    for (int l = 0; l < c.nlevels; l++) hsf[l] = c.scale[l];
-    for (int i = 0; i < n_frames; i++) {
-        FrameDev& f = hF[i];
-        const int img = 2 * i;
-        f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32; f.uRight = nullptr;
-        f.n_ptr = c.d_counts + img; f.n = kpi;
-        f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi);
-        f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
-        WinJob& J = hJ[i];
-        memset(&J, 0, sizeof(J));
-        J.frame = dF + i; J.nq = nq; J.mode = WM_PROJ; J.kpCap = kpi; J.th = th; J.nnratio = nnratio; J.scaleFactors = dsf;
-        const size_t o = (size_t)i * nq;
-        J.q_valid = d_queries->q_valid ? d_queries->q_valid + o : nullptr;
-        J.q_x = d_queries->q_u + o; J.q_y = d_queries->q_v + o; J.q_aux = d_queries->q_uR + o; J.q_level = d_queries->q_level + o;
-        J.q_viewcos = d_queries->q_viewcos + o; J.q_desc = d_queries->q_desc + o * 32;
-        J.q_obs_pos = d_queries->q_obs_pos ? d_queries->q_obs_pos + o : nullptr;
-        J.scratch = A.take<int>(win_scratch_ints(kpi, nq));
-        J.out_best_idx = d_out_best_idx + o; J.out_best_dist = d_out_best_dist + o;
-        J.out_per_kp = A.take<int32_t>(kpi);
-        J.out_nmatches = d_nmatches + i;
+    // The frame/job descriptors only hold pointers and parameters: build them once per distinct argument
+    // set and keep them on the device, so that the steady-state step never synchronises with the host.
+    StepPlan key{};
+    key.q = *d_queries; key.nq = nq; key.n_frames = n_frames; key.kpi = kpi; key.th = th; key.nnratio = nnratio;
+    key.minX = min_x; key.minY = min_y; key.invW = inv_w; key.invH = inv_h;
+    key.o0 = d_out_best_idx; key.o1 = d_out_best_dist; key.o2 = d_nmatches;
+    StepPlan* plan = nullptr;
+    for (auto& p : c.plans)
+        if (memcmp(&p, &key, offsetof(StepPlan, dF)) == 0) { plan = &p; break; }
+    if (!plan) {
+        if (c.plans.size() >= 16) {   // bounded cache: drop everything (rare: callers reuse a few buffer sets)
+            cudaStreamSynchronize(c.stream);
+            for (auto& p : c.plans) cudaFree(p.block);
+            c.plans.clear();
+        }
+        const size_t perFrame = align_up(4 * (size_t)(GRID_CELLS + 1), 256) + align_up(4 * (size_t)kpi, 256) * 2 +
+                                align_up(4 * win_scratch_ints(kpi, nq), 256);
+        const size_t bytes = align_up(sizeof(FrameDev) * n_frames, 256) + align_up(sizeof(WinJob) * n_frames, 256) + 256 + perFrame * n_frames + 4096;
+        ORBB200_CUDA_OK(c, cudaMalloc(&key.block, bytes));
+        Arena A((uint8_t*)key.block, bytes);
+        key.dF = A.take<FrameDev>(n_frames);
+        key.dJ = A.take<WinJob>(n_frames);
+        float* dsf = A.take<float>(MAX_LEVELS);
+        std::vector<FrameDev> hF(n_frames);
+        std::vector<WinJob> hJ(n_frames);
+        for (int i = 0; i < n_frames; i++) {
+            FrameDev& f = hF[i];
+            const int img = 2 * i;
+            f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32; f.uRight = nullptr;
+            f.n_ptr = c.d_counts + img; f.n = kpi;
+            f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi);
+            f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
+            WinJob& J = hJ[i];
+            memset(&J, 0, sizeof(J));
+            J.frame = key.dF + i; J.nq = nq; J.mode = WM_PROJ; J.kpCap = kpi; J.th = th; J.nnratio = nnratio; J.scaleFactors = dsf;
+            const size_t o = (size_t)i * nq;
+            J.q_valid = d_queries->q_valid ? d_queries->q_valid + o : nullptr;
+            J.q_x = d_queries->q_u + o; J.q_y = d_queries->q_v + o; J.q_aux = d_queries->q_uR + o; J.q_level = d_queries->q_level + o;
+            J.q_viewcos = d_queries->q_viewcos + o; J.q_desc = d_queries->q_desc + o * 32;
+            J.q_obs_pos = d_queries->q_obs_pos ? d_queries->q_obs_pos + o : nullptr;
+            J.scratch = A.take<int>(win_scratch_ints(kpi, nq));
+            J.out_best_idx = d_out_best_idx + o; J.out_best_dist = d_out_best_dist + o;
+            J.out_per_kp = A.take<int32_t>(kpi);
+            J.out_nmatches = d_nmatches + i;
+        }
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(key.dF, hF.data(), sizeof(FrameDev) * n_frames, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(key.dJ, hJ.data(), sizeof(WinJob) * n_frames, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));   // one-time: host vectors go out of scope
+        c.plans.push_back(key);
+        plan = &c.plans.back();
     }
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dF, hF, sizeof(FrameDev) * n_frames, cudaMemcpyHostToDevice, c.stream));
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, hJ, sizeof(WinJob) * n_frames, cudaMemcpyHostToDevice, c.stream));
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dsf, hsf, sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream));
-    launch_grid_build(c, dF, n_frames);
-    launch_window_match(c, dJ, n_frames);
+    FrameDev* dF = plan->dF;
+    WinJob* dJ = plan->dJ;
+    { StageTimer t(c, 6); launch_grid_build(c, dF, n_frames); }
+    { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames); }
     ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_frames, int w, int h, size_t stride,
+                             const orbb200_proj_queries* hq, int nq,
+                             float th, float nnratio, float min_x, float min_y, float inv_w, float inv_h,
+                             orbb200_kp_t* h_kps, uint8_t* h_desc, int cap_per_img,
+                             int32_t* h_counts, int32_t* h_best_idx, int32_t* h_best_dist, int32_t* h_nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!h_imgs || n_frames <= 0 || 2 * n_frames > c.maxBatch || !hq || nq < 0 || !h_kps || !h_desc || !h_counts || !h_best_idx || !h_best_dist ||
+        !h_nmatches || stride < (size_t)w) { c.err = "stereo_step_host: bad argument"; return ORBB200_ERR_ARG; }
+    const int ni = 2 * n_frames;
+    const size_t imgBytes = (size_t)h * stride, Q = (size_t)n_frames * nq;
+    const size_t need = align_up(imgBytes * ni, 256) + align_up(Q, 256) * 2 + align_up(Q * 4, 256) * 7 + align_up(Q * 32, 256) + align_up(4 * (size_t)n_frames, 256) + 4096;
+    if (need > c.d_step_bytes) {
+        cudaStreamSynchronize(c.stream);
+        if (c.d_step) cudaFree(c.d_step);
+        c.d_step = nullptr; c.d_step_bytes = 0;
+        ORBB200_CUDA_OK(c, cudaMalloc(&c.d_step, need));
+        c.d_step_bytes = need;
+    }
+    Arena A(c.d_step, c.d_step_bytes);
+    uint8_t* dImgs = A.take<uint8_t>(imgBytes * ni);
+    orbb200_proj_queries dq{};
+    auto up = [&](const void* src, size_t bytes) -> void* {
+        if (!src) return nullptr;
+        uint8_t* d = A.take<uint8_t>(bytes);
+        cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c.stream);
+        return d;
+    };
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dImgs, h_imgs, imgBytes * ni, cudaMemcpyHostToDevice, c.stream));
+    dq.q_valid = (const uint8_t*)up(hq->q_valid, Q); dq.q_u = (const float*)up(hq->q_u, Q * 4); dq.q_v = (const float*)up(hq->q_v, Q * 4);
+    dq.q_uR = (const float*)up(hq->q_uR, Q * 4); dq.q_level = (const int32_t*)up(hq->q_level, Q * 4);
+    dq.q_viewcos = (const float*)up(hq->q_viewcos, Q * 4); dq.q_desc = (const uint8_t*)up(hq->q_desc, Q * 32);
+    dq.q_obs_pos = (const uint8_t*)up(hq->q_obs_pos, Q);
+    if (!dq.q_u || !dq.q_v || !dq.q_uR || !dq.q_level || !dq.q_viewcos || !dq.q_desc) { c.err = "stereo_step_host: missing query array"; return ORBB200_ERR_ARG; }
+    int32_t* dBi = A.take<int32_t>(Q);
+    int32_t* dBd = A.take<int32_t>(Q);
+    int32_t* dNm = A.take<int32_t>(n_frames);
+    int rc = orbb200_stereo_step_device(ctx, dImgs, imgBytes, n_frames, w, h, stride, &dq, nq, th, nnratio, min_x, min_y, inv_w, inv_h, dBi, dBd, dNm);
+    if (rc != ORBB200_OK) return rc;
+    const int kpi = c.cur->g.kpPerImg, take = std::min(cap_per_img, kpi);
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(h_kps, (size_t)cap_per_img * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t),
+                                         (size_t)take * sizeof(orbb200_kp_t), ni, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(h_desc, (size_t)cap_per_img * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, ni, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_counts, c.d_counts, 4 * (size_t)ni, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_best_idx, dBi, 4 * Q, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_best_dist, dBd, 4 * Q, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_nmatches, dNm, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, c.stream));
+    return ORBB200_OK;
+}
+
+int orbb200_stage_timing(orbb200_ctx* ctx, int enable)
+{
+    CTX_ENTER(ctx);
+    drain_stage_events(c);
+    c.timing = enable != 0;
+    return ORBB200_OK;
+}
+
+int orbb200_stage_times(orbb200_ctx* ctx, float* ms, int32_t* groups, int reset)
+{
+    CTX_ENTER(ctx);
+    drain_stage_events(c);
+    for (int i = 0; i < 8; i++) {
+        if (ms) ms[i] = c.stageMs[i];
+        if (groups) groups[i] = c.stageGroups[i];
+        if (reset) { c.stageMs[i] = 0; c.stageGroups[i] = 0; }
+    }
     return ORBB200_OK;
 }
 

@@ -14,6 +14,20 @@ struct ShapeTables {
     int4* d_cells = nullptr;    // FAST cells of all levels: {x0|y0<<16, x1|y1<<16, level, order index}
 };
 
+struct WinJob;
+
+// Cached device-side descriptors of one batched step (orbb200_stereo_step_device); the leading fields are
+// the cache key.
+struct StepPlan {
+    orbb200_proj_queries q;
+    int nq, n_frames, kpi;
+    float th, nnratio, minX, minY, invW, invH;
+    void *o0, *o1, *o2;
+    FrameDev* dF;       // <- offsetof(StepPlan, dF) ends the key
+    WinJob* dJ;
+    void* block;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -53,7 +67,29 @@ struct Ctx {
     size_t d_scratch_bytes = 0;
     uint8_t* h_scratch = nullptr;            // pinned generic
     size_t h_scratch_bytes = 0;
+    uint8_t* d_step = nullptr;               // device staging of the host step (images, queries, results)
+    size_t d_step_bytes = 0;
+
+    std::vector<StepPlan> plans;
+
+    // per-stage timing (bench)
+    bool timing = false;
+    struct Pending { int stage; cudaEvent_t e0, e1; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> freeEvents;
+    float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int stageGroups[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+// RAII: events around one stage when timing is on
+struct StageTimer {
+    Ctx& c;
+    Ctx::Pending p{};
+    bool on;
+    StageTimer(Ctx& c_, int stage);
+    ~StageTimer();
+};
+void drain_stage_events(Ctx& c);
 
 bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes);
 const ShapeTables* get_shape(Ctx& c, int w, int h);   // nullptr + c.err on failure

@@ -68,3 +68,29 @@ def perturb_descriptors(desc, max_flips, seed):
             pos = rng.choice(256, size=int(k), replace=False)
             bits[i, pos] ^= 1
     return np.packbits(bits, axis=1)
+
+
+def projection_queries(kps, desc, w, h, nq, seed, levels=8, on_kp_frac=0.7, max_flips=40, jitter=3.0):
+    """Local-map style queries for SearchByProjection: 70 % sit on a
+    (jittered) frame keypoint with that keypoint's descriptor under 0..40 random bit flips, 30 % are uniform
+    random positions with random descriptors; level from the keypoint octaves; viewCos in {0.999, 0.9}."""
+    rng = np.random.default_rng(int(seed))
+    n = len(kps)
+    src = rng.integers(0, max(n, 1), nq)
+    on = (rng.random(nq) < on_kp_frac) & (n > 0)
+    kx = kps["x"][src] if n else np.zeros(nq, np.float32)
+    ky = kps["y"][src] if n else np.zeros(nq, np.float32)
+    ko = kps["octave"][src] if n else np.zeros(nq, np.int32)
+    u = np.where(on, kx + rng.uniform(-jitter, jitter, nq), rng.uniform(0, w, nq)).astype(np.float32)
+    v = np.where(on, ky + rng.uniform(-jitter, jitter, nq), rng.uniform(0, h, nq)).astype(np.float32)
+    lvl = np.where(on, np.clip(ko + rng.integers(0, 2, nq), 0, levels - 1), rng.integers(0, levels, nq)).astype(np.int32)
+    base = desc[src] if n else np.zeros((nq, 32), np.uint8)
+    # bit flips: XOR with a random mask of up to max_flips set bits (vectorised)
+    nflip = rng.integers(0, max_flips + 1, nq)
+    bits = (rng.random((nq, 256)).argsort(1) < nflip[:, None]).astype(np.uint8)
+    qd = base ^ np.packbits(bits, axis=1)
+    rnd = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    qd = np.where(on[:, None], qd, rnd).astype(np.uint8)
+    viewcos = np.where(rng.random(nq) < 0.5, 0.999, 0.9).astype(np.float32)
+    return dict(valid=np.ones(nq, np.uint8), u=u, v=v, uR=np.full(nq, -1, np.float32), level=lvl, viewcos=viewcos,
+                desc=np.ascontiguousarray(qd), obs_pos=np.ones(nq, np.uint8))

@@ -69,3 +69,16 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "liborb_oracle" not in txt and "orb_oracle.h" not in txt, os.path.join(dirpath, f)
+
+
+def test_cpp_shim_compiles(pkg):
+    """cpp/ORBextractor.h keeps the reference class interface and links against the C ABI."""
+    import subprocess
+    d = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp")
+    subprocess.run(["make", "-s", "-C", d], check=True)
+    assert os.path.exists(os.path.join(d, "shim_driver"))
+    hdr = open(os.path.join(d, "ORBextractor.h")).read()
+    for sig in ("ORBextractor(int nfeatures_, float scaleFactor_, int nlevels_, int iniThFAST_, int minThFAST_)",
+                "void operator()( cv::InputArray _image, cv::InputArray /*_mask*/,", "std::vector<cv::Mat> mvImagePyramid;",
+                "GetScaleFactors()", "GetInverseScaleSigmaSquares()"):
+        assert sig in hdr, sig

@@ -288,3 +288,27 @@ def test_stereo_step_device_matches_host_calls(pkg):
     bench = pytest.importorskip("bench")
     res = bench.parity_check(n_frames=3, nq=600, w=1241, h=376, nfeatures=2000)
     assert res["ok"], res
+
+
+def test_cpp_shim(pkg, tmp_path):
+    """The C++ ORB_SLAM2::ORBextractor shim (cpp/ORBextractor.h) called like Frame::ExtractORB == oracle."""
+    import subprocess
+    from helpers import ROOT
+    drv = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp", "shim_driver")
+    if not os.path.exists(drv):
+        subprocess.run(["make", "-s", "-C", os.path.dirname(drv)], check=True)
+    img = synth.synth_frame(480, 752, 1000)
+    raw, out = tmp_path / "in.raw", tmp_path / "out.bin"
+    img.tofile(raw)
+    subprocess.run([drv, str(raw), "752", "480", "1000", "20", "7", str(out)], check=True, timeout=120)
+    buf = open(out, "rb").read()
+    n = int(np.frombuffer(buf, np.int32, 1)[0])
+    k = np.frombuffer(buf, pkg.KP_DTYPE, n, 4)
+    d = np.frombuffer(buf, np.uint8, n * 32, 4 + 28 * n).reshape(n, 32)
+    orc = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    k0, d0 = orc(img)
+    _compare_extract(k, d, k0, d0, "cpp shim")
+    off = 4 + 60 * n
+    pw, ph = np.frombuffer(buf, np.int32, 2, off)
+    lvl1 = np.frombuffer(buf, np.uint8, pw * ph, off + 8).reshape(ph, pw)
+    assert np.array_equal(lvl1, orc.level_image(1))          # mvImagePyramid[1]
