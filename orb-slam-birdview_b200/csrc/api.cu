@@ -170,9 +170,28 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                 if (iniX >= L.maxBX - 6) continue;
                 if (maxX > L.maxBX) maxX = (float)L.maxBX;
                 cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
+                {   // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
+                    const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3, tw = x1 - xa;
+                    const int wi = x1 - x0 - 6, hi = th - 6;
+                    if (wi > 0 && hi > 0) {
+                        const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1, nw = (tw + 3) >> 2;
+                        int P = npr;
+                        while (P < 2 * nw + 3) P += 32;
+                        st.fastTileWords = std::max(st.fastTileWords, th * P);
+                        st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
+                        st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
+                    }
+                }
             }
         }
     }
+    std::vector<int4> btiles;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        for (int y0 = 0; y0 < L.h; y0 += 32)
+            for (int x0 = 0; x0 < L.w; x0 += 128) btiles.push_back(make_int4(l, x0, y0, 0));
+    }
+    st.nBlurTiles = (int)btiles.size();
     auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {
         if (bytes == 0) bytes = 16;
         if (cudaMalloc(dptr, bytes) != cudaSuccess) return false;
@@ -181,7 +200,8 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     };
     bool ok = up((void**)&st.d_xtab, xtab.data(), xtab.size() * sizeof(int2)) &&
               up((void**)&st.d_ytab, ytab.data(), ytab.size() * sizeof(int4)) &&
-              up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4));
+              up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4)) &&
+              up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4));
     cudaStreamSynchronize(c.stream);   // host vectors go out of scope
     if (!ok) { c.err = "cudaMalloc(shape tables) failed"; return nullptr; }
     auto res = c.shapes.emplace(std::make_pair(w, h), st);
@@ -346,7 +366,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (auto& p : c.plans) cudaFree(p.block);
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); }
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.h_stage) cudaFreeHost(c.h_stage);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -715,7 +735,7 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     J.out_nmatches = A.take<int32_t>(1);
     WinJob* dJ = A.take<WinJob>(1);
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, &J, sizeof(J), cudaMemcpyHostToDevice, c.stream));
-    launch_window_match(c, dJ, 1);
+    launch_window_match(c, dJ, 1, nq);
     ORBB200_CUDA_OK(c, cudaGetLastError());
     if (h_best_idx) cudaMemcpyAsync(h_best_idx, J.out_best_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
     if (h_best_dist) cudaMemcpyAsync(h_best_dist, J.out_best_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
@@ -939,7 +959,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
     FrameDev* dF = plan->dF;
     WinJob* dJ = plan->dJ;
     { StageTimer t(c, 6); launch_grid_build(c, dF, n_frames); }
-    { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames); }
+    { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames, nq); }
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;
 }

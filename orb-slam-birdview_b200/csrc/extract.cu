@@ -66,67 +66,88 @@ __global__ void __launch_bounds__(256) resize_kernel(uint8_t* __restrict__ pyr, 
 // Q8.8 kernel {18,34,48,56,48,34,18}; H in u16, V in u32, (v + 2^15) >> 16.
 // One launch covers all levels: blockIdx.y indexes a flattened (level, tile-row) table.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BL_TW = 128, BL_TH = 16;
+// Streaming form: one warp owns a 128-column x BL_ROWS-row tile; each lane owns 4 adjacent columns (one output
+// word), walks down the rows, keeps the horizontal sums of the last 7 rows in a register ring and emits one
+// output word per row.  No shared memory, one launch for all levels (tiles come from a flattened table).
+constexpr int BL_ROWS = 32;      // output rows per warp tile (6 extra rows of horizontal work per tile)
+constexpr int BL_WARPS = 4;
 
 __device__ __forceinline__ int reflect101(int p, int len)
 {
     if (p < 0) p = -p;
     if (p >= len) p = 2 * (len - 1) - p;
-    return p;
+    return min(max(p, 0), len - 1);    // second clamp only matters for levels narrower than the kernel
 }
 
-__global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned pyrBytes,
-                                                   Geom g, int level)
+// horizontal 7-tap sums of the 4 pixels starting at byte 4 of the 12-byte window (w0,w1,w2)
+__device__ __forceinline__ void blur_hrow(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&h)[4])
 {
-    __shared__ __align__(16) uint8_t sIn[BL_TH + 6][BL_TW + 8];
-    __shared__ __align__(16) uint16_t sH[BL_TH + 6][BL_TW];
-    const LevelGeom L = g.lv[level];
-    const int img = blockIdx.z;
-    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
-    if (x0 >= L.w || y0 >= L.h) return;
+    // packed pixel pairs (u16x2) starting at window bytes 1..9: pair s = (b[s], b[s+1])
+    const uint32_t v = __funnelshift_r(w0, w1, 24);    // b3,b4,b5,b6
+    const uint32_t u = __funnelshift_r(w1, w2, 24);    // b7,b8,b9,b10
+    const uint32_t p1 = __byte_perm(w0, 0, 0x4241);    // b1,b2
+    const uint32_t p2 = __byte_perm(w0, 0, 0x4342);    // b2,b3
+    const uint32_t p3 = __byte_perm(v, 0, 0x4140);     // b3,b4
+    const uint32_t p4 = __byte_perm(w1, 0, 0x4140);    // b4,b5
+    const uint32_t p5 = __byte_perm(w1, 0, 0x4241);    // b5,b6
+    const uint32_t p6 = __byte_perm(w1, 0, 0x4342);    // b6,b7
+    const uint32_t p7 = __byte_perm(u, 0, 0x4140);     // b7,b8
+    const uint32_t p8 = __byte_perm(w2, 0, 0x4140);    // b8,b9
+    const uint32_t p9 = __byte_perm(w2, 0, 0x4241);    // b9,b10
+    // outputs (b4,b5): taps b1..b7 / b2..b8 -> pairs p1..p7 ; outputs (b6,b7): pairs p3..p9.  Lanes stay < 2^16.
+    const uint32_t ha = 18u * (p1 + p7) + 34u * (p2 + p6) + 48u * (p3 + p5) + 56u * p4;
+    const uint32_t hb = 18u * (p3 + p9) + 34u * (p4 + p8) + 48u * (p5 + p7) + 56u * p6;
+    h[0] = ha & 0xffffu; h[1] = ha >> 16; h[2] = hb & 0xffffu; h[3] = hb >> 16;
+}
+
+__global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned pyrBytes,
+                                                             Geom g, const int4* __restrict__ tiles, int nTiles)
+{
+    const int tileIdx = blockIdx.x * BL_WARPS + (threadIdx.x >> 5);
+    if (tileIdx >= nTiles) return;
+    const int lane = threadIdx.x & 31;
+    const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
+    const LevelGeom L = g.lv[t.x];
+    const int img = blockIdx.y;
+    const int x = t.y + 4 * lane, y0 = t.z;
+    if (x >= L.w) return;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + L.off;
     uint8_t* D = blur + (size_t)img * pyrBytes + L.off;
-    const int tid = threadIdx.x;
-    // load (BL_TH+6) x (BL_TW+8) bytes, columns x0-4 .. x0+BL_TW+3, as 32-bit words where fully inside
-    constexpr int WPR = (BL_TW + 8) / 4;
-    for (int i = tid; i < (BL_TH + 6) * WPR; i += 256) {
-        const int r = i / WPR, k = i - r * WPR;
-        int gy = reflect101(y0 - 3 + r, L.h);
-        gy = min(max(gy, 0), L.h - 1);   // tiles past the bottom edge (tiny levels)
-        const int gx = x0 - 4 + 4 * k;
-        const uint8_t* row = S + (size_t)gy * L.pitch;
-        uint32_t v;
-        if (gx >= 0 && gx + 3 < L.w) {
-            v = *reinterpret_cast<const uint32_t*>(row + gx);
+    const bool interior = (x - 4 >= 0) && (x + 7 < L.w);
+    const int rows = min(BL_ROWS, L.h - y0);
+
+    auto load_row = [&](int yy, uint32_t (&h)[4]) {
+        const uint8_t* row = S + (size_t)reflect101(yy, L.h) * L.pitch;
+        uint32_t w0, w1, w2;
+        if (interior) {
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(row + x);
+            w0 = r[-1]; w1 = r[0]; w2 = r[1];
         } else {
-            v = 0;
+            w0 = w1 = w2 = 0;
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                int xx = reflect101(gx + b, L.w);
-                xx = min(max(xx, 0), L.w - 1);
-                v |= (uint32_t)row[xx] << (8 * b);
+                w0 |= (uint32_t)row[reflect101(x - 4 + b, L.w)] << (8 * b);
+                w1 |= (uint32_t)row[reflect101(x + b, L.w)] << (8 * b);
+                w2 |= (uint32_t)row[reflect101(x + 4 + b, L.w)] << (8 * b);
             }
         }
-        *reinterpret_cast<uint32_t*>(&sIn[r][4 * k]) = v;
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += 256) {
-        const int r = i / BL_TW, x = i - r * BL_TW;
-        const uint8_t* p = &sIn[r][x + 1];   // column x0+x-3
-        sH[r][x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    for (int i = tid; i < BL_TH * (BL_TW / 4); i += 256) {
-        const int r = i / (BL_TW / 4), x = (i - r * (BL_TW / 4)) * 4;
-        if (y0 + r >= L.h || x0 + x >= L.w) continue;
+        blur_hrow(w0, w1, w2, h);
+    };
+
+    uint32_t h0[4], h1[4], h2[4], h3[4], h4[4], h5[4], h6[4];
+    load_row(y0 - 3, h0); load_row(y0 - 2, h1); load_row(y0 - 1, h2);
+    load_row(y0, h3); load_row(y0 + 1, h4); load_row(y0 + 2, h5);
+    for (int r = 0; r < rows; r++) {
+        load_row(y0 + r + 3, h6);
         uint32_t out = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const uint32_t s = 18u * ((uint32_t)sH[r][x + b] + sH[r + 6][x + b]) + 34u * ((uint32_t)sH[r + 1][x + b] + sH[r + 5][x + b]) +
-                               48u * ((uint32_t)sH[r + 2][x + b] + sH[r + 4][x + b]) + 56u * (uint32_t)sH[r + 3][x + b];
-            out |= ((s + 32768u) >> 16) << (8 * b);
+            const uint32_t v = 18u * (h0[b] + h6[b]) + 34u * (h1[b] + h5[b]) + 48u * (h2[b] + h4[b]) + 56u * h3[b] + 32768u;
+            out |= (v >> 16) << (8 * b);
         }
-        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * L.pitch + x0 + x) = out;
+        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * L.pitch + x) = out;
+#pragma unroll
+        for (int b = 0; b < 4; b++) { h0[b] = h1[b]; h1[b] = h2[b]; h2[b] = h3[b]; h3[b] = h4[b]; h4[b] = h5[b]; h5[b] = h6[b]; }
     }
 }
 
@@ -138,10 +159,6 @@ __global__ void __launch_bounds__(256) blur_kernel(const uint8_t* __restrict__ p
 // S >= iniThFAST, or, when the cell has none, if S >= minThFAST.
 // Candidates are appended unordered to the level's pool: the octree only needs (x, y, response).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FT_PITCH_W = 38;     // u32 words per tile row (2 pixels each): 68 px + bias, padded
-constexpr int FT_MAXH = 66;
-constexpr int FT_SCW = 80;         // score row pitch (bytes)
-constexpr int FT_MAXC = 1024;      // >= ceil(59/2)^2 local maxima per cell
 constexpr int FT_THREADS = 128;
 
 __device__ __forceinline__ uint32_t min3s(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
@@ -179,12 +196,18 @@ __device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (
     return s - 0x02000200u;
 }
 
-__global__ void __launch_bounds__(FT_THREADS) fast_cells_kernel(Geom g, const uint8_t* __restrict__ pyr, const int4* __restrict__ cells,
-                                                                uint32_t* __restrict__ cand, int32_t* __restrict__ candCount)
+__global__ void __launch_bounds__(FT_THREADS, 8) fast_cells_kernel(Geom g, const uint8_t* __restrict__ pyr, const int4* __restrict__ cells,
+                                                                   uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
+                                                                   int tileWords, int scrWords, int clistCap)
 {
-    __shared__ uint32_t tile[FT_MAXH][FT_PITCH_W];
-    __shared__ __align__(4) uint8_t scr[FT_MAXH - 4][FT_SCW];
-    __shared__ uint32_t clist[FT_MAXC];
+    // tile[r][1+m] = pixels (2m, 2m+1) of cell-image row r as u16x2; score tile in the same layout with a
+    // zero row above/below.  Row pitch == pairs-per-row (mod 32): the flattened (row, pair) -> lane mapping
+    // then walks consecutive banks across row boundaries (no bank conflicts).
+    // Shared memory is sized by the host for the largest cell of this image shape (typically ~17 KB).
+    extern __shared__ uint32_t ftSmem[];
+    uint32_t* tile = ftSmem;
+    uint32_t* scr = tile + tileWords;
+    uint32_t* clist = scr + scrWords;
     __shared__ int sN, sNini, sBase, sOut;
 
     const int img = blockIdx.y;
@@ -198,84 +221,99 @@ __global__ void __launch_bounds__(FT_THREADS) fast_cells_kernel(Geom g, const ui
     const int wi = x1 - x0 - 6, hi = th - 6;
     if (wi <= 0 || hi <= 0) return;
     const int cx0 = x0 - xa + 3, cx1 = cx0 + wi;    // inner columns in tile coordinates
+    const int m0 = cx0 >> 1, m1 = (cx1 - 1) >> 1, npr = m1 - m0 + 1;
+    const int nw = (tw + 3) >> 2;                   // 32-bit words loaded per row
+    int P = npr;
+    while (P < 2 * nw + 3) P += 32;                 // <= 63
 
     if (tid == 0) { sN = 0; sNini = 0; sOut = 0; }
-    // zero the score tile (borders must read as 0)
-    for (int i = tid; i < (hi + 2) * (FT_SCW / 4); i += FT_THREADS) reinterpret_cast<uint32_t*>(&scr[0][0])[i] = 0;
-    // load the cell image: 32-bit words, widened to u16 pairs; pixel column tc lives at u16 index tc+2
+    for (int i = tid; i < (hi + 2) * P; i += FT_THREADS) scr[i] = 0;
+    // load the cell image: 32-bit words widened to u16 pairs; pixel column tc lives in word 1 + tc/2
     const uint8_t* S = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)y0 * L.pitch + xa;
-    const int nw = (tw + 3) >> 2;
+    const uint32_t magicNw = 0xffffffffu / (uint32_t)nw + 1u;
     for (int i = tid; i < th * nw; i += FT_THREADS) {
-        const int r = __float2int_rz(__fmul_rz((float)i + 0.5f, __frcp_rn((float)nw)));
+        const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
         const int k = i - r * nw;
         const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * L.pitch + 4 * k);
-        tile[r][1 + 2 * k] = __byte_perm(v, 0, 0x4140);
-        tile[r][2 + 2 * k] = __byte_perm(v, 0, 0x4342);
+        uint32_t* t = tile + r * P;
+        t[1 + 2 * k] = __byte_perm(v, 0, 0x4140);
+        t[2 + 2 * k] = __byte_perm(v, 0, 0x4342);
         // words next to the loaded span are read by masked lanes only, but must hold byte-range values:
         // a lane above 255 would borrow into its neighbour lane in the packed subtraction
-        if (k == 0) tile[r][0] = 0;
-        if (k == nw - 1) { tile[r][2 * nw + 1] = 0; tile[r][2 * nw + 2] = 0; }
+        if (k == 0) t[0] = 0;
+        if (k == nw - 1) { t[2 * nw + 1] = 0; t[2 * nw + 2] = 0; }
     }
     __syncthreads();
 
-    // scores: pairs (2m, 2m+1) covering the inner columns
-    const int m0 = cx0 >> 1, m1 = (cx1 - 1) >> 1, npr = m1 - m0 + 1;
-    const float rnpr = __frcp_rn((float)npr);
+    // ---- scores: pairs (2m, 2m+1) covering the inner columns ----
+    const uint32_t magicNpr = 0xffffffffu / (uint32_t)npr + 1u;
     for (int i = tid; i < hi * npr; i += FT_THREADS) {
-        const int rr = __float2int_rz(__fmul_rz((float)i + 0.5f, rnpr));
+        const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
         const int m = m0 + (i - rr * npr);
-        const int tr = rr + 3;
-        const uint32_t* t = &tile[tr][m + 1];
+        const uint32_t* t = tile + (rr + 3) * P + m + 1;
         // ring order k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
         uint32_t r[16];
         {
-            const uint32_t* p = t + 3 * FT_PITCH_W;                 // dy = +3 : dx -1,0,1
+            const uint32_t* p = t + 3 * P;                          // dy = +3 : dx -1,0,1
             const uint32_t wl = p[-1], wc = p[0], wr = p[1];
             r[15] = __funnelshift_r(wl, wc, 16); r[0] = wc; r[1] = __funnelshift_r(wc, wr, 16);
         }
         {
-            const uint32_t* p = t - 3 * FT_PITCH_W;                 // dy = -3
+            const uint32_t* p = t - 3 * P;                          // dy = -3
             const uint32_t wl = p[-1], wc = p[0], wr = p[1];
             r[9] = __funnelshift_r(wl, wc, 16); r[8] = wc; r[7] = __funnelshift_r(wc, wr, 16);
         }
-        r[14] = t[2 * FT_PITCH_W - 1]; r[2] = t[2 * FT_PITCH_W + 1];      // dy=+2: dx -2, +2
-        r[10] = t[-2 * FT_PITCH_W - 1]; r[6] = t[-2 * FT_PITCH_W + 1];    // dy=-2
+        r[14] = t[2 * P - 1]; r[2] = t[2 * P + 1];                  // dy=+2: dx -2, +2
+        r[10] = t[-2 * P - 1]; r[6] = t[-2 * P + 1];                // dy=-2
         {
-            const uint32_t* p = t + FT_PITCH_W;                     // dy = +1 : dx -3, +3
+            const uint32_t* p = t + P;                              // dy = +1 : dx -3, +3
             r[13] = __funnelshift_r(p[-2], p[-1], 16); r[3] = __funnelshift_r(p[1], p[2], 16);
         }
         {
-            const uint32_t* p = t - FT_PITCH_W;                     // dy = -1
+            const uint32_t* p = t - P;                              // dy = -1
             r[11] = __funnelshift_r(p[-2], p[-1], 16); r[5] = __funnelshift_r(p[1], p[2], 16);
         }
         r[12] = __funnelshift_r(t[-2], t[-1], 16); r[4] = __funnelshift_r(t[1], t[2], 16);   // dy = 0
-        const uint32_t s = fast_score_pair(t[0], r);
+        uint32_t s = fast_score_pair(t[0], r);
         const int c = 2 * m;
-        uint8_t* o = &scr[rr + 1][c];
-        if (c >= cx0 && c < cx1) o[0] = (uint8_t)(s & 0xff);
-        if (c + 1 >= cx0 && c + 1 < cx1) o[1] = (uint8_t)((s >> 16) & 0xff);
+        if (c < cx0 || c >= cx1) s &= 0xffff0000u;                  // pixels outside the inner rectangle score 0
+        if (c + 1 < cx0 || c + 1 >= cx1) s &= 0x0000ffffu;
+        scr[(rr + 1) * P + m + 1] = s;
     }
     __syncthreads();
 
-    // NMS + threshold (raw neighbour scores suffice: a neighbour below the threshold is below S anyway)
-    const float rwi = __frcp_rn((float)wi);
+    // ---- NMS + threshold on packed pairs (raw neighbour scores suffice: a neighbour below the threshold
+    //      is below S anyway) ----
     const int minTh = g.minTh, iniTh = g.iniTh;
-    for (int i = tid; i < hi * wi; i += FT_THREADS) {
-        const int rr = __float2int_rz(__fmul_rz((float)i + 0.5f, rwi));
-        const int c = cx0 + (i - rr * wi);
-        const uint8_t* p = &scr[rr + 1][c];
-        const int s = p[0];
-        if (s < minTh) continue;
-        if (s > p[-1] && s > p[1] && s > p[-FT_SCW - 1] && s > p[-FT_SCW] && s > p[-FT_SCW + 1] &&
-            s > p[FT_SCW - 1] && s > p[FT_SCW] && s > p[FT_SCW + 1]) {
-            const int slot = atomicAdd(&sN, 1);
-            if (s >= iniTh) atomicAdd(&sNini, 1);
-            const int rx = xa + c - FAST_BORDER, ry = y0 + rr + 3 - FAST_BORDER;   // region coordinates
-            if (slot < FT_MAXC) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)s << 24);
+    for (int i = tid; i < hi * npr; i += FT_THREADS) {
+        const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
+        const int m = m0 + (i - rr * npr);
+        const uint32_t* q = scr + (rr + 1) * P + m + 1;
+        const uint32_t w = q[0];
+        const int sl = w & 0xffff, sh = w >> 16;
+        if (max(sl, sh) < minTh) continue;
+        const uint32_t u0 = q[-P - 1], u1 = q[-P], u2 = q[-P + 1];
+        const uint32_t c0 = q[-1], c2 = q[1];
+        const uint32_t d0 = q[P - 1], d1 = q[P], d2 = q[P + 1];
+        uint32_t nb = max3s(u1, __funnelshift_r(u0, u1, 16), __funnelshift_r(u1, u2, 16));
+        nb = max3s(nb, __funnelshift_r(c0, w, 16), __funnelshift_r(w, c2, 16));
+        nb = max3s(nb, d1, __funnelshift_r(d0, d1, 16));
+        nb = __vmaxs2(nb, __funnelshift_r(d1, d2, 16));
+        const int nl = nb & 0xffff, nh = nb >> 16;
+        const int ry = y0 + rr + 3 - FAST_BORDER;                   // region coordinates
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int sv = e ? sh : sl, nv = e ? nh : nl;
+            if (sv >= minTh && sv > nv) {
+                const int slot = atomicAdd(&sN, 1);
+                if (sv >= iniTh) atomicAdd(&sNini, 1);
+                const int rx = xa + 2 * m + e - FAST_BORDER;
+                if (slot < clistCap) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sv << 24);
+            }
         }
     }
     __syncthreads();
-    const int nAll = min(sN, FT_MAXC), nIni = sNini;
+    const int nAll = min(sN, clistCap), nIni = sNini;
     const int nEmit = nIni > 0 ? nIni : nAll;
     if (nEmit == 0) return;
     if (tid == 0) sBase = atomicAdd(&candCount[img * MAX_LEVELS + level], nEmit);
@@ -695,6 +733,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 constexpr int DS_WARPS = 8;
+constexpr int DS_KPB = 32;        // keypoints per CTA: one lane each for the scalar (atan2, sincos) part
 
 __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                                                                  const uint32_t* __restrict__ lvlKp, const int32_t* __restrict__ lvlCount,
@@ -702,82 +741,106 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(Geom g, const u
                                                                  int32_t* __restrict__ counts)
 {
     __shared__ signed char sPX[512], sPY[512];
+    __shared__ int sLevel[DS_KPB], sX[DS_KPB], sY[DS_KPB], sResp[DS_KPB], sM01[DS_KPB], sM10[DS_KPB];
+    __shared__ float sA[DS_KPB], sB[DS_KPB];
     const int img = blockIdx.y;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { sPX[i] = c_patX[i]; sPY[i] = c_patY[i]; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gk = blockIdx.x * DS_WARPS + (threadIdx.x >> 5);    // keypoint index within the image (output order)
-    // locate level
-    int level = -1, off = 0, total = 0;
-    for (int l = 0; l < g.nlevels; l++) {
-        const int c = lvlCount[img * MAX_LEVELS + l];
-        if (level < 0 && gk < total + c) { level = l; off = total; }
-        total += c;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 512; i += blockDim.x) { sPX[i] = c_patX[i]; sPY[i] = c_patY[i]; }
+    // ---- phase 0: which keypoint (output order = level-major, octree list order inside a level) ----
+    if (tid < DS_KPB) {
+        const int gk = blockIdx.x * DS_KPB + tid;
+        int level = -1, off = 0, total = 0;
+        for (int l = 0; l < g.nlevels; l++) {
+            const int c = lvlCount[img * MAX_LEVELS + l];
+            if (level < 0 && gk < total + c) { level = l; off = total; }
+            total += c;
+        }
+        if (blockIdx.x == 0 && tid == 0) counts[img] = total;
+        sLevel[tid] = level;
+        if (level >= 0) {
+            const uint32_t v = lvlKp[(size_t)img * g.kpPerImg + g.lv[level].kpOff + (gk - off)];
+            sX[tid] = (int)(v & 0xfff) + FAST_BORDER;
+            sY[tid] = (int)((v >> 12) & 0xfff) + FAST_BORDER;
+            sResp[tid] = (int)(v >> 24);
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = total;
-    if (level < 0) return;
-    const LevelGeom L = g.lv[level];
-    const uint32_t v = lvlKp[(size_t)img * g.kpPerImg + L.kpOff + (gk - off)];
-    const int x = (int)(v & 0xfff) + FAST_BORDER, y = (int)((v >> 12) & 0xfff) + FAST_BORDER;
-    const int resp = (int)(v >> 24);
+    __syncthreads();
+    if (sLevel[0] < 0) return;      // keypoints are dense from index 0: nothing in this CTA
 
-    // ---- IC_Angle on the un-blurred level ----
-    const uint8_t* center = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)y * L.pitch + x;
-    int m01 = 0, m10 = 0;
-    const int u = lane - HALF_PATCH;      // lanes 0..30 -> u = -15..15
-    if (lane < 31) {
-        m10 = u * center[u];
+    // ---- phase 1: IC_Angle moments on the un-blurred level, one warp per keypoint ----
+    for (int j = wid; j < DS_KPB; j += DS_WARPS) {
+        const int level = sLevel[j];
+        if (level < 0) break;
+        const LevelGeom& L = g.lv[level];
+        const uint8_t* center = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)sY[j] * L.pitch + sX[j];
+        int m01 = 0, m10 = 0;
+        const int u = lane - HALF_PATCH;      // lanes 0..30 -> u = -15..15
+        if (lane < 31) {
+            m10 = u * center[u];
 #pragma unroll
-        for (int vv = 1; vv <= HALF_PATCH; vv++) {
-            if (abs(u) <= c_umax[vv]) {
-                const int vp = center[u + vv * L.pitch], vm = center[u - vv * L.pitch];
-                m01 += vv * (vp - vm);
-                m10 += u * (vp + vm);
+            for (int vv = 1; vv <= HALF_PATCH; vv++) {
+                if (abs(u) <= c_umax[vv]) {
+                    const int vp = center[u + vv * L.pitch], vm = center[u - vv * L.pitch];
+                    m01 += vv * (vp - vm);
+                    m10 += u * (vp + vm);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- rBRIEF on the blurred level ----
-    constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);   // (float)(CV_PI/180.f), :106
-    const float ang = __fmul_rn(angle, factorPI);
-    // cosf/sinf of the host libm are correctly rounded for all but ~1e-8 of inputs; round a double
-    // evaluation to float to match them (float parity)
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);
-    const float a = (float)cd, b = (float)sd;
-    const uint8_t* bc = blur + (size_t)img * g.pyrBytes + L.off + (size_t)y * L.pitch + x;
-    int val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int t[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int idx = lane * 16 + 2 * k + e;
-            const float px = (float)sPX[idx], py = (float)sPY[idx];
-            const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            t[e] = bc[yy * L.pitch + xx];
+        for (int o = 16; o > 0; o >>= 1) {
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
         }
-        val |= (t[0] < t[1]) << k;
+        if (lane == 0) { sM01[j] = m01; sM10[j] = m10; }
     }
-    const size_t o = (size_t)img * g.kpPerImg + gk;
-    desc[o * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
+    __syncthreads();
+
+    // ---- phase 2: angle, cos/sin and the keypoint record, one lane per keypoint ----
+    if (tid < DS_KPB && sLevel[tid] >= 0) {
+        const int level = sLevel[tid];
+        const LevelGeom& L = g.lv[level];
+        const float angle = fast_atan2_deg((float)sM01[tid], (float)sM10[tid]);
+        constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);   // (float)(CV_PI/180.f), :106
+        const float ang = __fmul_rn(angle, factorPI);
+        // cosf/sinf of the host libm are correctly rounded for all but ~1e-8 of inputs; round a double
+        // evaluation to float to match them (float parity)
+        double sd, cd;
+        sincos((double)ang, &sd, &cd);
+        sA[tid] = (float)cd; sB[tid] = (float)sd;
         orbb200_kp_t kp;
-        kp.x = (float)x; kp.y = (float)y;
+        kp.x = (float)sX[tid]; kp.y = (float)sY[tid];
         if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }
         kp.size = (float)L.patchSize;
         kp.angle = angle;
-        kp.response = (float)resp;
+        kp.response = (float)sResp[tid];
         kp.octave = level;
         kp.class_id = -1;
-        kps[o] = kp;
+        kps[(size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + tid] = kp;
+    }
+    __syncthreads();
+
+    // ---- phase 3: rBRIEF on the blurred level, one warp per keypoint, one descriptor byte per lane ----
+    for (int j = wid; j < DS_KPB; j += DS_WARPS) {
+        const int level = sLevel[j];
+        if (level < 0) break;
+        const LevelGeom& L = g.lv[level];
+        const float a = sA[j], b = sB[j];
+        const uint8_t* bc = blur + (size_t)img * g.pyrBytes + L.off + (size_t)sY[j] * L.pitch + sX[j];
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int t[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int idx = lane * 16 + 2 * k + e;
+                const float px = (float)sPX[idx], py = (float)sPY[idx];
+                const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+                const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+                t[e] = bc[yy * L.pitch + xx];
+            }
+            val |= (t[0] < t[1]) << k;
+        }
+        desc[((size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + j) * 32 + lane] = (uint8_t)val;
     }
 }
 
@@ -809,13 +872,10 @@ void launch_pyramid(Ctx& c, int n)
 void launch_blur(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
-    for (int l = 0; l < g.nlevels; l++) {
-        const LevelGeom& L = g.lv[l];
-        if (L.w <= 0 || L.h <= 0) continue;
-        dim3 grid((L.w + BL_TW - 1) / BL_TW, (L.h + BL_TH - 1) / BL_TH, n);
-        blur_kernel<<<grid, 256, 0, c.stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, l);
-        c.launches++;
-    }
+    if (c.cur->nBlurTiles == 0) return;
+    dim3 grid((c.cur->nBlurTiles + BL_WARPS - 1) / BL_WARPS, n);
+    blur_kernel<<<grid, BL_WARPS * 32, 0, c.stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, c.cur->d_blurTiles, c.cur->nBlurTiles);
+    c.launches++;
 }
 
 void launch_fast(Ctx& c, int n)
@@ -823,8 +883,16 @@ void launch_fast(Ctx& c, int n)
     const Geom& g = c.cur->g;
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
     if (g.totalCells > 0) {
+        const ShapeTables& st = *c.cur;
+        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap);
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
         dim3 grid(g.totalCells, n);
-        fast_cells_kernel<<<grid, FT_THREADS, 0, c.stream>>>(g, c.d_pyr, c.cur->d_cells, c.d_cand, c.d_candCount);
+        fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(g, c.d_pyr, st.d_cells, c.d_cand, c.d_candCount,
+                                                               st.fastTileWords, st.fastScrWords, st.fastClistCap);
         c.launches++;
     }
 }
@@ -848,7 +916,7 @@ void launch_octree(Ctx& c, int n)
 void launch_describe(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
-    dim3 grid((g.kpPerImg + DS_WARPS - 1) / DS_WARPS, n);
+    dim3 grid((g.kpPerImg + DS_KPB - 1) / DS_KPB, n);
     describe_kernel<<<grid, DS_WARPS * 32, 0, c.stream>>>(g, c.d_pyr, c.d_blur, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts);
     c.launches++;
 }

@@ -281,6 +281,77 @@ __device__ void three_maxima(const int* histo, int& ind1, int& ind2, int& ind3)
 }
 
 constexpr int WM_THREADS = 512;
+constexpr int WC_THREADS = 128;
+
+// Per-mode search window of query q (reference: SearchByProjection :62-69, :1385-1398; BirdviewMatch :1684-1688,
+// :1807; SearchByMatchBird :2029; SearchByProjectionBird :1948).  Returns false when the query is skipped.
+struct Window { float x, y, r, urRef, urTol; int minL, maxL; bool urCheck; };
+
+__device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
+{
+    if (J.q_valid != nullptr && !J.q_valid[q]) return false;
+    W.minL = -1; W.maxL = -1; W.urCheck = false; W.urRef = 0.f; W.urTol = 0.f;
+    W.x = J.q_x[q]; W.y = J.q_y[q];
+    const int mode = J.mode;
+    if (mode == WM_PROJ) {
+        const int lvl = J.q_level[q];
+        float r = J.q_viewcos[q] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
+        if (J.th != 1.0f) r = __fmul_rn(r, J.th);
+        W.r = __fmul_rn(r, J.scaleFactors[lvl]);
+        W.minL = lvl - 1; W.maxL = lvl;
+        W.urCheck = true; W.urRef = J.q_aux[q]; W.urTol = W.r;
+    } else if (mode == WM_PROJ_FRAME) {
+        const int oct = J.q_level[q];
+        W.r = __fmul_rn(J.th, J.scaleFactors[oct]);
+        if (J.levelMode == 1) { W.minL = oct; W.maxL = -1; }
+        else if (J.levelMode == 2) { W.minL = 0; W.maxL = oct; }
+        else { W.minL = oct - 1; W.maxL = oct + 1; }
+        W.urCheck = true; W.urRef = __fsub_rn(W.x, __fmul_rn(J.mbf, J.q_aux[q])); W.urTol = W.r;
+    } else if (mode == WM_BIRD) {
+        const int lvl = J.q_level[q];
+        if (J.levelMode == 1 && lvl > 0) return false;                  // prevMatched variant: octave 0 only
+        W.r = J.th; W.minL = lvl; W.maxL = lvl;
+    } else {   // WM_BIRD_KF, WM_PROJ_BIRD
+        W.r = J.th;
+    }
+    return true;
+}
+
+// Phase 1 (fully parallel, thread per query): scan the window once, apply every filter that does not depend
+// on the loop-carried state (level, window, initial kp_blocked, uRight) and cache (index, distance | level<<16)
+// of the survivors in scan order.  Queries with more than WM_LISTCAP survivors are re-scanned in phase 2.
+__global__ void __launch_bounds__(WC_THREADS) window_cands_kernel(const WinJob* __restrict__ jobs)
+{
+    const WinJob J = jobs[blockIdx.y];
+    const int q = blockIdx.x * WC_THREADS + threadIdx.x;
+    if (q >= J.nq) return;
+    const FrameDev F = *J.frame;
+    int* ccount = J.scratch + 2 * J.kpCap + 6 * J.nq;
+    int2* clist = reinterpret_cast<int2*>(J.scratch + win_clist_offset(J.kpCap, J.nq)) + (size_t)q * WM_LISTCAP;
+    Window W;
+    int n = 0;
+    if (query_window(J, q, W)) {
+        const bool distSem = (J.mode == WM_BIRD || J.mode == WM_BIRD_KF);
+        const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
+        const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+        scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
+            if (!distSem) {
+                if (J.kp_blocked && J.kp_blocked[idx]) return;
+                if (W.urCheck && F.uRight) {
+                    const float ur = F.uRight[idx];
+                    if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
+                }
+            }
+            const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
+            const int d = hamming256(qa, qb, kd[0], kd[1]);
+            if (n < WM_LISTCAP) clist[n] = make_int2(idx, d | (kp.octave << 16));
+            n++;
+        });
+    } else {
+        n = -1;     // skipped query
+    }
+    ccount[q] = n;
+}
 
 __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* __restrict__ jobs)
 {
@@ -303,6 +374,8 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     int* newCdist = newChoice + nq;         // [nq]
     int* nextq = newCdist + nq;             // [nq]    DIST: claimant list link
     int* qbin = nextq + nq;                 // [nq]    rotation bin of an accepted query
+    const int* ccount = qbin + nq;          // [nq]    phase-1 candidate counts
+    const int2* clistAll = reinterpret_cast<const int2*>(J.scratch + win_clist_offset(J.kpCap, nq));
 
     for (int i = tid; i < nkp; i += WM_THREADS) { owner[i] = distSem ? -1 : 0x7fffffff; lastOwner[i] = -1; }
     for (int i = tid; i < nq; i += WM_THREADS) { choice[i] = -1; cdist[i] = 0; }
@@ -312,68 +385,55 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
         int changed = 0;
         for (int q = tid; q < nq; q += WM_THREADS) {
             int selIdx = -1, selDist = 0;
-            if (J.q_valid == nullptr || J.q_valid[q]) {
-                // ---- per-mode window ----
-                float x, y, r, urRef = 0.f, urTol = 0.f;
-                int minL = -1, maxL = -1;
-                bool skip = false, urCheck = false;
-                if (mode == WM_PROJ) {
-                    const int lvl = J.q_level[q];
-                    r = J.q_viewcos[q] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
-                    if (J.th != 1.0f) r = __fmul_rn(r, J.th);
-                    r = __fmul_rn(r, J.scaleFactors[lvl]);
-                    x = J.q_x[q]; y = J.q_y[q]; minL = lvl - 1; maxL = lvl;
-                    urCheck = true; urRef = J.q_aux[q]; urTol = r;
-                } else if (mode == WM_PROJ_FRAME) {
-                    const int oct = J.q_level[q];
-                    r = __fmul_rn(J.th, J.scaleFactors[oct]);
-                    x = J.q_x[q]; y = J.q_y[q];
-                    if (J.levelMode == 1) { minL = oct; maxL = -1; }
-                    else if (J.levelMode == 2) { minL = 0; maxL = oct; }
-                    else { minL = oct - 1; maxL = oct + 1; }
-                    urCheck = true; urRef = __fsub_rn(x, __fmul_rn(J.mbf, J.q_aux[q])); urTol = r;
-                } else if (mode == WM_BIRD) {
-                    const int lvl = J.q_level[q];
-                    if (J.levelMode == 1 && lvl > 0) skip = true;             // prevMatched variant: octave 0 only
-                    x = J.q_x[q]; y = J.q_y[q]; r = J.th; minL = lvl; maxL = lvl;
-                } else {   // WM_BIRD_KF, WM_PROJ_BIRD
-                    x = J.q_x[q]; y = J.q_y[q]; r = J.th;
-                }
-                if (!skip) {
+            const int cnt = ccount[q];
+            if (cnt > 0) {
+                const int big = distSem ? 0x7fffffff : 256;
+                int best = big, second = big, bestIdx = -1, bestLevel = -1, secondLevel = -1;
+                auto consider = [&](int idx, int d, int level) {
+                    if (!distSem) {
+                        if (owner[idx] < q) return;
+                    } else {
+                        // vMatchedDistance[idx] <= d as left by the accepted queries < q
+                        for (int c = owner[idx]; c >= 0; c = nextq[c])
+                            if (c < q && cdist[c] <= d) return;
+                    }
+                    if (d < best) { second = best; best = d; secondLevel = bestLevel; bestLevel = level; bestIdx = idx; }
+                    else if (d < second) { secondLevel = level; second = d; }
+                };
+                if (cnt <= WM_LISTCAP) {
+                    const int2* cl = clistAll + (size_t)q * WM_LISTCAP;
+                    for (int k = 0; k < cnt; k++) {
+                        const int2 e = cl[k];
+                        consider(e.x, e.y & 0xffff, e.y >> 16);
+                    }
+                } else {
+                    // overflow: re-scan the window (same filters as phase 1)
+                    Window W;
+                    query_window(J, q, W);
                     const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
                     const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
-                    const int big = distSem ? 0x7fffffff : 256;
-                    int best = big, second = big, bestIdx = -1, bestLevel = -1, secondLevel = -1;
-                    scan_window(F, x, y, r, minL, maxL, [&](int idx, const orbb200_kp_t& kp) {
+                    scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
                         if (!distSem) {
                             if (J.kp_blocked && J.kp_blocked[idx]) return;
-                            if (owner[idx] < q) return;
-                            if (urCheck && F.uRight) {
+                            if (W.urCheck && F.uRight) {
                                 const float ur = F.uRight[idx];
-                                if (ur > 0 && fabsf(__fsub_rn(urRef, ur)) > urTol) return;
+                                if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
                             }
                         }
                         const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
-                        const int d = hamming256(qa, qb, kd[0], kd[1]);
-                        if (distSem) {
-                            // vMatchedDistance[idx] <= d as left by the accepted queries < q
-                            for (int c = owner[idx]; c >= 0; c = nextq[c])
-                                if (c < q && cdist[c] <= d) return;
-                        }
-                        if (d < best) { second = best; best = d; secondLevel = bestLevel; bestLevel = kp.octave; bestIdx = idx; }
-                        else if (d < second) { secondLevel = kp.octave; second = d; }
+                        consider(idx, hamming256(qa, qb, kd[0], kd[1]), kp.octave);
                     });
-                    bool acc;
-                    if (mode == WM_PROJ || mode == WM_PROJ_BIRD)
-                        acc = best <= TH_HIGH && !(bestLevel == secondLevel && (float)best > __fmul_rn(J.nnratio, (float)second));
-                    else if (mode == WM_PROJ_FRAME)
-                        acc = best <= TH_HIGH;
-                    else if (mode == WM_BIRD)
-                        acc = best <= TH_LOW && (float)best < __fmul_rn((float)second, J.nnratio);
-                    else
-                        acc = best <= TH_HIGH && (bestLevel != secondLevel || (float)best < __fmul_rn((float)second, J.nnratio));
-                    if (acc) { selIdx = bestIdx; selDist = best; }
                 }
+                bool acc;
+                if (mode == WM_PROJ || mode == WM_PROJ_BIRD)
+                    acc = best <= TH_HIGH && !(bestLevel == secondLevel && (float)best > __fmul_rn(J.nnratio, (float)second));
+                else if (mode == WM_PROJ_FRAME)
+                    acc = best <= TH_HIGH;
+                else if (mode == WM_BIRD)
+                    acc = best <= TH_LOW && (float)best < __fmul_rn((float)second, J.nnratio);
+                else
+                    acc = best <= TH_HIGH && (bestLevel != secondLevel || (float)best < __fmul_rn((float)second, J.nnratio));
+                if (acc) { selIdx = bestIdx; selDist = best; }
             }
             if (selIdx != choice[q] || selDist != cdist[q]) changed = 1;
             newChoice[q] = selIdx;      // published after the barrier: other threads still read choice/cdist
@@ -462,8 +522,13 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     if (tid == 0) *J.out_nmatches = sCount - sRemoved;
 }
 
-void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs)
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq)
 {
+    if (maxNq > 0) {
+        dim3 grid((maxNq + WC_THREADS - 1) / WC_THREADS, njobs);
+        window_cands_kernel<<<grid, WC_THREADS, 0, c.stream>>>(d_jobs);
+        c.launches++;
+    }
     window_match_kernel<<<njobs, WM_THREADS, 0, c.stream>>>(d_jobs);
     c.launches++;
 }

@@ -22,7 +22,7 @@ struct WinJob {
     const uint8_t* q_desc;
     const uint8_t* q_obs_pos;   // may be null (all 1)
     const uint8_t* kp_blocked;  // may be null (none)
-    int* scratch;               // 2*kpCap + 6*nq ints
+    int* scratch;               // win_scratch_ints(kpCap, nq) ints
     int32_t* out_best_idx;      // [nq] or null
     int32_t* out_best_dist;     // [nq] or null
     int32_t* out_per_kp;        // [n] query assigned to each keypoint (all modes but WM_BIRD)
@@ -30,7 +30,10 @@ struct WinJob {
     int32_t* out_nmatches;
 };
 
-static inline size_t win_scratch_ints(int kpCap, int nq) { return (size_t)2 * kpCap + (size_t)6 * nq; }
+constexpr int WM_LISTCAP = 24;   // cached candidates per query (more -> that query re-scans its window)
+// owner, lastOwner [kpCap]; choice, cdist, newChoice, newCdist, nextq, qbin, ccount [nq]; clist int2[nq][WM_LISTCAP]
+__host__ __device__ static inline size_t win_clist_offset(int kpCap, int nq) { return ((size_t)2 * kpCap + (size_t)7 * nq + 1) & ~(size_t)1; }
+static inline size_t win_scratch_ints(int kpCap, int nq) { return win_clist_offset(kpCap, nq) + (size_t)2 * WM_LISTCAP * nq + 2; }
 
 struct TriJob {
     const orbb200_kp_t* kps1; const uint8_t* desc1; const float* uR1; const uint8_t* has_mp1; int n1;
@@ -51,7 +54,7 @@ void launch_popc_peak(Ctx& c, uint32_t* d_out, int blocks, int iters);
 void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes);
 void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, float r, int minLevel, int maxLevel,
                              int32_t* d_out, int cap, int32_t* d_count);
-void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs);
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq);
 void launch_triangulation(Ctx& c, const TriJob& J);
 
 }  // namespace orbb200
