@@ -39,9 +39,12 @@ bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err)
         LevelGeom& L = g.lv[l];
         L.w = std::max(cvRoundF((float)w * c.invScale[l]), 0);
         L.h = std::max(cvRoundF((float)h * c.invScale[l]), 0);
-        L.pitch = (int)align_up((size_t)std::max(L.w, 1), 128);
-        L.off = (unsigned)off;
-        off += align_up((size_t)L.pitch * std::max(L.h, 1), 256);
+        // bordered storage (cf. the reference's copyMakeBorder, src/ORBextractor.cc:1122-1128): PYR_MARGIN_Y
+        // rows above/below and PYR_MARGIN_X bytes left of every row hold the reflect-101 border, so that the
+        // stencil kernels never branch on image edges; L.off addresses pixel (0,0)
+        L.pitch = (int)align_up((size_t)PYR_MARGIN_X + std::max(L.w, 1) + 16, 128);
+        L.off = (unsigned)(off + (size_t)PYR_MARGIN_Y * L.pitch + PYR_MARGIN_X);
+        off += align_up((size_t)L.pitch * (std::max(L.h, 1) + 2 * PYR_MARGIN_Y), 256);
         L.scale = c.scale[l];
         L.quota = c.quota[l];
         L.patchSize = (int)(PATCH_SIZE * c.scale[l]);
@@ -170,6 +173,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                 if (iniX >= L.maxBX - 6) continue;
                 if (maxX > L.maxBX) maxX = (float)L.maxBX;
                 cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
+                cells.push_back(make_int4((int)L.off, L.pitch, (int)L.candOff, L.candCap));
                 {   // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
                     const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3, tw = x1 - xa;
                     const int wi = x1 - x0 - 6, hi = th - 6;
@@ -180,16 +184,21 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                         st.fastTileWords = std::max(st.fastTileWords, th * P);
                         st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
                         st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
+                        st.fastWorkCap = std::max(st.fastWorkCap, ((hi * npr + 1) & ~1) + 2);
                     }
                 }
             }
         }
     }
-    std::vector<int4> btiles;
+    std::vector<int4> btiles, rtiles;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         for (int y0 = 0; y0 < L.h; y0 += 32)
             for (int x0 = 0; x0 < L.w; x0 += 128) btiles.push_back(make_int4(l, x0, y0, 0));
+        if (l > 0)
+            for (int y0 = 0; y0 < L.h; y0 += RS_ROWS)
+                for (int x0 = 0; x0 < L.w; x0 += 128) { rtiles.push_back(make_int4(l, x0, y0, 0)); st.resizeTileCount[l]++; }
+        st.resizeTileBase[l + 1] = (int)rtiles.size();
     }
     st.nBlurTiles = (int)btiles.size();
     auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {
@@ -201,7 +210,8 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     bool ok = up((void**)&st.d_xtab, xtab.data(), xtab.size() * sizeof(int2)) &&
               up((void**)&st.d_ytab, ytab.data(), ytab.size() * sizeof(int4)) &&
               up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4)) &&
-              up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4));
+              up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4)) &&
+              up((void**)&st.d_resizeTiles, rtiles.data(), rtiles.size() * sizeof(int4));
     cudaStreamSynchronize(c.stream);   // host vectors go out of scope
     if (!ok) { c.err = "cudaMalloc(shape tables) failed"; return nullptr; }
     auto res = c.shapes.emplace(std::make_pair(w, h), st);
@@ -243,7 +253,7 @@ void drain_stage_events(Ctx& c)
 
 static int run_extract(Ctx& c, int n)
 {
-    { StageTimer t(c, 1); launch_pyramid(c, n); }
+    { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
     { StageTimer t(c, 2); launch_fast(c, n); }
     { StageTimer t(c, 3); launch_blur(c, n); }
     { StageTimer t(c, 4); launch_octree(c, n); }
@@ -332,8 +342,8 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     const size_t nb = (size_t)max_batch;
     bool ok = true;
     auto alloc = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, std::max<size_t>(bytes, 256)) != cudaSuccess) ok = false; };
-    alloc((void**)&c.d_pyr, nb * g.pyrBytes);
-    alloc((void**)&c.d_blur, nb * g.pyrBytes);
+    alloc((void**)&c.d_pyr, nb * g.pyrBytes + 4096);
+    alloc((void**)&c.d_blur, nb * g.pyrBytes + 4096);
     alloc((void**)&c.d_cand, nb * candSlots * sizeof(uint32_t));
     alloc((void**)&c.d_nodeOf, nb * candSlots * sizeof(uint16_t));
     alloc((void**)&c.d_candCount, nb * MAX_LEVELS * sizeof(int32_t));
@@ -366,7 +376,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (auto& p : c.plans) cudaFree(p.block);
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); }
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.h_stage) cudaFreeHost(c.h_stage);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -449,7 +459,7 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
     (void)contiguous;
     for (int i = 0; i < n; i++) {
         if (!imgs[i]) { c.err = "extract: null image"; return ORBB200_ERR_ARG; }
-        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes, g.lv[0].pitch, imgs[i], stride, (size_t)w, (size_t)h,
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[i], stride, (size_t)w, (size_t)h,
                                              cudaMemcpyHostToDevice, c.stream));
     }
     int rc = run_extract(c, n);

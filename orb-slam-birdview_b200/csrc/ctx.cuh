@@ -11,10 +11,13 @@ struct ShapeTables {
     Geom g;
     int2* d_xtab = nullptr;     // resize: per output x of levels>=1: {sx, a0 | a1<<16}
     int4* d_ytab = nullptr;     // resize: per output y of levels>=1: {sy0, sy1, b0, b1}
-    int4* d_cells = nullptr;    // FAST cells of all levels: {x0|y0<<16, x1|y1<<16, level, order index}
+    int4* d_cells = nullptr;    // FAST cells of all levels, 2 x int4 each: {x0|y0<<16, x1|y1<<16, level, order}, {level offset, pitch, candOff, candCap}
     int4* d_blurTiles = nullptr;  // blur tiles of all levels: {level, x0, y0, 0}, 128 x 32 pixels each
     int nBlurTiles = 0;
-    int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0;   // shared-memory carve of fast_cells_kernel
+    int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1: {level, x0, y0, 0}, 128 x RS_ROWS pixels each
+    int resizeTileBase[MAX_LEVELS + 1] = {0};
+    int resizeTileCount[MAX_LEVELS] = {0};
+    int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0, fastWorkCap = 0;   // shared-memory carve of fast_cells_kernel
 };
 
 struct WinJob;

@@ -4,6 +4,8 @@
 // Integer arithmetic follows OpenCV 4.x exactly (DESIGN.md
 // and SURVEY.md Appendix A lists each primitive); float arithmetic uses explicit round-to-nearest intrinsics so that nvcc
 // never contracts it into FMAs.
+#include <cuda_fp16.h>
+
 #include "ctx.cuh"
 #include "../../include/orbb200_pattern.inc"
 
@@ -13,12 +15,12 @@ namespace orbb200 {
 // import: user images (arbitrary stride) -> level 0 of the pyramid pool (pitch 128-aligned)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__ src, size_t img_bytes, size_t stride,
-                                                     uint8_t* __restrict__ pyr, unsigned pyrBytes, int w, int h, int pitch)
+                                                     uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned off0, int w, int h, int pitch)
 {
     const int img = blockIdx.z;
     const int y = blockIdx.y;
     const uint8_t* s = src + (size_t)img * img_bytes + (size_t)y * stride;
-    uint8_t* d = pyr + (size_t)img * pyrBytes + (size_t)y * pitch;
+    uint8_t* d = pyr + (size_t)img * pyrBytes + off0 + (size_t)y * pitch;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= w) return;
     if (((reinterpret_cast<uintptr_t>(s) & 3) == 0) && x4 + 3 < w) {
@@ -32,33 +34,93 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 // cv::resize INTER_LINEAR u8 (reference src/ORBextractor.cc:1120): level l-1 -> l.
 // 11-bit fixed-point coefficients from host-built tables; vertical pass
 // (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
+// Streaming form: a warp owns 128 output columns x RS_ROWS output rows; each lane owns 4 adjacent output
+// columns, keeps their column coefficients in registers, walks down the rows and reuses the horizontal
+// interpolation of a source row for the next output row (a source row serves ~1.7 output rows at 1/1.2).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
-                                                     const int2* __restrict__ xtab, const int4* __restrict__ ytab)
+constexpr int RS_WARPS = 4;
+
+__global__ void __launch_bounds__(RS_WARPS * 32) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
+                                                              const int2* __restrict__ xtab, const int4* __restrict__ ytab,
+                                                              const int4* __restrict__ tiles, int nTiles)
 {
-    const int img = blockIdx.z;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (y >= dst.h || x4 >= dst.w) return;
+    const int tileIdx = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (tileIdx >= nTiles) return;
+    const int lane = threadIdx.x & 31;
+    const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
+    const int img = blockIdx.y;
+    const int x4 = t.y + 4 * lane, y0 = t.z;
+    if (x4 >= dst.w) return;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + src.off;
-    uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off + (size_t)y * dst.pitch;
-    const int4 yt = __ldg(ytab + dst.ytabOff + y);
-    const uint8_t* S0 = S + (size_t)yt.x * src.pitch;
-    const uint8_t* S1 = S + (size_t)yt.y * src.pitch;
-    const int b0 = yt.z, b1 = yt.w;
-    uint32_t out = 0;
+    uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off;
+    // column setup, once per thread: source offsets and 11-bit coefficients of its 4 columns
+    int sx[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int x = min(x4 + i, dst.w - 1);
-        const int2 xt = __ldg(xtab + dst.xtabOff + x);
-        const int sx = xt.x, sx1 = min(sx + 1, src.w - 1);
-        const int a0 = xt.y & 0xffff, a1 = xt.y >> 16;
-        const int r0 = S0[sx] * a0 + S0[sx1] * a1;
-        const int r1 = S1[sx] * a0 + S1[sx1] * a1;
-        const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        out |= (uint32_t)(v & 0xff) << (8 * i);
+        const int2 xt = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
+        sx[i] = xt.x; sx1[i] = min(xt.x + 1, src.w - 1);
+        a0[i] = xt.y & 0xffff; a1[i] = xt.y >> 16;
     }
-    *reinterpret_cast<uint32_t*>(D + x4) = out;   // pitch padding absorbs the tail
+    auto hrow = [&](int sy, int (&h)[4]) {
+        const uint8_t* r = S + (size_t)sy * src.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = (r[sx[i]] * a0[i] + r[sx1[i]] * a1[i]) >> 4;
+    };
+    int ha[4], hb[4];
+    int ia = -1, ib = -1;
+    const int rows = min(RS_ROWS, dst.h - y0);
+    for (int r = 0; r < rows; r++) {
+        const int4 yt = __ldg(ytab + dst.ytabOff + y0 + r);               // {sy0, sy1, b0, b1}: warp-uniform
+        if (yt.x != ia) {
+            if (yt.x == ib) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) ha[i] = hb[i];
+            } else {
+                hrow(yt.x, ha);
+            }
+            ia = yt.x;
+        }
+        if (yt.y != ib) {
+            if (yt.y == ia) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) hb[i] = ha[i];
+            } else {
+                hrow(yt.y, hb);
+            }
+            ib = yt.y;
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int v = (((yt.z * ha[i]) >> 16) + ((yt.w * hb[i]) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xff) << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * dst.pitch + x4) = out;   // row padding absorbs the tail
+    }
+}
+
+// Reflect-101 border of every level: PYR_MARGIN_X(>=4 used) columns left, 8 right, 3 rows above/below.
+__global__ void __launch_bounds__(256) border_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, Geom g)
+{
+    const int level = blockIdx.x, img = blockIdx.y;
+    const LevelGeom L = g.lv[level];
+    if (L.w < 8 || L.h < 4) return;
+    uint8_t* B = pyr + (size_t)img * pyrBytes + L.off;
+    auto rx = [&](int x) { return x < 0 ? -x : (x >= L.w ? 2 * (L.w - 1) - x : x); };
+    auto ry = [&](int y) { return y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y); };
+    // rows -3..-1 and h..h+2, columns -4 .. w+7
+    const int wide = L.w + 12;
+    for (int i = threadIdx.x; i < 6 * wide; i += 256) {
+        const int k = i / wide, x = i - k * wide - 4;
+        const int y = k < 3 ? k - 3 : L.h + (k - 3);
+        B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)ry(y) * L.pitch + rx(x)];
+    }
+    // columns -4..-1 and w..w+7 of the image rows
+    for (int i = threadIdx.x; i < 12 * L.h; i += 256) {
+        const int y = i / 12, k = i - y * 12;
+        const int x = k < 4 ? k - 4 : L.w + (k - 4);
+        B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)y * L.pitch + rx(x)];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -113,42 +175,40 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
     if (x >= L.w) return;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + L.off;
     uint8_t* D = blur + (size_t)img * pyrBytes + L.off;
-    const bool interior = (x - 4 >= 0) && (x + 7 < L.w);
     const int rows = min(BL_ROWS, L.h - y0);
 
+    // the level is stored with its reflect-101 border (border_kernel): no edge handling here
     auto load_row = [&](int yy, uint32_t (&h)[4]) {
-        const uint8_t* row = S + (size_t)reflect101(yy, L.h) * L.pitch;
-        uint32_t w0, w1, w2;
-        if (interior) {
-            const uint32_t* r = reinterpret_cast<const uint32_t*>(row + x);
-            w0 = r[-1]; w1 = r[0]; w2 = r[1];
-        } else {
-            w0 = w1 = w2 = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                w0 |= (uint32_t)row[reflect101(x - 4 + b, L.w)] << (8 * b);
-                w1 |= (uint32_t)row[reflect101(x + b, L.w)] << (8 * b);
-                w2 |= (uint32_t)row[reflect101(x + 4 + b, L.w)] << (8 * b);
-            }
-        }
-        blur_hrow(w0, w1, w2, h);
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)yy * L.pitch + x);
+        blur_hrow(r[-1], r[0], r[1], h);
     };
 
     uint32_t h0[4], h1[4], h2[4], h3[4], h4[4], h5[4], h6[4];
     load_row(y0 - 3, h0); load_row(y0 - 2, h1); load_row(y0 - 1, h2);
     load_row(y0, h3); load_row(y0 + 1, h4); load_row(y0 + 2, h5);
-    for (int r = 0; r < rows; r++) {
-        load_row(y0 + r + 3, h6);
+    auto emit = [&](int r, const uint32_t (&a)[4], const uint32_t (&b)[4], const uint32_t (&c)[4], const uint32_t (&d)[4],
+                    const uint32_t (&e)[4], const uint32_t (&f)[4], const uint32_t (&gq)[4]) {
         uint32_t out = 0;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint32_t v = 18u * (h0[b] + h6[b]) + 34u * (h1[b] + h5[b]) + 48u * (h2[b] + h4[b]) + 56u * h3[b] + 32768u;
-            out |= (v >> 16) << (8 * b);
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = 18u * (a[k] + gq[k]) + 34u * (b[k] + f[k]) + 48u * (c[k] + e[k]) + 56u * d[k] + 32768u;
+            out |= (v >> 16) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * L.pitch + x) = out;
-#pragma unroll
-        for (int b = 0; b < 4; b++) { h0[b] = h1[b]; h1[b] = h2[b]; h2[b] = h3[b]; h3[b] = h4[b]; h4[b] = h5[b]; h5[b] = h6[b]; }
+    };
+    // the 7-row ring rotates by renaming (unrolled x7), not by moving registers
+#define ORBB200_BLUR_STEP(A, B, C, Dd, E, F, G) \
+    if (r < rows) { load_row(y0 + r + 3, G); emit(r, A, B, C, Dd, E, F, G); r++; }
+    for (int r = 0; r < rows;) {
+        ORBB200_BLUR_STEP(h0, h1, h2, h3, h4, h5, h6)
+        ORBB200_BLUR_STEP(h1, h2, h3, h4, h5, h6, h0)
+        ORBB200_BLUR_STEP(h2, h3, h4, h5, h6, h0, h1)
+        ORBB200_BLUR_STEP(h3, h4, h5, h6, h0, h1, h2)
+        ORBB200_BLUR_STEP(h4, h5, h6, h0, h1, h2, h3)
+        ORBB200_BLUR_STEP(h5, h6, h0, h1, h2, h3, h4)
+        ORBB200_BLUR_STEP(h6, h0, h1, h2, h3, h4, h5)
     }
+#undef ORBB200_BLUR_STEP
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -159,23 +219,42 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
 // S >= iniThFAST, or, when the cell has none, if S >= minThFAST.
 // Candidates are appended unordered to the level's pool: the octree only needs (x, y, response).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FT_THREADS = 128;
+constexpr int FT_THREADS = 96;
 
 __device__ __forceinline__ uint32_t min3s(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3s(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+// The same per-lane min/max on the FP16 pipe (HMNMX2): lanes are 0x6400 + byte, i.e. the positive normal
+// halves 1024..1279, whose order as halves equals their order as integers.  Used for part of the network so
+// that the integer ALU pipe (VIMNMX3) and the FMA pipe share the work.
+__device__ __forceinline__ uint32_t hmin2u(uint32_t a, uint32_t b)
+{
+    const __half2 r = __hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b)
+{
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+constexpr int FT_NHALF = 8;        // first-stage triples computed on the FP16 pipe (0..16)
+constexpr uint32_t FT_BIAS = 0x64006400u;
 
-// score of the two pixels packed in `c` given the 16 ring pairs; lanes hold u8 values
+// score of the two pixels packed in `c` given the 16 ring pairs; lanes hold u8 values.
+// With d_k = v - p_k:  M_dark = max_arcs min_arc d = v - min_arcs max_arc p,  M_bright = max_arcs min_arc (-d)
+// = max_arcs min_arc p - v, so the min/max network runs on the ring values themselves and the centre is
+// subtracted once at the end.
 __device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (&r)[16])
 {
-    uint32_t d[16];
-    const uint32_t cb = c + 0x01000100u;            // bias 256 per lane: no cross-lane borrow below
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = cb - r[k];  // 256 + (v - p_k) in [1,511]
     uint32_t lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        lo3[k] = min3s(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        hi3[k] = max3s(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        if (k < FT_NHALF) {
+            lo3[k] = hmin2u(hmin2u(r[k], r[(k + 1) & 15]), r[(k + 2) & 15]);
+            hi3[k] = hmax2u(hmax2u(r[k], r[(k + 1) & 15]), r[(k + 2) & 15]);
+        } else {
+            lo3[k] = min3s(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+            hi3[k] = max3s(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        }
     }
     uint32_t mn[16], mx[16];
 #pragma unroll
@@ -186,35 +265,40 @@ __device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (
     uint32_t a = max3s(mn[0], mn[1], mn[2]);
     a = max3s(a, mn[3], mn[4]); a = max3s(a, mn[5], mn[6]); a = max3s(a, mn[7], mn[8]);
     a = max3s(a, mn[9], mn[10]); a = max3s(a, mn[11], mn[12]); a = max3s(a, mn[13], mn[14]);
-    a = __vmaxs2(a, mn[15]);                        // 256 + M_dark
+    a = __vmaxs2(a, mn[15]);                        // max_arcs min_arc p  = v + M_bright
     uint32_t b = min3s(mx[0], mx[1], mx[2]);
     b = min3s(b, mx[3], mx[4]); b = min3s(b, mx[5], mx[6]); b = min3s(b, mx[7], mx[8]);
     b = min3s(b, mx[9], mx[10]); b = min3s(b, mx[11], mx[12]); b = min3s(b, mx[13], mx[14]);
-    b = __vmins2(b, mx[15]);                        // 256 - M_bright
-    // S + 512 = max(M_dark - 1, M_bright - 1, 0) + 512
-    const uint32_t s = max3s(a + 0x00ff00ffu, 0x02ff02ffu - b, 0x02000200u);
+    b = __vmins2(b, mx[15]);                        // min_arcs max_arc p  = v - M_dark
+    // S + 512 = max(M_dark - 1, M_bright - 1, 0) + 512; per-lane biases keep every lane positive (no borrow)
+    const uint32_t dark = (c + 0x01ff01ffu) - b;    // v + 511 - (v - M_dark)  = M_dark - 1 + 512
+    const uint32_t bright = (a + 0x01ff01ffu) - c;  // v + M_bright + 511 - v = M_bright - 1 + 512
+    const uint32_t s = max3s(dark, bright, 0x02000200u);
     return s - 0x02000200u;
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 8) fast_cells_kernel(Geom g, const uint8_t* __restrict__ pyr, const int4* __restrict__ cells,
+__global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
+                                                                   int minTh, int iniTh, const int4* __restrict__ cells,
                                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
                                                                    int tileWords, int scrWords, int clistCap)
 {
     // tile[r][1+m] = pixels (2m, 2m+1) of cell-image row r as u16x2; score tile in the same layout with a
     // zero row above/below.  Row pitch == pairs-per-row (mod 32): the flattened (row, pair) -> lane mapping
     // then walks consecutive banks across row boundaries (no bank conflicts).
-    // Shared memory is sized by the host for the largest cell of this image shape (typically ~17 KB).
+    // Shared memory is sized by the host for the largest cell of this image shape (typically ~18 KB).
     extern __shared__ uint32_t ftSmem[];
     uint32_t* tile = ftSmem;
     uint32_t* scr = tile + tileWords;
     uint32_t* clist = scr + scrWords;
-    __shared__ int sN, sNini, sBase, sOut;
+    uint16_t* wlist = reinterpret_cast<uint16_t*>(clist + clistCap);    // pairs that may hold a local maximum
+    __shared__ int sN, sNini, sBase, sOut, sW;
 
     const int img = blockIdx.y;
-    const int4 cell = __ldg(cells + blockIdx.x);
+    const int4 cell = __ldg(cells + 2 * blockIdx.x);         // {x0|y0<<16, x1|y1<<16, level, -}
+    const int4 lvl = __ldg(cells + 2 * blockIdx.x + 1);      // {level byte offset, pitch, candOff, candCap}
     const int x0 = cell.x & 0xffff, y0 = cell.x >> 16, x1 = cell.y & 0xffff, y1 = cell.y >> 16;
     const int level = cell.z;
-    const LevelGeom L = g.lv[level];
+    const int pitch = lvl.y;
     const int tid = threadIdx.x;
     const int xa = x0 & ~3;
     const int tw = x1 - xa, th = y1 - y0;
@@ -226,22 +310,24 @@ __global__ void __launch_bounds__(FT_THREADS, 8) fast_cells_kernel(Geom g, const
     int P = npr;
     while (P < 2 * nw + 3) P += 32;                 // <= 63
 
-    if (tid == 0) { sN = 0; sNini = 0; sOut = 0; }
-    for (int i = tid; i < (hi + 2) * P; i += FT_THREADS) scr[i] = 0;
+    if (tid == 0) { sN = 0; sNini = 0; sOut = 0; sW = 0; }
+    // zero frame of the score tile: the rows above/below and the words left/right of the inner span
+    for (int i = tid; i < P; i += FT_THREADS) { scr[i] = 0; scr[(hi + 1) * P + i] = 0; }
+    for (int i = tid; i < hi; i += FT_THREADS) { scr[(i + 1) * P + m0] = 0; scr[(i + 1) * P + m1 + 2] = 0; }
     // load the cell image: 32-bit words widened to u16 pairs; pixel column tc lives in word 1 + tc/2
-    const uint8_t* S = pyr + (size_t)img * g.pyrBytes + L.off + (size_t)y0 * L.pitch + xa;
+    const uint8_t* S = pyr + (size_t)img * pyrBytes + (unsigned)lvl.x + (size_t)y0 * pitch + xa;
     const uint32_t magicNw = 0xffffffffu / (uint32_t)nw + 1u;
     for (int i = tid; i < th * nw; i += FT_THREADS) {
         const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
         const int k = i - r * nw;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * L.pitch + 4 * k);
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * pitch + 4 * k);
         uint32_t* t = tile + r * P;
-        t[1 + 2 * k] = __byte_perm(v, 0, 0x4140);
-        t[2 + 2 * k] = __byte_perm(v, 0, 0x4342);
-        // words next to the loaded span are read by masked lanes only, but must hold byte-range values:
-        // a lane above 255 would borrow into its neighbour lane in the packed subtraction
-        if (k == 0) t[0] = 0;
-        if (k == nw - 1) { t[2 * nw + 1] = 0; t[2 * nw + 2] = 0; }
+        t[1 + 2 * k] = __byte_perm(v, 0, 0x4140) | FT_BIAS;
+        t[2 + 2 * k] = __byte_perm(v, 0, 0x4342) | FT_BIAS;
+        // words next to the loaded span are read by masked lanes only, but must hold in-range values: a lane
+        // outside [0x6400, 0x64ff] would borrow into its neighbour lane in the packed subtraction (or be a NaN)
+        if (k == 0) t[0] = FT_BIAS;
+        if (k == nw - 1) { t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS; }
     }
     __syncthreads();
 
@@ -279,19 +365,21 @@ __global__ void __launch_bounds__(FT_THREADS, 8) fast_cells_kernel(Geom g, const
         if (c < cx0 || c >= cx1) s &= 0xffff0000u;                  // pixels outside the inner rectangle score 0
         if (c + 1 < cx0 || c + 1 >= cx1) s &= 0x0000ffffu;
         scr[(rr + 1) * P + m + 1] = s;
+        // a pair goes on the NMS work list when one of its pixels reaches minThFAST
+        if ((int)(s & 0xffffu) >= minTh || (int)(s >> 16) >= minTh) wlist[atomicAdd(&sW, 1)] = (uint16_t)i;
     }
     __syncthreads();
 
-    // ---- NMS + threshold on packed pairs (raw neighbour scores suffice: a neighbour below the threshold
-    //      is below S anyway) ----
-    const int minTh = g.minTh, iniTh = g.iniTh;
-    for (int i = tid; i < hi * npr; i += FT_THREADS) {
+    // ---- NMS + threshold on the listed pairs (raw neighbour scores suffice: a neighbour below the
+    //      threshold is below S anyway) ----
+    const int nWork = sW;
+    for (int j = tid; j < nWork; j += FT_THREADS) {
+        const int i = wlist[j];
         const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
         const int m = m0 + (i - rr * npr);
         const uint32_t* q = scr + (rr + 1) * P + m + 1;
         const uint32_t w = q[0];
         const int sl = w & 0xffff, sh = w >> 16;
-        if (max(sl, sh) < minTh) continue;
         const uint32_t u0 = q[-P - 1], u1 = q[-P], u2 = q[-P + 1];
         const uint32_t c0 = q[-1], c2 = q[1];
         const uint32_t d0 = q[P - 1], d1 = q[P], d2 = q[P + 1];
@@ -318,13 +406,13 @@ __global__ void __launch_bounds__(FT_THREADS, 8) fast_cells_kernel(Geom g, const
     if (nEmit == 0) return;
     if (tid == 0) sBase = atomicAdd(&candCount[img * MAX_LEVELS + level], nEmit);
     __syncthreads();
-    uint32_t* out = cand + (size_t)img * g.candPerImg + L.candOff;
-    const int base = sBase;
+    uint32_t* out = cand + (size_t)img * candPerImg + (unsigned)lvl.z;
+    const int base = sBase, candCap = lvl.w;
     for (int i = tid; i < nAll; i += FT_THREADS) {
         const uint32_t v = clist[i];
         if (nIni > 0 && (int)(v >> 24) < iniTh) continue;
         const int o = atomicAdd(&sOut, 1);
-        if (base + o < L.candCap) out[base + o] = v;
+        if (base + o < candCap) out[base + o] = v;
     }
 }
 
@@ -740,12 +828,15 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(Geom g, const u
                                                                  orbb200_kp_t* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                  int32_t* __restrict__ counts)
 {
-    __shared__ signed char sPX[512], sPY[512];
+    __shared__ float sPX[16 * 32], sPY[16 * 32];      // [sample within the byte][lane]: conflict-free
     __shared__ int sLevel[DS_KPB], sX[DS_KPB], sY[DS_KPB], sResp[DS_KPB], sM01[DS_KPB], sM10[DS_KPB];
     __shared__ float sA[DS_KPB], sB[DS_KPB];
     const int img = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 512; i += blockDim.x) { sPX[i] = c_patX[i]; sPY[i] = c_patY[i]; }
+    for (int i = tid; i < 512; i += blockDim.x) {
+        const int o = (i & 15) * 32 + (i >> 4);
+        sPX[o] = (float)c_patX[i]; sPY[o] = (float)c_patY[i];
+    }
     // ---- phase 0: which keypoint (output order = level-major, octree list order inside a level) ----
     if (tid < DS_KPB) {
         const int gk = blockIdx.x * DS_KPB + tid;
@@ -832,10 +923,11 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(Geom g, const u
             int t[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int idx = lane * 16 + 2 * k + e;
-                const float px = (float)sPX[idx], py = (float)sPY[idx];
-                const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-                const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+                const int idx = (2 * k + e) * 32 + lane;
+                const float px = sPX[idx], py = sPY[idx];
+                // cvRound == round-half-even: adding 1.5*2^23 rounds to an integer in the float adder
+                const int yy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
+                const int xx = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
                 t[e] = bc[yy * L.pitch + xx];
             }
             val |= (t[0] < t[1]) << k;
@@ -852,21 +944,24 @@ void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t strid
     const Geom& g = c.cur->g;
     dim3 grid((g.w / 4 + 255) / 256 + 1, g.h, n);
     grid.x = ((g.w + 3) / 4 + 255) / 256;
-    import_kernel<<<grid, 256, 0, c.stream>>>(d_imgs, img_bytes, stride, c.d_pyr, g.pyrBytes, g.w, g.h, g.lv[0].pitch);
+    import_kernel<<<grid, 256, 0, c.stream>>>(d_imgs, img_bytes, stride, c.d_pyr, g.pyrBytes, g.lv[0].off, g.w, g.h, g.lv[0].pitch);
     c.launches++;
 }
 
 void launch_pyramid(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
+    const ShapeTables& st = *c.cur;
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& d = g.lv[l];
-        if (d.w <= 0 || d.h <= 0) break;
-        dim3 block(64, 4);
-        dim3 grid(((d.w + 3) / 4 + 63) / 64, (d.h + 3) / 4, n);
-        resize_kernel<<<grid, block, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, c.cur->d_xtab, c.cur->d_ytab);
+        if (d.w <= 0 || d.h <= 0 || st.resizeTileCount[l] == 0) break;
+        dim3 grid((st.resizeTileCount[l] + RS_WARPS - 1) / RS_WARPS, n);
+        resize_kernel<<<grid, RS_WARPS * 32, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
+                                                            st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l]);
         c.launches++;
     }
+    border_kernel<<<dim3(g.nlevels, n), 256, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
+    c.launches++;
 }
 
 void launch_blur(Ctx& c, int n)
@@ -884,15 +979,15 @@ void launch_fast(Ctx& c, int n)
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
     if (g.totalCells > 0) {
         const ShapeTables& st = *c.cur;
-        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap);
+        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap) + sizeof(uint16_t) * (size_t)st.fastWorkCap;
         static thread_local size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
         dim3 grid(g.totalCells, n);
-        fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(g, c.d_pyr, st.d_cells, c.d_cand, c.d_candCount,
-                                                               st.fastTileWords, st.fastScrWords, st.fastClistCap);
+        fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_cells, c.d_cand,
+                                                               c.d_candCount, st.fastTileWords, st.fastScrWords, st.fastClistCap);
         c.launches++;
     }
 }

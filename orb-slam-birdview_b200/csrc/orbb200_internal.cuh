@@ -19,6 +19,9 @@ constexpr int GRID_COLS = 64;           // include/Frame.h:40
 constexpr int GRID_ROWS = 48;           // include/Frame.h:39
 constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // src/ORBmatcher.cc:37-39
+constexpr int PYR_MARGIN_X = 32;        // bytes of reflect-101 border stored left of each level row (>= 4 used)
+constexpr int PYR_MARGIN_Y = 4;         // border rows stored above/below each level (>= 3 used)
+constexpr int RS_ROWS = 16;             // output rows per resize warp tile
 
 // Geometry of one pyramid level for one image shape (host-computed, passed to kernels by value).
 struct LevelGeom {
