@@ -179,8 +179,8 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                     const int wi = x1 - x0 - 6, hi = th - 6;
                     if (wi > 0 && hi > 0) {
                         const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1, nw = (tw + 3) >> 2;
-                        int P = npr;
-                        while (P < 2 * nw + 3) P += 32;
+                        const int P = 49;   // FT_PITCH in extract.cu
+                        (void)npr; (void)nw;
                         st.fastTileWords = std::max(st.fastTileWords, th * P);
                         st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
                         st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));

@@ -23,11 +23,15 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
     uint8_t* d = pyr + (size_t)img * pyrBytes + off0 + (size_t)y * pitch;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x4 >= w) return;
-    if (((reinterpret_cast<uintptr_t>(s) & 3) == 0) && x4 + 3 < w) {
-        *reinterpret_cast<uint32_t*>(d + x4) = __ldg(reinterpret_cast<const uint32_t*>(s + x4));
-    } else {
-        for (int i = 0; i < 4 && x4 + i < w; i++) d[x4 + i] = __ldg(s + x4 + i);
-    }
+    // source rows are rarely 4-byte aligned (stride 1241): read the two aligned words around the unaligned
+    // address and funnel-shift; the last word of the allocation is only touched when it holds needed bytes
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s + x4);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t lo = __ldg(wp);
+    const bool needHi = sh != 0 && x4 + 4 - (int)(a & 3) < w;     // bytes of the next word that lie inside the row
+    const uint32_t hi = needHi ? __ldg(wp + 1) : 0u;
+    *reinterpret_cast<uint32_t*>(d + x4) = __funnelshift_r(lo, hi, sh);   // row padding absorbs the tail
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -223,9 +227,11 @@ constexpr int FT_THREADS = 96;
 
 __device__ __forceinline__ uint32_t min3s(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3s(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
-// The same per-lane min/max on the FP16 pipe (HMNMX2): lanes are 0x6400 + byte, i.e. the positive normal
-// halves 1024..1279, whose order as halves equals their order as integers.  Used for part of the network so
-// that the integer ALU pipe (VIMNMX3) and the FMA pipe share the work.
+// The same per-lane min/max as half2 ops (HMNMX2/VHMNMX): lanes are 0x6400 + byte, i.e. the positive normal
+// halves 1024..1279, whose order as halves equals their order as integers, so the results are identical.
+// Measured on B200 (tools/ubench/pipes.cu): HMNMX2 issues to the same ALU pipe as VIMNMX (interleaving them
+// takes the sum of both times, 64 lanes/clk/SM either way; VIMNMX3 costs the same as VIMNMX; IMAD overlaps
+// fully), so splitting the network over both instruction kinds buys nothing: FT_NHALF stays 0.
 __device__ __forceinline__ uint32_t hmin2u(uint32_t a, uint32_t b)
 {
     const __half2 r = __hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
@@ -236,7 +242,8 @@ __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b)
     const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
-constexpr int FT_NHALF = 8;        // first-stage triples computed on the FP16 pipe (0..16)
+constexpr int FT_PITCH = 49;       // u32 words per shared tile row (needs >= 2*ceil(68/4)+3 = 37)
+constexpr int FT_NHALF = 0;        // first-stage triples computed with HMNMX2/VHMNMX (0..16); see note above
 constexpr uint32_t FT_BIAS = 0x64006400u;
 
 // score of the two pixels packed in `c` given the 16 ring pairs; lanes hold u8 values.
@@ -307,8 +314,10 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     const int cx0 = x0 - xa + 3, cx1 = cx0 + wi;    // inner columns in tile coordinates
     const int m0 = cx0 >> 1, m1 = (cx1 - 1) >> 1, npr = m1 - m0 + 1;
     const int nw = (tw + 3) >> 2;                   // 32-bit words loaded per row
-    int P = npr;
-    while (P < 2 * nw + 3) P += 32;                 // <= 63
+    // Row pitch of both shared tiles: 49 words.  With the usual 16-18 pairs per row the flattened
+    // (row, pair) -> lane mapping then touches (almost) disjoint banks for the rows a warp spans, and a
+    // compile-time pitch turns every ring offset into an immediate.
+    constexpr int P = FT_PITCH;
 
     if (tid == 0) { sN = 0; sNini = 0; sOut = 0; sW = 0; }
     // zero frame of the score tile: the rows above/below and the words left/right of the inner span
