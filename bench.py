@@ -529,7 +529,7 @@ def run_reference(args):
         return
     cores = host_cores()
     cpu = CpuArm(cores)
-    F = max(cores, 8) if args.ref_frames_per_step <= 0 else args.ref_frames_per_step
+    F = max(4 * cores, 16) if args.ref_frames_per_step <= 0 else args.ref_frames_per_step   # 4 frames per thread per step: keeps every core busy
     npool = min(F, 32)
     imgs = make_images(npool, 2000)
     q = cpu_queries_for(imgs, npool, NQ, 2500, cpu)
