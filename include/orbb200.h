@@ -163,6 +163,47 @@ int orbb200_search_for_triangulation(orbb200_ctx* ctx,
                                      const float* scale_factors2, const float* level_sigma2_2,
                                      int only_stereo, int check_ori, int32_t* pairs, int* npairs);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:405-520):
+ * octave-0 keypoints of F1, window around vbPrevMatched[i1] in F2's grid; prev_xy updated in place. */
+int orbb200_search_for_initialization(orbb200_ctx* ctx, const orbb200_kp_t* kps1, const uint8_t* desc1, int n1,
+                                      const orbb200_frame* F2, float* prev_xy, int window_size, float nnratio, int check_ori,
+                                      int32_t* matches12, int* nmatches);
+
+/* Generic "best descriptor in a window" search shared by the remaining projection searches.  The caller (the
+ * ORBmatcher adapter) does the geometry on the host exactly as the reference does and passes, per query, the
+ * window centre (q_x,q_y), radius q_r and level range [q_min_level,q_max_level] (reference conventions of
+ * GetFeaturesInArea: -1 = unbounded).  flags:
+ *   ORBB200_WB_BLOCK    an accepted match blocks its keypoint for later queries (loop-carried state)
+ *   ORBB200_WB_URCHECK  skip a keypoint with uRight>0 when |q_aux - uRight| > radius
+ *   ORBB200_WB_CHI2     Fuse's reprojection gate: (q_x,q_y,q_aux=ur) vs the keypoint, 5.99 / 7.8 * sigma2[level]
+ *   ORBB200_WB_ORI      rotation-histogram filter on the accepted matches (q_angle)
+ * Accept when best <= acc_th.  Covers:
+ *   SearchByProjection(Frame&,KeyFrame*,set,th,ORBdist) (:1472-1599): r=th*s[pred], levels pred-1..pred+1, BLOCK|ORI, ORBdist
+ *   SearchByProjection(KeyFrame*,Scw,points,vpMatched,th) (:290-403): levels pred-1..pred, BLOCK, TH_LOW
+ *   Fuse(KeyFrame*,points,th) / Fuse(KeyFrame*,Scw,...) (:825-1100): levels pred-1..pred, CHI2 (first form), TH_LOW, independent
+ *   SearchBySim3 (:1102-1326), each direction: levels pred-1..pred, TH_HIGH, independent, kp_blocked = vbAlreadyMatched */
+#define ORBB200_WB_BLOCK 1
+#define ORBB200_WB_URCHECK 2
+#define ORBB200_WB_CHI2 4
+#define ORBB200_WB_ORI 8
+int orbb200_search_window_best(orbb200_ctx* ctx, const orbb200_frame* F, int nq, const uint8_t* q_valid,
+                               const float* q_x, const float* q_y, const float* q_r, const int32_t* q_min_level,
+                               const int32_t* q_max_level, const uint8_t* q_desc, const float* q_aux, const float* q_angle,
+                               const uint8_t* q_obs_pos, const uint8_t* kp_blocked, const float* inv_level_sigma2,
+                               int acc_th, int flags, int32_t* out_best_idx, int32_t* out_best_dist,
+                               int32_t* out_query_of_kp, int* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:159-288) when kf_kf == 0 and
+ * ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (:522-655) when kf_kf != 0.  valid1[i]: KF1 keypoint i
+ * has a good MapPoint; valid2 (kf_kf only): same for KF2.  Feature vectors as CSR over ascending node ids.
+ * out: kf_kf == 0 -> [n2] KF keypoint index whose MapPoint each F keypoint received (-1 none);
+ *      kf_kf != 0 -> [n1] KF2 keypoint index matched to each KF1 keypoint (-1 none). */
+int orbb200_search_by_bow(orbb200_ctx* ctx, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                          const orbb200_frame* F2, const uint8_t* valid2,
+                          const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                          const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                          float nnratio, int check_ori, int kf_kf, int32_t* out, int* nmatches);
+
 /* ---- batched front-end step (bench / sequence processing) -----------------------------------------
  * One pass of the C2 hot path over a batch: extract 2*n_frames images (left,right interleaved: image 2i is
  * the left image of frame i), build the left frame's grid and run SearchByProjection of nq_per_frame

@@ -72,6 +72,9 @@ def lib(native=False):
         "oracle_birdview_match": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp]),
         "oracle_search_by_match_bird_kf": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_float, C.c_int, vp]),
         "oracle_search_by_projection_bird": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]),
+        "oracle_search_for_initialization": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp]),
+        "oracle_search_window_best": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+        "oracle_search_by_bow": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
         "oracle_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
                                                       vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
                                                       vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int, vp]),
@@ -303,3 +306,39 @@ def search_for_triangulation(kps1, desc1, uR1, has_mp1, kps2, desc2, uR2, has_mp
         _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]), _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
         _p(F12), ex, ey, _p(sf2), _p(ls2), int(only_stereo), int(check_ori), _p(pairs))
     return n, pairs[:n].copy()
+
+
+WB_BLOCK, WB_URCHECK, WB_CHI2, WB_ORI = 1, 2, 4, 8
+
+
+def search_for_initialization(kps1, desc1, F2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    kps1 = _c(kps1, KP_DTYPE)
+    desc1 = _c(desc1, np.uint8)
+    prev = np.array(prev_xy, np.float32, copy=True).reshape(-1, 2)
+    m12 = np.empty(len(kps1), np.int32)
+    n = F2._L.oracle_search_for_initialization(_p(kps1), _p(desc1), len(kps1), F2._h, _p(prev), int(window), nnratio, int(check_ori), _p(m12))
+    return n, m12, prev
+
+
+def search_window_best(F, q_valid, q_x, q_y, q_r, q_minL, q_maxL, q_desc, q_aux=None, q_angle=None, q_obs_pos=None, kp_blocked=None,
+                       inv_level_sigma2=None, acc_th=50, flags=0):
+    nq = len(q_x)
+    a = [_c(q_valid, np.uint8), _c(q_x, np.float32), _c(q_y, np.float32), _c(q_r, np.float32), _c(q_minL, np.int32), _c(q_maxL, np.int32),
+         _c(q_desc, np.uint8), _c(q_aux, np.float32), _c(q_angle, np.float32), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8),
+         _c(inv_level_sigma2, np.float32)]
+    bi, bd = np.empty(nq, np.int32), np.empty(nq, np.int32)
+    qk = np.empty(F.n, np.int32)
+    n = F._L.oracle_search_window_best(F._h, nq, *[_p(x) for x in a], int(acc_th), int(flags), _p(bi), _p(bd), _p(qk))
+    return n, bi, bd, qk
+
+
+def search_by_bow(desc1, angle1, valid1, F2, valid2, fv1, fv2, nnratio=0.7, check_ori=True, kf_kf=False):
+    desc1, angle1, valid1 = _c(desc1, np.uint8), _c(angle1, np.float32), _c(valid1, np.uint8)
+    valid2 = _c(valid2, np.uint8)
+    f1 = [_c(x, np.int32) for x in fv1]
+    f2 = [_c(x, np.int32) for x in fv2]
+    n1 = len(desc1)
+    out = np.empty(n1 if kf_kf else F2.n, np.int32)
+    n = F2._L.oracle_search_by_bow(_p(desc1), _p(angle1), _p(valid1), n1, F2._h, _p(valid2), _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]),
+                                   _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]), nnratio, int(check_ori), int(kf_kf), _p(out))
+    return n, out

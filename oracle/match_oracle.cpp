@@ -412,6 +412,143 @@ int oracle_search_by_projection_bird(const oracle_frame* F, int nq, const uint8_
     return nmatches;
 }
 
+/* src/ORBmatcher.cc:405-520: the loop BirdviewMatch(F1,F2,..,vPrevMatched,..) was copied from (identical
+ * statements on mvKeysUn/mDescriptors/GetFeaturesInArea instead of the *Bird members) */
+int oracle_search_for_initialization(const oracle_kp_t* kps1, const uint8_t* desc1, int n1, const oracle_frame* F2,
+                                     float* prev_xy, int windowSize, float nnratio, int checkOri, int32_t* vnMatches12)
+{
+    return oracle_birdview_match(kps1, desc1, n1, F2, prev_xy, windowSize, nnratio, checkOri, vnMatches12);
+}
+
+/* Generic best-only windowed search; with the host-side geometry factored out this is the common loop of
+ * SearchByProjection(Frame&,KeyFrame*,set,th,ORBdist) (:1472-1599), SearchByProjection(KeyFrame*,Scw,...) (:290-403),
+ * Fuse (:825-975, :977-1100) and each direction of SearchBySim3 (:1102-1326).  flags: 1 BLOCK, 2 URCHECK, 4 CHI2, 8 ORI */
+int oracle_search_window_best(const oracle_frame* F, int nq, const uint8_t* q_valid, const float* q_x, const float* q_y,
+                              const float* q_r, const int32_t* q_minL, const int32_t* q_maxL, const uint8_t* q_desc,
+                              const float* q_aux, const float* q_angle, const uint8_t* q_obs_pos, const uint8_t* kp_blocked,
+                              const float* invLevelSigma2, int accTh, int flags,
+                              int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp)
+{
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<uint8_t> blocked(F->N, 0);
+    if (kp_blocked) blocked.assign(kp_blocked, kp_blocked + F->N);
+    for (int i = 0; i < F->N; i++) out_query_of_kp[i] = -1;
+    std::vector<int> vIndices;
+    for (int i = 0; i < nq; i++) {
+        out_best_idx[i] = -1; out_best_dist[i] = 256;
+        if (q_valid && !q_valid[i]) continue;
+        const float u = q_x[i], v = q_y[i], radius = q_r[i];
+        F->GetFeaturesInArea(u, v, radius, q_minL[i], q_maxL[i], vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = q_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const int idx = vIndices[k];
+            if (blocked[idx]) continue;
+            if ((flags & 2) && F->uRight[idx] > 0) {
+                const float er = fabs(q_aux[i] - F->uRight[idx]);
+                if (er > radius) continue;
+            }
+            if (flags & 4) {
+                const oracle_kp_t& kp = F->keys[idx];
+                const int kpLevel = kp.octave;
+                if (F->uRight[idx] >= 0) {
+                    const float ex = u - kp.x, ey = v - kp.y, er = q_aux[i] - F->uRight[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = DescriptorDistance(dMP, &F->desc[(size_t)idx * 32]);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= accTh) {
+            out_best_idx[i] = bestIdx; out_best_dist[i] = bestDist;
+            out_query_of_kp[bestIdx] = i;
+            if (flags & 1) blocked[bestIdx] = q_obs_pos ? q_obs_pos[i] : 1;
+            nmatches++;
+            if (flags & 8) rotHist[rot_bin(q_angle[i], F->keys[bestIdx].angle)].push_back(bestIdx);
+        }
+    }
+    if (flags & 8) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) { out_query_of_kp[rotHist[i][j]] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+/* src/ORBmatcher.cc:159-288 (kf_kf == 0) and :522-655 (kf_kf != 0) */
+int oracle_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                         const oracle_frame* F2, const uint8_t* valid2,
+                         const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                         const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                         float nnratio, int checkOri, int kf_kf, int32_t* out)
+{
+    int nmatches = 0;
+    const int n2 = F2->N;
+    std::vector<int> vpMapPointMatches(n2, -1);     /* (KF,F): KF index whose MapPoint the F keypoint received */
+    std::vector<int> vpMatches12(n1, -1);           /* (KF,KF) */
+    std::vector<bool> vbMatched2(n2, false);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int f1 = 0, f2 = 0;
+    while (f1 < nn1 && f2 < nn2) {
+        if (fv1_node[f1] == fv2_node[f2]) {
+            for (int i1 = fv1_ptr[f1]; i1 < fv1_ptr[f1 + 1]; i1++) {
+                const int idx1 = fv1_idx[i1];
+                if (!valid1[idx1]) continue;
+                const uint8_t* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = fv2_ptr[f2]; i2 < fv2_ptr[f2 + 1]; i2++) {
+                    const int idx2 = fv2_idx[i2];
+                    if (kf_kf) {
+                        if (vbMatched2[idx2] || !(valid2 ? valid2[idx2] : 1)) continue;
+                    } else {
+                        if (vpMapPointMatches[idx2] >= 0) continue;
+                    }
+                    const int dist = DescriptorDistance(d1, &F2->desc[(size_t)idx2 * 32]);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                const bool th = kf_kf ? (bestDist1 < TH_LOW) : (bestDist1 <= TH_LOW);
+                if (th) {
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        if (kf_kf) { vpMatches12[idx1] = bestIdx2; vbMatched2[bestIdx2] = true; }
+                        else vpMapPointMatches[bestIdx2] = idx1;
+                        if (checkOri) rotHist[rot_bin(angle1[idx1], F2->keys[bestIdx2].angle)].push_back(kf_kf ? idx1 : bestIdx2);
+                        nmatches++;
+                    }
+                }
+            }
+            f1++; f2++;
+        } else if (fv1_node[f1] < fv2_node[f2]) {
+            while (f1 < nn1 && fv1_node[f1] < fv2_node[f2]) f1++;
+        } else {
+            while (f2 < nn2 && fv2_node[f2] < fv1_node[f1]) f2++;
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) {
+                if (kf_kf) vpMatches12[rotHist[i][j]] = -1; else vpMapPointMatches[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    if (kf_kf) for (int i = 0; i < n1; i++) out[i] = vpMatches12[i];
+    else for (int i = 0; i < n2; i++) out[i] = vpMapPointMatches[i];
+    return nmatches;
+}
+
 /* ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:140-157 */
 static bool CheckDistEpipolarLine(const oracle_kp_t& kp1, const oracle_kp_t& kp2, const float* F12, const float* levelSigma2_2)
 {

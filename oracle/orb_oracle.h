@@ -124,6 +124,23 @@ int oracle_search_by_projection_bird(const oracle_frame* F, int nq, const uint8_
                                      const uint8_t* q_obs_pos, const uint8_t* kp_blocked, float r, float nnratio,
                                      int32_t* out_query_of_kp /*[n]*/);
 
+/* ORBmatcher::SearchForInitialization (:405-520) */
+int oracle_search_for_initialization(const oracle_kp_t* kps1, const uint8_t* desc1, int n1, const oracle_frame* F2,
+                                     float* prev_xy, int windowSize, float nnratio, int checkOri, int32_t* vnMatches12);
+/* common loop of SearchByProjection(Frame&,KeyFrame*,set,..) (:1472-1599), SearchByProjection(KeyFrame*,Scw,..) (:290-403),
+ * Fuse (:825-1100), SearchBySim3 directions (:1102-1326) after the host geometry; flags: 1 BLOCK, 2 URCHECK, 4 CHI2, 8 ORI */
+int oracle_search_window_best(const oracle_frame* F, int nq, const uint8_t* q_valid, const float* q_x, const float* q_y,
+                              const float* q_r, const int32_t* q_minL, const int32_t* q_maxL, const uint8_t* q_desc,
+                              const float* q_aux, const float* q_angle, const uint8_t* q_obs_pos, const uint8_t* kp_blocked,
+                              const float* invLevelSigma2, int accTh, int flags,
+                              int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp);
+/* ORBmatcher::SearchByBoW(KeyFrame*,Frame&,..) (:159-288; kf_kf == 0) / (KeyFrame*,KeyFrame*,..) (:522-655; kf_kf != 0) */
+int oracle_search_by_bow(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                         const oracle_frame* F2, const uint8_t* valid2,
+                         const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                         const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                         float nnratio, int checkOri, int kf_kf, int32_t* out);
+
 /* ORBmatcher::SearchForTriangulation(KF1,KF2,F12,pairs,bOnlyStereo) (:657-823).
  * Feature vectors are given as CSR over shared-vocabulary node ids sorted ascending:
  * fv?_node[nn?], fv?_ptr[nn?+1], fv?_idx[...].  has_mp?: keypoint already has a MapPoint.

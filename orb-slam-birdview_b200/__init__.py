@@ -72,6 +72,9 @@ _SIGNATURES = {
     "orbb200_search_by_projection_bird": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, C.POINTER(_i)]),
     "orbb200_search_for_triangulation": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i,
                                               _vp, _f, _f, _vp, _vp, _i, _i, _vp, C.POINTER(_i)]),
+    "orbb200_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _i, _vp, C.POINTER(_i)]),
+    "orbb200_search_window_best": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_search_by_bow": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _i, _i, _vp, C.POINTER(_i)]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "orbb200_stage_timing": (_i, [_vp, _i]),
@@ -375,3 +378,44 @@ class ORBmatcher:
             _p(F12), ex, ey, _p(sf2), _p(ls2), int(bOnlyStereo), int(self.mbCheckOrientation), _p(pairs), C.byref(npairs)),
             "SearchForTriangulation")
         return npairs.value, pairs[:npairs.value].copy()
+
+    WB_BLOCK, WB_URCHECK, WB_CHI2, WB_ORI = 1, 2, 4, 8
+
+    def SearchForInitialization(self, kps1, desc1, F2, vbPrevMatched, windowSize=100):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:405-520)"""
+        kps1, desc1 = _c(kps1, KP_DTYPE), _c(desc1, np.uint8)
+        prev = np.array(vbPrevMatched, np.float32, copy=True).reshape(-1, 2)
+        m12 = np.full(max(len(kps1), 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_for_initialization(self.ctx._h, _p(kps1), _p(desc1), len(kps1), F2._h, _p(prev), int(windowSize),
+                                                                 self.mfNNratio, int(self.mbCheckOrientation), _p(m12), C.byref(nm)),
+                       "SearchForInitialization")
+        return nm.value, m12[:len(kps1)], prev
+
+    def search_window_best(self, F, q_valid, q_x, q_y, q_r, q_minL, q_maxL, q_desc, q_aux=None, q_angle=None, q_obs_pos=None,
+                           kp_blocked=None, inv_level_sigma2=None, acc_th=50, flags=0):
+        """Generic best-in-window search behind SearchByProjection(Frame,KF,set) / (KF,Scw), Fuse, SearchBySim3
+        (include/orbb200.h: orbb200_search_window_best)."""
+        nq = len(q_x)
+        a = [_c(q_valid, np.uint8), _c(q_x, np.float32), _c(q_y, np.float32), _c(q_r, np.float32), _c(q_minL, np.int32), _c(q_maxL, np.int32),
+             _c(q_desc, np.uint8), _c(q_aux, np.float32), _c(q_angle, np.float32), _c(q_obs_pos, np.uint8), _c(kp_blocked, np.uint8),
+             _c(inv_level_sigma2, np.float32)]
+        bi, bd = np.empty(nq, np.int32), np.empty(nq, np.int32)
+        qk = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_window_best(self.ctx._h, F._h, nq, *[_p(x) for x in a], int(acc_th), int(flags),
+                                                          _p(bi), _p(bd), _p(qk), C.byref(nm)), "search_window_best")
+        return nm.value, bi, bd, qk[:F.n]
+
+    def SearchByBoW(self, desc1, angle1, valid1, F2, fv1, fv2, valid2=None, kf_kf=False):
+        """SearchByBoW(KeyFrame*, Frame&, ..) (src/ORBmatcher.cc:159-288) / (KeyFrame*, KeyFrame*, ..) (:522-655)"""
+        desc1, angle1, valid1, valid2 = _c(desc1, np.uint8), _c(angle1, np.float32), _c(valid1, np.uint8), _c(valid2, np.uint8)
+        f1 = [_c(x, np.int32) for x in fv1]
+        f2 = [_c(x, np.int32) for x in fv2]
+        n1 = len(desc1)
+        out = np.full(max(n1 if kf_kf else F2.n, 1), -1, np.int32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_search_by_bow(self.ctx._h, _p(desc1), _p(angle1), _p(valid1), n1, F2._h, _p(valid2),
+                                                     _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]), _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]),
+                                                     self.mfNNratio, int(self.mbCheckOrientation), int(kf_kf), _p(out), C.byref(nm)), "SearchByBoW")
+        return nm.value, out[:(n1 if kf_kf else F2.n)]

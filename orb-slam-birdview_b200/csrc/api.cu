@@ -706,6 +706,8 @@ struct QueryHost {
     const uint8_t* valid = nullptr; const float* x = nullptr; const float* y = nullptr; const float* aux = nullptr;
     const int32_t* level = nullptr; const float* viewcos = nullptr; const float* angle = nullptr;
     const uint8_t* desc = nullptr; const uint8_t* obs_pos = nullptr; const uint8_t* kp_blocked = nullptr;
+    const float* r = nullptr; const int32_t* maxlevel = nullptr; const int32_t* cand_idx = nullptr; int n_cand = 0;
+    const float* inv_sigma2 = nullptr; int acc_th = 0, flags = 0;
 };
 
 // Upload one job's queries, run it, return device pointers of the outputs inside the scratch arena.
@@ -714,7 +716,8 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
                    int32_t* h_best_idx, int32_t* h_best_dist, int32_t* h_per_kp, int32_t* h_per_query, int* h_nmatches)
 {
     const int nq = Q.nq, kpCap = std::max(F->cap, 1);
-    const size_t need = (size_t)nq * (32 + 4 * 6 + 2 + 4 * 3) + (size_t)kpCap * (1 + 4) + win_scratch_ints(kpCap, nq) * 4 + 64 * 256 + sizeof(WinJob);
+    const size_t need = (size_t)nq * (32 + 4 * 8 + 2 + 4 * 3) + (size_t)kpCap * (1 + 4) + (size_t)Q.n_cand * 4 + win_scratch_ints(kpCap, nq) * 4 +
+                        80 * 256 + sizeof(WinJob);
     if (!ensure_scratch(c, need, 0)) return ORBB200_ERR_CUDA;
     Arena A(c.d_scratch, c.d_scratch_bytes);
     WinJob J{};
@@ -737,7 +740,11 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     J.scaleFactors = dsf;
     J.q_valid = upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
     if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
-    J.q_viewcos = upF(Q.viewcos); J.q_angle = upF(Q.angle);
+    J.q_viewcos = upF(Q.viewcos); J.q_angle = upF(Q.angle); J.q_r = upF(Q.r);
+    if (Q.maxlevel) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.maxlevel, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_maxlevel = d; }
+    if (Q.cand_idx && Q.n_cand > 0) { int32_t* d = A.take<int32_t>(Q.n_cand); cudaMemcpyAsync(d, Q.cand_idx, 4 * (size_t)Q.n_cand, cudaMemcpyHostToDevice, c.stream); J.cand_idx = d; }
+    if (Q.inv_sigma2) { float* d = A.take<float>(MAX_LEVELS); cudaMemcpyAsync(d, Q.inv_sigma2, sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream); J.invLevelSigma2 = d; }
+    J.accTh = Q.acc_th; J.flags = Q.flags;
     J.q_desc = upB(Q.desc, (size_t)nq * 32); J.q_obs_pos = upB(Q.obs_pos, nq); J.kp_blocked = upB(Q.kp_blocked, F->cap);
     J.scratch = A.take<int>(win_scratch_ints(kpCap, nq));
     J.out_best_idx = A.take<int32_t>(nq); J.out_best_dist = A.take<int32_t>(nq);
@@ -898,6 +905,86 @@ int orbb200_search_for_triangulation(orbb200_ctx* ctx,
         ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
     }
     *npairs = np;
+    return ORBB200_OK;
+}
+
+int orbb200_search_for_initialization(orbb200_ctx* ctx, const orbb200_kp_t* kps1, const uint8_t* desc1, int n1,
+                                      const orbb200_frame* F2, float* prev_xy, int window_size, float nnratio, int check_ori,
+                                      int32_t* matches12, int* nmatches)
+{
+    // SearchForInitialization (:405-520) is the loop BirdviewMatch(F1,F2,..,vPrevMatched,..) (:1667-1786) was copied
+    // from: octave-0 keypoints of F1, window around vbPrevMatched in F2's grid, same acceptance and stealing
+    if (ctx && !prev_xy) { ctx->c.err = "search_for_initialization: prev_xy required"; return ORBB200_ERR_ARG; }
+    return orbb200_birdview_match(ctx, kps1, desc1, n1, F2, prev_xy, window_size, nnratio, check_ori, matches12, nmatches);
+}
+
+int orbb200_search_window_best(orbb200_ctx* ctx, const orbb200_frame* F, int nq, const uint8_t* q_valid,
+                               const float* q_x, const float* q_y, const float* q_r, const int32_t* q_min_level,
+                               const int32_t* q_max_level, const uint8_t* q_desc, const float* q_aux, const float* q_angle,
+                               const uint8_t* q_obs_pos, const uint8_t* kp_blocked, const float* inv_level_sigma2,
+                               int acc_th, int flags, int32_t* out_best_idx, int32_t* out_best_dist,
+                               int32_t* out_query_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    const bool ori = (flags & ORBB200_WB_ORI) != 0;
+    if (!F || nq < 0 || (nq > 0 && (!q_x || !q_y || !q_r || !q_min_level || !q_max_level || !q_desc)) ||
+        ((flags & (ORBB200_WB_URCHECK | ORBB200_WB_CHI2)) && nq > 0 && !q_aux) || ((flags & ORBB200_WB_CHI2) && !inv_level_sigma2) ||
+        (ori && nq > 0 && !q_angle)) {
+        c.err = "search_window_best: bad argument"; return ORBB200_ERR_ARG;
+    }
+    QueryHost Q; Q.nq = nq; Q.valid = q_valid; Q.x = q_x; Q.y = q_y; Q.r = q_r; Q.level = q_min_level; Q.maxlevel = q_max_level;
+    Q.desc = q_desc; Q.aux = q_aux; Q.angle = q_angle; Q.obs_pos = q_obs_pos; Q.kp_blocked = kp_blocked; Q.inv_sigma2 = inv_level_sigma2;
+    Q.acc_th = acc_th;
+    Q.flags = ((flags & ORBB200_WB_BLOCK) ? WF_BLOCK : 0) | ((flags & ORBB200_WB_URCHECK) ? WF_URCHECK : 0) | ((flags & ORBB200_WB_CHI2) ? WF_CHI2 : 0);
+    return run_window_job(c, F, Q, WM_BEST, 0, ori ? 1 : 0, 0.f, 0.f, 0.f, out_best_idx, out_best_dist, out_query_of_kp, nullptr, nmatches);
+}
+
+int orbb200_search_by_bow(orbb200_ctx* ctx, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                          const orbb200_frame* F2, const uint8_t* valid2,
+                          const int32_t* fv1_node, const int32_t* fv1_ptr, const int32_t* fv1_idx, int nn1,
+                          const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
+                          float nnratio, int check_ori, int kf_kf, int32_t* out, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F2 || n1 < 0 || !out || !nmatches || (n1 > 0 && (!desc1 || !valid1 || (check_ori && !angle1))) ||
+        (nn1 > 0 && (!fv1_node || !fv1_ptr || !fv1_idx)) || (nn2 > 0 && (!fv2_node || !fv2_ptr || !fv2_idx))) {
+        c.err = "search_by_bow: bad argument"; return ORBB200_ERR_ARG;
+    }
+    // queries in the reference's visiting order: shared nodes ascending, KF1 indices in node order (:178-255)
+    std::vector<int32_t> qidx1, qb, qe;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (fv1_node[a] == fv2_node[b]) {
+            for (int i = fv1_ptr[a]; i < fv1_ptr[a + 1]; i++) {
+                const int idx1 = fv1_idx[i];
+                if (!valid1[idx1]) continue;                      // no MapPoint / bad MapPoint (:189-195)
+                qidx1.push_back(idx1); qb.push_back(fv2_ptr[b]); qe.push_back(fv2_ptr[b + 1]);
+            }
+            a++; b++;
+        } else if (fv1_node[a] < fv2_node[b]) a++;
+        else b++;
+    }
+    const int nq = (int)qidx1.size();
+    std::vector<uint8_t> qdesc((size_t)std::max(nq, 1) * 32);
+    std::vector<float> qang(std::max(nq, 1), 0.f);
+    for (int q = 0; q < nq; q++) { memcpy(&qdesc[(size_t)q * 32], desc1 + (size_t)qidx1[q] * 32, 32); if (angle1) qang[q] = angle1[qidx1[q]]; }
+    QueryHost Q; Q.nq = nq; Q.level = qb.data(); Q.maxlevel = qe.data(); Q.desc = qdesc.data(); Q.angle = qang.data();
+    Q.kp_blocked = kf_kf ? valid2 : nullptr;   // inverted below: kp_blocked means "not a candidate"
+    std::vector<uint8_t> inv;
+    if (kf_kf && valid2) { inv.resize(std::max(F2->cap, 1)); for (int i = 0; i < F2->cap; i++) inv[i] = !valid2[i]; Q.kp_blocked = inv.data(); }
+    Q.cand_idx = fv2_idx; Q.n_cand = nn2 > 0 ? fv2_ptr[nn2] : 0;
+    std::vector<int32_t> perKp(std::max(F2->cap, 1)), perQ(std::max(nq, 1));
+    int nm = 0;
+    int rc = ORBB200_OK;
+    if (nq > 0) rc = run_window_job(c, F2, Q, kf_kf ? WM_BOW_KF_KF : WM_BOW_KF_F, 0, check_ori, 0.f, nnratio, 0.f, nullptr, nullptr, perKp.data(), perQ.data(), &nm);
+    if (rc != ORBB200_OK) return rc;
+    if (kf_kf) {
+        for (int i = 0; i < n1; i++) out[i] = -1;                                   // vpMatches12 as KF2 keypoint indices
+        for (int q = 0; q < nq; q++) if (perQ[q] >= 0) out[qidx1[q]] = perQ[q];
+    } else {
+        for (int i = 0; i < F2->cap; i++) out[i] = (nq > 0 && perKp[i] >= 0) ? qidx1[perKp[i]] : -1;   // vpMapPointMatches as KF keypoint indices
+    }
+    *nmatches = nm;
     return ORBB200_OK;
 }
 

@@ -283,6 +283,9 @@ __device__ void three_maxima(const int* histo, int& ind1, int& ind2, int& ind3)
 constexpr int WM_THREADS = 512;
 constexpr int WC_THREADS = 128;
 
+__device__ __forceinline__ bool is_dist_sem(int mode) { return mode == WM_BIRD || mode == WM_BIRD_KF; }
+__device__ __forceinline__ bool is_bow(int mode) { return mode == WM_BOW_KF_F || mode == WM_BOW_KF_KF; }
+
 // Per-mode search window of query q (reference: SearchByProjection :62-69, :1385-1398; BirdviewMatch :1684-1688,
 // :1807; SearchByMatchBird :2029; SearchByProjectionBird :1948).  Returns false when the query is skipped.
 struct Window { float x, y, r, urRef, urTol; int minL, maxL; bool urCheck; };
@@ -291,8 +294,9 @@ __device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
 {
     if (J.q_valid != nullptr && !J.q_valid[q]) return false;
     W.minL = -1; W.maxL = -1; W.urCheck = false; W.urRef = 0.f; W.urTol = 0.f;
-    W.x = J.q_x[q]; W.y = J.q_y[q];
     const int mode = J.mode;
+    if (is_bow(mode)) return true;
+    W.x = J.q_x[q]; W.y = J.q_y[q];
     if (mode == WM_PROJ) {
         const int lvl = J.q_level[q];
         float r = J.q_viewcos[q] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
@@ -311,15 +315,65 @@ __device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
         const int lvl = J.q_level[q];
         if (J.levelMode == 1 && lvl > 0) return false;                  // prevMatched variant: octave 0 only
         W.r = J.th; W.minL = lvl; W.maxL = lvl;
+    } else if (mode == WM_BEST) {
+        // generic best-only search: per-query radius and level range from the host adapter
+        W.r = J.q_r[q]; W.minL = J.q_level[q]; W.maxL = J.q_maxlevel[q];
+        if (J.flags & WF_URCHECK) { W.urCheck = true; W.urRef = J.q_aux[q]; W.urTol = W.r; }
     } else {   // WM_BIRD_KF, WM_PROJ_BIRD
         W.r = J.th;
     }
     return true;
 }
 
-// Phase 1 (fully parallel, thread per query): scan the window once, apply every filter that does not depend
-// on the loop-carried state (level, window, initial kp_blocked, uRight) and cache (index, distance | level<<16)
-// of the survivors in scan order.  Queries with more than WM_LISTCAP survivors are re-scanned in phase 2.
+// Enumerate, in the reference's scan order, the candidates of query q that pass every filter which does not
+// depend on the loop-carried state, with their Hamming distance: visit(idx, dist, octave).
+template <class Visit>
+__device__ __forceinline__ void static_candidates(const WinJob& J, const FrameDev& F, int q, const Window& W, Visit&& visit)
+{
+    const int mode = J.mode;
+    const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
+    const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+    if (is_bow(mode)) {
+        // SearchByBoW (:159-288, :522-655): every keypoint of the same vocabulary node, node list order
+        for (int p = J.q_level[q]; p < J.q_maxlevel[q]; p++) {
+            const int idx = J.cand_idx[p];
+            if (J.kp_blocked && J.kp_blocked[idx]) continue;         // (KF,KF): no / bad MapPoint on the KF2 keypoint
+            const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
+            visit(idx, hamming256(qa, qb, kd[0], kd[1]), 0);
+        }
+        return;
+    }
+    const bool distSem = is_dist_sem(mode);
+    scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
+        if (!distSem) {
+            if (J.kp_blocked && J.kp_blocked[idx]) return;
+            if (W.urCheck && F.uRight) {
+                const float ur = F.uRight[idx];
+                if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
+            }
+            if (mode == WM_BEST && (J.flags & WF_CHI2)) {
+                // reprojection gate of Fuse (:913-936): 7.8 with a stereo observation, 5.99 without
+                const float ex = __fsub_rn(W.x, kp.x), ey = __fsub_rn(W.y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                const float kpr = F.uRight ? F.uRight[idx] : -1.f;
+                const float inv = J.invLevelSigma2[kp.octave];
+                if (kpr >= 0) {
+                    const float er = __fsub_rn(J.q_aux[q], kpr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, inv) > 7.8) return;
+                } else {
+                    if ((double)__fmul_rn(e2, inv) > 5.99) return;
+                }
+            }
+        }
+        const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
+        visit(idx, hamming256(qa, qb, kd[0], kd[1]), kp.octave);
+    });
+}
+
+// Phase 1 (fully parallel, thread per query): enumerate the static candidates once and cache
+// (index, distance | level<<16) in scan order.  Queries with more than WM_LISTCAP survivors are re-scanned
+// in phase 2.
 __global__ void __launch_bounds__(WC_THREADS) window_cands_kernel(const WinJob* __restrict__ jobs)
 {
     const WinJob J = jobs[blockIdx.y];
@@ -329,26 +383,13 @@ __global__ void __launch_bounds__(WC_THREADS) window_cands_kernel(const WinJob* 
     int* ccount = J.scratch + 2 * J.kpCap + 6 * J.nq;
     int2* clist = reinterpret_cast<int2*>(J.scratch + win_clist_offset(J.kpCap, J.nq)) + (size_t)q * WM_LISTCAP;
     Window W;
-    int n = 0;
+    int n = -1;     // skipped query
     if (query_window(J, q, W)) {
-        const bool distSem = (J.mode == WM_BIRD || J.mode == WM_BIRD_KF);
-        const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
-        const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
-        scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
-            if (!distSem) {
-                if (J.kp_blocked && J.kp_blocked[idx]) return;
-                if (W.urCheck && F.uRight) {
-                    const float ur = F.uRight[idx];
-                    if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
-                }
-            }
-            const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
-            const int d = hamming256(qa, qb, kd[0], kd[1]);
-            if (n < WM_LISTCAP) clist[n] = make_int2(idx, d | (kp.octave << 16));
+        n = 0;
+        static_candidates(J, F, q, W, [&](int idx, int d, int level) {
+            if (n < WM_LISTCAP) clist[n] = make_int2(idx, d | (level << 16));
             n++;
         });
-    } else {
-        n = -1;     // skipped query
     }
     ccount[q] = n;
 }
@@ -364,7 +405,8 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     const int nq = J.nq;
     const int tid = threadIdx.x;
     const int mode = J.mode;
-    const bool distSem = (mode == WM_BIRD || mode == WM_BIRD_KF);
+    const bool distSem = is_dist_sem(mode);
+    const bool independent = (mode == WM_BEST) && !(J.flags & WF_BLOCK);    // Fuse / SearchBySim3: no loop-carried state
 
     int* owner = J.scratch;                 // [kpCap] BLOCK: min blocking query; DIST: head of claimant list
     int* lastOwner = owner + J.kpCap;       // [kpCap] max accepted query per keypoint
@@ -407,30 +449,23 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
                         consider(e.x, e.y & 0xffff, e.y >> 16);
                     }
                 } else {
-                    // overflow: re-scan the window (same filters as phase 1)
-                    Window W;
+                    Window W;               // overflow: enumerate again (same filters as phase 1)
                     query_window(J, q, W);
-                    const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
-                    const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
-                    scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
-                        if (!distSem) {
-                            if (J.kp_blocked && J.kp_blocked[idx]) return;
-                            if (W.urCheck && F.uRight) {
-                                const float ur = F.uRight[idx];
-                                if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
-                            }
-                        }
-                        const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
-                        consider(idx, hamming256(qa, qb, kd[0], kd[1]), kp.octave);
-                    });
+                    static_candidates(J, F, q, W, consider);
                 }
                 bool acc;
                 if (mode == WM_PROJ || mode == WM_PROJ_BIRD)
                     acc = best <= TH_HIGH && !(bestLevel == secondLevel && (float)best > __fmul_rn(J.nnratio, (float)second));
                 else if (mode == WM_PROJ_FRAME)
                     acc = best <= TH_HIGH;
+                else if (mode == WM_BEST)
+                    acc = best <= J.accTh;
                 else if (mode == WM_BIRD)
                     acc = best <= TH_LOW && (float)best < __fmul_rn((float)second, J.nnratio);
+                else if (mode == WM_BOW_KF_F)
+                    acc = best <= TH_LOW && (float)best < __fmul_rn(J.nnratio, (float)second);     // :228-230
+                else if (mode == WM_BOW_KF_KF)
+                    acc = best < TH_LOW && (float)best < __fmul_rn(J.nnratio, (float)second);      // :593-595
                 else
                     acc = best <= TH_HIGH && (bestLevel != secondLevel || (float)best < __fmul_rn((float)second, J.nnratio));
                 if (acc) { selIdx = bestIdx; selDist = best; }
@@ -442,6 +477,7 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
         const int any = __syncthreads_or(changed);
         if (!any) break;
         for (int q = tid; q < nq; q += WM_THREADS) { choice[q] = newChoice[q]; cdist[q] = newCdist[q]; }
+        if (independent) { __syncthreads(); break; }
         for (int i = tid; i < nkp; i += WM_THREADS) owner[i] = distSem ? -1 : 0x7fffffff;
         __syncthreads();
         for (int q = tid; q < nq; q += WM_THREADS) {
@@ -499,6 +535,19 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
         if (tid == 0) sCount = 0;
         __syncthreads();
         if (owned) atomicAdd(&sCount, owned);
+        if (removed) atomicAdd(&sRemoved, removed);
+        __syncthreads();
+        if (tid == 0) *J.out_nmatches = sCount - sRemoved;
+        return;
+    }
+    if (mode == WM_BOW_KF_KF) {
+        // vpMatches12[idx1] (:597, :643-647): per query, cleared when its rotation bin is discarded
+        int removed = 0;
+        for (int q = tid; q < nq; q += WM_THREADS) {
+            int m = choice[q];
+            if (m >= 0 && J.checkOri) { const int b = qbin[q]; if (b != k1 && b != k2 && b != k3) { m = -1; removed++; } }
+            J.out_per_query[q] = m;
+        }
         if (removed) atomicAdd(&sRemoved, removed);
         __syncthreads();
         if (tid == 0) *J.out_nmatches = sCount - sRemoved;

@@ -4,7 +4,8 @@
 
 namespace orbb200 {
 
-enum WinMode { WM_PROJ = 0, WM_PROJ_FRAME = 1, WM_BIRD = 2, WM_BIRD_KF = 3, WM_PROJ_BIRD = 4 };
+enum WinMode { WM_PROJ = 0, WM_PROJ_FRAME = 1, WM_BIRD = 2, WM_BIRD_KF = 3, WM_PROJ_BIRD = 4, WM_BOW_KF_F = 5, WM_BOW_KF_KF = 6, WM_BEST = 7 };
+enum WinFlags { WF_BLOCK = 1, WF_URCHECK = 2, WF_CHI2 = 4 };
 
 // One windowed-search call (all pointers are device pointers).
 struct WinJob {
@@ -16,6 +17,11 @@ struct WinJob {
     const float* q_x;
     const float* q_y;
     const float* q_aux;         // WM_PROJ: projected uR; WM_PROJ_FRAME: 1/z
+    int accTh, flags;           // WM_BEST: acceptance threshold, WinFlags
+    const float* q_r;           // WM_BEST: per-query radius
+    const int32_t* q_maxlevel;  // WM_BEST: max level (q_level = min level); BoW modes: end of the candidate range (q_level = begin)
+    const int32_t* cand_idx;    // BoW modes: keypoint indices of the second frame grouped by vocabulary node
+    const float* invLevelSigma2;   // WF_CHI2
     const int32_t* q_level;     // predicted level / octave
     const float* q_viewcos;     // WM_PROJ
     const float* q_angle;       // rotation histogram

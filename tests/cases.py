@@ -122,3 +122,46 @@ def triangulation_case(n1, n2, w, h, seed, n_nodes=60):
     sigma2 = (SCALE_FACTORS * SCALE_FACTORS).astype(np.float32)
     return dict(k1=k1, d1=d1, uR1=uR1, has1=has1, k2=k2, d2=d2, uR2=uR2, has2=has2, fv1=csr(node1), fv2=csr(node2),
                 F12=F12, ex=np.float32(w * 0.5), ey=np.float32(h * 0.5), sf2=SCALE_FACTORS, sigma2=sigma2)
+
+
+def csr_from_nodes(nodes):
+    """node id per keypoint -> (ascending ids, ptr, idx) = DBoW2::FeatureVector as CSR"""
+    ids = np.unique(nodes)
+    ptr, idx = [0], []
+    for nid in ids:
+        idx.extend(np.nonzero(nodes == nid)[0].tolist())
+        ptr.append(len(idx))
+    return ids.astype(np.int32), np.array(ptr, np.int32), np.array(idx, np.int32)
+
+
+def csr_to_dict(fv):
+    return {int(n): fv[2][fv[1][i]:fv[1][i + 1]].tolist() for i, n in enumerate(fv[0])}
+
+
+def bow_case(n1, n2, w, h, seed, n_nodes=80, max_flips=25):
+    """Two keyframes sharing vocabulary nodes: KF2 keypoints are perturbed copies of KF1 keypoints placed
+    (mostly) in the same node, plus distractors; some nodes exist on one side only."""
+    rng = np.random.default_rng(seed)
+    k1, d1, _, grid = frame_case(n1, w, h, seed)
+    src = rng.integers(0, n1, n2)
+    k2 = k1[src].copy()
+    k2["angle"] = (k2["angle"] + rng.normal(0, 6, n2).astype(np.float32)) % np.float32(360)
+    d2 = synth.perturb_descriptors(d1[src], max_flips, seed + 3)
+    rnd = rng.random(n2) < 0.25
+    d2[rnd] = synth.synth_descriptors(int(rnd.sum()), seed + 4)
+    node1 = rng.integers(0, n_nodes, n1)
+    node2 = np.where(rng.random(n2) < 0.85, node1[src], rng.integers(0, n_nodes, n2))
+    node1 = np.where(node1 % 9 == 4, node1 + n_nodes, node1)
+    node2 = np.where(node2 % 13 == 6, node2 + 2 * n_nodes, node2)
+    valid1 = (rng.random(n1) < 0.7).astype(np.uint8)
+    valid2 = (rng.random(n2) < 0.8).astype(np.uint8)
+    return dict(k1=k1, d1=d1, k2=k2, d2=d2, fv1=csr_from_nodes(node1), fv2=csr_from_nodes(node2), valid1=valid1, valid2=valid2, grid=grid)
+
+
+def best_window_queries(kps, desc, u_right, w, h, nq, seed, th):
+    """Projected map points with a predicted level (SearchByProjection(Frame,KF,set) / (KF,Scw) / Fuse style)"""
+    q = projection_queries(kps, desc, u_right, w, h, nq, seed, jitter=2.0)
+    pred = q["level"]
+    r = (np.float32(th) * SCALE_FACTORS[pred]).astype(np.float32)
+    ur = (q["u"] - np.float32(12.0) * q["invz"]).astype(np.float32)
+    return dict(valid=q["valid"], u=q["u"], v=q["v"], pred=pred, r=r, ur=ur, angle=q["angle"], desc=q["desc"], obs_pos=q["obs_pos"])

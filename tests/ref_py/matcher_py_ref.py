@@ -367,3 +367,211 @@ def search_for_triangulation(kps1, desc1, uR1, has_mp1, kps2, desc2, uR2, has_mp
                 nm -= 1
     pairs = [(i, m12[i]) for i in range(len(kps1)) if m12[i] >= 0]
     return nm, pairs
+
+
+# ---- second batch: literal transcriptions of the remaining ORBmatcher scans (after the host-side geometry) ----
+def search_for_initialization(kps1, desc1, F2, prev_xy, window, nnratio, check_ori):
+    """src/ORBmatcher.cc:405-520"""
+    n1 = len(kps1)
+    m12 = [-1] * n1
+    m21 = [-1] * F2.n
+    md = [INT_MAX] * F2.n
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    nm = 0
+    prev = np.array(prev_xy, F32).reshape(-1, 2)
+    for i1 in range(n1):
+        l1 = int(kps1["octave"][i1])
+        if l1 > 0:
+            continue
+        idxs = F2.features_in_area(prev[i1, 0], prev[i1, 1], window, l1, l1)
+        if not idxs:
+            continue
+        bd, bd2, bi = INT_MAX, INT_MAX, -1
+        for i2 in idxs:
+            d = descriptor_distance(desc1[i1], F2.desc[i2])
+            if md[i2] <= d:
+                continue
+            if d < bd:
+                bd2, bd, bi = bd, d, i2
+            elif d < bd2:
+                bd2 = d
+        if bd <= TH_LOW and F32(bd) < F32(F32(bd2) * F32(nnratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1
+                nm -= 1
+            m12[i1] = bi
+            m21[bi] = i1
+            md[bi] = bd
+            nm += 1
+            if check_ori:
+                hist[rot_bin(kps1["angle"][i1], F2.kps["angle"][bi])].append(i1)
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    nm -= 1
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev[i1, 0] = F2.kps["x"][m12[i1]]
+            prev[i1, 1] = F2.kps["y"][m12[i1]]
+    return nm, m12, prev
+
+
+def search_by_projection_kf(Cur, sf, q_valid, q_u, q_v, q_pred, q_angle, q_desc, kp_has_mp, th, orb_dist, check_ori):
+    """SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist), src/ORBmatcher.cc:1472-1599, after projection"""
+    has = [bool(b) for b in kp_has_mp]
+    out = [-1] * Cur.n
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    nm = 0
+    for i in range(len(q_u)):
+        if not q_valid[i]:
+            continue
+        p = int(q_pred[i])
+        radius = F32(F32(th) * F32(sf[p]))
+        idxs = Cur.features_in_area(q_u[i], q_v[i], radius, p - 1, p + 1)
+        if not idxs:
+            continue
+        bd, bi = 256, -1
+        for i2 in idxs:
+            if has[i2]:
+                continue
+            d = descriptor_distance(q_desc[i], Cur.desc[i2])
+            if d < bd:
+                bd, bi = d, i2
+        if bd <= orb_dist:
+            out[bi] = i
+            has[bi] = True
+            nm += 1
+            if check_ori:
+                hist[rot_bin(q_angle[i], Cur.kps["angle"][bi])].append(bi)
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for j in hist[b]:
+                    out[j] = -1
+                    nm -= 1
+    return nm, out
+
+
+def search_by_projection_scw(KF, sf, q_valid, q_u, q_v, q_pred, q_desc, kp_matched, th):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:290-403, after projection.
+    KeyFrame::GetFeaturesInArea has no level argument (src/KeyFrame.cc:586-625); the level test is in the loop."""
+    matched = [bool(b) for b in kp_matched]
+    out = [-1] * KF.n
+    nm = 0
+    for i in range(len(q_u)):
+        if not q_valid[i]:
+            continue
+        p = int(q_pred[i])
+        radius = F32(F32(th) * F32(sf[p]))
+        idxs = KF.features_in_area(q_u[i], q_v[i], radius)
+        if not idxs:
+            continue
+        bd, bi = 256, -1
+        for idx in idxs:
+            if matched[idx]:
+                continue
+            lvl = int(KF.kps["octave"][idx])
+            if lvl < p - 1 or lvl > p:
+                continue
+            d = descriptor_distance(q_desc[i], KF.desc[idx])
+            if d < bd:
+                bd, bi = d, idx
+        if bd <= TH_LOW:
+            out[bi] = i
+            matched[bi] = True
+            nm += 1
+    return nm, out
+
+
+def fuse_best(KF, sf, inv_sigma2, q_valid, q_u, q_v, q_ur, q_pred, q_desc, th):
+    """matching part of Fuse(KeyFrame*, vpMapPoints, th), src/ORBmatcher.cc:825-975: best keypoint per point"""
+    best_idx = [-1] * len(q_u)
+    nf = 0
+    for i in range(len(q_u)):
+        if not q_valid[i]:
+            continue
+        p = int(q_pred[i])
+        u, v, ur = F32(q_u[i]), F32(q_v[i]), F32(q_ur[i])
+        radius = F32(F32(th) * F32(sf[p]))
+        idxs = KF.features_in_area(u, v, radius)
+        if not idxs:
+            continue
+        bd, bi = 256, -1
+        for idx in idxs:
+            lvl = int(KF.kps["octave"][idx])
+            if lvl < p - 1 or lvl > p:
+                continue
+            kpx, kpy = F32(KF.kps["x"][idx]), F32(KF.kps["y"][idx])
+            if KF.u_right[idx] >= 0:
+                ex, ey, er = F32(u - kpx), F32(v - kpy), F32(ur - KF.u_right[idx])
+                e2 = F32(F32(F32(ex * ex) + F32(ey * ey)) + F32(er * er))
+                if float(F32(e2 * F32(inv_sigma2[lvl]))) > 7.8:
+                    continue
+            else:
+                ex, ey = F32(u - kpx), F32(v - kpy)
+                e2 = F32(F32(ex * ex) + F32(ey * ey))
+                if float(F32(e2 * F32(inv_sigma2[lvl]))) > 5.99:
+                    continue
+            d = descriptor_distance(q_desc[i], KF.desc[idx])
+            if d < bd:
+                bd, bi = d, idx
+        if bd <= TH_LOW:
+            best_idx[i] = bi
+            nf += 1
+    return nf, best_idx
+
+
+def search_by_bow(desc1, angle1, valid1, F2, valid2, fv1, fv2, nnratio, check_ori, kf_kf):
+    """SearchByBoW(KeyFrame*, Frame&, ..) src/ORBmatcher.cc:159-288 (kf_kf False) and
+    SearchByBoW(KeyFrame*, KeyFrame*, ..) :522-655 (kf_kf True).  fv: dict node -> index list."""
+    n1 = len(desc1)
+    out_f = [-1] * F2.n
+    out_12 = [-1] * n1
+    matched2 = [False] * F2.n
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    nm = 0
+    for node in sorted(set(fv1) & set(fv2)):
+        for idx1 in fv1[node]:
+            if not valid1[idx1]:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for idx2 in fv2[node]:
+                if kf_kf:
+                    if matched2[idx2] or not valid2[idx2]:
+                        continue
+                else:
+                    if out_f[idx2] >= 0:
+                        continue
+                d = descriptor_distance(desc1[idx1], F2.desc[idx2])
+                if d < b1:
+                    b2, b1, bi = b1, d, idx2
+                elif d < b2:
+                    b2 = d
+            ok = (b1 < TH_LOW) if kf_kf else (b1 <= TH_LOW)
+            if ok and F32(b1) < F32(F32(nnratio) * F32(b2)):
+                if kf_kf:
+                    out_12[idx1] = bi
+                    matched2[bi] = True
+                else:
+                    out_f[bi] = idx1
+                if check_ori:
+                    hist[rot_bin(angle1[idx1], F2.kps["angle"][bi])].append(idx1 if kf_kf else bi)
+                nm += 1
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for j in hist[b]:
+                if kf_kf:
+                    out_12[j] = -1
+                else:
+                    out_f[j] = -1
+                nm -= 1
+    return nm, (out_12 if kf_kf else out_f)

@@ -312,3 +312,66 @@ def test_cpp_shim(pkg, tmp_path):
     pw, ph = np.frombuffer(buf, np.int32, 2, off)
     lvl1 = np.frombuffer(buf, np.uint8, pw * ph, off + 8).reshape(ph, pw)
     assert np.array_equal(lvl1, orc.level_image(1))          # mvImagePyramid[1]
+
+
+def test_search_for_initialization(pkg):
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+    (k1, d1), (k2, d2), grid = cases.bird_pair(2000, 600, 71, shift=(5, -4), max_flips=12)
+    F2, O2 = _frames(pkg, ctx, k2, d2, grid)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    for win in (30, 100):
+        nm, m12, p1 = pkg.ORBmatcher(ctx, 0.9, True).SearchForInitialization(k1, d1, F2, prev, win)
+        nm0, m120, p0 = oracle.search_for_initialization(k1, d1, O2, prev, win, 0.9, True)
+        assert nm == nm0 and nm > 0 and np.array_equal(m12, m120) and np.array_equal(p1, p0)
+
+
+@pytest.mark.parametrize("kf_kf", [False, True])
+def test_search_by_bow(pkg, kf_kf):
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+    b = cases.bow_case(2000, 2000, 1241, 376, 81, n_nodes=100)
+    F2, O2 = _frames(pkg, ctx, b["k2"], b["d2"], b["grid"])
+    for ratio in (0.75, 0.9):
+        m = pkg.ORBmatcher(ctx, ratio, True)
+        nm, out = m.SearchByBoW(b["d1"], b["k1"]["angle"], b["valid1"], F2, b["fv1"], b["fv2"], b["valid2"], kf_kf)
+        nm0, out0 = oracle.search_by_bow(b["d1"], b["k1"]["angle"], b["valid1"], O2, b["valid2"], b["fv1"], b["fv2"], ratio, True, kf_kf)
+        assert nm == nm0 and nm > 0 and np.array_equal(out, out0)
+    # one big node (> the cached-candidate capacity): the overflow path
+    n = 300
+    k, d, _, grid = cases.frame_case(n, 400, 300, 82)
+    d2 = synth.perturb_descriptors(d, 10, 83)
+    fv = (np.array([7], np.int32), np.array([0, n], np.int32), np.arange(n, dtype=np.int32))
+    F2, O2 = _frames(pkg, ctx, k, d2, grid)
+    ones = np.ones(n, np.uint8)
+    nm, out = pkg.ORBmatcher(ctx, 0.9, True).SearchByBoW(d, k["angle"], ones, F2, fv, fv, ones, kf_kf)
+    nm0, out0 = oracle.search_by_bow(d, k["angle"], ones, O2, ones, fv, fv, 0.9, True, kf_kf)
+    assert nm == nm0 and nm > 100 and np.array_equal(out, out0)
+
+
+def test_search_window_best_family(pkg):
+    """SearchByProjection(Frame,KF,set), SearchByProjection(KF,Scw), Fuse and SearchBySim3 configurations of the
+    generic best-in-window entry point."""
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+    w, h = 1241, 376
+    sf = cases.SCALE_FACTORS
+    inv_s2 = (np.float32(1) / (sf * sf)).astype(np.float32)
+    kps, desc, uR, grid = cases.frame_case(2000, w, h, 91, stereo_frac=0.5)
+    F, O = _frames(pkg, ctx, kps, desc, grid, uR)
+    has = (np.random.default_rng(92).random(len(kps)) < 0.2).astype(np.uint8)
+    m = pkg.ORBmatcher(ctx, 0.9, True)
+    WB = (pkg.ORBmatcher.WB_BLOCK, pkg.ORBmatcher.WB_URCHECK, pkg.ORBmatcher.WB_CHI2, pkg.ORBmatcher.WB_ORI)
+    configs = [
+        ("Frame,KF,set th=10 ORBdist=100", 10.0, -1, +1, WB[0] | WB[3], 100, False),
+        ("Frame,KF,set th=3 ORBdist=64", 3.0, -1, +1, WB[0] | WB[3], 64, False),
+        ("KF,Scw th=10", 10.0, -1, 0, WB[0], 50, False),
+        ("Fuse th=3", 3.0, -1, 0, WB[2], 50, True),
+        ("Sim3 th=7.5", 7.5, -1, 0, 0, 100, False),
+        ("Cur,Last style with uRight check", 15.0, -1, +1, WB[0] | WB[1] | WB[3], 100, True),
+    ]
+    for name, th, lo, hi, flags, acc, use_aux in configs:
+        q = cases.best_window_queries(kps, desc, uR, w, h, 2500, 93 + int(th), th=th)
+        args = (q["valid"], q["u"], q["v"], q["r"], q["pred"] + lo, q["pred"] + hi, q["desc"], q["ur"] if use_aux else None,
+                q["angle"] if flags & WB[3] else None, q["obs_pos"], has, inv_s2 if flags & WB[2] else None)
+        nm, bi, bd, qk = m.search_window_best(F, *args, acc, flags)
+        nm0, bi0, bd0, qk0 = oracle.search_window_best(O, *args, acc, flags)
+        assert nm == nm0 and nm > 0, name
+        assert np.array_equal(bi, bi0) and np.array_equal(bd[bi0 >= 0], bd0[bi0 >= 0]) and np.array_equal(qk, qk0), name

@@ -234,3 +234,51 @@ def test_matchers_vs_python_live_small():
         n, m12, _ = oracle.birdview_match(k1, d1, F2, None, 20, 0.9, True)
         n2, m122, _ = mref.birdview_match(k1, d1, P2, None, 20, 0.9, True)
         assert n == n2 and m12.tolist() == m122
+
+
+def test_second_batch_matchers_vs_python_live():
+    """SearchForInitialization, SearchByBoW x2 and the best-in-window family: oracle vs the literal Python
+    transcriptions of the reference functions (fresh small cases)."""
+    import matcher_py_ref as mref
+    sf = cases.SCALE_FACTORS
+    inv_s2 = (np.float32(1) / (sf * sf)).astype(np.float32)
+    for seed in (301, 302):
+        # SearchForInitialization on a front-camera grid
+        (k1, d1), (k2, d2), gr = cases.bird_pair(260, 300, seed, shift=(4, 3), max_flips=12)
+        F2 = oracle.Frame(k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+        P2 = mref.PyFrame(k2, d2, gr["min_x"], gr["min_y"], gr["inv_w"], gr["inv_h"])
+        prev = np.stack([k1["x"], k1["y"]], 1)
+        n, m12, p = oracle.search_for_initialization(k1, d1, F2, prev, 30, 0.9, True)
+        n0, m120, p0 = mref.search_for_initialization(k1, d1, P2, prev, 30, 0.9, True)
+        assert n == n0 and m12.tolist() == m120 and np.array_equal(p, p0)
+        # SearchByBoW both variants
+        b = cases.bow_case(220, 240, 400, 300, seed + 10)
+        F2 = oracle.Frame(b["k2"], b["d2"], 0, 0, 64 / 400, 48 / 300)
+        P2 = mref.PyFrame(b["k2"], b["d2"], 0, 0, 64 / 400, 48 / 300)
+        for kf_kf in (False, True):
+            n, out = oracle.search_by_bow(b["d1"], b["k1"]["angle"], b["valid1"], F2, b["valid2"], b["fv1"], b["fv2"], 0.75, True, kf_kf)
+            n0, out0 = mref.search_by_bow(b["d1"], b["k1"]["angle"], b["valid1"], P2, b["valid2"], cases.csr_to_dict(b["fv1"]),
+                                          cases.csr_to_dict(b["fv2"]), 0.75, True, kf_kf)
+            assert n == n0 and n > 0 and out.tolist() == out0, (seed, kf_kf)
+        # best-in-window family
+        kps, desc, uR, grid = cases.frame_case(300, 400, 300, seed + 20, stereo_frac=0.5)
+        F = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+        P = mref.PyFrame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+        q = cases.best_window_queries(kps, desc, uR, 400, 300, 350, seed + 21, th=10.0)
+        has = (np.random.default_rng(seed).random(len(kps)) < 0.2).astype(np.uint8)
+        # SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist): levels pred-1..pred+1, BLOCK|ORI
+        n, bi, bd, qk = oracle.search_window_best(F, q["valid"], q["u"], q["v"], q["r"], q["pred"] - 1, q["pred"] + 1, q["desc"], None, q["angle"],
+                                                  None, has, None, 64, oracle.WB_BLOCK | oracle.WB_ORI)
+        n0, qk0 = mref.search_by_projection_kf(P, sf, q["valid"], q["u"], q["v"], q["pred"], q["angle"], q["desc"], has, 10.0, 64, True)
+        assert n == n0 and qk.tolist() == qk0
+        # SearchByProjection(KeyFrame*, Scw, ...): levels pred-1..pred, BLOCK, TH_LOW
+        n, bi, bd, qk = oracle.search_window_best(F, q["valid"], q["u"], q["v"], q["r"], q["pred"] - 1, q["pred"], q["desc"], None, None,
+                                                  None, has, None, 50, oracle.WB_BLOCK)
+        n0, qk0 = mref.search_by_projection_scw(P, sf, q["valid"], q["u"], q["v"], q["pred"], q["desc"], has, 10.0)
+        assert n == n0 and qk.tolist() == qk0
+        # Fuse: independent, chi2 gate
+        q3 = cases.best_window_queries(kps, desc, uR, 400, 300, 350, seed + 22, th=3.0)
+        n, bi, bd, qk = oracle.search_window_best(F, q3["valid"], q3["u"], q3["v"], q3["r"], q3["pred"] - 1, q3["pred"], q3["desc"], q3["ur"],
+                                                  None, None, None, inv_s2, 50, oracle.WB_CHI2)
+        n0, bi0 = mref.fuse_best(P, sf, inv_s2, q3["valid"], q3["u"], q3["v"], q3["ur"], q3["pred"], q3["desc"], 3.0)
+        assert n == n0 and n > 0 and bi.tolist() == bi0
