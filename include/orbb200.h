@@ -204,6 +204,20 @@ int orbb200_search_by_bow(orbb200_ctx* ctx, const uint8_t* desc1, const float* a
                           const int32_t* fv2_node, const int32_t* fv2_ptr, const int32_t* fv2_idx, int nn2,
                           float nnratio, int check_ori, int kf_kf, int32_t* out, int* nmatches);
 
+/* ---- stereo matching -------------------------------------------------------------------------------------
+ * Frame::ComputeStereoMatches (src/Frame.cc:662-836) on the results of the last extraction: row-band descriptor
+ * search, 11x11 SAD refinement on the pyramid level of the left keypoint, parabola sub-pixel fit, median outlier
+ * cut.  Frame f uses images left0 + f*stride_imgs and right0 + f*stride_imgs of the extracted batch.  The device
+ * keeps mvuRight / mvDepth per left image ([max_batch][cap]); mb = baseline, mbf = baseline*fx. */
+int orbb200_stereo_matches_device(orbb200_ctx* ctx, int n_frames, int left0, int right0, int stride_imgs, float mb, float mbf);
+int orbb200_stereo_results_device(orbb200_ctx* ctx, const float** d_uright, const float** d_depth, const int32_t** d_nkept);
+/* One stereo pair, results copied to the host: u_right[cap], depth[cap] (first N entries meaningful). */
+int orbb200_compute_stereo_matches(orbb200_ctx* ctx, int img_left, int img_right, float mb, float mbf,
+                                   float* u_right, float* depth, int cap, int* n_matches);
+/* Frame over the left image of the last extraction whose uRight comes from the stereo matching above. */
+int orbb200_frame_from_extract_stereo(orbb200_ctx* ctx, orbb200_frame** f, int img_left,
+                                      float min_x, float min_y, float inv_w, float inv_h);
+
 /* ---- batched front-end step (bench / sequence processing) -----------------------------------------
  * One pass of the C2 hot path over a batch: extract 2*n_frames images (left,right interleaved: image 2i is
  * the left image of frame i), build the left frame's grid and run SearchByProjection of nq_per_frame

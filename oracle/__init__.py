@@ -59,6 +59,7 @@ def lib(native=False):
         "oracle_extractor_level_image": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
         "oracle_extractor_level_candidates": (C.c_int, [vp, C.c_int, vp, C.c_int]),
         "oracle_extractor_level_keypoints": (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        "oracle_compute_stereo_matches": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]),
         "oracle_distribute_octree": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
         "oracle_descriptor_distance": (C.c_int, [vp, vp]),
         "oracle_hamming_knn2": (None, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
@@ -342,3 +343,14 @@ def search_by_bow(desc1, angle1, valid1, F2, valid2, fv1, fv2, nnratio=0.7, chec
     n = F2._L.oracle_search_by_bow(_p(desc1), _p(angle1), _p(valid1), n1, F2._h, _p(valid2), _p(f1[0]), _p(f1[1]), _p(f1[2]), len(f1[0]),
                                    _p(f2[0]), _p(f2[1]), _p(f2[2]), len(f2[0]), nnratio, int(check_ori), int(kf_kf), _p(out))
     return n, out
+
+
+def compute_stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mb, mbf):
+    """Frame::ComputeStereoMatches; ex_left/ex_right are Extractor objects whose last call was on the left/right image"""
+    kps_l, kps_r = _c(kps_l, KP_DTYPE), _c(kps_r, KP_DTYPE)
+    desc_l, desc_r = _c(desc_l, np.uint8), _c(desc_r, np.uint8)
+    ur = np.empty(len(kps_l), np.float32)
+    dp = np.empty(len(kps_l), np.float32)
+    n = ex_left._L.oracle_compute_stereo_matches(ex_left._h, ex_right._h, _p(kps_l), _p(desc_l), len(kps_l), _p(kps_r), _p(desc_r), len(kps_r),
+                                                 mb, mbf, _p(ur), _p(dp))
+    return n, ur, dp

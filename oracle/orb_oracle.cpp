@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -593,7 +594,133 @@ struct oracle_extractor {
     }
 };
 
+/* Frame::ComputeStereoMatches, src/Frame.cc:662-836.  L and R are the two extractors after operator() on the left
+ * and right image (the reference reads their public mvImagePyramid, :669,759,771,776). */
+static int ComputeStereoMatches(const oracle_extractor* EL, const oracle_extractor* ER,
+                                const oracle_kp_t* mvKeys, const uint8_t* mDescriptors, int N,
+                                const oracle_kp_t* mvKeysRight, const uint8_t* mDescriptorsRight, int Nr,
+                                float mb, float mbf, float* mvuRight, float* mvDepth)
+{
+    const int TH_HIGH = 100, TH_LOW = 50;
+    for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = EL->mvImagePyramid[0].rows;
+    const std::vector<float>& mvScaleFactors = EL->mvScaleFactor;
+    const std::vector<float>& mvInvScaleFactors = EL->mvInvScaleFactor;
+    std::vector<std::vector<size_t> > vRowIndices(nRows, std::vector<size_t>());
+    for (int iR = 0; iR < Nr; iR++) {
+        const oracle_kp_t& kp = mvKeysRight[iR];
+        const float kpY = kp.y;
+        const float r = 2.0f * mvScaleFactors[kp.octave];
+        const int maxr = (int)ceil(kpY + r);
+        const int minr = (int)floor(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);   /* bounds: UB guard only */
+    }
+    const float minZ = mb;
+    const float minD = 0;
+    const float maxD = mbf / minZ;
+    std::vector<std::pair<int, int> > vDistIdx;
+    vDistIdx.reserve(N);
+    auto desc_dist = [](const uint8_t* a, const uint8_t* b) {
+        int d = 0;
+        for (int i = 0; i < 8; i++) { uint32_t wa, wb; memcpy(&wa, a + 4 * i, 4); memcpy(&wb, b + 4 * i, 4); d += __builtin_popcount(wa ^ wb); }
+        return d;
+    };
+    for (int iL = 0; iL < N; iL++) {
+        const oracle_kp_t& kpL = mvKeys[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y;
+        const float uL = kpL.x;
+        if ((size_t)vL >= (size_t)nRows) continue;                     /* UB guard only */
+        const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        size_t bestIdxR = 0;
+        const uint8_t* dL = mDescriptors + (size_t)iL * 32;
+        for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+            const size_t iR = vCandidates[iC];
+            const oracle_kp_t& kpR = mvKeysRight[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = desc_dist(dL, mDescriptorsRight + iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = mvKeysRight[bestIdxR].x;
+            const float scaleFactor = mvInvScaleFactors[kpL.octave];
+            const float scaleduL = roundf(kpL.x * scaleFactor);
+            const float scaledvL = roundf(kpL.y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5;
+            const Img& PL = EL->mvImagePyramid[kpL.octave];
+            const Img& PR = ER->mvImagePyramid[kpL.octave];
+            /* IL = patch - centre (CV_32F); values are small integers, so float sums below are exact */
+            const int yL0 = (int)(scaledvL - w), xL0 = (int)(scaleduL - w);
+            const float cL = (float)*PL.ptr(yL0 + w, xL0 + w);
+            int bestDistS = INT32_MAX;
+            int bestincR = 0;
+            const int L = 5;
+            std::vector<float> vDists(2 * L + 1);
+            const float iniu = scaleduR0 + L - w;
+            const float endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= PR.cols) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const int xR0 = (int)(scaleduR0 + incR - w);
+                const float cR = (float)*PR.ptr(yL0 + w, xR0 + w);
+                float dist = 0;   /* cv::norm(IL,IR,NORM_L1) */
+                for (int dy = 0; dy < 2 * w + 1; dy++)
+                    for (int dx = 0; dx < 2 * w + 1; dx++) {
+                        const float a = (float)*PL.ptr(yL0 + dy, xL0 + dx) - cL;
+                        const int xr = std::min(std::max(xR0 + dx, 0), PR.cols - 1);   /* the reference reads its 19-px border here; never reached for real keypoints */
+                        const float b = (float)*PR.ptr(yL0 + dy, xr) - cR;
+                        dist += fabsf(a - b);
+                    }
+                if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = mvScaleFactors[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;                                    /* reference indexes an empty vector here */
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = (float)vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1;
+        mvDepth[vDistIdx[i].second] = -1;
+        kept--;
+    }
+    return kept;
+}
+
 extern "C" {
+
+int oracle_compute_stereo_matches(oracle_extractor* EL, oracle_extractor* ER,
+                                  const oracle_kp_t* kpsL, const uint8_t* descL, int nL,
+                                  const oracle_kp_t* kpsR, const uint8_t* descR, int nR,
+                                  float mb, float mbf, float* uRight, float* depth)
+{ return ComputeStereoMatches(EL, ER, kpsL, descL, nL, kpsR, descR, nR, mb, mbf, uRight, depth); }
 
 void oracle_resize_u8(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep)
 { resize_u8(src, sw, sh, sstep, dst, dw, dh, dstep); }

@@ -61,6 +61,12 @@ int oracle_extractor_level_image(oracle_extractor*, int level, int blurred, uint
 int oracle_extractor_level_candidates(oracle_extractor*, int level, int32_t* xyr, int cap);
 /* keypoints per level after octree+orientation, level coordinates (before pt*=scale) */
 int oracle_extractor_level_keypoints(oracle_extractor*, int level, oracle_kp_t* kps, int cap);
+/* Frame::ComputeStereoMatches (src/Frame.cc:662-836): EL/ER = extractors after operator() on the left/right image
+ * (their mvImagePyramid is read); returns the number of stereo matches kept, writes mvuRight / mvDepth */
+int oracle_compute_stereo_matches(oracle_extractor* EL, oracle_extractor* ER,
+                                  const oracle_kp_t* kpsL, const uint8_t* descL, int nL,
+                                  const oracle_kp_t* kpsR, const uint8_t* descR, int nR,
+                                  float mb, float mbf, float* uRight, float* depth);
 /* standalone DistributeOctTree on (x,y,response) candidates in region coords */
 int oracle_distribute_octree(const int32_t* xyr, int n, int minX, int maxX, int minY, int maxY, int N,
                              int32_t* out_xyr, int cap);

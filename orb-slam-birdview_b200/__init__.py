@@ -75,6 +75,10 @@ _SIGNATURES = {
     "orbb200_search_for_initialization": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _i, _vp, C.POINTER(_i)]),
     "orbb200_search_window_best": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i)]),
     "orbb200_search_by_bow": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _i, _i, _vp, C.POINTER(_i)]),
+    "orbb200_stereo_matches_device": (_i, [_vp, _i, _i, _i, _i, _f, _f]),
+    "orbb200_stereo_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "orbb200_compute_stereo_matches": (_i, [_vp, _i, _i, _f, _f, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbb200_frame_from_extract_stereo": (_i, [_vp, C.POINTER(_vp), _i, _f, _f, _f, _f]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "orbb200_stage_timing": (_i, [_vp, _i]),
@@ -221,6 +225,16 @@ class ORBextractor:
         self.ctx.check(self._L.orbb200_extract_batch(self.ctx._h, ptrs, n, w, h, stride, _p(kps), _p(desc), cap, _p(counts)), "extract")
         self.last_n = n
         return kps, desc, counts
+
+    def ComputeStereoMatches(self, img_left, img_right, mb, mbf):
+        """Frame::ComputeStereoMatches (src/Frame.cc:662-836) on two images of the last extract_batch call
+        -> (n_matches, mvuRight[cap], mvDepth[cap])"""
+        cap = self.ctx.max_keypoints
+        ur, dp = np.empty(cap, np.float32), np.empty(cap, np.float32)
+        nm = C.c_int()
+        self.ctx.check(self._L.orbb200_compute_stereo_matches(self.ctx._h, img_left, img_right, mb, mbf, _p(ur), _p(dp), cap, C.byref(nm)),
+                       "ComputeStereoMatches")
+        return nm.value, ur, dp
 
     def image_pyramid(self, img_index=0, blurred=False):
         """mvImagePyramid (include/ORBextractor.h:85) of the last extraction, downloaded on demand."""

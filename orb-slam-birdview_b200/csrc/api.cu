@@ -253,6 +253,7 @@ void drain_stage_events(Ctx& c)
 
 static int run_extract(Ctx& c, int n)
 {
+    c.stereoValid = false;
     { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
     { StageTimer t(c, 2); launch_fast(c, n); }
     { StageTimer t(c, 3); launch_blur(c, n); }
@@ -353,8 +354,14 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     alloc((void**)&c.d_desc, nb * g.kpPerImg * 32);
     alloc((void**)&c.d_counts, nb * sizeof(int32_t));
     alloc((void**)&c.d_status, 256);
+    alloc((void**)&c.d_uRight, nb * g.kpPerImg * sizeof(float));
+    alloc((void**)&c.d_depth, nb * g.kpPerImg * sizeof(float));
+    alloc((void**)&c.d_sad, nb * g.kpPerImg * sizeof(int32_t));
+    alloc((void**)&c.d_nKept, nb * sizeof(int32_t));
+    alloc((void**)&c.d_invScale, MAX_LEVELS * sizeof(float));
     if (!ok) return fail("orbb200_create: cudaMalloc of the device pools failed", ORBB200_ERR_CUDA);
     cudaMemsetAsync(c.d_status, 0, 256, c.stream);
+    cudaMemcpyAsync(c.d_invScale, c.invScale.data(), sizeof(float) * nlevels, cudaMemcpyHostToDevice, c.stream);
     cudaMemsetAsync(c.d_counts, 0, nb * sizeof(int32_t), c.stream);
     cudaMemsetAsync(c.d_lvlCount, 0, nb * MAX_LEVELS * sizeof(int32_t), c.stream);
     // pyramid pools are read up to the row pitch (never past it): start from defined bytes
@@ -374,7 +381,8 @@ void orbb200_destroy(orbb200_ctx* ctx)
     drain_stage_events(c);
     for (cudaEvent_t e : c.freeEvents) cudaEventDestroy(e);
     for (auto& p : c.plans) cudaFree(p.block);
-    void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step};
+    void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
+                    c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
@@ -665,6 +673,18 @@ int orbb200_frame_from_extract(orbb200_ctx* ctx, orbb200_frame** out, int img_in
     int rc = frame_finish(c, f);
     if (rc != ORBB200_OK) { orbb200_frame_free(f); return rc; }
     *out = f;
+    return ORBB200_OK;
+}
+
+int orbb200_frame_from_extract_stereo(orbb200_ctx* ctx, orbb200_frame** out, int img_left, float min_x, float min_y, float inv_w, float inv_h)
+{
+    CTX_ENTER(ctx);
+    if (!c.stereoValid) { c.err = "frame_from_extract_stereo: no stereo matching since the last extraction"; return ORBB200_ERR_ARG; }
+    int rc = orbb200_frame_from_extract(ctx, out, img_left, min_x, min_y, inv_w, inv_h);
+    if (rc != ORBB200_OK) return rc;
+    (*out)->h.uRight = c.d_uRight + (size_t)img_left * c.cur->g.kpPerImg;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync((*out)->d_self, &(*out)->h, sizeof(FrameDev), cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
     return ORBB200_OK;
 }
 
@@ -985,6 +1005,48 @@ int orbb200_search_by_bow(orbb200_ctx* ctx, const uint8_t* desc1, const float* a
         for (int i = 0; i < F2->cap; i++) out[i] = (nq > 0 && perKp[i] >= 0) ? qidx1[perKp[i]] : -1;   // vpMapPointMatches as KF keypoint indices
     }
     *nmatches = nm;
+    return ORBB200_OK;
+}
+
+// ---- stereo matching ----------------------------------------------------------------
+int orbb200_stereo_matches_device(orbb200_ctx* ctx, int n_frames, int left0, int right0, int stride_imgs, float mb, float mbf)
+{
+    CTX_ENTER(ctx);
+    if (!c.cur || n_frames <= 0 || left0 < 0 || right0 < 0 || stride_imgs < 0 ||
+        left0 + (n_frames - 1) * stride_imgs >= c.curN || right0 + (n_frames - 1) * stride_imgs >= c.curN || !(mb > 0.f)) {
+        c.err = "stereo_matches: bad argument (needs a previous extraction holding both images)"; return ORBB200_ERR_ARG;
+    }
+    launch_stereo(c, n_frames, left0, right0, stride_imgs, mb, mbf, c.d_invScale, c.d_nKept);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    c.stereoValid = true;
+    return ORBB200_OK;
+}
+
+int orbb200_stereo_results_device(orbb200_ctx* ctx, const float** d_uright, const float** d_depth, const int32_t** d_nkept)
+{
+    if (!ctx || !ctx->c.cur) return ORBB200_ERR_ARG;
+    if (d_uright) *d_uright = ctx->c.d_uRight;
+    if (d_depth) *d_depth = ctx->c.d_depth;
+    if (d_nkept) *d_nkept = ctx->c.d_nKept;
+    return ORBB200_OK;
+}
+
+int orbb200_compute_stereo_matches(orbb200_ctx* ctx, int img_left, int img_right, float mb, float mbf,
+                                   float* u_right, float* depth, int cap, int* n_matches)
+{
+    CTX_ENTER(ctx);
+    if (!u_right || !depth || cap < 0) { c.err = "compute_stereo_matches: bad argument"; return ORBB200_ERR_ARG; }
+    int rc = orbb200_stereo_matches_device(ctx, 1, img_left, img_right, 0, mb, mbf);
+    if (rc != ORBB200_OK) return rc;
+    const int kpi = c.cur->g.kpPerImg, take = std::min(cap, kpi);
+    int32_t nk = 0;
+    if (take > 0) {
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(u_right, c.d_uRight + (size_t)img_left * kpi, sizeof(float) * take, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(depth, c.d_depth + (size_t)img_left * kpi, sizeof(float) * take, cudaMemcpyDeviceToHost, c.stream));
+    }
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&nk, c.d_nKept, sizeof(nk), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (n_matches) *n_matches = nk;
     return ORBB200_OK;
 }
 

@@ -65,6 +65,12 @@ struct Ctx {
     uint8_t* d_desc = nullptr;               // [maxBatch][kpPerImg][32]
     int32_t* d_counts = nullptr;             // [maxBatch]
     int32_t* d_status = nullptr;             // device-side error flags (octree overflow etc.)
+    float* d_uRight = nullptr;               // [maxBatch][kpPerImg]   Frame::mvuRight of the last stereo matching (left images)
+    float* d_depth = nullptr;                // [maxBatch][kpPerImg]   Frame::mvDepth
+    int32_t* d_sad = nullptr;                // [maxBatch][kpPerImg]   SAD distance of each stereo match (-1 none)
+    int32_t* d_nKept = nullptr;              // [maxBatch]             stereo matches kept per frame
+    float* d_invScale = nullptr;             // [MAX_LEVELS]
+    bool stereoValid = false;
 
     // staging for host entry points
     uint8_t* h_stage = nullptr;              // pinned

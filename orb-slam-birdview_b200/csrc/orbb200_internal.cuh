@@ -78,5 +78,6 @@ void launch_fast(Ctx& c, int n);
 void launch_octree(Ctx& c, int n);
 void launch_describe(Ctx& c, int n);
 size_t octree_smem_bytes(int maxNodes);
+void launch_stereo(Ctx& c, int n_frames, int left0, int right0, int strideImgs, float mb, float mbf, const float* d_invScale, int32_t* d_nKept);
 
 }  // namespace orbb200

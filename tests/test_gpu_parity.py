@@ -375,3 +375,36 @@ def test_search_window_best_family(pkg):
         nm0, bi0, bd0, qk0 = oracle.search_window_best(O, *args, acc, flags)
         assert nm == nm0 and nm > 0, name
         assert np.array_equal(bi, bi0) and np.array_equal(bd[bi0 >= 0], bd0[bi0 >= 0]) and np.array_equal(qk, qk0), name
+
+
+@pytest.mark.parametrize("h,w,nf,shift,seed", [(376, 1241, 2000, -7, 2000), (240, 320, 500, -6, 77), (200, 400, 600, -25, 5), (480, 752, 1000, -40, 9)])
+def test_compute_stereo_matches(pkg, h, w, nf, shift, seed):
+    """Frame::ComputeStereoMatches on the device-resident extraction results == oracle (bit-exact uRight, depth)."""
+    left = synth.synth_frame(h, w, seed)
+    right = synth.shift_frame(left, shift, 0)
+    right = np.clip(right.astype(int) + np.random.default_rng(seed).integers(-3, 4, right.shape), 0, 255).astype(np.uint8)
+    ex = pkg.ORBextractor(nf, 1.2, 8, 20, 7, max_size=(w, h), max_batch=2)
+    K, D, N = ex.extract_batch([left, right])
+    mb, mbf = 0.537, 386.1448
+    nm, ur, dp = ex.ComputeStereoMatches(0, 1, mb, mbf)
+    eL, eR = oracle.Extractor(nf, 1.2, 8, 20, 7), oracle.Extractor(nf, 1.2, 8, 20, 7)
+    kl, dl = eL(left)
+    kr, dr = eR(right)
+    nm0, ur0, dp0 = oracle.compute_stereo_matches(eL, eR, kl, dl, kr, dr, mb, mbf)
+    assert nm == nm0 and nm > 50
+    assert np.array_equal(ur[:len(kl)].view(np.uint32), ur0.view(np.uint32))
+    assert np.array_equal(dp[:len(kl)].view(np.uint32), dp0.view(np.uint32))
+    # and the stereo frame feeds SearchByProjection's uRight consistency test
+    import ctypes as C
+    h_ = C.c_void_p()
+    ctx = ex.ctx
+    ctx.check(ctx._L.orbb200_frame_from_extract_stereo(ctx._h, C.byref(h_), 0, 0.0, 0.0, 64.0 / w, 48.0 / h))
+    F = pkg.Frame.__new__(pkg.Frame)
+    F.ctx, F._L, F._h, F.n = ctx, ctx._L, h_, ctx.max_keypoints
+    O = oracle.Frame(kl, dl, 0.0, 0.0, 64.0 / w, 48.0 / h, ur0)
+    q = cases.projection_queries(kl, dl, ur0, w, h, 1500, seed + 1)
+    m = pkg.ORBmatcher(ctx, 0.8)
+    nm1, bi, bd, qk = m.SearchByProjection(F, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"], q["desc"], q["obs_pos"], None, 2.0)
+    nm2, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
+                                                     q["desc"], q["obs_pos"], None, 2.0, 0.8)
+    assert nm1 == nm2 and np.array_equal(bi, bi0) and np.array_equal(qk[:len(kl)], qk0)

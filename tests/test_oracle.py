@@ -282,3 +282,21 @@ def test_second_batch_matchers_vs_python_live():
                                                   None, None, None, inv_s2, 50, oracle.WB_CHI2)
         n0, bi0 = mref.fuse_best(P, sf, inv_s2, q3["valid"], q3["u"], q3["v"], q3["ur"], q3["pred"], q3["desc"], 3.0)
         assert n == n0 and n > 0 and bi.tolist() == bi0
+
+
+def test_stereo_matches_vs_python_live():
+    """Frame::ComputeStereoMatches: C++ oracle vs the literal Python transcription (tests/ref_py/stereo_py_ref.py)."""
+    from stereo_py_ref import compute_stereo_matches as pyref
+    for (h, w, nf, sh, seed) in [(240, 320, 500, -6, 77), (200, 400, 600, -25, 5)]:
+        left = synth.synth_frame(h, w, seed)
+        right = synth.shift_frame(left, sh, 0)
+        right = np.clip(right.astype(int) + np.random.default_rng(seed).integers(-3, 4, right.shape), 0, 255).astype(np.uint8)
+        eL, eR = oracle.Extractor(nf, 1.2, 8, 20, 7), oracle.Extractor(nf, 1.2, 8, 20, 7)
+        kl, dl = eL(left)
+        kr, dr = eR(right)
+        n, ur, dp = oracle.compute_stereo_matches(eL, eR, kl, dl, kr, dr, 0.537, 386.1448)
+        sf = eL.scale_factors()
+        n0, ur0, dp0 = pyref([eL.level_image(l) for l in range(8)], [eR.level_image(l) for l in range(8)], kl, dl, kr, dr, sf,
+                             (np.float32(1) / sf).astype(np.float32), 0.537, 386.1448)
+        assert n == n0 and n > 100
+        assert np.array_equal(ur.view(np.uint32), ur0.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp0.view(np.uint32))
