@@ -33,7 +33,8 @@ W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 1241, 376, 2000, 8, 1.2, 20, 7
 NQ, TH, RATIO = 3000, 1.0, 0.8
 GRID = (0.0, 0.0, 64.0 / W, 48.0 / H)        # mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv (k1 == 0)
 METRIC = "ORB extract+match frames/sec"
-STAGES = ["import", "pyramid", "fast", "blur", "octree", "describe", "grid", "match"]
+STAGES = ["import", "pyramid", "fast", "blur", "octree", "describe", "grid", "match", "stereo"]
+MB, MBF = 0.537, 386.1448                      # KITTI00-02.yaml: Camera.bf / Camera.fx, Camera.bf
 
 
 def _synth():
@@ -80,6 +81,12 @@ class CpuArm:
             self.native = False
         self.tls = threading.local()
         self.sf = None
+        self.with_stereo = False
+
+    def _extractor2(self):
+        if not hasattr(self.tls, "ex2"):
+            self.tls.ex2 = self.oracle.Extractor(self.nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, native=self.native)
+        return self.tls.ex2
 
     def _extractor(self):
         if not hasattr(self.tls, "ex"):
@@ -92,8 +99,14 @@ class CpuArm:
         all cores being busy with other frames), grid + SearchByProjection on the left frame"""
         ex = self._extractor()
         kl, dl = ex(left)
-        kr, dr = ex(right)
-        F = self.oracle.Frame(kl, dl, *GRID, native=self.native)
+        if self.with_stereo:
+            ex2 = self._extractor2()
+            kr, dr = ex2(right)
+            _, ur, _ = self.oracle.compute_stereo_matches(ex, ex2, kl, dl, kr, dr, MB, MBF)
+            F = self.oracle.Frame(kl, dl, *GRID, u_right=ur, native=self.native)
+        else:
+            kr, dr = ex(right)
+            F = self.oracle.Frame(kl, dl, *GRID, native=self.native)
         n, bi, bd, qk = self.oracle.search_by_projection(F, self.sf, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
                                                          q["desc"], q["obs_pos"], None, TH, RATIO)
         return len(kl), len(kr), n, bi, bd
@@ -350,6 +363,9 @@ def run_ours(args):
     B, P = args.frames_per_step, args.pools
     arm = GpuArm(local, B, P, n_ctx=2)
     arm.setup_data(100000 * rank + 2000)
+    if args.with_stereo:
+        for c in arm.ctxs:
+            c.check(arm.L.orbb200_step_enable_stereo(c._h, 1, MB, MBF), "step_enable_stereo")
     K, Wm = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -380,8 +396,8 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = arm.launches() - l0
     clocks = sampler.stop() if rank == 0 else None
-    st_ms = np.zeros(8, np.float32)
-    st_n = np.zeros(8, np.int32)
+    st_ms = np.zeros(9, np.float32)
+    st_n = np.zeros(9, np.int32)
     arm.L.orbb200_stage_times(ctx._h, C.c_void_p(st_ms.ctypes.data), C.c_void_p(st_n.ctypes.data), 1)
     arm.L.orbb200_stage_timing(ctx._h, 0)
 
@@ -471,7 +487,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "stage_ms_per_step": {STAGES[i]: float(st_ms[i] / K) for i in range(8)},
+        "stage_ms_per_step": {STAGES[i]: float(st_ms[i] / K) for i in range(9)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
@@ -503,6 +519,7 @@ def cpu_baseline(arm, args, target_s=15.0):
     try:
         cores = host_cores()
         cpu = CpuArm(cores)
+        cpu.with_stereo = bool(args.with_stereo)
         imgs = arm.h_imgs[0].numpy()
         q = {k: v.numpy() for k, v in arm.h_q[0].items()}
         navail = imgs.shape[0] // 2
@@ -565,6 +582,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=64)
     ap.add_argument("--pools", type=int, default=3)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
+    ap.add_argument("--with-stereo", action="store_true", help="also run ComputeStereoMatches in the step (side measurement; not the C2 headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()

@@ -243,12 +243,17 @@ int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_fram
                              int32_t* h_counts /*[2n]*/, int32_t* h_best_idx /*[n][nq]*/, int32_t* h_best_dist,
                              int32_t* h_nmatches /*[n]*/);
 
+/* Make the batched step also run ComputeStereoMatches between extraction and matching (the left frames then carry
+ * mvuRight, which SearchByProjection's stereo-consistency test reads, src/ORBmatcher.cc:91-96). */
+int orbb200_step_enable_stereo(orbb200_ctx* ctx, int enable, float mb, float mbf);
+
 /* Per-stage device timing (bench): CUDA events on the context's stream around each stage.
- * stages: 0 import, 1 pyramid, 2 FAST, 3 blur, 4 octree, 5 orientation+descriptors, 6 grid build, 7 windowed match */
-#define ORBB200_NUM_STAGES 8
+ * stages: 0 import, 1 pyramid, 2 FAST, 3 blur, 4 octree, 5 orientation+descriptors, 6 grid build, 7 windowed match,
+ * 8 stereo matching */
+#define ORBB200_NUM_STAGES 9
 int orbb200_stage_timing(orbb200_ctx* ctx, int enable);
 /* Synchronises, then returns accumulated milliseconds and launch-group counts per stage; reset!=0 clears. */
-int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[8]*/, int32_t* groups /*[8]*/, int reset);
+int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[9]*/, int32_t* groups /*[9]*/, int reset);
 /* Measured POPC issue rate of this device in G popc/s (denominator of the matching roofline). */
 double orbb200_measure_popc_peak(orbb200_ctx* ctx);
 

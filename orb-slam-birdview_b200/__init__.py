@@ -81,6 +81,7 @@ _SIGNATURES = {
     "orbb200_frame_from_extract_stereo": (_i, [_vp, C.POINTER(_vp), _i, _f, _f, _f, _f]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "orbb200_step_enable_stereo": (_i, [_vp, _i, _f, _f]),
     "orbb200_stage_timing": (_i, [_vp, _i]),
     "orbb200_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orbb200_launch_count": (C.c_longlong, [_vp]),

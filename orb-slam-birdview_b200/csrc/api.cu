@@ -359,6 +359,13 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     alloc((void**)&c.d_sad, nb * g.kpPerImg * sizeof(int32_t));
     alloc((void**)&c.d_nKept, nb * sizeof(int32_t));
     alloc((void**)&c.d_invScale, MAX_LEVELS * sizeof(float));
+    {   // stereo row table: a right keypoint of octave o spans at most 2*ceil(2*scale[o]) + 2 rows
+        const int span = 2 * (int)ceilf(2.0f * c.scale[nlevels - 1]) + 3;
+        c.stereoItemCap = g.kpPerImg * span;
+        const size_t nf = nb / 2 + 1;
+        alloc((void**)&c.d_rowStart, nf * (size_t)(max_h + 2) * sizeof(int32_t));
+        alloc((void**)&c.d_rowItems, nf * (size_t)c.stereoItemCap * sizeof(int32_t));
+    }
     if (!ok) return fail("orbb200_create: cudaMalloc of the device pools failed", ORBB200_ERR_CUDA);
     cudaMemsetAsync(c.d_status, 0, 256, c.stream);
     cudaMemcpyAsync(c.d_invScale, c.invScale.data(), sizeof(float) * nlevels, cudaMemcpyHostToDevice, c.stream);
@@ -382,7 +389,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (cudaEvent_t e : c.freeEvents) cudaEventDestroy(e);
     for (auto& p : c.plans) cudaFree(p.block);
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
-                    c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale};
+                    c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
@@ -1013,7 +1020,8 @@ int orbb200_stereo_matches_device(orbb200_ctx* ctx, int n_frames, int left0, int
 {
     CTX_ENTER(ctx);
     if (!c.cur || n_frames <= 0 || left0 < 0 || right0 < 0 || stride_imgs < 0 ||
-        left0 + (n_frames - 1) * stride_imgs >= c.curN || right0 + (n_frames - 1) * stride_imgs >= c.curN || !(mb > 0.f)) {
+        left0 + (n_frames - 1) * stride_imgs >= c.curN || right0 + (n_frames - 1) * stride_imgs >= c.curN || !(mb > 0.f) ||
+        n_frames > c.maxBatch / 2 + 1) {
         c.err = "stereo_matches: bad argument (needs a previous extraction holding both images)"; return ORBB200_ERR_ARG;
     }
     launch_stereo(c, n_frames, left0, right0, stride_imgs, mb, mbf, c.d_invScale, c.d_nKept);
@@ -1068,7 +1076,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
     StepPlan key{};
     key.q = *d_queries; key.nq = nq; key.n_frames = n_frames; key.kpi = kpi; key.th = th; key.nnratio = nnratio;
     key.minX = min_x; key.minY = min_y; key.invW = inv_w; key.invH = inv_h;
-    key.o0 = d_out_best_idx; key.o1 = d_out_best_dist; key.o2 = d_nmatches;
+    key.o0 = d_out_best_idx; key.o1 = d_out_best_dist; key.o2 = d_nmatches; key.stereo = c.stepStereo ? 1 : 0;
     StepPlan* plan = nullptr;
     for (auto& p : c.plans)
         if (memcmp(&p, &key, offsetof(StepPlan, dF)) == 0) { plan = &p; break; }
@@ -1091,7 +1099,8 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
         for (int i = 0; i < n_frames; i++) {
             FrameDev& f = hF[i];
             const int img = 2 * i;
-            f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32; f.uRight = nullptr;
+            f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32;
+            f.uRight = c.stepStereo ? c.d_uRight + (size_t)img * kpi : nullptr;
             f.n_ptr = c.d_counts + img; f.n = kpi;
             f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi);
             f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
@@ -1117,6 +1126,11 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
     }
     FrameDev* dF = plan->dF;
     WinJob* dJ = plan->dJ;
+    if (c.stepStereo) {
+        StageTimer t(c, 8);
+        launch_stereo(c, n_frames, 0, 1, 2, c.stepMb, c.stepMbf, c.d_invScale, c.d_nKept);
+        c.stereoValid = true;
+    }
     { StageTimer t(c, 6); launch_grid_build(c, dF, n_frames); }
     { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames, nq); }
     ORBB200_CUDA_OK(c, cudaGetLastError());
@@ -1173,6 +1187,14 @@ int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_fram
     return ORBB200_OK;
 }
 
+int orbb200_step_enable_stereo(orbb200_ctx* ctx, int enable, float mb, float mbf)
+{
+    CTX_ENTER(ctx);
+    if (enable && !(mb > 0.f)) { c.err = "step_enable_stereo: mb must be positive"; return ORBB200_ERR_ARG; }
+    c.stepStereo = enable != 0; c.stepMb = mb; c.stepMbf = mbf;
+    return ORBB200_OK;
+}
+
 int orbb200_stage_timing(orbb200_ctx* ctx, int enable)
 {
     CTX_ENTER(ctx);
@@ -1185,7 +1207,7 @@ int orbb200_stage_times(orbb200_ctx* ctx, float* ms, int32_t* groups, int reset)
 {
     CTX_ENTER(ctx);
     drain_stage_events(c);
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < ORBB200_NUM_STAGES; i++) {
         if (ms) ms[i] = c.stageMs[i];
         if (groups) groups[i] = c.stageGroups[i];
         if (reset) { c.stageMs[i] = 0; c.stageGroups[i] = 0; }

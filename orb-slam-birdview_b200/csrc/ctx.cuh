@@ -29,6 +29,7 @@ struct StepPlan {
     int nq, n_frames, kpi;
     float th, nnratio, minX, minY, invW, invH;
     void *o0, *o1, *o2;
+    int stereo;
     FrameDev* dF;       // <- offsetof(StepPlan, dF) ends the key
     WinJob* dJ;
     void* block;
@@ -70,7 +71,12 @@ struct Ctx {
     int32_t* d_sad = nullptr;                // [maxBatch][kpPerImg]   SAD distance of each stereo match (-1 none)
     int32_t* d_nKept = nullptr;              // [maxBatch]             stereo matches kept per frame
     float* d_invScale = nullptr;             // [MAX_LEVELS]
+    int32_t* d_rowStart = nullptr;           // [maxBatch/2+1][maxH+1] stereo row table (CSR over image rows)
+    int32_t* d_rowItems = nullptr;           // [maxBatch/2+1][stereoItemCap]
+    int stereoItemCap = 0;
     bool stereoValid = false;
+    bool stepStereo = false;                 // orbb200_step_enable_stereo: the batched step also runs stereo matching
+    float stepMb = 0.f, stepMbf = 0.f;
 
     // staging for host entry points
     uint8_t* h_stage = nullptr;              // pinned
@@ -89,8 +95,8 @@ struct Ctx {
     struct Pending { int stage; cudaEvent_t e0, e1; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> freeEvents;
-    float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int stageGroups[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float stageMs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int stageGroups[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // RAII: events around one stage when timing is on

@@ -104,9 +104,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resize_kernel(uint8_t* __restri
 }
 
 // Reflect-101 border of every level: PYR_MARGIN_X(>=4 used) columns left, 8 right, 3 rows above/below.
-__global__ void __launch_bounds__(256) border_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, Geom g)
+// blockIdx.x = level * BD_CHUNKS + chunk: the (few thousand) border bytes of a level are split over BD_CHUNKS CTAs.
+constexpr int BD_CHUNKS = 8;
+
+__global__ void __launch_bounds__(128) border_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, Geom g)
 {
-    const int level = blockIdx.x, img = blockIdx.y;
+    const int level = blockIdx.x / BD_CHUNKS, chunk = blockIdx.x - level * BD_CHUNKS, img = blockIdx.y;
     const LevelGeom L = g.lv[level];
     if (L.w < 8 || L.h < 4) return;
     uint8_t* B = pyr + (size_t)img * pyrBytes + L.off;
@@ -114,16 +117,20 @@ __global__ void __launch_bounds__(256) border_kernel(uint8_t* __restrict__ pyr, 
     auto ry = [&](int y) { return y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y); };
     // rows -3..-1 and h..h+2, columns -4 .. w+7
     const int wide = L.w + 12;
-    for (int i = threadIdx.x; i < 6 * wide; i += 256) {
-        const int k = i / wide, x = i - k * wide - 4;
-        const int y = k < 3 ? k - 3 : L.h + (k - 3);
+    const int nA = 6 * wide, nB = 12 * L.h;
+    for (int i = chunk * 128 + threadIdx.x; i < nA + nB; i += BD_CHUNKS * 128) {
+        int x, y;
+        if (i < nA) {
+            const int k = i / wide;
+            x = i - k * wide - 4;
+            y = k < 3 ? k - 3 : L.h + (k - 3);
+        } else {
+            const int j = i - nA;
+            y = j / 12;
+            const int k = j - y * 12;
+            x = k < 4 ? k - 4 : L.w + (k - 4);
+        }
         B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)ry(y) * L.pitch + rx(x)];
-    }
-    // columns -4..-1 and w..w+7 of the image rows
-    for (int i = threadIdx.x; i < 12 * L.h; i += 256) {
-        const int y = i / 12, k = i - y * 12;
-        const int x = k < 4 ? k - 4 : L.w + (k - 4);
-        B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)y * L.pitch + rx(x)];
     }
 }
 
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
 // (the documented tie rule).  Winner per final node: max response, first in
 // (cell row, cell col, y, x) order on ties (:744-759).
 // ---------------------------------------------------------------------------------------------------
-constexpr int OT_THREADS = 512;
+constexpr int OT_THREADS = 256;
 
 struct OtNode { short x0, y0, x1, y1; };
 
@@ -969,7 +976,7 @@ void launch_pyramid(Ctx& c, int n)
                                                             st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l]);
         c.launches++;
     }
-    border_kernel<<<dim3(g.nlevels, n), 256, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
+    border_kernel<<<dim3(g.nlevels * BD_CHUNKS, n), 128, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
     c.launches++;
 }
 

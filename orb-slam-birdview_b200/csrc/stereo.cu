@@ -15,20 +15,79 @@ __device__ __forceinline__ int hamming256s(const uint4 a0, const uint4 a1, const
 
 constexpr int SM_WARPS = 8;
 
-// One warp per left keypoint.  The reference walks vRowIndices[vL] (right keypoints whose row band
-// [floor(y-r), ceil(y+r)], r = 2*scale[octave], contains row (int)vL) in ascending right index; scanning all
-// right keypoints in ascending index with the same band test visits the same candidates in the same order.
+// vRowIndices (:673-686): for every image row the right keypoints whose band [floor(y-r), ceil(y+r)], r = 2*scale[octave],
+// contains it.  CSR per frame, built by one CTA; the lists are unordered (the match reduction is order-free).
+__global__ void __launch_bounds__(1024) stereo_rows_kernel(Geom g, const orbb200_kp_t* __restrict__ kps, const int32_t* __restrict__ counts,
+                                                           int right0, int strideImgs, int32_t* __restrict__ rowStart, int32_t* __restrict__ rowItems,
+                                                           int rowCap, int itemCap)
+{
+    extern __shared__ int sRow[];            // [nRows + 1]
+    __shared__ int warpTot[32];
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int imgR = right0 + frame * strideImgs;
+    const int nR = min(counts[imgR], g.kpPerImg);
+    const int nRows = g.h;
+    const orbb200_kp_t* K = kps + (size_t)imgR * g.kpPerImg;
+    int32_t* RS = rowStart + (size_t)frame * rowCap;
+    int32_t* RI = rowItems + (size_t)frame * itemCap;
+    for (int i = tid; i <= nRows; i += 1024) sRow[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 1024) {
+        const float y = K[i].y, r = __fmul_rn(2.0f, g.lv[K[i].octave].scale);
+        const int lo = max((int)floorf(__fsub_rn(y, r)), 0), hi = min((int)ceilf(__fadd_rn(y, r)), nRows - 1);
+        for (int yy = lo; yy <= hi; yy++) atomicAdd(&sRow[yy], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the rows (chunks of 1024)
+    int carry = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < nRows; base += 1024) {
+        const int i = base + tid;
+        const int v = i < nRows ? sRow[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warpTot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int t = warpTot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            warpTot[lane] = t;
+        }
+        __syncthreads();
+        const int ex = carry + (wid ? warpTot[wid - 1] : 0) + x - v;
+        if (i < nRows) { RS[i] = ex; sRow[i] = ex; }
+        carry += warpTot[31];
+        __syncthreads();
+    }
+    if (tid == 0) RS[nRows] = carry;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 1024) {
+        const float y = K[i].y, r = __fmul_rn(2.0f, g.lv[K[i].octave].scale);
+        const int lo = max((int)floorf(__fsub_rn(y, r)), 0), hi = min((int)ceilf(__fadd_rn(y, r)), nRows - 1);
+        for (int yy = lo; yy <= hi; yy++) {
+            const int p = atomicAdd(&sRow[yy], 1);
+            if (p < itemCap) RI[p] = i;
+        }
+    }
+}
+
+// One warp per left keypoint.  The reference walks vRowIndices[vL] in ascending right index and keeps the first
+// minimum; the lexicographic (distance, right index) minimum over the unordered row list is the same element.
 __global__ void __launch_bounds__(SM_WARPS * 32) stereo_match_kernel(Geom g, const uint8_t* __restrict__ pyr,
                                                                     const orbb200_kp_t* __restrict__ kps, const uint8_t* __restrict__ desc,
                                                                     const int32_t* __restrict__ counts, int left0, int right0, int strideImgs,
                                                                     const float* __restrict__ invScale, float mb, float mbf,
+                                                                    const int32_t* __restrict__ rowStart, const int32_t* __restrict__ rowItems,
+                                                                    int rowCap, int itemCap,
                                                                     float* __restrict__ uRight, float* __restrict__ depth, int32_t* __restrict__ sad)
 {
     const int frame = blockIdx.y;
     const int imgL = left0 + frame * strideImgs, imgR = right0 + frame * strideImgs;
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * SM_WARPS + (threadIdx.x >> 5);
-    const int nL = min(counts[imgL], g.kpPerImg), nR = min(counts[imgR], g.kpPerImg);
+    const int nL = min(counts[imgL], g.kpPerImg);
     if (iL >= nL) return;
     const size_t oL = (size_t)imgL * g.kpPerImg, oR = (size_t)imgR * g.kpPerImg;
     float outU = -1.0f, outD = -1.0f;
@@ -44,18 +103,21 @@ __global__ void __launch_bounds__(SM_WARPS * 32) stereo_match_kernel(Geom g, con
     if (!(maxU < 0)) {
         const uint4* dl = reinterpret_cast<const uint4*>(desc) + 2 * (oL + iL);
         const uint4 qa = dl[0], qb = dl[1];
-        for (int iR = lane; iR < nR; iR += 32) {
-            const orbb200_kp_t* kr = kps + oR + iR;
-            const int octR = kr->octave;
-            if (octR < levelL - 1 || octR > levelL + 1) continue;
-            const float kpY = kr->y;
-            const float r = __fmul_rn(2.0f, g.lv[octR].scale);
-            if (row > (int)ceilf(__fadd_rn(kpY, r)) || row < (int)floorf(__fsub_rn(kpY, r))) continue;
-            const float uR = kr->x;
-            if (!(uR >= minU && uR <= maxU)) continue;
-            const uint4* dr = reinterpret_cast<const uint4*>(desc) + 2 * (oR + iR);
-            const int d = hamming256s(qa, qb, dr[0], dr[1]);
-            if (d < best) { best = d; bestR = iR; }      // ascending iR within a lane: first minimum kept
+        if (row >= 0 && row < g.h) {
+            const int32_t* RS = rowStart + (size_t)frame * rowCap;
+            const int32_t* RI = rowItems + (size_t)frame * itemCap;
+            const int pb = RS[row], pe = min(RS[row + 1], itemCap);
+            for (int p = pb + lane; p < pe; p += 32) {
+                const int iR = RI[p];
+                const orbb200_kp_t* kr = kps + oR + iR;
+                const int octR = kr->octave;
+                if (octR < levelL - 1 || octR > levelL + 1) continue;
+                const float uR = kr->x;
+                if (!(uR >= minU && uR <= maxU)) continue;
+                const uint4* dr = reinterpret_cast<const uint4*>(desc) + 2 * (oR + iR);
+                const int d = hamming256s(qa, qb, dr[0], dr[1]);
+                if (d < best || (d == best && iR < bestR)) { best = d; bestR = iR; }   // first minimum in right-index order
+            }
         }
     }
 #pragma unroll
@@ -189,11 +251,14 @@ __global__ void __launch_bounds__(256) stereo_median_kernel(int kpPerImg, const 
 void launch_stereo(Ctx& c, int n_frames, int left0, int right0, int strideImgs, float mb, float mbf, const float* d_invScale, int32_t* d_nKept)
 {
     const Geom& g = c.cur->g;
+    const int rowCap = g.h + 1, itemCap = c.stereoItemCap;
+    const size_t smem = sizeof(int) * (size_t)(g.h + 1);
+    stereo_rows_kernel<<<n_frames, 1024, smem, c.stream>>>(g, c.d_kps, c.d_counts, right0, strideImgs, c.d_rowStart, c.d_rowItems, rowCap, itemCap);
     dim3 grid((g.kpPerImg + SM_WARPS - 1) / SM_WARPS, n_frames);
     stereo_match_kernel<<<grid, SM_WARPS * 32, 0, c.stream>>>(g, c.d_pyr, c.d_kps, c.d_desc, c.d_counts, left0, right0, strideImgs, d_invScale, mb, mbf,
-                                                              c.d_uRight, c.d_depth, c.d_sad);
+                                                              c.d_rowStart, c.d_rowItems, rowCap, itemCap, c.d_uRight, c.d_depth, c.d_sad);
     stereo_median_kernel<<<n_frames, 256, 0, c.stream>>>(g.kpPerImg, c.d_counts, left0, strideImgs, c.d_uRight, c.d_depth, c.d_sad, d_nKept);
-    c.launches += 2;
+    c.launches += 3;
 }
 
 }  // namespace orbb200
