@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resize_kernel(uint8_t* __restri
                                                               const int2* __restrict__ xtab, const int4* __restrict__ ytab,
                                                               const int4* __restrict__ tiles, int nTiles)
 {
-    const int tileIdx = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    const int tileIdx = blockIdx.x * RS_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (tileIdx >= nTiles) return;
     const int lane = threadIdx.x & 31;
     const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
@@ -176,7 +176,9 @@ __device__ __forceinline__ void blur_hrow(uint32_t w0, uint32_t w1, uint32_t w2,
 __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned pyrBytes,
                                                              Geom g, const int4* __restrict__ tiles, int nTiles)
 {
-    const int tileIdx = blockIdx.x * BL_WARPS + (threadIdx.x >> 5);
+    // warp index through a shuffle: lets the compiler treat everything derived from the tile (level, row base
+    // pointers) as warp-uniform and address the loads as uniform base + 32-bit lane offset
+    const int tileIdx = blockIdx.x * BL_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (tileIdx >= nTiles) return;
     const int lane = threadIdx.x & 31;
     const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
@@ -188,10 +190,14 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
     uint8_t* D = blur + (size_t)img * pyrBytes + L.off;
     const int rows = min(BL_ROWS, L.h - y0);
 
-    // the level is stored with its reflect-101 border (border_kernel): no edge handling here
-    auto load_row = [&](int yy, uint32_t (&h)[4]) {
-        const uint32_t* r = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)yy * L.pitch + x);
-        blur_hrow(r[-1], r[0], r[1], h);
+    // the level is stored with its reflect-101 border (border_kernel): no edge handling here; rows are
+    // visited in order, so the row pointers just advance by the pitch
+    const uint32_t* rp = reinterpret_cast<const uint32_t*>(S + (ptrdiff_t)(y0 - 3) * L.pitch + x);
+    uint32_t* wp = reinterpret_cast<uint32_t*>(D + (size_t)y0 * L.pitch + x);
+    const int pitchW = L.pitch >> 2;
+    auto load_row = [&](int, uint32_t (&h)[4]) {
+        blur_hrow(rp[-1], rp[0], rp[1], h);
+        rp += pitchW;
     };
 
     uint32_t h0[4], h1[4], h2[4], h3[4], h4[4], h5[4], h6[4];
@@ -205,7 +211,9 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
             const uint32_t v = 18u * (a[k] + gq[k]) + 34u * (b[k] + f[k]) + 48u * (c[k] + e[k]) + 56u * d[k] + 32768u;
             out |= (v >> 16) << (8 * k);
         }
-        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * L.pitch + x) = out;
+        (void)r;
+        *wp = out;
+        wp += pitchW;
     };
     // the 7-row ring rotates by renaming (unrolled x7), not by moving registers
 #define ORBB200_BLUR_STEP(A, B, C, Dd, E, F, G) \
@@ -232,6 +240,8 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
 // ---------------------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 96;
 
+// (Tried: funnel shifts as two IMADs on the FMA pipe instead of one SHF on the ALU pipe -- slower, the kernel is then
+// issue-bound: 0.93 -> 0.96 ms per 128 images.)
 __device__ __forceinline__ uint32_t min3s(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3s(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 // The same per-lane min/max as half2 ops (HMNMX2/VHMNMX): lanes are 0x6400 + byte, i.e. the positive normal
