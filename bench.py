@@ -373,23 +373,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (value): CUDA events on the context's stream ----
-    ctx = arm.ctxs[0]
+    # ---- device-resident throughput (value): CUDA events on the contexts' streams ----
+    # One context / one stream by default (--two-streams alternates steps over two contexts; measured slower).
+    nctx = len(arm.ctxs) if args.two_streams else 1
     for s in range(Wm):
-        arm.step_device(s % P)
-    ctx.sync()
-    arm.L.orbb200_stage_timing(ctx._h, 1)
-    arm.L.orbb200_stage_times(ctx._h, None, None, 1)
+        arm.step_device(s % P, s % nctx)
+    for c in arm.ctxs:
+        c.sync()
+    for c in arm.ctxs[:nctx]:
+        arm.L.orbb200_stage_timing(c._h, 1)
+        arm.L.orbb200_stage_times(c._h, None, None, 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     l0 = arm.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    join = torch.cuda.Event()
     sampler.mark()
     e0.record(arm.streams[0])
+    if nctx > 1:
+        arm.streams[1].wait_event(e0)
     for s in range(K):
-        arm.step_device(s % P)
+        arm.step_device(s % P, s % nctx)
+    if nctx > 1:
+        join.record(arm.streams[1])
+        arm.streams[0].wait_event(join)
     e1.record(arm.streams[0])
     barrier()
     sampler.mark()
@@ -398,8 +407,13 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     st_ms = np.zeros(9, np.float32)
     st_n = np.zeros(9, np.int32)
-    arm.L.orbb200_stage_times(ctx._h, C.c_void_p(st_ms.ctypes.data), C.c_void_p(st_n.ctypes.data), 1)
-    arm.L.orbb200_stage_timing(ctx._h, 0)
+    for c in arm.ctxs[:nctx]:
+        a_ms = np.zeros(9, np.float32)
+        a_n = np.zeros(9, np.int32)
+        arm.L.orbb200_stage_times(c._h, C.c_void_p(a_ms.ctypes.data), C.c_void_p(a_n.ctypes.data), 1)
+        arm.L.orbb200_stage_timing(c._h, 0)
+        st_ms += a_ms
+        st_n += a_n
 
     # ---- end to end through the host-buffer C-ABI call: two contexts in flight ----
     for s in range(Wm if not args.no_e2e else 0):
@@ -579,11 +593,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--pools", type=int, default=3)
     ap.add_argument("--ref-frames-per-step", type=int, default=0)
     ap.add_argument("--with-stereo", action="store_true", help="also run ComputeStereoMatches in the step (side measurement; not the C2 headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
+    ap.add_argument("--two-streams", action="store_true", help="device-resident leg alternating over two contexts (measured slower: kernels of the two streams contend)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
