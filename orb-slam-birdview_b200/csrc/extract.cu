@@ -152,25 +152,18 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return min(max(p, 0), len - 1);    // second clamp only matters for levels narrower than the kernel
 }
 
-// horizontal 7-tap sums of the 4 pixels starting at byte 4 of the 12-byte window (w0,w1,w2)
+// horizontal 7-tap sums of the 4 pixels starting at byte 4 of the 12-byte window (w0,w1,w2): two 4-way byte dot
+// products (IDP.4A) per output, taps {18,34,48,56} on bytes x-3..x and {48,34,18,0} on bytes x+1..x+4
 __device__ __forceinline__ void blur_hrow(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&h)[4])
 {
-    // packed pixel pairs (u16x2) starting at window bytes 1..9: pair s = (b[s], b[s+1])
-    const uint32_t v = __funnelshift_r(w0, w1, 24);    // b3,b4,b5,b6
-    const uint32_t u = __funnelshift_r(w1, w2, 24);    // b7,b8,b9,b10
-    const uint32_t p1 = __byte_perm(w0, 0, 0x4241);    // b1,b2
-    const uint32_t p2 = __byte_perm(w0, 0, 0x4342);    // b2,b3
-    const uint32_t p3 = __byte_perm(v, 0, 0x4140);     // b3,b4
-    const uint32_t p4 = __byte_perm(w1, 0, 0x4140);    // b4,b5
-    const uint32_t p5 = __byte_perm(w1, 0, 0x4241);    // b5,b6
-    const uint32_t p6 = __byte_perm(w1, 0, 0x4342);    // b6,b7
-    const uint32_t p7 = __byte_perm(u, 0, 0x4140);     // b7,b8
-    const uint32_t p8 = __byte_perm(w2, 0, 0x4140);    // b8,b9
-    const uint32_t p9 = __byte_perm(w2, 0, 0x4241);    // b9,b10
-    // outputs (b4,b5): taps b1..b7 / b2..b8 -> pairs p1..p7 ; outputs (b6,b7): pairs p3..p9.  Lanes stay < 2^16.
-    const uint32_t ha = 18u * (p1 + p7) + 34u * (p2 + p6) + 48u * (p3 + p5) + 56u * p4;
-    const uint32_t hb = 18u * (p3 + p9) + 34u * (p4 + p8) + 48u * (p5 + p7) + 56u * p6;
-    h[0] = ha & 0xffffu; h[1] = ha >> 16; h[2] = hb & 0xffffu; h[3] = hb >> 16;
+    constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);
+    const uint32_t a0 = __funnelshift_r(w0, w1, 8), a1 = __funnelshift_r(w0, w1, 16), a2 = __funnelshift_r(w0, w1, 24);   // bytes x-3+j .. x+j
+    const uint32_t b0 = __funnelshift_r(w1, w2, 8), b1 = __funnelshift_r(w1, w2, 16), b2 = __funnelshift_r(w1, w2, 24);   // bytes x+1+j .. x+4+j
+    h[0] = __dp4a(b0, KB, __dp4a(a0, KA, 0u));
+    h[1] = __dp4a(b1, KB, __dp4a(a1, KA, 0u));
+    h[2] = __dp4a(b2, KB, __dp4a(a2, KA, 0u));
+    h[3] = __dp4a(w2, KB, __dp4a(w1, KA, 0u));
 }
 
 __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned pyrBytes,
