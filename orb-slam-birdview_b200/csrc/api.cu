@@ -175,12 +175,11 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                 cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
                 cells.push_back(make_int4((int)L.off, L.pitch, (int)L.candOff, L.candCap));
                 {   // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
-                    const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3, tw = x1 - xa;
+                    const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3;
                     const int wi = x1 - x0 - 6, hi = th - 6;
                     if (wi > 0 && hi > 0) {
-                        const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1, nw = (tw + 3) >> 2;
-                        const int P = 49;   // FT_PITCH in extract.cu
-                        (void)npr; (void)nw;
+                        const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1;
+                        const int P = FT_PITCH;
                         st.fastTileWords = std::max(st.fastTileWords, th * P);
                         st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
                         st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
@@ -393,7 +392,6 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
-    if (c.h_stage) cudaFreeHost(c.h_stage);
     if (c.stream) cudaStreamDestroy(c.stream);
     delete ctx;
 }
@@ -469,9 +467,6 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
     c.cur = st; c.curN = n;
     const Geom& g = st->g;
     // rows go straight into level 0 of the pyramid pool (row pitch conversion by the copy engine)
-    bool contiguous = true;
-    for (int i = 1; i < n; i++) contiguous &= (imgs[i] == imgs[0] + (size_t)i * h * stride);
-    (void)contiguous;
     for (int i = 0; i < n; i++) {
         if (!imgs[i]) { c.err = "extract: null image"; return ORBB200_ERR_ARG; }
         ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[i], stride, (size_t)w, (size_t)h,

@@ -79,8 +79,6 @@ struct Ctx {
     float stepMb = 0.f, stepMbf = 0.f;
 
     // staging for host entry points
-    uint8_t* h_stage = nullptr;              // pinned
-    size_t h_stage_bytes = 0;
     uint8_t* d_scratch = nullptr;            // generic device scratch (matcher uploads)
     size_t d_scratch_bytes = 0;
     uint8_t* h_scratch = nullptr;            // pinned generic

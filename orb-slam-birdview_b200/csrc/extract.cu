@@ -252,7 +252,6 @@ __device__ __forceinline__ uint32_t hmax2u(uint32_t a, uint32_t b)
     const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
-constexpr int FT_PITCH = 49;       // u32 words per shared tile row (needs >= 2*ceil(68/4)+3 = 37)
 constexpr int FT_NHALF = 0;        // first-stage triples computed with HMNMX2/VHMNMX (0..16); see note above
 constexpr uint32_t FT_BIAS = 0x64006400u;
 

@@ -408,3 +408,38 @@ def test_compute_stereo_matches(pkg, h, w, nf, shift, seed):
     nm2, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
                                                      q["desc"], q["obs_pos"], None, 2.0, 0.8)
     assert nm1 == nm2 and np.array_equal(bi, bi0) and np.array_equal(qk[:len(kl)], qk0)
+
+
+@pytest.mark.parametrize("h,w,nf,scale,nlevels,ini,mn,seed", [
+    (480, 640, 100, 1.2, 8, 20, 7, 1),        # tiny quota
+    (480, 640, 8000, 1.2, 8, 20, 7, 2),       # quota far above what the image offers on upper levels
+    (333, 517, 1500, 1.2, 8, 12, 5, 3),       # odd sizes (rows not 4-byte aligned), KITTI04-12 thresholds
+    (400, 600, 1200, 1.5, 5, 20, 7, 4),       # other scale factor / level count
+    (400, 600, 1200, 2.0, 4, 20, 7, 5),       # scale 2
+    (376, 1241, 2000, 1.1, 12, 20, 7, 6),     # 12 levels
+    (90, 1400, 800, 1.2, 3, 20, 7, 7),        # wide strip: many octree roots; 1-2 cell rows
+    (107, 109, 300, 1.2, 2, 20, 7, 8),        # FAST cells up to 50 px wide
+    (1080, 1920, 4000, 1.2, 8, 15, 5, 9),     # fisheye thresholds at full HD
+])
+def test_extract_parameter_sweep(pkg, h, w, nf, scale, nlevels, ini, mn, seed):
+    img = synth.synth_frame(h, w, 8000 + seed)
+    ex = pkg.ORBextractor(nf, scale, nlevels, ini, mn, max_size=(w, h))
+    k, d = ex(img)
+    orc = oracle.Extractor(nf, scale, nlevels, ini, mn)
+    k0, d0 = orc(img)
+    assert len(k0) > 0
+    _compare_extract(k, d, k0, d0, f"sweep {h}x{w} nf={nf} s={scale} L={nlevels}")
+
+
+def test_extract_noise_and_saturated_images(pkg):
+    """Every pixel a corner candidate (uniform noise), saturated blocks, and a checkerboard."""
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (240, 320), dtype=np.uint8)
+    blocks = np.kron(rng.integers(0, 2, (15, 20)) * 255, np.ones((16, 16))).astype(np.uint8)
+    checker = (np.indices((240, 320)).sum(0) // 7 % 2 * 255).astype(np.uint8)
+    ex = pkg.ORBextractor(1000, 1.2, 8, 20, 7, max_size=(320, 240))
+    orc = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    for name, img in (("noise", noise), ("blocks", blocks), ("checker", checker)):
+        k, d = ex(img)
+        k0, d0 = orc(img)
+        _compare_extract(k, d, k0, d0, name)
