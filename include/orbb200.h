@@ -218,6 +218,26 @@ int orbb200_compute_stereo_matches(orbb200_ctx* ctx, int img_left, int img_right
 int orbb200_frame_from_extract_stereo(orbb200_ctx* ctx, orbb200_frame** f, int img_left,
                                       float min_x, float min_y, float inv_w, float inv_h);
 
+/* ---- DBoW2 vocabulary transform ----------------------------------------------------------------------------
+ * Frame::ComputeBoW (src/Frame.cc:562-569) -> ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup)
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1203,1230-1271), TF_IDF weighting + L1 scoring.  The tree is
+ * passed flattened: children as CSR (child_ptr[n_nodes+1], child_idx), node descriptors [n_nodes][32], and per node
+ * the word id (-1 for inner nodes) and weight (idf; 0 = stopped word).  Node 0 is the root.
+ * Outputs: per-feature word and node id, the BowVector as ascending (word, value) pairs and the FeatureVector as CSR
+ * over ascending node ids -- the form orbb200_search_by_bow / orbb200_search_for_triangulation take. */
+typedef struct orbb200_voc orbb200_voc;
+int orbb200_voc_create(orbb200_ctx* ctx, orbb200_voc** voc, int n_nodes, const int32_t* child_ptr, const int32_t* child_idx,
+                       const uint8_t* node_desc, const int32_t* word_id, const double* weight, int L);
+void orbb200_voc_free(orbb200_voc* voc);
+int orbb200_bow_transform(orbb200_ctx* ctx, const orbb200_voc* voc, const uint8_t* desc, int n, int levelsup,
+                          int32_t* out_word /*[n] or NULL*/, int32_t* out_node /*[n] or NULL*/,
+                          int32_t* bow_word /*[n]*/, double* bow_value /*[n]*/, int* n_words,
+                          int32_t* fv_node /*[n]*/, int32_t* fv_ptr /*[n+1]*/, int32_t* fv_idx /*[n]*/, int* n_fv);
+/* Same on the descriptors of image `img_index` of the last extraction (no upload). */
+int orbb200_bow_transform_extracted(orbb200_ctx* ctx, const orbb200_voc* voc, int img_index, int levelsup,
+                                    int32_t* out_word, int32_t* out_node, int32_t* bow_word, double* bow_value, int* n_words,
+                                    int32_t* fv_node, int32_t* fv_ptr, int32_t* fv_idx, int* n_fv);
+
 /* ---- batched front-end step (bench / sequence processing) -----------------------------------------
  * One pass of the C2 hot path over a batch: extract 2*n_frames images (left,right interleaved: image 2i is
  * the left image of frame i), build the left frame's grid and run SearchByProjection of nq_per_frame

@@ -76,6 +76,9 @@ def lib(native=False):
         "oracle_search_for_initialization": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_int, vp]),
         "oracle_search_window_best": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
         "oracle_search_by_bow": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
+        "oracle_voc_create": (vp, [C.c_int, vp, vp, vp, vp, vp, C.c_int]),
+        "oracle_voc_destroy": (None, [vp]),
+        "oracle_voc_transform": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "oracle_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
                                                       vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
                                                       vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int, vp]),
@@ -354,3 +357,30 @@ def compute_stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mb, 
     n = ex_left._L.oracle_compute_stereo_matches(ex_left._h, ex_right._h, _p(kps_l), _p(desc_l), len(kps_l), _p(kps_r), _p(desc_r), len(kps_r),
                                                  mb, mbf, _p(ur), _p(dp))
     return n, ur, dp
+
+
+class Vocabulary:
+    """Flattened DBoW2 vocabulary tree: child_ptr/child_idx (CSR), node descriptors, leaf word ids (-1 inner), weights"""
+
+    def __init__(self, child_ptr, child_idx, node_desc, word_id, weight, L):
+        self._L = lib()
+        self.child_ptr, self.child_idx = _c(child_ptr, np.int32), _c(child_idx, np.int32)
+        self.node_desc, self.word_id, self.weight, self.L = _c(node_desc, np.uint8), _c(word_id, np.int32), _c(weight, np.float64), L
+        self._h = self._L.oracle_voc_create(len(self.word_id), _p(self.child_ptr), _p(self.child_idx), _p(self.node_desc), _p(self.word_id),
+                                            _p(self.weight), L)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.oracle_voc_destroy(self._h)
+            self._h = None
+
+    def transform(self, desc, levelsup=4):
+        """-> (word[n], node[n], (bow_word, bow_value), (fv_node, fv_ptr, fv_idx))"""
+        desc = _c(desc, np.uint8)
+        n = len(desc)
+        word, node = np.empty(n, np.int32), np.empty(n, np.int32)
+        bw, bv = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64)
+        fn, fp, fi = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32)
+        nw, nf = C.c_int32(), C.c_int32()
+        self._L.oracle_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(node), _p(bw), _p(bv), C.byref(nw), _p(fn), _p(fp), _p(fi), C.byref(nf))
+        return word, node, (bw[:nw.value].copy(), bv[:nw.value].copy()), (fn[:nf.value].copy(), fp[:nf.value + 1].copy(), fi[:fp[nf.value]].copy())

@@ -10,6 +10,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace {
@@ -634,6 +635,88 @@ int oracle_search_for_triangulation(const oracle_kp_t* kps1, const uint8_t* desc
         np++;
     }
     return nmatches;
+}
+
+}  // extern "C"
+
+
+/* ---- DBoW2 vocabulary transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1203, 1230-1271; FORB::distance
+ * FORB.cpp:81-101; BowVector.cpp:34-46,62-84; FeatureVector.cpp:31-45), TF_IDF weighting + L1 scoring as used by
+ * ORBVocabulary.  The tree is passed flattened: children CSR, node descriptors, leaf word ids and weights. ---- */
+struct oracle_voc {
+    int nNodes, L;
+    std::vector<int> childPtr, childIdx, wordId;
+    std::vector<uint8_t> desc;
+    std::vector<double> weight;
+};
+
+extern "C" {
+
+oracle_voc* oracle_voc_create(int nNodes, const int32_t* child_ptr, const int32_t* child_idx, const uint8_t* node_desc,
+                              const int32_t* word_id, const double* weight, int L)
+{
+    oracle_voc* v = new oracle_voc;
+    v->nNodes = nNodes; v->L = L;
+    v->childPtr.assign(child_ptr, child_ptr + nNodes + 1);
+    v->childIdx.assign(child_idx, child_idx + child_ptr[nNodes]);
+    v->desc.assign(node_desc, node_desc + (size_t)nNodes * 32);
+    v->wordId.assign(word_id, word_id + nNodes);
+    v->weight.assign(weight, weight + nNodes);
+    return v;
+}
+
+void oracle_voc_destroy(oracle_voc* v) { delete v; }
+
+/* transform(features, BowVector, FeatureVector, levelsup); outputs: per-feature word/node, the BowVector as ascending
+ * (word, value) and the FeatureVector as CSR over ascending node ids */
+int oracle_voc_transform(const oracle_voc* V, const uint8_t* features, int n, int levelsup,
+                         int32_t* out_word, int32_t* out_node,
+                         int32_t* bow_word, double* bow_value, int32_t* n_words,
+                         int32_t* fv_node, int32_t* fv_ptr, int32_t* fv_idx, int32_t* n_fv)
+{
+    std::map<unsigned, double> v;
+    std::map<unsigned, std::vector<unsigned> > fv;
+    for (int i_feature = 0; i_feature < n; i_feature++) {
+        const uint8_t* feature = features + (size_t)i_feature * 32;
+        const int nid_level = V->L - levelsup;
+        unsigned nid = 0;
+        unsigned final_id = 0;
+        int current_level = 0;
+        do {
+            ++current_level;
+            const int cb = V->childPtr[final_id], ce = V->childPtr[final_id + 1];
+            final_id = V->childIdx[cb];
+            double best_d = DescriptorDistance(feature, &V->desc[(size_t)final_id * 32]);
+            for (int c = cb + 1; c < ce; c++) {
+                const unsigned id = V->childIdx[c];
+                double d = DescriptorDistance(feature, &V->desc[(size_t)id * 32]);
+                if (d < best_d) { best_d = d; final_id = id; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (V->childPtr[final_id] != V->childPtr[final_id + 1]);
+        const unsigned word_id = V->wordId[final_id];
+        const double w = V->weight[final_id];
+        out_word[i_feature] = (int32_t)word_id; out_node[i_feature] = (int32_t)nid;
+        if (w > 0) {
+            v[word_id] += w;                 /* BowVector::addWeight */
+            fv[nid].push_back(i_feature);    /* FeatureVector::addFeature */
+        }
+    }
+    double norm = 0.0;                        /* BowVector::normalize(L1) */
+    for (auto it = v.begin(); it != v.end(); ++it) norm += fabs(it->second);
+    if (norm > 0.0)
+        for (auto it = v.begin(); it != v.end(); ++it) it->second /= norm;
+    int k = 0;
+    for (auto it = v.begin(); it != v.end(); ++it, ++k) { bow_word[k] = (int32_t)it->first; bow_value[k] = it->second; }
+    *n_words = k;
+    int nn = 0, p = 0;
+    for (auto it = fv.begin(); it != fv.end(); ++it, ++nn) {
+        fv_node[nn] = (int32_t)it->first; fv_ptr[nn] = p;
+        for (unsigned idx : it->second) fv_idx[p++] = (int32_t)idx;
+    }
+    fv_ptr[nn] = p;
+    *n_fv = nn;
+    return n;
 }
 
 }  // extern "C"

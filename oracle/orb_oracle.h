@@ -160,6 +160,16 @@ int oracle_search_for_triangulation(const oracle_kp_t* kps1, const uint8_t* desc
                                     int onlyStereo, int checkOri,
                                     int32_t* pairs /*[n1][2]*/);
 
+/* ---- DBoW2 transform (TemplatedVocabulary.h:1139-1271), TF_IDF + L1 ------------------------------------- */
+typedef struct oracle_voc oracle_voc;
+oracle_voc* oracle_voc_create(int nNodes, const int32_t* child_ptr, const int32_t* child_idx, const uint8_t* node_desc,
+                              const int32_t* word_id, const double* weight, int L);
+void oracle_voc_destroy(oracle_voc*);
+int oracle_voc_transform(const oracle_voc* V, const uint8_t* features, int n, int levelsup,
+                         int32_t* out_word, int32_t* out_node,
+                         int32_t* bow_word, double* bow_value, int32_t* n_words,
+                         int32_t* fv_node, int32_t* fv_ptr, int32_t* fv_idx, int32_t* n_fv);
+
 #ifdef __cplusplus
 }
 #endif

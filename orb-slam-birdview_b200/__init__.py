@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["ORBextractor", "ORBmatcher", "Frame", "Context", "OrbB200Error", "KP_DTYPE", "load_library", "build"]
+__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "Frame", "Context", "OrbB200Error", "KP_DTYPE", "load_library", "build"]
 
 _HERE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "orb-slam-birdview_b200") \
     if os.path.basename(os.path.dirname(os.path.abspath(__file__))) != "orb-slam-birdview_b200" else os.path.dirname(os.path.abspath(__file__))
@@ -79,6 +79,10 @@ _SIGNATURES = {
     "orbb200_stereo_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "orbb200_compute_stereo_matches": (_i, [_vp, _i, _i, _f, _f, _vp, _vp, _i, C.POINTER(_i)]),
     "orbb200_frame_from_extract_stereo": (_i, [_vp, C.POINTER(_vp), _i, _f, _f, _f, _f]),
+    "orbb200_voc_create": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "orbb200_voc_free": (None, [_vp]),
+    "orbb200_bow_transform": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_bow_transform_extracted": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "orbb200_step_enable_stereo": (_i, [_vp, _i, _f, _f]),
@@ -290,6 +294,43 @@ class Frame:
         out = np.empty(max(self.n, 1), np.int32)
         n = self.ctx.check(self._L.orbb200_frame_features_in_area(self.ctx._h, self._h, x, y, r, minLevel, maxLevel, _p(out), len(out)))
         return out[:n].copy()
+
+
+class ORBVocabulary:
+    """Flattened DBoW2 vocabulary (include/ORBVocabulary.h:30-31) with the transform used by Frame::ComputeBoW."""
+
+    def __init__(self, ctx, child_ptr, child_idx, node_desc, word_id, weight, L):
+        self.ctx, self._L = ctx, ctx._L
+        a = [_c(child_ptr, np.int32), _c(child_idx, np.int32), _c(node_desc, np.uint8), _c(word_id, np.int32), _c(weight, np.float64)]
+        h = C.c_void_p()
+        ctx.check(self._L.orbb200_voc_create(ctx._h, C.byref(h), len(a[3]), *[_p(x) for x in a], int(L)), "voc_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbb200_voc_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def transform(self, desc=None, levelsup=4, img_index=None):
+        """transform(features, BowVector, FeatureVector, levelsup)
+        -> (word[n], node[n], (bow_word, bow_value), (fv_node, fv_ptr, fv_idx)); desc=None + img_index uses the descriptors
+        of that image of the last extraction."""
+        n = self.ctx.max_keypoints if desc is None else len(desc)
+        word, node = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+        bw, bv = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64)
+        fn, fp, fi = np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32)
+        nw, nf = C.c_int(), C.c_int()
+        if desc is None:
+            self.ctx.check(self._L.orbb200_bow_transform_extracted(self.ctx._h, self._h, int(img_index), int(levelsup), _p(word), _p(node), _p(bw),
+                                                                   _p(bv), C.byref(nw), _p(fn), _p(fp), _p(fi), C.byref(nf)), "bow_transform")
+        else:
+            desc = _c(desc, np.uint8)
+            self.ctx.check(self._L.orbb200_bow_transform(self.ctx._h, self._h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(bw), _p(bv),
+                                                         C.byref(nw), _p(fn), _p(fp), _p(fi), C.byref(nf)), "bow_transform")
+        nfeat = int(fp[nf.value]) if nf.value > 0 else 0
+        return word, node, (bw[:nw.value].copy(), bv[:nw.value].copy()), (fn[:nf.value].copy(), fp[:nf.value + 1].copy(), fi[:nfeat].copy())
 
 
 class ORBmatcher:

@@ -8,7 +8,6 @@
 
 using namespace orbb200;
 
-struct orbb200_ctx { Ctx c; };
 
 struct orbb200_frame {
     Ctx* ctx = nullptr;

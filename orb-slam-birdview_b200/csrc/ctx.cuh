@@ -111,6 +111,12 @@ bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes);
 const ShapeTables* get_shape(Ctx& c, int w, int h);   // nullptr + c.err on failure
 bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err);
 
+}  // namespace orbb200
+
+struct orbb200_ctx { orbb200::Ctx c; };
+
+namespace orbb200 {
+
 #define ORBB200_CUDA_OK(c, call)                                                           \
     do {                                                                                   \
         cudaError_t e__ = (call);                                                          \

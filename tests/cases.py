@@ -165,3 +165,37 @@ def best_window_queries(kps, desc, u_right, w, h, nq, seed, th):
     r = (np.float32(th) * SCALE_FACTORS[pred]).astype(np.float32)
     ur = (q["u"] - np.float32(12.0) * q["invz"]).astype(np.float32)
     return dict(valid=q["valid"], u=q["u"], v=q["v"], pred=pred, r=r, ur=ur, angle=q["angle"], desc=q["desc"], obs_pos=q["obs_pos"])
+
+
+def synthetic_vocabulary(k=10, L=3, seed=0, stop_frac=0.03):
+    """A DBoW2-style vocabulary tree (k children, L levels) with random node descriptors; children are small
+    perturbations of their parent so that the descent is meaningful.  ORBvoc itself (k=10, L=6) is not part of the
+    reference checkout (.MISSING_LARGE_BLOBS); the algorithm does not depend on the tree's contents."""
+    rng = np.random.default_rng(seed)
+    desc = [synth.synth_descriptors(1, seed)[0]]
+    children = [[]]
+    level_nodes = [0]
+    for lvl in range(L):
+        nxt = []
+        for p in level_nodes:
+            for _ in range(k):
+                nid = len(desc)
+                flips = 64 >> lvl
+                d = synth.perturb_descriptors(desc[p][None, :], flips, int(rng.integers(1 << 30)))[0]
+                desc.append(d)
+                children.append([])
+                children[p].append(nid)
+                nxt.append(nid)
+        level_nodes = nxt
+    n = len(desc)
+    word_id = np.full(n, -1, np.int32)
+    weight = np.zeros(n, np.float64)
+    for w, nid in enumerate(level_nodes):
+        word_id[nid] = w
+        weight[nid] = 0.0 if rng.random() < stop_frac else float(rng.uniform(0.5, 8.0))    # idf; 0 = stopped word
+    ptr = np.zeros(n + 1, np.int32)
+    idx = []
+    for i, c in enumerate(children):
+        idx.extend(c)
+        ptr[i + 1] = len(idx)
+    return dict(child_ptr=ptr, child_idx=np.array(idx, np.int32), node_desc=np.stack(desc), word_id=word_id, weight=weight, L=L)

@@ -443,3 +443,49 @@ def test_extract_noise_and_saturated_images(pkg):
         k, d = ex(img)
         k0, d0 = orc(img)
         _compare_extract(k, d, k0, d0, name)
+
+
+@pytest.mark.parametrize("k,L,levelsup", [(10, 3, 1), (10, 3, 2), (10, 4, 4), (4, 6, 4)])
+def test_bow_transform(pkg, k, L, levelsup):
+    """DBoW2 transform (Frame::ComputeBoW) on a synthetic vocabulary tree: words, nodes, BowVector values (double bits)
+    and FeatureVector == oracle; then the FeatureVectors drive SearchByBoW."""
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+    voc = cases.synthetic_vocabulary(k, L, seed=k * 10 + L)
+    V = pkg.ORBVocabulary(ctx, **voc)
+    O = oracle.Vocabulary(**voc)
+    leaf = np.nonzero(voc["word_id"] >= 0)[0]
+    rng = np.random.default_rng(5)
+    feats = synth.perturb_descriptors(voc["node_desc"][rng.choice(leaf, 2000)], 40, 6)
+    w, n, (bw, bv), (fn, fp, fi) = V.transform(feats, levelsup)
+    w0, n0, (bw0, bv0), (fn0, fp0, fi0) = O.transform(feats, levelsup)
+    assert np.array_equal(w[:len(w0)], w0) and np.array_equal(n[:len(n0)], n0)
+    assert np.array_equal(bw, bw0) and np.array_equal(bv.view(np.uint64), bv0.view(np.uint64))
+    assert np.array_equal(fn, fn0) and np.array_equal(fp, fp0) and np.array_equal(fi, fi0)
+    assert abs(bv.sum() - 1.0) < 1e-9 and len(bw) > 50
+
+
+def test_extract_bow_searchbybow_chain(pkg):
+    """extract two views -> BoW transform of the device-resident descriptors -> SearchByBoW(KF, F): the chain of
+    Tracking::TrackReferenceKeyFrame (src/Tracking.cc:1022-1035), each step against the oracle."""
+    h, w = 376, 1241
+    a = synth.synth_frame(h, w, 2000)
+    b = synth.shift_frame(a, 5, 2)
+    ex = pkg.ORBextractor(2000, 1.2, 8, 20, 7, max_size=(w, h), max_batch=2)
+    K, D, N = ex.extract_batch([a, b])
+    voc = cases.synthetic_vocabulary(10, 3, seed=9)
+    V = pkg.ORBVocabulary(ex.ctx, **voc)
+    O = oracle.Vocabulary(**voc)
+    fvs = []
+    for i in range(2):
+        _, _, (bw, bv), fv = V.transform(None, 2, img_index=i)
+        _, _, (bw0, bv0), fv0 = O.transform(D[i, :N[i]], 2)
+        assert np.array_equal(bw, bw0) and np.array_equal(bv.view(np.uint64), bv0.view(np.uint64))
+        assert all(np.array_equal(x, y) for x, y in zip(fv, fv0))
+        fvs.append(fv)
+    grid = (0.0, 0.0, 64.0 / w, 48.0 / h)
+    F2 = pkg.Frame(ex.ctx, K[1, :N[1]], D[1, :N[1]], *grid)
+    O2 = oracle.Frame(K[1, :N[1]], D[1, :N[1]], *grid)
+    valid1 = (np.random.default_rng(3).random(N[0]) < 0.8).astype(np.uint8)
+    nm, out = pkg.ORBmatcher(ex.ctx, 0.7, True).SearchByBoW(D[0, :N[0]], K[0, :N[0]]["angle"], valid1, F2, fvs[0], fvs[1])
+    nm0, out0 = oracle.search_by_bow(D[0, :N[0]], K[0, :N[0]]["angle"], valid1, O2, None, fvs[0], fvs[1], 0.7, True, False)
+    assert nm == nm0 and nm > 100 and np.array_equal(out, out0)

@@ -300,3 +300,18 @@ def test_stereo_matches_vs_python_live():
                              (np.float32(1) / sf).astype(np.float32), 0.537, 386.1448)
         assert n == n0 and n > 100
         assert np.array_equal(ur.view(np.uint32), ur0.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp0.view(np.uint32))
+
+
+def test_bow_transform_vs_python_live():
+    """DBoW2 transform: C++ oracle vs the literal Python transcription (tests/ref_py/bow_py_ref.py)."""
+    import bow_py_ref
+    voc = cases.synthetic_vocabulary(10, 3, 1)
+    V = oracle.Vocabulary(**voc)
+    leaf = np.nonzero(voc["word_id"] >= 0)[0]
+    feats = synth.perturb_descriptors(voc["node_desc"][np.random.default_rng(2).choice(leaf, 300)], 20, 3)
+    for lu in (1, 2, 4):
+        w, n, (bw, bv), (fn, fp, fi) = V.transform(feats, lu)
+        w0, n0, v0, fv0 = bow_py_ref.transform(voc, feats, lu)
+        assert w.tolist() == w0 and n.tolist() == n0
+        assert bw.tolist() == [k for k, _ in v0] and bv.tolist() == [x for _, x in v0]
+        assert fn.tolist() == [k for k, _ in fv0] and all(fi[fp[i]:fp[i + 1]].tolist() == fv0[i][1] for i in range(len(fv0)))
