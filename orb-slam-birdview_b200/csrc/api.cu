@@ -197,6 +197,13 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             for (int y0 = 0; y0 < L.h; y0 += RS_ROWS)
                 for (int x0 = 0; x0 < L.w; x0 += 128) { rtiles.push_back(make_int4(l, x0, y0, 0)); st.resizeTileCount[l]++; }
         st.resizeTileBase[l + 1] = (int)rtiles.size();
+        if (l > 0 && L.w > 0 && L.h > 0) {
+            // shared-memory window of a 128 x RS_ROWS tile: source columns (16-byte aligned start) and rows it touches
+            const LevelGeom& Sg = g.lv[l - 1];
+            const int span = (int)ceil(128.0 * Sg.w / L.w) + 3 + 15, rows = (int)ceil((double)RS_ROWS * Sg.h / L.h) + 3;
+            st.resizeSmemPitch[l] = (int)align_up((size_t)span + 16, 16);
+            st.resizeSmemRows[l] = rows;
+        }
     }
     st.nBlurTiles = (int)btiles.size();
     auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {

@@ -17,6 +17,7 @@ struct ShapeTables {
     int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1: {level, x0, y0, 0}, 128 x RS_ROWS pixels each
     int resizeTileBase[MAX_LEVELS + 1] = {0};
     int resizeTileCount[MAX_LEVELS] = {0};
+    int resizeSmemPitch[MAX_LEVELS] = {0}, resizeSmemRows[MAX_LEVELS] = {0};   // staged source window of a resize tile
     int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0, fastWorkCap = 0;   // shared-memory carve of fast_cells_kernel
 };
 

@@ -38,43 +38,58 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 // cv::resize INTER_LINEAR u8 (reference src/ORBextractor.cc:1120): level l-1 -> l.
 // 11-bit fixed-point coefficients from host-built tables; vertical pass
 // (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
-// Streaming form: a warp owns 128 output columns x RS_ROWS output rows; each lane owns 4 adjacent output
-// columns, keeps their column coefficients in registers, walks down the rows and reuses the horizontal
-// interpolation of a source row for the next output row (a source row serves ~1.7 output rows at 1/1.2).
+// A CTA owns 128 output columns x RS_ROWS output rows and stages their source footprint in shared memory; each
+// lane owns 4 adjacent output columns, keeps their column coefficients in registers, walks down 8 rows and reuses
+// the horizontal interpolation of a source row for the next output row (a source row serves ~1.7 output rows
+// at 1/1.2).
 // ---------------------------------------------------------------------------------------------------
-constexpr int RS_WARPS = 4;
+constexpr int RS_THREADS = 128;                 // one CTA per 128 x RS_ROWS output tile; warp w owns rows [8w, 8w+8) of it
 
-__global__ void __launch_bounds__(RS_WARPS * 32) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
-                                                              const int2* __restrict__ xtab, const int4* __restrict__ ytab,
-                                                              const int4* __restrict__ tiles, int nTiles)
+__global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
+                                                            const int2* __restrict__ xtab, const int4* __restrict__ ytab,
+                                                            const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows)
 {
-    const int tileIdx = blockIdx.x * RS_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    if (tileIdx >= nTiles) return;
-    const int lane = threadIdx.x & 31;
-    const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
+    // The source footprint of the tile is staged in shared memory with coalesced 16-byte loads, so the
+    // interpolation reads (two bytes per output column and source row) never wait on global memory.
+    extern __shared__ __align__(16) uint8_t rsSmem[];
+    const int4 t = __ldg(tiles + blockIdx.x);       // {level, x0, y0, -}
     const int img = blockIdx.y;
-    const int x4 = t.y + 4 * lane, y0 = t.z;
-    if (x4 >= dst.w) return;
+    const int x0 = t.y, y0 = t.z;
+    const int tid = threadIdx.x;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + src.off;
     uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off;
-    // column setup, once per thread: source offsets and 11-bit coefficients of its 4 columns
+    const int yLast = min(y0 + RS_ROWS, dst.h) - 1, xLast = min(x0 + 127, dst.w - 1);
+    const int ry0 = __ldg(ytab + dst.ytabOff + y0).x, ry1 = __ldg(ytab + dst.ytabOff + yLast).y;
+    const int cx0 = __ldg(xtab + dst.xtabOff + x0).x & ~15;
+    const int cx1 = min(__ldg(xtab + dst.xtabOff + xLast).x + 1, src.w - 1);
+    const int nvec = (cx1 - cx0) / 16 + 1, nrows = ry1 - ry0 + 1;     // <= smemPitch/16, smemRows (host-sized)
+    for (int i = tid; i < nrows * nvec; i += RS_THREADS) {
+        const int r = i / nvec, k = i - r * nvec;
+        // rows are 128-byte pitched and start 32 bytes into the pitch: column multiples of 16 are 16-byte aligned
+        *reinterpret_cast<uint4*>(rsSmem + r * smemPitch + 16 * k) =
+            *reinterpret_cast<const uint4*>(S + (size_t)(ry0 + r) * src.pitch + cx0 + 16 * k);
+    }
+    __syncthreads();
+    const int x4 = x0 + 4 * (tid & 31);
+    if (x4 >= dst.w) return;
+    // column setup, once per thread: source offsets (relative to the staged window) and 11-bit coefficients
     int sx[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int2 xt = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
-        sx[i] = xt.x; sx1[i] = min(xt.x + 1, src.w - 1);
+        sx[i] = xt.x - cx0; sx1[i] = min(xt.x + 1, src.w - 1) - cx0;
         a0[i] = xt.y & 0xffff; a1[i] = xt.y >> 16;
     }
     auto hrow = [&](int sy, int (&h)[4]) {
-        const uint8_t* r = S + (size_t)sy * src.pitch;
+        const uint8_t* r = rsSmem + (sy - ry0) * smemPitch;
 #pragma unroll
         for (int i = 0; i < 4; i++) h[i] = (r[sx[i]] * a0[i] + r[sx1[i]] * a1[i]) >> 4;
     };
     int ha[4], hb[4];
     int ia = -1, ib = -1;
-    const int rows = min(RS_ROWS, dst.h - y0);
-    for (int r = 0; r < rows; r++) {
-        const int4 yt = __ldg(ytab + dst.ytabOff + y0 + r);               // {sy0, sy1, b0, b1}: warp-uniform
+    const int yb = y0 + 8 * (tid >> 5), ye = min(yb + 8, dst.h);
+    for (int y = yb; y < ye; y++) {
+        const int4 yt = __ldg(ytab + dst.ytabOff + y);                    // {sy0, sy1, b0, b1}: warp-uniform
         if (yt.x != ia) {
             if (yt.x == ib) {
 #pragma unroll
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resize_kernel(uint8_t* __restri
             const int v = (((yt.z * ha[i]) >> 16) + ((yt.w * hb[i]) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 0xff) << (8 * i);
         }
-        *reinterpret_cast<uint32_t*>(D + (size_t)(y0 + r) * dst.pitch + x4) = out;   // row padding absorbs the tail
+        *reinterpret_cast<uint32_t*>(D + (size_t)y * dst.pitch + x4) = out;   // row padding absorbs the tail
     }
 }
 
@@ -973,9 +988,11 @@ void launch_pyramid(Ctx& c, int n)
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& d = g.lv[l];
         if (d.w <= 0 || d.h <= 0 || st.resizeTileCount[l] == 0) break;
-        dim3 grid((st.resizeTileCount[l] + RS_WARPS - 1) / RS_WARPS, n);
-        resize_kernel<<<grid, RS_WARPS * 32, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                            st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l]);
+        dim3 grid(st.resizeTileCount[l], n);
+        const size_t smem = (size_t)st.resizeSmemPitch[l] * st.resizeSmemRows[l];
+        resize_kernel<<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
+                                                           st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
+                                                           st.resizeSmemPitch[l], st.resizeSmemRows[l]);
         c.launches++;
     }
     border_kernel<<<dim3(g.nlevels * BD_CHUNKS, n), 128, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
