@@ -256,15 +256,52 @@ void drain_stage_events(Ctx& c)
     c.pending.clear();
 }
 
-static int run_extract(Ctx& c, int n)
+static void enqueue_extract_kernels(Ctx& c, int n)
 {
-    c.stereoValid = false;
     { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
     { StageTimer t(c, 2); launch_fast(c, n); }
     { StageTimer t(c, 3); launch_blur(c, n); }
     { StageTimer t(c, 4); launch_octree(c, n); }
     { StageTimer t(c, 5); launch_describe(c, n); }
-    ORBB200_CUDA_OK(c, cudaGetLastError());
+}
+
+// The ~20 launches of one extraction are captured once per (shape, image count) into a CUDA graph and replayed:
+// for single frames (the real-time use of the drop-in) the CPU launch cost is a large part of the latency.
+// Per-stage timing needs events between the kernels, so it uses the plain launches.
+static int run_extract(Ctx& c, int n)
+{
+    c.stereoValid = false;
+    if (c.timing || !c.useGraphs) {
+        enqueue_extract_kernels(c, n);
+        ORBB200_CUDA_OK(c, cudaGetLastError());
+        return ORBB200_OK;
+    }
+    ShapeTables* st = const_cast<ShapeTables*>(c.cur);
+    auto it = st->graphs.find(n);
+    if (it == st->graphs.end()) {
+        // warm the lazily configured kernel attributes outside the capture, then capture
+        const long long before = c.launches;
+        enqueue_extract_kernels(c, n);
+        ORBB200_CUDA_OK(c, cudaGetLastError());
+        const long long perRun = c.launches - before;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        ORBB200_CUDA_OK(c, cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_extract_kernels(c, n);
+        c.launches -= perRun;                      // the capture pass enqueues nothing
+        cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {                    // fall back to plain launches for this context (still the CUDA path)
+            cudaGetLastError();
+            c.useGraphs = false;
+            return ORBB200_OK;                     // the warm-up run above already produced this call's result
+        }
+        st->graphs[n] = {exec, perRun};
+        return ORBB200_OK;                         // ditto
+    }
+    ORBB200_CUDA_OK(c, cudaGraphLaunch(it->second.exec, c.stream));
+    c.launches += it->second.launches;
     return ORBB200_OK;
 }
 
@@ -396,7 +433,8 @@ void orbb200_destroy(orbb200_ctx* ctx)
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); }
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles);
+                               for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.stream) cudaStreamDestroy(c.stream);
     delete ctx;

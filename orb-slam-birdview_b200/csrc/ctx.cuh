@@ -18,6 +18,8 @@ struct ShapeTables {
     int resizeTileBase[MAX_LEVELS + 1] = {0};
     int resizeTileCount[MAX_LEVELS] = {0};
     int resizeSmemPitch[MAX_LEVELS] = {0}, resizeSmemRows[MAX_LEVELS] = {0};   // staged source window of a resize tile
+    struct GraphExec { cudaGraphExec_t exec; long long launches; };
+    std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count
     int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0, fastWorkCap = 0;   // shared-memory carve of fast_cells_kernel
 };
 
@@ -76,6 +78,7 @@ struct Ctx {
     int32_t* d_rowItems = nullptr;           // [maxBatch/2+1][stereoItemCap]
     int stereoItemCap = 0;
     bool stereoValid = false;
+    bool useGraphs = true;                   // replay the extraction launches from a CUDA graph
     bool stepStereo = false;                 // orbb200_step_enable_stereo: the batched step also runs stereo matching
     float stepMb = 0.f, stepMbf = 0.f;
 
