@@ -361,7 +361,8 @@ def run_ours(args):
     import torch
     rank, world, local, dist = dist_setup(args)
     B, P = args.frames_per_step, args.pools
-    arm = GpuArm(local, B, P, n_ctx=2)
+    NE = max(2, args.e2e_contexts)
+    arm = GpuArm(local, B, P, n_ctx=NE)
     arm.setup_data(100000 * rank + 2000)
     if args.with_stereo:
         for c in arm.ctxs:
@@ -375,7 +376,7 @@ def run_ours(args):
 
     # ---- device-resident throughput (value): CUDA events on the contexts' streams ----
     # One context / one stream by default (--two-streams alternates steps over two contexts; measured slower).
-    nctx = len(arm.ctxs) if args.two_streams else 1
+    nctx = 2 if args.two_streams else 1
     for s in range(Wm):
         arm.step_device(s % P, s % nctx)
     for c in arm.ctxs:
@@ -415,17 +416,17 @@ def run_ours(args):
         st_ms += a_ms
         st_n += a_n
 
-    # ---- end to end through the host-buffer C-ABI call: two contexts in flight ----
-    for s in range(Wm if not args.no_e2e else 0):
-        arm.step_host(s % P, s % 2)
+    # ---- end to end through the host-buffer C-ABI call: NE contexts in flight ----
+    for s in range(max(Wm, 2 * NE) if not args.no_e2e else 0):
+        arm.step_host(s % P, s % NE)
     for c in arm.ctxs:
         c.sync()
     barrier()
     t0 = time.perf_counter()
     for s in range(K if not args.no_e2e else 0):
-        ci = s % 2
-        if s >= 2:
-            arm.ctxs[ci].sync()          # results of step s-2 are on the host: consume before reuse
+        ci = s % NE
+        if s >= NE:
+            arm.ctxs[ci].sync()          # results of step s-NE are on the host: consume before reuse
             _ = int(arm.h_out[ci]["nm"][0])
         arm.step_host(s % P, ci)
     for c in arm.ctxs:
@@ -445,6 +446,16 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+
+    # host->device copy rate of this box (pinned, one stream): the floor under the host-buffer leg
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    arm.d_imgs[0].copy_(arm.h_imgs[0], non_blocking=True)
+    pe0.record()
+    for _ in range(4):
+        arm.d_imgs[0].copy_(arm.h_imgs[0], non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * arm.h_imgs[0].numel() / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
 
     frames_total = world * B * K
     value = frames_total / (ms * 1e-3)
@@ -497,7 +508,7 @@ def run_ours(args):
                    "l2": f"{P} rotating input batches of {2 * B} images + {2 * B}-image pyramid/blur pools: working set "
                          f"{working_set_mb(B, P):.0f} MB per GPU > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": arm.h2d_bytes(), "d2h_bytes_per_step": arm.d2h_bytes(),
-                "ms_per_step": e2e_ms / K, "contexts_in_flight": 2},
+                "ms_per_step": e2e_ms / K, "contexts_in_flight": NE, "h2d_copy_gbs_measured": h2d_gbs},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -599,6 +610,7 @@ def main():
     ap.add_argument("--with-stereo", action="store_true", help="also run ComputeStereoMatches in the step (side measurement; not the C2 headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
     ap.add_argument("--two-streams", action="store_true", help="device-resident leg alternating over two contexts (measured slower: kernels of the two streams contend)")
+    ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts (streams) the host-buffer leg keeps in flight")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

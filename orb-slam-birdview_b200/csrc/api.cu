@@ -1,6 +1,7 @@
 // C ABI of liborbb200.so (include/orbb200.h): context, geometry, host/device entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -173,16 +174,20 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                 if (maxX > L.maxBX) maxX = (float)L.maxBX;
                 cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
                 cells.push_back(make_int4((int)L.off, L.pitch, (int)L.candOff, L.candCap));
+                cells.push_back(make_int4(0, 0, 0, 0));
                 {   // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
                     const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3;
                     const int wi = x1 - x0 - 6, hi = th - 6;
                     if (wi > 0 && hi > 0) {
                         const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1;
+                        const int nw = (x1 - xa + 3) >> 2;
+                        // floor(i / d) == umulhi(i, 2^32 / d + 1) for the small i used; d == 1 is special-cased in the kernel
+                        cells.back() = make_int4((int)(0xffffffffu / (uint32_t)nw + 1u), (int)(0xffffffffu / (uint32_t)npr + 1u), 0, 0);
                         const int P = FT_PITCH;
                         st.fastTileWords = std::max(st.fastTileWords, th * P);
                         st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
                         st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
-                        st.fastWorkCap = std::max(st.fastWorkCap, ((hi * npr + 1) & ~1) + 2);
+                        st.fastWorkCap = std::max(st.fastWorkCap, ((hi * npr + 1) & ~1) + 128);   // per-warp list segments: total + slack
                     }
                 }
             }
@@ -206,6 +211,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
         }
     }
     st.nBlurTiles = (int)btiles.size();
+    st.nFastCells = (int)(cells.size() / 3);
     auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {
         if (bytes == 0) bytes = 16;
         if (cudaMalloc(dptr, bytes) != cudaSuccess) return false;
@@ -256,11 +262,25 @@ void drain_stage_events(Ctx& c)
     c.pending.clear();
 }
 
-static void enqueue_extract_kernels(Ctx& c, int n)
+// fork == true: the blur (FMA pipe + memory bound; only the descriptors need it) runs on a second stream beside
+// FAST + octree (integer-ALU bound) and joins before the descriptor kernel.  In a captured graph this becomes
+// two parallel branches.  With per-stage timing the stages run back to back on one stream.
+static void enqueue_extract_kernels(Ctx& c, int n, bool fork)
 {
     { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
+    if (fork) {
+        cudaEventRecord(c.evFork, c.stream);
+        cudaStreamWaitEvent(c.stream2, c.evFork, 0);
+        launch_blur(c, n, c.stream2);
+        cudaEventRecord(c.evJoin, c.stream2);
+        launch_fast(c, n);
+        launch_octree(c, n);
+        cudaStreamWaitEvent(c.stream, c.evJoin, 0);
+        launch_describe(c, n);
+        return;
+    }
     { StageTimer t(c, 2); launch_fast(c, n); }
-    { StageTimer t(c, 3); launch_blur(c, n); }
+    { StageTimer t(c, 3); launch_blur(c, n, c.stream); }
     { StageTimer t(c, 4); launch_octree(c, n); }
     { StageTimer t(c, 5); launch_describe(c, n); }
 }
@@ -272,7 +292,7 @@ static int run_extract(Ctx& c, int n)
 {
     c.stereoValid = false;
     if (c.timing || !c.useGraphs) {
-        enqueue_extract_kernels(c, n);
+        enqueue_extract_kernels(c, n, !c.timing && c.forkBlur);
         ORBB200_CUDA_OK(c, cudaGetLastError());
         return ORBB200_OK;
     }
@@ -281,13 +301,13 @@ static int run_extract(Ctx& c, int n)
     if (it == st->graphs.end()) {
         // warm the lazily configured kernel attributes outside the capture, then capture
         const long long before = c.launches;
-        enqueue_extract_kernels(c, n);
+        enqueue_extract_kernels(c, n, c.forkBlur);
         ORBB200_CUDA_OK(c, cudaGetLastError());
         const long long perRun = c.launches - before;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         ORBB200_CUDA_OK(c, cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_extract_kernels(c, n);
+        enqueue_extract_kernels(c, n, c.forkBlur);
         c.launches -= perRun;                      // the capture pass enqueues nothing
         cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
         if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
@@ -356,7 +376,12 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     c.device = device;
     auto fail = [&](const std::string& m, int code) { g_create_err = m; orbb200_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed", ORBB200_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess)
+        return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
+    c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
     c.scale.resize(nlevels); c.sigma2.resize(nlevels); c.invScale.resize(nlevels); c.invSigma2.resize(nlevels); c.quota.resize(nlevels);
@@ -436,6 +461,9 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
+    if (c.evFork) cudaEventDestroy(c.evFork);
+    if (c.evJoin) cudaEventDestroy(c.evJoin);
+    if (c.stream2) cudaStreamDestroy(c.stream2);
     if (c.stream) cudaStreamDestroy(c.stream);
     delete ctx;
 }

@@ -11,7 +11,7 @@ struct ShapeTables {
     Geom g;
     int2* d_xtab = nullptr;     // resize: per output x of levels>=1: {sx, a0 | a1<<16}
     int4* d_ytab = nullptr;     // resize: per output y of levels>=1: {sy0, sy1, b0, b1}
-    int4* d_cells = nullptr;    // FAST cells of all levels, 2 x int4 each: {x0|y0<<16, x1|y1<<16, level, order}, {level offset, pitch, candOff, candCap}
+    int4* d_cells = nullptr;    // FAST cells of all levels, 3 x int4 each: {x0|y0<<16, x1|y1<<16, level, order}, {level offset, pitch, candOff, candCap}, {2^32/nw+1, 2^32/npr+1, -, -}
     int4* d_blurTiles = nullptr;  // blur tiles of all levels: {level, x0, y0, 0}, 128 x 32 pixels each
     int nBlurTiles = 0;
     int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1: {level, x0, y0, 0}, 128 x RS_ROWS pixels each
@@ -20,6 +20,7 @@ struct ShapeTables {
     int resizeSmemPitch[MAX_LEVELS] = {0}, resizeSmemRows[MAX_LEVELS] = {0};   // staged source window of a resize tile
     struct GraphExec { cudaGraphExec_t exec; long long launches; };
     std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count
+    int nFastCells = 0;         // entries of d_cells (cells the reference skips at the image edge are not listed)
     int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0, fastWorkCap = 0;   // shared-memory carve of fast_cells_kernel
 };
 
@@ -41,6 +42,8 @@ struct StepPlan {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // side branch of the extraction graph (blur runs beside FAST + octree)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;
     long long launches = 0;
 
@@ -78,6 +81,7 @@ struct Ctx {
     int32_t* d_rowItems = nullptr;           // [maxBatch/2+1][stereoItemCap]
     int stereoItemCap = 0;
     bool stereoValid = false;
+    bool forkBlur = true;                    // blur on the side stream (ORBB200_SERIAL=1 in the environment turns it off)
     bool useGraphs = true;                   // replay the extraction launches from a CUDA graph
     bool stepStereo = false;                 // orbb200_step_enable_stereo: the batched step also runs stereo matching
     float stepMb = 0.f, stepMbf = 0.f;

@@ -308,29 +308,91 @@ __device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (
     return s - 0x02000200u;
 }
 
+// The 16 ring pairs around the pixel pair whose centre word is t[0] (tile pitch FT_PITCH).
+// ring order k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+__device__ __forceinline__ void fast_load_ring(const uint32_t* t, uint32_t (&r)[16])
+{
+    constexpr int P = FT_PITCH;
+    {
+        const uint32_t* p = t + 3 * P;                          // dy = +3 : dx -1,0,1
+        const uint32_t wl = p[-1], wc = p[0], wr = p[1];
+        r[15] = __funnelshift_r(wl, wc, 16); r[0] = wc; r[1] = __funnelshift_r(wc, wr, 16);
+    }
+    {
+        const uint32_t* p = t - 3 * P;                          // dy = -3
+        const uint32_t wl = p[-1], wc = p[0], wr = p[1];
+        r[9] = __funnelshift_r(wl, wc, 16); r[8] = wc; r[7] = __funnelshift_r(wc, wr, 16);
+    }
+    r[14] = t[2 * P - 1]; r[2] = t[2 * P + 1];                  // dy=+2: dx -2, +2
+    r[10] = t[-2 * P - 1]; r[6] = t[-2 * P + 1];                // dy=-2
+    {
+        const uint32_t* p = t + P;                              // dy = +1 : dx -3, +3
+        r[13] = __funnelshift_r(p[-2], p[-1], 16); r[3] = __funnelshift_r(p[1], p[2], 16);
+    }
+    {
+        const uint32_t* p = t - P;                              // dy = -1
+        r[11] = __funnelshift_r(p[-2], p[-1], 16); r[5] = __funnelshift_r(p[1], p[2], 16);
+    }
+    r[12] = __funnelshift_r(t[-2], t[-1], 16); r[4] = __funnelshift_r(t[1], t[2], 16);   // dy = 0
+}
+
+// Necessary condition for score >= thr on either pixel of the pair: a 9-arc contains one pixel of every
+// opposite ring pair (k, k+8), so a bright arc needs max(p_k, p_k+8) > v + thr for all k and a dark arc needs
+// min(p_k, p_k+8) < v - thr.  Tested on the three opposite pairs whose words are aligned with the centre
+// word (k = 0, 2, 6: no funnel shifts): 7 loads + ~13 ALU ops instead of the ~130-instruction network.
+// Tp = (thr + 1) in both lanes.  Returns non-zero when a pixel of the pair may reach thr.
+__device__ __forceinline__ uint32_t fast_may_pass(const uint32_t* t, uint32_t Tp)
+{
+    constexpr int P = FT_PITCH;
+    const uint32_t c = t[0];
+    const uint32_t r0 = t[3 * P], r8 = t[-3 * P];
+    const uint32_t r2 = t[2 * P + 1], r10 = t[-2 * P - 1];
+    const uint32_t r6 = t[-2 * P + 1], r14 = t[2 * P - 1];
+    const uint32_t A = min3s(__vmaxs2(r0, r8), __vmaxs2(r2, r10), __vmaxs2(r6, r14));   // bright: A >= v + thr + 1
+    const uint32_t B = max3s(__vmins2(r0, r8), __vmins2(r2, r10), __vmins2(r6, r14));   // dark:   B <= v - thr - 1
+    // per-lane >= via bit 15 of a biased difference; every lane stays within [0x8000 - 511, 0x8000 + 255]
+    const uint32_t d1 = (A | 0x80008000u) - (c + Tp);
+    const uint32_t d2 = ((c | 0x80008000u) - Tp) - B;
+    return (d1 | d2) & 0x80008000u;
+}
+
+constexpr int FT_WARPS = FT_THREADS / 32;
+
+// entry j of a list kept as FT_WARPS per-warp segments of `seg` slots holding n[0..FT_WARPS) entries
+__device__ __forceinline__ int seg_list_at(const uint16_t* list, int seg, const int (&n)[FT_WARPS], int j)
+{
+    int w = 0;
+#pragma unroll
+    for (int k = 0; k < FT_WARPS - 1; k++)
+        if (j >= n[k]) { j -= n[k]; w++; } else break;
+    return list[w * seg + j];
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
                                                                    int minTh, int iniTh, const int4* __restrict__ cells,
                                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
-                                                                   int tileWords, int scrWords, int clistCap)
+                                                                   int tileWords, int scrWords, int clistCap, int workCap)
 {
     // tile[r][1+m] = pixels (2m, 2m+1) of cell-image row r as u16x2; score tile in the same layout with a
     // zero row above/below.  Row pitch == pairs-per-row (mod 32): the flattened (row, pair) -> lane mapping
     // then walks consecutive banks across row boundaries (no bank conflicts).
-    // Shared memory is sized by the host for the largest cell of this image shape (typically ~18 KB).
+    // Shared memory is sized by the host for the largest cell of this image shape (typically ~19 KB).
     extern __shared__ uint32_t ftSmem[];
     uint32_t* tile = ftSmem;
     uint32_t* scr = tile + tileWords;
     uint32_t* clist = scr + scrWords;
     uint16_t* wlist = reinterpret_cast<uint16_t*>(clist + clistCap);    // pairs that may hold a local maximum
-    __shared__ int sN, sNini, sBase, sOut, sW;
+    uint16_t* qlist = wlist + workCap;                                  // pairs that pass the quick test
+    __shared__ int sN, sBase, sQn[FT_WARPS], sWn[FT_WARPS];
 
     const int img = blockIdx.y;
-    const int4 cell = __ldg(cells + 2 * blockIdx.x);         // {x0|y0<<16, x1|y1<<16, level, -}
-    const int4 lvl = __ldg(cells + 2 * blockIdx.x + 1);      // {level byte offset, pitch, candOff, candCap}
+    const int4 cell = __ldg(cells + 3 * blockIdx.x);         // {x0|y0<<16, x1|y1<<16, level, -}
+    const int4 lvl = __ldg(cells + 3 * blockIdx.x + 1);      // {level byte offset, pitch, candOff, candCap}
+    const int4 mg = __ldg(cells + 3 * blockIdx.x + 2);       // {2^32/nw + 1, 2^32/npr + 1, -, -}
     const int x0 = cell.x & 0xffff, y0 = cell.x >> 16, x1 = cell.y & 0xffff, y1 = cell.y >> 16;
     const int level = cell.z;
     const int pitch = lvl.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int xa = x0 & ~3;
     const int tw = x1 - xa, th = y1 - y0;
     const int wi = x1 - x0 - 6, hi = th - 6;
@@ -343,110 +405,136 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     // compile-time pitch turns every ring offset into an immediate.
     constexpr int P = FT_PITCH;
 
-    if (tid == 0) { sN = 0; sNini = 0; sOut = 0; sW = 0; }
     // zero frame of the score tile: the rows above/below and the words left/right of the inner span
     for (int i = tid; i < P; i += FT_THREADS) { scr[i] = 0; scr[(hi + 1) * P + i] = 0; }
     for (int i = tid; i < hi; i += FT_THREADS) { scr[(i + 1) * P + m0] = 0; scr[(i + 1) * P + m1 + 2] = 0; }
-    // load the cell image: 32-bit words widened to u16 pairs; pixel column tc lives in word 1 + tc/2
+    // words next to the loaded span are read by masked lanes only, but must hold in-range values: a lane
+    // outside [0x6400, 0x64ff] would borrow into its neighbour lane in the packed subtraction (or be a NaN)
+    for (int r = tid; r < th; r += FT_THREADS) {
+        uint32_t* t = tile + r * P;
+        t[0] = FT_BIAS; t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS;
+    }
+    // load the cell image: 32-bit words widened to u16 pairs (+ bias); pixel column tc lives in word 1 + tc/2
     const uint8_t* S = pyr + (size_t)img * pyrBytes + (unsigned)lvl.x + (size_t)y0 * pitch + xa;
-    const uint32_t magicNw = 0xffffffffu / (uint32_t)nw + 1u;
+    const uint32_t magicNw = (uint32_t)mg.x, magicNpr = (uint32_t)mg.y;
     for (int i = tid; i < th * nw; i += FT_THREADS) {
         const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
         const int k = i - r * nw;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (size_t)r * pitch + 4 * k);
-        uint32_t* t = tile + r * P;
-        t[1 + 2 * k] = __byte_perm(v, 0, 0x4140) | FT_BIAS;
-        t[2 + 2 * k] = __byte_perm(v, 0, 0x4342) | FT_BIAS;
-        // words next to the loaded span are read by masked lanes only, but must hold in-range values: a lane
-        // outside [0x6400, 0x64ff] would borrow into its neighbour lane in the packed subtraction (or be a NaN)
-        if (k == 0) t[0] = FT_BIAS;
-        if (k == nw - 1) { t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS; }
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(S + (unsigned)(r * pitch + 4 * k));
+        uint32_t* t = tile + r * P + 2 * k;
+        t[1] = __byte_perm(v, FT_BIAS, 0x5150);
+        t[2] = __byte_perm(v, FT_BIAS, 0x5352);
     }
-    __syncthreads();
 
-    // ---- scores: pairs (2m, 2m+1) covering the inner columns ----
-    const uint32_t magicNpr = 0xffffffffu / (uint32_t)npr + 1u;
-    for (int i = tid; i < hi * npr; i += FT_THREADS) {
-        const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
-        const int m = m0 + (i - rr * npr);
-        const uint32_t* t = tile + (rr + 3) * P + m + 1;
-        // ring order k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-        uint32_t r[16];
-        {
-            const uint32_t* p = t + 3 * P;                          // dy = +3 : dx -1,0,1
-            const uint32_t wl = p[-1], wc = p[0], wr = p[1];
-            r[15] = __funnelshift_r(wl, wc, 16); r[0] = wc; r[1] = __funnelshift_r(wc, wr, 16);
-        }
-        {
-            const uint32_t* p = t - 3 * P;                          // dy = -3
-            const uint32_t wl = p[-1], wc = p[0], wr = p[1];
-            r[9] = __funnelshift_r(wl, wc, 16); r[8] = wc; r[7] = __funnelshift_r(wc, wr, 16);
-        }
-        r[14] = t[2 * P - 1]; r[2] = t[2 * P + 1];                  // dy=+2: dx -2, +2
-        r[10] = t[-2 * P - 1]; r[6] = t[-2 * P + 1];                // dy=-2
-        {
-            const uint32_t* p = t + P;                              // dy = +1 : dx -3, +3
-            r[13] = __funnelshift_r(p[-2], p[-1], 16); r[3] = __funnelshift_r(p[1], p[2], 16);
-        }
-        {
-            const uint32_t* p = t - P;                              // dy = -1
-            r[11] = __funnelshift_r(p[-2], p[-1], 16); r[5] = __funnelshift_r(p[1], p[2], 16);
-        }
-        r[12] = __funnelshift_r(t[-2], t[-1], 16); r[4] = __funnelshift_r(t[1], t[2], 16);   // dy = 0
-        uint32_t s = fast_score_pair(t[0], r);
-        const int c = 2 * m;
-        if (c < cx0 || c >= cx1) s &= 0xffff0000u;                  // pixels outside the inner rectangle score 0
-        if (c + 1 < cx0 || c + 1 >= cx1) s &= 0x0000ffffu;
-        scr[(rr + 1) * P + m + 1] = s;
-        // a pair goes on the NMS work list when one of its pixels reaches minThFAST
-        if ((int)(s & 0xffffu) >= minTh || (int)(s >> 16) >= minTh) wlist[atomicAdd(&sW, 1)] = (uint16_t)i;
-    }
-    __syncthreads();
+    // cv::FAST(cell, iniThFAST) and, only when that leaves the cell empty, cv::FAST(cell, minThFAST)
+    // (reference :809-816).  Per pass: quick test on every pair -> full score network on the pairs that pass
+    // (every pixel that reaches the threshold is among them, the others score 0 exactly as a non-corner does
+    // in cv::FAST's score buffer) -> 3x3 strict-greater NMS.
+    // Work lists are kept as one segment per warp, filled with ballots (no atomics).
+    const int total = hi * npr;
+    const int qseg = (total + FT_WARPS - 1) / FT_WARPS;                 // pairs per warp in the quick test
+    const int wseg = ((total + FT_THREADS - 1) / FT_THREADS) * 32;      // upper bound of a warp's share of the score loop
+    const unsigned ltmask = (1u << lane) - 1u;
+    int nEmit = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int thr = pass ? minTh : iniTh;
+        const uint32_t Tp = (uint32_t)(min(max(thr, 0), 255) + 1) * 0x00010001u;
+        if (tid == 0) sN = 0;
+        __syncthreads();                                                // tile loaded / previous pass done
 
-    // ---- NMS + threshold on the listed pairs (raw neighbour scores suffice: a neighbour below the
-    //      threshold is below S anyway) ----
-    const int nWork = sW;
-    for (int j = tid; j < nWork; j += FT_THREADS) {
-        const int i = wlist[j];
-        const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
-        const int m = m0 + (i - rr * npr);
-        const uint32_t* q = scr + (rr + 1) * P + m + 1;
-        const uint32_t w = q[0];
-        const int sl = w & 0xffff, sh = w >> 16;
-        const uint32_t u0 = q[-P - 1], u1 = q[-P], u2 = q[-P + 1];
-        const uint32_t c0 = q[-1], c2 = q[1];
-        const uint32_t d0 = q[P - 1], d1 = q[P], d2 = q[P + 1];
-        uint32_t nb = max3s(u1, __funnelshift_r(u0, u1, 16), __funnelshift_r(u1, u2, 16));
-        nb = max3s(nb, __funnelshift_r(c0, w, 16), __funnelshift_r(w, c2, 16));
-        nb = max3s(nb, d1, __funnelshift_r(d0, d1, 16));
-        nb = __vmaxs2(nb, __funnelshift_r(d1, d2, 16));
-        const int nl = nb & 0xffff, nh = nb >> 16;
-        const int ry = y0 + rr + 3 - FAST_BORDER;                   // region coordinates
+        // ---- quick test; also clears the pair's score word ----
+        {
+            const int cbeg = wid * qseg, cend = min(cbeg + qseg, total);
+            uint16_t* myq = qlist + cbeg;
+            int cnt = 0;
+            for (int b = cbeg; b < cend; b += 32) {
+                const int i = min(b + lane, cend - 1);                  // surplus lanes repeat the last pair
+                const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
+                const int m = m0 + (i - rr * npr);
+                const uint32_t hit = fast_may_pass(tile + (rr + 3) * P + m + 1, Tp);
+                scr[(rr + 1) * P + m + 1] = 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, hit != 0 && b + lane < cend);
+                if ((bal >> lane) & 1u) myq[cnt + __popc(bal & ltmask)] = (uint16_t)i;
+                cnt += __popc(bal);
+            }
+            if (lane == 0) sQn[wid] = cnt;
+        }
+        __syncthreads();
+
+        // ---- scores of the listed pairs ----
+        {
+            int nq[FT_WARPS], nQ = 0;
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int sv = e ? sh : sl, nv = e ? nh : nl;
-            if (sv >= minTh && sv > nv) {
-                const int slot = atomicAdd(&sN, 1);
-                if (sv >= iniTh) atomicAdd(&sNini, 1);
-                const int rx = xa + 2 * m + e - FAST_BORDER;
-                if (slot < clistCap) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sv << 24);
+            for (int k = 0; k < FT_WARPS; k++) { nq[k] = sQn[k]; nQ += nq[k]; }
+            uint16_t* myw = wlist + wid * wseg;
+            int cnt = 0;
+            for (int b = wid * 32; b < nQ; b += FT_THREADS) {
+                const int j = min(b + lane, nQ - 1);
+                const int i = seg_list_at(qlist, qseg, nq, j);
+                const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
+                const int m = m0 + (i - rr * npr);
+                const uint32_t* t = tile + (rr + 3) * P + m + 1;
+                uint32_t r[16];
+                fast_load_ring(t, r);
+                uint32_t s = fast_score_pair(t[0], r);
+                const int c = 2 * m;
+                if (c < cx0 || c >= cx1) s &= 0xffff0000u;              // pixels outside the inner rectangle score 0
+                if (c + 1 < cx0 || c + 1 >= cx1) s &= 0x0000ffffu;
+                scr[(rr + 1) * P + m + 1] = s;
+                // a pair goes on the NMS work list when one of its pixels reaches the threshold
+                const bool keep = ((int)(s & 0xffffu) >= thr || (int)(s >> 16) >= thr) && b + lane < nQ;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if ((bal >> lane) & 1u) myw[cnt + __popc(bal & ltmask)] = (uint16_t)i;
+                cnt += __popc(bal);
+            }
+            if (lane == 0) sWn[wid] = cnt;
+        }
+        __syncthreads();
+
+        // ---- NMS + threshold on the listed pairs (raw neighbour scores suffice: a neighbour below the
+        //      threshold is below S anyway) ----
+        {
+            int nwk[FT_WARPS], nWork = 0;
+#pragma unroll
+            for (int k = 0; k < FT_WARPS; k++) { nwk[k] = sWn[k]; nWork += nwk[k]; }
+            for (int j = tid; j < nWork; j += FT_THREADS) {
+                const int i = seg_list_at(wlist, wseg, nwk, j);
+                const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
+                const int m = m0 + (i - rr * npr);
+                const uint32_t* q = scr + (rr + 1) * P + m + 1;
+                const uint32_t w = q[0];
+                const int sl = w & 0xffff, sh = w >> 16;
+                const uint32_t u0 = q[-P - 1], u1 = q[-P], u2 = q[-P + 1];
+                const uint32_t c0 = q[-1], c2 = q[1];
+                const uint32_t d0 = q[P - 1], d1 = q[P], d2 = q[P + 1];
+                uint32_t nb = max3s(u1, __funnelshift_r(u0, u1, 16), __funnelshift_r(u1, u2, 16));
+                nb = max3s(nb, __funnelshift_r(c0, w, 16), __funnelshift_r(w, c2, 16));
+                nb = max3s(nb, d1, __funnelshift_r(d0, d1, 16));
+                nb = __vmaxs2(nb, __funnelshift_r(d1, d2, 16));
+                const int nl = nb & 0xffff, nh = nb >> 16;
+                const int ry = y0 + rr + 3 - FAST_BORDER;               // region coordinates
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int sv = e ? sh : sl, nv = e ? nh : nl;
+                    if (sv >= thr && sv > nv) {
+                        const int slot = atomicAdd(&sN, 1);
+                        const int rx = xa + 2 * m + e - FAST_BORDER;
+                        if (slot < clistCap) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sv << 24);
+                    }
+                }
             }
         }
+        __syncthreads();
+        nEmit = min(sN, clistCap);
+        if (nEmit > 0) break;
     }
-    __syncthreads();
-    const int nAll = min(sN, clistCap), nIni = sNini;
-    const int nEmit = nIni > 0 ? nIni : nAll;
     if (nEmit == 0) return;
     if (tid == 0) sBase = atomicAdd(&candCount[img * MAX_LEVELS + level], nEmit);
     __syncthreads();
     uint32_t* out = cand + (size_t)img * candPerImg + (unsigned)lvl.z;
     const int base = sBase, candCap = lvl.w;
-    for (int i = tid; i < nAll; i += FT_THREADS) {
-        const uint32_t v = clist[i];
-        if (nIni > 0 && (int)(v >> 24) < iniTh) continue;
-        const int o = atomicAdd(&sOut, 1);
-        if (base + o < candCap) out[base + o] = v;
-    }
+    for (int i = tid; i < nEmit; i += FT_THREADS)
+        if (base + i < candCap) out[base + i] = clist[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -999,12 +1087,12 @@ void launch_pyramid(Ctx& c, int n)
     c.launches++;
 }
 
-void launch_blur(Ctx& c, int n)
+void launch_blur(Ctx& c, int n, cudaStream_t stream)
 {
     const Geom& g = c.cur->g;
     if (c.cur->nBlurTiles == 0) return;
     dim3 grid((c.cur->nBlurTiles + BL_WARPS - 1) / BL_WARPS, n);
-    blur_kernel<<<grid, BL_WARPS * 32, 0, c.stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, c.cur->d_blurTiles, c.cur->nBlurTiles);
+    blur_kernel<<<grid, BL_WARPS * 32, 0, stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, c.cur->d_blurTiles, c.cur->nBlurTiles);
     c.launches++;
 }
 
@@ -1012,17 +1100,17 @@ void launch_fast(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
-    if (g.totalCells > 0) {
+    if (c.cur->nFastCells > 0) {
         const ShapeTables& st = *c.cur;
-        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap) + sizeof(uint16_t) * (size_t)st.fastWorkCap;
+        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap) + sizeof(uint16_t) * 2 * (size_t)st.fastWorkCap;
         static thread_local size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
-        dim3 grid(g.totalCells, n);
+        dim3 grid(st.nFastCells, n);
         fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_cells, c.d_cand,
-                                                               c.d_candCount, st.fastTileWords, st.fastScrWords, st.fastClistCap);
+                                                               c.d_candCount, st.fastTileWords, st.fastScrWords, st.fastClistCap, st.fastWorkCap);
         c.launches++;
     }
 }

@@ -74,7 +74,7 @@ struct Ctx;
 // ---- kernels launchers (extract.cu) ----
 void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);
 void launch_pyramid(Ctx& c, int n);
-void launch_blur(Ctx& c, int n);
+void launch_blur(Ctx& c, int n, cudaStream_t stream);
 void launch_fast(Ctx& c, int n);
 void launch_octree(Ctx& c, int n);
 void launch_describe(Ctx& c, int n);
