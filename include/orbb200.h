@@ -218,6 +218,40 @@ int orbb200_compute_stereo_matches(orbb200_ctx* ctx, int img_left, int img_right
 int orbb200_frame_from_extract_stereo(orbb200_ctx* ctx, orbb200_frame** f, int img_left,
                                       float min_x, float min_y, float inv_w, float inv_h);
 
+/* ---- local map on the device: Frame::isInFrustum + SearchLocalPoints ---------------------------------------
+ * Tracking::SearchLocalPoints (src/Tracking.cc:1610-1660) projects every local map point with
+ * Frame::isInFrustum (src/Frame.cc:436-492; MapPoint::PredictScale src/MapPoint.cc:402-417) and then calls
+ * ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).  The map snapshot
+ * (world position, mean viewing direction, mfMaxDistance / mfMinDistance, representative descriptor per point) stays
+ * on the device between frames, so a frame only sends its pose. */
+typedef struct orbb200_map orbb200_map;
+typedef struct {
+    float Rcw[9], tcw[3], Ow[3];          /* Frame::mRcw (row-major), mtcw, mOw */
+    float fx, fy, cx, cy, mbf;
+    float min_x, max_x, min_y, max_y;     /* Frame::mnMinX .. mnMaxY */
+    float log_scale_factor;               /* Frame::mfLogScaleFactor */
+    int32_t n_levels;                     /* Frame::mnScaleLevels */
+} orbb200_camera_pose;
+int orbb200_map_upload(orbb200_ctx* ctx, orbb200_map** map, int n, const float* pos /*[n][3]*/, const float* normal /*[n][3]*/,
+                       const float* max_distance /*[n] mfMaxDistance*/, const float* min_distance /*[n] mfMinDistance*/,
+                       const uint8_t* desc /*[n][32]*/);
+void orbb200_map_free(orbb200_map* map);
+/* Frame::isInFrustum for every map point with candidate[i] != 0 (NULL: all; the caller clears points with
+ * mnLastFrameSeen == frame id or isBad(), src/Tracking.cc:1638-1641).  Outputs (host, [n], any may be NULL) are the
+ * MapPoint::mbTrackInView / mTrackProjX / mTrackProjY / mTrackProjXR / mnTrackScaleLevel / mTrackViewCos fields.
+ * *n_in_view = nToMatch. */
+int orbb200_is_in_frustum(orbb200_ctx* ctx, const orbb200_map* map, const orbb200_camera_pose* pose, float viewing_cos_limit,
+                          const uint8_t* candidate, uint8_t* out_in_view, float* out_u, float* out_v, float* out_uR,
+                          int32_t* out_level, float* out_viewcos, int* n_in_view);
+/* isInFrustum + SearchByProjection(F, local map, th) without the queries leaving the device.  obs_pos / kp_blocked /
+ * outputs as in orbb200_search_by_projection (queries = map points); out_in_view etc. as in orbb200_is_in_frustum. */
+int orbb200_search_local_points(orbb200_ctx* ctx, const orbb200_frame* F, const orbb200_map* map,
+                                const orbb200_camera_pose* pose, float viewing_cos_limit, const uint8_t* candidate,
+                                const uint8_t* obs_pos, const uint8_t* kp_blocked, float th, float nnratio,
+                                uint8_t* out_in_view, float* out_u, float* out_v, float* out_uR, int32_t* out_level,
+                                float* out_viewcos, int* n_in_view,
+                                int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp, int* nmatches);
+
 /* ---- DBoW2 vocabulary transform ----------------------------------------------------------------------------
  * Frame::ComputeBoW (src/Frame.cc:562-569) -> ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup)
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1203,1230-1271), TF_IDF weighting + L1 scoring.  The tree is

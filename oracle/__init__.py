@@ -78,6 +78,7 @@ def lib(native=False):
         "oracle_search_by_bow": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
         "oracle_voc_create": (vp, [C.c_int, vp, vp, vp, vp, vp, C.c_int]),
         "oracle_voc_destroy": (None, [vp]),
+        "oracle_is_in_frustum": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]),
         "oracle_voc_transform": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "oracle_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
                                                       vp, vp, vp, C.c_int, vp, vp, vp, C.c_int,
@@ -384,3 +385,37 @@ class Vocabulary:
         nw, nf = C.c_int32(), C.c_int32()
         self._L.oracle_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(node), _p(bw), _p(bv), C.byref(nw), _p(fn), _p(fp), _p(fi), C.byref(nf))
         return word, node, (bw[:nw.value].copy(), bv[:nw.value].copy()), (fn[:nf.value].copy(), fp[:nf.value + 1].copy(), fi[:fp[nf.value]].copy())
+
+
+class CameraPose(C.Structure):
+    """Frame pose + intrinsics read by Frame::isInFrustum (mirror of oracle_camera_pose / orbb200_camera_pose)."""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("log_scale_factor", C.c_float), ("n_levels", C.c_int32)]
+
+
+def camera_pose(Rcw, tcw, Ow, fx, fy, cx, cy, mbf, min_x, max_x, min_y, max_y, log_scale_factor, n_levels, cls=CameraPose):
+    p = cls()
+    p.Rcw[:] = [float(v) for v in np.asarray(Rcw, np.float32).reshape(9)]
+    p.tcw[:] = [float(v) for v in np.asarray(tcw, np.float32).reshape(3)]
+    p.Ow[:] = [float(v) for v in np.asarray(Ow, np.float32).reshape(3)]
+    p.fx, p.fy, p.cx, p.cy, p.mbf = fx, fy, cx, cy, mbf
+    p.min_x, p.max_x, p.min_y, p.max_y = min_x, max_x, min_y, max_y
+    p.log_scale_factor, p.n_levels = log_scale_factor, n_levels
+    return p
+
+
+def is_in_frustum(pos, normal, max_distance, min_distance, pose, viewing_cos_limit=0.5, candidate=None):
+    """Frame::isInFrustum over an array of map points -> (nToMatch, in_view, u, v, uR, level, viewcos)."""
+    L = lib()
+    pos, normal = _c(pos, np.float32), _c(normal, np.float32)
+    n = len(pos)
+    mx, mn = _c(max_distance, np.float32), _c(min_distance, np.float32)
+    cand = _c(candidate, np.uint8)
+    iv = np.empty(n, np.uint8)
+    u, v, uR, vc = (np.empty(n, np.float32) for _ in range(4))
+    lvl = np.empty(n, np.int32)
+    k = L.oracle_is_in_frustum(n, _p(pos), _p(normal), _p(mx), _p(mn), _p(cand), C.addressof(pose), viewing_cos_limit,
+                               _p(iv), _p(u), _p(v), _p(uR), _p(lvl), _p(vc))
+    return k, iv, u, v, uR, lvl, vc

@@ -720,3 +720,73 @@ int oracle_voc_transform(const oracle_voc* V, const uint8_t* features, int n, in
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Frame::isInFrustum (reference src/Frame.cc:436-492) + MapPoint::PredictScale (src/MapPoint.cc:402-417) for an
+// array of map points: the query generation of Tracking::SearchLocalPoints (src/Tracking.cc:1634-1648).
+// cv::Mat arithmetic as OpenCV 4.x evaluates it for these shapes (checked against cv2.gemm / cv2.norm by
+// tests/ref_py/frustum_py_ref.py): 3x3 * 3x1 + 3x1 through gemm's small-matrix path = float products summed left to
+// right in float, then (float)((double)sum + (double)c); cv::norm = sqrt of a double sum of squares; Mat::dot
+// accumulates in double.  Scalar float expressions as written, no FMA contraction (oracle policy).
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+struct oracle_camera_pose {
+    float Rcw[9], tcw[3], Ow[3];
+    float fx, fy, cx, cy, mbf;
+    float min_x, max_x, min_y, max_y;
+    float log_scale_factor;
+    int32_t n_levels;
+};
+
+int oracle_is_in_frustum(int n, const float* pos, const float* normal, const float* max_distance, const float* min_distance,
+                         const uint8_t* candidate, const oracle_camera_pose* F, float viewingCosLimit,
+                         uint8_t* out_in_view, float* out_u, float* out_v, float* out_uR, int32_t* out_level, float* out_viewcos)
+{
+    int nToMatch = 0;
+    for (int i = 0; i < n; i++) {
+        out_in_view[i] = 0; out_u[i] = 0; out_v[i] = 0; out_uR[i] = 0; out_level[i] = 0; out_viewcos[i] = 0;
+        if (candidate && !candidate[i]) continue;                 // mnLastFrameSeen == current frame, or isBad()
+        const float* P = pos + 3 * i;
+        // 3D in camera coordinates: Pc = mRcw*P + mtcw
+        float Pc[3];
+        for (int r = 0; r < 3; r++) {
+            float t = F->Rcw[3 * r] * P[0] + F->Rcw[3 * r + 1] * P[1];
+            t = t + F->Rcw[3 * r + 2] * P[2];
+            Pc[r] = (float)((double)t + (double)F->tcw[r]);
+        }
+        const float PcX = Pc[0], PcY = Pc[1], PcZ = Pc[2];
+        if (PcZ < 0.0f) continue;
+        const float invz = 1.0f / PcZ;
+        const float u = F->fx * PcX * invz + F->cx;
+        const float v = F->fy * PcY * invz + F->cy;
+        if (u < F->min_x || u > F->max_x) continue;
+        if (v < F->min_y || v > F->max_y) continue;
+        const float maxDistance = 1.2f * max_distance[i];         // GetMaxDistanceInvariance, src/MapPoint.cc:380-383
+        const float minDistance = 0.8f * min_distance[i];         // GetMinDistanceInvariance, :374-377
+        const float PO[3] = {P[0] - F->Ow[0], P[1] - F->Ow[1], P[2] - F->Ow[2]};
+        const float dist = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float* Pn = normal + 3 * i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+        const float viewCos = (float)(dot / dist);
+        if (viewCos < viewingCosLimit) continue;
+        // PredictScale
+        const float ratio = max_distance[i] / dist;
+        const float c = std::ceil(std::log(ratio) / F->log_scale_factor);
+        // int conversion as x86 cvttss2si: out-of-range / NaN -> INT_MIN
+        int nScale = (c > -2147483648.f && c < 2147483648.f) ? (int)c : INT32_MIN;
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= F->n_levels) nScale = F->n_levels - 1;
+        out_in_view[i] = 1;
+        out_u[i] = u;
+        out_uR[i] = u - F->mbf * invz;
+        out_v[i] = v;
+        out_level[i] = nScale;
+        out_viewcos[i] = viewCos;
+        nToMatch++;
+    }
+    return nToMatch;
+}
+
+}  // extern "C"

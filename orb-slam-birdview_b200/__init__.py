@@ -83,6 +83,11 @@ _SIGNATURES = {
     "orbb200_voc_free": (None, [_vp]),
     "orbb200_bow_transform": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
     "orbb200_bow_transform_extracted": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_map_upload": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _vp]),
+    "orbb200_map_free": (None, [_vp]),
+    "orbb200_is_in_frustum": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_search_local_points": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i),
+                                         _vp, _vp, _vp, C.POINTER(_i)]),
     "orbb200_stereo_step_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "orbb200_stereo_step_host": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "orbb200_step_enable_stereo": (_i, [_vp, _i, _f, _f]),
@@ -95,6 +100,25 @@ _SIGNATURES = {
 class ProjQueries(C.Structure):
     """orbb200_proj_queries: device pointers of [n_frames][nq] query arrays"""
     _fields_ = [(n, C.c_void_p) for n in ("q_valid", "q_u", "q_v", "q_uR", "q_level", "q_viewcos", "q_desc", "q_obs_pos")]
+
+
+class CameraPose(C.Structure):
+    """orbb200_camera_pose: the Frame members Frame::isInFrustum reads (src/Frame.cc:436-492)"""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("log_scale_factor", C.c_float), ("n_levels", C.c_int32)]
+
+    @classmethod
+    def make(cls, Rcw, tcw, Ow, fx, fy, cx, cy, mbf, min_x, max_x, min_y, max_y, log_scale_factor, n_levels):
+        p = cls()
+        p.Rcw[:] = [float(v) for v in np.asarray(Rcw, np.float32).reshape(9)]
+        p.tcw[:] = [float(v) for v in np.asarray(tcw, np.float32).reshape(3)]
+        p.Ow[:] = [float(v) for v in np.asarray(Ow, np.float32).reshape(3)]
+        p.fx, p.fy, p.cx, p.cy, p.mbf = fx, fy, cx, cy, mbf
+        p.min_x, p.max_x, p.min_y, p.max_y = min_x, max_x, min_y, max_y
+        p.log_scale_factor, p.n_levels = log_scale_factor, n_levels
+        return p
 
 
 def load_library():
@@ -333,6 +357,41 @@ class ORBVocabulary:
         return word, node, (bw[:nw.value].copy(), bv[:nw.value].copy()), (fn[:nf.value].copy(), fp[:nf.value + 1].copy(), fi[:nfeat].copy())
 
 
+class LocalMap:
+    """Device-resident snapshot of Tracking::mvpLocalMapPoints: world position, normal, mfMaxDistance / mfMinDistance
+    and descriptor per map point.  isInFrustum mirrors Frame::isInFrustum over the whole map (src/Frame.cc:436-492)."""
+
+    def __init__(self, ctx, pos, normal, max_distance, min_distance, desc):
+        self.ctx, self._L = ctx, ctx._L
+        a = [_c(pos, np.float32), _c(normal, np.float32), _c(max_distance, np.float32), _c(min_distance, np.float32), _c(desc, np.uint8)]
+        self.n = len(a[2])
+        h = C.c_void_p()
+        ctx.check(self._L.orbb200_map_upload(ctx._h, C.byref(h), self.n, *[_p(x) for x in a]), "map_upload")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbb200_map_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _outs(self):
+        n = max(self.n, 1)
+        return (np.empty(n, np.uint8), np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32),
+                np.empty(n, np.int32), np.empty(n, np.float32))
+
+    def isInFrustum(self, pose, viewingCosLimit=0.5, candidate=None):
+        """-> (nToMatch, mbTrackInView, mTrackProjX, mTrackProjY, mTrackProjXR, mnTrackScaleLevel, mTrackViewCos)"""
+        iv, u, v, uR, lvl, vc = self._outs()
+        cand = _c(candidate, np.uint8)
+        k = C.c_int()
+        self.ctx.check(self._L.orbb200_is_in_frustum(self.ctx._h, self._h, C.addressof(pose), viewingCosLimit, _p(cand), _p(iv), _p(u), _p(v),
+                                                     _p(uR), _p(lvl), _p(vc), C.byref(k)), "isInFrustum")
+        n = self.n
+        return k.value, iv[:n], u[:n], v[:n], uR[:n], lvl[:n], vc[:n]
+
+
 class ORBmatcher:
     """Mirror of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:38-120) on flattened inputs.
 
@@ -371,6 +430,21 @@ class ORBmatcher:
         self.ctx.check(self._L.orbb200_search_by_projection(self.ctx._h, F._h, nq, *[_p(x) for x in a], th, self.mfNNratio,
                                                             _p(bi), _p(bd), _p(qk), C.byref(nm)), "SearchByProjection")
         return nm.value, bi, bd, qk[:F.n]
+
+    def SearchLocalPoints(self, F, local_map, pose, candidate=None, obs_pos=None, kp_blocked=None, th=1.0, viewingCosLimit=0.5):
+        """Tracking::SearchLocalPoints (src/Tracking.cc:1634-1660): isInFrustum over the device-resident local map, then
+        SearchByProjection(F, local map, th).  -> (nToMatch, in_view, (u, v, uR, level, viewcos), nmatches, best_idx, best_dist,
+        query_of_kp)"""
+        iv, u, v, uR, lvl, vc = local_map._outs()
+        n = local_map.n
+        a = [_c(candidate, np.uint8), _c(obs_pos, np.uint8), _c(kp_blocked, np.uint8)]
+        bi, bd = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+        qk = np.full(max(F.n, 1), -1, np.int32)
+        k, nm = C.c_int(), C.c_int()
+        self.ctx.check(self._L.orbb200_search_local_points(self.ctx._h, F._h, local_map._h, C.addressof(pose), viewingCosLimit, *[_p(x) for x in a],
+                                                           th, self.mfNNratio, _p(iv), _p(u), _p(v), _p(uR), _p(lvl), _p(vc), C.byref(k),
+                                                           _p(bi), _p(bd), _p(qk), C.byref(nm)), "SearchLocalPoints")
+        return k.value, iv[:n], (u[:n], v[:n], uR[:n], lvl[:n], vc[:n]), nm.value, bi[:n], bd[:n], qk[:F.n]
 
     def SearchByProjectionFrame(self, Cur, q_valid, q_u, q_v, q_invz, q_octave, q_angle, q_desc, q_obs_pos=None, kp_blocked=None,
                                 th=15.0, mbf=0.0, mode=0):

@@ -18,6 +18,17 @@ struct orbb200_frame {
     int cap = 0;
 };
 
+// Local map snapshot on the device + the per-point projection results of the last isInFrustum pass.
+struct orbb200_map {
+    Ctx* ctx = nullptr;
+    int n = 0;
+    float* d_pos = nullptr; float* d_normal = nullptr; float* d_maxDist = nullptr; float* d_minDist = nullptr;
+    uint8_t* d_desc = nullptr;
+    uint8_t* d_candidate = nullptr; uint8_t* d_inView = nullptr;
+    float* d_u = nullptr; float* d_v = nullptr; float* d_uR = nullptr; float* d_viewcos = nullptr;
+    int32_t* d_level = nullptr; int32_t* d_count = nullptr;
+};
+
 namespace orbb200 {
 
 static std::string g_create_err;
@@ -802,6 +813,7 @@ struct QueryHost {
     const uint8_t* desc = nullptr; const uint8_t* obs_pos = nullptr; const uint8_t* kp_blocked = nullptr;
     const float* r = nullptr; const int32_t* maxlevel = nullptr; const int32_t* cand_idx = nullptr; int n_cand = 0;
     const float* inv_sigma2 = nullptr; int acc_th = 0, flags = 0;
+    bool dev_queries = false;      // valid/x/y/aux/level/viewcos/desc already are device arrays (no upload)
 };
 
 // Upload one job's queries, run it, return device pointers of the outputs inside the scratch arena.
@@ -816,7 +828,7 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     Arena A(c.d_scratch, c.d_scratch_bytes);
     WinJob J{};
     auto upF = [&](const float* src) -> const float* {
-        if (!src) return nullptr;
+        if (!src || Q.dev_queries) return src;
         float* d = A.take<float>(nq);
         cudaMemcpyAsync(d, src, sizeof(float) * nq, cudaMemcpyHostToDevice, c.stream);
         return d;
@@ -832,14 +844,15 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     float* dsf = A.take<float>(MAX_LEVELS);
     cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream);
     J.scaleFactors = dsf;
-    J.q_valid = upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
-    if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
+    J.q_valid = Q.dev_queries ? Q.valid : upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
+    if (Q.level && Q.dev_queries) J.q_level = Q.level;
+    else if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
     J.q_viewcos = upF(Q.viewcos); J.q_angle = upF(Q.angle); J.q_r = upF(Q.r);
     if (Q.maxlevel) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.maxlevel, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_maxlevel = d; }
     if (Q.cand_idx && Q.n_cand > 0) { int32_t* d = A.take<int32_t>(Q.n_cand); cudaMemcpyAsync(d, Q.cand_idx, 4 * (size_t)Q.n_cand, cudaMemcpyHostToDevice, c.stream); J.cand_idx = d; }
     if (Q.inv_sigma2) { float* d = A.take<float>(MAX_LEVELS); cudaMemcpyAsync(d, Q.inv_sigma2, sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream); J.invLevelSigma2 = d; }
     J.accTh = Q.acc_th; J.flags = Q.flags;
-    J.q_desc = upB(Q.desc, (size_t)nq * 32); J.q_obs_pos = upB(Q.obs_pos, nq); J.kp_blocked = upB(Q.kp_blocked, F->cap);
+    J.q_desc = Q.dev_queries ? Q.desc : upB(Q.desc, (size_t)nq * 32); J.q_obs_pos = upB(Q.obs_pos, nq); J.kp_blocked = upB(Q.kp_blocked, F->cap);
     J.scratch = A.take<int>(win_scratch_ints(kpCap, nq));
     J.out_best_idx = A.take<int32_t>(nq); J.out_best_dist = A.take<int32_t>(nq);
     J.out_per_kp = A.take<int32_t>(kpCap); J.out_per_query = A.take<int32_t>(nq);
@@ -874,6 +887,111 @@ int orbb200_search_by_projection(orbb200_ctx* ctx, const orbb200_frame* F, int n
     QueryHost Q; Q.nq = nq; Q.valid = q_valid; Q.x = q_u; Q.y = q_v; Q.aux = q_uR; Q.level = q_level; Q.viewcos = q_viewcos;
     Q.desc = q_desc; Q.obs_pos = q_obs_pos; Q.kp_blocked = kp_blocked;
     return run_window_job(c, F, Q, WM_PROJ, 0, 0, th, nnratio, 0.f, out_best_idx, out_best_dist, out_query_of_kp, nullptr, nmatches);
+}
+
+int orbb200_map_upload(orbb200_ctx* ctx, orbb200_map** map, int n, const float* pos, const float* normal,
+                       const float* max_distance, const float* min_distance, const uint8_t* desc)
+{
+    CTX_ENTER(ctx);
+    if (!map || n < 0 || (n > 0 && (!pos || !normal || !max_distance || !min_distance || !desc))) { c.err = "map_upload: bad argument"; return ORBB200_ERR_ARG; }
+    orbb200_map* m = new orbb200_map();
+    m->ctx = &c; m->n = n;
+    const size_t k = (size_t)std::max(n, 1);
+    bool ok = cudaMalloc((void**)&m->d_pos, k * 12) == cudaSuccess && cudaMalloc((void**)&m->d_normal, k * 12) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_maxDist, k * 4) == cudaSuccess && cudaMalloc((void**)&m->d_minDist, k * 4) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_desc, k * 32) == cudaSuccess && cudaMalloc((void**)&m->d_candidate, k) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_inView, k) == cudaSuccess && cudaMalloc((void**)&m->d_u, k * 4) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_v, k * 4) == cudaSuccess && cudaMalloc((void**)&m->d_uR, k * 4) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_viewcos, k * 4) == cudaSuccess && cudaMalloc((void**)&m->d_level, k * 4) == cudaSuccess &&
+              cudaMalloc((void**)&m->d_count, 4) == cudaSuccess;
+    if (!ok) { orbb200_map_free(m); cudaGetLastError(); c.err = "map_upload: cudaMalloc failed"; return ORBB200_ERR_CUDA; }
+    if (n > 0) {
+        cudaMemcpyAsync(m->d_pos, pos, (size_t)n * 12, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(m->d_normal, normal, (size_t)n * 12, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(m->d_maxDist, max_distance, (size_t)n * 4, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(m->d_minDist, min_distance, (size_t)n * 4, cudaMemcpyHostToDevice, c.stream);
+        cudaMemcpyAsync(m->d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, c.stream);
+    }
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    *map = m;
+    return ORBB200_OK;
+}
+
+void orbb200_map_free(orbb200_map* m)
+{
+    if (!m) return;
+    if (m->ctx) { cudaSetDevice(m->ctx->device); cudaStreamSynchronize(m->ctx->stream); }
+    void* ptrs[] = {m->d_pos, m->d_normal, m->d_maxDist, m->d_minDist, m->d_desc, m->d_candidate, m->d_inView, m->d_u, m->d_v,
+                    m->d_uR, m->d_viewcos, m->d_level, m->d_count};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete m;
+}
+
+// enqueue the projection of the whole map; results stay in the map's device arrays
+static int enqueue_frustum(Ctx& c, const orbb200_map* m, const orbb200_camera_pose* pose, float cosLimit, const uint8_t* candidate)
+{
+    if (candidate && m->n > 0) ORBB200_CUDA_OK(c, cudaMemcpyAsync(m->d_candidate, candidate, (size_t)m->n, cudaMemcpyHostToDevice, c.stream));
+    FrustumJob J{};
+    J.pose = *pose; J.cosLimit = cosLimit; J.n = m->n;
+    J.pos = m->d_pos; J.normal = m->d_normal; J.maxDist = m->d_maxDist; J.minDist = m->d_minDist;
+    J.candidate = candidate ? m->d_candidate : nullptr;
+    J.inView = m->d_inView; J.u = m->d_u; J.v = m->d_v; J.uR = m->d_uR; J.level = m->d_level; J.viewcos = m->d_viewcos;
+    J.count = m->d_count;
+    launch_frustum(c, J);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+static void download_frustum(Ctx& c, const orbb200_map* m, uint8_t* in_view, float* u, float* v, float* uR, int32_t* level,
+                             float* viewcos, int32_t* h_count)
+{
+    const size_t n = (size_t)m->n;
+    if (n > 0) {
+        if (in_view) cudaMemcpyAsync(in_view, m->d_inView, n, cudaMemcpyDeviceToHost, c.stream);
+        if (u) cudaMemcpyAsync(u, m->d_u, n * 4, cudaMemcpyDeviceToHost, c.stream);
+        if (v) cudaMemcpyAsync(v, m->d_v, n * 4, cudaMemcpyDeviceToHost, c.stream);
+        if (uR) cudaMemcpyAsync(uR, m->d_uR, n * 4, cudaMemcpyDeviceToHost, c.stream);
+        if (level) cudaMemcpyAsync(level, m->d_level, n * 4, cudaMemcpyDeviceToHost, c.stream);
+        if (viewcos) cudaMemcpyAsync(viewcos, m->d_viewcos, n * 4, cudaMemcpyDeviceToHost, c.stream);
+    }
+    cudaMemcpyAsync(h_count, m->d_count, 4, cudaMemcpyDeviceToHost, c.stream);
+}
+
+int orbb200_is_in_frustum(orbb200_ctx* ctx, const orbb200_map* map, const orbb200_camera_pose* pose, float viewing_cos_limit,
+                          const uint8_t* candidate, uint8_t* out_in_view, float* out_u, float* out_v, float* out_uR,
+                          int32_t* out_level, float* out_viewcos, int* n_in_view)
+{
+    CTX_ENTER(ctx);
+    if (!map || !pose || map->ctx != &c) { c.err = "is_in_frustum: bad argument"; return ORBB200_ERR_ARG; }
+    const int rc = enqueue_frustum(c, map, pose, viewing_cos_limit, candidate);
+    if (rc != ORBB200_OK) return rc;
+    int32_t cnt = 0;
+    download_frustum(c, map, out_in_view, out_u, out_v, out_uR, out_level, out_viewcos, &cnt);
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (n_in_view) *n_in_view = cnt;
+    return ORBB200_OK;
+}
+
+int orbb200_search_local_points(orbb200_ctx* ctx, const orbb200_frame* F, const orbb200_map* map,
+                                const orbb200_camera_pose* pose, float viewing_cos_limit, const uint8_t* candidate,
+                                const uint8_t* obs_pos, const uint8_t* kp_blocked, float th, float nnratio,
+                                uint8_t* out_in_view, float* out_u, float* out_v, float* out_uR, int32_t* out_level,
+                                float* out_viewcos, int* n_in_view,
+                                int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp, int* nmatches)
+{
+    CTX_ENTER(ctx);
+    if (!F || !map || !pose || map->ctx != &c) { c.err = "search_local_points: bad argument"; return ORBB200_ERR_ARG; }
+    int rc = enqueue_frustum(c, map, pose, viewing_cos_limit, candidate);
+    if (rc != ORBB200_OK) return rc;
+    int32_t cnt = 0;
+    download_frustum(c, map, out_in_view, out_u, out_v, out_uR, out_level, out_viewcos, &cnt);
+    // the projected map points are the queries of SearchByProjection: mbTrackInView -> valid
+    QueryHost Q; Q.nq = map->n; Q.dev_queries = true;
+    Q.valid = map->d_inView; Q.x = map->d_u; Q.y = map->d_v; Q.aux = map->d_uR; Q.level = map->d_level; Q.viewcos = map->d_viewcos;
+    Q.desc = map->d_desc; Q.obs_pos = obs_pos; Q.kp_blocked = kp_blocked;
+    rc = run_window_job(c, F, Q, WM_PROJ, 0, 0, th, nnratio, 0.f, out_best_idx, out_best_dist, out_query_of_kp, nullptr, nmatches);
+    if (n_in_view) *n_in_view = cnt;      // run_window_job synchronised the stream
+    return rc;
 }
 
 int orbb200_search_by_projection_frame(orbb200_ctx* ctx, const orbb200_frame* Cur, int nq,

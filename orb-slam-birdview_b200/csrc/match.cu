@@ -698,4 +698,70 @@ void launch_triangulation(Ctx& c, const TriJob& J)
     c.launches++;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Frame::isInFrustum (reference src/Frame.cc:436-492) + MapPoint::PredictScale (src/MapPoint.cc:402-417),
+// one thread per map point.  cv::Mat arithmetic as OpenCV evaluates it for these shapes: mRcw*P+mtcw = float
+// products summed left to right, then the translation added (the double add + float rounding gemm performs equals
+// one float add); cv::norm and Mat::dot accumulate in double (the products of two floats are exact in double, so
+// DFMA contraction cannot change them).  logf is evaluated in double and rounded (host libm's logf is correctly
+// rounded for all but ~2^-10 of inputs, and the level only changes when log(ratio)/log(1.2) sits on an integer).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) frustum_kernel(FrustumJob J)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    float u = 0.f, v = 0.f, uR = 0.f, viewCos = 0.f;
+    int nScale = 0;
+    if (i < J.n && (!J.candidate || J.candidate[i])) {
+        const orbb200_camera_pose& F = J.pose;
+        const float Px = J.pos[3 * i], Py = J.pos[3 * i + 1], Pz = J.pos[3 * i + 2];
+        float Pc[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            float t = __fadd_rn(__fmul_rn(F.Rcw[3 * r], Px), __fmul_rn(F.Rcw[3 * r + 1], Py));
+            t = __fadd_rn(t, __fmul_rn(F.Rcw[3 * r + 2], Pz));
+            Pc[r] = __fadd_rn(t, F.tcw[r]);
+        }
+        do {
+            if (Pc[2] < 0.0f) break;
+            const float invz = __fdiv_rn(1.0f, Pc[2]);
+            u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, Pc[0]), invz), F.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, Pc[1]), invz), F.cy);
+            if (u < F.min_x || u > F.max_x) break;
+            if (v < F.min_y || v > F.max_y) break;
+            const float maxD = J.maxDist[i];
+            const float maxDistance = __fmul_rn(1.2f, maxD), minDistance = __fmul_rn(0.8f, J.minDist[i]);
+            const float POx = __fsub_rn(Px, F.Ow[0]), POy = __fsub_rn(Py, F.Ow[1]), POz = __fsub_rn(Pz, F.Ow[2]);
+            const float dist = (float)sqrt((double)POx * POx + (double)POy * POy + (double)POz * POz);
+            if (dist < minDistance || dist > maxDistance) break;
+            const double dot = (double)POx * J.normal[3 * i] + (double)POy * J.normal[3 * i + 1] + (double)POz * J.normal[3 * i + 2];
+            viewCos = (float)(dot / (double)dist);
+            if (viewCos < J.cosLimit) break;
+            const float ratio = __fdiv_rn(maxD, dist);
+            const float cl = ceilf(__fdiv_rn((float)log((double)ratio), F.log_scale_factor));
+            // (int) as the host's cvttss2si: NaN / out of range -> INT_MIN
+            nScale = (cl > -2147483648.f && cl < 2147483648.f) ? (int)cl : INT_MIN;
+            nScale = nScale < 0 ? 0 : (nScale >= F.n_levels ? F.n_levels - 1 : nScale);
+            uR = __fsub_rn(u, __fmul_rn(F.mbf, invz));
+            ok = true;
+        } while (false);
+    }
+    if (i < J.n) {
+        J.inView[i] = ok ? 1 : 0;
+        J.u[i] = ok ? u : 0.f; J.v[i] = ok ? v : 0.f; J.uR[i] = ok ? uR : 0.f;
+        J.level[i] = ok ? nScale : 0; J.viewcos[i] = ok ? viewCos : 0.f;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(J.count, __popc(bal));
+}
+
+void launch_frustum(Ctx& c, const FrustumJob& J)
+{
+    cudaMemsetAsync(J.count, 0, sizeof(int32_t), c.stream);
+    if (J.n > 0) {
+        frustum_kernel<<<(J.n + 127) / 128, 128, 0, c.stream>>>(J);
+        c.launches++;
+    }
+}
+
 }  // namespace orbb200

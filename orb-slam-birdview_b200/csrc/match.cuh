@@ -63,4 +63,14 @@ void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, 
 void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq);
 void launch_triangulation(Ctx& c, const TriJob& J);
 
+// Frame::isInFrustum over a device-resident map
+struct FrustumJob {
+    orbb200_camera_pose pose;
+    float cosLimit;
+    int n;
+    const float* pos; const float* normal; const float* maxDist; const float* minDist; const uint8_t* candidate;
+    uint8_t* inView; float* u; float* v; float* uR; int32_t* level; float* viewcos; int32_t* count;
+};
+void launch_frustum(Ctx& c, const FrustumJob& J);
+
 }  // namespace orbb200

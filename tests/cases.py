@@ -199,3 +199,47 @@ def synthetic_vocabulary(k=10, L=3, seed=0, stop_frac=0.03):
         idx.extend(c)
         ptr[i + 1] = len(idx)
     return dict(child_ptr=ptr, child_idx=np.array(idx, np.int32), node_desc=np.stack(desc), word_id=word_id, weight=weight, L=L)
+
+
+def local_map_case(kps, desc, w, h, n, seed, on_kp_frac=0.6, max_flips=40):
+    """A local map + camera pose for Frame::isInFrustum / SearchLocalPoints: a fraction of the map points are
+    back-projections of frame keypoints at random depths (their descriptors perturbed copies), the rest are random
+    world points, some behind the camera, outside the image, out of their scale-invariance range or seen from a
+    bad angle.  Returns (pose dict, map dict)."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    fx, fy, cx, cy, bf = f32(718.856), f32(718.856), f32(w / 2 - 13.3), f32(h / 2 - 2.8), f32(386.1448)
+    ax, ay, az = rng.normal(0, 0.05, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    R = (Rz @ Ry @ Rx).astype(f32)
+    t = rng.normal(0, 2.0, 3).astype(f32)
+    Ow = (-(R.T.astype(f32) @ t)).astype(f32)
+    nk = len(kps)
+    src = rng.integers(0, nk, n)
+    on = rng.random(n) < on_kp_frac
+    z = rng.uniform(2.0, 60.0, n)
+    uu = np.where(on, kps["x"][src] + rng.uniform(-2, 2, n), rng.uniform(-0.2 * w, 1.2 * w, n))
+    vv = np.where(on, kps["y"][src] + rng.uniform(-2, 2, n), rng.uniform(-0.2 * h, 1.2 * h, n))
+    z = np.where(~on & (rng.random(n) < 0.15), -z, z)                       # some behind the camera
+    Xc = np.stack([(uu - cx) * z / fx, (vv - cy) * z / fy, z], 1)
+    P = ((Xc - t[None, :].astype(np.float64)) @ R.astype(np.float64)).astype(f32)          # R^T (Xc - t)
+    PO = P.astype(np.float64) - Ow[None, :]
+    d = np.linalg.norm(PO, axis=1)
+    nrm = PO / np.maximum(d, 1e-9)[:, None]
+    tilt = rng.normal(0, 0.5, (n, 3)) * (rng.random(n) < 0.3)[:, None] * 3.0
+    nrm = nrm + tilt
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(f32)
+    lvl = np.where(on, kps["octave"][src], rng.integers(0, 8, n))
+    maxd = (d * np.power(1.2, lvl) * rng.uniform(0.9, 1.1, n)).astype(f32)
+    far = rng.random(n) < 0.1
+    maxd = np.where(far, maxd * rng.choice([0.2, 6.0], n), maxd).astype(f32)    # out of range either way
+    mind = (maxd / f32(1.2 ** 7)).astype(f32)
+    qd = np.where(on[:, None], synth.perturb_descriptors(desc[src], max_flips, seed + 1), synth.synth_descriptors(n, seed + 2))
+    pose = dict(Rcw=R.reshape(9), tcw=t, Ow=Ow, fx=float(fx), fy=float(fy), cx=float(cx), cy=float(cy), mbf=float(bf),
+                min_x=0.0, max_x=float(w), min_y=0.0, max_y=float(h), log_scale_factor=float(np.log(f32(1.2), dtype=f32)),
+                n_levels=8)
+    mp = dict(pos=P, normal=nrm, max_distance=maxd, min_distance=mind, desc=np.ascontiguousarray(qd, np.uint8),
+              candidate=(rng.random(n) < 0.95).astype(np.uint8), obs_pos=(rng.random(n) < 0.9).astype(np.uint8))
+    return pose, mp

@@ -489,3 +489,44 @@ def test_extract_bow_searchbybow_chain(pkg):
     nm, out = pkg.ORBmatcher(ex.ctx, 0.7, True).SearchByBoW(D[0, :N[0]], K[0, :N[0]]["angle"], valid1, F2, fvs[0], fvs[1])
     nm0, out0 = oracle.search_by_bow(D[0, :N[0]], K[0, :N[0]]["angle"], valid1, O2, None, fvs[0], fvs[1], 0.7, True, False)
     assert nm == nm0 and nm > 100 and np.array_equal(out, out0)
+
+
+@pytest.mark.parametrize("n,seed", [(3000, 61), (700, 62), (1, 63)])
+def test_is_in_frustum(pkg, n, seed):
+    """Frame::isInFrustum + PredictScale over a device-resident map: flags and levels exact, floats bitwise."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    w, h = 1241, 376
+    kps, desc, _, _ = cases.frame_case(2000, w, h, seed)
+    pose, mp = cases.local_map_case(kps, desc, w, h, n, seed + 100)
+    M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+    for cand, lim in ((mp["candidate"], 0.5), (None, 0.5), (mp["candidate"], 0.9)):
+        k, iv, u, v, uR, lvl, vc = M.isInFrustum(pkg.CameraPose.make(**pose), lim, cand)
+        k0, iv0, u0, v0, uR0, lvl0, vc0 = oracle.is_in_frustum(mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"],
+                                                               oracle.camera_pose(**pose), lim, cand)
+        assert k == k0 and np.array_equal(iv, iv0) and np.array_equal(lvl, lvl0)
+        for a, b in ((u, u0), (v, v0), (uR, uR0), (vc, vc0)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if n > 100:
+        assert 0.2 * n < k0 < 0.9 * n
+
+
+def test_search_local_points(pkg):
+    """Tracking::SearchLocalPoints: projection on the device feeding SearchByProjection == oracle isInFrustum + oracle
+    SearchByProjection."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    w, h = 1241, 376
+    kps, desc, uR, grid = cases.frame_case(2000, w, h, 71, stereo_frac=0.4)
+    F, O = _frames(pkg, ctx, kps, desc, grid, uR)
+    pose, mp = cases.local_map_case(kps, desc, w, h, 3000, 72)
+    blocked = (np.random.default_rng(73).random(len(kps)) < 0.1).astype(np.uint8)
+    M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+    for th in (1.0, 3.0, 5.0):
+        k, iv, (u, v, uRq, lvl, vc), nm, bi, bd, qk = pkg.ORBmatcher(ctx, 0.8).SearchLocalPoints(
+            F, M, pkg.CameraPose.make(**pose), mp["candidate"], mp["obs_pos"], blocked, th)
+        k0, iv0, u0, v0, uR0, lvl0, vc0 = oracle.is_in_frustum(mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"],
+                                                               oracle.camera_pose(**pose), 0.5, mp["candidate"])
+        nm0, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, iv0, u0, v0, uR0, lvl0, vc0, mp["desc"], mp["obs_pos"],
+                                                         blocked, th, 0.8)
+        assert k == k0 and np.array_equal(iv, iv0) and np.array_equal(lvl, lvl0)
+        assert nm == nm0 and nm > 50, (th, nm, nm0)
+        assert np.array_equal(bi, bi0) and np.array_equal(bd[bi >= 0], bd0[bi0 >= 0]) and np.array_equal(qk, qk0)

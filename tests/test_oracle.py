@@ -315,3 +315,22 @@ def test_bow_transform_vs_python_live():
         assert w.tolist() == w0 and n.tolist() == n0
         assert bw.tolist() == [k for k, _ in v0] and bv.tolist() == [x for _, x in v0]
         assert fn.tolist() == [k for k, _ in fv0] and all(fi[fp[i]:fp[i + 1]].tolist() == fv0[i][1] for i in range(len(fv0)))
+
+
+def test_is_in_frustum_matches_cv2_composition():
+    """The oracle's restatement of the cv::Mat arithmetic in Frame::isInFrustum against cv2.gemm / cv2.norm."""
+    import oracle
+    from ref_py import frustum_py_ref
+    k, d, _, _ = cases.frame_case(600, 1241, 376, 77)
+    for seed in (1, 2, 3):
+        pose, mp = cases.local_map_case(k, d, 1241, 376, 500, 900 + seed)
+        P = oracle.camera_pose(**pose)
+        n, iv, u, v, uR, lvl, vc = oracle.is_in_frustum(mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], P, 0.5,
+                                                        mp["candidate"])
+        ref = frustum_py_ref.is_in_frustum(mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], pose, 0.5, mp["candidate"])
+        assert n == int(iv.sum()) and 0.2 * len(iv) < n < 0.9 * len(iv)          # the case exercises both outcomes
+        assert np.array_equal(iv, ref["in_view"])
+        for a, b in ((u, ref["u"]), (v, ref["v"]), (uR, ref["uR"]), (vc, ref["viewcos"])):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.array_equal(lvl, ref["level"])
+        assert len(np.unique(lvl[iv == 1])) >= 4
