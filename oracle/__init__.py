@@ -21,13 +21,13 @@ def build(native=False, force=False, out_dir=None):
     """Compile the oracle.  native=True -> -march=native copy (bench CPU baseline, built on the box)."""
     name = "liborb_oracle_native.so" if native else "liborb_oracle.so"
     out = os.path.join(out_dir or _HERE, name)
-    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "match_oracle.cpp", "orb_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.cpp", "match_oracle.cpp", "bird_oracle.cpp", "orb_oracle.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "orbb200_pattern.inc"))
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
     cmd = [os.environ.get("CXX", "g++"), "-O3", "-march=native" if native else "-march=x86-64-v3", "-std=c++17",
            "-ffp-contract=off", "-fPIC", "-shared", "-o", out,
-           os.path.join(_HERE, "orb_oracle.cpp"), os.path.join(_HERE, "match_oracle.cpp")]
+           os.path.join(_HERE, "orb_oracle.cpp"), os.path.join(_HERE, "match_oracle.cpp"), os.path.join(_HERE, "bird_oracle.cpp")]
     subprocess.run(cmd, check=True, cwd=_HERE)
     return out
 
@@ -78,6 +78,13 @@ def lib(native=False):
         "oracle_search_by_bow": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp]),
         "oracle_voc_create": (vp, [C.c_int, vp, vp, vp, vp, vp, C.c_int]),
         "oracle_voc_destroy": (None, [vp]),
+        "oracle_resize_linear_exact_u8": (None, [vp, C.c_int, C.c_int, sz, vp, C.c_int, C.c_int, sz]),
+        "oracle_sep_gauss7_f32_u8": (None, [vp, C.c_int, C.c_int, sz, vp, sz]),
+        "oracle_bird_detect": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, sz, C.c_int, vp, C.c_int]),
+        "oracle_get_rect_sub_pix_8u32f": (None, [vp, C.c_int, C.c_int, sz, C.c_float, C.c_float, C.c_int, C.c_int, vp]),
+        "oracle_corner_subpix": (None, [vp, C.c_int, C.c_int, sz, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+        "oracle_bird_compute": (C.c_int, [vp, C.c_int, C.c_int, sz, vp, C.c_int, vp]),
+        "oracle_bird_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, sz, C.c_int, vp, vp, C.c_int]),
         "oracle_is_in_frustum": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]),
         "oracle_voc_transform": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "oracle_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
@@ -419,3 +426,60 @@ def is_in_frustum(pos, normal, max_distance, min_distance, pose, viewing_cos_lim
     k = L.oracle_is_in_frustum(n, _p(pos), _p(normal), _p(mx), _p(mn), _p(cand), C.addressof(pose), viewing_cos_limit,
                                _p(iv), _p(u), _p(v), _p(uR), _p(lvl), _p(vc))
     return k, iv, u, v, uR, lvl, vc
+
+
+# ---- birdview front-end: cv::ORB + cornerSubPix (reference src/Frame.cc:328-342) ---------------------------
+def resize_linear_exact_u8(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_exact_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def sep_gauss7_f32_u8(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().oracle_sep_gauss7_f32_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def bird_detect(img, mask=None, nfeatures=2000):
+    img = np.ascontiguousarray(img, np.uint8)
+    mask = _c(mask, np.uint8)
+    h, w = img.shape
+    cap = 4 * nfeatures + 64
+    out = np.empty(cap, KP_DTYPE)
+    n = lib().oracle_bird_detect(_p(img), _p(mask), w, h, img.strides[0], 0 if mask is None else mask.strides[0], nfeatures, _p(out), cap)
+    return out[:n].copy()
+
+
+def get_rect_sub_pix(img, cx, cy, win_w, win_h):
+    img = np.ascontiguousarray(img, np.uint8)
+    dst = np.empty((win_h, win_w), np.float32)
+    lib().oracle_get_rect_sub_pix_8u32f(_p(img), img.shape[1], img.shape[0], img.strides[0], cx, cy, win_w, win_h, _p(dst))
+    return dst
+
+
+def corner_subpix(img, pts, win=(5, 5), max_iter=40, eps=0.001):
+    img = np.ascontiguousarray(img, np.uint8)
+    pts = np.array(pts, np.float32, copy=True).reshape(-1, 2)
+    lib().oracle_corner_subpix(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(pts), len(pts), win[0], win[1], max_iter, eps)
+    return pts
+
+
+def bird_compute(img, kps):
+    img = np.ascontiguousarray(img, np.uint8)
+    kps = np.array(kps, KP_DTYPE, copy=True)
+    desc = np.empty((max(len(kps), 1), 32), np.uint8)
+    n = lib().oracle_bird_compute(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(desc))
+    return kps[:n].copy(), desc[:n].copy()
+
+
+def bird_extract(img, mask=None, nfeatures=2000):
+    img = np.ascontiguousarray(img, np.uint8)
+    mask = _c(mask, np.uint8)
+    h, w = img.shape
+    cap = 4 * nfeatures + 64
+    kps, desc = np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8)
+    n = lib().oracle_bird_extract(_p(img), _p(mask), w, h, img.strides[0], 0 if mask is None else mask.strides[0], nfeatures, _p(kps), _p(desc), cap)
+    return kps[:n].copy(), desc[:n].copy()

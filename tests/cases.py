@@ -243,3 +243,16 @@ def local_map_case(kps, desc, w, h, n, seed, on_kp_frac=0.6, max_flips=40):
     mp = dict(pos=P, normal=nrm, max_distance=maxd, min_distance=mind, desc=np.ascontiguousarray(qd, np.uint8),
               candidate=(rng.random(n) < 0.95).astype(np.uint8), obs_pos=(rng.random(n) < 0.9).astype(np.uint8))
     return pose, mp
+
+
+def birdview_case(size, seed, vehicle=(80, 140)):
+    """Birdview image + mask as src/Frame.cc:317-327 prepares them: mask 255 with the vehicle footprint (plus the
+    15 px boundary) zeroed in the middle."""
+    h = w = size if isinstance(size, int) else None
+    if h is None:
+        w, h = size
+    img = synth.synth_frame(h, w, seed)
+    mask = np.full((h, w), 255, np.uint8)
+    vw, vh = vehicle
+    mask[h // 2 - vh // 2:h // 2 + vh // 2 + 1, w // 2 - vw // 2:w // 2 + vw // 2 + 1] = 0
+    return img, mask
