@@ -252,6 +252,34 @@ int orbb200_search_local_points(orbb200_ctx* ctx, const orbb200_frame* F, const 
                                 float* out_viewcos, int* n_in_view,
                                 int32_t* out_best_idx, int32_t* out_best_dist, int32_t* out_query_of_kp, int* nmatches);
 
+/* ---- birdview front-end: cv::ORB + cv::cornerSubPix ------------------------------------------------------------
+ * What Frame::Frame runs on the birdview image (src/Frame.cc:328-342):
+ *     cv::Ptr<cv::ORB> e = cv::ORB::create(2000);  e->detect(img, kps, mask);
+ *     cv::cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001));  e->compute(img, kps, desc);
+ * cv::ORB defaults: scaleFactor 1.2f, 8 levels, edgeThreshold 31, HARRIS_SCORE, patchSize 31, fastThreshold 20, WTA_K 2.
+ * Results follow OpenCV 4.x's own C++ code bit for bit (cv2 4.13 with cv2.setUseOptimized(False)), including the order
+ * in which KeyPointsFilter::retainBest leaves the keypoints.  mask may be NULL; rows of `stride` / `mask_stride` bytes. */
+/* Upper bound of the keypoints one image can return (size your buffers with it). */
+int orbb200_bird_max_keypoints(orbb200_ctx* ctx, int w, int h, int nfeatures);
+/* cv::ORB::detect(img, kps, mask) */
+int orbb200_bird_detect(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mask, int w, int h, size_t stride, size_t mask_stride,
+                        int nfeatures, orbb200_kp_t* kps, int cap, int* n_out);
+/* cv::cornerSubPix(img, pts, Size(win_w, win_h), Size(-1,-1), TermCriteria(EPS + MAX_ITER, max_iter, eps)); pts [n][2] in/out;
+ * window half-sizes 1..7. */
+int orbb200_corner_subpix(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, float* pts, int n, int win_w, int win_h,
+                          int max_iter, double eps);
+/* cv::ORB::compute(img, kps, desc): kps [n] in/out (keypoints closer than 31 px to the image border are removed, the
+ * rest keep their order), desc [n][32]; *n_out = keypoints left. */
+int orbb200_bird_compute(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, orbb200_kp_t* kps, int n, uint8_t* desc,
+                         int* n_out);
+/* detect + cornerSubPix(5,5; 40 it; 1e-3) + compute without leaving the device: mvKeysBird / mDescriptorsBird. */
+int orbb200_bird_extract(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mask, int w, int h, size_t stride, size_t mask_stride,
+                         int nfeatures, orbb200_kp_t* kps, uint8_t* desc, int cap, int* n_out);
+/* n images (and masks, or masks == NULL) of one size per call; outputs [n][cap_per_img]. */
+int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, const uint8_t* const* masks, int n, int w, int h,
+                               size_t stride, size_t mask_stride, int nfeatures, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img,
+                               int* n_out);
+
 /* ---- DBoW2 vocabulary transform ----------------------------------------------------------------------------
  * Frame::ComputeBoW (src/Frame.cc:562-569) -> ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup)
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1203,1230-1271), TF_IDF weighting + L1 scoring.  The tree is

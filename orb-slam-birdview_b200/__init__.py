@@ -83,6 +83,12 @@ _SIGNATURES = {
     "orbb200_voc_free": (None, [_vp]),
     "orbb200_bow_transform": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
     "orbb200_bow_transform_extracted": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i), _vp, _vp, _vp, C.POINTER(_i)]),
+    "orbb200_bird_max_keypoints": (_i, [_vp, _i, _i, _i]),
+    "orbb200_bird_detect": (_i, [_vp, _vp, _vp, _i, _i, _sz, _sz, _i, _vp, _i, C.POINTER(_i)]),
+    "orbb200_corner_subpix": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, _i, _i, _i, C.c_double]),
+    "orbb200_bird_compute": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, _vp, C.POINTER(_i)]),
+    "orbb200_bird_extract": (_i, [_vp, _vp, _vp, _i, _i, _sz, _sz, _i, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbb200_bird_extract_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _sz, _sz, _i, _vp, _vp, _i, _vp]),
     "orbb200_map_upload": (_i, [_vp, C.POINTER(_vp), _i, _vp, _vp, _vp, _vp, _vp]),
     "orbb200_map_free": (None, [_vp]),
     "orbb200_is_in_frustum": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
@@ -355,6 +361,69 @@ class ORBVocabulary:
                                                          C.byref(nw), _p(fn), _p(fp), _p(fi), C.byref(nf)), "bow_transform")
         nfeat = int(fp[nf.value]) if nf.value > 0 else 0
         return word, node, (bw[:nw.value].copy(), bv[:nw.value].copy()), (fn[:nf.value].copy(), fp[:nf.value + 1].copy(), fi[:nfeat].copy())
+
+
+class BirdviewORB:
+    """The birdview front-end of the reference (src/Frame.cc:328-342): cv::ORB::create(nfeatures) detect(mask) +
+    cv::cornerSubPix(5x5, 40 it, 1e-3) + compute, with cv::ORB's method names.  Results equal OpenCV 4.x's own C++ code
+    (cv2 with setUseOptimized(False)) bit for bit, keypoint order included."""
+
+    def __init__(self, ctx, nfeatures=2000):
+        self.ctx, self._L, self.nfeatures = ctx, ctx._L, int(nfeatures)
+
+    def _cap(self, w, h):
+        cap = self._L.orbb200_bird_max_keypoints(self.ctx._h, w, h, self.nfeatures)
+        if cap <= 0:
+            raise OrbB200Error("bird_max_keypoints: " + self._L.orbb200_last_error(self.ctx._h).decode())
+        return cap
+
+    def detect(self, image, mask=None):
+        img, msk = _c(image, np.uint8), _c(mask, np.uint8)
+        h, w = img.shape
+        cap = self._cap(w, h)
+        kps = np.empty(cap, KP_DTYPE)
+        n = C.c_int()
+        self.ctx.check(self._L.orbb200_bird_detect(self.ctx._h, _p(img), _p(msk), w, h, img.strides[0], 0 if msk is None else msk.strides[0],
+                                                   self.nfeatures, _p(kps), cap, C.byref(n)), "bird_detect")
+        return kps[:n.value].copy()
+
+    def cornerSubPix(self, image, pts, winSize=(5, 5), maxCount=40, epsilon=0.001):
+        img = _c(image, np.uint8)
+        pts = np.array(pts, np.float32, copy=True).reshape(-1, 2)
+        self.ctx.check(self._L.orbb200_corner_subpix(self.ctx._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(pts), len(pts),
+                                                     int(winSize[0]), int(winSize[1]), int(maxCount), float(epsilon)), "cornerSubPix")
+        return pts
+
+    def compute(self, image, kps):
+        img = _c(image, np.uint8)
+        kps = np.array(kps, KP_DTYPE, copy=True)
+        desc = np.empty((max(len(kps), 1), 32), np.uint8)
+        n = C.c_int()
+        self.ctx.check(self._L.orbb200_bird_compute(self.ctx._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), len(kps), _p(desc),
+                                                    C.byref(n)), "bird_compute")
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def __call__(self, image, mask=None):
+        """detect + cornerSubPix + compute on the device -> (mvKeysBird, mDescriptorsBird)"""
+        k, d = self.extract_batch([image], None if mask is None else [mask])
+        return k[0], d[0]
+
+    def extract_batch(self, images, masks=None):
+        imgs = [_c(i, np.uint8) for i in images]
+        msks = None if masks is None else [_c(m, np.uint8) for m in masks]
+        n = len(imgs)
+        h, w = imgs[0].shape
+        if any(i.shape != (h, w) or i.strides[0] != imgs[0].strides[0] for i in imgs):
+            raise ValueError("images of one batch must share shape and stride")
+        cap = self._cap(w, h)
+        kps = np.empty((n, cap), KP_DTYPE)
+        desc = np.empty((n, cap, 32), np.uint8)
+        cnt = np.empty(n, np.int32)
+        ip = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+        mp = None if msks is None else (C.c_void_p * n)(*[m.ctypes.data for m in msks])
+        self.ctx.check(self._L.orbb200_bird_extract_batch(self.ctx._h, ip, mp, n, w, h, imgs[0].strides[0], 0 if msks is None else msks[0].strides[0],
+                                                          self.nfeatures, _p(kps), _p(desc), cap, _p(cnt)), "bird_extract")
+        return [kps[i, :cnt[i]].copy() for i in range(n)], [desc[i, :cnt[i]].copy() for i in range(n)]
 
 
 class LocalMap:

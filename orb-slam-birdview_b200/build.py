@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborbb200.so")
-SOURCES = ["api.cu", "extract.cu", "match.cu", "stereo.cu", "bow.cu"]
-DEPS = SOURCES + ["ctx.cuh", "match.cuh", "orbb200_internal.cuh",
+SOURCES = ["api.cu", "extract.cu", "match.cu", "stereo.cu", "bow.cu", "bird.cu"]
+DEPS = SOURCES + ["ctx.cuh", "match.cuh", "orbb200_internal.cuh", "device_math.cuh",
                   os.path.join("..", "..", "include", "orbb200.h"), os.path.join("..", "..", "include", "orbb200_pattern.inc")]
 
 

@@ -183,24 +183,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
                 float maxX = iniX + L.wCell + 6;
                 if (iniX >= L.maxBX - 6) continue;
                 if (maxX > L.maxBX) maxX = (float)L.maxBX;
-                cells.push_back(make_int4((int)iniX | ((int)iniY << 16), (int)maxX | ((int)maxY << 16), l, i * L.nCols + j));
-                cells.push_back(make_int4((int)L.off, L.pitch, (int)L.candOff, L.candCap));
-                cells.push_back(make_int4(0, 0, 0, 0));
-                {   // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
-                    const int x0 = (int)iniX, x1 = (int)maxX, th = (int)maxY - (int)iniY, xa = x0 & ~3;
-                    const int wi = x1 - x0 - 6, hi = th - 6;
-                    if (wi > 0 && hi > 0) {
-                        const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1;
-                        const int nw = (x1 - xa + 3) >> 2;
-                        // floor(i / d) == umulhi(i, 2^32 / d + 1) for the small i used; d == 1 is special-cased in the kernel
-                        cells.back() = make_int4((int)(0xffffffffu / (uint32_t)nw + 1u), (int)(0xffffffffu / (uint32_t)npr + 1u), 0, 0);
-                        const int P = FT_PITCH;
-                        st.fastTileWords = std::max(st.fastTileWords, th * P);
-                        st.fastScrWords = std::max(st.fastScrWords, (hi + 2) * P);
-                        st.fastClistCap = std::max(st.fastClistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
-                        st.fastWorkCap = std::max(st.fastWorkCap, ((hi * npr + 1) & ~1) + 128);   // per-warp list segments: total + slack
-                    }
-                }
+                push_fast_cell(cells, st.fastSmem, (int)iniX, (int)iniY, (int)maxX, (int)maxY, l, L.off, L.pitch, L.candOff, L.candCap);
             }
         }
     }
@@ -464,6 +447,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
     drain_stage_events(c);
+    bird_destroy(c);
     for (cudaEvent_t e : c.freeEvents) cudaEventDestroy(e);
     for (auto& p : c.plans) cudaFree(p.block);
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,

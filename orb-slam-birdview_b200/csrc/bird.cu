@@ -1,0 +1,1035 @@
+// Birdview front-end of the reference (src/Frame.cc:328-342):
+//     cv::ORB::create(2000)->detect(img, kps, mask);  cv::cornerSubPix(img, pts, (5,5), (-1,-1), (EPS+ITER, 40, 1e-3));
+//     ->compute(img, kps, desc)
+// as CUDA kernels.  cv::ORB / cv::cornerSubPix are OpenCV code (not under the reference tree); the arithmetic followed
+// here is OpenCV 4.x's own C++ (features2d/src/orb.cpp, keypoint.cpp, imgproc resize.cpp [INTER_LINEAR_EXACT],
+// cornersubpix.cpp, samplers.cpp, filter sepFilter2D), each step restated in the test suite and checked bit-exactly
+// against cv2 4.13 there.
+//
+// Device layout: every pyramid level of every image is its own plane with a 32-pixel reflect-101 margin (what the packed
+// cv::ORB buffer provides around each layer); the mask pyramid uses the same geometry with a zero margin.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <map>
+#include <tuple>
+
+#include "ctx.cuh"
+#include "device_math.cuh"
+
+namespace orbb200 {
+
+namespace {
+
+constexpr int BV_LEVELS = 8;
+constexpr int BV_MARGIN = 32;            // max(edgeThreshold 31, ceil(15*sqrt2), 9/2) + 1   (orb.cpp)
+constexpr int BV_EDGE = 31;              // edgeThreshold
+constexpr int BV_FAST_TH = 20;
+constexpr int BV_SORT_CAP = 16384;       // FAST corners per level that the selection kernel can hold
+constexpr int BV_MAX_WIN = 7;            // cornerSubPix half window limit
+constexpr int BV_TILE = 30;              // emit tile of the whole-level FAST
+
+struct BirdLevel {
+    int w, h, pitch;
+    unsigned off;            // byte offset of pixel (0,0) inside one image's plane block
+    float scale, invScale;
+    int quota;
+    unsigned candOff;
+    int candCap;
+    int tabX, tabY;          // offsets into the resize tables
+    int kpOff, kpCap;        // per-level output slots
+};
+
+struct BirdGeom {
+    int w, h, nfeatures;
+    unsigned planeBytes;     // bytes per image of one pyramid (image / mask / blurred use the same geometry)
+    unsigned candPerImg;
+    int kpPerImg;
+    BirdLevel lv[BV_LEVELS];
+};
+
+struct BirdPlan {
+    BirdGeom g{};
+    int2* d_tab = nullptr;           // INTER_LINEAR_EXACT tables: {source index, c1} (c0 = 256 - c1)
+    int4* d_cells = nullptr;
+    int nCells = 0;
+    FastSmem need;
+    int batch = 0;
+    // per-batch pools
+    uint8_t* d_pyr = nullptr; uint8_t* d_mask = nullptr; uint8_t* d_blur = nullptr;
+    uint32_t* d_cand = nullptr; int32_t* d_candCount = nullptr;
+    float4* d_lvlKp = nullptr; int32_t* d_lvlCount = nullptr;          // {x, y, harris, -} per level slot
+    orbb200_kp_t* d_kps = nullptr; orbb200_kp_t* d_kps2 = nullptr; uint8_t* d_desc = nullptr;
+    int32_t* d_counts = nullptr; int32_t* d_counts2 = nullptr;
+    float* d_pts = nullptr;
+};
+
+struct BirdState {
+    std::map<std::tuple<int, int, int>, BirdPlan*> plans;
+    float* d_winMask = nullptr;      // cornerSubPix window weights of the last (win_w, win_h)
+    int winW = -1, winH = -1;
+};
+
+inline int cvRoundF(float v) { return (int)lrintf(v); }
+inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+// cv::resize(prev, cur, INTER_LINEAR_EXACT) (resize.cpp bit-exact path): horizontal pass in 8.8, vertical pass rounded
+// from 16.16.  isMask: followed by threshold(254, THRESH_TOZERO) (orb.cpp).
+__global__ void bird_resize_kernel(uint8_t* __restrict__ pyr, unsigned planeBytes, BirdLevel S, BirdLevel D, const int2* __restrict__ tab,
+                                   int isMask)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= D.w) return;
+    const int2 tx = __ldg(tab + D.tabX + x), ty = __ldg(tab + D.tabY + y);
+    const uint8_t* s = pyr + (size_t)img * planeBytes + S.off;
+    const int x0 = tx.x, x1 = min(x0 + 1, S.w - 1), y0 = ty.x, y1 = min(y0 + 1, S.h - 1);
+    const int a1 = tx.y, a0 = 256 - a1, b1 = ty.y, b0 = 256 - b1;
+    const uint32_t h0 = (uint32_t)(s[(size_t)y0 * S.pitch + x0] * a0 + s[(size_t)y0 * S.pitch + x1] * a1) & 0xffffu;
+    const uint32_t h1 = (uint32_t)(s[(size_t)y1 * S.pitch + x0] * a0 + s[(size_t)y1 * S.pitch + x1] * a1) & 0xffffu;
+    uint32_t v = min((h0 * b0 + h1 * b1 + 32768u) >> 16, 255u);
+    if (isMask && v <= 254u) v = 0;
+    pyr[(size_t)img * planeBytes + D.off + (size_t)y * D.pitch + x] = (uint8_t)v;
+}
+
+// copyMakeBorder(BORDER_REFLECT_101) of BV_MARGIN pixels around every level
+__global__ void bird_border_kernel(uint8_t* __restrict__ pyr, unsigned planeBytes, BirdGeom g)
+{
+    const int level = blockIdx.y, img = blockIdx.z;
+    const BirdLevel L = g.lv[level];
+    const int W = L.w + 2 * BV_MARGIN, H = L.h + 2 * BV_MARGIN;
+    uint8_t* B = pyr + (size_t)img * planeBytes + L.off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * H; i += gridDim.x * blockDim.x) {
+        const int yy = i / W, xx = i - yy * W;
+        const int x = xx - BV_MARGIN, y = yy - BV_MARGIN;
+        if (x >= 0 && x < L.w && y >= 0 && y < L.h) continue;
+        int sx = x < 0 ? -x : (x >= L.w ? 2 * (L.w - 1) - x : x);
+        int sy = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);
+        sx = min(max(sx, 0), L.w - 1); sy = min(max(sy, 0), L.h - 1);      // (levels narrower than the margin)
+        B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)sy * L.pitch + sx];
+    }
+}
+
+// ---- KeyPointsFilter::retainBest (keypoint.cpp) = libstdc++ std::nth_element + std::partition, run literally by one
+//      thread on (response, payload) arrays in shared memory: the ORDER of the survivors is part of cv::ORB's output ----
+struct RB {
+    float* r; uint32_t* p;
+    __device__ __forceinline__ void swp(int i, int j) { const float a = r[i]; r[i] = r[j]; r[j] = a; const uint32_t b = p[i]; p[i] = p[j]; p[j] = b; }
+    __device__ __forceinline__ bool gt(int i, int j) const { return r[i] > r[j]; }
+};
+
+__device__ void rb_move_median_to_first(RB v, int result, int a, int b, int c)
+{
+    if (v.gt(a, b)) {
+        if (v.gt(b, c)) v.swp(result, b);
+        else if (v.gt(a, c)) v.swp(result, c);
+        else v.swp(result, a);
+    } else if (v.gt(a, c)) v.swp(result, a);
+    else if (v.gt(b, c)) v.swp(result, c);
+    else v.swp(result, b);
+}
+
+__device__ int rb_unguarded_partition(RB v, int first, int last, int pivot)
+{
+    const float pv = v.r[pivot];
+    while (true) {
+        while (v.r[first] > pv) ++first;
+        --last;
+        while (pv > v.r[last]) --last;
+        if (!(first < last)) return first;
+        v.swp(first, last);
+        ++first;
+    }
+}
+
+__device__ void rb_insertion_sort(RB v, int first, int last)
+{
+    if (first == last) return;
+    for (int i = first + 1; i < last; i++) {
+        const float vr = v.r[i]; const uint32_t vp = v.p[i];
+        if (vr > v.r[first]) {
+            for (int j = i; j > first; j--) { v.r[j] = v.r[j - 1]; v.p[j] = v.p[j - 1]; }
+            v.r[first] = vr; v.p[first] = vp;
+        } else {
+            int j = i;
+            while (vr > v.r[j - 1]) { v.r[j] = v.r[j - 1]; v.p[j] = v.p[j - 1]; j--; }
+            v.r[j] = vr; v.p[j] = vp;
+        }
+    }
+}
+
+__device__ void rb_adjust_heap(RB v, int base, int holeIndex, int len, float valr, uint32_t valp)
+{
+    const int topIndex = holeIndex;
+    int secondChild = holeIndex;
+    while (secondChild < (len - 1) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        if (v.r[base + secondChild] > v.r[base + secondChild - 1]) secondChild--;
+        v.r[base + holeIndex] = v.r[base + secondChild]; v.p[base + holeIndex] = v.p[base + secondChild];
+        holeIndex = secondChild;
+    }
+    if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        v.r[base + holeIndex] = v.r[base + secondChild - 1]; v.p[base + holeIndex] = v.p[base + secondChild - 1];
+        holeIndex = secondChild - 1;
+    }
+    int parent = (holeIndex - 1) / 2;
+    while (holeIndex > topIndex && v.r[base + parent] > valr) {
+        v.r[base + holeIndex] = v.r[base + parent]; v.p[base + holeIndex] = v.p[base + parent];
+        holeIndex = parent;
+        parent = (holeIndex - 1) / 2;
+    }
+    v.r[base + holeIndex] = valr; v.p[base + holeIndex] = valp;
+}
+
+__device__ void rb_heap_select(RB v, int first, int middle, int last)
+{
+    const int len = middle - first;
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; parent--) {
+            rb_adjust_heap(v, first, parent, len, v.r[first + parent], v.p[first + parent]);
+            if (parent == 0) break;
+        }
+    for (int i = middle; i < last; i++)
+        if (v.r[i] > v.r[first]) {
+            const float vr = v.r[i]; const uint32_t vp = v.p[i];
+            v.r[i] = v.r[first]; v.p[i] = v.p[first];
+            rb_adjust_heap(v, first, 0, len, vr, vp);
+        }
+}
+
+__device__ int rb_retain_best(RB v, int n, int n_points)
+{
+    if (!(n_points >= 0 && n > n_points)) return n;
+    if (n_points == 0) return 0;
+    // std::nth_element(begin, begin + n_points - 1, end, greater)
+    {
+        const int nth = n_points - 1;
+        int first = 0, last = n, depth = 0;
+        for (int k = n; k > 1; k >>= 1) depth++;
+        depth *= 2;
+        bool done = false;
+        while (last - first > 3) {
+            if (depth == 0) {
+                rb_heap_select(v, first, nth + 1, last);
+                v.swp(first, nth);
+                done = true;
+                break;
+            }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            rb_move_median_to_first(v, first, first + 1, mid, last - 1);
+            const int cut = rb_unguarded_partition(v, first + 1, last, first);
+            if (cut <= nth) first = cut; else last = cut;
+        }
+        if (!done) rb_insertion_sort(v, first, last);
+    }
+    const float amb = v.r[n_points - 1];
+    // std::partition(begin + n_points, end, response >= amb)
+    int first = n_points, last = n;
+    while (true) {
+        bool out = false;
+        while (true) {
+            if (first == last) { out = true; break; }
+            if (v.r[first] >= amb) ++first; else break;
+        }
+        if (out) break;
+        --last;
+        while (true) {
+            if (first == last) { out = true; break; }
+            if (!(v.r[last] >= amb)) --last; else break;
+        }
+        if (out) break;
+        v.swp(first, last);
+        ++first;
+    }
+    return first;
+}
+
+// HarrisResponses (orb.cpp), blockSize 7, k 0.04
+__device__ float bird_harris(const uint8_t* img, int pitch, int x0, int y0)
+{
+    const uint8_t* ptr0 = img + (ptrdiff_t)(y0 - 3) * pitch + (x0 - 3);
+    int a = 0, b = 0, c = 0;
+    for (int i = 0; i < 7; i++)
+        for (int j = 0; j < 7; j++) {
+            const uint8_t* p = ptr0 + i * pitch + j;
+            const int Ix = (p[1] - p[-1]) * 2 + (p[-pitch + 1] - p[-pitch - 1]) + (p[pitch + 1] - p[pitch - 1]);
+            const int Iy = (p[pitch] - p[-pitch]) * 2 + (p[pitch - 1] - p[-pitch - 1]) + (p[pitch + 1] - p[-pitch + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+    const float scale = __fdiv_rn(1.f, (float)(4 * 7) * 255.f);
+    const float ssq = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float sum = __fadd_rn(fa, fb);
+    const float t = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sum), sum));
+    return __fmul_rn(t, ssq);
+}
+
+// Per (image, level): FAST corners -> mask filter -> row-major order (cv::FAST's) -> retainBest(2 * quota) on the FAST
+// score -> Harris responses -> retainBest(quota) (orb.cpp computeKeyPoints).  Writes the level's survivors in order.
+constexpr int SEL_THREADS = 256;
+
+__global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ mpyr,
+                                                                  const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
+                                                                  float4* __restrict__ lvlKp, int32_t* __restrict__ lvlCount,
+                                                                  int32_t* __restrict__ status)
+{
+    extern __shared__ uint32_t selSmem[];
+    uint32_t* key = selSmem;                                              // [BV_SORT_CAP]
+    float* resp = reinterpret_cast<float*>(selSmem + BV_SORT_CAP);        // [BV_SORT_CAP]
+    __shared__ int sCount;
+    const int level = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const BirdLevel L = g.lv[level];
+    int n = candCount[img * MAX_LEVELS + level];            // fast_cells_kernel's layout
+    if (n > L.candCap || n > BV_SORT_CAP) {
+        if (tid == 0) { atomicExch(status, 3); lvlCount[img * BV_LEVELS + level] = 0; }
+        return;
+    }
+    const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
+    const uint8_t* M = mpyr ? mpyr + (size_t)img * g.planeBytes + L.off : nullptr;
+    int P2 = 1;
+    while (P2 < n) P2 <<= 1;
+    // key = (y << 20) | (x << 8) | score : ascending == cv::FAST's row-major output order
+    for (int i = tid; i < P2; i += SEL_THREADS) {
+        uint32_t k = 0xffffffffu;
+        if (i < n) {
+            const uint32_t v = C[i];
+            const int x = (int)(v & 0xfff) + FAST_BORDER, y = (int)((v >> 12) & 0xfff) + FAST_BORDER;
+            // KeyPointsFilter::runByPixelsMask: mask((int)(y + 0.5f), (int)(x + 0.5f)) == 0 -> dropped
+            if (!M || M[(size_t)y * L.pitch + x] != 0) k = ((uint32_t)y << 20) | ((uint32_t)x << 8) | (v >> 24);
+        }
+        key[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P2; i += SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = key[i], b = key[ixj];
+                    if (((i & k) == 0) == (a > b)) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // dropped entries sorted to the end: count the survivors
+    if (tid == 0) sCount = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < n; i += SEL_THREADS) local += key[i] != 0xffffffffu;
+    if (local) atomicAdd(&sCount, local);
+    __syncthreads();
+    n = sCount;
+    for (int i = tid; i < n; i += SEL_THREADS) resp[i] = (float)(key[i] & 0xffu);
+    __syncthreads();
+    RB v{resp, key};
+    if (tid == 0) sCount = rb_retain_best(v, n, 2 * L.quota);
+    __syncthreads();
+    n = sCount;
+    const uint8_t* I = pyr + (size_t)img * g.planeBytes + L.off;
+    for (int i = tid; i < n; i += SEL_THREADS) resp[i] = bird_harris(I, L.pitch, (int)((key[i] >> 8) & 0xfff), (int)(key[i] >> 20));
+    __syncthreads();
+    if (tid == 0) sCount = rb_retain_best(v, n, L.quota);
+    __syncthreads();
+    n = sCount;
+    if (n > L.kpCap) {
+        if (tid == 0) atomicExch(status, 4);
+        n = L.kpCap;
+    }
+    float4* out = lvlKp + (size_t)img * g.kpPerImg + L.kpOff;
+    for (int i = tid; i < n; i += SEL_THREADS) out[i] = make_float4((float)((key[i] >> 8) & 0xfff), (float)(key[i] >> 20), resp[i], 0.f);
+    if (tid == 0) lvlCount[img * BV_LEVELS + level] = n;
+}
+
+// ICAngles (orb.cpp) + the final keypoint record of computeKeyPoints (pt *= scale, size = patchSize * scale); one warp per
+// keypoint, output order = level-major, retainBest order inside a level.
+__global__ void __launch_bounds__(256) bird_finish_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const float4* __restrict__ lvlKp,
+                                                          const int32_t* __restrict__ lvlCount, orbb200_kp_t* __restrict__ kps,
+                                                          int32_t* __restrict__ counts)
+{
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const int gk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int level = -1, off = 0, total = 0;
+    for (int l = 0; l < BV_LEVELS; l++) {
+        const int c = lvlCount[img * BV_LEVELS + l];
+        if (level < 0 && gk < total + c) { level = l; off = total; }
+        total += c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = min(total, g.kpPerImg);
+    if (level < 0 || gk >= g.kpPerImg) return;
+    const BirdLevel L = g.lv[level];
+    const float4 k = lvlKp[(size_t)img * g.kpPerImg + L.kpOff + (gk - off)];
+    const int x = (int)k.x, y = (int)k.y;
+    const uint8_t* center = pyr + (size_t)img * g.planeBytes + L.off + (size_t)y * L.pitch + x;
+    int m01 = 0, m10 = 0;
+    const int u = lane - HALF_PATCH;
+    if (lane < 31) {
+        m10 = u * center[u];
+#pragma unroll
+        for (int vv = 1; vv <= HALF_PATCH; vv++)
+            if (abs(u) <= c_umax[vv]) {
+                const int vp = center[u + vv * L.pitch], vm = center[u - vv * L.pitch];
+                m01 += vv * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    if (lane == 0) {
+        orbb200_kp_t kp;
+        kp.x = __fmul_rn(k.x, L.scale); kp.y = __fmul_rn(k.y, L.scale);
+        kp.size = __fmul_rn((float)PATCH_SIZE, L.scale);
+        kp.angle = fast_atan2_deg((float)m01, (float)m10);
+        kp.response = k.z;
+        kp.octave = level;
+        kp.class_id = -1;
+        kps[(size_t)img * g.kpPerImg + gk] = kp;
+    }
+}
+
+// ---- cv::getRectSubPix CV_8U -> CV_32F (samplers.cpp: getRectSubPix_8u32f; windows leaving the image go through
+//      getRectSubPix_Cn_ + adjustRect = replicated border) ----
+__device__ void bird_get_rect_sub_pix(const uint8_t* src, int src_step, int src_w, int src_h, float* dst, int win_w, int win_h,
+                                      float cx, float cy)
+{
+    const float centerx = __fsub_rn(cx, __fmul_rn((float)(win_w - 1), 0.5f));
+    const float centery = __fsub_rn(cy, __fmul_rn((float)(win_h - 1), 0.5f));
+    const int ipx = (int)floorf(centerx), ipy = (int)floorf(centery);
+    if (0 <= ipx && ipx + win_w < src_w && 0 <= ipy && ipy + win_h < src_h) {
+        float a = __fsub_rn(centerx, (float)ipx);
+        const float b = __fsub_rn(centery, (float)ipy);
+        a = fmaxf(a, 0.0001f);
+        const float b1 = __fsub_rn(1.f, b), b2 = b;
+        const float a12 = __fmul_rn(a, b1), a22 = __fmul_rn(a, b);
+        const float oma = __fsub_rn(1.f, a);
+        const double s = __ddiv_rn(__dsub_rn(1.0, (double)a), (double)a);
+        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w) {
+            float prev = __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, (float)p[0]), __fmul_rn(b2, (float)p[src_step])));
+            for (int j = 0; j < win_w; j++) {
+                const float t = __fadd_rn(__fmul_rn(a12, (float)p[j + 1]), __fmul_rn(a22, (float)p[j + 1 + src_step]));
+                dst[j] = __fadd_rn(prev, t);
+                prev = (float)__dmul_rn((double)t, s);
+            }
+        }
+        return;
+    }
+    const float a = __fsub_rn(centerx, (float)ipx), b = __fsub_rn(centery, (float)ipy);
+    const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
+    const float a11 = __fmul_rn(oma, omb), a12 = __fmul_rn(a, omb), a21 = __fmul_rn(oma, b), a22 = __fmul_rn(a, b);
+    const float b1 = omb, b2 = b;
+    auto tap4 = [&](const uint8_t* r0, const uint8_t* r1, int j) {
+        return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)r0[j], a11), __fmul_rn((float)r0[j + 1], a12)), __fmul_rn((float)r1[j], a21)),
+                         __fmul_rn((float)r1[j + 1], a22));
+    };
+    if (0 <= ipx && ipx < src_w - win_w && 0 <= ipy && ipy < src_h - win_h) {
+        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w)
+            for (int j = 0; j < win_w; j++) dst[j] = tap4(p, p + src_step, j);
+        return;
+    }
+    // adjustRect
+    int rx, ry, rw, rh;
+    const uint8_t* p = src;
+    if (ipx >= 0) { p += ipx; rx = 0; } else { rx = -ipx; if (rx > win_w) rx = win_w; }
+    if (ipx < src_w - win_w) rw = win_w;
+    else { rw = src_w - ipx - 1; if (rw < 0) { p += rw; rw = 0; } }
+    if (ipy >= 0) { p += (ptrdiff_t)ipy * src_step; ry = 0; } else ry = -ipy;
+    if (ipy < src_h - win_h) rh = win_h;
+    else { rh = src_h - ipy - 1; if (rh < 0) { p += (ptrdiff_t)rh * src_step; rh = 0; } }
+    p -= rx;
+    for (int i = 0; i < win_h; i++, dst += win_w) {
+        const uint8_t* p2 = p + src_step;
+        if (i < ry || i >= rh) p2 -= src_step;
+        float s0 = __fadd_rn(__fmul_rn((float)p[rx], b1), __fmul_rn((float)p2[rx], b2));
+        for (int j = 0; j < rx; j++) dst[j] = s0;
+        s0 = __fadd_rn(__fmul_rn((float)p[rw], b1), __fmul_rn((float)p2[rw], b2));
+        for (int j = rw; j < win_w; j++) dst[j] = s0;
+        for (int j = rx; j < rw; j++) dst[j] = tap4(p, p2, j);
+        if (i < rh) p = p2;
+    }
+}
+
+// cv::cornerSubPix (cornersubpix.cpp), zeroZone (-1,-1): one thread per corner.  The sums are accumulated in double in
+// the reference's element order (floating-point addition is not associative), without FMA contraction.
+constexpr int SP_THREADS = 64;
+
+__global__ void __launch_bounds__(SP_THREADS) bird_subpix_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
+                                                                 int rows, float* __restrict__ pts, size_t ptsPerImg,
+                                                                 const int32_t* __restrict__ counts, int nFixed, const float* __restrict__ winMask,
+                                                                 int winW, int winH, int maxIters, double eps)
+{
+    const int img = blockIdx.y;
+    const int i = blockIdx.x * SP_THREADS + threadIdx.x;
+    const int n = counts ? counts[img] : nFixed;
+    if (i >= n) return;
+    const uint8_t* src = imgs + (size_t)img * imgStrideBytes;
+    float* P = pts + (size_t)img * ptsPerImg * 2 + 2 * (size_t)i;
+    const int win_w = winW * 2 + 1, win_h = winH * 2 + 1, bw = win_w + 2;
+    float buf[(2 * BV_MAX_WIN + 3) * (2 * BV_MAX_WIN + 3)];
+    const float cTx = P[0], cTy = P[1];
+    float cIx = cTx, cIy = cTy;
+    int iter = 0;
+    double err = 0;
+    do {
+        double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
+        bird_get_rect_sub_pix(src, pitch, cols, rows, buf, win_w + 2, win_h + 2, cIx, cIy);
+        const float* subpix = buf + bw + 1;
+        for (int ii = 0, k = 0; ii < win_h; ii++, subpix += bw) {
+            const double py = (double)(ii - winH);
+            for (int j = 0; j < win_w; j++, k++) {
+                const double m = (double)winMask[k];
+                const double tgx = (double)__fsub_rn(subpix[j + 1], subpix[j - 1]);
+                const double tgy = (double)__fsub_rn(subpix[j + bw], subpix[j - bw]);
+                const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
+                const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
+                const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                const double px = (double)(j - winW);
+                a = __dadd_rn(a, gxx); b = __dadd_rn(b, gxy); c = __dadd_rn(c, gyy);
+                bb1 = __dadd_rn(bb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
+                bb2 = __dadd_rn(bb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
+            }
+        }
+        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = __ddiv_rn(1.0, det);
+        const float nx = (float)__dsub_rn(__dadd_rn((double)cIx, __dmul_rn(__dmul_rn(c, scale), bb1)), __dmul_rn(__dmul_rn(b, scale), bb2));
+        const float ny = (float)__dadd_rn(__dsub_rn((double)cIy, __dmul_rn(__dmul_rn(b, scale), bb1)), __dmul_rn(__dmul_rn(a, scale), bb2));
+        const float dx = __fsub_rn(nx, cIx), dy = __fsub_rn(ny, cIy);
+        err = (double)__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        cIx = nx; cIy = ny;
+        if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) break;
+    } while (++iter < maxIters && err > eps);
+    if (fabsf(__fsub_rn(cIx, cTx)) > winW || fabsf(__fsub_rn(cIy, cTy)) > winH) { cIx = cTx; cIy = cTy; }
+    P[0] = cIx; P[1] = cIy;
+}
+
+__global__ void bird_kps_to_pts_kernel(const orbb200_kp_t* __restrict__ kps, float* __restrict__ pts, int kpPerImg, const int32_t* __restrict__ counts,
+                                       int toKps)
+{
+    const int img = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[img]) return;
+    orbb200_kp_t* k = const_cast<orbb200_kp_t*>(kps) + (size_t)img * kpPerImg + i;
+    float* p = pts + ((size_t)img * kpPerImg + i) * 2;
+    if (toKps) { k->x = p[0]; k->y = p[1]; } else { p[0] = k->x; p[1] = k->y; }
+}
+
+// ORB::compute on provided keypoints: KeyPointsFilter::runByImageBorder(kps, image size, 31) keeping the order, then a
+// stable regrouping by octave when the input is not sorted by level (orb.cpp detectAndCompute).  One CTA per image.
+__global__ void __launch_bounds__(256) bird_filter_kernel(BirdGeom g, const orbb200_kp_t* __restrict__ in, const int32_t* __restrict__ inCount,
+                                                          orbb200_kp_t* __restrict__ out, int32_t* __restrict__ outCount)
+{
+    __shared__ int sBase[BV_LEVELS + 1], sWarp[8], sSorted;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = min(inCount[img], g.kpPerImg);
+    const orbb200_kp_t* K = in + (size_t)img * g.kpPerImg;
+    orbb200_kp_t* O = out + (size_t)img * g.kpPerImg;
+    auto keep = [&](const orbb200_kp_t& k) {
+        if (g.h <= BV_EDGE * 2 || g.w <= BV_EDGE * 2) return false;
+        const int x = __float2int_rn(k.x), y = __float2int_rn(k.y);
+        return x >= BV_EDGE && x < g.w - BV_EDGE && y >= BV_EDGE && y < g.h - BV_EDGE && k.octave >= 0 && k.octave < BV_LEVELS;
+    };
+    // sortedByLevel?
+    if (tid == 0) sSorted = 1;
+    __syncthreads();
+    for (int i = tid + 1; i < n; i += 256) if (K[i].octave < K[i - 1].octave) sSorted = 0;
+    __syncthreads();
+    const bool sorted = sSorted != 0;
+    // pass 1: per-level counts of kept keypoints (one level "all" when already sorted)
+    if (tid <= BV_LEVELS) sBase[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) if (keep(K[i])) atomicAdd(&sBase[sorted ? 0 : K[i].octave], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l <= BV_LEVELS; l++) { const int c = sBase[l]; sBase[l] = acc; acc += c; }
+        outCount[img] = acc;
+    }
+    __syncthreads();
+    // pass 2: stable scatter, chunks of 256 in order
+    for (int l = 0; l < (sorted ? 1 : BV_LEVELS); l++) {
+        int base = sBase[l];
+        for (int c0 = 0; c0 < n; c0 += 256) {
+            const int i = c0 + tid;
+            orbb200_kp_t k;
+            bool f = false;
+            if (i < n) { k = K[i]; f = keep(k) && (sorted || k.octave == l); }
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) sWarp[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, totalc = 0;
+            for (int w = 0; w < 8; w++) { if (w < wid) before += sWarp[w]; totalc += sWarp[w]; }
+            if (f) O[base + before + __popc(bal & ((1u << lane) - 1u))] = k;
+            base += totalc;
+            __syncthreads();
+        }
+    }
+}
+
+// sepFilter2D(8U -> 8U, float getGaussianKernel(7, 2)) -- what GaussianBlur(7x7, 2, 2, BORDER_REFLECT_101) does on a
+// sub-matrix (orb.cpp blurs the layers inside the packed buffer): rows = float sum k[i]*p[i] left to right; columns =
+// k[3]*H[y] then += k[3+j]*(H[y+j] + H[y-j]); cvRound + saturate.  One thread per output pixel column segment.
+struct GaussK { float k[7]; };
+
+__global__ void __launch_bounds__(128) bird_blur_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, unsigned planeBytes, BirdGeom g,
+                                                        GaussK gk, int nLevels)
+{
+    const int level = blockIdx.z % BV_LEVELS, img = blockIdx.z / BV_LEVELS;
+    if (level >= nLevels) return;
+    const BirdLevel L = g.lv[level];
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y0 = blockIdx.y * 16;
+    if (x >= L.w || y0 >= L.h) return;
+    const uint8_t* S = pyr + (size_t)img * planeBytes + L.off;
+    uint8_t* D = blur + (size_t)img * planeBytes + L.off;
+    float H[22];
+    const int rows = min(16, L.h - y0);
+    for (int r = 0; r < rows + 6; r++) {
+        const uint8_t* s = S + (ptrdiff_t)(y0 + r - 3) * L.pitch + x - 3;
+        float acc = __fmul_rn(gk.k[0], (float)s[0]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) acc = __fadd_rn(acc, __fmul_rn(gk.k[k], (float)s[k]));
+        H[r] = acc;
+    }
+    for (int r = 0; r < rows; r++) {
+        float acc = __fmul_rn(gk.k[3], H[r + 3]);
+#pragma unroll
+        for (int j = 1; j <= 3; j++) acc = __fadd_rn(acc, __fmul_rn(gk.k[3 + j], __fadd_rn(H[r + 3 + j], H[r + 3 - j])));
+        const int v = __float2int_rn(acc);
+        D[(size_t)(y0 + r) * L.pitch + x] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// computeOrbDescriptors (orb.cpp, WTA_K 2): one warp per keypoint, one descriptor byte per lane; the keypoint's angle is
+// taken as given, its position is cvRound(pt / layerScale) on the blurred layer.
+__global__ void __launch_bounds__(256) bird_describe_kernel(BirdGeom g, const uint8_t* __restrict__ blur, const orbb200_kp_t* __restrict__ kps,
+                                                            const int32_t* __restrict__ counts, uint8_t* __restrict__ desc)
+{
+    __shared__ float sPX[16 * 32], sPY[16 * 32];
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 512; i += blockDim.x) {
+        const int o = (i & 15) * 32 + (i >> 4);
+        sPX[o] = (float)c_patX[i]; sPY[o] = (float)c_patY[i];
+    }
+    __syncthreads();
+    const int gk = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    if (gk >= counts[img]) return;
+    const orbb200_kp_t kp = kps[(size_t)img * g.kpPerImg + gk];
+    const BirdLevel L = g.lv[kp.octave];
+    constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);
+    const float ang = __fmul_rn(kp.angle, factorPI);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);                    // == host cosf/sinf for all but ~1e-8 of inputs
+    const float a = (float)cd, b = (float)sd;
+    const int cx = __float2int_rn(__fmul_rn(kp.x, L.invScale)), cy = __float2int_rn(__fmul_rn(kp.y, L.invScale));
+    const uint8_t* bc = blur + (size_t)img * g.planeBytes + L.off + (ptrdiff_t)cy * L.pitch + cx;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int idx = (2 * k + e) * 32 + lane;
+            const float px = sPX[idx], py = sPY[idx];
+            const int xx = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
+            const int yy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
+            t[e] = bc[yy * L.pitch + xx];
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    desc[((size_t)img * g.kpPerImg + gk) * 32 + lane] = (uint8_t)val;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+BirdState& state(Ctx& c)
+{
+    if (!c.bird) c.bird = new BirdState();
+    return *static_cast<BirdState*>(c.bird);
+}
+
+void free_plan(BirdPlan* p)
+{
+    void* ptrs[] = {p->d_tab, p->d_cells, p->d_pyr, p->d_mask, p->d_blur, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount,
+                    p->d_kps, p->d_kps2, p->d_desc, p->d_counts, p->d_counts2, p->d_pts};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete p;
+}
+
+void exact_table(int ssize, int dsize, std::vector<int2>& tab)
+{
+    // resize.cpp interpolationLinear<ufixedpoint16>: coordinates in (soft)double, coefficients rounded to 8.8
+    const double scale = 1.0 / ((double)dsize / ssize);
+    for (int v = 0; v < dsize; v++) {
+        const double fval = scale * ((double)v + 0.5) - 0.5;
+        const int ival = cvFloorD(fval);
+        int2 e = make_int2(0, 0);
+        if (ival >= 0 && ssize > 1) {
+            if (ival < ssize - 1) { e.x = ival; e.y = (int)std::nearbyint((fval - (double)ival) * 256.0); }
+            else e.x = ssize - 1;
+        }
+        tab.push_back(e);
+    }
+}
+
+BirdPlan* get_plan(Ctx& c, int w, int h, int nfeatures, int batch)
+{
+    BirdState& S = state(c);
+    const auto key = std::make_tuple(w, h, nfeatures);
+    auto it = S.plans.find(key);
+    BirdPlan* p = it == S.plans.end() ? nullptr : it->second;
+    if (p && p->batch >= batch) return p;
+    if (p) { cudaStreamSynchronize(c.stream); free_plan(p); S.plans.erase(key); }
+    p = new BirdPlan();
+    BirdGeom& g = p->g;
+    g.w = w; g.h = h; g.nfeatures = nfeatures;
+    // per-level quotas (orb.cpp computeKeyPoints)
+    const double scaleFactor = (double)1.2f;
+    const float factor = (float)(1.0 / scaleFactor);
+    float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)BV_LEVELS));
+    int sum = 0;
+    size_t off = 0, candOff = 0;
+    int kpOff = 0;
+    std::vector<int2> tab;
+    std::vector<int4> cells;
+    for (int l = 0; l < BV_LEVELS; l++) {
+        BirdLevel& L = g.lv[l];
+        L.scale = (float)std::pow(scaleFactor, (double)l);
+        L.invScale = 1.0f / L.scale;
+        L.w = cvRoundF(w * L.invScale); L.h = cvRoundF(h * L.invScale);
+        if (l < BV_LEVELS - 1) { L.quota = cvRoundF(nd); sum += L.quota; nd *= factor; }
+        else L.quota = std::max(nfeatures - sum, 0);
+        L.pitch = (int)align_up((size_t)L.w + 2 * BV_MARGIN, 128);
+        L.off = (unsigned)(off + (size_t)BV_MARGIN * L.pitch + BV_MARGIN);
+        off += align_up((size_t)(L.h + 2 * BV_MARGIN) * L.pitch, 128);
+        L.candCap = std::min(std::max((L.w * L.h) / 4, 64), BV_SORT_CAP);
+        L.candOff = (unsigned)candOff; candOff += L.candCap;
+        L.kpCap = std::min(L.candCap, 2 * L.quota + 64);
+        L.kpOff = kpOff; kpOff += L.kpCap;
+        if (l > 0) {
+            L.tabX = (int)tab.size(); exact_table(g.lv[l - 1].w, L.w, tab);
+            L.tabY = (int)tab.size(); exact_table(g.lv[l - 1].h, L.h, tab);
+        }
+        // whole-level FAST as tiles: a tile's cell image is the emit tile grown by 4 (3 ring pixels + 1 for the NMS
+        // neighbourhood), clipped to the level; corners closer than edgeThreshold to the level border are dropped by
+        // runByImageBorder anyway, so only [31, w-31) x [31, h-31) is emitted
+        if (L.w > 2 * BV_EDGE && L.h > 2 * BV_EDGE)
+            for (int ty = BV_EDGE; ty < L.h - BV_EDGE; ty += BV_TILE)
+                for (int tx = BV_EDGE; tx < L.w - BV_EDGE; tx += BV_TILE) {
+                    const int ex1 = std::min(tx + BV_TILE, L.w - BV_EDGE), ey1 = std::min(ty + BV_TILE, L.h - BV_EDGE);
+                    push_fast_cell(cells, p->need, tx - 4, ty - 4, std::min(ex1 + 4, L.w), std::min(ey1 + 4, L.h), l, L.off, L.pitch,
+                                   L.candOff, L.candCap, tx, ty, ex1, ey1);
+                }
+    }
+    g.planeBytes = (unsigned)align_up(off, 256);
+    g.candPerImg = (unsigned)candOff;
+    g.kpPerImg = kpOff;
+    p->nCells = (int)(cells.size() / 3);
+    p->batch = batch;
+    const size_t B = (size_t)batch;
+    bool ok = cudaMalloc((void**)&p->d_tab, std::max<size_t>(tab.size(), 1) * sizeof(int2)) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_cells, std::max<size_t>(cells.size(), 1) * sizeof(int4)) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_pyr, B * g.planeBytes) == cudaSuccess && cudaMalloc((void**)&p->d_mask, B * g.planeBytes) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_blur, B * g.planeBytes) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_cand, B * g.candPerImg * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_candCount, B * MAX_LEVELS * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_lvlKp, B * g.kpPerImg * sizeof(float4)) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_lvlCount, B * BV_LEVELS * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_kps, B * g.kpPerImg * sizeof(orbb200_kp_t)) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_kps2, B * g.kpPerImg * sizeof(orbb200_kp_t)) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_desc, B * g.kpPerImg * 32) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_counts, B * 4) == cudaSuccess && cudaMalloc((void**)&p->d_counts2, B * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_pts, B * g.kpPerImg * 8) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemcpyAsync(p->d_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream) == cudaSuccess &&
+             cudaMemcpyAsync(p->d_cells, cells.data(), cells.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream) == cudaSuccess &&
+             cudaMemsetAsync(p->d_mask, 0, B * g.planeBytes, c.stream) == cudaSuccess &&
+             cudaMemsetAsync(p->d_pyr, 0, B * g.planeBytes, c.stream) == cudaSuccess &&
+             cudaStreamSynchronize(c.stream) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); free_plan(p); c.err = "bird: cudaMalloc failed"; return nullptr; }
+    S.plans[key] = p;
+    return p;
+}
+
+// upload n images (host pointers) into level 0 of the planes; mask optional
+int upload_images(Ctx& c, BirdPlan* p, const uint8_t* const* imgs, const uint8_t* const* masks, int n, size_t stride, size_t mstride)
+{
+    const BirdGeom& g = p->g;
+    const BirdLevel& L0 = g.lv[0];
+    for (int i = 0; i < n; i++) {
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_pyr + (size_t)i * g.planeBytes + L0.off, L0.pitch, imgs[i], stride, g.w, g.h,
+                                             cudaMemcpyHostToDevice, c.stream));
+        if (masks)
+            ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_mask + (size_t)i * g.planeBytes + L0.off, L0.pitch, masks[i], mstride, g.w, g.h,
+                                                 cudaMemcpyHostToDevice, c.stream));
+    }
+    return ORBB200_OK;
+}
+
+void enqueue_pyramid(Ctx& c, BirdPlan* p, int n, bool withMask, int nLevels)
+{
+    const BirdGeom& g = p->g;
+    for (int l = 1; l < nLevels; l++) {
+        const BirdLevel& D = g.lv[l];
+        dim3 grid((D.w + 127) / 128, D.h, n);
+        bird_resize_kernel<<<grid, 128, 0, c.stream>>>(p->d_pyr, g.planeBytes, g.lv[l - 1], D, p->d_tab, 0);
+        c.launches++;
+        if (withMask) {
+            bird_resize_kernel<<<grid, 128, 0, c.stream>>>(p->d_mask, g.planeBytes, g.lv[l - 1], D, p->d_tab, 1);
+            c.launches++;
+        }
+    }
+    bird_border_kernel<<<dim3(64, nLevels, n), 256, 0, c.stream>>>(p->d_pyr, g.planeBytes, g);
+    c.launches++;
+}
+
+int enqueue_detect(Ctx& c, BirdPlan* p, int n, bool withMask)
+{
+    const BirdGeom& g = p->g;
+    enqueue_pyramid(c, p, n, withMask, BV_LEVELS);
+    cudaMemsetAsync(p->d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
+    launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
+                      p->d_candCount, n);
+    const size_t smem = (size_t)BV_SORT_CAP * 8;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(bird_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    bird_select_kernel<<<dim3(BV_LEVELS, n), SEL_THREADS, smem, c.stream>>>(g, p->d_pyr, withMask ? p->d_mask : nullptr, p->d_cand, p->d_candCount,
+                                                                          p->d_lvlKp, p->d_lvlCount, c.d_status);
+    c.launches++;
+    bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
+    c.launches++;
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+int ensure_win_mask(Ctx& c, int winW, int winH)
+{
+    BirdState& S = state(c);
+    if (S.winW == winW && S.winH == winH) return ORBB200_OK;
+    const int ww = 2 * winW + 1, wh = 2 * winH + 1;
+    std::vector<float> m((size_t)ww * wh);
+    for (int i = 0; i < wh; i++) {
+        const float y = (float)(i - winH) / winH;
+        const float vy = std::exp(-y * y);
+        for (int j = 0; j < ww; j++) {
+            const float x = (float)(j - winW) / winW;
+            m[(size_t)i * ww + j] = (float)(vy * std::exp(-x * x));
+        }
+    }
+    if (!S.d_winMask) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_winMask, sizeof(float) * (2 * BV_MAX_WIN + 1) * (2 * BV_MAX_WIN + 1)));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(S.d_winMask, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    S.winW = winW; S.winH = winH;
+    return ORBB200_OK;
+}
+
+int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFixed, int winW, int winH, int maxCount, double epsilon)
+{
+    const BirdGeom& g = p->g;
+    if (winW <= 0 || winH <= 0 || winW > BV_MAX_WIN || winH > BV_MAX_WIN) { c.err = "cornerSubPix: window half-size must be in 1..7"; return ORBB200_ERR_ARG; }
+    if (g.w < winW * 2 + 5 || g.h < winH * 2 + 5) { c.err = "cornerSubPix: image smaller than the window"; return ORBB200_ERR_ARG; }
+    const int rc = ensure_win_mask(c, winW, winH);
+    if (rc != ORBB200_OK) return rc;
+    const int maxIters = std::min(std::max(maxCount, 1), 100);
+    double eps = std::max(epsilon, 0.);
+    eps *= eps;
+    const BirdLevel& L0 = g.lv[0];
+    bird_subpix_kernel<<<dim3((g.kpPerImg + SP_THREADS - 1) / SP_THREADS, n), SP_THREADS, 0, c.stream>>>(
+        p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
+    c.launches++;
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+// d_kps/d_counts -> filtered into d_kps2/d_counts2, descriptors in d_desc
+int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels)
+{
+    const BirdGeom& g = p->g;
+    bird_filter_kernel<<<n, 256, 0, c.stream>>>(g, p->d_kps, p->d_counts, p->d_kps2, p->d_counts2);
+    c.launches++;
+    GaussK gk;
+    {   // cv::getGaussianKernel(7, 2, CV_32F)
+        double sum = 0;
+        for (int i = 0; i < 7; i++) { const double x = i - 3.0; gk.k[i] = (float)std::exp(-0.5 / 4.0 * x * x); sum += gk.k[i]; }
+        sum = 1. / sum;
+        for (int i = 0; i < 7; i++) gk.k[i] = (float)(gk.k[i] * sum);
+    }
+    int maxW = 1, maxH = 1;
+    for (int l = 0; l < nLevels; l++) { maxW = std::max(maxW, g.lv[l].w); maxH = std::max(maxH, g.lv[l].h); }
+    bird_blur_kernel<<<dim3((maxW + 127) / 128, (maxH + 15) / 16, n * BV_LEVELS), 128, 0, c.stream>>>(p->d_pyr, p->d_blur, g.planeBytes, g, gk, nLevels);
+    c.launches++;
+    bird_describe_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_blur, p->d_kps2, p->d_counts2, p->d_desc);
+    c.launches++;
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+int check_bird_status(Ctx& c)
+{
+    int32_t st = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&st, c.d_status, sizeof(st), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (st != 0) {
+        cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
+        c.err = st == 3 ? "bird: more FAST corners on a level than the selection kernel holds (16384)"
+                        : "bird: more keypoints tie at the retainBest threshold than the output holds";
+        return ORBB200_ERR_CAPACITY;
+    }
+    return ORBB200_OK;
+}
+
+int download(Ctx& c, BirdPlan* p, int n, const orbb200_kp_t* d_kps, const int32_t* d_counts, orbb200_kp_t* kps, uint8_t* desc, int cap, int* n_out)
+{
+    const BirdGeom& g = p->g;
+    std::vector<int32_t> cnt(n);
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(cnt.data(), d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+    const int rc = check_bird_status(c);        // synchronises
+    if (rc != ORBB200_OK) return rc;
+    for (int i = 0; i < n; i++) {
+        const int m = std::min(cnt[i], cap);
+        if (cnt[i] > cap) { c.err = "bird: output capacity too small"; return ORBB200_ERR_CAPACITY; }
+        if (m > 0 && kps) ORBB200_CUDA_OK(c, cudaMemcpyAsync(kps + (size_t)i * cap, d_kps + (size_t)i * g.kpPerImg, sizeof(orbb200_kp_t) * m, cudaMemcpyDeviceToHost, c.stream));
+        if (m > 0 && desc) ORBB200_CUDA_OK(c, cudaMemcpyAsync(desc + (size_t)i * cap * 32, p->d_desc + (size_t)i * g.kpPerImg * 32, (size_t)m * 32, cudaMemcpyDeviceToHost, c.stream));
+        n_out[i] = m;
+    }
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
+}  // namespace
+
+void bird_destroy(Ctx& c)
+{
+    if (!c.bird) return;
+    BirdState* S = static_cast<BirdState*>(c.bird);
+    for (auto& kv : S->plans) free_plan(kv.second);
+    if (S->d_winMask) cudaFree(S->d_winMask);
+    delete S;
+    c.bird = nullptr;
+}
+
+}  // namespace orbb200
+
+using namespace orbb200;
+
+#define BIRD_ENTER(ctx)                                             \
+    if (!(ctx)) return ORBB200_ERR_ARG;                             \
+    Ctx& c = (ctx)->c;                                              \
+    ORBB200_CUDA_OK(c, cudaSetDevice(c.device))
+
+extern "C" {
+
+int orbb200_bird_max_keypoints(orbb200_ctx* ctx, int w, int h, int nfeatures)
+{
+    BIRD_ENTER(ctx);
+    if (w <= 0 || h <= 0 || nfeatures <= 0) return 0;
+    BirdPlan* p = get_plan(c, w, h, nfeatures, 1);
+    return p ? p->g.kpPerImg : 0;
+}
+
+int orbb200_bird_detect(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mask, int w, int h, size_t stride, size_t mask_stride,
+                        int nfeatures, orbb200_kp_t* kps, int cap, int* n_out)
+{
+    BIRD_ENTER(ctx);
+    if (!img || !kps || !n_out || w <= 0 || h <= 0 || nfeatures <= 0 || w > 4000 || h > 4000) { c.err = "bird_detect: bad argument"; return ORBB200_ERR_ARG; }
+    BirdPlan* p = get_plan(c, w, h, nfeatures, 1);
+    if (!p) return ORBB200_ERR_CUDA;
+    int rc = upload_images(c, p, &img, mask ? &mask : nullptr, 1, stride, mask_stride);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, 1, mask != nullptr);
+    if (rc != ORBB200_OK) return rc;
+    return download(c, p, 1, p->d_kps, p->d_counts, kps, nullptr, cap, n_out);
+}
+
+int orbb200_corner_subpix(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, float* pts, int n, int win_w, int win_h,
+                          int max_iter, double eps)
+{
+    BIRD_ENTER(ctx);
+    if (!img || n < 0 || (n > 0 && !pts) || w <= 0 || h <= 0 || w > 4000 || h > 4000) { c.err = "corner_subpix: bad argument"; return ORBB200_ERR_ARG; }
+    if (n == 0) return ORBB200_OK;
+    BirdPlan* p = get_plan(c, w, h, 2000, 1);
+    if (!p) return ORBB200_ERR_CUDA;
+    int rc = upload_images(c, p, &img, nullptr, 1, stride, 0);
+    if (rc != ORBB200_OK) return rc;
+    const int cap = p->g.kpPerImg;
+    for (int o = 0; o < n; o += cap) {
+        const int m = std::min(cap, n - o);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_pts, pts + 2 * (size_t)o, sizeof(float) * 2 * m, cudaMemcpyHostToDevice, c.stream));
+        rc = enqueue_subpix(c, p, 1, nullptr, m, win_w, win_h, max_iter, eps);
+        if (rc != ORBB200_OK) return rc;
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(pts + 2 * (size_t)o, p->d_pts, sizeof(float) * 2 * m, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    }
+    return ORBB200_OK;
+}
+
+int orbb200_bird_compute(orbb200_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, orbb200_kp_t* kps, int n, uint8_t* desc,
+                         int* n_out)
+{
+    BIRD_ENTER(ctx);
+    if (!img || n < 0 || !n_out || (n > 0 && (!kps || !desc)) || w <= 0 || h <= 0 || w > 4000 || h > 4000) { c.err = "bird_compute: bad argument"; return ORBB200_ERR_ARG; }
+    *n_out = 0;
+    if (n == 0) return ORBB200_OK;
+    BirdPlan* p = get_plan(c, w, h, 2000, 1);
+    if (!p) return ORBB200_ERR_CUDA;
+    if (n > p->g.kpPerImg) { c.err = "bird_compute: too many keypoints for one call"; return ORBB200_ERR_ARG; }
+    int nLevels = 0;
+    for (int i = 0; i < n; i++) {
+        if (kps[i].octave < 0 || kps[i].octave >= BV_LEVELS) { c.err = "bird_compute: keypoint octave out of range"; return ORBB200_ERR_ARG; }
+        nLevels = std::max(nLevels, kps[i].octave);
+    }
+    nLevels++;
+    int rc = upload_images(c, p, &img, nullptr, 1, stride, 0);
+    if (rc != ORBB200_OK) return rc;
+    const int32_t cnt = n;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_kps, kps, sizeof(orbb200_kp_t) * n, cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_counts, &cnt, 4, cudaMemcpyHostToDevice, c.stream));
+    enqueue_pyramid(c, p, 1, false, nLevels);
+    rc = enqueue_compute(c, p, 1, nLevels);
+    if (rc != ORBB200_OK) return rc;
+    return download(c, p, 1, p->d_kps2, p->d_counts2, kps, desc, n, n_out);
+}
+
+int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, const uint8_t* const* masks, int n, int w, int h, size_t stride,
+                               size_t mask_stride, int nfeatures, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out)
+{
+    BIRD_ENTER(ctx);
+    if (!imgs || n <= 0 || !kps || !desc || !n_out || w <= 0 || h <= 0 || nfeatures <= 0 || w > 4000 || h > 4000) { c.err = "bird_extract: bad argument"; return ORBB200_ERR_ARG; }
+    BirdPlan* p = get_plan(c, w, h, nfeatures, n);
+    if (!p) return ORBB200_ERR_CUDA;
+    const BirdGeom& g = p->g;
+    int rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr);
+    if (rc != ORBB200_OK) return rc;
+    // cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001))   (src/Frame.cc:335-336)
+    bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
+    c.launches++;
+    if (g.w >= 15 && g.h >= 15) {
+        rc = enqueue_subpix(c, p, n, p->d_counts, 0, 5, 5, 40, 0.001);
+        if (rc != ORBB200_OK) return rc;
+    }
+    bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 1);
+    c.launches++;
+    rc = enqueue_compute(c, p, n, BV_LEVELS);
+    if (rc != ORBB200_OK) return rc;
+    return download(c, p, n, p->d_kps2, p->d_counts2, kps, desc, cap_per_img, n_out);
+}
+
+int orbb200_bird_extract(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mask, int w, int h, size_t stride, size_t mask_stride,
+                         int nfeatures, orbb200_kp_t* kps, uint8_t* desc, int cap, int* n_out)
+{
+    return orbb200_bird_extract_batch(ctx, &img, mask ? &mask : nullptr, 1, w, h, stride, mask_stride, nfeatures, kps, desc, cap, n_out);
+}
+
+}  // extern "C"

@@ -21,7 +21,7 @@ struct ShapeTables {
     struct GraphExec { cudaGraphExec_t exec; long long launches; };
     std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count
     int nFastCells = 0;         // entries of d_cells (cells the reference skips at the image edge are not listed)
-    int fastTileWords = 0, fastScrWords = 0, fastClistCap = 0, fastWorkCap = 0;   // shared-memory carve of fast_cells_kernel
+    FastSmem fastSmem;          // shared-memory carve of fast_cells_kernel
 };
 
 struct WinJob;
@@ -81,6 +81,7 @@ struct Ctx {
     int32_t* d_rowItems = nullptr;           // [maxBatch/2+1][stereoItemCap]
     int stereoItemCap = 0;
     bool stereoValid = false;
+    void* bird = nullptr;                    // birdview front-end plans (bird.cu)
     bool forkBlur = true;                    // blur on the side stream (ORBB200_SERIAL=1 in the environment turns it off)
     bool useGraphs = true;                   // replay the extraction launches from a CUDA graph
     bool stepStereo = false;                 // orbb200_step_enable_stereo: the batched step also runs stereo matching

@@ -7,7 +7,7 @@
 #include <cuda_fp16.h>
 
 #include "ctx.cuh"
-#include "../../include/orbb200_pattern.inc"
+#include "device_math.cuh"
 
 namespace orbb200 {
 
@@ -371,7 +371,7 @@ __device__ __forceinline__ int seg_list_at(const uint16_t* list, int seg, const 
 __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
                                                                    int minTh, int iniTh, const int4* __restrict__ cells,
                                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
-                                                                   int tileWords, int scrWords, int clistCap, int workCap)
+                                                                   int tileWords, int scrWords, int clistCap, int workCap, int passes)
 {
     // tile[r][1+m] = pixels (2m, 2m+1) of cell-image row r as u16x2; score tile in the same layout with a
     // zero row above/below.  Row pitch == pairs-per-row (mod 32): the flattened (row, pair) -> lane mapping
@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     const int img = blockIdx.y;
     const int4 cell = __ldg(cells + 3 * blockIdx.x);         // {x0|y0<<16, x1|y1<<16, level, -}
     const int4 lvl = __ldg(cells + 3 * blockIdx.x + 1);      // {level byte offset, pitch, candOff, candCap}
-    const int4 mg = __ldg(cells + 3 * blockIdx.x + 2);       // {2^32/nw + 1, 2^32/npr + 1, -, -}
+    const int4 mg = __ldg(cells + 3 * blockIdx.x + 2);       // {2^32/nw + 1, 2^32/npr + 1, emit x0|y0<<16, emit x1|y1<<16}
+    const int ex0 = mg.z & 0xffff, ey0 = mg.z >> 16, ex1 = mg.w ? (mg.w & 0xffff) : 0x7fff, ey1 = mg.w ? (mg.w >> 16) : 0x7fff;
     const int x0 = cell.x & 0xffff, y0 = cell.x >> 16, x1 = cell.y & 0xffff, y1 = cell.y >> 16;
     const int level = cell.z;
     const int pitch = lvl.y;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     const int wseg = ((total + FT_THREADS - 1) / FT_THREADS) * 32;      // upper bound of a warp's share of the score loop
     const unsigned ltmask = (1u << lane) - 1u;
     int nEmit = 0;
-    for (int pass = 0; pass < 2; pass++) {
+    for (int pass = 0; pass < passes; pass++) {
         const int thr = pass ? minTh : iniTh;
         const uint32_t Tp = (uint32_t)(min(max(thr, 0), 255) + 1) * 0x00010001u;
         if (tid == 0) sN = 0;
@@ -512,13 +513,15 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
                 nb = max3s(nb, d1, __funnelshift_r(d0, d1, 16));
                 nb = __vmaxs2(nb, __funnelshift_r(d1, d2, 16));
                 const int nl = nb & 0xffff, nh = nb >> 16;
-                const int ry = y0 + rr + 3 - FAST_BORDER;               // region coordinates
+                const int ly = y0 + rr + 3;
+                const int ry = ly - FAST_BORDER;                        // region coordinates
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int sv = e ? sh : sl, nv = e ? nh : nl;
-                    if (sv >= thr && sv > nv) {
+                    const int lx = xa + 2 * m + e;
+                    if (sv >= thr && sv > nv && lx >= ex0 && lx < ex1 && ly >= ey0 && ly < ey1) {
                         const int slot = atomicAdd(&sN, 1);
-                        const int rx = xa + 2 * m + e - FAST_BORDER;
+                        const int rx = lx - FAST_BORDER;
                         if (slot < clistCap) clist[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sv << 24);
                     }
                 }
@@ -914,33 +917,6 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
 // (computeOrbDescriptor :108-147): one warp per keypoint.  Writes the final cv::KeyPoint records
 // (operator() :1095-1103: pt *= scale for level > 0) and descriptors in level-major order.
 // ---------------------------------------------------------------------------------------------------
-__constant__ signed char c_patX[512] = {ORBB200_PATTERN_X_INIT};
-__constant__ signed char c_patY[512] = {ORBB200_PATTERN_Y_INIT};
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // :454-469
-
-__device__ __forceinline__ float fast_atan2_deg(float y, float x)
-{
-    // cv::fastAtan2, float32 without FMA contraction
-    constexpr float k180pi = (float)(180.0 / 3.14159265358979323846);
-    constexpr float p1 = 0.9997878412794807f * k180pi, p3 = -0.3258083974640975f * k180pi;
-    constexpr float p5 = 0.1555786518463281f * k180pi, p7 = -0.04432655554792128f * k180pi;
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    const float eps = 2.22044605e-16f;   // (float)DBL_EPSILON
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
-}
-
 constexpr int DS_WARPS = 8;
 constexpr int DS_KPB = 32;        // keypoints per CTA: one lane each for the scalar (atan2, sincos) part
 
@@ -1096,23 +1072,51 @@ void launch_blur(Ctx& c, int n, cudaStream_t stream)
     c.launches++;
 }
 
+void push_fast_cell(std::vector<int4>& cells, FastSmem& need, int x0, int y0, int x1, int y1, int level, unsigned levelOff, int pitch,
+                    unsigned candOff, int candCap, int ex0, int ey0, int ex1, int ey1)
+{
+    cells.push_back(make_int4(x0 | (y0 << 16), x1 | (y1 << 16), level, 0));
+    cells.push_back(make_int4((int)levelOff, pitch, (int)candOff, candCap));
+    cells.push_back(make_int4(0, 0, ex0 | (ey0 << 16), ex1 | (ey1 << 16)));
+    // shared-memory needs of this cell, mirroring fast_cells_kernel's carve
+    const int th = y1 - y0, xa = x0 & ~3;
+    const int wi = x1 - x0 - 6, hi = th - 6;
+    if (wi > 0 && hi > 0) {
+        const int cx0 = x0 - xa + 3, cx1 = cx0 + wi, npr = ((cx1 - 1) >> 1) - (cx0 >> 1) + 1;
+        const int nw = (x1 - xa + 3) >> 2;
+        // floor(i / d) == umulhi(i, 2^32 / d + 1) for the small i used; d == 1 is special-cased in the kernel
+        cells.back().x = (int)(0xffffffffu / (uint32_t)nw + 1u);
+        cells.back().y = (int)(0xffffffffu / (uint32_t)npr + 1u);
+        need.tileWords = std::max(need.tileWords, th * FT_PITCH);
+        need.scrWords = std::max(need.scrWords, (hi + 2) * FT_PITCH);
+        need.clistCap = std::max(need.clistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
+        need.workCap = std::max(need.workCap, ((hi * npr + 1) & ~1) + 128);   // per-warp list segments: total + slack
+    }
+}
+
+void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh, int passes,
+                       const int4* d_cells, int nCells, const FastSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n)
+{
+    if (nCells <= 0 || n <= 0) return;
+    const size_t smem = need.bytes();
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid(nCells, n);
+    fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_cells, d_cand, d_candCount,
+                                                           need.tileWords, need.scrWords, need.clistCap, need.workCap, passes);
+    c.launches++;
+}
+
 void launch_fast(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
+    const ShapeTables& st = *c.cur;
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
-    if (c.cur->nFastCells > 0) {
-        const ShapeTables& st = *c.cur;
-        const size_t smem = sizeof(uint32_t) * ((size_t)st.fastTileWords + st.fastScrWords + st.fastClistCap) + sizeof(uint16_t) * 2 * (size_t)st.fastWorkCap;
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
-        dim3 grid(st.nFastCells, n);
-        fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_cells, c.d_cand,
-                                                               c.d_candCount, st.fastTileWords, st.fastScrWords, st.fastClistCap, st.fastWorkCap);
-        c.launches++;
-    }
+    launch_fast_cells(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, 2, st.d_cells, st.nFastCells, st.fastSmem, c.d_cand,
+                      c.d_candCount, n);
 }
 
 void launch_octree(Ctx& c, int n)

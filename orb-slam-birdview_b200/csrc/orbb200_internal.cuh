@@ -71,6 +71,21 @@ struct FrameDev {
 
 struct Ctx;
 
+// Shared-memory carve of fast_cells_kernel for a set of cells (host-computed maxima).
+struct FastSmem {
+    int tileWords = 0, scrWords = 0, clistCap = 0, workCap = 0;
+    size_t bytes() const { return sizeof(uint32_t) * ((size_t)tileWords + scrWords + clistCap) + sizeof(uint16_t) * 2 * (size_t)workCap; }
+};
+// Append one FAST cell (3 x int4) to a host cell table and grow `need`.  [x0,x1) x [y0,y1) is the cell image in level
+// coordinates (3-pixel FAST margin included); candidates are only emitted inside [ex0,ex1) x [ey0,ey1) (ex1 == 0: anywhere).
+void push_fast_cell(std::vector<int4>& cells, FastSmem& need, int x0, int y0, int x1, int y1, int level, unsigned levelOff, int pitch,
+                    unsigned candOff, int candCap, int ex0 = 0, int ey0 = 0, int ex1 = 0, int ey1 = 0);
+// passes: 2 = cv::FAST(iniTh) and, when the cell stays empty, cv::FAST(minTh) (ORBextractor); 1 = iniTh only
+void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh, int passes,
+                       const int4* d_cells, int nCells, const FastSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n);
+
+void bird_destroy(Ctx& c);   // bird.cu
+
 // ---- kernels launchers (extract.cu) ----
 void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);
 void launch_pyramid(Ctx& c, int n);

@@ -530,3 +530,80 @@ def test_search_local_points(pkg):
         assert k == k0 and np.array_equal(iv, iv0) and np.array_equal(lvl, lvl0)
         assert nm == nm0 and nm > 50, (th, nm, nm0)
         assert np.array_equal(bi, bi0) and np.array_equal(bd[bi >= 0], bd0[bi0 >= 0]) and np.array_equal(qk, qk0)
+
+
+# ---- birdview front-end: cv::ORB detect + cornerSubPix + compute (src/Frame.cc:328-342) -------------------------------
+def _same_kps(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+
+
+@pytest.mark.parametrize("size,seed,with_mask,nf", [(400, 3101, True, 2000), (384, 3102, False, 2000), ((500, 360), 3103, True, 2000),
+                                                    (240, 99, True, 700), ((131, 97), 7, False, 300)])
+def test_bird_detect_subpix_compute(pkg, size, seed, with_mask, nf):
+    """Every stage against the oracle (itself pinned bit-exactly on cv2 4.13): keypoints incl. ORDER, Harris responses,
+    angles; refined corners bitwise; descriptors exact."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    img, mask = cases.birdview_case(size, seed)
+    mask = mask if with_mask else None
+    B = pkg.BirdviewORB(ctx, nf)
+    det = B.detect(img, mask)
+    det0 = oracle.bird_detect(img, mask, nf)
+    assert _same_kps(det, det0) and len(det0) > 50
+    pts = np.stack([det0["x"], det0["y"]], 1)
+    sub = B.cornerSubPix(img, pts)
+    sub0 = oracle.corner_subpix(img, pts)
+    assert np.array_equal(sub.view(np.uint32), sub0.view(np.uint32))
+    moved = det0.copy()
+    moved["x"], moved["y"] = sub0[:, 0], sub0[:, 1]
+    k, d = B.compute(img, moved)
+    k0, d0 = oracle.bird_compute(img, moved)
+    assert _same_kps(k, k0) and np.array_equal(d, d0)
+    k, d = B(img, mask)                                        # the fused device pipeline
+    k0, d0 = oracle.bird_extract(img, mask, nf)
+    assert _same_kps(k, k0) and np.array_equal(d, d0)
+
+
+@pytest.mark.parametrize("name", ["400", "384_nomask", "500x360"])
+def test_bird_extract_golden(pkg, name):
+    """The device pipeline against vectors produced by cv2 itself (tests/golden/make_golden_bird.py)."""
+    g = np.load(os.path.join(GOLDEN, f"bird_orb_{name}.npz"))
+    w, h = (int(v) for v in g["size"])
+    img, mask = cases.birdview_case((w, h), int(g["seed"]))
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    k, d = pkg.BirdviewORB(ctx, 2000)(img, mask if int(g["with_mask"]) else None)
+    assert _same_kps(k, g["kps"]) and np.array_equal(d, g["desc"])
+
+
+def test_bird_corner_subpix_border_and_windows(pkg):
+    """Corners whose window leaves the image (getRectSubPix's replicate path), other window sizes, unsorted octaves in
+    compute, and a batch call."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    img, mask = cases.birdview_case(320, 4242, vehicle=(60, 100))
+    B = pkg.BirdviewORB(ctx, 1500)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(0, 319, (300, 2)), [[3.2, 4.1], [316.5, 200.2], [100.7, 317.9], [1.0, 318.0], [6.0, 6.0], [0, 0], [319, 319]]]).astype(np.float32)
+    for win, it, eps in (((5, 5), 40, 0.001), ((3, 3), 10, 0.01), ((7, 4), 100, 0.0), ((1, 1), 5, 0.1)):
+        a = B.cornerSubPix(img, pts, win, it, eps)
+        b = oracle.corner_subpix(img, pts, win, it, eps)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), win
+    det = oracle.bird_detect(img, mask, 1500)
+    perm = rng.permutation(len(det))
+    k, d = B.compute(img, det[perm])
+    k0, d0 = oracle.bird_compute(img, det[perm])
+    assert _same_kps(k, k0) and np.array_equal(d, d0)
+    imgs, masks = zip(*[cases.birdview_case(320, 600 + i, vehicle=(60, 100)) for i in range(3)])
+    ks, ds = B.extract_batch(list(imgs), list(masks))
+    for i in range(3):
+        k0, d0 = oracle.bird_extract(imgs[i], masks[i], 1500)
+        assert _same_kps(ks[i], k0) and np.array_equal(ds[i], d0)
+
+
+def test_bird_retain_best_ties(pkg):
+    """Heavily tied FAST scores: the survivors and their order come from the literal std::nth_element sequence."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    rng = np.random.default_rng(8)
+    blocks = (rng.integers(0, 2, (60, 60)) * 60 + 90).astype(np.uint8)
+    img = np.repeat(np.repeat(blocks, 5, 0), 5, 1)
+    a = pkg.BirdviewORB(ctx, 300).detect(img, None)
+    b = oracle.bird_detect(img, None, 300)
+    assert _same_kps(a, b) and len(b) > 100
