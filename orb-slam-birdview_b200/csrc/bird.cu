@@ -395,13 +395,16 @@ __global__ void __launch_bounds__(256) bird_finish_kernel(BirdGeom g, const uint
 }
 
 // ---- cv::getRectSubPix CV_8U -> CV_32F (samplers.cpp: getRectSubPix_8u32f; windows leaving the image go through
-//      getRectSubPix_Cn_ + adjustRect = replicated border) ----
-__device__ void bird_get_rect_sub_pix(const uint8_t* src, int src_step, int src_w, int src_h, float* dst, int win_w, int win_h,
-                                      float cx, float cy)
+//      getRectSubPix_Cn_ + adjustRect = replicated border), one warp per window: every output sample only depends on
+//      its own taps (the "prev" carry of the 8u32f path is (float)(t[j-1] * s), a function of the previous column's
+//      taps), so the lanes fill the window independently with the reference's operation order per sample ----
+__device__ void bird_get_rect_sub_pix_warp(const uint8_t* src, int src_step, int src_w, int src_h, float* dst, int win_w, int win_h,
+                                           float cx, float cy, int lane)
 {
     const float centerx = __fsub_rn(cx, __fmul_rn((float)(win_w - 1), 0.5f));
     const float centery = __fsub_rn(cy, __fmul_rn((float)(win_h - 1), 0.5f));
     const int ipx = (int)floorf(centerx), ipy = (int)floorf(centery);
+    const int total = win_w * win_h;
     if (0 <= ipx && ipx + win_w < src_w && 0 <= ipy && ipy + win_h < src_h) {
         float a = __fsub_rn(centerx, (float)ipx);
         const float b = __fsub_rn(centery, (float)ipy);
@@ -410,14 +413,18 @@ __device__ void bird_get_rect_sub_pix(const uint8_t* src, int src_step, int src_
         const float a12 = __fmul_rn(a, b1), a22 = __fmul_rn(a, b);
         const float oma = __fsub_rn(1.f, a);
         const double s = __ddiv_rn(__dsub_rn(1.0, (double)a), (double)a);
-        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
-        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w) {
-            float prev = __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, (float)p[0]), __fmul_rn(b2, (float)p[src_step])));
-            for (int j = 0; j < win_w; j++) {
-                const float t = __fadd_rn(__fmul_rn(a12, (float)p[j + 1]), __fmul_rn(a22, (float)p[j + 1 + src_step]));
-                dst[j] = __fadd_rn(prev, t);
-                prev = (float)__dmul_rn((double)t, s);
+        const uint8_t* p0 = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / win_w, j = e - i * win_w;
+            const uint8_t* p = p0 + (ptrdiff_t)i * src_step;
+            const float t = __fadd_rn(__fmul_rn(a12, (float)p[j + 1]), __fmul_rn(a22, (float)p[j + 1 + src_step]));
+            float prev;
+            if (j == 0) prev = __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, (float)p[0]), __fmul_rn(b2, (float)p[src_step])));
+            else {
+                const float tp = __fadd_rn(__fmul_rn(a12, (float)p[j]), __fmul_rn(a22, (float)p[j + src_step]));
+                prev = (float)__dmul_rn((double)tp, s);
             }
+            dst[e] = __fadd_rn(prev, t);
         }
         return;
     }
@@ -430,73 +437,89 @@ __device__ void bird_get_rect_sub_pix(const uint8_t* src, int src_step, int src_
                          __fmul_rn((float)r1[j + 1], a22));
     };
     if (0 <= ipx && ipx < src_w - win_w && 0 <= ipy && ipy < src_h - win_h) {
-        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
-        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w)
-            for (int j = 0; j < win_w; j++) dst[j] = tap4(p, p + src_step, j);
+        const uint8_t* p0 = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / win_w, j = e - i * win_w;
+            const uint8_t* p = p0 + (ptrdiff_t)i * src_step;
+            dst[e] = tap4(p, p + src_step, j);
+        }
         return;
     }
-    // adjustRect
+    // adjustRect: the source pointer of window row i advances only while i < rh, and only from row ry on
     int rx, ry, rw, rh;
-    const uint8_t* p = src;
-    if (ipx >= 0) { p += ipx; rx = 0; } else { rx = -ipx; if (rx > win_w) rx = win_w; }
+    const uint8_t* base = src;
+    if (ipx >= 0) { base += ipx; rx = 0; } else { rx = -ipx; if (rx > win_w) rx = win_w; }
     if (ipx < src_w - win_w) rw = win_w;
-    else { rw = src_w - ipx - 1; if (rw < 0) { p += rw; rw = 0; } }
-    if (ipy >= 0) { p += (ptrdiff_t)ipy * src_step; ry = 0; } else ry = -ipy;
+    else { rw = src_w - ipx - 1; if (rw < 0) { base += rw; rw = 0; } }
+    if (ipy >= 0) { base += (ptrdiff_t)ipy * src_step; ry = 0; } else ry = -ipy;
     if (ipy < src_h - win_h) rh = win_h;
-    else { rh = src_h - ipy - 1; if (rh < 0) { p += (ptrdiff_t)rh * src_step; rh = 0; } }
-    p -= rx;
-    for (int i = 0; i < win_h; i++, dst += win_w) {
-        const uint8_t* p2 = p + src_step;
-        if (i < ry || i >= rh) p2 -= src_step;
-        float s0 = __fadd_rn(__fmul_rn((float)p[rx], b1), __fmul_rn((float)p2[rx], b2));
-        for (int j = 0; j < rx; j++) dst[j] = s0;
-        s0 = __fadd_rn(__fmul_rn((float)p[rw], b1), __fmul_rn((float)p2[rw], b2));
-        for (int j = rw; j < win_w; j++) dst[j] = s0;
-        for (int j = rx; j < rw; j++) dst[j] = tap4(p, p2, j);
-        if (i < rh) p = p2;
+    else { rh = src_h - ipy - 1; if (rh < 0) { base += (ptrdiff_t)rh * src_step; rh = 0; } }
+    base -= rx;
+    for (int e = lane; e < total; e += 32) {
+        const int i = e / win_w, j = e - i * win_w;
+        // rows advanced before window row i: one per earlier row k with ry <= k < rh
+        const int adv = max(min(i, rh) - min(ry, min(i, rh)), 0);
+        const uint8_t* p = base + (ptrdiff_t)adv * src_step;
+        const uint8_t* p2 = (i < ry || i >= rh) ? p : p + src_step;
+        float v;
+        if (j < rx) v = __fadd_rn(__fmul_rn((float)p[rx], b1), __fmul_rn((float)p2[rx], b2));
+        else if (j >= rw) v = __fadd_rn(__fmul_rn((float)p[rw], b1), __fmul_rn((float)p2[rw], b2));
+        else v = tap4(p, p2, j);
+        dst[e] = v;
     }
 }
 
-// cv::cornerSubPix (cornersubpix.cpp), zeroZone (-1,-1): one thread per corner.  The sums are accumulated in double in
-// the reference's element order (floating-point addition is not associative), without FMA contraction.
-constexpr int SP_THREADS = 64;
+// cv::cornerSubPix (cornersubpix.cpp), zeroZone (-1,-1): one warp per corner.  The window samples and the per-pixel
+// gradient products are computed by all lanes; the five sums (a, b, c, bb1, bb2) are accumulated in double in the
+// reference's element order -- floating-point addition is not associative -- by one lane each, without FMA contraction.
+constexpr int SP_WARPS = 4;
+constexpr int SP_BUF = (2 * BV_MAX_WIN + 3) * (2 * BV_MAX_WIN + 3);
+constexpr int SP_WIN = (2 * BV_MAX_WIN + 1) * (2 * BV_MAX_WIN + 1);
 
-__global__ void __launch_bounds__(SP_THREADS) bird_subpix_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
-                                                                 int rows, float* __restrict__ pts, size_t ptsPerImg,
-                                                                 const int32_t* __restrict__ counts, int nFixed, const float* __restrict__ winMask,
-                                                                 int winW, int winH, int maxIters, double eps)
+__global__ void __launch_bounds__(SP_WARPS * 32) bird_subpix_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
+                                                                    int rows, float* __restrict__ pts, size_t ptsPerImg,
+                                                                    const int32_t* __restrict__ counts, int nFixed, const float* __restrict__ winMask,
+                                                                    int winW, int winH, int maxIters, double eps)
 {
-    const int img = blockIdx.y;
-    const int i = blockIdx.x * SP_THREADS + threadIdx.x;
+    __shared__ float sBuf[SP_WARPS][SP_BUF];
+    __shared__ double sG[SP_WARPS][5][SP_WIN];          // gxx, gxy, gyy, (gxx*px + gxy*py), (gxy*px + gyy*py)
+    const int img = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * SP_WARPS + wid;
     const int n = counts ? counts[img] : nFixed;
     if (i >= n) return;
     const uint8_t* src = imgs + (size_t)img * imgStrideBytes;
     float* P = pts + (size_t)img * ptsPerImg * 2 + 2 * (size_t)i;
-    const int win_w = winW * 2 + 1, win_h = winH * 2 + 1, bw = win_w + 2;
-    float buf[(2 * BV_MAX_WIN + 3) * (2 * BV_MAX_WIN + 3)];
+    const int win_w = winW * 2 + 1, win_h = winH * 2 + 1, bw = win_w + 2, nwin = win_w * win_h;
+    float* buf = sBuf[wid];
     const float cTx = P[0], cTy = P[1];
     float cIx = cTx, cIy = cTy;
     int iter = 0;
     double err = 0;
     do {
-        double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
-        bird_get_rect_sub_pix(src, pitch, cols, rows, buf, win_w + 2, win_h + 2, cIx, cIy);
-        const float* subpix = buf + bw + 1;
-        for (int ii = 0, k = 0; ii < win_h; ii++, subpix += bw) {
-            const double py = (double)(ii - winH);
-            for (int j = 0; j < win_w; j++, k++) {
-                const double m = (double)winMask[k];
-                const double tgx = (double)__fsub_rn(subpix[j + 1], subpix[j - 1]);
-                const double tgy = (double)__fsub_rn(subpix[j + bw], subpix[j - bw]);
-                const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
-                const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
-                const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
-                const double px = (double)(j - winW);
-                a = __dadd_rn(a, gxx); b = __dadd_rn(b, gxy); c = __dadd_rn(c, gyy);
-                bb1 = __dadd_rn(bb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
-                bb2 = __dadd_rn(bb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
-            }
+        bird_get_rect_sub_pix_warp(src, pitch, cols, rows, buf, win_w + 2, win_h + 2, cIx, cIy, lane);
+        __syncwarp();
+        for (int k = lane; k < nwin; k += 32) {
+            const int ii = k / win_w, j = k - ii * win_w;
+            const float* subpix = buf + (ii + 1) * bw + 1;
+            const double py = (double)(ii - winH), px = (double)(j - winW);
+            const double m = (double)winMask[k];
+            const double tgx = (double)__fsub_rn(subpix[j + 1], subpix[j - 1]);
+            const double tgy = (double)__fsub_rn(subpix[j + bw], subpix[j - bw]);
+            const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
+            const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
+            const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+            sG[wid][0][k] = gxx; sG[wid][1][k] = gxy; sG[wid][2][k] = gyy;
+            sG[wid][3][k] = __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py));
+            sG[wid][4][k] = __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py));
         }
+        __syncwarp();
+        double acc = 0;
+        if (lane < 5) {
+            const double* g = sG[wid][lane];
+            for (int k = 0; k < nwin; k++) acc = __dadd_rn(acc, g[k]);
+        }
+        const double a = __shfl_sync(0xffffffffu, acc, 0), b = __shfl_sync(0xffffffffu, acc, 1), c = __shfl_sync(0xffffffffu, acc, 2);
+        const double bb1 = __shfl_sync(0xffffffffu, acc, 3), bb2 = __shfl_sync(0xffffffffu, acc, 4);
         const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
         if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
         const double scale = __ddiv_rn(1.0, det);
@@ -508,7 +531,7 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_kernel(const uint8_t* 
         if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) break;
     } while (++iter < maxIters && err > eps);
     if (fabsf(__fsub_rn(cIx, cTx)) > winW || fabsf(__fsub_rn(cIy, cTy)) > winH) { cIx = cTx; cIy = cTy; }
-    P[0] = cIx; P[1] = cIy;
+    if (lane == 0) { P[0] = cIx; P[1] = cIy; }
 }
 
 __global__ void bird_kps_to_pts_kernel(const orbb200_kp_t* __restrict__ kps, float* __restrict__ pts, int kpPerImg, const int32_t* __restrict__ counts,
@@ -846,7 +869,7 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
     double eps = std::max(epsilon, 0.);
     eps *= eps;
     const BirdLevel& L0 = g.lv[0];
-    bird_subpix_kernel<<<dim3((g.kpPerImg + SP_THREADS - 1) / SP_THREADS, n), SP_THREADS, 0, c.stream>>>(
+    bird_subpix_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
         p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
