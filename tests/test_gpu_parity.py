@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import GOLDEN, oracle, synth
+from helpers import GOLDEN, KP_DTYPE, oracle, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -607,3 +607,52 @@ def test_bird_retain_best_ties(pkg):
     a = pkg.BirdviewORB(ctx, 300).detect(img, None)
     b = oracle.bird_detect(img, None, 300)
     assert _same_kps(a, b) and len(b) > 100
+
+
+def test_bird_edge_cases(pkg):
+    """No corners, everything masked, images too small for the 31-pixel edge threshold, strided input, empty inputs."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    B = pkg.BirdviewORB(ctx, 500)
+    flat = np.full((200, 200), 128, np.uint8)
+    k, d = B(flat, None)
+    assert len(k) == 0 and d.shape == (0, 32)
+    img, mask = cases.birdview_case(200, 31)
+    k, d = B(img, np.zeros_like(mask))
+    assert len(k) == 0
+    small = synth.synth_frame(60, 60, 5)                       # <= 2 * edgeThreshold: runByImageBorder clears every level
+    assert len(B.detect(small, None)) == 0 and len(oracle.bird_detect(small, None, 500)) == 0
+    med = synth.synth_frame(90, 110, 6)                        # only the first levels are wider than 62 pixels
+    a, b = B.detect(med, None), oracle.bird_detect(med, None, 500)
+    assert _same_kps(a, b) and len(b) > 0
+    k, d = B(med, None)
+    k0, d0 = oracle.bird_extract(med, None, 500)
+    assert _same_kps(k, k0) and np.array_equal(d, d0)
+    big = np.zeros((200, 260), np.uint8)                       # row stride != width
+    big[:, :200] = img
+    k, d = B(big[:, :200], mask)
+    k0, d0 = oracle.bird_extract(img, mask, 500)
+    assert _same_kps(k, k0) and np.array_equal(d, d0)
+    assert len(B.cornerSubPix(img, np.zeros((0, 2), np.float32))) == 0
+    k, d = B.compute(img, np.zeros(0, KP_DTYPE))
+    assert len(k) == 0
+    with pytest.raises(pkg.OrbB200Error):
+        B.cornerSubPix(img, [[50, 50]], (9, 9))                # window half-size beyond the supported 7
+
+
+def test_frustum_empty_and_degenerate(pkg):
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    kps, desc, _, _ = cases.frame_case(500, 640, 480, 5)
+    pose, mp = cases.local_map_case(kps, desc, 640, 480, 64, 6)
+    M = pkg.LocalMap(ctx, mp["pos"][:0], mp["normal"][:0], mp["max_distance"][:0], mp["min_distance"][:0], mp["desc"][:0])
+    k, iv, *_ = M.isInFrustum(pkg.CameraPose.make(**pose))
+    assert k == 0 and len(iv) == 0
+    # points at the camera centre, on the image border, zero distance bounds
+    pos = mp["pos"].copy()
+    pos[0] = pose["Ow"]
+    mx, mn = mp["max_distance"].copy(), mp["min_distance"].copy()
+    mx[1], mn[1] = 0.0, 0.0
+    M = pkg.LocalMap(ctx, pos, mp["normal"], mx, mn, mp["desc"])
+    k, iv, u, v, uR, lvl, vc = M.isInFrustum(pkg.CameraPose.make(**pose))
+    k0, iv0, u0, v0, uR0, lvl0, vc0 = oracle.is_in_frustum(pos, mp["normal"], mx, mn, oracle.camera_pose(**pose))
+    assert k == k0 and np.array_equal(iv, iv0) and np.array_equal(lvl, lvl0)
+    assert np.array_equal(u.view(np.uint32), u0.view(np.uint32)) and np.array_equal(vc.view(np.uint32), vc0.view(np.uint32))
