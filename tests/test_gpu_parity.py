@@ -314,6 +314,32 @@ def test_cpp_shim(pkg, tmp_path):
     assert np.array_equal(lvl1, orc.level_image(1))          # mvImagePyramid[1]
 
 
+def test_cpp_birdview_shim(pkg, tmp_path):
+    """cpp/BirdviewExtractor.h called like the birdview block of Frame::Frame (src/Frame.cc:328-342) == oracle."""
+    import subprocess
+    from helpers import ROOT
+    drv = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp", "shim_driver")
+    subprocess.run(["make", "-s", "-C", os.path.dirname(drv)], check=True)
+    img = synth.synth_frame(240, 320, 77)
+    bimg, bmask = cases.birdview_case(400, 3101)
+    raw, braw, mraw, out = tmp_path / "in.raw", tmp_path / "b.raw", tmp_path / "m.raw", tmp_path / "out.bin"
+    img.tofile(raw)
+    bimg.tofile(braw)
+    bmask.tofile(mraw)
+    subprocess.run([drv, str(raw), "320", "240", "500", "20", "7", str(out), str(braw), str(mraw), "400", "400"], check=True, timeout=120)
+    buf = open(out, "rb").read()
+    n = int(np.frombuffer(buf, np.int32, 1)[0])
+    off = 4 + 60 * n
+    pw, ph = np.frombuffer(buf, np.int32, 2, off)
+    off += 8 + int(pw) * int(ph)
+    nb = int(np.frombuffer(buf, np.int32, 1, off)[0])
+    k = np.frombuffer(buf, pkg.KP_DTYPE, nb, off + 4)
+    d = np.frombuffer(buf, np.uint8, nb * 32, off + 4 + 28 * nb).reshape(nb, 32)
+    same = int(np.frombuffer(buf, np.int32, 1, off + 4 + 60 * nb)[0])
+    k0, d0 = oracle.bird_extract(bimg, bmask, 2000)
+    assert _same_kps(k, k0) and np.array_equal(d, d0) and same == 1
+
+
 def test_search_for_initialization(pkg):
     ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
     (k1, d1), (k2, d2), grid = cases.bird_pair(2000, 600, 71, shift=(5, -4), max_flips=12)
