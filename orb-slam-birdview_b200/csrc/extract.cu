@@ -310,9 +310,9 @@ __device__ __forceinline__ uint32_t fast_score_pair(uint32_t c, const uint32_t (
 
 // The 16 ring pairs around the pixel pair whose centre word is t[0] (tile pitch FT_PITCH).
 // ring order k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+template <int P>
 __device__ __forceinline__ void fast_load_ring(const uint32_t* t, uint32_t (&r)[16])
 {
-    constexpr int P = FT_PITCH;
     {
         const uint32_t* p = t + 3 * P;                          // dy = +3 : dx -1,0,1
         const uint32_t wl = p[-1], wc = p[0], wr = p[1];
@@ -341,9 +341,9 @@ __device__ __forceinline__ void fast_load_ring(const uint32_t* t, uint32_t (&r)[
 // min(p_k, p_k+8) < v - thr.  Tested on the three opposite pairs whose words are aligned with the centre
 // word (k = 0, 2, 6: no funnel shifts): 7 loads + ~13 ALU ops instead of the ~130-instruction network.
 // Tp = (thr + 1) in both lanes.  Returns non-zero when a pixel of the pair may reach thr.
+template <int P>
 __device__ __forceinline__ uint32_t fast_may_pass(const uint32_t* t, uint32_t Tp)
 {
-    constexpr int P = FT_PITCH;
     const uint32_t c = t[0];
     const uint32_t r0 = t[3 * P], r8 = t[-3 * P];
     const uint32_t r2 = t[2 * P + 1], r10 = t[-2 * P - 1];
@@ -368,6 +368,7 @@ __device__ __forceinline__ int seg_list_at(const uint16_t* list, int seg, const 
     return list[w * seg + j];
 }
 
+template <int P>
 __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
                                                                    int minTh, int iniTh, const int4* __restrict__ cells,
                                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
@@ -379,8 +380,8 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     // Shared memory is sized by the host for the largest cell of this image shape (typically ~19 KB).
     extern __shared__ uint32_t ftSmem[];
     uint32_t* tile = ftSmem;
-    uint32_t* scr = tile + tileWords;
-    uint32_t* clist = scr + scrWords;
+    uint32_t* scr = tile + tileWords * P;
+    uint32_t* clist = scr + scrWords * P;
     uint16_t* wlist = reinterpret_cast<uint16_t*>(clist + clistCap);    // pairs that may hold a local maximum
     uint16_t* qlist = wlist + workCap;                                  // pairs that pass the quick test
     __shared__ int sN, sBase, sQn[FT_WARPS], sWn[FT_WARPS];
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     const int nw = (tw + 3) >> 2;                   // 32-bit words loaded per row
     // Row pitch of both shared tiles: 49 words.  With the usual 16-18 pairs per row the flattened
     // (row, pair) -> lane mapping then touches (almost) disjoint banks for the rows a warp spans, and a
-    // compile-time pitch turns every ring offset into an immediate.
-    constexpr int P = FT_PITCH;
+    // compile-time pitch turns every ring offset into an immediate.  (P = 25 for the usual <= 44-pixel cells: more
+    // 2-way conflicts between the rows a warp spans, half the shared memory -- measured faster.)
 
     // zero frame of the score tile: the rows above/below and the words left/right of the inner span
     for (int i = tid; i < P; i += FT_THREADS) { scr[i] = 0; scr[(hi + 1) * P + i] = 0; }
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
                 const int i = min(b + lane, cend - 1);                  // surplus lanes repeat the last pair
                 const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
                 const int m = m0 + (i - rr * npr);
-                const uint32_t hit = fast_may_pass(tile + (rr + 3) * P + m + 1, Tp);
+                const uint32_t hit = fast_may_pass<P>(tile + (rr + 3) * P + m + 1, Tp);
                 scr[(rr + 1) * P + m + 1] = 0;
                 const unsigned bal = __ballot_sync(0xffffffffu, hit != 0 && b + lane < cend);
                 if ((bal >> lane) & 1u) myq[cnt + __popc(bal & ltmask)] = (uint16_t)i;
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
                 const int m = m0 + (i - rr * npr);
                 const uint32_t* t = tile + (rr + 3) * P + m + 1;
                 uint32_t r[16];
-                fast_load_ring(t, r);
+                fast_load_ring<P>(t, r);
                 uint32_t s = fast_score_pair(t[0], r);
                 const int c = 2 * m;
                 if (c < cx0 || c >= cx1) s &= 0xffff0000u;              // pixels outside the inner rectangle score 0
@@ -1110,8 +1111,9 @@ void push_fast_cell(std::vector<int4>& cells, FastSmem& need, int x0, int y0, in
         // floor(i / d) == umulhi(i, 2^32 / d + 1) for the small i used; d == 1 is special-cased in the kernel
         cells.back().x = (int)(0xffffffffu / (uint32_t)nw + 1u);
         cells.back().y = (int)(0xffffffffu / (uint32_t)npr + 1u);
-        need.tileWords = std::max(need.tileWords, th * FT_PITCH);
-        need.scrWords = std::max(need.scrWords, (hi + 2) * FT_PITCH);
+        need.tileWords = std::max(need.tileWords, th);
+        need.scrWords = std::max(need.scrWords, hi + 2);
+        need.maxRowWords = std::max(need.maxRowWords, 2 * nw + 3);
         need.clistCap = std::max(need.clistCap, ((wi + 1) / 2) * ((hi + 1) / 2));
         need.workCap = std::max(need.workCap, ((hi * npr + 1) & ~1) + 128);   // per-warp list segments: total + slack
     }
@@ -1122,14 +1124,20 @@ void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned
 {
     if (nCells <= 0 || n <= 0) return;
     const size_t smem = need.bytes();
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    static thread_local size_t configured[2] = {0, 0};
+    const bool small = need.pitch() == FT_PITCH_SMALL;
+    if (smem > 48 * 1024 && smem > configured[small]) {
+        if (small) cudaFuncSetAttribute(fast_cells_kernel<FT_PITCH_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(fast_cells_kernel<FT_PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[small] = smem;
     }
     dim3 grid(nCells, n);
-    fast_cells_kernel<<<grid, FT_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_cells, d_cand, d_candCount,
-                                                           need.tileWords, need.scrWords, need.clistCap, need.workCap, passes);
+    if (small)
+        fast_cells_kernel<FT_PITCH_SMALL><<<grid, FT_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_cells, d_cand, d_candCount,
+                                                                               need.tileWords, need.scrWords, need.clistCap, need.workCap, passes);
+    else
+        fast_cells_kernel<FT_PITCH><<<grid, FT_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_cells, d_cand, d_candCount,
+                                                                         need.tileWords, need.scrWords, need.clistCap, need.workCap, passes);
     c.launches++;
 }
 

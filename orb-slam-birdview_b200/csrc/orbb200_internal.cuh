@@ -22,7 +22,8 @@ constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // src/ORBmatcher
 constexpr int PYR_MARGIN_X = 32;        // bytes of reflect-101 border stored left of each level row (>= 4 used)
 constexpr int PYR_MARGIN_Y = 4;         // border rows stored above/below each level (>= 3 used)
 constexpr int RS_ROWS = 32;             // output rows per resize tile (128 columns wide)
-constexpr int FT_PITCH = 49;            // u32 words per row of fast_cells_kernel's shared tiles (>= 2*ceil(68/4)+3 = 37)
+constexpr int FT_PITCH = 49;            // u32 words per row of fast_cells_kernel's shared tiles (>= 2*ceil(68/4)+3 = 37), general case
+constexpr int FT_PITCH_SMALL = 25;      // the same for shapes whose cell images are at most 44 pixels wide (2*11+3): half the shared memory
 
 // Geometry of one pyramid level for one image shape (host-computed, passed to kernels by value).
 struct LevelGeom {
@@ -73,8 +74,10 @@ struct Ctx;
 
 // Shared-memory carve of fast_cells_kernel for a set of cells (host-computed maxima).
 struct FastSmem {
-    int tileWords = 0, scrWords = 0, clistCap = 0, workCap = 0;
-    size_t bytes() const { return sizeof(uint32_t) * ((size_t)tileWords + scrWords + clistCap) + sizeof(uint16_t) * 2 * (size_t)workCap; }
+    int tileWords = 0, scrWords = 0, clistCap = 0, workCap = 0;   // tile/scr in rows (multiply by the pitch in use)
+    int maxRowWords = 0;                                           // widest cell row in words (2*nw+3): selects the tile pitch
+    int pitch() const { return maxRowWords <= FT_PITCH_SMALL ? FT_PITCH_SMALL : FT_PITCH; }
+    size_t bytes() const { return sizeof(uint32_t) * ((size_t)(tileWords + scrWords) * pitch() + clistCap) + sizeof(uint16_t) * 2 * (size_t)workCap; }
 };
 // Append one FAST cell (3 x int4) to a host cell table and grow `need`.  [x0,x1) x [y0,y1) is the cell image in level
 // coordinates (3-pixel FAST margin included); candidates are only emitted inside [ex0,ex1) x [ey0,ey1) (ex1 == 0: anywhere).
