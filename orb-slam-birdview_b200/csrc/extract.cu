@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
     // in cv::FAST's score buffer) -> 3x3 strict-greater NMS.
     // Work lists are kept as one segment per warp, filled with ballots (no atomics).
     const int total = hi * npr;
-    const int qseg = (total + FT_WARPS - 1) / FT_WARPS;                 // pairs per warp in the quick test
+    const int qseg2s = ((((hi + 1) >> 1) * npr) + FT_WARPS - 1) / FT_WARPS;   // quick-test items (two rows each) per warp
     const int wseg = ((total + FT_THREADS - 1) / FT_THREADS) * 32;      // upper bound of a warp's share of the score loop
     const unsigned ltmask = (1u << lane) - 1u;
     int nEmit = 0;
@@ -444,20 +444,32 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
         if (tid == 0) sN = 0;
         __syncthreads();                                                // tile loaded / previous pass done
 
-        // ---- quick test; also clears the pair's score word ----
+        // ---- quick test; also clears the pairs' score words.  An item is a pixel pair in two vertically adjacent rows:
+        //      one index computation, the second row's addresses are immediates ----
         {
-            const int cbeg = wid * qseg, cend = min(cbeg + qseg, total);
-            uint16_t* myq = qlist + cbeg;
+            const int total2 = ((hi + 1) >> 1) * npr;
+            const int qseg2 = (total2 + FT_WARPS - 1) / FT_WARPS;
+            const int cbeg = wid * qseg2, cend = min(cbeg + qseg2, total2);
+            uint16_t* myq = qlist + 2 * cbeg;
             int cnt = 0;
             for (int b = cbeg; b < cend; b += 32) {
-                const int i = min(b + lane, cend - 1);                  // surplus lanes repeat the last pair
-                const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
-                const int m = m0 + (i - rr * npr);
-                const uint32_t hit = fast_may_pass<P>(tile + (rr + 3) * P + m + 1, Tp);
-                scr[(rr + 1) * P + m + 1] = 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, hit != 0 && b + lane < cend);
-                if ((bal >> lane) & 1u) myq[cnt + __popc(bal & ltmask)] = (uint16_t)i;
-                cnt += __popc(bal);
+                const int i = min(b + lane, cend - 1);                  // surplus lanes repeat the last item
+                const int rp = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
+                const int m = m0 + (i - rp * npr);
+                const int rr = 2 * rp;
+                const uint32_t* t = tile + (rr + 3) * P + m + 1;
+                const uint32_t hit0 = fast_may_pass<P>(t, Tp);
+                const uint32_t hit1 = fast_may_pass<P>(t + P, Tp);      // row hi of an odd cell: reads stay inside shared memory, result unused
+                uint32_t* z = scr + (rr + 1) * P + m + 1;
+                z[0] = 0; z[P] = 0;                                     // (row hi + 1 is the zero frame row)
+                const bool live = b + lane < cend;
+                const unsigned bal0 = __ballot_sync(0xffffffffu, hit0 != 0 && live);
+                const unsigned bal1 = __ballot_sync(0xffffffffu, hit1 != 0 && live && rr + 1 < hi);
+                const int idx = rr * npr + (m - m0);
+                if ((bal0 >> lane) & 1u) myq[cnt + __popc(bal0 & ltmask)] = (uint16_t)idx;
+                cnt += __popc(bal0);
+                if ((bal1 >> lane) & 1u) myq[cnt + __popc(bal1 & ltmask)] = (uint16_t)(idx + npr);
+                cnt += __popc(bal1);
             }
             if (lane == 0) sQn[wid] = cnt;
         }
@@ -472,7 +484,7 @@ __global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_
             int cnt = 0;
             for (int b = wid * 32; b < nQ; b += FT_THREADS) {
                 const int j = min(b + lane, nQ - 1);
-                const int i = seg_list_at(qlist, qseg, nq, j);
+                const int i = seg_list_at(qlist, 2 * qseg2s, nq, j);
                 const int rr = npr == 1 ? i : (int)__umulhi((uint32_t)i, magicNpr);
                 const int m = m0 + (i - rr * npr);
                 const uint32_t* t = tile + (rr + 3) * P + m + 1;
