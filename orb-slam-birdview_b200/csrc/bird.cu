@@ -114,7 +114,9 @@ __global__ void bird_border_kernel(uint8_t* __restrict__ pyr, unsigned planeByte
 }
 
 // ---- KeyPointsFilter::retainBest (keypoint.cpp) = libstdc++ std::nth_element + std::partition, run literally by one
-//      thread on (response, payload) arrays in shared memory: the ORDER of the survivors is part of cv::ORB's output ----
+//      on (response, payload) arrays in shared memory: the ORDER of the survivors is part of cv::ORB's output.
+//      Sequential pieces (median of three, final insertion sort of <= 3 elements, the heap-select fallback) run on one
+//      thread; the partition steps, where the time goes, run on the whole CTA (below) ----
 struct RB {
     float* r; uint32_t* p;
     __device__ __forceinline__ void swp(int i, int j) { const float a = r[i]; r[i] = r[j]; r[j] = a; const uint32_t b = p[i]; p[i] = p[j]; p[j] = b; }
@@ -130,19 +132,6 @@ __device__ void rb_move_median_to_first(RB v, int result, int a, int b, int c)
     } else if (v.gt(a, c)) v.swp(result, a);
     else if (v.gt(b, c)) v.swp(result, c);
     else v.swp(result, b);
-}
-
-__device__ int rb_unguarded_partition(RB v, int first, int last, int pivot)
-{
-    const float pv = v.r[pivot];
-    while (true) {
-        while (v.r[first] > pv) ++first;
-        --last;
-        while (pv > v.r[last]) --last;
-        if (!(first < last)) return first;
-        v.swp(first, last);
-        ++first;
-    }
 }
 
 __device__ void rb_insertion_sort(RB v, int first, int last)
@@ -201,52 +190,123 @@ __device__ void rb_heap_select(RB v, int first, int middle, int last)
         }
 }
 
-__device__ int rb_retain_best(RB v, int n, int n_points)
+// ---- partition steps with the whole CTA: the control flow of std::nth_element stays sequential (and identical in
+//      every thread), but each partition step is done in parallel.  A Hoare partition swaps the k-th "left stopper"
+//      (ascending indices that do not belong left of the pivot) with the k-th "right stopper" (descending indices that
+//      do not belong right of it) while the former lies before the latter; the stoppers are a property of the
+//      untouched data, so two stream compactions give both lists, a count gives the number of swaps K, and the K
+//      disjoint swaps and the returned cut point follow -- the exact element order of the sequential code. ----
+constexpr int SEL_THREADS = 256;
+
+struct RBPar { float* r; uint32_t* p; uint16_t* A; uint16_t* B; int* sc; };   // sc: [SEL_THREADS / 32 + 4] ints of scratch
+
+// exclusive block scan of one int per thread (all threads call); total returned through sc
+__device__ __forceinline__ int rb_block_scan(int v, int* sc, int& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sc[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int t = lane < SEL_THREADS / 32 ? sc[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        if (lane < SEL_THREADS / 32) sc[lane] = t;
+    }
+    __syncthreads();
+    const int base = wid ? sc[wid - 1] : 0;
+    total = sc[SEL_THREADS / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+// ge == false: std::__unguarded_partition(lo, hi, pivot value pv) with comp = greater  -> cut
+// ge == true : std::partition(lo, hi, response >= pv)                                   -> first element of the false group
+__device__ int rb_partition_block(RBPar v, int lo, int hi, float pv, bool ge)
+{
+    const int tid = threadIdx.x;
+    const int len = hi - lo;
+    if (len <= 0) return lo;
+    const int chunk = (len + SEL_THREADS - 1) / SEL_THREADS;
+    const int b = min(lo + tid * chunk, hi), e = min(b + chunk, hi);
+    int cnt = 0;                                        // low 16 bits: left stoppers, high 16: right stoppers
+    for (int i = b; i < e; i++) {
+        const float x = v.r[i];
+        const bool isL = ge ? !(x >= pv) : !(x > pv);
+        const bool isR = ge ? (x >= pv) : !(pv > x);
+        cnt += (int)isL + ((int)isR << 16);
+    }
+    int total;
+    const int base = rb_block_scan(cnt, v.sc, total);
+    const int nL = total & 0xffff, nR = total >> 16;
+    int kL = base & 0xffff, kR = base >> 16;
+    for (int i = b; i < e; i++) {
+        const float x = v.r[i];
+        const bool isL = ge ? !(x >= pv) : !(x > pv);
+        const bool isR = ge ? (x >= pv) : !(pv > x);
+        if (isL) v.A[kL++] = (uint16_t)i;
+        if (isR) v.B[nR - 1 - kR++] = (uint16_t)i;      // descending
+    }
+    int* sK = v.sc + SEL_THREADS / 32;
+    if (tid == 0) *sK = 0;
+    __syncthreads();
+    const int m = min(nL, nR);
+    int local = 0;
+    for (int k = tid; k < m; k += SEL_THREADS) local += v.A[k] < v.B[k];
+    if (local) atomicAdd(sK, local);
+    __syncthreads();
+    const int K = *sK;
+    for (int k = tid; k < K; k += SEL_THREADS) {
+        const int i = v.A[k], j = v.B[k];
+        const float a = v.r[i]; v.r[i] = v.r[j]; v.r[j] = a;
+        const uint32_t q = v.p[i]; v.p[i] = v.p[j]; v.p[j] = q;
+    }
+    int cut;
+    if (ge) cut = lo + nR;
+    else {
+        const int lim = K ? (int)v.B[K - 1] : hi;
+        cut = (K < nL && (int)v.A[K] < lim) ? (int)v.A[K] : lim;
+    }
+    __syncthreads();
+    return cut;
+}
+
+// KeyPointsFilter::retainBest, all threads of the CTA call; returns the new count
+__device__ int rb_retain_best_block(RBPar v, int n, int n_points)
 {
     if (!(n_points >= 0 && n > n_points)) return n;
     if (n_points == 0) return 0;
-    // std::nth_element(begin, begin + n_points - 1, end, greater)
-    {
-        const int nth = n_points - 1;
-        int first = 0, last = n, depth = 0;
-        for (int k = n; k > 1; k >>= 1) depth++;
-        depth *= 2;
-        bool done = false;
-        while (last - first > 3) {
-            if (depth == 0) {
-                rb_heap_select(v, first, nth + 1, last);
-                v.swp(first, nth);
-                done = true;
-                break;
-            }
-            --depth;
-            const int mid = first + (last - first) / 2;
-            rb_move_median_to_first(v, first, first + 1, mid, last - 1);
-            const int cut = rb_unguarded_partition(v, first + 1, last, first);
-            if (cut <= nth) first = cut; else last = cut;
+    const int tid = threadIdx.x;
+    RB s{v.r, v.p};
+    const int nth = n_points - 1;
+    int first = 0, last = n, depth = 0;
+    for (int k = n; k > 1; k >>= 1) depth++;
+    depth *= 2;
+    bool done = false;
+    while (last - first > 3) {
+        if (depth == 0) {
+            if (tid == 0) { rb_heap_select(s, first, nth + 1, last); s.swp(first, nth); }
+            done = true;
+            break;
         }
-        if (!done) rb_insertion_sort(v, first, last);
+        --depth;
+        const int mid = first + (last - first) / 2;
+        if (tid == 0) rb_move_median_to_first(s, first, first + 1, mid, last - 1);
+        __syncthreads();
+        const int cut = rb_partition_block(v, first + 1, last, v.r[first], false);
+        if (cut <= nth) first = cut; else last = cut;
     }
-    const float amb = v.r[n_points - 1];
-    // std::partition(begin + n_points, end, response >= amb)
-    int first = n_points, last = n;
-    while (true) {
-        bool out = false;
-        while (true) {
-            if (first == last) { out = true; break; }
-            if (v.r[first] >= amb) ++first; else break;
-        }
-        if (out) break;
-        --last;
-        while (true) {
-            if (first == last) { out = true; break; }
-            if (!(v.r[last] >= amb)) --last; else break;
-        }
-        if (out) break;
-        v.swp(first, last);
-        ++first;
-    }
-    return first;
+    if (!done && tid == 0) rb_insertion_sort(s, first, last);
+    __syncthreads();
+    return rb_partition_block(v, n_points, n, v.r[n_points - 1], true);
 }
 
 // HarrisResponses (orb.cpp), blockSize 7, k 0.04
@@ -271,8 +331,6 @@ __device__ float bird_harris(const uint8_t* img, int pitch, int x0, int y0)
 
 // Per (image, level): FAST corners -> mask filter -> row-major order (cv::FAST's) -> retainBest(2 * quota) on the FAST
 // score -> Harris responses -> retainBest(quota) (orb.cpp computeKeyPoints).  Writes the level's survivors in order.
-constexpr int SEL_THREADS = 256;
-
 __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ mpyr,
                                                                   const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                                   float4* __restrict__ lvlKp, int32_t* __restrict__ lvlCount,
@@ -281,7 +339,9 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
     extern __shared__ uint32_t selSmem[];
     uint32_t* key = selSmem;                                              // [BV_SORT_CAP]
     float* resp = reinterpret_cast<float*>(selSmem + BV_SORT_CAP);        // [BV_SORT_CAP]
-    __shared__ int sCount;
+    uint16_t* stopA = reinterpret_cast<uint16_t*>(selSmem + 2 * BV_SORT_CAP);   // [BV_SORT_CAP] left stoppers of a partition step
+    uint16_t* stopB = stopA + BV_SORT_CAP;                                      // [BV_SORT_CAP] right stoppers
+    __shared__ int sCount, sScratch[SEL_THREADS / 32 + 4];
     const int level = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     const BirdLevel L = g.lv[level];
     int n = candCount[img * MAX_LEVELS + level];            // fast_cells_kernel's layout
@@ -326,16 +386,12 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
     n = sCount;
     for (int i = tid; i < n; i += SEL_THREADS) resp[i] = (float)(key[i] & 0xffu);
     __syncthreads();
-    RB v{resp, key};
-    if (tid == 0) sCount = rb_retain_best(v, n, 2 * L.quota);
-    __syncthreads();
-    n = sCount;
+    RBPar v{resp, key, stopA, stopB, sScratch};
+    n = rb_retain_best_block(v, n, 2 * L.quota);
     const uint8_t* I = pyr + (size_t)img * g.planeBytes + L.off;
     for (int i = tid; i < n; i += SEL_THREADS) resp[i] = bird_harris(I, L.pitch, (int)((key[i] >> 8) & 0xfff), (int)(key[i] >> 20));
     __syncthreads();
-    if (tid == 0) sCount = rb_retain_best(v, n, L.quota);
-    __syncthreads();
-    n = sCount;
+    n = rb_retain_best_block(v, n, L.quota);
     if (n > L.kpCap) {
         if (tid == 0) atomicExch(status, 4);
         n = L.kpCap;
@@ -822,7 +878,7 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, bool withMask)
     cudaMemsetAsync(p->d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
                       p->d_candCount, n);
-    const size_t smem = (size_t)BV_SORT_CAP * 8;
+    const size_t smem = (size_t)BV_SORT_CAP * 12;      // keys + responses + two u16 stopper lists
     static thread_local bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(bird_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
