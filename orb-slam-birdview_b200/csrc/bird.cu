@@ -590,6 +590,123 @@ __global__ void __launch_bounds__(SP_WARPS * 32) bird_subpix_kernel(const uint8_
     if (lane == 0) { P[0] = cIx; P[1] = cIy; }
 }
 
+// ---- the same sampler run by one thread (throughput form of cornerSubPix below) ----
+__device__ void bird_get_rect_sub_pix(const uint8_t* src, int src_step, int src_w, int src_h, float* dst, int win_w, int win_h,
+                                      float cx, float cy)
+{
+    const float centerx = __fsub_rn(cx, __fmul_rn((float)(win_w - 1), 0.5f));
+    const float centery = __fsub_rn(cy, __fmul_rn((float)(win_h - 1), 0.5f));
+    const int ipx = (int)floorf(centerx), ipy = (int)floorf(centery);
+    if (0 <= ipx && ipx + win_w < src_w && 0 <= ipy && ipy + win_h < src_h) {
+        float a = __fsub_rn(centerx, (float)ipx);
+        const float b = __fsub_rn(centery, (float)ipy);
+        a = fmaxf(a, 0.0001f);
+        const float b1 = __fsub_rn(1.f, b), b2 = b;
+        const float a12 = __fmul_rn(a, b1), a22 = __fmul_rn(a, b);
+        const float oma = __fsub_rn(1.f, a);
+        const double s = __ddiv_rn(__dsub_rn(1.0, (double)a), (double)a);
+        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w) {
+            float prev = __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, (float)p[0]), __fmul_rn(b2, (float)p[src_step])));
+            for (int j = 0; j < win_w; j++) {
+                const float t = __fadd_rn(__fmul_rn(a12, (float)p[j + 1]), __fmul_rn(a22, (float)p[j + 1 + src_step]));
+                dst[j] = __fadd_rn(prev, t);
+                prev = (float)__dmul_rn((double)t, s);
+            }
+        }
+        return;
+    }
+    const float a = __fsub_rn(centerx, (float)ipx), b = __fsub_rn(centery, (float)ipy);
+    const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
+    const float a11 = __fmul_rn(oma, omb), a12 = __fmul_rn(a, omb), a21 = __fmul_rn(oma, b), a22 = __fmul_rn(a, b);
+    const float b1 = omb, b2 = b;
+    auto tap4 = [&](const uint8_t* r0, const uint8_t* r1, int j) {
+        return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)r0[j], a11), __fmul_rn((float)r0[j + 1], a12)), __fmul_rn((float)r1[j], a21)),
+                         __fmul_rn((float)r1[j + 1], a22));
+    };
+    if (0 <= ipx && ipx < src_w - win_w && 0 <= ipy && ipy < src_h - win_h) {
+        const uint8_t* p = src + (ptrdiff_t)ipy * src_step + ipx;
+        for (int i = 0; i < win_h; i++, p += src_step, dst += win_w)
+            for (int j = 0; j < win_w; j++) dst[j] = tap4(p, p + src_step, j);
+        return;
+    }
+    // adjustRect
+    int rx, ry, rw, rh;
+    const uint8_t* p = src;
+    if (ipx >= 0) { p += ipx; rx = 0; } else { rx = -ipx; if (rx > win_w) rx = win_w; }
+    if (ipx < src_w - win_w) rw = win_w;
+    else { rw = src_w - ipx - 1; if (rw < 0) { p += rw; rw = 0; } }
+    if (ipy >= 0) { p += (ptrdiff_t)ipy * src_step; ry = 0; } else ry = -ipy;
+    if (ipy < src_h - win_h) rh = win_h;
+    else { rh = src_h - ipy - 1; if (rh < 0) { p += (ptrdiff_t)rh * src_step; rh = 0; } }
+    p -= rx;
+    for (int i = 0; i < win_h; i++, dst += win_w) {
+        const uint8_t* p2 = p + src_step;
+        if (i < ry || i >= rh) p2 -= src_step;
+        float s0 = __fadd_rn(__fmul_rn((float)p[rx], b1), __fmul_rn((float)p2[rx], b2));
+        for (int j = 0; j < rx; j++) dst[j] = s0;
+        s0 = __fadd_rn(__fmul_rn((float)p[rw], b1), __fmul_rn((float)p2[rw], b2));
+        for (int j = rw; j < win_w; j++) dst[j] = s0;
+        for (int j = rx; j < rw; j++) dst[j] = tap4(p, p2, j);
+        if (i < rh) p = p2;
+    }
+}
+
+// cornerSubPix with one thread per corner: 4x the latency of the warp form, twice its throughput once tens of
+// thousands of corners are in flight (measured at 64 images x 1850 corners: 2.9 ms vs 5.6 ms; eight lanes per corner:
+// 8.1 ms).  Used for batches; single images use the warp form.
+constexpr int SP_THREADS = 64;
+
+__global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
+                                                                 int rows, float* __restrict__ pts, size_t ptsPerImg,
+                                                                 const int32_t* __restrict__ counts, int nFixed, const float* __restrict__ winMask,
+                                                                 int winW, int winH, int maxIters, double eps)
+{
+    const int img = blockIdx.y;
+    const int i = blockIdx.x * SP_THREADS + threadIdx.x;
+    const int n = counts ? counts[img] : nFixed;
+    if (i >= n) return;
+    const uint8_t* src = imgs + (size_t)img * imgStrideBytes;
+    float* P = pts + (size_t)img * ptsPerImg * 2 + 2 * (size_t)i;
+    const int win_w = winW * 2 + 1, win_h = winH * 2 + 1, bw = win_w + 2;
+    float buf[(2 * BV_MAX_WIN + 3) * (2 * BV_MAX_WIN + 3)];
+    const float cTx = P[0], cTy = P[1];
+    float cIx = cTx, cIy = cTy;
+    int iter = 0;
+    double err = 0;
+    do {
+        double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
+        bird_get_rect_sub_pix(src, pitch, cols, rows, buf, win_w + 2, win_h + 2, cIx, cIy);
+        const float* subpix = buf + bw + 1;
+        for (int ii = 0, k = 0; ii < win_h; ii++, subpix += bw) {
+            const double py = (double)(ii - winH);
+            for (int j = 0; j < win_w; j++, k++) {
+                const double m = (double)winMask[k];
+                const double tgx = (double)__fsub_rn(subpix[j + 1], subpix[j - 1]);
+                const double tgy = (double)__fsub_rn(subpix[j + bw], subpix[j - bw]);
+                const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
+                const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
+                const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                const double px = (double)(j - winW);
+                a = __dadd_rn(a, gxx); b = __dadd_rn(b, gxy); c = __dadd_rn(c, gyy);
+                bb1 = __dadd_rn(bb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
+                bb2 = __dadd_rn(bb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
+            }
+        }
+        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = __ddiv_rn(1.0, det);
+        const float nx = (float)__dsub_rn(__dadd_rn((double)cIx, __dmul_rn(__dmul_rn(c, scale), bb1)), __dmul_rn(__dmul_rn(b, scale), bb2));
+        const float ny = (float)__dadd_rn(__dsub_rn((double)cIy, __dmul_rn(__dmul_rn(b, scale), bb1)), __dmul_rn(__dmul_rn(a, scale), bb2));
+        const float dx = __fsub_rn(nx, cIx), dy = __fsub_rn(ny, cIy);
+        err = (double)__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        cIx = nx; cIy = ny;
+        if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) break;
+    } while (++iter < maxIters && err > eps);
+    if (fabsf(__fsub_rn(cIx, cTx)) > winW || fabsf(__fsub_rn(cIy, cTy)) > winH) { cIx = cTx; cIy = cTy; }
+    P[0] = cIx; P[1] = cIy;
+}
+
 __global__ void bird_kps_to_pts_kernel(const orbb200_kp_t* __restrict__ kps, float* __restrict__ pts, int kpPerImg, const int32_t* __restrict__ counts,
                                        int toKps)
 {
@@ -925,8 +1042,12 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
     double eps = std::max(epsilon, 0.);
     eps *= eps;
     const BirdLevel& L0 = g.lv[0];
-    bird_subpix_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
-        p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
+    if (n >= 8)      // many corners in flight: the one-thread-per-corner form has the higher throughput
+        bird_subpix_thread_kernel<<<dim3((g.kpPerImg + SP_THREADS - 1) / SP_THREADS, n), SP_THREADS, 0, c.stream>>>(
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
+    else
+        bird_subpix_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;

@@ -622,6 +622,12 @@ def test_bird_corner_subpix_border_and_windows(pkg):
     for i in range(3):
         k0, d0 = oracle.bird_extract(imgs[i], masks[i], 1500)
         assert _same_kps(ks[i], k0) and np.array_equal(ds[i], d0)
+    # batches of >= 8 images refine the corners with the one-thread-per-corner kernel
+    imgs, masks = zip(*[cases.birdview_case(200, 700 + i, vehicle=(40, 60)) for i in range(9)])
+    ks, ds = pkg.BirdviewORB(ctx, 600).extract_batch(list(imgs), list(masks))
+    for i in range(9):
+        k0, d0 = oracle.bird_extract(imgs[i], masks[i], 600)
+        assert _same_kps(ks[i], k0) and np.array_equal(ds[i], d0)
 
 
 def test_bird_retain_best_ties(pkg):
