@@ -150,6 +150,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
         const LevelGeom &S = g.lv[l - 1], &D = g.lv[l];
         if (D.w <= 0 || D.h <= 0) continue;
         const double sx_ = (double)S.w / D.w, sy_ = (double)S.h / D.h;
+        const size_t xbase = xtab.size();
         for (int dx = 0; dx < D.w; dx++) {
             float fx = (float)((dx + 0.5) * sx_ - 0.5);
             int sx = cvFloorF(fx);
@@ -160,6 +161,12 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             const int a1 = std::min(std::max(cvRoundF(fx * 2048), -32768), 32767);
             xtab.push_back(make_int2(sx, (a0 & 0xffff) | (a1 << 16)));
         }
+        bool narrow = true;     // resize_kernel<NARROW>: groups of 4 output columns (x4 = 0, 4, ...) within an 8-byte source window
+        for (int x4 = 0; x4 < D.w; x4 += 4) {
+            const int first = xtab[xbase + x4].x, last = std::min(xtab[xbase + std::min(x4 + 3, D.w - 1)].x + 1, S.w - 1);
+            if (last - first > 7) narrow = false;
+        }
+        st.resizeNarrow[l] = narrow;
         for (int dy = 0; dy < D.h; dy++) {
             float fy = (float)((dy + 0.5) * sy_ - 0.5);
             int sy = cvFloorF(fy);

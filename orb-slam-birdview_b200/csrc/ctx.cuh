@@ -17,6 +17,7 @@ struct ShapeTables {
     int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1: {level, x0, y0, 0}, 128 x RS_ROWS pixels each
     int resizeTileBase[MAX_LEVELS + 1] = {0};
     int resizeTileCount[MAX_LEVELS] = {0};
+    bool resizeNarrow[MAX_LEVELS] = {false};  // taps of any 4 adjacent output columns span <= 8 source bytes (scale <= 2)
     int resizeSmemPitch[MAX_LEVELS] = {0}, resizeSmemRows[MAX_LEVELS] = {0};   // staged source window of a resize tile
     struct GraphExec { cudaGraphExec_t exec; long long launches; };
     std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count

@@ -48,8 +48,13 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 // at 1/1.2).  (Tried: a separable two-phase form -- every H row once into shared memory, then the vertical pass --
 // with fewer instructions per pixel: 0.44 -> 0.53 ms per step, slower.)
 // ---------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 128;                 // one CTA per 128 x RS_ROWS output tile; warp w owns rows [8w, 8w+8) of it
+#ifndef ORBB200_RS_THREADS
+#define ORBB200_RS_THREADS 128
+#endif
+constexpr int RS_THREADS = ORBB200_RS_THREADS;  // one CTA per 128 x RS_ROWS output tile; warp w owns RS_RPW consecutive rows of it
+constexpr int RS_RPW = RS_ROWS / (RS_THREADS / 32);
 
+template <bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
                                                             const int2* __restrict__ xtab, const int4* __restrict__ ytab,
                                                             const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows)
@@ -68,31 +73,65 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
     const int cx0 = __ldg(xtab + dst.xtabOff + x0).x & ~15;
     const int cx1 = min(__ldg(xtab + dst.xtabOff + xLast).x + 1, src.w - 1);
     const int nvec = (cx1 - cx0) / 16 + 1, nrows = ry1 - ry0 + 1;     // <= smemPitch/16, smemRows (host-sized)
-    for (int i = tid; i < nrows * nvec; i += RS_THREADS) {
-        const int r = i / nvec, k = i - r * nvec;
-        // rows are 128-byte pitched and start 32 bytes into the pitch: column multiples of 16 are 16-byte aligned
-        *reinterpret_cast<uint4*>(rsSmem + r * smemPitch + 16 * k) =
-            *reinterpret_cast<const uint4*>(S + (size_t)(ry0 + r) * src.pitch + cx0 + 16 * k);
+    {
+        // floor(i / nvec) by a 16-bit reciprocal: exact while i * nvec < 2^16 (i < 64 rows x 16 vectors)
+        const unsigned rcp = 65536u / (unsigned)nvec + 1u;
+        const uint8_t* Sw = S + (size_t)ry0 * src.pitch + cx0;
+        for (int i = tid; i < nrows * nvec; i += RS_THREADS) {
+            const int r = (int)(((unsigned)i * rcp) >> 16), k = i - r * nvec;
+            // rows are 128-byte pitched and start 32 bytes into the pitch: column multiples of 16 are 16-byte aligned
+            *reinterpret_cast<uint4*>(rsSmem + r * smemPitch + 16 * k) =
+                *reinterpret_cast<const uint4*>(Sw + (unsigned)(r * src.pitch + 16 * k));
+        }
     }
     __syncthreads();
+    // warp index through a shuffle: everything derived from it (output row, table entries, staged row bases) is
+    // warp-uniform for the compiler, so a staged byte is addressed as (uniform row base + per-lane column offset)
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int x4 = x0 + 4 * (tid & 31);
     if (x4 >= dst.w) return;
-    // column setup, once per thread: source offsets (relative to the staged window) and 11-bit coefficients
-    int sx[4], sx1[4], a0[4], a1[4];
+    // column setup, once per thread.  NARROW (scale <= 2: the taps of 4 adjacent output columns lie within 8 source
+    // bytes): one row address, three aligned word loads funnel-shifted to an 8-byte window that starts at the first
+    // tap, then per column one PRMT (both taps as bytes 0/1) and one IDP2A with the coefficient pair.
+    // General form: two byte loads and two multiplies per column.
+    const uint8_t* p0[4];
+    const uint8_t* p1[4];
+    int a0[4], a1[4];
+    uint32_t sel[4], cf[4];
+    const uint8_t* pw = rsSmem;
+    int sh = 0;
+    {
+        int sx0 = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int2 xt = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
-        sx[i] = xt.x - cx0; sx1[i] = min(xt.x + 1, src.w - 1) - cx0;
-        a0[i] = xt.y & 0xffff; a1[i] = xt.y >> 16;
+        for (int i = 0; i < 4; i++) {
+            const int2 xt = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
+            const int s0 = xt.x - cx0, s1 = min(xt.x + 1, src.w - 1) - cx0;
+            if (i == 0) sx0 = s0;
+            p0[i] = rsSmem + s0; p1[i] = rsSmem + s1;
+            a0[i] = xt.y & 0xffff; a1[i] = xt.y >> 16;
+            sel[i] = (uint32_t)((s0 - sx0) | ((s1 - sx0) << 4)) | 0x4400u;    // bytes 2,3 <- byte 4 (unused by IDP2A.LO)
+            cf[i] = (uint32_t)xt.y;                                           // a0 | a1 << 16
+        }
+        pw = rsSmem + (sx0 & ~3);
+        sh = (sx0 & 3) * 8;
     }
     auto hrow = [&](int sy, int (&h)[4]) {
-        const uint8_t* r = rsSmem + (sy - ry0) * smemPitch;
+        const int ro = (sy - ry0) * smemPitch;
+        if (NARROW) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(pw + ro);
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];                   // the staged pitch has >= 16 spare bytes
+            const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-        for (int i = 0; i < 4; i++) h[i] = (r[sx[i]] * a0[i] + r[sx1[i]] * a1[i]) >> 4;
+            for (int i = 0; i < 4; i++) h[i] = (int)(__dp2a_lo(cf[i], __byte_perm(W0, W1, sel[i]), 0u) >> 4);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) h[i] = (p0[i][ro] * a0[i] + p1[i][ro] * a1[i]) >> 4;
+        }
     };
     int ha[4], hb[4];
     int ia = -1, ib = -1;
-    const int yb = y0 + 8 * (tid >> 5), ye = min(yb + 8, dst.h);
+    const int yb = y0 + RS_RPW * wid, ye = min(yb + RS_RPW, dst.h);
+    uint8_t* Dp = D + (size_t)yb * dst.pitch + x4;
     for (int y = yb; y < ye; y++) {
         const int4 yt = __ldg(ytab + dst.ytabOff + y);                    // {sy0, sy1, b0, b1}: warp-uniform
         if (yt.x != ia) {
@@ -113,13 +152,14 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
             }
             ib = yt.y;
         }
-        uint32_t out = 0;
+        // (((b0*H0)>>16) + ((b1*H1)>>16) + 2) >> 2; the +2 rides on the first product as 2 << 16
+        uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int v = (((yt.z * ha[i]) >> 16) + ((yt.w * hb[i]) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 0xff) << (8 * i);
-        }
-        *reinterpret_cast<uint32_t*>(D + (size_t)y * dst.pitch + x4) = out;   // row padding absorbs the tail
+        for (int i = 0; i < 4; i++)
+            v[i] = ((uint32_t)(yt.z * ha[i] + 0x20000) >> 16) + ((uint32_t)(yt.w * hb[i]) >> 16) >> 2;   // <= 255
+        const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        *reinterpret_cast<uint32_t*>(Dp) = out;                           // row padding absorbs the tail
+        Dp += dst.pitch;
     }
 }
 
@@ -251,7 +291,13 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
 // S >= iniThFAST, or, when the cell has none, if S >= minThFAST.
 // Candidates are appended unordered to the level's pool: the octree only needs (x, y, response).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FT_THREADS = 96;
+#ifndef ORBB200_FT_THREADS
+#define ORBB200_FT_THREADS 64
+#endif
+#ifndef ORBB200_FT_MINBLK
+#define ORBB200_FT_MINBLK 10
+#endif
+constexpr int FT_THREADS = ORBB200_FT_THREADS;
 
 // (Tried: funnel shifts as two IMADs on the FMA pipe instead of one SHF on the ALU pipe -- slower, the kernel is then
 // issue-bound: 0.93 -> 0.96 ms per 128 images.)
@@ -374,7 +420,7 @@ __device__ __forceinline__ int seg_list_at(const uint16_t* list, int seg, const 
 }
 
 template <int P>
-__global__ void __launch_bounds__(FT_THREADS, 10) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
+__global__ void __launch_bounds__(FT_THREADS, ORBB200_FT_MINBLK) fast_cells_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
                                                                    int minTh, int iniTh, const int4* __restrict__ cells,
                                                                    uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
                                                                    int tileWords, int scrWords, int clistCap, int workCap, int passes)
@@ -1094,9 +1140,14 @@ void launch_pyramid(Ctx& c, int n)
         if (d.w <= 0 || d.h <= 0 || st.resizeTileCount[l] == 0) break;
         dim3 grid(st.resizeTileCount[l], n);
         const size_t smem = (size_t)st.resizeSmemPitch[l] * st.resizeSmemRows[l];
-        resize_kernel<<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                           st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
-                                                           st.resizeSmemPitch[l], st.resizeSmemRows[l]);
+        if (st.resizeNarrow[l])
+            resize_kernel<true><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
+                                                                     st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
+                                                                     st.resizeSmemPitch[l], st.resizeSmemRows[l]);
+        else
+            resize_kernel<false><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
+                                                                      st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
+                                                                      st.resizeSmemPitch[l], st.resizeSmemRows[l]);
         c.launches++;
     }
     border_kernel<<<dim3(g.nlevels * BD_CHUNKS, n), 128, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
