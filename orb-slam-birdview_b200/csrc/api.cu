@@ -201,8 +201,21 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             for (int x0 = 0; x0 < L.w; x0 += 128) btiles.push_back(make_int4(l, x0, y0, 0));
         if (l > 0)
             for (int y0 = 0; y0 < L.h; y0 += RS_ROWS)
-                for (int x0 = 0; x0 < L.w; x0 += 128) { rtiles.push_back(make_int4(l, x0, y0, 0)); st.resizeTileCount[l]++; }
-        st.resizeTileBase[l + 1] = (int)rtiles.size();
+                for (int x0 = 0; x0 < L.w; x0 += 128) {
+                    // {x0, y0, first staged source row, rows}, {first staged source column (16-aligned), 16-byte vectors per
+                    // row, 2^16 / vectors + 1, -}: the window of resize_kernel, so that its staging loads depend on one load
+                    const LevelGeom& Sg = g.lv[l - 1];
+                    const int4* yt = ytab.data() + L.ytabOff;
+                    const int2* xt = xtab.data() + L.xtabOff;
+                    const int yLast = std::min(y0 + RS_ROWS, L.h) - 1, xLast = std::min(x0 + 127, L.w - 1);
+                    const int ry0 = yt[y0].x, ry1 = yt[yLast].y;
+                    const int cx0 = xt[x0].x & ~15, cx1 = std::min(xt[xLast].x + 1, Sg.w - 1);
+                    const int nvec = (cx1 - cx0) / 16 + 1;
+                    rtiles.push_back(make_int4(x0, y0, ry0, ry1 - ry0 + 1));
+                    rtiles.push_back(make_int4(cx0, nvec, (int)(65536u / (unsigned)nvec + 1u), 0));
+                    st.resizeTileCount[l]++;
+                }
+        st.resizeTileBase[l + 1] = (int)rtiles.size() / 2;
         if (l > 0 && L.w > 0 && L.h > 0) {
             // shared-memory window of a 128 x RS_ROWS tile: source columns (16-byte aligned start) and rows it touches
             const LevelGeom& Sg = g.lv[l - 1];

@@ -54,28 +54,54 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 constexpr int RS_THREADS = ORBB200_RS_THREADS;  // one CTA per 128 x RS_ROWS output tile; warp w owns RS_RPW consecutive rows of it
 constexpr int RS_RPW = RS_ROWS / (RS_THREADS / 32);
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// prmt.b32 with a selector whose nibbles are all < 8 (no sign-replication mode): spares the "& 0x7777" __byte_perm adds
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 template <bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
                                                             const int2* __restrict__ xtab, const int4* __restrict__ ytab,
                                                             const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows)
 {
     // The source footprint of the tile is staged in shared memory with coalesced 16-byte loads, so the
-    // interpolation reads (two bytes per output column and source row) never wait on global memory.
+    // interpolation reads never wait on global memory.  Every table entry the CTA needs (tile window, the rows'
+    // vertical coefficients, the lane's four column entries) is requested before the staging loop, so that the
+    // dependent-load chain in front of the first output row is tile -> {window, coefficients} -> staged bytes.
     extern __shared__ __align__(16) uint8_t rsSmem[];
-    const int4 t = __ldg(tiles + blockIdx.x);       // {level, x0, y0, -}
+    __shared__ int4 sY[RS_ROWS];
+    const int4 t = __ldg(tiles + 2 * blockIdx.x);       // {x0, y0, first staged source row, rows}
+    const int4 u = __ldg(tiles + 2 * blockIdx.x + 1);   // {first staged source column, vectors per row, 2^16/vectors + 1, -}
     const int img = blockIdx.y;
-    const int x0 = t.y, y0 = t.z;
+    const int x0 = t.x, y0 = t.y, ry0 = t.z, nrows = t.w;              // rows <= smemRows, vectors <= smemPitch/16 (host-sized)
+    const int cx0 = u.x, nvec = u.y;
     const int tid = threadIdx.x;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + src.off;
     uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off;
-    const int yLast = min(y0 + RS_ROWS, dst.h) - 1, xLast = min(x0 + 127, dst.w - 1);
-    const int ry0 = __ldg(ytab + dst.ytabOff + y0).x, ry1 = __ldg(ytab + dst.ytabOff + yLast).y;
-    const int cx0 = __ldg(xtab + dst.xtabOff + x0).x & ~15;
-    const int cx1 = min(__ldg(xtab + dst.xtabOff + xLast).x + 1, src.w - 1);
-    const int nvec = (cx1 - cx0) / 16 + 1, nrows = ry1 - ry0 + 1;     // <= smemPitch/16, smemRows (host-sized)
+    const int x4 = x0 + 4 * (tid & 31);
+    int2 xt[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xt[i] = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
+    if (tid < RS_ROWS) sY[tid] = __ldg(ytab + dst.ytabOff + min(y0 + tid, dst.h - 1));
     {
         // floor(i / nvec) by a 16-bit reciprocal: exact while i * nvec < 2^16 (i < 64 rows x 16 vectors)
-        const unsigned rcp = 65536u / (unsigned)nvec + 1u;
+        const unsigned rcp = (unsigned)u.z;
         const uint8_t* Sw = S + (size_t)ry0 * src.pitch + cx0;
         for (int i = tid; i < nrows * nvec; i += RS_THREADS) {
             const int r = (int)(((unsigned)i * rcp) >> 16), k = i - r * nvec;
@@ -85,55 +111,44 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
         }
     }
     __syncthreads();
-    // warp index through a shuffle: everything derived from it (output row, table entries, staged row bases) is
-    // warp-uniform for the compiler, so a staged byte is addressed as (uniform row base + per-lane column offset)
+    // warp index through a shuffle: the output row and everything derived from it is warp-uniform for the compiler
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int x4 = x0 + 4 * (tid & 31);
     if (x4 >= dst.w) return;
     // column setup, once per thread.  NARROW (scale <= 2: the taps of 4 adjacent output columns lie within 8 source
     // bytes): one row address, three aligned word loads funnel-shifted to an 8-byte window that starts at the first
     // tap, then per column one PRMT (both taps as bytes 0/1) and one IDP2A with the coefficient pair.
-    // General form: two byte loads and two multiplies per column.
-    const uint8_t* p0[4];
-    const uint8_t* p1[4];
-    int a0[4], a1[4];
-    uint32_t sel[4], cf[4];
-    const uint8_t* pw = rsSmem;
-    int sh = 0;
-    {
-        int sx0 = 0;
+    // General form: two byte loads and two multiplies per column.  Shared memory is addressed through 32-bit
+    // shared-space addresses (one add per source row instead of a generic-pointer rebuild).
+    const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(rsSmem);
+    uint32_t o0[4], o1[4], sel[4], cf[4];
+    const int sx0 = xt[0].x - cx0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int2 xt = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
-            const int s0 = xt.x - cx0, s1 = min(xt.x + 1, src.w - 1) - cx0;
-            if (i == 0) sx0 = s0;
-            p0[i] = rsSmem + s0; p1[i] = rsSmem + s1;
-            a0[i] = xt.y & 0xffff; a1[i] = xt.y >> 16;
-            sel[i] = (uint32_t)((s0 - sx0) | ((s1 - sx0) << 4)) | 0x4400u;    // bytes 2,3 <- byte 4 (unused by IDP2A.LO)
-            cf[i] = (uint32_t)xt.y;                                           // a0 | a1 << 16
-        }
-        pw = rsSmem + (sx0 & ~3);
-        sh = (sx0 & 3) * 8;
+    for (int i = 0; i < 4; i++) {
+        const int s0 = xt[i].x - cx0, s1 = min(xt[i].x + 1, src.w - 1) - cx0;
+        o0[i] = smemBase + s0; o1[i] = smemBase + s1;
+        sel[i] = (uint32_t)((s0 - sx0) | ((s1 - sx0) << 4)) | 0x4400u;    // bytes 2,3 <- byte 4 (unused by IDP2A.LO)
+        cf[i] = (uint32_t)xt[i].y;                                        // a0 | a1 << 16
     }
-    auto hrow = [&](int sy, int (&h)[4]) {
-        const int ro = (sy - ry0) * smemPitch;
+    const uint32_t pw = smemBase + (sx0 & ~3);
+    const int sh = (sx0 & 3) * 8;
+    auto hrow = [&](int sy, uint32_t (&h)[4]) {
+        const uint32_t ro = (uint32_t)((sy - ry0) * smemPitch);
         if (NARROW) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(pw + ro);
-            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];                   // the staged pitch has >= 16 spare bytes
+            const uint32_t w0 = lds_u32(pw + ro), w1 = lds_u32(pw + ro + 4), w2 = lds_u32(pw + ro + 8);   // pitch has >= 16 spare bytes
             const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-            for (int i = 0; i < 4; i++) h[i] = (int)(__dp2a_lo(cf[i], __byte_perm(W0, W1, sel[i]), 0u) >> 4);
+            for (int i = 0; i < 4; i++) h[i] = __dp2a_lo(cf[i], prmt_raw(W0, W1, sel[i]), 0u) >> 4;
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) h[i] = (p0[i][ro] * a0[i] + p1[i][ro] * a1[i]) >> 4;
+            for (int i = 0; i < 4; i++) h[i] = (lds_u8(o0[i] + ro) * (cf[i] & 0xffffu) + lds_u8(o1[i] + ro) * (cf[i] >> 16)) >> 4;
         }
     };
-    int ha[4], hb[4];
+    uint32_t ha[4], hb[4];
     int ia = -1, ib = -1;
     const int yb = y0 + RS_RPW * wid, ye = min(yb + RS_RPW, dst.h);
-    uint8_t* Dp = D + (size_t)yb * dst.pitch + x4;
+    unsigned doff = (unsigned)(yb * dst.pitch + x4);
     for (int y = yb; y < ye; y++) {
-        const int4 yt = __ldg(ytab + dst.ytabOff + y);                    // {sy0, sy1, b0, b1}: warp-uniform
+        const int4 yt = sY[y - y0];                                       // {sy0, sy1, b0, b1}: warp-uniform
         if (yt.x != ia) {
             if (yt.x == ib) {
 #pragma unroll
@@ -152,14 +167,14 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
             }
             ib = yt.y;
         }
-        // (((b0*H0)>>16) + ((b1*H1)>>16) + 2) >> 2; the +2 rides on the first product as 2 << 16
+        // (((b0*H0)>>16) + ((b1*H1)>>16) + 2) >> 2, the >>16 as the high word of (b << 16) * H
+        const uint32_t bz = (uint32_t)yt.z << 16, bw = (uint32_t)yt.w << 16;
         uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            v[i] = ((uint32_t)(yt.z * ha[i] + 0x20000) >> 16) + ((uint32_t)(yt.w * hb[i]) >> 16) >> 2;   // <= 255
+        for (int i = 0; i < 4; i++) v[i] = (__umulhi(bz, ha[i]) + __umulhi(bw, hb[i]) + 2u) >> 2;     // <= 255
         const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-        *reinterpret_cast<uint32_t*>(Dp) = out;                           // row padding absorbs the tail
-        Dp += dst.pitch;
+        *reinterpret_cast<uint32_t*>(D + doff) = out;                     // row padding absorbs the tail
+        doff += (unsigned)dst.pitch;
     }
 }
 
@@ -1142,11 +1157,11 @@ void launch_pyramid(Ctx& c, int n)
         const size_t smem = (size_t)st.resizeSmemPitch[l] * st.resizeSmemRows[l];
         if (st.resizeNarrow[l])
             resize_kernel<true><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                                     st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
+                                                                     st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
                                                                      st.resizeSmemPitch[l], st.resizeSmemRows[l]);
         else
             resize_kernel<false><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                                      st.d_resizeTiles + st.resizeTileBase[l], st.resizeTileCount[l],
+                                                                      st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
                                                                       st.resizeSmemPitch[l], st.resizeSmemRows[l]);
         c.launches++;
     }
