@@ -357,9 +357,46 @@ def dist_setup(args):
     return rank, world, local, dist
 
 
+def bind_near_gpu(device, enable=True):
+    """Pin this process (and the threads / pinned host allocations it makes afterwards) to the CPUs NVML reports as
+    closest to the GPU, so that each rank's staging buffers live on the NUMA node its GPU's PCIe root hangs off.
+    Returns a small description for the JSON line."""
+    info = {"enabled": bool(enable), "cpus_before": len(os.sched_getaffinity(0))}
+    if not enable:
+        return info
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        try:
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+        except Exception:
+            pass
+        h = None
+        if uuid:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(hh)
+                if (u.decode() if isinstance(u, bytes) else u) == uuid:
+                    h = hh
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        before = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus = (ideal & before) or before          # stay inside the container's cpuset
+        os.sched_setaffinity(0, cpus)
+        info.update({"cpus_after": len(cpus), "first_cpu": min(cpus), "last_cpu": max(cpus)})
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
 def run_ours(args):
     import torch
     rank, world, local, dist = dist_setup(args)
+    host_bind = bind_near_gpu(local, not args.no_numa_bind)
     B, P = args.frames_per_step, args.pools
     NE = max(2, args.e2e_contexts)
     arm = GpuArm(local, B, P, n_ctx=NE)
@@ -445,10 +482,28 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # host->device copy rate with every rank copying at the same time (pinned, one stream each): what the host side
+    # (PCIe switches, NUMA placement of the staging buffers) gives N GPUs together; the floor under the host-buffer leg
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    arm.d_imgs[0].copy_(arm.h_imgs[0], non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    ce0.record()
+    for _ in range(4):
+        arm.d_imgs[0].copy_(arm.h_imgs[0], non_blocking=True)
+    ce1.record()
+    torch.cuda.synchronize()
+    h2d_conc = 4 * arm.h_imgs[0].numel() / (ce0.elapsed_time(ce1) * 1e-3) / 1e9
+    h2d_conc_min, h2d_conc_sum = h2d_conc, h2d_conc
+    barrier()
+
     if dist is not None:
-        t = torch.tensor([ms, e2e_s * 1e3], device=f"cuda:{local}", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s * 1e3, -h2d_conc], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, h2d_conc_min = float(t[0]), float(t[1]), -float(t[2])
+        t2 = torch.tensor([h2d_conc], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        h2d_conc_sum = float(t2[0])
     else:
         e2e_ms = e2e_s * 1e3
     if rank != 0:
@@ -521,7 +576,8 @@ def run_ours(args):
                    "l2": f"{P} rotating input batches of {2 * B} images + {2 * B}-image pyramid/blur pools: working set "
                          f"{working_set_mb(B, P):.0f} MB per GPU > 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": arm.h2d_bytes(), "d2h_bytes_per_step": arm.d2h_bytes(),
-                "ms_per_step": e2e_ms / K, "contexts_in_flight": NE, "h2d_copy_gbs_measured": h2d_gbs},
+                "ms_per_step": e2e_ms / K, "contexts_in_flight": NE, "h2d_copy_gbs_measured": h2d_gbs,
+                "h2d_copy_gbs_all_ranks_at_once": {"min_rank": h2d_conc_min, "sum": h2d_conc_sum}, "host_binding": host_bind},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -572,9 +628,72 @@ def cpu_baseline(arm, args, target_s=15.0):
         dt, _ = cpu.run(imgs, q, frames)
         return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
                 "sample": f"{n} stereo frames of the same workload on {cores} host threads ({dt:.1f} s); 1 thread: {1.0 / t1:.2f} frames/s",
-                "single_thread_value": 1.0 / t1, "native_build": cpu.native}
+                "single_thread_value": 1.0 / t1, "native_build": cpu.native,
+                "cv2_crosscheck": cv2_primitive_times(imgs[0], 1e3 * t1 / 2)}
     except Exception as e:   # the baseline is reported, never required for the GPU number
         return {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+
+
+def cv2_primitive_times(img, oracle_ms_per_image):
+    """SURVEY.md 8(d) cross-check of the scalar oracle port against OpenCV's own SIMD builds of the three stencil
+    stages (cv2.resize, per-cell cv2.FAST with the 20/7 fallback, cv2.GaussianBlur), one thread, one image.  The
+    per-cell FAST calls are made from Python, so the cost of the same number of calls on a 7x7 cell (no interior pixel
+    to test) is measured and subtracted.  Octree, orientation and descriptors have no cv2 counterpart and are not in
+    this sum, so it is a LOWER bound of an OpenCV-based CPU extraction; reported next to the oracle's time per image."""
+    try:
+        import cv2
+        import numpy as np
+    except Exception as e:
+        return {"available": False, "why": repr(e)}
+    cv2.setNumThreads(1)
+    f20, f7 = cv2.FastFeatureDetector_create(20, True), cv2.FastFeatureDetector_create(7, True)
+    tiny = np.zeros((7, 7), np.uint8)
+
+    def once():
+        t0 = time.perf_counter()
+        levels, scale = [img], np.float32(1.0)
+        for _ in range(1, 8):
+            scale = np.float32(scale * np.float32(1.2))
+            inv = np.float32(1.0) / scale
+            w, h = int(round(float(np.float32(img.shape[1]) * inv))), int(round(float(np.float32(img.shape[0]) * inv)))
+            levels.append(cv2.resize(levels[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+        t1 = time.perf_counter()
+        calls = 0
+        for L in levels:
+            h, w = L.shape
+            W_, H_ = w - 32, h - 32
+            nc, nr = W_ // 30, H_ // 30
+            wc, hc = -(-W_ // nc), -(-H_ // nr)
+            for i in range(nr):
+                y0 = 16 + i * hc
+                if y0 >= h - 16 - 3:
+                    continue
+                y1 = min(y0 + hc + 6, h - 16)
+                for j in range(nc):
+                    x0 = 16 + j * wc
+                    if x0 >= w - 16 - 6:
+                        continue
+                    c = L[y0:y1, x0:min(x0 + wc + 6, w - 16)]
+                    calls += 1
+                    if not f20.detect(c):
+                        f7.detect(c)
+                        calls += 1
+        t2 = time.perf_counter()
+        for L in levels:
+            cv2.GaussianBlur(L, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        for _ in range(calls):
+            f20.detect(tiny)
+        t4 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3
+
+    once()
+    r = min((once() for _ in range(3)), key=lambda x: x[1])
+    stencil = r[0] + max(r[1] - r[3], 0.0) + r[2]
+    return {"available": True, "version": cv2.__version__, "threads": 1, "resize_ms": round(r[0], 3), "fast_cells_ms": round(r[1], 3),
+            "fast_call_overhead_ms": round(r[3], 3), "blur_ms": round(r[2], 3), "stencil_stages_ms_per_image": round(stencil, 3),
+            "oracle_ms_per_image_all_stages": round(oracle_ms_per_image, 3),
+            "note": "cv2 covers pyramid + FAST + blur only (no octree / orientation / descriptors / matching)"}
 
 
 def run_reference(args):
@@ -629,6 +748,7 @@ def main():
     ap.add_argument("--stage-timing-in-region", action="store_true",
                     help="record the per-stage events inside the timed region (plain launches, no graph replay, blur not forked: ~2.5 %% slower); "
                          "default: the timed region replays the captured graph and a second pass of the same K steps times the stages")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the CPUs nearest its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -92,6 +92,17 @@ int orbb200_hamming_knn2(orbb200_ctx* ctx, const uint8_t* q, int nq, const uint8
 int orbb200_hamming_knn2_device(orbb200_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm,
                                 int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
 
+/* ---- representative descriptor of a landmark -----------------------------------------------------
+ * The selection step of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301) and
+ * MapPointBird::ComputeDistinctiveDescriptors (src/MapPointBird.cc:117-146), batched over landmarks: group g is the
+ * descriptors desc[group_ptr[g] .. group_ptr[g+1]) of one landmark's observations (in the order the reference
+ * pushes them: std::map<KeyFrame*,size_t> iteration order, for MapPointBird preceded by its own descriptor when it
+ * has no reference keyframe).  Per group: all pairwise DescriptorDistance, per row the element [0.5*(N-1)] of the
+ * sorted row (self distance 0 included), best_idx = FIRST row with the smallest median, best_median = that value;
+ * -1 / -1 for an empty group (the reference returns without touching mDescriptor). */
+int orbb200_distinctive_descriptors(orbb200_ctx* ctx, const uint8_t* desc, const int32_t* group_ptr, int n_groups,
+                                    int32_t* best_idx, int32_t* best_median);
+
 /* ---- frames: keypoints + descriptors + 64x48 lookup grid on the device ---------------------------
  * Replaces Frame::AssignFeaturesToGrid / PosInGrid[Birdview] (src/Frame.cc:378-412,549-559,879-889) and is
  * what Frame::GetFeaturesInArea[Birdview] (src/Frame.cc:494-547,891-944) scans.  Front camera:

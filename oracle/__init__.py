@@ -63,6 +63,7 @@ def lib(native=False):
         "oracle_distribute_octree": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
         "oracle_descriptor_distance": (C.c_int, [vp, vp]),
         "oracle_hamming_knn2": (None, [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
+        "oracle_distinctive_descriptors": (None, [vp, vp, C.c_int, vp, vp]),
         "oracle_frame_create": (vp, [vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
         "oracle_frame_destroy": (None, [vp]),
         "oracle_frame_features_in_area": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]),
@@ -227,6 +228,16 @@ def hamming_knn2(q, m, native=False):
     bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
     lib(native).oracle_hamming_knn2(_p(q), nq, _p(m), nm, _p(bi), _p(bd), _p(sd))
     return bi, bd, sd
+
+
+def distinctive_descriptors(desc, group_ptr, native=False):
+    """MapPoint[Bird]::ComputeDistinctiveDescriptors selection (src/MapPoint.cc:272-301, src/MapPointBird.cc:117-146)
+    -> (best index inside each group or -1, its median distance)"""
+    desc, group_ptr = _c(desc, np.uint8), _c(group_ptr, np.int32)
+    ng = len(group_ptr) - 1
+    bi, bm = np.empty(ng, np.int32), np.empty(ng, np.int32)
+    lib(native).oracle_distinctive_descriptors(_p(desc), _p(group_ptr), ng, _p(bi), _p(bm))
+    return bi, bm
 
 
 class Frame:

@@ -7,6 +7,7 @@
  */
 #include "orb_oracle.h"
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -787,6 +788,30 @@ int oracle_is_in_frustum(int n, const float* pos, const float* normal, const flo
         nToMatch++;
     }
     return nToMatch;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) and MapPointBird::ComputeDistinctiveDescriptors
+// (src/MapPointBird.cc:87-152), the selection step: for every landmark the descriptors of its observations form one
+// group (CSR `group_ptr`); Distances[i][j] = DescriptorDistance, Distances[i][i] = 0; per row the sorted distances'
+// element [0.5*(N-1)] is the median; the FIRST row with the strictly smallest median wins (:288-301).
+void oracle_distinctive_descriptors(const uint8_t* desc, const int32_t* group_ptr, int n_groups,
+                                    int32_t* best_idx, int32_t* best_median)
+{
+    std::vector<int> row;
+    for (int g = 0; g < n_groups; g++) {
+        const int b = group_ptr[g], N = group_ptr[g + 1] - b;
+        best_idx[g] = -1; best_median[g] = -1;
+        if (N <= 0) continue;                                   // observations.empty() / vDescriptors.empty(): nothing chosen
+        int BestMedian = INT32_MAX, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            row.assign(N, 0);
+            for (int j = 0; j < N; j++) row[j] = i == j ? 0 : DescriptorDistance(desc + (size_t)(b + i) * 32, desc + (size_t)(b + j) * 32);
+            std::sort(row.begin(), row.end());
+            const int median = row[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_idx[g] = BestIdx; best_median[g] = BestMedian;
+    }
 }
 
 }  // extern "C"

@@ -74,6 +74,8 @@ int oracle_distribute_octree(const int32_t* xyr, int n, int minX, int maxX, int 
 /* ---- ORBmatcher / Frame grid ------------------------------------------------------------------- */
 int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b);
 /* brute force best / second best (strict '<': first minimum in scan order wins) */
+void oracle_distinctive_descriptors(const uint8_t* desc, const int32_t* group_ptr, int n_groups,
+                                    int32_t* best_idx, int32_t* best_median);
 void oracle_hamming_knn2(const uint8_t* q, int nq, const uint8_t* m, int nm,
                          int32_t* best_idx, int32_t* best_d, int32_t* second_d);
 

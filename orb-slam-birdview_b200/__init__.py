@@ -59,6 +59,7 @@ _SIGNATURES = {
     "orbb200_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "orbb200_level_candidates": (_i, [_vp, _i, _i, _vp, _i]),
     "orbb200_hamming_knn2": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "orbb200_distinctive_descriptors": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "orbb200_hamming_knn2_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbb200_measure_popc_peak": (C.c_double, [_vp]),
     "orbb200_frame_upload": (_i, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _i, _f, _f, _f, _f]),
@@ -486,6 +487,18 @@ class ORBmatcher:
         bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
         self.ctx.check(self._L.orbb200_hamming_knn2(self.ctx._h, _p(q), nq, _p(m), nm, _p(bi), _p(bd), _p(sd)), "hamming_knn2")
         return bi, bd, sd
+
+    def ComputeDistinctiveDescriptors(self, desc, group_ptr):
+        """Selection step of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301) and
+        MapPointBird::ComputeDistinctiveDescriptors (src/MapPointBird.cc:117-146) for many landmarks at once:
+        descriptors of landmark g's observations are desc[group_ptr[g]:group_ptr[g+1]]
+        -> (best index inside each group or -1, its median distance)"""
+        desc, group_ptr = _c(desc, np.uint8), _c(group_ptr, np.int32)
+        ng = len(group_ptr) - 1
+        bi, bm = np.empty(max(ng, 0), np.int32), np.empty(max(ng, 0), np.int32)
+        self.ctx.check(self._L.orbb200_distinctive_descriptors(self.ctx._h, _p(desc), _p(group_ptr), ng, _p(bi), _p(bm)),
+                       "distinctive_descriptors")
+        return bi, bm
 
     def SearchByProjection(self, F, q_valid, q_u, q_v, q_uR, q_level, q_viewcos, q_desc, q_obs_pos=None, kp_blocked=None, th=1.0):
         """SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129)

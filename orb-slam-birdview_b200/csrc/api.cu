@@ -676,6 +676,34 @@ int orbb200_hamming_knn2(orbb200_ctx* ctx, const uint8_t* q, int nq, const uint8
     return ORBB200_OK;
 }
 
+int orbb200_distinctive_descriptors(orbb200_ctx* ctx, const uint8_t* desc, const int32_t* group_ptr, int n_groups,
+                                    int32_t* best_idx, int32_t* best_median)
+{
+    CTX_ENTER(ctx);
+    if (n_groups <= 0) return ORBB200_OK;
+    if (!group_ptr || !best_idx || !best_median) { c.err = "distinctive_descriptors: bad argument"; return ORBB200_ERR_ARG; }
+    const int total = group_ptr[n_groups];
+    if (group_ptr[0] != 0 || total < 0 || (total > 0 && !desc)) { c.err = "distinctive_descriptors: bad group_ptr"; return ORBB200_ERR_ARG; }
+    for (int g = 0; g < n_groups; g++) {
+        const int n = group_ptr[g + 1] - group_ptr[g];
+        if (n < 0 || n >= (1 << 20)) { c.err = "distinctive_descriptors: group sizes must be in [0, 2^20)"; return ORBB200_ERR_ARG; }
+    }
+    const size_t dB = align_up((size_t)std::max(total, 1) * 32, 256), pB = align_up((size_t)(n_groups + 1) * 4, 256), oB = align_up((size_t)n_groups * 4, 256);
+    if (!ensure_scratch(c, dB + pB + 2 * oB + 4096, 0)) return ORBB200_ERR_CUDA;
+    uint8_t* dDesc = c.d_scratch;
+    int32_t* dPtr = reinterpret_cast<int32_t*>(dDesc + dB);
+    int32_t* dBi = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(dPtr) + pB);
+    int32_t* dBm = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(dBi) + oB);
+    if (total > 0) ORBB200_CUDA_OK(c, cudaMemcpyAsync(dDesc, desc, (size_t)total * 32, cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dPtr, group_ptr, (size_t)(n_groups + 1) * 4, cudaMemcpyHostToDevice, c.stream));
+    launch_distinctive(c, dDesc, dPtr, n_groups, dBi, dBm);
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(best_idx, dBi, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(best_median, dBm, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
 // POPC issue peak in G popc/s measured on this device (roofline denominator for matching)
 double orbb200_measure_popc_peak(orbb200_ctx* ctx)
 {

@@ -764,4 +764,79 @@ void launch_frustum(Ctx& c, const FrustumJob& J)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// MapPoint[Bird]::ComputeDistinctiveDescriptors selection (src/MapPoint.cc:272-301): one CTA per landmark, one warp
+// per row of the distance matrix.  The median of a row is a rank selection, not a sort: the row's distances (0..256)
+// are counted into a per-warp histogram in shared memory and the bin where the running count first exceeds
+// k = (int)(0.5*(N-1)) is the k-th smallest.  First row with the smallest median = lexicographic min of (median, row).
+// ---------------------------------------------------------------------------------------------------
+constexpr int DD_WARPS = 4;
+constexpr int DD_BINS = 288;      // 257 used; 9 bins per lane
+
+__global__ void __launch_bounds__(DD_WARPS * 32) distinctive_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ groupPtr,
+                                                                    int32_t* __restrict__ bestIdx, int32_t* __restrict__ bestMedian)
+{
+    __shared__ int hist[DD_WARPS][DD_BINS];
+    __shared__ int sKey[DD_WARPS];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = groupPtr[g], N = groupPtr[g + 1] - b;
+    if (N <= 0) {
+        if (threadIdx.x == 0) { bestIdx[g] = -1; bestMedian[g] = -1; }
+        return;
+    }
+    const uint4* D = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)b;
+    const int k = (int)(0.5 * (N - 1));
+    int* h = hist[wid];
+    for (int i = lane; i < DD_BINS; i += 32) h[i] = 0;
+    __syncwarp();
+    int best = 0x7fffffff;                                          // median << 20 | row  (N < 2^20 checked by the host)
+    for (int i = wid; i < N; i += DD_WARPS) {
+        const uint4 a0 = __ldg(D + 2 * i), a1 = __ldg(D + 2 * i + 1);
+        for (int j = lane; j < N; j += 32) {
+            const int d = j == i ? 0 : hamming256(a0, a1, __ldg(D + 2 * j), __ldg(D + 2 * j + 1));
+            atomicAdd(&h[d], 1);
+        }
+        __syncwarp();
+        int c[9], sum = 0;
+#pragma unroll
+        for (int t = 0; t < 9; t++) { c[t] = h[9 * lane + t]; sum += c[t]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - sum, med = -1;                             // elements in the bins before this lane's
+        const bool mine = run <= k && k < incl;                     // exactly one lane
+        if (mine) {
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                if (med < 0 && k < run + c[t]) med = 9 * lane + t;
+                run += c[t];
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        med = __shfl_sync(0xffffffffu, med, __ffs(who) - 1);
+#pragma unroll
+        for (int t = 0; t < 9; t++) h[9 * lane + t] = 0;
+        __syncwarp();
+        best = min(best, (med << 20) | i);
+    }
+    if (lane == 0) sKey[wid] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int r = sKey[0];
+#pragma unroll
+        for (int w = 1; w < DD_WARPS; w++) r = min(r, sKey[w]);
+        bestIdx[g] = r & 0xfffff; bestMedian[g] = r >> 20;
+    }
+}
+
+void launch_distinctive(Ctx& c, const uint8_t* d_desc, const int32_t* d_groupPtr, int nGroups, int32_t* d_bestIdx, int32_t* d_bestMedian)
+{
+    if (nGroups <= 0) return;
+    distinctive_kernel<<<nGroups, DD_WARPS * 32, 0, c.stream>>>(d_desc, d_groupPtr, d_bestIdx, d_bestMedian);
+    c.launches++;
+}
+
 }  // namespace orbb200

@@ -57,6 +57,7 @@ struct TriJob {
 void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
                  int32_t* bi, int32_t* bd, int32_t* sd);
 void launch_popc_peak(Ctx& c, uint32_t* d_out, int blocks, int iters);
+void launch_distinctive(Ctx& c, const uint8_t* d_desc, const int32_t* d_groupPtr, int nGroups, int32_t* d_bestIdx, int32_t* d_bestMedian);
 void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes);
 void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, float r, int minLevel, int maxLevel,
                              int32_t* d_out, int cap, int32_t* d_count);

@@ -256,3 +256,26 @@ def birdview_case(size, seed, vehicle=(80, 140)):
     vw, vh = vehicle
     mask[h // 2 - vh // 2:h // 2 + vh // 2 + 1, w // 2 - vw // 2:w // 2 + vw // 2 + 1] = 0
     return img, mask
+
+
+def distinctive_groups(sizes, seed):
+    """Observation descriptors of landmarks for ComputeDistinctiveDescriptors: per landmark a base descriptor and
+    noisy copies of it (0-60 flipped bits), a few exact duplicates so that medians tie between rows.
+    Returns (desc [total][32], group_ptr [len(sizes)+1])."""
+    rng = np.random.default_rng(seed)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = np.zeros((int(ptr[-1]), 32), np.uint8)
+    for g, n in enumerate(sizes):
+        if n == 0:
+            continue
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        bits = np.unpackbits(np.tile(base, (n, 1)), axis=1)
+        for i in range(n):
+            flips = rng.choice(256, size=int(rng.integers(0, 61)), replace=False)
+            bits[i, flips] ^= 1
+        rows = np.packbits(bits, axis=1)
+        if n >= 4:
+            rows[n - 1] = rows[0]          # duplicates: equal rows of the distance matrix -> first index must win
+            rows[n // 2] = rows[1]
+        desc[ptr[g]:ptr[g + 1]] = rows
+    return desc, ptr

@@ -575,3 +575,28 @@ def search_by_bow(desc1, angle1, valid1, F2, valid2, fv1, fv2, nnratio, check_or
                     out_f[j] = -1
                 nm -= 1
     return nm, (out_12 if kf_kf else out_f)
+
+
+def compute_distinctive_descriptors(vDescriptors):
+    """Literal transcription of the selection in MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:272-301;
+    identical in MapPointBird.cc:117-146).  vDescriptors: list of 32-byte rows.  Returns (BestIdx, BestMedian) or
+    (-1, -1) when the list is empty (the reference returns before choosing)."""
+    N = len(vDescriptors)
+    if N == 0:
+        return -1, -1
+    Distances = [[0.0] * N for _ in range(N)]
+    for i in range(N):
+        Distances[i][i] = 0
+        for j in range(i + 1, N):
+            distij = int(np.unpackbits(np.bitwise_xor(vDescriptors[i], vDescriptors[j])).sum())
+            Distances[i][j] = distij
+            Distances[j][i] = distij
+    BestMedian = 2 ** 31 - 1
+    BestIdx = 0
+    for i in range(N):
+        vDists = sorted(int(d) for d in Distances[i])
+        median = vDists[int(0.5 * (N - 1))]
+        if median < BestMedian:
+            BestMedian = median
+            BestIdx = i
+    return BestIdx, BestMedian

@@ -147,6 +147,23 @@ def test_knn2_vs_oracle(pkg, nq, nm):
     assert np.array_equal(bi, bi0) and np.array_equal(bd, bd0) and np.array_equal(sd, sd0)
 
 
+def test_distinctive_descriptors_vs_oracle(pkg):
+    """MapPoint[Bird]::ComputeDistinctiveDescriptors selection, batched over landmarks (incl. empty groups, single
+    observations, ties between duplicate observations, a group larger than one warp pass)."""
+    ctx = pkg.Context(500, 1.2, 8, 20, 7, 320, 240, 1)
+    m = pkg.ORBmatcher(ctx)
+    sizes = [0, 1, 2, 3, 4, 5, 8, 13, 32, 33, 40, 0, 7, 129, 300] + [int(x) for x in np.random.default_rng(5).integers(1, 25, 400)]
+    desc, ptr = cases.distinctive_groups(sizes, 32)
+    bi, bm = m.ComputeDistinctiveDescriptors(desc, ptr)
+    bi0, bm0 = oracle.distinctive_descriptors(desc, ptr)
+    assert np.array_equal(bi, bi0) and np.array_equal(bm, bm0)
+    # no landmarks / only empty landmarks
+    bi, bm = m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.array([0], np.int32))
+    assert len(bi) == 0
+    bi, bm = m.ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.array([0, 0, 0], np.int32))
+    assert bi.tolist() == [-1, -1] and bm.tolist() == [-1, -1]
+
+
 def test_knn2_full_size_properties(pkg):
     """C4 at 2k x 200k: checked through size-independent properties + a sampled exact check."""
     nq, nm = 2000, 200000

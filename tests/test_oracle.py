@@ -159,6 +159,21 @@ def test_knn2_vs_numpy():
     assert bi.tolist() == [-1, -1] and bd.tolist() == [256, 256]
 
 
+def test_distinctive_descriptors_vs_python():
+    """MapPoint[Bird]::ComputeDistinctiveDescriptors selection: oracle vs the literal transcription."""
+    import matcher_py_ref as mref
+    sizes = [0, 1, 2, 3, 4, 5, 8, 13, 32, 33, 40, 0, 7]
+    desc, ptr = cases.distinctive_groups(sizes, 31)
+    bi, bm = oracle.distinctive_descriptors(desc, ptr)
+    for g, n in enumerate(sizes):
+        want = mref.compute_distinctive_descriptors([desc[i] for i in range(ptr[g], ptr[g + 1])])
+        assert (int(bi[g]), int(bm[g])) == want, f"group {g} (N={n})"
+    # all descriptors equal: every median is 0, the first row wins
+    same = np.tile(desc[:1], (6, 1))
+    bi, bm = oracle.distinctive_descriptors(same, np.array([0, 6], np.int32))
+    assert bi.tolist() == [0] and bm.tolist() == [0]
+
+
 def _golden_frame():
     w, h = 620, 188
     kps, desc, uR, grid = cases.frame_case(500, w, h, 11, stereo_frac=0.4)
