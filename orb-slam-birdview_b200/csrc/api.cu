@@ -197,7 +197,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     std::vector<int4> btiles, rtiles;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
-        for (int y0 = 0; y0 < L.h; y0 += 32)
+        for (int y0 = 0; y0 < L.h; y0 += BL_ROWS)
             for (int x0 = 0; x0 < L.w; x0 += 128) btiles.push_back(make_int4(l, x0, y0, 0));
         if (l > 0)
             for (int y0 = 0; y0 < L.h; y0 += RS_ROWS)

@@ -21,6 +21,10 @@ constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
 constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;   // src/ORBmatcher.cc:37-39
 constexpr int PYR_MARGIN_X = 32;        // bytes of reflect-101 border stored left of each level row (>= 4 used)
 constexpr int PYR_MARGIN_Y = 4;         // border rows stored above/below each level (>= 3 used)
+#ifndef ORBB200_BL_ROWS
+#define ORBB200_BL_ROWS 48
+#endif
+constexpr int BL_ROWS = ORBB200_BL_ROWS;   // output rows per blur warp tile, 128 columns wide (6 extra rows of horizontal work per tile)
 constexpr int RS_ROWS = 32;             // output rows per resize tile (128 columns wide)
 constexpr int FT_PITCH = 49;            // u32 words per row of fast_cells_kernel's shared tiles (>= 2*ceil(68/4)+3 = 37), general case
 constexpr int FT_PITCH_SMALL = 25;      // the same for shapes whose cell images are at most 44 pixels wide (2*11+3): half the shared memory
