@@ -891,7 +891,7 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     J.out_nmatches = A.take<int32_t>(1);
     WinJob* dJ = A.take<WinJob>(1);
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, &J, sizeof(J), cudaMemcpyHostToDevice, c.stream));
-    launch_window_match(c, dJ, 1, nq);
+    launch_window_match(c, dJ, 1, nq, kpCap);
     ORBB200_CUDA_OK(c, cudaGetLastError());
     if (h_best_idx) cudaMemcpyAsync(h_best_idx, J.out_best_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
     if (h_best_dist) cudaMemcpyAsync(h_best_dist, J.out_best_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
@@ -1349,7 +1349,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
         c.stereoValid = true;
     }
     { StageTimer t(c, 6); launch_grid_build(c, dF, n_frames); }
-    { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames, nq); }
+    { StageTimer t(c, 7); launch_window_match(c, dJ, n_frames, nq, c.cur->g.kpPerImg); }
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;
 }

@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
 
 // Reflect-101 border of every level: PYR_MARGIN_X(>=4 used) columns left, 8 right, 3 rows above/below.
 // blockIdx.x = level * BD_CHUNKS + chunk: the (few thousand) border bytes of a level are split over BD_CHUNKS CTAs.
-constexpr int BD_CHUNKS = 8;
+#ifndef ORBB200_BD_CHUNKS
+#define ORBB200_BD_CHUNKS 32
+#endif
+constexpr int BD_CHUNKS = ORBB200_BD_CHUNKS;
 
 __global__ void __launch_bounds__(128) border_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, Geom g)
 {
@@ -713,6 +716,31 @@ size_t octree_smem_bytes(int maxNodes)
     return (size_t)maxNodes * (8 * 2 + 4 * 2 + 16 + 4 + 16 + 4 + 4) + (size_t)P2 * 4 + 256;
 }
 
+// One sweep over a level's candidates: the packed candidate and its node label of OT_UNROLL strided items are
+// requested before any of them is used.  A thread that loads one item, uses it and only then loads the next keeps a
+// single L2 request in flight, and the (image, level) CTAs with ~10^4 candidates then set the kernel's duration by
+// their ~20 dependent sweeps (measured: latency-bound, not issue-bound).
+constexpr int OT_UNROLL = 4;
+template <bool NEED_NODE, typename F>
+__device__ __forceinline__ void ot_sweep(const uint32_t* __restrict__ C, const uint16_t* nodeOf, int n, int tid, F f)
+{
+    for (int base = tid; base < n; base += OT_UNROLL * OT_THREADS) {
+        uint32_t v[OT_UNROLL];
+        int p[OT_UNROLL];
+#pragma unroll
+        for (int k = 0; k < OT_UNROLL; k++) {
+            const int i = base + k * OT_THREADS;
+            v[k] = i < n ? C[i] : 0u;
+            p[k] = (NEED_NODE && i < n) ? (int)nodeOf[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < OT_UNROLL; k++) {
+            const int i = base + k * OT_THREADS;
+            if (i < n) f(i, v[k], p[k]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                             uint16_t* __restrict__ nodeOfAll, uint32_t* __restrict__ lvlKp,
                                                             int32_t* __restrict__ lvlCount, int32_t* __restrict__ status)
@@ -768,14 +796,13 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         curCnt[i] = 0;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += OT_THREADS) {
-        const uint32_t v = C[i];
+    ot_sweep<false>(C, nodeOf, n, tid, [&](int i, uint32_t v, int) {
         const int x = v & 0xfff;
         int r = (int)__fdiv_rn((float)x, hX);
         r = min(r, nIni - 1);
         nodeOf[i] = (uint16_t)r;
         atomicAdd(&curCnt[r], 1);
-    }
+    });
     __syncthreads();
     // drop empty roots (compaction in order)
     int listSize;
@@ -792,7 +819,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         }
         __syncthreads();
         total = sFlag;
-        for (int i = tid; i < n; i += OT_THREADS) nodeOf[i] = (uint16_t)newPos[nodeOf[i]];
+        ot_sweep<true>(C, nodeOf, n, tid, [&](int i, uint32_t, int p) { nodeOf[i] = (uint16_t)newPos[p]; });
         __syncthreads();
         listSize = total;
         OtNode* t = cur; cur = nxt; nxt = t;
@@ -861,16 +888,14 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
             cc[4 * p + 0] = 0; cc[4 * p + 1] = 0; cc[4 * p + 2] = 0; cc[4 * p + 3] = 0;
         }
         __syncthreads();
-        for (int i = tid; i < n; i += OT_THREADS) {
-            const int p = nodeOf[i];
-            if (aux[p] < 0) continue;
-            const uint32_t v = C[i];
+        ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+            if (aux[p] < 0) return;
             const int x = v & 0xfff, y = (v >> 12) & 0xfff;
             const OtNode nd = cur[p];
             const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
             const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
             atomicAdd(&cc[4 * p + q], 1);
-        }
+        });
         __syncthreads();
 
         // ---- 3. how many of `order` are actually split (sorted pass stops once |list| >= N) ----
@@ -970,17 +995,15 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         __syncthreads();
 
         // ---- 5. relabel candidates ----
-        for (int i = tid; i < n; i += OT_THREADS) {
-            const int p = nodeOf[i];
+        ot_sweep<true>(C, nodeOf, n, tid, [&](int i, uint32_t v, int p) {
             const int np = newPos[p];
-            if (np >= 0) { nodeOf[i] = (uint16_t)np; continue; }
-            const uint32_t v = C[i];
+            if (np >= 0) { nodeOf[i] = (uint16_t)np; return; }
             const int x = v & 0xfff, y = (v >> 12) & 0xfff;
             const OtNode nd = cur[p];
             const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
             const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
             nodeOf[i] = (uint16_t)childPos[4 * p + q];
-        }
+        });
         __syncthreads();
         {
             OtNode* t = cur; cur = nxt; nxt = t;
@@ -1003,28 +1026,24 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
     uint32_t* bestVal = reinterpret_cast<uint32_t*>(newPos);   // [listSize] packed candidate
     for (int i = tid; i < listSize; i += OT_THREADS) { best[i] = 0; bestKey[i] = 0xffffffffu; }
     __syncthreads();
-    for (int i = tid; i < n; i += OT_THREADS) atomicMax(&best[nodeOf[i]], C[i] >> 24);
+    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) { atomicMax(&best[p], v >> 24); });
     __syncthreads();
     const int wCell = L.wCell, hCell = L.hCell, nCols = L.nCols;
-    for (int i = tid; i < n; i += OT_THREADS) {
-        const uint32_t v = C[i];
-        const int p = nodeOf[i];
-        if ((v >> 24) != best[p]) continue;
+    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+        if ((v >> 24) != best[p]) return;
         const int x = v & 0xfff, y = (v >> 12) & 0xfff;
         const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
         const uint32_t key = ((uint32_t)(ci * nCols + cj) << 12) | ((uint32_t)(y - 3 - ci * hCell) << 6) | (uint32_t)(x - 3 - cj * wCell);
         atomicMin(&bestKey[p], key);
-    }
+    });
     __syncthreads();
-    for (int i = tid; i < n; i += OT_THREADS) {
-        const uint32_t v = C[i];
-        const int p = nodeOf[i];
-        if ((v >> 24) != best[p]) continue;
+    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+        if ((v >> 24) != best[p]) return;
         const int x = v & 0xfff, y = (v >> 12) & 0xfff;
         const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
         const uint32_t key = ((uint32_t)(ci * nCols + cj) << 12) | ((uint32_t)(y - 3 - ci * hCell) << 6) | (uint32_t)(x - 3 - cj * wCell);
         if (key == bestKey[p]) bestVal[p] = v;
-    }
+    });
     __syncthreads();
     const int nOut = min(listSize, L.kpCap);
     for (int i = tid; i < nOut; i += OT_THREADS) outKp[i] = bestVal[i];

@@ -1,5 +1,7 @@
 // Matching kernels: 256-bit Hamming brute force (best / second best), device lookup grid, and the
 // windowed greedy searches of ORBmatcher restated as parallel fixed-point iterations.
+#include <algorithm>
+
 #include "match.cuh"
 
 namespace orbb200 {
@@ -394,8 +396,11 @@ __global__ void __launch_bounds__(WC_THREADS) window_cands_kernel(const WinJob* 
     ccount[q] = n;
 }
 
-__global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* __restrict__ jobs)
+__global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* __restrict__ jobs, int smemInts)
 {
+    // the per-call state (2 * kpCap + 6 * nq ints) lives in shared memory when it fits: the rounds are chains of
+    // dependent reads of it, and with one CTA per call there is nothing else on the SM to cover L2 latency
+    extern __shared__ int wmState[];
     __shared__ int sHist[HISTO_LENGTH];
     __shared__ int sKeep[3];
     __shared__ int sCount, sRemoved;
@@ -408,7 +413,8 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     const bool distSem = is_dist_sem(mode);
     const bool independent = (mode == WM_BEST) && !(J.flags & WF_BLOCK);    // Fuse / SearchBySim3: no loop-carried state
 
-    int* owner = J.scratch;                 // [kpCap] BLOCK: min blocking query; DIST: head of claimant list
+    int* state = (2 * (size_t)J.kpCap + 6 * (size_t)nq <= (size_t)smemInts) ? wmState : J.scratch;
+    int* owner = state;                     // [kpCap] BLOCK: min blocking query; DIST: head of claimant list
     int* lastOwner = owner + J.kpCap;       // [kpCap] max accepted query per keypoint
     int* choice = lastOwner + J.kpCap;      // [nq]    published: accepted keypoint or -1
     int* cdist = choice + nq;               // [nq]    published: its distance
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     int* newCdist = newChoice + nq;         // [nq]
     int* nextq = newCdist + nq;             // [nq]    DIST: claimant list link
     int* qbin = nextq + nq;                 // [nq]    rotation bin of an accepted query
-    const int* ccount = qbin + nq;          // [nq]    phase-1 candidate counts
+    const int* ccount = J.scratch + 2 * (size_t)J.kpCap + 6 * (size_t)nq;   // [nq] phase-1 candidate counts (global: written by window_cands_kernel)
     const int2* clistAll = reinterpret_cast<const int2*>(J.scratch + win_clist_offset(J.kpCap, nq));
 
     for (int i = tid; i < nkp; i += WM_THREADS) { owner[i] = distSem ? -1 : 0x7fffffff; lastOwner[i] = -1; }
@@ -571,14 +577,23 @@ __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* 
     if (tid == 0) *J.out_nmatches = sCount - sRemoved;
 }
 
-void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq)
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq, int maxKpCap)
 {
+    // shared-memory budget of window_match_kernel's per-call state; larger calls keep it in their global scratch
+    constexpr size_t WM_SMEM_MAX = 200 * 1024;
+    size_t smem = sizeof(int) * (2 * (size_t)std::max(maxKpCap, 0) + 6 * (size_t)std::max(maxNq, 0));
+    if (smem > WM_SMEM_MAX) smem = 0;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaFuncSetAttribute(window_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_MAX);
+        configured = WM_SMEM_MAX;
+    }
     if (maxNq > 0) {
         dim3 grid((maxNq + WC_THREADS - 1) / WC_THREADS, njobs);
         window_cands_kernel<<<grid, WC_THREADS, 0, c.stream>>>(d_jobs);
         c.launches++;
     }
-    window_match_kernel<<<njobs, WM_THREADS, 0, c.stream>>>(d_jobs);
+    window_match_kernel<<<njobs, WM_THREADS, smem, c.stream>>>(d_jobs, (int)(smem / sizeof(int)));
     c.launches++;
 }
 

@@ -61,7 +61,7 @@ void launch_distinctive(Ctx& c, const uint8_t* d_desc, const int32_t* d_groupPtr
 void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes);
 void launch_features_in_area(Ctx& c, const FrameDev* d_frame, float x, float y, float r, int minLevel, int maxLevel,
                              int32_t* d_out, int cap, int32_t* d_count);
-void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq);
+void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq, int maxKpCap);
 void launch_triangulation(Ctx& c, const TriJob& J);
 
 // Frame::isInFrustum over a device-resident map
