@@ -546,7 +546,7 @@ def run_ours(args):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(name)
         traffic = t["dram_bytes_per_image"] * 2 * B if t else None   # ncu dram read+write, scaled to this launch's image count
-        ncu_pipes = {k: t[k] for k in ("alu_pipe_pct_of_peak", "issue_active_pct_of_peak", "lsu_pipe_pct_of_peak") if t and k in t}
+        ncu_pipes = {k: t[k] for k in ("alu_pipe_pct_of_peak", "issue_active_pct_of_peak", "lsu_pipe_pct_of_peak", "l1tex_throughput_pct_of_peak") if t and k in t}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": name, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src, "traffic": traffic,
@@ -557,7 +557,7 @@ def run_ours(args):
         roofline["frac"] = roofline["achieved"] / hbm_peak
         roofline["algorithmic_bytes_per_launch"] = int(per_launch)
         if ncu_pipes:
-            roofline["ncu_pipe_utilisation"] = dict(ncu_pipes, source="profiles/r1h_summary.md (ncu --set full of this kernel; what actually bounds it)")
+            roofline["ncu_pipe_utilisation"] = dict(ncu_pipes, source=str(t.get("source", "profiles/")))
     else:
         roofline["achieved"] = None
         roofline["frac"] = None
