@@ -357,6 +357,9 @@ def dist_setup(args):
     return rank, world, local, dist
 
 
+_FULL_AFFINITY = None      # the process's CPU set before bind_near_gpu narrowed it (the CPU baseline gets all of it back)
+
+
 def bind_near_gpu(device, enable=True):
     """Pin this process (and the threads / pinned host allocations it makes afterwards) to the CPUs NVML reports as
     closest to the GPU, so that each rank's staging buffers live on the NUMA node its GPU's PCIe root hangs off.
@@ -383,6 +386,8 @@ def bind_near_gpu(device, enable=True):
         if h is None:
             h = pynvml.nvmlDeviceGetHandleByIndex(device)
         before = os.sched_getaffinity(0)
+        global _FULL_AFFINITY
+        _FULL_AFFINITY = set(before)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         ideal = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
         cpus = (ideal & before) or before          # stay inside the container's cpuset
@@ -613,6 +618,8 @@ def working_set_mb(B, P):
 def cpu_baseline(arm, args, target_s=15.0):
     """Oracle port on the host cores; bounded sample (about target_s seconds of wall time)."""
     try:
+        if _FULL_AFFINITY:
+            os.sched_setaffinity(0, _FULL_AFFINITY)      # the baseline may use every host core, not only the GPU's neighbours
         cores = host_cores()
         cpu = CpuArm(cores)
         cpu.with_stereo = bool(args.with_stereo)
