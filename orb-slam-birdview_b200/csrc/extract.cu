@@ -749,7 +749,8 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
     __shared__ int warpSums[OT_THREADS / 32];
     __shared__ int sFlag;
 
-    const int level = blockIdx.x, img = blockIdx.y;
+    // blockIdx.y = level: the CTAs of level 0 (most candidates, longest) are dispatched first, the short ones fill the tail
+    const int level = blockIdx.y, img = blockIdx.x;
     const LevelGeom L = g.lv[level];
     const int tid = threadIdx.x;
     const int N = L.quota;
@@ -1305,7 +1306,7 @@ void launch_octree(Ctx& c, int n)
         cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    dim3 grid(g.nlevels, n);
+    dim3 grid(n, g.nlevels);
     octree_kernel<<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
     c.launches++;
 }
