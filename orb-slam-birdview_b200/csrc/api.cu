@@ -14,7 +14,7 @@ struct orbb200_frame {
     Ctx* ctx = nullptr;
     FrameDev h{};
     FrameDev* d_self = nullptr;
-    void* owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* owned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int cap = 0;
 };
 
@@ -739,6 +739,8 @@ static int frame_finish(Ctx& c, orbb200_frame* f)
     ORBB200_CUDA_OK(c, cudaMalloc(&f->owned[4], sizeof(int32_t) * std::max(f->cap, 1)));
     f->h.cellStart = (int32_t*)f->owned[3];
     f->h.cellItems = (int32_t*)f->owned[4];
+    ORBB200_CUDA_OK(c, cudaMalloc(&f->owned[5], sizeof(int4) * std::max(f->cap, 1)));
+    f->h.cellKp = (int4*)f->owned[5];
     ORBB200_CUDA_OK(c, cudaMalloc((void**)&f->d_self, sizeof(FrameDev)));
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(f->d_self, &f->h, sizeof(FrameDev), cudaMemcpyHostToDevice, c.stream));
     launch_grid_build(c, f->d_self, 1);
@@ -1303,7 +1305,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
             for (auto& p : c.plans) cudaFree(p.block);
             c.plans.clear();
         }
-        const size_t perFrame = align_up(4 * (size_t)(GRID_CELLS + 1), 256) + align_up(4 * (size_t)kpi, 256) * 2 +
+        const size_t perFrame = align_up(4 * (size_t)(GRID_CELLS + 1), 256) + align_up(4 * (size_t)kpi, 256) * 2 + align_up(16 * (size_t)kpi, 256) +
                                 align_up(4 * win_scratch_ints(kpi, nq), 256);
         const size_t bytes = align_up(sizeof(FrameDev) * n_frames, 256) + align_up(sizeof(WinJob) * n_frames, 256) + 256 + perFrame * n_frames + 4096;
         ORBB200_CUDA_OK(c, cudaMalloc(&key.block, bytes));
@@ -1319,7 +1321,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
             f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32;
             f.uRight = c.stepStereo ? c.d_uRight + (size_t)img * kpi : nullptr;
             f.n_ptr = c.d_counts + img; f.n = kpi;
-            f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi);
+            f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi); f.cellKp = A.take<int4>(kpi);
             f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
             WinJob& J = hJ[i];
             memset(&J, 0, sizeof(J));

@@ -188,6 +188,13 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
             F.cellItems[j + 1] = key;
         }
     }
+    __syncthreads();
+    // position-sorted copy of what a window scan needs of each keypoint (no index -> keypoint indirection in the scan)
+    for (int k = tid; k < n; k += 1024) {
+        const int idx = F.cellItems[k];
+        const orbb200_kp_t kp = F.kps[idx];
+        F.cellKp[k] = make_int4(__float_as_int(kp.x), __float_as_int(kp.y), kp.octave, idx);
+    }
 }
 
 void launch_grid_build(Ctx& c, const FrameDev* d_frames, int nframes)
@@ -226,15 +233,23 @@ __device__ __forceinline__ void scan_window(const FrameDev& F, float x, float y,
     for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
         // cells (ix, nMinCellY..nMaxCellY) are contiguous in the column-major CSR
         const int b = F.cellStart[ix * GRID_ROWS + nMinCellY], e = F.cellStart[ix * GRID_ROWS + nMaxCellY + 1];
-        for (int k = b; k < e; k++) {
-            const int idx = F.cellItems[k];
-            const orbb200_kp_t kp = F.kps[idx];
+        auto item = [&](const int4 it) {
+            orbb200_kp_t kp;                      // the fields a visitor may read: position and octave
+            kp.x = __int_as_float(it.x); kp.y = __int_as_float(it.y); kp.octave = it.z;
+            kp.size = 0.f; kp.angle = 0.f; kp.response = 0.f; kp.class_id = -1;
             if (bCheckLevels) {
-                if (kp.octave < minLevel) continue;
-                if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                if (kp.octave < minLevel) return;
+                if (maxLevel >= 0 && kp.octave > maxLevel) return;
             }
             const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
-            if (fabsf(dx) < r && fabsf(dy) < r) visit(idx, kp);
+            if (fabsf(dx) < r && fabsf(dy) < r) visit(it.w, kp);
+        };
+        // two items in flight: the slice is contiguous, so the second load does not depend on the first
+        for (int k = b; k < e; k += 2) {
+            const int4 it0 = F.cellKp[k];
+            const int4 it1 = F.cellKp[min(k + 1, e - 1)];
+            item(it0);
+            if (k + 1 < e) item(it1);
         }
     }
 }

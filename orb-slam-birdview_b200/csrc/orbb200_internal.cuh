@@ -71,6 +71,7 @@ struct FrameDev {
     int n;                      // host-known count (uploaded frames) or capacity
     int32_t* cellStart;         // [GRID_CELLS+1]
     int32_t* cellItems;         // [cap]
+    int4* cellKp;               // [cap] {x bits, y bits, octave, keypoint index} of cellItems[k]: a window scan reads one contiguous slice
     float minX, minY, invW, invH;
 };
 
