@@ -1,0 +1,121 @@
+// Test driver for ORBmatcher_b200.cc: builds Frame / MapPoint / MapPointBird objects from a flat binary case file, calls
+// the ORB_SLAM2::ORBmatcher methods exactly like Tracking does (src/Tracking.cc:1652-1672 SearchByProjection on the
+// local map points, :1241 SearchByMatchBird, and BirdviewMatch directly) and dumps what they left in the objects.
+//   matcher_driver <case.bin> <out.bin>
+// case.bin: int32 {nF, nq, n1, n2, window}; float32 {th, nnratio, nnratioBird, minX, minY, invW, invH, invWbird, invHbird};
+//   front frame: kps[nF] (28 B), desc[nF][32], uRight[nF] f32, kp_obs[nF] i32 (-1: no MapPoint on the keypoint, else its Observations())
+//   map points:  inview[nq] u8, bad[nq] u8, u,v,uR,viewcos [nq] f32, level[nq] i32, obs[nq] i32, desc[nq][32]
+//   birdview:    kps1[n1], desc1[n1][32], hasmp1[n1] u8, kps2[n2], desc2[n2][32]
+// out.bin: int32 nmatches; int32 mp_of_kp[nF] (index of the map point now on the keypoint, -2: the pre-existing one, -1: none);
+//          int32 nmBird; int32 vnMatches12[n1]; int32 nmSearchByMatchBird; int32 bird_mp_of_kp2[n2] (LastFrame keypoint index or -1);
+//          int32 DescriptorDistance(desc1[0], desc2[0])
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ORBmatcher.h"
+
+using namespace ORB_SLAM2;
+
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mfGridElementWidthInvBirdview, Frame::mfGridElementHeightInvBirdview;
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+static std::vector<unsigned char> buf;
+static size_t off = 0;
+template <class T> static const T* take(size_t n) { const T* p = reinterpret_cast<const T*>(buf.data() + off); off += n * sizeof(T); if (off > buf.size()) { fprintf(stderr, "case file too short\n"); exit(2); } return p; }
+
+static cv::Mat rows32(const unsigned char* d, int n)
+{
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8U);
+    if (n > 0) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: matcher_driver case.bin out.bin\n"); return 2; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+    fseek(f, 0, SEEK_END); buf.resize(ftell(f)); fseek(f, 0, SEEK_SET);
+    if (fread(buf.data(), 1, buf.size(), f) != buf.size()) return 2;
+    fclose(f);
+    const int* hi = take<int>(5);
+    const int nF = hi[0], nq = hi[1], n1 = hi[2], n2 = hi[3], window = hi[4];
+    const float* hf = take<float>(9);
+    const float th = hf[0], nnratio = hf[1], nnratioBird = hf[2];
+    Frame::mnMinX = hf[3]; Frame::mnMinY = hf[4]; Frame::mfGridElementWidthInv = hf[5]; Frame::mfGridElementHeightInv = hf[6];
+    Frame::mfGridElementWidthInvBirdview = hf[7]; Frame::mfGridElementHeightInvBirdview = hf[8];
+
+    // ---- front frame + local map points: Tracking::SearchLocalPoints -> matcher.SearchByProjection(mCurrentFrame, mvpLocalMapPoints, th)
+    Frame F;
+    F.N = nF;
+    const cv::KeyPoint* kps = take<cv::KeyPoint>(nF);
+    F.mvKeysUn.assign(kps, kps + nF);
+    F.mDescriptors = rows32(take<unsigned char>((size_t)nF * 32), nF);
+    const float* ur = take<float>(nF);
+    F.mvuRight.assign(ur, ur + nF);
+    const int* kpObs = take<int>(nF);
+    std::vector<MapPoint> existing(nF);
+    F.mvpMapPoints.assign(nF, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < nF; i++)
+        if (kpObs[i] >= 0) { existing[i].nObs = kpObs[i]; F.mvpMapPoints[i] = &existing[i]; }
+    F.mvScaleFactors.resize(8);
+    F.mvScaleFactors[0] = 1.0f;
+    for (int i = 1; i < 8; i++) F.mvScaleFactors[i] = F.mvScaleFactors[i - 1] * 1.2f;
+
+    const unsigned char* inview = take<unsigned char>(nq);
+    const unsigned char* bad = take<unsigned char>(nq);
+    const float* qu = take<float>(nq); const float* qv = take<float>(nq); const float* quR = take<float>(nq); const float* qvc = take<float>(nq);
+    const int* qlvl = take<int>(nq); const int* qobs = take<int>(nq);
+    const unsigned char* qdesc = take<unsigned char>((size_t)nq * 32);
+    std::vector<MapPoint> mps(nq);
+    std::vector<MapPoint*> vpLocalMapPoints(nq);
+    for (int i = 0; i < nq; i++) {
+        MapPoint& p = mps[i];
+        p.mbTrackInView = inview[i] != 0; p.mbBad = bad[i] != 0;
+        p.mTrackProjX = qu[i]; p.mTrackProjY = qv[i]; p.mTrackProjXR = quR[i]; p.mTrackViewCos = qvc[i];
+        p.mnTrackScaleLevel = qlvl[i]; p.nObs = qobs[i];
+        p.mDescriptor = rows32(qdesc + (size_t)i * 32, 1);
+        vpLocalMapPoints[i] = &p;
+    }
+    ORBmatcher matcher(nnratio);
+    const int nmatches = matcher.SearchByProjection(F, vpLocalMapPoints, th);
+
+    // ---- birdview: BirdviewMatch(Last, Cur) and SearchByMatchBird(Cur, Last, window)
+    Frame Last, Cur;
+    const cv::KeyPoint* k1 = take<cv::KeyPoint>(n1);
+    Last.mvKeysBird.assign(k1, k1 + n1);
+    const unsigned char* d1 = take<unsigned char>((size_t)n1 * 32);
+    Last.mDescriptorsBird = rows32(d1, n1);
+    const unsigned char* hasmp1 = take<unsigned char>(n1);
+    std::vector<MapPointBird> birds(n1);
+    Last.mvpMapPointsBird.assign(n1, static_cast<MapPointBird*>(NULL));
+    for (int i = 0; i < n1; i++) { birds[i].mnId = i; if (hasmp1[i]) Last.mvpMapPointsBird[i] = &birds[i]; }
+    const cv::KeyPoint* k2 = take<cv::KeyPoint>(n2);
+    Cur.mvKeysBird.assign(k2, k2 + n2);
+    const unsigned char* d2 = take<unsigned char>((size_t)n2 * 32);
+    Cur.mDescriptorsBird = rows32(d2, n2);
+    Cur.mvpMapPointsBird.assign(n2, static_cast<MapPointBird*>(NULL));
+    ORBmatcher matcherBird(nnratioBird, true);                  // Tracking.cc:325-326: new ORBmatcher(0.99,true)
+    std::vector<int> vnMatches12;
+    const int nmBird = matcherBird.BirdviewMatch(Last, Cur, vnMatches12, window);
+    const int nmSBM = matcherBird.SearchByMatchBird(Cur, Last, window);
+
+    FILE* o = fopen(argv[2], "wb");
+    fwrite(&nmatches, 4, 1, o);
+    for (int i = 0; i < nF; i++) {
+        int v = -1;
+        if (F.mvpMapPoints[i]) v = F.mvpMapPoints[i] == &existing[i] ? -2 : (int)(F.mvpMapPoints[i] - &mps[0]);
+        fwrite(&v, 4, 1, o);
+    }
+    fwrite(&nmBird, 4, 1, o);
+    fwrite(vnMatches12.data(), 4, vnMatches12.size(), o);
+    fwrite(&nmSBM, 4, 1, o);
+    for (int i = 0; i < n2; i++) { const int v = Cur.mvpMapPointsBird[i] ? (int)Cur.mvpMapPointsBird[i]->mnId : -1; fwrite(&v, 4, 1, o); }
+    const int dd = (n1 > 0 && n2 > 0) ? ORBmatcher::DescriptorDistance(Last.mDescriptorsBird, Cur.mDescriptorsBird) : -1;
+    fwrite(&dd, 4, 1, o);
+    fclose(o);
+    printf("%d projection matches, %d birdview matches, %d birdview landmarks carried over\n", nmatches, nmBird, nmSBM);
+    return 0;
+}

@@ -331,6 +331,61 @@ def test_cpp_shim(pkg, tmp_path):
     assert np.array_equal(lvl1, orc.level_image(1))          # mvImagePyramid[1]
 
 
+def test_cpp_matcher_shim(pkg, tmp_path):
+    """cpp/ORBmatcher_b200.cc -- the bodies of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th),
+    BirdviewMatch(const Frame&, const Frame&, ...) and SearchByMatchBird(Frame&, const Frame&, ...) over the C ABI --
+    driven through Frame / MapPoint / MapPointBird objects like Tracking does, against the oracle."""
+    import subprocess
+    from helpers import ROOT
+    drv = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp", "matcher_driver")
+    if not os.path.exists(drv):
+        subprocess.run(["make", "-s", "-C", os.path.dirname(drv)], check=True)
+    rng = np.random.default_rng(77)
+    w, h, nF, nq, th, ratio = 620, 188, 900, 1200, 1.0, 0.8
+    kps, desc, uR, grid = cases.frame_case(nF, w, h, 71, stereo_frac=0.4)
+    q = cases.projection_queries(kps, desc, uR, w, h, nq, 72)
+    kp_obs = np.where(rng.random(nF) < 0.1, 3, np.where(rng.random(nF) < 0.1, 0, -1)).astype(np.int32)   # blocked / unobserved MapPoint / none
+    bad = ((rng.random(nq) < 0.03) & (q["valid"] == 1)).astype(np.uint8)
+    q_obs = np.where(q["obs_pos"] == 1, 2, 0).astype(np.int32)
+    window, ratio_bird = 15, 0.99
+    (k1, d1), (k2, d2), bgrid = cases.bird_pair(1500, 400, 73)
+    hasmp1 = (rng.random(len(k1)) < 0.7).astype(np.uint8)
+    case, out = tmp_path / "case.bin", tmp_path / "out.bin"
+    with open(case, "wb") as f:
+        np.array([nF, nq, len(k1), len(k2), window], np.int32).tofile(f)
+        np.array([th, ratio, ratio_bird, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], bgrid["inv_w"], bgrid["inv_h"]], np.float32).tofile(f)
+        for a in (kps, desc, uR, kp_obs, q["valid"], bad, q["u"], q["v"], q["uR"], q["viewcos"], q["level"], q_obs, q["desc"],
+                  k1, d1, hasmp1, k2, d2):
+            np.ascontiguousarray(a).tofile(f)
+    subprocess.run([drv, str(case), str(out)], check=True, timeout=120)
+    res = np.fromfile(out, np.int32)
+    nm, mp_of_kp = res[0], res[1:1 + nF]
+    o = 1 + nF
+    nm_bird, m12 = res[o], res[o + 1:o + 1 + len(k1)]
+    o += 1 + len(k1)
+    nm_sbm, cur_mp = res[o], res[o + 1:o + 1 + len(k2)]
+    dd = res[o + 1 + len(k2)]
+    # SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129)
+    O = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
+    valid = (q["valid"] == 1) & (bad == 0)
+    nm0, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, valid.astype(np.uint8), q["u"], q["v"], q["uR"], q["level"],
+                                                     q["viewcos"], q["desc"], (q_obs > 0).astype(np.uint8), (kp_obs > 0).astype(np.uint8), th, ratio)
+    want = np.where(qk0 >= 0, qk0, np.where(kp_obs >= 0, -2, -1))
+    assert nm == nm0 and nm > 0 and np.array_equal(mp_of_kp, want)
+    # BirdviewMatch(const Frame&, const Frame&, vnMatches12, windowSize) (:1788-1899), SearchByMatchBird(Cur, Last, windowSize) (:1901-1921)
+    O2 = oracle.Frame(k2, d2, bgrid["min_x"], bgrid["min_y"], bgrid["inv_w"], bgrid["inv_h"])
+    nmb0, m120, _ = oracle.birdview_match(k1, d1, O2, None, window, ratio_bird, True)
+    assert nm_bird == nmb0 and nmb0 > 0 and np.array_equal(m12, m120)
+    want_cur = np.full(len(k2), -1, np.int32)
+    carried = 0
+    for k in range(len(k1)):
+        if m120[k] >= 0 and hasmp1[k]:
+            want_cur[m120[k]] = k
+            carried += 1
+    assert nm_sbm == carried and np.array_equal(cur_mp, want_cur)
+    assert dd == int(np.unpackbits(d1[0] ^ d2[0]).sum())                     # DescriptorDistance (:1647-1663)
+
+
 def test_cpp_birdview_shim(pkg, tmp_path):
     """cpp/BirdviewExtractor.h called like the birdview block of Frame::Frame (src/Frame.cc:328-342) == oracle."""
     import subprocess
