@@ -9,12 +9,14 @@
 //
 //   ORBmatcher::DescriptorDistance                         src/ORBmatcher.cc:1647-1663   (host: one pair is not GPU work)
 //   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)      :45-129    -> orbb200_search_by_projection
+//   ORBmatcher::SearchForTriangulation(KF1, KF2, F12, vMatchedPairs, bOnlyStereo)    :657-823   -> orbb200_search_for_triangulation
 //   ORBmatcher::BirdviewMatch(const Frame&, const Frame&, vnMatches12, windowSize)  :1788-1899 -> orbb200_birdview_match
 //   ORBmatcher::SearchByMatchBird(Frame&, const Frame&, windowSize)     :1901-1921 -> the same + the reference's copy loop
 //
 // The remaining methods follow the same pattern; their adapters are listed in INTEGRATION.md section 3.
 #include "ORBmatcher.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -94,6 +96,62 @@ int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoint
     for (int i = 0; i < nq; i++)
         if (bi[i] >= 0) F.mvpMapPoints[bi[i]] = vpMapPoints[i];                      // in query order == the loop's writes (:123)
     return nmatches;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12,
+                                       vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo)
+{
+    //Compute epipole in second image (the reference's own lines, :663-670)
+    cv::Mat Cw = pKF1->GetCameraCenter();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w*Cw+t2w;
+    const float invz = 1.0f/C2.at<float>(2);
+    const float ex =pKF2->fx*C2.at<float>(0)*invz+pKF2->cx;
+    const float ey =pKF2->fy*C2.at<float>(1)*invz+pKF2->cy;
+
+    // flatten both keyframes; DBoW2::FeatureVector is a std::map, so its iteration order (ascending node id) is the
+    // order of the reference's merge loop (:687-780)
+    struct Flat
+    {
+        vector<uint8_t> desc, hasMP;
+        vector<int32_t> node, ptr, idx;
+        Flat(KeyFrame* pKF)
+        {
+            const int n = pKF->N;
+            desc.resize((size_t)n * 32); hasMP.resize(n);
+            for (int i = 0; i < n; i++)
+            {
+                memcpy(&desc[32 * (size_t)i], pKF->mDescriptors.ptr(i), 32);
+                hasMP[i] = pKF->GetMapPoint(i) != NULL;                                  // "If there is already a MapPoint skip" (:699-701, :727-729)
+            }
+            ptr.push_back(0);
+            for (DBoW2::FeatureVector::const_iterator it = pKF->mFeatVec.begin(); it != pKF->mFeatVec.end(); it++)
+            {
+                node.push_back((int32_t)it->first);
+                for (size_t k = 0; k < it->second.size(); k++) idx.push_back((int32_t)it->second[k]);
+                ptr.push_back((int32_t)idx.size());
+            }
+        }
+    };
+    Flat f1(pKF1), f2(pKF2);
+    float F[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
+    vector<int32_t> pairs(2 * (size_t)std::max(pKF1->N, 1));
+    int npairs = 0;
+    orbb200_host::check(orbb200_search_for_triangulation(orbb200_host::ThreadContext(),
+                            (const orbb200_kp_t*)pKF1->mvKeysUn.data(), f1.desc.data(), pKF1->mvuRight.data(), f1.hasMP.data(), pKF1->N,
+                            (const orbb200_kp_t*)pKF2->mvKeysUn.data(), f2.desc.data(), pKF2->mvuRight.data(), f2.hasMP.data(), pKF2->N,
+                            f1.node.data(), f1.ptr.data(), f1.idx.data(), (int)f1.node.size(),
+                            f2.node.data(), f2.ptr.data(), f2.idx.data(), (int)f2.node.size(),
+                            F, ex, ey, pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(),
+                            bOnlyStereo ? 1 : 0, mbCheckOrientation ? 1 : 0, pairs.data(), &npairs), "orbb200_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(npairs);
+    for (int i = 0; i < npairs; i++)
+        vMatchedPairs.push_back(make_pair((size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]));    // ascending idx1, as :814-819
+    return npairs;
 }
 
 int ORBmatcher::BirdviewMatch(const Frame &F1, const Frame &F2, vector<int> &vnMatches12, int windowSize)

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "Frame.h"
+#include "KeyFrame.h"
 #include "MapPoint.h"
 
 namespace ORB_SLAM2
@@ -19,6 +20,9 @@ public:
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
 
     int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3);
+
+    int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12,
+                               std::vector<std::pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo);
 
     int BirdviewMatch(const Frame &F1, const Frame &F2, std::vector<int> &vnMatches12, int windowSize = 10);
 

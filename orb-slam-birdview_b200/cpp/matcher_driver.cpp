@@ -8,7 +8,8 @@
 //   birdview:    kps1[n1], desc1[n1][32], hasmp1[n1] u8, kps2[n2], desc2[n2][32]
 // out.bin: int32 nmatches; int32 mp_of_kp[nF] (index of the map point now on the keypoint, -2: the pre-existing one, -1: none);
 //          int32 nmBird; int32 vnMatches12[n1]; int32 nmSearchByMatchBird; int32 bird_mp_of_kp2[n2] (LastFrame keypoint index or -1);
-//          int32 DescriptorDistance(desc1[0], desc2[0])
+//          int32 DescriptorDistance(desc1[0], desc2[0]); int32 nTri (-1: no keyframe section); int32 pairs[nTri][2]
+// optional keyframe section of case.bin: see the reader below
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +103,50 @@ int main(int argc, char** argv)
     const int nmBird = matcherBird.BirdviewMatch(Last, Cur, vnMatches12, window);
     const int nmSBM = matcherBird.SearchByMatchBird(Cur, Last, window);
 
+    // ---- two keyframes: LocalMapping::CreateNewMapPoints -> matcher.SearchForTriangulation(mpCurrentKeyFrame, pKF2, F12, vMatchedIndices, false)
+    std::vector<std::pair<size_t, size_t> > vMatchedIndices;
+    int nTri = -1;
+    if (off < buf.size()) {
+        const int* ti = take<int>(5);
+        const int m1 = ti[0], m2 = ti[1], nn1 = ti[2], nn2 = ti[3], onlyStereo = ti[4];
+        const float* tf = take<float>(4 + 3 + 3 + 9 + 9);     // fx fy cx cy | Ow(KF1) | tcw(KF2) | Rcw(KF2) | F12
+        KeyFrame KF1, KF2;
+        std::vector<MapPoint> dummy(1);
+        KeyFrame* kfs[2] = {&KF1, &KF2};
+        const int ms[2] = {m1, m2};
+        for (int s = 0; s < 2; s++) {
+            KeyFrame& K = *kfs[s];
+            K.N = ms[s];
+            const cv::KeyPoint* kk = take<cv::KeyPoint>(K.N);
+            K.mvKeysUn.assign(kk, kk + K.N);
+            K.mDescriptors = rows32(take<unsigned char>((size_t)K.N * 32), K.N);
+            const float* u = take<float>(K.N);
+            K.mvuRight.assign(u, u + K.N);
+            const unsigned char* has = take<unsigned char>(K.N);
+            K.mvpMapPoints.assign(K.N, static_cast<MapPoint*>(NULL));
+            for (int i = 0; i < K.N; i++) if (has[i]) K.mvpMapPoints[i] = &dummy[0];
+            K.fx = tf[0]; K.fy = tf[1]; K.cx = tf[2]; K.cy = tf[3];
+        }
+        const int nns[2] = {nn1, nn2};
+        for (int s = 0; s < 2; s++) {
+            const int* node = take<int>(nns[s]);
+            const int* ptr = take<int>(nns[s] + 1);
+            const int* idx = take<int>(ptr[nns[s]]);
+            for (int k = 0; k < nns[s]; k++)
+                for (int j = ptr[k]; j < ptr[k + 1]; j++) kfs[s]->mFeatVec[(unsigned)node[k]].push_back((unsigned)idx[j]);
+        }
+        const float* sf2 = take<float>(8);
+        const float* ls2 = take<float>(8);
+        KF2.mvScaleFactors.assign(sf2, sf2 + 8);
+        KF2.mvLevelSigma2.assign(ls2, ls2 + 8);
+        KF1.Ow = cv::Mat(3, 1, CV_32F); KF2.tcw = cv::Mat(3, 1, CV_32F); KF2.Rcw = cv::Mat(3, 3, CV_32F);
+        cv::Mat F12(3, 3, CV_32F);
+        for (int i = 0; i < 3; i++) { KF1.Ow.at<float>(i) = tf[4 + i]; KF2.tcw.at<float>(i) = tf[7 + i]; }
+        for (int i = 0; i < 9; i++) { KF2.Rcw.at<float>(i / 3, i % 3) = tf[10 + i]; F12.at<float>(i / 3, i % 3) = tf[19 + i]; }
+        ORBmatcher matcherTri(0.6, true);                       // LocalMapping.cc:225: ORBmatcher matcher(0.6,false) uses checkOri false; true exercises the histogram
+        nTri = matcherTri.SearchForTriangulation(&KF1, &KF2, F12, vMatchedIndices, onlyStereo != 0);
+    }
+
     FILE* o = fopen(argv[2], "wb");
     fwrite(&nmatches, 4, 1, o);
     for (int i = 0; i < nF; i++) {
@@ -115,6 +160,8 @@ int main(int argc, char** argv)
     for (int i = 0; i < n2; i++) { const int v = Cur.mvpMapPointsBird[i] ? (int)Cur.mvpMapPointsBird[i]->mnId : -1; fwrite(&v, 4, 1, o); }
     const int dd = (n1 > 0 && n2 > 0) ? ORBmatcher::DescriptorDistance(Last.mDescriptorsBird, Cur.mDescriptorsBird) : -1;
     fwrite(&dd, 4, 1, o);
+    fwrite(&nTri, 4, 1, o);
+    for (size_t i = 0; i < vMatchedIndices.size(); i++) { const int p[2] = {(int)vMatchedIndices[i].first, (int)vMatchedIndices[i].second}; fwrite(p, 4, 2, o); }
     fclose(o);
     printf("%d projection matches, %d birdview matches, %d birdview landmarks carried over\n", nmatches, nmBird, nmSBM);
     return 0;

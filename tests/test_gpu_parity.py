@@ -333,8 +333,9 @@ def test_cpp_shim(pkg, tmp_path):
 
 def test_cpp_matcher_shim(pkg, tmp_path):
     """cpp/ORBmatcher_b200.cc -- the bodies of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th),
-    BirdviewMatch(const Frame&, const Frame&, ...) and SearchByMatchBird(Frame&, const Frame&, ...) over the C ABI --
-    driven through Frame / MapPoint / MapPointBird objects like Tracking does, against the oracle."""
+    SearchForTriangulation(KF1, KF2, F12, ...), BirdviewMatch(const Frame&, const Frame&, ...) and
+    SearchByMatchBird(Frame&, const Frame&, ...) over the C ABI -- driven through Frame / KeyFrame / MapPoint /
+    MapPointBird objects like Tracking and LocalMapping do, against the oracle."""
     import subprocess
     from helpers import ROOT
     drv = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp", "matcher_driver")
@@ -357,6 +358,12 @@ def test_cpp_matcher_shim(pkg, tmp_path):
         for a in (kps, desc, uR, kp_obs, q["valid"], bad, q["u"], q["v"], q["uR"], q["viewcos"], q["level"], q_obs, q["desc"],
                   k1, d1, hasmp1, k2, d2):
             np.ascontiguousarray(a).tofile(f)
+        # two keyframes for SearchForTriangulation; pose chosen so that the epipole (:663-670) is exactly (cx, cy)
+        t = cases.triangulation_case(1200, 1100, 1241, 376, 74, n_nodes=80)
+        np.array([len(t["k1"]), len(t["k2"]), len(t["fv1"][0]), len(t["fv2"][0]), 0], np.int32).tofile(f)
+        np.concatenate([[1, 1, t["ex"], t["ey"]], [0, 0, 0], [0, 0, 1], np.eye(3).ravel(), t["F12"].ravel()]).astype(np.float32).tofile(f)
+        for a in (t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], *t["fv1"], *t["fv2"], t["sf2"], t["sigma2"]):
+            np.ascontiguousarray(a).tofile(f)
     subprocess.run([drv, str(case), str(out)], check=True, timeout=120)
     res = np.fromfile(out, np.int32)
     nm, mp_of_kp = res[0], res[1:1 + nF]
@@ -365,6 +372,8 @@ def test_cpp_matcher_shim(pkg, tmp_path):
     o += 1 + len(k1)
     nm_sbm, cur_mp = res[o], res[o + 1:o + 1 + len(k2)]
     dd = res[o + 1 + len(k2)]
+    n_tri = res[o + 2 + len(k2)]
+    tri_pairs = res[o + 3 + len(k2):o + 3 + len(k2) + 2 * n_tri].reshape(-1, 2)
     # SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129)
     O = oracle.Frame(kps, desc, grid["min_x"], grid["min_y"], grid["inv_w"], grid["inv_h"], uR)
     valid = (q["valid"] == 1) & (bad == 0)
@@ -384,6 +393,10 @@ def test_cpp_matcher_shim(pkg, tmp_path):
             carried += 1
     assert nm_sbm == carried and np.array_equal(cur_mp, want_cur)
     assert dd == int(np.unpackbits(d1[0] ^ d2[0]).sum())                     # DescriptorDistance (:1647-1663)
+    # SearchForTriangulation(KF1, KF2, F12, vMatchedPairs, bOnlyStereo) (:657-823)
+    n0, pairs0 = oracle.search_for_triangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], t["fv1"], t["fv2"],
+                                                 t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"], False, True)
+    assert n_tri == n0 and n0 > 0 and np.array_equal(tri_pairs, pairs0)
 
 
 def test_cpp_birdview_shim(pkg, tmp_path):
