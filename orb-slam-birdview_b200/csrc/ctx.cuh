@@ -47,6 +47,9 @@ struct Ctx {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;
     long long launches = 0;
+    // largest dynamic shared-memory size already opted into on THIS context's device (cudaFuncSetAttribute is per device,
+    // so the record lives with the context, not in a process- or thread-wide static): FAST pitch 49 / 25, octree, window match, bird select
+    size_t smemOptIn[5] = {0, 0, 0, 0, 0};
 
     // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)
     int nfeatures = 0;

@@ -1269,7 +1269,7 @@ void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned
 {
     if (nCells <= 0 || n <= 0) return;
     const size_t smem = need.bytes();
-    static thread_local size_t configured[2] = {0, 0};
+    size_t* configured = c.smemOptIn;           // [0]: pitch 49, [1]: pitch 25
     const bool small = need.pitch() == FT_PITCH_SMALL;
     if (smem > 48 * 1024 && smem > configured[small]) {
         if (small) cudaFuncSetAttribute(fast_cells_kernel<FT_PITCH_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1301,7 +1301,7 @@ void launch_octree(Ctx& c, int n)
     int maxNodes = 2;
     for (int l = 0; l < g.nlevels; l++) maxNodes = std::max(maxNodes, g.lv[l].maxNodes);
     const size_t smem = octree_smem_bytes(maxNodes);
-    static thread_local size_t configured = 0;
+    size_t& configured = c.smemOptIn[2];
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;

@@ -598,7 +598,7 @@ void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq, int
     constexpr size_t WM_SMEM_MAX = 200 * 1024;
     size_t smem = sizeof(int) * (2 * (size_t)std::max(maxKpCap, 0) + 6 * (size_t)std::max(maxNq, 0));
     if (smem > WM_SMEM_MAX) smem = 0;
-    static thread_local size_t configured = 0;
+    size_t& configured = c.smemOptIn[3];
     if (smem > 48 * 1024 && smem > configured) {
         cudaFuncSetAttribute(window_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_MAX);
         configured = WM_SMEM_MAX;
