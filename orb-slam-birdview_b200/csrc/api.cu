@@ -224,6 +224,33 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             st.resizeSmemRows[l] = rows;
         }
     }
+    // TMA descriptors of the blurred pool (describe_kernel fetches a keypoint's 48 x 39-byte patch with one bulk tensor copy)
+    {
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            c.err = "cuTensorMapEncodeTiled is not available from this driver";
+            return nullptr;
+        }
+        memset(&st.dmaps, 0, sizeof(st.dmaps));
+        for (int l = 0; l < g.nlevels; l++) {
+            const LevelGeom& L = g.lv[l];
+            if (L.w <= 0 || L.h <= 0) continue;
+            const cuuint64_t dims[3] = {(cuuint64_t)(L.pitch - PYR_MARGIN_X), (cuuint64_t)(L.h + PYR_MARGIN_Y), (cuuint64_t)c.maxBatch};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyrBytes};
+            const cuuint32_t box[3] = {DS_TBOX_W, DS_TBOX_H, 1}, estr[3] = {1, 1, 1};
+            const CUresult r = ((EncodeTiled)fn)(&st.dmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c.d_blur + L.off, dims, strides, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS && L.nCells > 0) {      // levels without FAST cells never hold a keypoint
+                c.err = "cuTensorMapEncodeTiled failed for pyramid level " + std::to_string(l) + " (" + std::to_string((int)r) + ")";
+                return nullptr;
+            }
+        }
+    }
     st.nBlurTiles = (int)btiles.size();
     st.nFastCells = (int)(cells.size() / 3);
     auto up = [&](void** dptr, const void* src, size_t bytes) -> bool {
@@ -236,7 +263,8 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
               up((void**)&st.d_ytab, ytab.data(), ytab.size() * sizeof(int4)) &&
               up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4)) &&
               up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4)) &&
-              up((void**)&st.d_resizeTiles, rtiles.data(), rtiles.size() * sizeof(int4));
+              up((void**)&st.d_resizeTiles, rtiles.data(), rtiles.size() * sizeof(int4)) &&
+              up((void**)&st.d_dmaps, &st.dmaps, sizeof(st.dmaps));
     cudaStreamSynchronize(c.stream);   // host vectors go out of scope
     if (!ok) { c.err = "cudaMalloc(shape tables) failed"; return nullptr; }
     auto res = c.shapes.emplace(std::make_pair(w, h), st);
@@ -473,7 +501,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles);
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.evFork) cudaEventDestroy(c.evFork);

@@ -14,6 +14,8 @@ struct ShapeTables {
     int4* d_cells = nullptr;    // FAST cells of all levels, 3 x int4 each: {x0|y0<<16, x1|y1<<16, level, order}, {level offset, pitch, candOff, candCap}, {2^32/nw+1, 2^32/npr+1, -, -}
     int4* d_blurTiles = nullptr;  // blur tiles of all levels: {level, x0, y0, 0}, 128 x 32 pixels each
     int nBlurTiles = 0;
+    DescribeMaps dmaps;         // TMA descriptors of this context's blurred pool for this shape's levels (host copy)
+    CUtensorMap* d_dmaps = nullptr;   // the same in global memory (64-byte aligned): what describe_kernel hands to the TMA unit
     int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1, two int4 each: {x0, y0, srcRow0, rows}, {srcCol0, vectors, 2^16/vectors+1, 0}
     int resizeTileBase[MAX_LEVELS + 1] = {0};
     int resizeTileCount[MAX_LEVELS] = {0};

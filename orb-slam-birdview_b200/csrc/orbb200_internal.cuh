@@ -1,5 +1,6 @@
 // Internal declarations shared by the CUDA translation units of liborbb200.so.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -61,6 +62,14 @@ struct Geom {
     int totalCells;
     LevelGeom lv[MAX_LEVELS];
 };
+
+// TMA descriptors of the blurred pyramid pool, one per level: 3-D u8 tensors {row bytes, rows, images} whose boxes are the
+// 64 x 39-byte windows describe_kernel fetches around a keypoint.  The 39 x 39 patch starts at an arbitrary column, but
+// a box must start on a 16-byte boundary of the row (measured: an unaligned inner coordinate raises "illegal
+// instruction", tools/ubench/tma_box.cu), so the box starts at the patch column rounded down to 16 and is 15 + 39 -> 64
+// bytes wide.
+constexpr int DS_TBOX_W = 64, DS_TBOX_H = 39;
+struct DescribeMaps { CUtensorMap m[MAX_LEVELS]; };
 
 // Device-side frame (keypoints + descriptors + 64x48 CSR grid).
 struct FrameDev {
