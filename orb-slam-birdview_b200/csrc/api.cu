@@ -224,7 +224,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             st.resizeSmemRows[l] = rows;
         }
     }
-    // TMA descriptors of the blurred pool (describe_kernel fetches a keypoint's 48 x 39-byte patch with one bulk tensor copy)
+    // TMA descriptors of the blurred pool (describe_kernel fetches a keypoint's 64 x 39-byte box with one bulk tensor copy)
     {
         typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -236,6 +236,17 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             return nullptr;
         }
         memset(&st.dmaps, 0, sizeof(st.dmaps));
+        memset(&st.rmaps, 0, sizeof(st.rmaps));
+        for (int l = 1; l < g.nlevels; l++) {             // resize level l stages a window of level l-1
+            const LevelGeom& S = g.lv[l - 1];
+            if (S.w <= 0 || S.h <= 0 || st.resizeTileCount[l] == 0 || st.resizeSmemPitch[l] > 256 || st.resizeSmemRows[l] > 256) continue;
+            const cuuint64_t dims[3] = {(cuuint64_t)(S.pitch - PYR_MARGIN_X), (cuuint64_t)(S.h + PYR_MARGIN_Y), (cuuint64_t)c.maxBatch};
+            const cuuint64_t strides[2] = {(cuuint64_t)S.pitch, (cuuint64_t)g.pyrBytes};
+            const cuuint32_t box[3] = {(cuuint32_t)st.resizeSmemPitch[l], (cuuint32_t)st.resizeSmemRows[l], 1}, estr[3] = {1, 1, 1};
+            st.resizeMapOk[l] = ((EncodeTiled)fn)(&st.rmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c.d_pyr + S.off, dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
         for (int l = 0; l < g.nlevels; l++) {
             const LevelGeom& L = g.lv[l];
             if (L.w <= 0 || L.h <= 0) continue;
@@ -264,7 +275,8 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
               up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4)) &&
               up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4)) &&
               up((void**)&st.d_resizeTiles, rtiles.data(), rtiles.size() * sizeof(int4)) &&
-              up((void**)&st.d_dmaps, &st.dmaps, sizeof(st.dmaps));
+              up((void**)&st.d_dmaps, &st.dmaps, sizeof(st.dmaps)) &&
+              up((void**)&st.d_rmaps, &st.rmaps, sizeof(st.rmaps));
     cudaStreamSynchronize(c.stream);   // host vectors go out of scope
     if (!ok) { c.err = "cudaMalloc(shape tables) failed"; return nullptr; }
     auto res = c.shapes.emplace(std::make_pair(w, h), st);
@@ -501,7 +513,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps);
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps); cudaFree(kv.second.d_rmaps);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.evFork) cudaEventDestroy(c.evFork);

@@ -15,6 +15,9 @@ struct ShapeTables {
     int4* d_blurTiles = nullptr;  // blur tiles of all levels: {level, x0, y0, 0}, 128 x 32 pixels each
     int nBlurTiles = 0;
     DescribeMaps dmaps;         // TMA descriptors of this context's blurred pool for this shape's levels (host copy)
+    DescribeMaps rmaps;         // TMA descriptors of the pyramid pool, entry l = source level l-1 with the staging box of resize level l
+    CUtensorMap* d_rmaps = nullptr;
+    bool resizeMapOk[MAX_LEVELS] = {false};
     CUtensorMap* d_dmaps = nullptr;   // the same in global memory (64-byte aligned): what describe_kernel hands to the TMA unit
     int4* d_resizeTiles = nullptr;  // resize tiles of levels >= 1, two int4 each: {x0, y0, srcRow0, rows}, {srcCol0, vectors, 2^16/vectors+1, 0}
     int resizeTileBase[MAX_LEVELS + 1] = {0};

@@ -78,14 +78,17 @@ __device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t se
 template <bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
                                                             const int2* __restrict__ xtab, const int4* __restrict__ ytab,
-                                                            const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows)
+                                                            const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows,
+                                                            const CUtensorMap* __restrict__ srcMap)
 {
-    // The source footprint of the tile is staged in shared memory with coalesced 16-byte loads, so the
-    // interpolation reads never wait on global memory.  Every table entry the CTA needs (tile window, the rows'
-    // vertical coefficients, the lane's four column entries) is requested before the staging loop, so that the
-    // dependent-load chain in front of the first output row is tile -> {window, coefficients} -> staged bytes.
-    extern __shared__ __align__(16) uint8_t rsSmem[];
+    // The source footprint of the tile is staged in shared memory, so the interpolation reads never wait on global
+    // memory: one TMA box (cp.async.bulk.tensor.3d of smemPitch x smemRows bytes from the source level, its first column
+    // is 16-byte aligned by construction) when the box fits TMA's 256-byte inner limit (srcMap != nullptr), else
+    // coalesced 16-byte loads.  Every table entry the CTA needs (tile window, the rows' vertical coefficients, the lane's
+    // four column entries) is requested before the wait.
+    extern __shared__ __align__(128) uint8_t rsSmem[];
     __shared__ int4 sY[RS_ROWS];
+    __shared__ __align__(8) uint64_t sBar;
     const int4 t = __ldg(tiles + 2 * blockIdx.x);       // {x0, y0, first staged source row, rows}
     const int4 u = __ldg(tiles + 2 * blockIdx.x + 1);   // {first staged source column, vectors per row, 2^16/vectors + 1, -}
     const int img = blockIdx.y;
@@ -99,7 +102,20 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; i++) xt[i] = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
     if (tid < RS_ROWS) sY[tid] = __ldg(ytab + dst.ytabOff + min(y0 + tid, dst.h - 1));
-    {
+    if (srcMap != nullptr) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sBar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(smemPitch * smemRows) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(rsSmem)), "l"(reinterpret_cast<uint64_t>(srcMap)), "r"(cx0), "r"(ry0), "r"(img), "r"(bar)
+                         : "memory");
+        }
+        __syncthreads();                                                  // the barrier is initialised (and sY written) for everyone
+        asm volatile("{\n\t.reg .pred p;\n\tRSWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RSDONE;\n\tbra RSWAIT;\n\tRSDONE:\n\t}"
+                     :: "r"(bar), "r"(0) : "memory");
+    } else {
         // floor(i / nvec) by a 16-bit reciprocal: exact while i * nvec < 2^16 (i < 64 rows x 16 vectors)
         const unsigned rcp = (unsigned)u.z;
         const uint8_t* Sw = S + (size_t)ry0 * src.pitch + cx0;
@@ -109,8 +125,8 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
             *reinterpret_cast<uint4*>(rsSmem + r * smemPitch + 16 * k) =
                 *reinterpret_cast<const uint4*>(Sw + (unsigned)(r * src.pitch + 16 * k));
         }
+        __syncthreads();
     }
-    __syncthreads();
     // warp index through a shuffle: the output row and everything derived from it is warp-uniform for the compiler
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (x4 >= dst.w) return;
@@ -1257,11 +1273,11 @@ void launch_pyramid(Ctx& c, int n)
         if (st.resizeNarrow[l])
             resize_kernel<true><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
                                                                      st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
-                                                                     st.resizeSmemPitch[l], st.resizeSmemRows[l]);
+                                                                     st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
         else
             resize_kernel<false><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
                                                                       st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
-                                                                      st.resizeSmemPitch[l], st.resizeSmemRows[l]);
+                                                                      st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
         c.launches++;
     }
     border_kernel<<<dim3(g.nlevels * BD_CHUNKS, n), 128, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
