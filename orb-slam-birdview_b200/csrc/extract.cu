@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 // with fewer instructions per pixel: 0.44 -> 0.53 ms per step, slower.)
 // ---------------------------------------------------------------------------------------------------
 #ifndef ORBB200_RS_THREADS
-#define ORBB200_RS_THREADS 128
+#define ORBB200_RS_THREADS 64
 #endif
 constexpr int RS_THREADS = ORBB200_RS_THREADS;  // one CTA per 128 x RS_ROWS output tile; warp w owns RS_RPW consecutive rows of it
 constexpr int RS_RPW = RS_ROWS / (RS_THREADS / 32);
