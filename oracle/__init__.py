@@ -494,3 +494,115 @@ def bird_extract(img, mask=None, nfeatures=2000):
     kps, desc = np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8)
     n = lib().oracle_bird_extract(_p(img), _p(mask), w, h, img.strides[0], 0 if mask is None else mask.strides[0], nfeatures, _p(kps), _p(desc), cap)
     return kps[:n].copy(), desc[:n].copy()
+
+
+# ---- oracle/_ref: the REFERENCE's own ORBextractor.cc, compiled unmodified (oracle/ref_standin/Makefile) -----------
+REF_DIR = os.path.join(_HERE, "_ref")
+REF_SRC = os.environ.get("ORB_REFERENCE_ROOT", "/root/reference")
+_REF_VARIANTS = {"glibc": "libref_orbextractor.so", "bump": "libref_orbextractor_bump.so", "nofma": "libref_orbextractor_nofma.so"}
+
+
+def build_ref(force=False):
+    """Build oracle/_ref/*.so from the reference sources where they lie.  Needs /root/reference (this container);
+    on the GPU box the prebuilt files travel with the snapshot.  Returns True when the libraries exist."""
+    have_src = os.path.exists(os.path.join(REF_SRC, "src", "ORBextractor.cc"))
+    if have_src:
+        cmd = ["make", "-s", "-C", os.path.join(_HERE, "ref_standin"), f"REF={REF_SRC}"]
+        if force:
+            cmd.insert(1, "-B")
+        subprocess.run(cmd, check=True)
+    return ref_available()
+
+
+def ref_available(variant="glibc"):
+    return os.path.exists(os.path.join(REF_DIR, _REF_VARIANTS[variant]))
+
+
+_ref_libs = {}
+
+
+def ref_lib(variant="glibc"):
+    if variant in _ref_libs:
+        return _ref_libs[variant]
+    path = os.path.join(REF_DIR, _REF_VARIANTS[variant])
+    if not os.path.exists(path):
+        build_ref()
+    L = C.CDLL(path)
+    vp, sz = C.c_void_p, C.c_size_t
+    sig = {
+        "ref_is_bump_alloc": (C.c_int, []),
+        "ref_extractor_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]),
+        "ref_extractor_destroy": (None, [vp]),
+        "ref_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, vp, C.c_int]),
+        "ref_extractor_levels": (C.c_int, [vp]),
+        "ref_extractor_scale_table": (C.c_int, [vp, C.c_int, vp]),
+        "ref_extractor_features_per_level": (C.c_int, [vp, vp]),
+        "ref_extractor_umax": (C.c_int, [vp, vp]),
+        "ref_extractor_level_size": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "ref_extractor_level_image": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
+        "ref_distribute_octree": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _ref_libs[variant] = L
+    return L
+
+
+class RefExtractor:
+    """ORB_SLAM2::ORBextractor of the reference itself (src/ORBextractor.cc compiled unmodified).
+    variant: "glibc" = the real binary's allocator (heap-address tie-break of ORBextractor.cc:684 as glibc gives it,
+    FMA contraction on like a -march=native build); "bump" = monotone operator new, no contraction (must equal
+    oracle.Extractor byte for byte); "nofma" = glibc allocator, no contraction."""
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, variant="glibc"):
+        self._L = ref_lib(variant)
+        self.nfeatures, self.nlevels, self.variant = nfeatures, nlevels, variant
+        self._h = self._L.ref_extractor_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_extractor_destroy(self._h)
+            self._h = None
+
+    def __call__(self, img):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = self.nfeatures * 2 + 4096
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = self._L.ref_extract(self._h, C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError("ref_extract: capacity too small")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def features_per_level(self):
+        out = np.empty(self.nlevels, np.int32)
+        self._L.ref_extractor_features_per_level(self._h, _p(out))
+        return out
+
+    def scale_table(self, which=0):
+        out = np.empty(self.nlevels, np.float32)
+        self._L.ref_extractor_scale_table(self._h, which, _p(out))
+        return out
+
+    def scale_factors(self):
+        return self.scale_table(0)
+
+    def umax(self):
+        out = np.empty(16, np.int32)
+        self._L.ref_extractor_umax(self._h, _p(out))
+        return out
+
+    def level_image(self, level, border=0):
+        w, h = C.c_int(), C.c_int()
+        self._L.ref_extractor_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.empty((h.value + 2 * border, w.value + 2 * border), np.uint8)
+        if out.size:
+            self._L.ref_extractor_level_image(self._h, level, border, _p(out), out.strides[0])
+        return out
+
+    def distribute_octree(self, xyr, minX, maxX, minY, maxY, N):
+        xyr = _c(xyr, np.int32).reshape(-1, 3)
+        out = np.empty((max(len(xyr), 1), 3), np.int32)
+        n = self._L.ref_distribute_octree(self._h, _p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), len(out))
+        return out[:n].copy()

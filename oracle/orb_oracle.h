@@ -8,16 +8,24 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use
  * this library; the product (orb-slam-birdview_b200/csrc) never links or calls it.
  *
- * Parity status: the reference ships no tests, golden vectors or fixtures ("parity unpinned" by the
- * reference itself) and cannot be compiled here (needs OpenCV/Eigen/Pangolin SDKs).  The pins are
- * (1) each primitive vs cv2 4.13, (2) the full extractor vs an independent Python composition of cv2
- * primitives (tests/ref_py), (3) matchers vs literal Python transcriptions.
+ * Parity status: the reference ships no tests, golden vectors or fixtures.  The pins are
+ * (0) EXTRACTOR: the reference's own src/ORBextractor.cc compiled unmodified (oracle/_ref, built by
+ *     oracle/ref_standin/Makefile against a stand-in for the OpenCV container types; its arithmetic primitives are the
+ *     cv2-pinned ones below) -- with a monotone allocator its output equals this oracle byte for byte on every tested
+ *     input (tests/test_oracle_ref.py);
+ * (1) each OpenCV primitive vs cv2 4.13, (2) the full extractor vs an independent Python composition of cv2
+ * primitives (tests/ref_py), (3) matchers vs literal Python transcriptions (the matcher sources need Eigen/DBoW2/g2o
+ * headers plus the whole Frame/KeyFrame/MapPoint graph: see DESIGN.md section 2 for what is compiled from them).
  *
  * Documented divergences from "the reference binary":
  *   - DistributeOctTree sorts pair<int,ExtractorNode*> (src/ORBextractor.cc:684): size ties are broken
  *     by heap address.  Oracle rule: among equal sizes the most recently created node is expanded first
- *     (what monotonically increasing allocation addresses give).
- *   - Float expressions are evaluated without FMA contraction (-ffp-contract=off).
+ *     (what monotonically increasing allocation addresses give: proven by the "bump" build of oracle/_ref).
+ *     Under glibc malloc the real binary reuses freed list nodes (tcache), its tie order follows the heap's history
+ *     and its output is not even a function of the image: two runs on the same image share 98-99 % of their keypoints,
+ *     the same figure as reference-vs-oracle (profiles/r2_ref_tie_report.json).
+ *   - Float expressions are evaluated without FMA contraction (-ffp-contract=off); a contracting build of the
+ *     reference differs in ~1e-5 of the descriptors (same report).
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

@@ -1,0 +1,2 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY: stand-in for <opencv2/imgproc/imgproc.hpp>, see ../../cv_standin.hpp */
+#include "../../cv_standin.hpp"
