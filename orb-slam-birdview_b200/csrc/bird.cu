@@ -1018,9 +1018,9 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, bool withMask)
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
                       p->d_candCount, n);
     const size_t smem = (size_t)BV_SORT_CAP * 12;      // keys + responses + two u16 stopper lists
-    if (smem > c.smemOptIn[4]) {
-        cudaFuncSetAttribute(bird_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        c.smemOptIn[4] = smem;
+    if (smem > 48 * 1024 && smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel, SMEM_BIRD_SELECT)) {
+        c.err = "bird_select_kernel: shared memory";
+        return ORBB200_ERR_CUDA;
     }
     bird_select_kernel<<<dim3(BV_LEVELS, n), SEL_THREADS, smem, c.stream>>>(g, p->d_pyr, withMask ? p->d_mask : nullptr, p->d_cand, p->d_candCount,
                                                                           p->d_lvlKp, p->d_lvlCount, c.d_status);

@@ -1,6 +1,7 @@
 // Context object behind orbb200_ctx: parameters, per-shape geometry cache, HBM-resident pools.
 #pragma once
 #include <map>
+#include <mutex>
 #include <utility>
 
 #include "orbb200_internal.cuh"
@@ -32,6 +33,28 @@ struct ShapeTables {
 
 struct WinJob;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (device, kernel) and SETS the limit, so a per-context record of
+// "what I asked for" lets a second context on the same GPU lower the first one's limit.  Each kernel that may need
+// more than 48 KB is instead raised ONCE per device to the device's opt-in maximum; the record is process-wide.
+// Returns that maximum (bytes) or 0 after a CUDA error.  slot: one small integer per kernel instantiation.
+enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_SLOTS };
+inline size_t ensure_max_dynamic_smem(int device, const void* kernel, int slot)
+{
+    static std::mutex mu;
+    static size_t limit[64][SMEM_SLOTS] = {};
+    if (device < 0 || device >= 64) return 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (limit[device][slot]) return limit[device][slot];
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess || optin <= 0) return 0;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 0;
+    const int dyn = optin - (int)fa.sharedSizeBytes;        // the opt-in maximum covers static + dynamic shared memory
+    if (dyn <= 0 || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) { cudaGetLastError(); return 0; }
+    limit[device][slot] = (size_t)dyn;
+    return (size_t)dyn;
+}
+
 // Cached device-side descriptors of one batched step (orbb200_stereo_step_device); the leading fields are
 // the cache key.
 struct StepPlan {
@@ -52,9 +75,6 @@ struct Ctx {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;
     long long launches = 0;
-    // largest dynamic shared-memory size already opted into on THIS context's device (cudaFuncSetAttribute is per device,
-    // so the record lives with the context, not in a process- or thread-wide static): FAST pitch 49 / 25, octree, window match, bird select
-    size_t smemOptIn[5] = {0, 0, 0, 0, 0};
 
     // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)
     int nfeatures = 0;

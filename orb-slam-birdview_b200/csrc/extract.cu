@@ -1321,12 +1321,10 @@ void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned
 {
     if (nCells <= 0 || n <= 0) return;
     const size_t smem = need.bytes();
-    size_t* configured = c.smemOptIn;           // [0]: pitch 49, [1]: pitch 25
     const bool small = need.pitch() == FT_PITCH_SMALL;
-    if (smem > 48 * 1024 && smem > configured[small]) {
-        if (small) cudaFuncSetAttribute(fast_cells_kernel<FT_PITCH_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else cudaFuncSetAttribute(fast_cells_kernel<FT_PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[small] = smem;
+    if (smem > 48 * 1024) {      // a request beyond the device's opt-in maximum fails at the launch below (cudaGetLastError)
+        if (small) ensure_max_dynamic_smem(c.device, (const void*)fast_cells_kernel<FT_PITCH_SMALL>, SMEM_FAST_SMALL);
+        else ensure_max_dynamic_smem(c.device, (const void*)fast_cells_kernel<FT_PITCH>, SMEM_FAST);
     }
     dim3 grid(nCells, n);
     if (small)
@@ -1353,11 +1351,7 @@ void launch_octree(Ctx& c, int n)
     int maxNodes = 2;
     for (int l = 0; l < g.nlevels; l++) maxNodes = std::max(maxNodes, g.lv[l].maxNodes);
     const size_t smem = octree_smem_bytes(maxNodes);
-    size_t& configured = c.smemOptIn[2];
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel, SMEM_OCTREE);
     dim3 grid(n, g.nlevels);
     octree_kernel<<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
     c.launches++;

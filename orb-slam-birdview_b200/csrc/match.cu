@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
 {
     __shared__ int sCnt[GRID_CELLS];
     __shared__ int warpTot[32];
+    __shared__ int sTotal;                  // keypoints that fell inside the grid (<= n: PosInGrid rejects the rest)
     const FrameDev F = frames[blockIdx.x];
     const int n = frame_count(F);
     const int tid = threadIdx.x;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
     int ex = (wid ? warpTot[wid - 1] : 0) + x - s;
 #pragma unroll
     for (int k = 0; k < 3; k++) { F.cellStart[tid * 3 + k] = ex; sCnt[tid * 3 + k] = ex; ex += v[k]; }
-    if (tid == 1023) F.cellStart[GRID_CELLS] = ex;
+    if (tid == 1023) { F.cellStart[GRID_CELLS] = ex; sTotal = ex; }
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         const int cid = grid_cell_of(F, F.kps[i]);
@@ -190,7 +191,9 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
     }
     __syncthreads();
     // position-sorted copy of what a window scan needs of each keypoint (no index -> keypoint indirection in the scan)
-    for (int k = tid; k < n; k += 1024) {
+    // (only the sTotal items the CSR holds: cellItems beyond them is unwritten memory)
+    const int nItems = sTotal;
+    for (int k = tid; k < nItems; k += 1024) {
         const int idx = F.cellItems[k];
         const orbb200_kp_t kp = F.kps[idx];
         F.cellKp[k] = make_int4(__float_as_int(kp.x), __float_as_int(kp.y), kp.octave, idx);
@@ -598,11 +601,7 @@ void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq, int
     constexpr size_t WM_SMEM_MAX = 200 * 1024;
     size_t smem = sizeof(int) * (2 * (size_t)std::max(maxKpCap, 0) + 6 * (size_t)std::max(maxNq, 0));
     if (smem > WM_SMEM_MAX) smem = 0;
-    size_t& configured = c.smemOptIn[3];
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(window_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WM_SMEM_MAX);
-        configured = WM_SMEM_MAX;
-    }
+    if (smem > 48 * 1024 && smem > ensure_max_dynamic_smem(c.device, (const void*)window_match_kernel, SMEM_WINDOW_MATCH)) smem = 0;
     if (maxNq > 0) {
         dim3 grid((maxNq + WC_THREADS - 1) / WC_THREADS, njobs);
         window_cands_kernel<<<grid, WC_THREADS, 0, c.stream>>>(d_jobs);

@@ -203,6 +203,34 @@ def test_features_in_area(pkg):
         assert F.GetFeaturesInArea(x, y, r, lo, hi).tolist() == O.features_in_area(x, y, r, lo, hi).tolist()
 
 
+@pytest.mark.parametrize("shift", [(-90.0, -35.0), (60.0, 25.0)])
+def test_keypoints_outside_the_lookup_grid(pkg, shift):
+    """Undistorted keypoints may fall outside the 64x48 grid (src/Frame.cc:549-559 PosInGrid returns false): they are in no
+    cell, GetFeaturesInArea never returns them and the searches never match them (grid_build_kernel read
+    unwritten cellItems beyond the in-grid count)."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    kps, desc, uR, grid = cases.frame_case(1800, 1241, 376, 21, stereo_frac=0.3)
+    grid = dict(grid, min_x=np.float32(shift[0]), min_y=np.float32(shift[1]))      # mnMinX/mnMinY of a distorted camera
+    if shift[0] > 0:    # a third of the keypoints left of / above the grid, some beyond its right/bottom edge
+        kps["x"][::7] += np.float32(60.0)
+    F, O = _frames(pkg, ctx, kps, desc, grid, uR)
+    rng = np.random.default_rng(22)
+    seen = set()
+    for _ in range(40):
+        x, y = rng.uniform(-60, 1300), rng.uniform(-60, 430)
+        r = float(rng.choice([10.0, 37.5, 120.0, 400.0]))
+        got = F.GetFeaturesInArea(x, y, r, -1, -1).tolist()
+        assert got == O.features_in_area(x, y, r, -1, -1).tolist()
+        seen.update(got)
+    assert 0 < len(seen) < len(kps)
+    q = cases.projection_queries(kps, desc, uR, 1241, 376, 2500, 23)
+    m = pkg.ORBmatcher(ctx, 0.8)
+    nm, bi, bd, qk = m.SearchByProjection(F, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"], q["desc"], q["obs_pos"], None, 3.0)
+    nm0, bi0, bd0, qk0 = oracle.search_by_projection(O, cases.SCALE_FACTORS, q["valid"], q["u"], q["v"], q["uR"], q["level"], q["viewcos"],
+                                                     q["desc"], q["obs_pos"], None, 3.0, 0.8)
+    assert nm == nm0 and nm > 0 and np.array_equal(bi, bi0) and np.array_equal(qk, qk0)
+
+
 @pytest.mark.parametrize("n,nq,w,h,seed,th,ratio", [(2000, 3000, 1241, 376, 11, 1.0, 0.8), (2000, 3000, 1241, 376, 12, 3.0, 0.8),
                                                      (500, 700, 620, 188, 13, 1.0, 0.8), (300, 2500, 200, 150, 14, 4.0, 0.9)])
 def test_search_by_projection(pkg, n, nq, w, h, seed, th, ratio):
