@@ -436,6 +436,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess)
         return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
+    if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(2, atoi(e)));
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
     c.scale.resize(nlevels); c.sigma2.resize(nlevels); c.invScale.resize(nlevels); c.invSigma2.resize(nlevels); c.quota.resize(nlevels);

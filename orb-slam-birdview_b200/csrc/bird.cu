@@ -62,12 +62,19 @@ struct BirdPlan {
     orbb200_kp_t* d_kps = nullptr; orbb200_kp_t* d_kps2 = nullptr; uint8_t* d_desc = nullptr;
     int32_t* d_counts = nullptr; int32_t* d_counts2 = nullptr;
     float* d_pts = nullptr;
+    int* d_slow = nullptr;           // corners bird_subpix5_kernel hands to the generic kernel ([batch][kpPerImg] slots)
+    int* d_list[2] = {nullptr, nullptr};   // corners continuing in the next phase (ping-pong)
+    float* d_pts0 = nullptr;         // their start points
+    int* d_iters = nullptr;          // and iteration counts
 };
 
 struct BirdState {
     std::map<std::tuple<int, int, int>, BirdPlan*> plans;
     float* d_winMask = nullptr;      // cornerSubPix window weights of the last (win_w, win_h)
-    int* d_work = nullptr;           // work counter of the persistent cornerSubPix kernel
+    double* d_winMaskD = nullptr;    // the same values widened to double (what the reference multiplies with)
+    int* d_work = nullptr;           // work counter of the generic persistent cornerSubPix kernel
+    int* d_work5 = nullptr;          // counters of the phased 5x5 form: [phases] heads, [phases] list lengths, hand-over count, generic head
+    size_t workInts = 0;
     int winW = -1, winH = -1;
 };
 
@@ -665,10 +672,12 @@ constexpr int SP_THREADS = 64;
 __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
                                                                  int rows, float* __restrict__ pts, int ptsPerImg, int nImages,
                                                                  const int32_t* __restrict__ counts, int nFixed, const float* __restrict__ winMask,
-                                                                 int winW, int winH, int maxIters, double eps, int* __restrict__ nextWork)
+                                                                 int winW, int winH, int maxIters, double eps, int* __restrict__ nextWork,
+                                                                 const int* __restrict__ workList, const int* __restrict__ workListCount)
 {
+    // workList != nullptr: only the listed (image, corner) slots (what bird_subpix5_kernel handed over)
     const int win_w = winW * 2 + 1, win_h = winH * 2 + 1, bw = win_w + 2;
-    const int totalSlots = nImages * ptsPerImg;
+    const int totalSlots = workList ? *workListCount : nImages * ptsPerImg;
     float buf[(2 * BV_MAX_WIN + 3) * (2 * BV_MAX_WIN + 3)];
     const uint8_t* src = nullptr;
     float* P = nullptr;
@@ -677,8 +686,9 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const ui
     // next valid (image, corner) slot, or false when the work is exhausted
     auto fetch = [&]() -> bool {
         while (true) {
-            const int w = atomicAdd(nextWork, 1);
+            int w = atomicAdd(nextWork, 1);
             if (w >= totalSlots) return false;
+            if (workList) w = workList[w];
             const int img = w / ptsPerImg, i = w - img * ptsPerImg;
             if (i >= (counts ? counts[img] : nFixed)) continue;
             src = imgs + (size_t)img * imgStrideBytes;
@@ -725,6 +735,219 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const ui
             if (fabsf(__fsub_rn(cIx, cTx)) > winW || fabsf(__fsub_rn(cIy, cTy)) > winH) { cIx = cTx; cIy = cTy; }
             P[0] = cIx; P[1] = cIy;
             active = fetch();
+        }
+    }
+}
+
+// ---- cornerSubPix, fast form for the window the reference uses (Size(5,5): 11x11 gradient window, 13x13 samples) ----
+// Measured on B200 (tools/ubench/fp64.cu): DADD / DMUL issue at ~60 lanes/clk/SM (17 T/s), a dependent DADD takes 8 cycles,
+// F2F.F64.F32 is free beside them, F2F.F32.F64 runs at ~16 lanes/clk/SM.  One corner-iteration needs 121 x (10 DMUL + 7 DADD)
+// + 169 DMUL = 2226 FP64-pipe instructions, i.e. ~1190 SM-cycles per warp of 32 corners: the floor of this kernel.  The
+// generic kernel above ran at 21 % of the FP64 pipe (ncu: XU pipe 45 % busy with I2F.U8 conversions, 18 of 32 lanes active,
+// long-scoreboard stalls on the thread-local sample window).  This form removes all three:
+//   * a 24x28-byte source patch around the current point is staged in shared memory (cooperatively, aligned words); a
+//     window that leaves it asks for a new patch around the new point (corners on straight edges jump many pixels per
+//     iteration); only a patch that is not inside the image sends the corner to the generic kernel (`slowList`);
+//   * bytes become floats with PRMT + FADD (0x4B0000bb - 2^23), not I2F;
+//   * the 13x13 sample window is never stored: rows stream through registers (two source rows, three sample rows) while the
+//     five double sums advance in the reference's element order;
+//   * corners need between 2 and 40 iterations, so a lane keeps a corner for at most `budget` iterations per turn and then
+//     queues it for the next launch ("phase"): the tail of a launch is at most `budget` iterations long, and the lanes of a
+//     warp stay in step.  ceil(maxIters / budget) launches finish every corner.
+constexpr int S5_THREADS = 128;
+constexpr int S5_WIN = 5;                           // half window
+constexpr int S5_PW = 7, S5_PH = 24;                // patch: 7 words x 24 rows
+constexpr int S5_STRIDE = S5_PW * S5_PH + 1;        // words per thread (odd: bank spread; the pad word absorbs the 5th-word over-read)
+constexpr int S5_BUDGET = 8;
+
+__device__ __forceinline__ float s5_byte(unsigned w, int k)
+{
+    // exact (float)byte: 0x4B0000bb is 2^23 + bb
+    const unsigned sel = k == 0 ? 0x7440u : k == 1 ? 0x7441u : k == 2 ? 0x7442u : 0x7443u;
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.f);
+}
+
+struct S5Args {
+    const uint8_t* imgs; size_t imgStrideBytes; int pitch, cols, rows;
+    float* pts;                  // [nImages][ptsPerImg][2]: start point in, current / final point out
+    float* pts0;                 // start points (cT) of corners that take more than one turn
+    int* iters;                  // iterations done so far by those corners
+    int ptsPerImg, nImages;
+    const int32_t* counts; int nFixed;
+    const double* winMaskD; int maxIters; double eps;
+    const int* listIn; const int* listInCount;      // this phase's corners (nullptr: every slot, first phase)
+    int* head;                                       // work counter of this launch
+    int* listOut; int* listOutCount;                 // corners that used up their budget
+    int* slowList; int* slowCount;                   // corners for the generic kernel
+};
+
+__global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Args A)
+{
+    extern __shared__ unsigned sPatch[];            // [S5_THREADS][S5_STRIDE]
+    __shared__ double sMask[121];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 121) sMask[tid] = A.winMaskD[tid];
+    __syncthreads();
+    unsigned* myPatch = sPatch + (size_t)tid * S5_STRIDE;
+    unsigned* warpPatch = sPatch + (size_t)(tid - lane) * S5_STRIDE;
+    const bool first = A.listIn == nullptr;
+    const int totalWork = first ? A.nImages * A.ptsPerImg : *A.listInCount;
+    const int pitch = A.pitch, cols = A.cols, rows = A.rows;
+    float* P = nullptr;
+    float cTx = 0, cTy = 0, cIx = 0, cIy = 0;
+    int iter = 0, turn = 0, X0 = 0, Y0 = 0, slot = -1, img = 0;
+    size_t srcOff = 0;                              // byte offset of the patch origin from imgs
+    bool active = false, exhausted = false, stage = false;
+
+    // new patch around (cIx, cIy); false: it would not lie inside the image
+    auto place_patch = [&]() -> bool {
+        const float fxf = floorf(cIx), fyf = floorf(cIy);
+        // columns [fx-11 rounded down to 4, +28), rows [fy-11, +24)
+        if (!(fxf >= 14.f && fxf <= (float)(cols - 17) && fyf >= 11.f && fyf <= (float)(rows - 13))) return false;
+        X0 = ((int)fxf - 11) & ~3; Y0 = (int)fyf - 11;
+        srcOff = (size_t)img * A.imgStrideBytes + (size_t)Y0 * pitch + X0;
+        return true;
+    };
+    auto to_generic = [&]() {                       // exact fallback: restart this corner from cT in the generic kernel
+        P[0] = cTx; P[1] = cTy;
+        A.slowList[atomicAdd(A.slowCount, 1)] = slot;
+        active = false;
+    };
+
+    while (true) {
+        // ---- refill: lanes without a corner fetch one; the warp stages the patches asked for ----
+        if (!active && !exhausted) {
+            while (true) {
+                int w = atomicAdd(A.head, 1);
+                if (w >= totalWork) { exhausted = true; break; }
+                if (!first) w = A.listIn[w];
+                img = w / A.ptsPerImg;
+                const int i = w - img * A.ptsPerImg;
+                if (first && i >= (A.counts ? A.counts[img] : A.nFixed)) continue;
+                slot = w;
+                P = A.pts + (size_t)w * 2;
+                cIx = P[0]; cIy = P[1];
+                if (first) { cTx = cIx; cTy = cIy; iter = 0; }
+                else { cTx = A.pts0[2 * (size_t)w]; cTy = A.pts0[2 * (size_t)w + 1]; iter = A.iters[w]; }
+                turn = 0; active = true;
+                if (!place_patch()) { to_generic(); continue; }
+                stage = true;
+                break;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, stage);
+        stage = false;
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const size_t off = __shfl_sync(0xffffffffu, (unsigned long long)srcOff, l);
+            const uint8_t* base = A.imgs + off;
+            unsigned* dst = warpPatch + (size_t)l * S5_STRIDE;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int idx = lane + 32 * k;
+                if (idx < S5_PW * S5_PH) {
+                    const int r = idx / S5_PW, wcol = idx - r * S5_PW;
+                    dst[idx] = __ldg(reinterpret_cast<const unsigned*>(base + (size_t)r * pitch) + wcol);
+                }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (!active) continue;
+
+        // ---- one iteration of cornerSubPix for this lane's corner ----
+        const float centerx = __fsub_rn(cIx, 6.f), centery = __fsub_rn(cIy, 6.f);      // (13 - 1) * 0.5f
+        const float fpx = floorf(centerx), fpy = floorf(centery);
+        const int dx = (int)fpx - X0, dy = (int)fpy - Y0;
+        if (!(dx >= 0 && dx <= 14 && dy >= 0 && dy <= 10)) {      // window left the staged patch (also NaN)
+            if (place_patch()) stage = true; else to_generic();
+            continue;
+        }
+        float a = __fsub_rn(centerx, fpx);
+        const float b = __fsub_rn(centery, fpy);
+        a = fmaxf(a, 0.0001f);
+        const float b1 = __fsub_rn(1.f, b), b2 = b;
+        const float a12 = __fmul_rn(a, b1), a22 = __fmul_rn(a, b);
+        const float oma = __fsub_rn(1.f, a);
+        const double s = __ddiv_rn(__dsub_rn(1.0, (double)a), (double)a);
+        const unsigned* rowp = myPatch + dy * S5_PW + (dx >> 2);
+        const int sh = (dx & 3) * 8;
+
+        double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
+        float top[14], cur[14], wm2[13], wm1[13], wn[13];
+#pragma unroll
+        for (int j = 0; j < 13; j++) { wm2[j] = 0.f; wm1[j] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < 14; j++) top[j] = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < 14; r++, rowp += S5_PW) {
+            {   // source row r: 14 bytes starting at patch byte column dx
+                const unsigned w0 = rowp[0], w1 = rowp[1], w2 = rowp[2], w3 = rowp[3], w4 = rowp[4];
+                const unsigned v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
+                               v3 = __funnelshift_r(w3, w4, sh);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { cur[k] = s5_byte(v0, k); cur[4 + k] = s5_byte(v1, k); cur[8 + k] = s5_byte(v2, k); }
+                cur[12] = s5_byte(v3, 0); cur[13] = s5_byte(v3, 1);
+            }
+            if (r >= 1) {
+                // sample row i = r-1 (getRectSubPix_8u32f): dst[j] = prev + t, prev' = (float)(t * s)
+                float prev = __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, top[0]), __fmul_rn(b2, cur[0])));
+#pragma unroll
+                for (int j = 0; j < 13; j++) {
+                    const float t = __fadd_rn(__fmul_rn(a12, top[j + 1]), __fmul_rn(a22, cur[j + 1]));
+                    wn[j] = __fadd_rn(prev, t);
+                    prev = (float)__dmul_rn((double)t, s);
+                }
+                if (r >= 3) {
+                    // gradient row ii = r-3: samples (ii+1, j+1) of the 13x13 window, rows wm2 / wm1 / wn = ii, ii+1, ii+2
+                    const int ii = r - 3;
+                    const double py = (double)(ii - S5_WIN);
+                    const double* mrow = sMask + ii * 11;
+#pragma unroll
+                    for (int j = 0; j < 11; j++) {
+                        const double m = mrow[j];
+                        const double tgx = (double)__fsub_rn(wm1[j + 2], wm1[j]);
+                        const double tgy = (double)__fsub_rn(wn[j + 1], wm2[j + 1]);
+                        const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
+                        const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
+                        const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                        const double px = (double)(j - S5_WIN);
+                        sa = __dadd_rn(sa, gxx); sb = __dadd_rn(sb, gxy); sc = __dadd_rn(sc, gyy);
+                        sbb1 = __dadd_rn(sbb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
+                        sbb2 = __dadd_rn(sbb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 13; j++) { wm2[j] = wm1[j]; wm1[j] = wn[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 14; j++) top[j] = cur[j];
+        }
+        bool finished = false;
+        const double det = __dsub_rn(__dmul_rn(sa, sc), __dmul_rn(sb, sb));
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) finished = true;
+        else {
+            const double scale = __ddiv_rn(1.0, det);
+            const float nx = (float)__dsub_rn(__dadd_rn((double)cIx, __dmul_rn(__dmul_rn(sc, scale), sbb1)), __dmul_rn(__dmul_rn(sb, scale), sbb2));
+            const float ny = (float)__dadd_rn(__dsub_rn((double)cIy, __dmul_rn(__dmul_rn(sb, scale), sbb1)), __dmul_rn(__dmul_rn(sa, scale), sbb2));
+            const float ex = __fsub_rn(nx, cIx), ey = __fsub_rn(ny, cIy);
+            const double err = (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            cIx = nx; cIy = ny;
+            if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) finished = true;
+            else finished = !(++iter < A.maxIters && err > A.eps);
+        }
+        if (finished) {
+            if (fabsf(__fsub_rn(cIx, cTx)) > S5_WIN || fabsf(__fsub_rn(cIy, cTy)) > S5_WIN) { cIx = cTx; cIy = cTy; }
+            P[0] = cIx; P[1] = cIy;
+            active = false;
+        }
+        else if (++turn >= S5_BUDGET) {              // budget used up: next phase continues from here
+            P[0] = cIx; P[1] = cIy;
+            A.pts0[2 * (size_t)slot] = cTx; A.pts0[2 * (size_t)slot + 1] = cTy;
+            A.iters[slot] = iter;
+            A.listOut[atomicAdd(A.listOutCount, 1)] = slot;
+            active = false;
         }
     }
 }
@@ -877,7 +1100,7 @@ BirdState& state(Ctx& c)
 void free_plan(BirdPlan* p)
 {
     void* ptrs[] = {p->d_tab, p->d_cells, p->d_pyr, p->d_mask, p->d_blur, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount,
-                    p->d_kps, p->d_kps2, p->d_desc, p->d_counts, p->d_counts2, p->d_pts};
+                    p->d_kps, p->d_kps2, p->d_desc, p->d_counts, p->d_counts2, p->d_pts, p->d_slow, p->d_list[0], p->d_list[1], p->d_pts0, p->d_iters};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
 }
@@ -965,7 +1188,10 @@ BirdPlan* get_plan(Ctx& c, int w, int h, int nfeatures, int batch)
               cudaMalloc((void**)&p->d_kps2, B * g.kpPerImg * sizeof(orbb200_kp_t)) == cudaSuccess &&
               cudaMalloc((void**)&p->d_desc, B * g.kpPerImg * 32) == cudaSuccess &&
               cudaMalloc((void**)&p->d_counts, B * 4) == cudaSuccess && cudaMalloc((void**)&p->d_counts2, B * 4) == cudaSuccess &&
-              cudaMalloc((void**)&p->d_pts, B * g.kpPerImg * 8) == cudaSuccess;
+              cudaMalloc((void**)&p->d_pts, B * g.kpPerImg * 8) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_slow, B * g.kpPerImg * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_list[0], B * g.kpPerImg * 4) == cudaSuccess && cudaMalloc((void**)&p->d_list[1], B * g.kpPerImg * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_pts0, B * g.kpPerImg * 8) == cudaSuccess && cudaMalloc((void**)&p->d_iters, B * g.kpPerImg * 4) == cudaSuccess;
     if (ok) {
         ok = cudaMemcpyAsync(p->d_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream) == cudaSuccess &&
              cudaMemcpyAsync(p->d_cells, cells.data(), cells.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream) == cudaSuccess &&
@@ -1046,7 +1272,10 @@ int ensure_win_mask(Ctx& c, int winW, int winH)
         }
     }
     if (!S.d_winMask) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_winMask, sizeof(float) * (2 * BV_MAX_WIN + 1) * (2 * BV_MAX_WIN + 1)));
+    if (!S.d_winMaskD) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_winMaskD, sizeof(double) * (2 * BV_MAX_WIN + 1) * (2 * BV_MAX_WIN + 1)));
+    std::vector<double> md(m.begin(), m.end());
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(S.d_winMask, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(S.d_winMaskD, md.data(), md.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
     S.winW = winW; S.winH = winH;
     return ORBB200_OK;
@@ -1063,19 +1292,55 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
     double eps = std::max(epsilon, 0.);
     eps *= eps;
     const BirdLevel& L0 = g.lv[0];
-    if (n >= 8) {    // many corners in flight: persistent one-thread-per-corner form
-        BirdState& S = state(c);
-        if (!S.d_work) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_work, sizeof(int)));
-        cudaMemsetAsync(S.d_work, 0, sizeof(int), c.stream);
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BirdState& S = state(c);
+    if (!S.d_work) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_work, 4 * sizeof(int)));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    if (winW == S5_WIN && winH == S5_WIN) {
+        // the reference's window: streaming form in ceil(maxIters / budget) phases + exact hand-over of the few corners
+        // whose patch is not inside the image
+        const int phases = (maxIters + S5_BUDGET - 1) / S5_BUDGET;
+        const size_t workInts = 2 * (size_t)phases + 8;
+        if (S.workInts < workInts) {
+            cudaStreamSynchronize(c.stream);
+            if (S.d_work5) cudaFree(S.d_work5);
+            S.d_work5 = nullptr; S.workInts = 0;
+            ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_work5, workInts * sizeof(int)));
+            S.workInts = workInts;
+        }
+        cudaMemsetAsync(S.d_work5, 0, workInts * sizeof(int), c.stream);
+        const size_t smem = sizeof(unsigned) * S5_THREADS * S5_STRIDE;
+        if (smem > ensure_max_dynamic_smem(c.device, (const void*)bird_subpix5_kernel, SMEM_BIRD_SUBPIX)) { c.err = "bird_subpix5_kernel: shared memory"; return ORBB200_ERR_CUDA; }
+        const long long slots = (long long)n * g.kpPerImg;
+        const int grid = std::max(1, (int)std::min<long long>((long long)sms * c.subpixCtasPerSm, (slots + S5_THREADS - 1) / S5_THREADS));
+        int* heads = S.d_work5;                      // [phases]
+        int* outCounts = S.d_work5 + phases;         // [phases]
+        int* slowCount = S.d_work5 + 2 * phases;     // + head of the generic kernel
+        S5Args A{};
+        A.imgs = p->d_pyr + L0.off; A.imgStrideBytes = g.planeBytes; A.pitch = L0.pitch; A.cols = g.w; A.rows = g.h;
+        A.pts = p->d_pts; A.pts0 = p->d_pts0; A.iters = p->d_iters; A.ptsPerImg = g.kpPerImg; A.nImages = n; A.counts = d_counts; A.nFixed = nFixed;
+        A.winMaskD = S.d_winMaskD; A.maxIters = maxIters; A.eps = eps; A.slowList = p->d_slow; A.slowCount = slowCount;
+        for (int ph = 0; ph < phases; ph++) {
+            A.listIn = ph == 0 ? nullptr : p->d_list[(ph - 1) & 1];
+            A.listInCount = ph == 0 ? nullptr : outCounts + (ph - 1);
+            A.head = heads + ph;
+            A.listOut = p->d_list[ph & 1]; A.listOutCount = outCounts + ph;
+            bird_subpix5_kernel<<<grid, S5_THREADS, smem, c.stream>>>(A);
+            c.launches++;
+        }
+        bird_subpix_thread_kernel<<<std::min(sms, std::max(n, 1) * 4), SP_THREADS, 0, c.stream>>>(
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, g.kpPerImg, n, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps, slowCount + 1,
+            p->d_slow, slowCount);
+    }
+    else if (n >= 8) {    // many corners in flight: persistent one-thread-per-corner form
+        cudaMemsetAsync(S.d_work, 0, 4 * sizeof(int), c.stream);
         bird_subpix_thread_kernel<<<sms * 8, SP_THREADS, 0, c.stream>>>(
-            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, g.kpPerImg, n, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps, S.d_work);
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, g.kpPerImg, n, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps, S.d_work,
+            nullptr, nullptr);
     }
     else
         bird_subpix_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
-            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, state(c).d_winMask, winW, winH, maxIters, eps);
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;
@@ -1144,7 +1409,9 @@ void bird_destroy(Ctx& c)
     BirdState* S = static_cast<BirdState*>(c.bird);
     for (auto& kv : S->plans) free_plan(kv.second);
     if (S->d_winMask) cudaFree(S->d_winMask);
+    if (S->d_winMaskD) cudaFree(S->d_winMaskD);
     if (S->d_work) cudaFree(S->d_work);
+    if (S->d_work5) cudaFree(S->d_work5);
     delete S;
     c.bird = nullptr;
 }

@@ -75,6 +75,7 @@ struct Ctx {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;
     long long launches = 0;
+    int subpixCtasPerSm = 2;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS)
 
     // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)
     int nfeatures = 0;
