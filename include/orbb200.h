@@ -340,10 +340,65 @@ int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_fram
  * mvuRight, which SearchByProjection's stereo-consistency test reads, src/ORBmatcher.cc:91-96). */
 int orbb200_step_enable_stereo(orbb200_ctx* ctx, int enable, float mb, float mbf);
 
+/* ---- batched frame step: stereo front camera + birdview (the north-star frame) -------------------------------
+ * Everything the data-parallel side of one tracked frame does in the reference, for n_frames frames per call:
+ *   Frame::Frame (src/Frame.cc:84-142, 263-375): ORBextractor on the left and right image (:124-127), ComputeStereoMatches
+ *     (:662-836), cv::ORB(2000) detect(mask) + cornerSubPix + compute on the birdview image (:328-342), the two lookup grids
+ *     (:378-412);
+ *   Tracking::SearchLocalPoints (src/Tracking.cc:1610-1660): Frame::isInFrustum for every local map point, then
+ *     ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129);
+ *   ORBmatcher::SearchByMatchBird(Cur, Last, window) = BirdviewMatch(Last, Cur, vnMatches12, window)
+ *     (src/ORBmatcher.cc:1901-1921, 1788-1899) against the previous frame: frame i-1 of the call, or, for frame 0 with
+ *     chain != 0, the last frame of the previous call on this context (sequence processing).
+ * The local map stays on the device (orbb200_map_upload); a frame sends its pose.  The birdview mask is the constant
+ * vehicle mask of the reference (Examples/Monocular/mask_new_front.png is its front-camera analogue): set it once. */
+typedef struct {
+    int n_frames;
+    int w, h; size_t stride;                   /* front camera: 2*n_frames images, image 2i = left, 2i+1 = right of frame i */
+    float mb, mbf;                             /* stereo baseline, baseline*fx; mb <= 0: no ComputeStereoMatches (monocular) */
+    float min_x, min_y, inv_w, inv_h;          /* front lookup grid (mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv) */
+    const orbb200_map* map;                    /* local map or NULL (no SearchLocalPoints) */
+    float viewing_cos_limit, th, nnratio;      /* isInFrustum(pMP, 0.5); SearchByProjection(F, points, th) of ORBmatcher(nnratio) */
+    int bird_w, bird_h; size_t bird_stride;    /* birdview: n_frames images; bird_w == 0: no birdview */
+    int bird_nfeatures;                        /* cv::ORB::create(bird_nfeatures) */
+    int bird_window; float bird_nnratio; int bird_check_ori;   /* SearchByMatchBird(Cur, Last, 15) of ORBmatcher(0.99, true) */
+    int chain;                                 /* frame 0 continues the sequence of the previous call */
+} orbb200_frame_step_params;
+typedef struct {                               /* device pointers (_device) or host pointers (_host) */
+    const uint8_t* imgs;                       /* [2*n_frames] front images, contiguous, h*stride bytes each */
+    const uint8_t* bird_imgs;                  /* [n_frames] birdview images, bird_h*bird_stride bytes each */
+    const orbb200_camera_pose* poses;          /* [n_frames] */
+} orbb200_frame_step_inputs;
+typedef struct {                               /* any pointer may be NULL (result not wanted / stays in the device pools) */
+    orbb200_kp_t* kps; uint8_t* desc; int32_t* counts;           /* [2n][cap] / [2n][cap][32] / [2n]   mvKeys, mvKeysRight, mDescriptors[Right] */
+    float* u_right; float* depth;                                /* [n][cap]                          mvuRight, mvDepth */
+    int32_t* map_best_idx; int32_t* map_best_dist;               /* [n][map_n]  keypoint matched to each map point (-1) and its distance */
+    int32_t* map_nmatches;                                       /* [n] */
+    orbb200_kp_t* bird_kps; uint8_t* bird_desc; int32_t* bird_counts;   /* [n][bird_cap]                 mvKeysBird, mDescriptorsBird */
+    int32_t* bird_matches12; int32_t* bird_nmatches;             /* [n][bird_cap]: vnMatches12 of BirdviewMatch(previous, frame i); [n] */
+    int cap, bird_cap;                                           /* row capacities of the arrays above (host variant) */
+} orbb200_frame_step_outputs;
+/* capacity (row length) of the birdview keypoint pools for this size: bird_cap of the device variant */
+int orbb200_bird_set_mask(orbb200_ctx* ctx, int w, int h, int nfeatures, int max_batch, const uint8_t* mask, size_t mask_stride);
+/* Device variant: asynchronous on the context's stream; the map_* / bird_matches12 / bird_nmatches arrays are device arrays with
+ * rows of map_n / orbb200_bird_max_keypoints() entries; kps/desc/u_right/bird_kps/... are ignored (results stay in the pools:
+ * orbb200_results_device, orbb200_stereo_results_device, orbb200_bird_results_device). */
+int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* d_in,
+                              const orbb200_frame_step_outputs* d_out);
+/* Host variant (the end-to-end path): copies images and poses to the device, runs the step, copies every non-NULL output back.
+ * Asynchronous: outputs are valid after orbb200_sync().  Pinned host memory lets the copies overlap other contexts' work. */
+int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* h_in,
+                            const orbb200_frame_step_outputs* h_out);
+int orbb200_bird_results_device(orbb200_ctx* ctx, int w, int h, int nfeatures, const orbb200_kp_t** d_kps, const uint8_t** d_desc,
+                                const int32_t** d_counts, int* cap_per_img);
+/* Device-side error flags raised since the last call (octree / birdview selection overflow): 0 = none.  Synchronises. */
+int orbb200_device_status(orbb200_ctx* ctx, int* status);
+
 /* Per-stage device timing (bench): CUDA events on the context's stream around each stage.
  * stages: 0 import, 1 pyramid, 2 FAST, 3 blur, 4 octree, 5 orientation+descriptors, 6 grid build, 7 windowed match,
- * 8 stereo matching */
-#define ORBB200_NUM_STAGES 9
+ * 8 stereo matching, 9 birdview import+pyramid, 10 birdview FAST+retainBest+Harris+angles, 11 birdview cornerSubPix,
+ * 12 birdview blur+descriptors, 13 isInFrustum, 14-15 reserved */
+#define ORBB200_NUM_STAGES 16
 int orbb200_stage_timing(orbb200_ctx* ctx, int enable);
 /* Synchronises, then returns accumulated milliseconds and launch-group counts per stage; reset!=0 clears. */
 int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[9]*/, int32_t* groups /*[9]*/, int reset);

@@ -52,6 +52,7 @@ def lib(native=False):
         "oracle_extractor_create": (vp, [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]),
         "oracle_extractor_destroy": (None, [vp]),
         "oracle_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, sz, vp, vp, C.c_int]),
+        "oracle_extractor_stage_ms": (None, [vp, vp, C.c_int]),
         "oracle_extractor_features_per_level": (C.c_int, [vp, vp]),
         "oracle_extractor_scale_factors": (C.c_int, [vp, vp]),
         "oracle_extractor_umax": (C.c_int, [vp, vp]),
@@ -175,6 +176,12 @@ class Extractor:
         out = np.empty(self.nlevels, np.int32)
         self._L.oracle_extractor_features_per_level(self._h, _p(out))
         return out
+
+    def stage_ms(self, reset=False):
+        """accumulated wall ms per stage: dict(pyramid, fast, octree, orientation, blur, describe)"""
+        out = np.zeros(6, np.float64)
+        self._L.oracle_extractor_stage_ms(self._h, _p(out), int(reset))
+        return dict(zip(("pyramid", "fast", "octree", "orientation", "blur", "describe"), out.tolist()))
 
     def scale_factors(self):
         out = np.empty(self.nlevels, np.float32)

@@ -9,12 +9,14 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <list>
 #include <utility>
+#include <chrono>
 #include <vector>
 
 namespace {
@@ -436,6 +438,9 @@ struct oracle_extractor {
     std::vector<Img> mvImagePyramid, blurred;
     std::vector<std::vector<XYR> > candidates;          /* debug: per level, region coords */
     std::vector<std::vector<oracle_kp_t> > levelKeys;   /* debug: per level, level coords */
+    /* accumulated wall time per stage (bench.py's per-stage CPU denominators): pyramid, FAST cells, octree, orientation, blur, descriptors */
+    double stageNs[6] = {0, 0, 0, 0, 0, 0};
+    static double now_ns() { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     /* ORBextractor::ORBextractor, src/ORBextractor.cc:410-470 */
     oracle_extractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
@@ -517,6 +522,7 @@ struct oracle_extractor {
             if (nCols <= 0 || nRows <= 0) continue;
             const int wCell = (int)ceil(width / nCols);
             const int hCell = (int)ceil(height / nRows);
+            const double tFast0 = now_ns();
             for (int i = 0; i < nRows; i++) {
                 const float iniY = (float)(minBorderY + i * hCell);
                 float maxY = iniY + hCell + 6;
@@ -541,8 +547,11 @@ struct oracle_extractor {
                     }
                 }
             }
+            const double tOct0 = now_ns();
+            stageNs[1] += tOct0 - tFast0;
             std::vector<KP> keys = DistributeOctTree(vToDistributeKeys, minBorderX, maxBorderX, minBorderY, maxBorderY,
                                                      mnFeaturesPerLevel[level]);
+            stageNs[2] += now_ns() - tOct0;
             const int scaledPatchSize = (int)(PATCH_SIZE * mvScaleFactor[level]);
             std::vector<oracle_kp_t>& keypoints = allKeypoints[level];
             keypoints.resize(keys.size());
@@ -557,16 +566,20 @@ struct oracle_extractor {
                 k.class_id = -1;
             }
         }
+        const double tOri0 = now_ns();
         for (int level = 0; level < nlevels; ++level)
             for (size_t i = 0; i < allKeypoints[level].size(); i++)
                 allKeypoints[level][i].angle = IC_Angle(mvImagePyramid[level], allKeypoints[level][i].x, allKeypoints[level][i].y, umax);
+        stageNs[3] += now_ns() - tOri0;
     }
 
     /* ORBextractor::operator(), src/ORBextractor.cc:1043-1105 */
     int extract(const uchar* img, int w, int h, size_t step, oracle_kp_t* kps, uchar* desc, int cap)
     {
         if (!img || w <= 0 || h <= 0) return 0;
+        const double tPyr0 = now_ns();
         ComputePyramid(img, w, h, step);
+        stageNs[0] += now_ns() - tPyr0;
         ComputeKeyPointsOctTree(levelKeys);
         int nkeypoints = 0;
         for (int level = 0; level < nlevels; ++level) nkeypoints += (int)levelKeys[level].size();
@@ -576,12 +589,16 @@ struct oracle_extractor {
             std::vector<oracle_kp_t>& keypoints = levelKeys[level];
             int nkeypointsLevel = (int)keypoints.size();
             const Img& src = mvImagePyramid[level];
+            const double tBlur0 = now_ns();
             blurred[level].create(src.cols, src.rows);
             if (src.cols > 0 && src.rows > 0)
                 gauss7_u8(src.buf.data(), src.cols, src.rows, src.step, blurred[level].buf.data(), blurred[level].step);
+            const double tDesc0 = now_ns();
+            stageNs[4] += tDesc0 - tBlur0;
             if (nkeypointsLevel == 0) continue;
             for (int i = 0; i < nkeypointsLevel; i++)
                 computeOrbDescriptor(keypoints[i], blurred[level], desc + (size_t)(offset + i) * 32);
+            stageNs[5] += now_ns() - tDesc0;
             float scale = mvScaleFactor[level];
             for (int i = 0; i < nkeypointsLevel; i++) {
                 oracle_kp_t k = keypoints[i];
@@ -746,6 +763,12 @@ void oracle_extractor_destroy(oracle_extractor* e) { delete e; }
 
 int oracle_extract(oracle_extractor* e, const uint8_t* img, int w, int h, size_t step, oracle_kp_t* kps, uint8_t* desc, int cap)
 { return e->extract(img, w, h, step, kps, desc, cap); }
+
+/* accumulated milliseconds per stage since creation / the last reset: pyramid, FAST cells, octree, orientation, blur, descriptors */
+void oracle_extractor_stage_ms(oracle_extractor* e, double* out6, int reset)
+{
+    for (int i = 0; i < 6; i++) { if (out6) out6[i] = e->stageNs[i] * 1e-6; if (reset) e->stageNs[i] = 0; }
+}
 
 int oracle_extractor_features_per_level(oracle_extractor* e, int32_t* out)
 { for (int i = 0; i < e->nlevels; i++) out[i] = e->mnFeaturesPerLevel[i]; return e->nlevels; }

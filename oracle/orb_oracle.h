@@ -58,6 +58,8 @@ void oracle_extractor_destroy(oracle_extractor*);
 /* ORBextractor::operator(); returns N (number of keypoints), or -1 if cap too small */
 int oracle_extract(oracle_extractor*, const uint8_t* img, int w, int h, size_t step,
                    oracle_kp_t* kps, uint8_t* desc, int cap);
+/* accumulated wall milliseconds per stage (pyramid, FAST cells, octree, orientation, blur, descriptors); reset != 0 clears */
+void oracle_extractor_stage_ms(oracle_extractor*, double* out6, int reset);
 /* tables */
 int oracle_extractor_features_per_level(oracle_extractor*, int32_t* out);
 int oracle_extractor_scale_factors(oracle_extractor*, float* out);

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "Frame", "Context", "OrbB200Error", "KP_DTYPE", "load_library", "build"]
+__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "Frame", "FrameStep", "LocalMap", "BirdviewORB", "Context", "OrbB200Error", "KP_DTYPE", "load_library", "build"]
 
 _HERE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "orb-slam-birdview_b200") \
     if os.path.basename(os.path.dirname(os.path.abspath(__file__))) != "orb-slam-birdview_b200" else os.path.dirname(os.path.abspath(__file__))
@@ -101,12 +101,38 @@ _SIGNATURES = {
     "orbb200_stage_timing": (_i, [_vp, _i]),
     "orbb200_stage_times": (_i, [_vp, _vp, _vp, _i]),
     "orbb200_launch_count": (C.c_longlong, [_vp]),
+    "orbb200_bird_set_mask": (_i, [_vp, _i, _i, _i, _i, _vp, _sz]),
+    "orbb200_frame_step_device": (_i, [_vp, _vp, _vp, _vp]),
+    "orbb200_frame_step_host": (_i, [_vp, _vp, _vp, _vp]),
+    "orbb200_bird_results_device": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i)]),
+    "orbb200_device_status": (_i, [_vp, C.POINTER(_i)]),
 }
 
 
 class ProjQueries(C.Structure):
     """orbb200_proj_queries: device pointers of [n_frames][nq] query arrays"""
     _fields_ = [(n, C.c_void_p) for n in ("q_valid", "q_u", "q_v", "q_uR", "q_level", "q_viewcos", "q_desc", "q_obs_pos")]
+
+
+class FrameStepParams(C.Structure):
+    """orbb200_frame_step_params"""
+    _fields_ = [("n_frames", C.c_int), ("w", C.c_int), ("h", C.c_int), ("stride", C.c_size_t), ("mb", C.c_float), ("mbf", C.c_float),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float), ("inv_h", C.c_float), ("map", C.c_void_p),
+                ("viewing_cos_limit", C.c_float), ("th", C.c_float), ("nnratio", C.c_float),
+                ("bird_w", C.c_int), ("bird_h", C.c_int), ("bird_stride", C.c_size_t), ("bird_nfeatures", C.c_int),
+                ("bird_window", C.c_int), ("bird_nnratio", C.c_float), ("bird_check_ori", C.c_int), ("chain", C.c_int)]
+
+
+class FrameStepInputs(C.Structure):
+    """orbb200_frame_step_inputs"""
+    _fields_ = [("imgs", C.c_void_p), ("bird_imgs", C.c_void_p), ("poses", C.c_void_p)]
+
+
+class FrameStepOutputs(C.Structure):
+    """orbb200_frame_step_outputs"""
+    _fields_ = [(n, C.c_void_p) for n in ("kps", "desc", "counts", "u_right", "depth", "map_best_idx", "map_best_dist", "map_nmatches",
+                                          "bird_kps", "bird_desc", "bird_counts", "bird_matches12", "bird_nmatches")] + \
+               [("cap", C.c_int), ("bird_cap", C.c_int)]
 
 
 class CameraPose(C.Structure):
@@ -460,6 +486,72 @@ class LocalMap:
                                                      _p(uR), _p(lvl), _p(vc), C.byref(k)), "isInFrustum")
         n = self.n
         return k.value, iv[:n], u[:n], v[:n], uR[:n], lvl[:n], vc[:n]
+
+
+class FrameStep:
+    """The batched north-star frame (orbb200_frame_step_host): per frame L+R ORBextractor, ComputeStereoMatches, birdview
+    cv::ORB + cornerSubPix + compute, SearchLocalPoints against a device-resident local map and SearchByMatchBird against the
+    previous frame -- what Frame::Frame (src/Frame.cc:84-142, 263-375) and Tracking::Track (src/Tracking.cc:1241, 1610-1660)
+    run on the data-parallel side, for n frames per call on numpy (host) buffers."""
+
+    def __init__(self, ctx, w, h, local_map=None, mb=0.0, mbf=0.0, grid=None, th=1.0, nnratio=0.8, viewing_cos_limit=0.5,
+                 bird_size=None, bird_nfeatures=2000, bird_mask=None, bird_window=15, bird_nnratio=0.99, bird_check_ori=True):
+        self.ctx, self._L = ctx, ctx._L
+        self.w, self.h, self.map = w, h, local_map
+        P = FrameStepParams()
+        P.w, P.h, P.stride, P.mb, P.mbf = w, h, w, mb, mbf
+        g = grid or (0.0, 0.0, FRAME_GRID_COLS / w, FRAME_GRID_ROWS / h)
+        P.min_x, P.min_y, P.inv_w, P.inv_h = g
+        P.map = local_map._h if local_map is not None else None
+        P.viewing_cos_limit, P.th, P.nnratio = viewing_cos_limit, th, nnratio
+        if bird_size:
+            P.bird_w, P.bird_h = bird_size
+            P.bird_stride, P.bird_nfeatures = bird_size[0], bird_nfeatures
+            P.bird_window, P.bird_nnratio, P.bird_check_ori = bird_window, bird_nnratio, int(bird_check_ori)
+            self.bird_cap = self._L.orbb200_bird_max_keypoints(ctx._h, P.bird_w, P.bird_h, bird_nfeatures)
+            m = _c(bird_mask, np.uint8)
+            ctx.check(self._L.orbb200_bird_set_mask(ctx._h, P.bird_w, P.bird_h, bird_nfeatures, max(ctx.max_batch // 2, 1), _p(m),
+                                                    m.strides[0] if m is not None else 0), "bird_set_mask")
+        else:
+            self.bird_cap = 0
+        self.P = P
+        self.cap = ctx.max_keypoints
+
+    def __call__(self, imgs, bird_imgs=None, poses=None, chain=False):
+        """imgs [2n][h][w] (left, right interleaved), bird_imgs [n][bh][bw], poses: list of n CameraPose.
+        -> dict of host arrays (kps, desc, counts, u_right, depth, map_best_idx, map_best_dist, map_nmatches, bird_kps, bird_desc,
+        bird_counts, bird_matches12, bird_nmatches)"""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        n = imgs.shape[0] // 2
+        P = self.P
+        P.n_frames, P.chain = n, int(chain)
+        I, O = FrameStepInputs(), FrameStepOutputs()
+        I.imgs = imgs.ctypes.data
+        out = dict(kps=np.zeros((2 * n, self.cap), KP_DTYPE), desc=np.zeros((2 * n, self.cap, 32), np.uint8), counts=np.zeros(2 * n, np.int32))
+        if P.mb > 0:
+            out.update(u_right=np.zeros((n, self.cap), np.float32), depth=np.zeros((n, self.cap), np.float32))
+        keep = [imgs]
+        if self.map is not None:
+            arr = (CameraPose * n)(*poses)
+            keep.append(arr)
+            I.poses = C.addressof(arr)
+            out.update(map_best_idx=np.zeros((n, self.map.n), np.int32), map_best_dist=np.zeros((n, self.map.n), np.int32),
+                       map_nmatches=np.zeros(n, np.int32))
+        if P.bird_w > 0:
+            b = np.ascontiguousarray(bird_imgs, np.uint8)
+            keep.append(b)
+            I.bird_imgs = b.ctypes.data
+            out.update(bird_kps=np.zeros((n, self.bird_cap), KP_DTYPE), bird_desc=np.zeros((n, self.bird_cap, 32), np.uint8),
+                       bird_counts=np.zeros(n, np.int32), bird_matches12=np.full((n, self.bird_cap), -1, np.int32),
+                       bird_nmatches=np.zeros(n, np.int32))
+        for k, v in out.items():
+            setattr(O, k, v.ctypes.data)
+        O.cap, O.bird_cap = self.cap, self.bird_cap
+        self.ctx.check(self._L.orbb200_frame_step_host(self.ctx._h, C.byref(P), C.byref(I), C.byref(O)), "frame_step_host")
+        self.ctx.sync()
+        st = C.c_int()
+        self.ctx.check(self._L.orbb200_device_status(self.ctx._h, C.byref(st)), "device_status")
+        return out
 
 
 class ORBmatcher:

@@ -511,6 +511,8 @@ void orbb200_destroy(orbb200_ctx* ctx)
     bird_destroy(c);
     for (cudaEvent_t e : c.freeEvents) cudaEventDestroy(e);
     for (auto& p : c.plans) cudaFree(p.block);
+    for (auto& p : c.framePlans) cudaFree(p.block);
+    if (c.d_fstep) cudaFree(c.d_fstep);
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -1445,6 +1447,245 @@ int orbb200_stereo_step_host(orbb200_ctx* ctx, const uint8_t* h_imgs, int n_fram
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_best_dist, dBd, 4 * Q, cudaMemcpyDeviceToHost, c.stream));
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(h_nmatches, dNm, 4 * (size_t)n_frames, cudaMemcpyDeviceToHost, c.stream));
     return ORBB200_OK;
+}
+
+// ---- batched frame step: stereo front camera + birdview ---------------------------------------------------------------
+static int frame_step_check(Ctx& c, const orbb200_frame_step_params* p)
+{
+    if (!p || p->n_frames <= 0 || 2 * p->n_frames > c.maxBatch || p->w <= 0 || p->h <= 0 || p->stride < (size_t)p->w) { c.err = "frame_step: bad argument"; return ORBB200_ERR_ARG; }
+    if (p->bird_w < 0 || p->bird_h < 0 || (p->bird_w > 0 && (p->bird_h <= 0 || p->bird_stride < (size_t)p->bird_w || p->bird_nfeatures <= 0 || p->bird_window <= 0))) {
+        c.err = "frame_step: bad birdview argument"; return ORBB200_ERR_ARG;
+    }
+    if (p->map && p->map->ctx != &c) { c.err = "frame_step: the map belongs to another context"; return ORBB200_ERR_ARG; }
+    return ORBB200_OK;
+}
+
+int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* in,
+                              const orbb200_frame_step_outputs* out)
+{
+    CTX_ENTER(ctx);
+    int rc = frame_step_check(c, p);
+    if (rc != ORBB200_OK) return rc;
+    const int n = p->n_frames;
+    const bool hasMap = p->map && p->map->n > 0, hasBird = p->bird_w > 0, stereo = p->mb > 0.f;
+    if (!in || !out || !in->imgs || (hasBird && !in->bird_imgs) || (hasMap && (!in->poses || !out->map_best_idx || !out->map_best_dist || !out->map_nmatches)) ||
+        (hasBird && (!out->bird_matches12 || !out->bird_nmatches))) { c.err = "frame_step: missing input or output array"; return ORBB200_ERR_ARG; }
+    // front camera: both images of every frame in one extraction, then the stereo matcher on its pools
+    rc = orbb200_extract_device(ctx, in->imgs, (size_t)p->h * p->stride, 2 * n, p->w, p->h, p->stride);
+    if (rc != ORBB200_OK) return rc;
+    if (stereo) {
+        StageTimer t(c, 8);
+        launch_stereo(c, n, 0, 1, 2, p->mb, p->mbf, c.d_invScale, c.d_nKept);
+        c.stereoValid = true;
+    }
+    // birdview front-end + the query arrays of BirdviewMatch(previous, current)
+    BirdStepView bv{};
+    if (hasBird) {
+        rc = bird_step_enqueue(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, in->bird_imgs, (size_t)p->bird_h * p->bird_stride, p->bird_stride,
+                               p->chain != 0, &bv);
+        if (rc != ORBB200_OK) return rc;
+    }
+    const int kpi = c.cur->g.kpPerImg, mapN = hasMap ? p->map->n : 0;
+    FramePlan key{};
+    key.n = n; key.kpi = kpi; key.birdKpi = hasBird ? bv.kpPerImg : 0; key.mapN = mapN; key.stereo = stereo ? 1 : 0; key.birdWindow = p->bird_window;
+    key.birdOri = p->bird_check_ori; key.hasBird = hasBird ? 1 : 0; key.th = p->th; key.nnratio = p->nnratio; key.minX = p->min_x; key.minY = p->min_y;
+    key.invW = p->inv_w; key.invH = p->inv_h;
+    // Frame: mfGridElementWidthInvBirdview = FRAME_GRID_COLS / width, HeightInv = FRAME_GRID_ROWS / height (src/Frame.cc:350-351)
+    key.birdInvW = hasBird ? (float)GRID_COLS / (float)p->bird_w : 0.f; key.birdInvH = hasBird ? (float)GRID_ROWS / (float)p->bird_h : 0.f;
+    key.birdRatio = p->bird_nnratio; key.map = hasMap ? p->map : nullptr; key.birdKps = bv.d_kps; key.birdQx = bv.d_qx;
+    key.oBi = out->map_best_idx; key.oBd = out->map_best_dist; key.oNm = out->map_nmatches; key.oM12 = out->bird_matches12; key.oBnm = out->bird_nmatches;
+    FramePlan* plan = nullptr;
+    for (auto& q : c.framePlans)
+        if (memcmp(&q, &key, offsetof(FramePlan, dF)) == 0) { plan = &q; break; }
+    if (!plan) {
+        if (c.framePlans.size() >= 16) {
+            cudaStreamSynchronize(c.stream);
+            for (auto& q : c.framePlans) cudaFree(q.block);
+            c.framePlans.clear();
+        }
+        const int bk = key.birdKpi;
+        const size_t gridBytes = align_up(4 * (size_t)(GRID_CELLS + 1), 256);
+        const size_t perFront = gridBytes + align_up(4 * (size_t)kpi, 256) * 2 + align_up(16 * (size_t)kpi, 256) + align_up(4 * win_scratch_ints(kpi, mapN), 256) +
+                                align_up((size_t)mapN, 256) + align_up(4 * (size_t)mapN, 256) * 5;
+        const size_t perBird = hasBird ? gridBytes + align_up(4 * (size_t)bk, 256) * 2 + align_up(16 * (size_t)bk, 256) + align_up(4 * win_scratch_ints(bk, bk), 256) : 0;
+        const size_t bytes = align_up(sizeof(FrameDev) * 2 * n, 256) + align_up(sizeof(WinJob) * 2 * n, 256) + 1024 + (perFront + perBird) * n + align_up(4 * (size_t)n, 256) + 8192;
+        ORBB200_CUDA_OK(c, cudaMalloc(&key.block, bytes));
+        Arena A((uint8_t*)key.block, bytes);
+        key.dF = A.take<FrameDev>(2 * n);
+        key.dJ = A.take<WinJob>(2 * n);
+        float* dsf = A.take<float>(MAX_LEVELS);
+        key.inView = A.take<uint8_t>((size_t)n * std::max(mapN, 1));
+        key.u = A.take<float>((size_t)n * std::max(mapN, 1)); key.v = A.take<float>((size_t)n * std::max(mapN, 1));
+        key.uR = A.take<float>((size_t)n * std::max(mapN, 1)); key.viewcos = A.take<float>((size_t)n * std::max(mapN, 1));
+        key.level = A.take<int32_t>((size_t)n * std::max(mapN, 1));
+        key.count = A.take<int32_t>(n);
+        std::vector<FrameDev> hF(2 * n);
+        std::vector<WinJob> hJ;
+        for (int i = 0; i < n; i++) {              // front frames: grid over the left image's keypoints
+            FrameDev& f = hF[i];
+            const int img = 2 * i;
+            f.kps = c.d_kps + (size_t)img * kpi; f.desc = c.d_desc + (size_t)img * kpi * 32;
+            f.uRight = stereo ? c.d_uRight + (size_t)img * kpi : nullptr;
+            f.n_ptr = c.d_counts + img; f.n = kpi;
+            f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(kpi); f.cellKp = A.take<int4>(kpi);
+            f.minX = p->min_x; f.minY = p->min_y; f.invW = p->inv_w; f.invH = p->inv_h;
+            if (!hasMap) continue;
+            WinJob J;
+            memset(&J, 0, sizeof(J));
+            const size_t o = (size_t)i * mapN;
+            J.frame = key.dF + i; J.nq = mapN; J.mode = WM_PROJ; J.kpCap = kpi; J.th = p->th; J.nnratio = p->nnratio; J.scaleFactors = dsf;
+            J.q_valid = key.inView + o; J.q_x = key.u + o; J.q_y = key.v + o; J.q_aux = key.uR + o; J.q_level = key.level + o; J.q_viewcos = key.viewcos + o;
+            J.q_desc = p->map->d_desc;             // the map points' representative descriptors, shared by every frame
+            J.scratch = A.take<int>(win_scratch_ints(kpi, mapN));
+            J.out_best_idx = out->map_best_idx + o; J.out_best_dist = out->map_best_dist + o;
+            J.out_per_kp = A.take<int32_t>(kpi);
+            J.out_nmatches = out->map_nmatches + i;
+            hJ.push_back(J);
+        }
+        for (int i = 0; hasBird && i < n; i++) {   // birdview frames: grid over frame i, queries = frame i-1 (slot i of the query arrays)
+            FrameDev& f = hF[n + i];
+            f.kps = bv.d_kps + (size_t)i * bk; f.desc = bv.d_desc + (size_t)i * bk * 32; f.uRight = nullptr;
+            f.n_ptr = bv.d_counts + i; f.n = bk;
+            f.cellStart = A.take<int32_t>(GRID_CELLS + 1); f.cellItems = A.take<int32_t>(bk); f.cellKp = A.take<int4>(bk);
+            f.minX = 0.f; f.minY = 0.f; f.invW = key.birdInvW; f.invH = key.birdInvH;
+            WinJob J;
+            memset(&J, 0, sizeof(J));
+            const size_t qo = (size_t)i * bk;
+            J.frame = key.dF + n + i; J.nq = bk; J.mode = WM_BIRD; J.levelMode = 0; J.checkOri = p->bird_check_ori; J.kpCap = bk;
+            J.th = (float)p->bird_window; J.nnratio = p->bird_nnratio; J.scaleFactors = dsf;
+            J.q_valid = bv.d_qvalid + qo; J.q_x = bv.d_qx + qo; J.q_y = bv.d_qy + qo; J.q_level = bv.d_qlevel + qo; J.q_angle = bv.d_qangle + qo;
+            J.q_desc = i == 0 ? bv.d_carryDesc : bv.d_desc + (size_t)(i - 1) * bk * 32;
+            J.scratch = A.take<int>(win_scratch_ints(bk, bk));
+            J.out_per_query = out->bird_matches12 + (size_t)i * bk;
+            J.out_per_kp = A.take<int32_t>(bk);
+            J.out_nmatches = out->bird_nmatches + i;
+            hJ.push_back(J);
+        }
+        key.nFrames = hasBird ? 2 * n : n; key.nJobs = (int)hJ.size();
+        key.maxNq = std::max(mapN, hasBird ? bk : 0); key.maxKpCap = std::max(kpi, hasBird ? bk : 0);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(key.dF, hF.data(), sizeof(FrameDev) * hF.size(), cudaMemcpyHostToDevice, c.stream));
+        if (!hJ.empty()) ORBB200_CUDA_OK(c, cudaMemcpyAsync(key.dJ, hJ.data(), sizeof(WinJob) * hJ.size(), cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));   // one-time: host vectors go out of scope
+        c.framePlans.push_back(key);
+        plan = &c.framePlans.back();
+    }
+    if (hasMap) {                                  // Frame::isInFrustum for every (frame, map point)
+        StageTimer t(c, 13);
+        FrustumJob J{};
+        J.poses = in->poses; J.nFrames = n; J.cosLimit = p->viewing_cos_limit; J.n = mapN;
+        J.pos = p->map->d_pos; J.normal = p->map->d_normal; J.maxDist = p->map->d_maxDist; J.minDist = p->map->d_minDist; J.candidate = nullptr;
+        J.inView = plan->inView; J.u = plan->u; J.v = plan->v; J.uR = plan->uR; J.level = plan->level; J.viewcos = plan->viewcos; J.count = plan->count;
+        launch_frustum(c, J);
+    }
+    { StageTimer t(c, 6); launch_grid_build(c, plan->dF, plan->nFrames); }
+    if (plan->nJobs > 0) { StageTimer t(c, 7); launch_window_match(c, plan->dJ, plan->nJobs, plan->maxNq, plan->maxKpCap); }
+    if (hasBird) {
+        rc = bird_step_carry(c, bv, n);
+        if (rc != ORBB200_OK) return rc;
+    }
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    return ORBB200_OK;
+}
+
+int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* in,
+                            const orbb200_frame_step_outputs* out)
+{
+    CTX_ENTER(ctx);
+    int rc = frame_step_check(c, p);
+    if (rc != ORBB200_OK) return rc;
+    if (!in || !out || !in->imgs) { c.err = "frame_step_host: missing input"; return ORBB200_ERR_ARG; }
+    const int n = p->n_frames, ni = 2 * n;
+    const bool hasMap = p->map && p->map->n > 0, hasBird = p->bird_w > 0;
+    const int mapN = hasMap ? p->map->n : 0;
+    const int bk = hasBird ? orbb200_bird_max_keypoints(ctx, p->bird_w, p->bird_h, p->bird_nfeatures) : 0;
+    if (hasBird && bk <= 0) return ORBB200_ERR_CUDA;
+    if ((hasBird && !in->bird_imgs) || (hasMap && !in->poses)) { c.err = "frame_step_host: missing input"; return ORBB200_ERR_ARG; }
+    const size_t imgBytes = (size_t)p->h * p->stride, birdBytes = hasBird ? (size_t)p->bird_h * p->bird_stride : 0;
+    const size_t Qm = (size_t)n * mapN, Qb = (size_t)n * bk;
+    const size_t need = align_up(imgBytes * ni, 256) + align_up(birdBytes * n, 256) + align_up(sizeof(orbb200_camera_pose) * n, 256) + align_up(4 * Qm, 256) * 2 +
+                        align_up(4 * Qb, 256) + align_up(4 * (size_t)n, 256) * 2 + 4096;
+    if (need > c.d_fstep_bytes) {
+        cudaStreamSynchronize(c.stream);
+        if (c.d_fstep) cudaFree(c.d_fstep);
+        c.d_fstep = nullptr; c.d_fstep_bytes = 0;
+        for (auto& q : c.framePlans) cudaFree(q.block);     // their output pointers refer to the old staging block
+        c.framePlans.clear();
+        ORBB200_CUDA_OK(c, cudaMalloc(&c.d_fstep, need));
+        c.d_fstep_bytes = need;
+    }
+    Arena A(c.d_fstep, c.d_fstep_bytes);
+    orbb200_frame_step_inputs din{};
+    orbb200_frame_step_outputs dout{};
+    uint8_t* dImgs = A.take<uint8_t>(imgBytes * ni);
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dImgs, in->imgs, imgBytes * ni, cudaMemcpyHostToDevice, c.stream));
+    din.imgs = dImgs;
+    if (hasBird) {
+        uint8_t* dBird = A.take<uint8_t>(birdBytes * n);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dBird, in->bird_imgs, birdBytes * n, cudaMemcpyHostToDevice, c.stream));
+        din.bird_imgs = dBird;
+    }
+    if (hasMap) {
+        orbb200_camera_pose* dP = A.take<orbb200_camera_pose>(n);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dP, in->poses, sizeof(orbb200_camera_pose) * n, cudaMemcpyHostToDevice, c.stream));
+        din.poses = dP;
+        dout.map_best_idx = A.take<int32_t>(Qm); dout.map_best_dist = A.take<int32_t>(Qm); dout.map_nmatches = A.take<int32_t>(n);
+    }
+    if (hasBird) { dout.bird_matches12 = A.take<int32_t>(Qb); dout.bird_nmatches = A.take<int32_t>(n); }
+    rc = orbb200_frame_step_device(ctx, p, &din, &dout);
+    if (rc != ORBB200_OK) return rc;
+    const int kpi = c.cur->g.kpPerImg;
+    if (out->kps || out->desc || out->u_right || out->depth) {
+        if (out->cap <= 0) { c.err = "frame_step_host: cap"; return ORBB200_ERR_ARG; }
+        const int take = std::min(out->cap, kpi);
+        if (out->kps) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->kps, (size_t)out->cap * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t),
+                                                           (size_t)take * sizeof(orbb200_kp_t), ni, cudaMemcpyDeviceToHost, c.stream));
+        if (out->desc) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->desc, (size_t)out->cap * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, ni, cudaMemcpyDeviceToHost, c.stream));
+        // mvuRight / mvDepth live in the left images' rows of the pools (image 2i)
+        if (out->u_right && p->mb > 0.f) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->u_right, (size_t)out->cap * 4, c.d_uRight, (size_t)kpi * 8, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
+        if (out->depth && p->mb > 0.f) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->depth, (size_t)out->cap * 4, c.d_depth, (size_t)kpi * 8, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (out->counts) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->counts, c.d_counts, 4 * (size_t)ni, cudaMemcpyDeviceToHost, c.stream));
+    if (hasMap) {
+        if (out->map_best_idx) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_best_idx, dout.map_best_idx, 4 * Qm, cudaMemcpyDeviceToHost, c.stream));
+        if (out->map_best_dist) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_best_dist, dout.map_best_dist, 4 * Qm, cudaMemcpyDeviceToHost, c.stream));
+        if (out->map_nmatches) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_nmatches, dout.map_nmatches, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (hasBird) {
+        const orbb200_kp_t* bKps = nullptr; const uint8_t* bDesc = nullptr; const int32_t* bCnt = nullptr; int bcap = 0;
+        rc = orbb200_bird_results_device(ctx, p->bird_w, p->bird_h, p->bird_nfeatures, &bKps, &bDesc, &bCnt, &bcap);
+        if (rc != ORBB200_OK) return rc;
+        if (out->bird_kps || out->bird_desc || out->bird_matches12) {
+            if (out->bird_cap <= 0) { c.err = "frame_step_host: bird_cap"; return ORBB200_ERR_ARG; }
+            const int take = std::min(out->bird_cap, bk);
+            if (out->bird_kps) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_kps, (size_t)out->bird_cap * sizeof(orbb200_kp_t), bKps, (size_t)bk * sizeof(orbb200_kp_t),
+                                                                    (size_t)take * sizeof(orbb200_kp_t), n, cudaMemcpyDeviceToHost, c.stream));
+            if (out->bird_desc) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_desc, (size_t)out->bird_cap * 32, bDesc, (size_t)bk * 32, (size_t)take * 32, n, cudaMemcpyDeviceToHost, c.stream));
+            if (out->bird_matches12) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_matches12, (size_t)out->bird_cap * 4, dout.bird_matches12, (size_t)bk * 4, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
+        }
+        if (out->bird_counts) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->bird_counts, bCnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        if (out->bird_nmatches) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->bird_nmatches, dout.bird_nmatches, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    return ORBB200_OK;
+}
+
+int orbb200_device_status(orbb200_ctx* ctx, int* status)
+{
+    CTX_ENTER(ctx);
+    int32_t st = 0;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(&st, c.d_status, sizeof(st), cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (st != 0) cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
+    if (status) *status = st;
+    if (st != 0) { c.err = "device-side capacity overflow (status " + std::to_string(st) + "): results of the last calls are incomplete"; return ORBB200_ERR_CAPACITY; }
+    return ORBB200_OK;
+}
+
+int orbb200_bird_set_mask(orbb200_ctx* ctx, int w, int h, int nfeatures, int max_batch, const uint8_t* mask, size_t mask_stride)
+{
+    CTX_ENTER(ctx);
+    if (w <= 0 || h <= 0 || nfeatures <= 0 || w > 4000 || h > 4000 || (mask && mask_stride < (size_t)w)) { c.err = "bird_set_mask: bad argument"; return ORBB200_ERR_ARG; }
+    return bird_set_mask(c, w, h, nfeatures, max_batch, mask, mask_stride);
 }
 
 int orbb200_step_enable_stereo(orbb200_ctx* ctx, int enable, float mb, float mbf)

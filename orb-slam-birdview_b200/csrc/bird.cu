@@ -57,6 +57,7 @@ struct BirdPlan {
     int batch = 0;
     // per-batch pools
     uint8_t* d_pyr = nullptr; uint8_t* d_mask = nullptr; uint8_t* d_blur = nullptr;
+    uint8_t* d_maskShared = nullptr;  // one mask pyramid used for every image (orbb200_bird_set_mask), or null
     uint32_t* d_cand = nullptr; int32_t* d_candCount = nullptr;
     float4* d_lvlKp = nullptr; int32_t* d_lvlCount = nullptr;          // {x, y, harris, -} per level slot
     orbb200_kp_t* d_kps = nullptr; orbb200_kp_t* d_kps2 = nullptr; uint8_t* d_desc = nullptr;
@@ -66,6 +67,11 @@ struct BirdPlan {
     int* d_list[2] = {nullptr, nullptr};   // corners continuing in the next phase (ping-pong)
     float* d_pts0 = nullptr;         // their start points
     int* d_iters = nullptr;          // and iteration counts
+    // frame-to-frame birdview matching inside the batched frame step: query arrays of "frame i-1" for job i, slot 0 = the
+    // last frame of the previous step (carry)
+    float* d_qx = nullptr; float* d_qy = nullptr; float* d_qangle = nullptr; int32_t* d_qlevel = nullptr; uint8_t* d_qvalid = nullptr;   // [batch+1][kpPerImg]
+    orbb200_kp_t* d_carryKps = nullptr; uint8_t* d_carryDesc = nullptr; int32_t* d_carryCount = nullptr;
+    bool carryValid = false;
 };
 
 struct BirdState {
@@ -340,6 +346,7 @@ __device__ float bird_harris(const uint8_t* img, int pitch, int x0, int y0)
 // Per (image, level): FAST corners -> mask filter -> row-major order (cv::FAST's) -> retainBest(2 * quota) on the FAST
 // score -> Harris responses -> retainBest(quota) (orb.cpp computeKeyPoints).  Writes the level's survivors in order.
 __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ mpyr,
+                                                                  unsigned maskPlaneBytes,      // 0: one mask pyramid for every image
                                                                   const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                                   float4* __restrict__ lvlKp, int32_t* __restrict__ lvlCount,
                                                                   int32_t* __restrict__ status)
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
         return;
     }
     const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
-    const uint8_t* M = mpyr ? mpyr + (size_t)img * g.planeBytes + L.off : nullptr;
+    const uint8_t* M = mpyr ? mpyr + (size_t)img * maskPlaneBytes + L.off : nullptr;
     int P2 = 1;
     while (P2 < n) P2 <<= 1;
     // key = (y << 20) | (x << 8) | score : ascending == cv::FAST's row-major output order
@@ -962,6 +969,40 @@ __global__ void bird_kps_to_pts_kernel(const orbb200_kp_t* __restrict__ kps, flo
     if (toKps) { k->x = p[0]; k->y = p[1]; } else { p[0] = k->x; p[1] = k->y; }
 }
 
+// n device-resident images (rows of `stride` bytes, image i at imgs + i*imgBytes) into level 0 of the planes
+__global__ void __launch_bounds__(128) bird_import_kernel(const uint8_t* __restrict__ imgs, size_t imgBytes, size_t stride, uint8_t* __restrict__ pyr,
+                                                          unsigned planeBytes, BirdLevel L0)
+{
+    const int y = blockIdx.x, img = blockIdx.y;
+    const uint8_t* s = imgs + (size_t)img * imgBytes + (size_t)y * stride;
+    uint8_t* d = pyr + (size_t)img * planeBytes + L0.off + (size_t)y * L0.pitch;      // 32-byte aligned (margin 32, pitch % 128 == 0)
+    if (((uintptr_t)s & 3) == 0) {
+        const int nw = L0.w >> 2;
+        for (int x = threadIdx.x; x < nw; x += 128) reinterpret_cast<uint32_t*>(d)[x] = __ldg(reinterpret_cast<const uint32_t*>(s) + x);
+        for (int x = (nw << 2) + threadIdx.x; x < L0.w; x += 128) d[x] = s[x];
+    } else
+        for (int x = threadIdx.x; x < L0.w; x += 128) d[x] = s[x];
+}
+
+// Query arrays of BirdviewMatch(Last, Cur) (src/ORBmatcher.cc:1788-1899) for every frame of a step: slot 0 = the frame
+// carried over from the previous step, slot s = frame s-1 of this step.  Query i1 is keypoint i1 of the "last" frame:
+// window centre = its position, level = its octave, angle for the rotation histogram.
+__global__ void __launch_bounds__(256) bird_queries_kernel(const orbb200_kp_t* __restrict__ kps, const int32_t* __restrict__ counts,
+                                                           const orbb200_kp_t* __restrict__ carryKps, const int32_t* __restrict__ carryCount,
+                                                           int kpPerImg, float* __restrict__ qx, float* __restrict__ qy, float* __restrict__ qangle,
+                                                           int32_t* __restrict__ qlevel, uint8_t* __restrict__ qvalid)
+{
+    const int slot = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kpPerImg) return;
+    const orbb200_kp_t* K = slot == 0 ? carryKps : kps + (size_t)(slot - 1) * kpPerImg;
+    const int n = min(slot == 0 ? *carryCount : counts[slot - 1], kpPerImg);
+    const size_t o = (size_t)slot * kpPerImg + i;
+    const bool ok = i < n;
+    orbb200_kp_t k{};
+    if (ok) k = K[i];
+    qx[o] = k.x; qy[o] = k.y; qangle[o] = k.angle; qlevel[o] = k.octave; qvalid[o] = ok ? 1 : 0;
+}
+
 // ORB::compute on provided keypoints: KeyPointsFilter::runByImageBorder(kps, image size, 31) keeping the order, then a
 // stable regrouping by octave when the input is not sorted by level (orb.cpp detectAndCompute).  One CTA per image.
 __global__ void __launch_bounds__(256) bird_filter_kernel(BirdGeom g, const orbb200_kp_t* __restrict__ in, const int32_t* __restrict__ inCount,
@@ -1100,7 +1141,8 @@ BirdState& state(Ctx& c)
 void free_plan(BirdPlan* p)
 {
     void* ptrs[] = {p->d_tab, p->d_cells, p->d_pyr, p->d_mask, p->d_blur, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount,
-                    p->d_kps, p->d_kps2, p->d_desc, p->d_counts, p->d_counts2, p->d_pts, p->d_slow, p->d_list[0], p->d_list[1], p->d_pts0, p->d_iters};
+                    p->d_kps, p->d_kps2, p->d_desc, p->d_counts, p->d_counts2, p->d_pts, p->d_slow, p->d_list[0], p->d_list[1], p->d_pts0, p->d_iters, p->d_maskShared,
+                    p->d_qx, p->d_qy, p->d_qangle, p->d_qlevel, p->d_qvalid, p->d_carryKps, p->d_carryDesc, p->d_carryCount};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
 }
@@ -1236,10 +1278,13 @@ void enqueue_pyramid(Ctx& c, BirdPlan* p, int n, bool withMask, int nLevels)
     c.launches++;
 }
 
-int enqueue_detect(Ctx& c, BirdPlan* p, int n, bool withMask)
+// maskMode: 0 none; 1 one mask per image in p->d_mask level 0 (its pyramid is built here); 2 the shared mask pyramid of
+// orbb200_bird_set_mask (p->d_maskShared, already built)
+int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
 {
     const BirdGeom& g = p->g;
-    enqueue_pyramid(c, p, n, withMask, BV_LEVELS);
+    { StageTimer t(c, 9); enqueue_pyramid(c, p, n, maskMode == 1, BV_LEVELS); }
+    StageTimer t(c, 10);
     cudaMemsetAsync(p->d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
                       p->d_candCount, n);
@@ -1248,7 +1293,8 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, bool withMask)
         c.err = "bird_select_kernel: shared memory";
         return ORBB200_ERR_CUDA;
     }
-    bird_select_kernel<<<dim3(BV_LEVELS, n), SEL_THREADS, smem, c.stream>>>(g, p->d_pyr, withMask ? p->d_mask : nullptr, p->d_cand, p->d_candCount,
+    const uint8_t* mask = maskMode == 1 ? p->d_mask : maskMode == 2 ? p->d_maskShared : nullptr;
+    bird_select_kernel<<<dim3(BV_LEVELS, n), SEL_THREADS, smem, c.stream>>>(g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount,
                                                                           p->d_lvlKp, p->d_lvlCount, c.d_status);
     c.launches++;
     bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
@@ -1403,6 +1449,105 @@ int download(Ctx& c, BirdPlan* p, int n, const orbb200_kp_t* d_kps, const int32_
 
 }  // namespace
 
+// ---- device-resident pipeline for the batched frame step (api.cu) -------------------------------------------------------
+static int ensure_step_buffers(Ctx& c, BirdPlan* p)
+{
+    if (p->d_qx) return ORBB200_OK;
+    const size_t Q = ((size_t)p->batch + 1) * p->g.kpPerImg;
+    const size_t K = (size_t)p->g.kpPerImg;
+    const bool ok = cudaMalloc((void**)&p->d_qx, Q * 4) == cudaSuccess && cudaMalloc((void**)&p->d_qy, Q * 4) == cudaSuccess &&
+                    cudaMalloc((void**)&p->d_qangle, Q * 4) == cudaSuccess && cudaMalloc((void**)&p->d_qlevel, Q * 4) == cudaSuccess &&
+                    cudaMalloc((void**)&p->d_qvalid, Q) == cudaSuccess && cudaMalloc((void**)&p->d_carryKps, K * sizeof(orbb200_kp_t)) == cudaSuccess &&
+                    cudaMalloc((void**)&p->d_carryDesc, K * 32) == cudaSuccess && cudaMalloc((void**)&p->d_carryCount, 4) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); c.err = "bird step: cudaMalloc failed"; return ORBB200_ERR_CUDA; }
+    ORBB200_CUDA_OK(c, cudaMemsetAsync(p->d_carryCount, 0, 4, c.stream));
+    p->carryValid = false;
+    return ORBB200_OK;
+}
+
+int bird_set_mask(Ctx& c, int w, int h, int nfeatures, int batch, const uint8_t* mask, size_t stride)
+{
+    BirdPlan* p = get_plan(c, w, h, nfeatures, std::max(batch, 1));
+    if (!p) return ORBB200_ERR_CUDA;
+    const BirdGeom& g = p->g;
+    if (!mask) {
+        if (p->d_maskShared) { cudaStreamSynchronize(c.stream); cudaFree(p->d_maskShared); p->d_maskShared = nullptr; }
+        return ORBB200_OK;
+    }
+    if (!p->d_maskShared) {
+        ORBB200_CUDA_OK(c, cudaMalloc((void**)&p->d_maskShared, g.planeBytes));
+        ORBB200_CUDA_OK(c, cudaMemsetAsync(p->d_maskShared, 0, g.planeBytes, c.stream));      // zero margin: masked outside the image
+    }
+    const BirdLevel& L0 = g.lv[0];
+    ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_maskShared + L0.off, L0.pitch, mask, stride, g.w, g.h, cudaMemcpyHostToDevice, c.stream));
+    for (int l = 1; l < BV_LEVELS; l++) {       // resize(prev mask level, INTER_LINEAR_EXACT) + threshold(254, TOZERO) (orb.cpp)
+        const BirdLevel& D = g.lv[l];
+        bird_resize_kernel<<<dim3((D.w + 127) / 128, D.h, 1), 128, 0, c.stream>>>(p->d_maskShared, g.planeBytes, g.lv[l - 1], D, p->d_tab, 1);
+        c.launches++;
+    }
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));      // the host mask may be pageable memory
+    return ORBB200_OK;
+}
+
+// cv::ORB detect(mask) + cornerSubPix(5,5; 40; 1e-3) + compute on n device-resident images, everything enqueued on the
+// context's stream; then the query arrays of the frame-to-frame birdview matching.  chain == false forgets the carried frame.
+int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t* d_imgs, size_t imgBytes, size_t stride, bool chain, BirdStepView* out)
+{
+    BirdPlan* p = get_plan(c, w, h, nfeatures, n);
+    if (!p) return ORBB200_ERR_CUDA;
+    int rc = ensure_step_buffers(c, p);
+    if (rc != ORBB200_OK) return rc;
+    const BirdGeom& g = p->g;
+    if (!chain || !p->carryValid) ORBB200_CUDA_OK(c, cudaMemsetAsync(p->d_carryCount, 0, 4, c.stream));
+    {
+        StageTimer t(c, 9);
+        bird_import_kernel<<<dim3(g.h, n), 128, 0, c.stream>>>(d_imgs, imgBytes, stride, p->d_pyr, g.planeBytes, g.lv[0]);
+        c.launches++;
+    }
+    rc = enqueue_detect(c, p, n, p->d_maskShared ? 2 : 0);
+    if (rc != ORBB200_OK) return rc;
+    {
+        StageTimer t(c, 11);
+        bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
+        c.launches++;
+        if (g.w >= 15 && g.h >= 15) {
+            rc = enqueue_subpix(c, p, n, p->d_counts, 0, 5, 5, 40, 0.001);
+            if (rc != ORBB200_OK) return rc;
+        }
+        bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 1);
+        c.launches++;
+    }
+    {
+        StageTimer t(c, 12);
+        rc = enqueue_compute(c, p, n, BV_LEVELS);
+        if (rc != ORBB200_OK) return rc;
+        bird_queries_kernel<<<dim3((g.kpPerImg + 255) / 256, n + 1), 256, 0, c.stream>>>(p->d_kps2, p->d_counts2, p->d_carryKps, p->d_carryCount, g.kpPerImg,
+                                                                                        p->d_qx, p->d_qy, p->d_qangle, p->d_qlevel, p->d_qvalid);
+        c.launches++;
+    }
+    ORBB200_CUDA_OK(c, cudaGetLastError());
+    out->d_kps = p->d_kps2; out->d_desc = p->d_desc; out->d_counts = p->d_counts2; out->kpPerImg = g.kpPerImg;
+    out->d_qx = p->d_qx; out->d_qy = p->d_qy; out->d_qangle = p->d_qangle; out->d_qlevel = p->d_qlevel; out->d_qvalid = p->d_qvalid;
+    out->d_carryDesc = p->d_carryDesc;
+    out->plan = p;
+    return ORBB200_OK;
+}
+
+// after the matching has been enqueued: the last frame of this step becomes the carried frame of the next one
+int bird_step_carry(Ctx& c, const BirdStepView& v, int n)
+{
+    BirdPlan* p = static_cast<BirdPlan*>(v.plan);
+    const size_t K = (size_t)p->g.kpPerImg;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_carryKps, p->d_kps2 + (size_t)(n - 1) * K, K * sizeof(orbb200_kp_t), cudaMemcpyDeviceToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_carryDesc, p->d_desc + (size_t)(n - 1) * K * 32, K * 32, cudaMemcpyDeviceToDevice, c.stream));
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(p->d_carryCount, p->d_counts2 + (n - 1), 4, cudaMemcpyDeviceToDevice, c.stream));
+    p->carryValid = true;
+    return ORBB200_OK;
+}
+
+int bird_step_status(Ctx& c) { return check_bird_status(c); }
+
 void bird_destroy(Ctx& c)
 {
     if (!c.bird) return;
@@ -1443,7 +1588,7 @@ int orbb200_bird_detect(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mas
     BirdPlan* p = get_plan(c, w, h, nfeatures, 1);
     if (!p) return ORBB200_ERR_CUDA;
     int rc = upload_images(c, p, &img, mask ? &mask : nullptr, 1, stride, mask_stride);
-    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, 1, mask != nullptr);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, 1, mask != nullptr ? 1 : 0);
     if (rc != ORBB200_OK) return rc;
     return download(c, p, 1, p->d_kps, p->d_counts, kps, nullptr, cap, n_out);
 }
@@ -1506,7 +1651,7 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     if (!p) return ORBB200_ERR_CUDA;
     const BirdGeom& g = p->g;
     int rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
-    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0);
     if (rc != ORBB200_OK) return rc;
     // cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001))   (src/Frame.cc:335-336)
     bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
@@ -1520,6 +1665,21 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     rc = enqueue_compute(c, p, n, BV_LEVELS);
     if (rc != ORBB200_OK) return rc;
     return download(c, p, n, p->d_kps2, p->d_counts2, kps, desc, cap_per_img, n_out);
+}
+
+int orbb200_bird_results_device(orbb200_ctx* ctx, int w, int h, int nfeatures, const orbb200_kp_t** d_kps, const uint8_t** d_desc,
+                                const int32_t** d_counts, int* cap_per_img)
+{
+    BIRD_ENTER(ctx);
+    BirdState& S = state(c);
+    auto it = S.plans.find(std::make_tuple(w, h, nfeatures));
+    if (it == S.plans.end()) { c.err = "bird_results_device: no birdview extraction of this size yet"; return ORBB200_ERR_ARG; }
+    BirdPlan* p = it->second;
+    if (d_kps) *d_kps = p->d_kps2;
+    if (d_desc) *d_desc = p->d_desc;
+    if (d_counts) *d_counts = p->d_counts2;
+    if (cap_per_img) *cap_per_img = p->g.kpPerImg;
+    return ORBB200_OK;
 }
 
 int orbb200_bird_extract(orbb200_ctx* ctx, const uint8_t* img, const uint8_t* mask, int w, int h, size_t stride, size_t mask_stride,

@@ -68,6 +68,19 @@ struct StepPlan {
     void* block;
 };
 
+// Cached device-side descriptors of one batched frame step (orbb200_frame_step_device); the fields up to `dF` are the cache key.
+struct FramePlan {
+    int n, kpi, birdKpi, mapN, stereo, birdWindow, birdOri, hasBird;
+    float th, nnratio, minX, minY, invW, invH, birdInvW, birdInvH, birdRatio;
+    const void* map; const void* birdKps; const void* birdQx;
+    void *oBi, *oBd, *oNm, *oM12, *oBnm;
+    FrameDev* dF;       // <- offsetof(FramePlan, dF) ends the key; front frames [0,n), birdview frames [n,2n)
+    WinJob* dJ;         // front jobs [0,nFront), birdview jobs after them
+    int nFrames, nJobs, maxNq, maxKpCap;
+    uint8_t* inView; float *u, *v, *uR, *viewcos; int32_t* level; int32_t* count;     // isInFrustum results [n][mapN], [n]
+    void* block;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -126,14 +139,17 @@ struct Ctx {
     size_t d_step_bytes = 0;
 
     std::vector<StepPlan> plans;
+    std::vector<FramePlan> framePlans;
+    uint8_t* d_fstep = nullptr;              // device staging of the host frame step
+    size_t d_fstep_bytes = 0;
 
     // per-stage timing (bench)
     bool timing = false;
     struct Pending { int stage; cudaEvent_t e0, e1; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> freeEvents;
-    float stageMs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    int stageGroups[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float stageMs[ORBB200_NUM_STAGES] = {};
+    int stageGroups[ORBB200_NUM_STAGES] = {};
 };
 
 // RAII: events around one stage when timing is on

@@ -741,8 +741,11 @@ __global__ void __launch_bounds__(128) frustum_kernel(FrustumJob J)
     bool ok = false;
     float u = 0.f, v = 0.f, uR = 0.f, viewCos = 0.f;
     int nScale = 0;
+    // batched form (J.poses != null): blockIdx.y = frame, its pose from device memory, its outputs at [frame][n]
+    const size_t fo = J.poses ? (size_t)blockIdx.y * J.n : 0;
+    const orbb200_camera_pose Fp = J.poses ? J.poses[blockIdx.y] : J.pose;
     if (i < J.n && (!J.candidate || J.candidate[i])) {
-        const orbb200_camera_pose& F = J.pose;
+        const orbb200_camera_pose& F = Fp;
         const float Px = J.pos[3 * i], Py = J.pos[3 * i + 1], Pz = J.pos[3 * i + 2];
         float Pc[3];
 #pragma unroll
@@ -776,19 +779,20 @@ __global__ void __launch_bounds__(128) frustum_kernel(FrustumJob J)
         } while (false);
     }
     if (i < J.n) {
-        J.inView[i] = ok ? 1 : 0;
-        J.u[i] = ok ? u : 0.f; J.v[i] = ok ? v : 0.f; J.uR[i] = ok ? uR : 0.f;
-        J.level[i] = ok ? nScale : 0; J.viewcos[i] = ok ? viewCos : 0.f;
+        J.inView[fo + i] = ok ? 1 : 0;
+        J.u[fo + i] = ok ? u : 0.f; J.v[fo + i] = ok ? v : 0.f; J.uR[fo + i] = ok ? uR : 0.f;
+        J.level[fo + i] = ok ? nScale : 0; J.viewcos[fo + i] = ok ? viewCos : 0.f;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(J.count, __popc(bal));
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(J.count + (J.poses ? blockIdx.y : 0), __popc(bal));
 }
 
 void launch_frustum(Ctx& c, const FrustumJob& J)
 {
-    cudaMemsetAsync(J.count, 0, sizeof(int32_t), c.stream);
+    const int frames = J.poses ? J.nFrames : 1;
+    cudaMemsetAsync(J.count, 0, sizeof(int32_t) * frames, c.stream);
     if (J.n > 0) {
-        frustum_kernel<<<(J.n + 127) / 128, 128, 0, c.stream>>>(J);
+        frustum_kernel<<<dim3((J.n + 127) / 128, frames), 128, 0, c.stream>>>(J);
         c.launches++;
     }
 }

@@ -67,6 +67,8 @@ void launch_triangulation(Ctx& c, const TriJob& J);
 // Frame::isInFrustum over a device-resident map
 struct FrustumJob {
     orbb200_camera_pose pose;
+    const orbb200_camera_pose* poses;   // device array of nFrames poses (batched form), or null: `pose`
+    int nFrames;
     float cosLimit;
     int n;
     const float* pos; const float* normal; const float* maxDist; const float* minDist; const uint8_t* candidate;

@@ -102,6 +102,17 @@ void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned
                        const int4* d_cells, int nCells, const FastSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n);
 
 void bird_destroy(Ctx& c);   // bird.cu
+// bird.cu: the birdview front-end on device-resident images, for the batched frame step (api.cu)
+struct BirdStepView {
+    const orbb200_kp_t* d_kps; const uint8_t* d_desc; const int32_t* d_counts; int kpPerImg;      // mvKeysBird / mDescriptorsBird per image
+    const float* d_qx; const float* d_qy; const float* d_qangle; const int32_t* d_qlevel; const uint8_t* d_qvalid;   // [n+1][kpPerImg], slot 0 = carried frame
+    const uint8_t* d_carryDesc;
+    void* plan;
+};
+int bird_set_mask(Ctx& c, int w, int h, int nfeatures, int batch, const uint8_t* mask, size_t stride);
+int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t* d_imgs, size_t imgBytes, size_t stride, bool chain, BirdStepView* out);
+int bird_step_carry(Ctx& c, const BirdStepView& v, int n);
+int bird_step_status(Ctx& c);
 
 // ---- kernels launchers (extract.cu) ----
 void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);

@@ -801,3 +801,64 @@ def test_frustum_empty_and_degenerate(pkg):
     k0, iv0, u0, v0, uR0, lvl0, vc0 = oracle.is_in_frustum(pos, mp["normal"], mx, mn, oracle.camera_pose(**pose))
     assert k == k0 and np.array_equal(iv, iv0) and np.array_equal(lvl, lvl0)
     assert np.array_equal(u.view(np.uint32), u0.view(np.uint32)) and np.array_equal(vc.view(np.uint32), vc0.view(np.uint32))
+
+
+# ---- the batched north-star frame step (stereo front camera + birdview), device-resident -----------------------------------
+def _oracle_frame_step(seq, mp, frames, nfeat, bird_nf, w, h, bw, bh, th, ratio, window, bird_ratio, prev_bird=None):
+    """The same frames through the oracle, one by one: what Frame::Frame + SearchLocalPoints + SearchByMatchBird compute."""
+    ex, ex2 = oracle.Extractor(nfeat, 1.2, 8, 20, 7), oracle.Extractor(nfeat, 1.2, 8, 20, 7)
+    res = []
+    for i in frames:
+        kl, dl = ex(seq["imgs"][2 * i])
+        kr, dr = ex2(seq["imgs"][2 * i + 1])
+        nst, ur, dep = oracle.compute_stereo_matches(ex, ex2, kl, dl, kr, dr, 0.537, 386.1448)
+        O = oracle.Frame(kl, dl, np.float32(0), np.float32(0), np.float32(64.0 / w), np.float32(48.0 / h), ur)
+        k0, iv, u, v, uR, lvl, vc = oracle.is_in_frustum(mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"],
+                                                         oracle.camera_pose(**seq["poses"][i]), 0.5, None)
+        nm, bi, bd, qk = oracle.search_by_projection(O, ex.scale_factors(), iv, u, v, uR, lvl, vc, mp["desc"], None, None, th, ratio)
+        bk, bdsc = oracle.bird_extract(seq["bird_imgs"][i], seq["bird_mask"], bird_nf)
+        m12, nbm = None, 0
+        if prev_bird is not None:
+            OB = oracle.Frame(bk, bdsc, np.float32(0), np.float32(0), np.float32(64.0 / bw), np.float32(48.0 / bh))
+            nbm, m12, _ = oracle.birdview_match(prev_bird[0], prev_bird[1], OB, None, window, bird_ratio, True)
+        prev_bird = (bk, bdsc)
+        res.append(dict(kl=kl, dl=dl, kr=kr, dr=dr, ur=ur, dep=dep, nm=nm, bi=bi, bd=bd, bk=bk, bdsc=bdsc, m12=m12, nbm=nbm))
+    return res, prev_bird
+
+
+def test_frame_step_vs_oracle(pkg):
+    """orbb200_frame_step_host: two consecutive calls (the second chained to the first) against the oracle frame by frame:
+    keypoints + descriptors of both cameras, mvuRight / mvDepth bits, SearchLocalPoints matches and distances, birdview
+    keypoints + descriptors, BirdviewMatch(previous, current) incl. across the call boundary."""
+    w, h, bw, bh, nfeat, bnf, nmap = 620, 188, 200, 200, 1000, 600, 1500
+    seq = synth.northstar_sequence(7, 11, w=w, h=h, bird=(bw, bh), vehicle=(40, 60))
+    orc = oracle.Extractor(nfeat, 1.2, 8, 20, 7)
+    mp = synth.northstar_map(seq, lambda im: orc(im), nmap, 3)
+    ctx = pkg.Context(nfeat, 1.2, 8, 20, 7, w, h, 8)
+    M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+    step = pkg.FrameStep(ctx, w, h, M, mb=0.537, mbf=386.1448, th=1.0, nnratio=0.8, bird_size=(bw, bh), bird_nfeatures=bnf,
+                         bird_mask=seq["bird_mask"], bird_window=15, bird_nnratio=0.99)
+    poses = [pkg.CameraPose.make(**p) for p in seq["poses"]]
+    prev = None
+    for (a, b, chain) in ((0, 4, False), (4, 7, True)):
+        out = step(seq["imgs"][2 * a:2 * b], seq["bird_imgs"][a:b], poses[a:b], chain=chain)
+        want, prev = _oracle_frame_step(seq, mp, range(a, b), nfeat, bnf, w, h, bw, bh, 1.0, 0.8, 15, 0.99, prev)
+        for j, r in enumerate(want):
+            nl, nr = out["counts"][2 * j], out["counts"][2 * j + 1]
+            assert out["kps"][2 * j][:nl].tobytes() == r["kl"].tobytes() and out["kps"][2 * j + 1][:nr].tobytes() == r["kr"].tobytes()
+            assert np.array_equal(out["desc"][2 * j][:nl], r["dl"]) and np.array_equal(out["desc"][2 * j + 1][:nr], r["dr"])
+            assert np.array_equal(out["u_right"][j][:nl].view(np.uint32), r["ur"].view(np.uint32))
+            assert np.array_equal(out["depth"][j][:nl].view(np.uint32), r["dep"].view(np.uint32))
+            assert out["map_nmatches"][j] == r["nm"] and r["nm"] > 100
+            assert np.array_equal(out["map_best_idx"][j], r["bi"])
+            assert np.array_equal(out["map_best_dist"][j][r["bi"] >= 0], r["bd"][r["bi"] >= 0])
+            nb = out["bird_counts"][j]
+            assert out["bird_kps"][j][:nb].tobytes() == r["bk"].tobytes() and np.array_equal(out["bird_desc"][j][:nb], r["bdsc"])
+            if r["m12"] is None:                      # first frame of an unchained call: nothing to match against
+                assert out["bird_nmatches"][j] == 0 and (out["bird_matches12"][j] < 0).all()
+            else:
+                assert out["bird_nmatches"][j] == r["nbm"] and r["nbm"] > 20, (j, out["bird_nmatches"][j], r["nbm"])
+                assert np.array_equal(out["bird_matches12"][j][:len(r["m12"])], r["m12"])
+    # an unchained call forgets the carried frame
+    out = step(seq["imgs"][0:4], seq["bird_imgs"][0:2], poses[0:2], chain=False)
+    assert out["bird_nmatches"][0] == 0
