@@ -433,10 +433,14 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c.streamBird, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evBirdFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evBirdJoin, cudaEventDisableTiming) != cudaSuccess)
         return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
-    if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(2, atoi(e)));
+    c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
+    if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(3, atoi(e)));
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
     c.scale.resize(nlevels); c.sigma2.resize(nlevels); c.invScale.resize(nlevels); c.invSigma2.resize(nlevels); c.quota.resize(nlevels);
@@ -522,6 +526,9 @@ void orbb200_destroy(orbb200_ctx* ctx)
     if (c.evFork) cudaEventDestroy(c.evFork);
     if (c.evJoin) cudaEventDestroy(c.evJoin);
     if (c.stream2) cudaStreamDestroy(c.stream2);
+    if (c.evBirdFork) cudaEventDestroy(c.evBirdFork);
+    if (c.evBirdJoin) cudaEventDestroy(c.evBirdJoin);
+    if (c.streamBird) cudaStreamDestroy(c.streamBird);
     if (c.stream) cudaStreamDestroy(c.stream);
     delete ctx;
 }
@@ -1470,6 +1477,26 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     const bool hasMap = p->map && p->map->n > 0, hasBird = p->bird_w > 0, stereo = p->mb > 0.f;
     if (!in || !out || !in->imgs || (hasBird && !in->bird_imgs) || (hasMap && (!in->poses || !out->map_best_idx || !out->map_best_dist || !out->map_nmatches)) ||
         (hasBird && (!out->bird_matches12 || !out->bird_nmatches))) { c.err = "frame_step: missing input or output array"; return ORBB200_ERR_ARG; }
+    // birdview front-end + the query arrays of BirdviewMatch(previous, current): independent of the front camera until the
+    // matching, FP64- and latency-bound where the front extraction is integer-ALU-bound -> on a side stream beside it
+    // (per-stage timing keeps everything on one stream so that a stage's events bracket its kernels alone)
+    BirdStepView bv{};
+    const bool fork = hasBird && c.forkBird && !c.timing;
+    if (hasBird) {
+        cudaStream_t main = c.stream;
+        if (fork) {
+            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, main));
+            ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.streamBird, c.evBirdFork, 0));
+            c.stream = c.streamBird;
+        }
+        rc = bird_step_enqueue(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, in->bird_imgs, (size_t)p->bird_h * p->bird_stride, p->bird_stride,
+                               p->chain != 0, &bv);
+        if (fork) {
+            cudaEventRecord(c.evBirdJoin, c.streamBird);
+            c.stream = main;
+        }
+        if (rc != ORBB200_OK) return rc;
+    }
     // front camera: both images of every frame in one extraction, then the stereo matcher on its pools
     rc = orbb200_extract_device(ctx, in->imgs, (size_t)p->h * p->stride, 2 * n, p->w, p->h, p->stride);
     if (rc != ORBB200_OK) return rc;
@@ -1478,13 +1505,7 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
         launch_stereo(c, n, 0, 1, 2, p->mb, p->mbf, c.d_invScale, c.d_nKept);
         c.stereoValid = true;
     }
-    // birdview front-end + the query arrays of BirdviewMatch(previous, current)
-    BirdStepView bv{};
-    if (hasBird) {
-        rc = bird_step_enqueue(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, in->bird_imgs, (size_t)p->bird_h * p->bird_stride, p->bird_stride,
-                               p->chain != 0, &bv);
-        if (rc != ORBB200_OK) return rc;
-    }
+    if (fork) ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0));
     const int kpi = c.cur->g.kpPerImg, mapN = hasMap ? p->map->n : 0;
     FramePlan key{};
     key.n = n; key.kpi = kpi; key.birdKpi = hasBird ? bv.kpPerImg : 0; key.mapN = mapN; key.stereo = stereo ? 1 : 0; key.birdWindow = p->bird_window;

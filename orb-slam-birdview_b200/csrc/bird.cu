@@ -116,14 +116,79 @@ __global__ void bird_border_kernel(uint8_t* __restrict__ pyr, unsigned planeByte
     const BirdLevel L = g.lv[level];
     const int W = L.w + 2 * BV_MARGIN, H = L.h + 2 * BV_MARGIN;
     uint8_t* B = pyr + (size_t)img * planeBytes + L.off;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * H; i += gridDim.x * blockDim.x) {
-        const int yy = i / W, xx = i - yy * W;
-        const int x = xx - BV_MARGIN, y = yy - BV_MARGIN;
-        if (x >= 0 && x < L.w && y >= 0 && y < L.h) continue;
+    // only the margin is visited: BV_MARGIN full rows above and below, then 2 * BV_MARGIN pixels beside every image row
+    const int bandPx = BV_MARGIN * W, total = 2 * bandPx + L.h * 2 * BV_MARGIN;
+    (void)H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int x, y;
+        if (i < 2 * bandPx) {
+            const int band = i >= bandPx, j = i - band * bandPx;
+            const int yy = j / W;
+            x = j - yy * W - BV_MARGIN;
+            y = band ? L.h + yy : yy - BV_MARGIN;
+        } else {
+            const int j = i - 2 * bandPx;
+            const int cc = j & (2 * BV_MARGIN - 1);
+            y = j / (2 * BV_MARGIN);
+            x = cc < BV_MARGIN ? cc - BV_MARGIN : L.w + cc - BV_MARGIN;
+        }
         int sx = x < 0 ? -x : (x >= L.w ? 2 * (L.w - 1) - x : x);
         int sy = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);
         sx = min(max(sx, 0), L.w - 1); sy = min(max(sy, 0), L.h - 1);      // (levels narrower than the margin)
         B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)sy * L.pitch + sx];
+    }
+}
+
+// The whole pyramid of one image by one CTA (batched path): levels 1..7 in turn (each from the previous one, the reference's
+// order), then the reflect-101 margins of all levels.  Seven dependent resize launches + the border launch over a batch were
+// 0.35 ms per 128 images, mostly launch-to-launch latency of many small CTAs; here an image's 0.5 MP stay in one SM's L1/L2
+// and 128 images fill 128 SMs.  Same arithmetic as bird_resize_kernel / bird_border_kernel.
+__global__ void __launch_bounds__(1024) bird_pyramid_kernel(uint8_t* __restrict__ pyr, unsigned planeBytes, BirdGeom g, const int2* __restrict__ tab,
+                                                            int nLevels)
+{
+    uint8_t* P = pyr + (size_t)blockIdx.x * planeBytes;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int l = 1; l < nLevels; l++) {
+        const BirdLevel S = g.lv[l - 1], D = g.lv[l];
+        const uint8_t* s = P + S.off;
+        uint8_t* d = P + D.off;
+        for (int y = wid; y < D.h; y += 32) {
+            const int2 ty = tab[D.tabY + y];
+            const int y0 = ty.x, y1 = min(y0 + 1, S.h - 1), b1 = ty.y, b0 = 256 - b1;
+            const uint8_t* r0 = s + (size_t)y0 * S.pitch;
+            const uint8_t* r1 = s + (size_t)y1 * S.pitch;
+            for (int x = lane; x < D.w; x += 32) {
+                const int2 tx = tab[D.tabX + x];
+                const int x0 = tx.x, x1 = min(x0 + 1, S.w - 1), a1 = tx.y, a0 = 256 - a1;
+                const uint32_t h0 = (uint32_t)(r0[x0] * a0 + r0[x1] * a1) & 0xffffu;
+                const uint32_t h1 = (uint32_t)(r1[x0] * a0 + r1[x1] * a1) & 0xffffu;
+                d[(size_t)y * D.pitch + x] = (uint8_t)min((h0 * b0 + h1 * b1 + 32768u) >> 16, 255u);
+            }
+        }
+        __syncthreads();                    // level l complete (global writes of this CTA) before level l+1 reads it
+    }
+    for (int l = 0; l < nLevels; l++) {
+        const BirdLevel L = g.lv[l];
+        uint8_t* B = P + L.off;
+        const int W = L.w + 2 * BV_MARGIN;
+        // left / right margins of the image rows first (the top / bottom bands copy whole bordered rows afterwards)
+        for (int i = threadIdx.x; i < L.h * 2 * BV_MARGIN; i += 1024) {
+            const int y = i / (2 * BV_MARGIN), cc = i & (2 * BV_MARGIN - 1);
+            const int x = cc < BV_MARGIN ? cc - BV_MARGIN : L.w + cc - BV_MARGIN;
+            int sx = x < 0 ? -x : 2 * (L.w - 1) - x;
+            sx = min(max(sx, 0), L.w - 1);
+            B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)y * L.pitch + sx];
+        }
+        __syncthreads();
+        // top / bottom bands: bordered row y <- bordered row reflect(y), byte-wise over W (rows start 32 bytes left of x = 0)
+        for (int i = threadIdx.x; i < 2 * BV_MARGIN * W; i += 1024) {
+            const int band = i >= BV_MARGIN * W, j = i - band * BV_MARGIN * W;
+            const int yy = j / W, x = j - yy * W - BV_MARGIN;
+            const int y = band ? L.h + yy : yy - BV_MARGIN;
+            int sy = y < 0 ? -y : 2 * (L.h - 1) - y;
+            sy = min(max(sy, 0), L.h - 1);
+            B[(ptrdiff_t)y * L.pitch + x] = B[(ptrdiff_t)sy * L.pitch + x];
+        }
     }
 }
 
@@ -349,25 +414,32 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
                                                                   unsigned maskPlaneBytes,      // 0: one mask pyramid for every image
                                                                   const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                                   float4* __restrict__ lvlKp, int32_t* __restrict__ lvlCount,
-                                                                  int32_t* __restrict__ status)
+                                                                  int32_t* __restrict__ status,
+                                                                  int capKey, int capN,     // this launch: sort keys (power of two) and corners its shared memory holds
+                                                                  int prevKey, int prevN)   // the previous (smaller) launch's, 0 for the first
 {
+    // The kernel is a chain of block-wide steps (latency-bound), so residency matters: it is launched in tiers of growing
+    // shared memory -- 24 KB (levels of <= 2048 corners, 9 CTAs per SM), 72 KB (<= 5120, three per SM; a 400x400 level 0 holds
+    // 3-5 k), 196 KB (the NMS bound) -- and a CTA returns at once when its level belongs to another tier.
     extern __shared__ uint32_t selSmem[];
-    uint32_t* key = selSmem;                                              // [BV_SORT_CAP]
-    float* resp = reinterpret_cast<float*>(selSmem + BV_SORT_CAP);        // [BV_SORT_CAP]
-    uint16_t* stopA = reinterpret_cast<uint16_t*>(selSmem + 2 * BV_SORT_CAP);   // [BV_SORT_CAP] left stoppers of a partition step
-    uint16_t* stopB = stopA + BV_SORT_CAP;                                      // [BV_SORT_CAP] right stoppers
+    uint32_t* key = selSmem;                                              // [capKey]
+    float* resp = reinterpret_cast<float*>(selSmem + capKey);             // [capN]
+    uint16_t* stopA = reinterpret_cast<uint16_t*>(selSmem + capKey + capN);     // [capN] left stoppers of a partition step
+    uint16_t* stopB = stopA + capN;                                       // [capN] right stoppers
     __shared__ int sCount, sScratch[SEL_THREADS / 32 + 4];
-    const int level = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const int level = blockIdx.y, img = blockIdx.x, tid = threadIdx.x;      // x = image: the long level-0 CTAs of every image are dispatched first
     const BirdLevel L = g.lv[level];
     int n = candCount[img * MAX_LEVELS + level];            // fast_cells_kernel's layout
     if (n > L.candCap || n > BV_SORT_CAP) {
-        if (tid == 0) { atomicExch(status, 3); lvlCount[img * BV_LEVELS + level] = 0; }
+        if (tid == 0 && prevKey == 0) { atomicExch(status, 3); lvlCount[img * BV_LEVELS + level] = 0; }
         return;
     }
-    const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
-    const uint8_t* M = mpyr ? mpyr + (size_t)img * maskPlaneBytes + L.off : nullptr;
     int P2 = 1;
     while (P2 < n) P2 <<= 1;
+    if (P2 > capKey || n > capN) return;                    // a later tier's level
+    if (prevKey > 0 && P2 <= prevKey && n <= prevN) return; // an earlier tier did it
+    const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
+    const uint8_t* M = mpyr ? mpyr + (size_t)img * maskPlaneBytes + L.off : nullptr;
     // key = (y << 20) | (x << 8) | score : ascending == cv::FAST's row-major output order
     for (int i = tid; i < P2; i += SEL_THREADS) {
         uint32_t k = 0xffffffffu;
@@ -763,9 +835,16 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const ui
 //     warp stay in step.  ceil(maxIters / budget) launches finish every corner.
 constexpr int S5_THREADS = 128;
 constexpr int S5_WIN = 5;                           // half window
-constexpr int S5_PW = 7, S5_PH = 24;                // patch: 7 words x 24 rows
-constexpr int S5_STRIDE = S5_PW * S5_PH + 1;        // words per thread (odd: bank spread; the pad word absorbs the 5th-word over-read)
 constexpr int S5_BUDGET = 8;
+// patch geometry for a reach of R pixels around the point it was placed on: rows [fy-(R+6), +2R+14), columns from
+// fx-(R+6) rounded down to a word, 2R+14 (+3 for the rounding) bytes wide.  R = 5: 7 words x 24 rows, 86 KB per CTA, two CTAs
+// per SM; R = 3: 6 x 20, 62 KB, three CTAs per SM (12 warps: more latency hiding for a few more re-placements).
+template <int R> struct S5Geom {
+    static constexpr int PW = (2 * R + 14 + 3 + 3) / 4, PH = 2 * R + 14;
+    static constexpr int STRIDE = (PW * PH) | 1;    // words per thread, odd (bank spread); >= PW*PH+1 absorbs the 5th-word over-read
+    static constexpr int DXMAX = 4 * PW - 14, DYMAX = PH - 14;
+    static_assert(STRIDE > PW * PH && ((DXMAX >> 2) + 4) <= PW, "patch layout");
+};
 
 __device__ __forceinline__ float s5_byte(unsigned w, int k)
 {
@@ -788,8 +867,10 @@ struct S5Args {
     int* slowList; int* slowCount;                   // corners for the generic kernel
 };
 
-__global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Args A)
+template <int R, int MINB>
+__global__ void __launch_bounds__(S5_THREADS, MINB) bird_subpix5_kernel(const S5Args A)
 {
+    constexpr int S5_PW = S5Geom<R>::PW, S5_PH = S5Geom<R>::PH, S5_STRIDE = S5Geom<R>::STRIDE;
     extern __shared__ unsigned sPatch[];            // [S5_THREADS][S5_STRIDE]
     __shared__ double sMask[121];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -809,9 +890,9 @@ __global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Arg
     // new patch around (cIx, cIy); false: it would not lie inside the image
     auto place_patch = [&]() -> bool {
         const float fxf = floorf(cIx), fyf = floorf(cIy);
-        // columns [fx-11 rounded down to 4, +28), rows [fy-11, +24)
-        if (!(fxf >= 14.f && fxf <= (float)(cols - 17) && fyf >= 11.f && fyf <= (float)(rows - 13))) return false;
-        X0 = ((int)fxf - 11) & ~3; Y0 = (int)fyf - 11;
+        // columns [fx-(R+6) rounded down to 4, +4*PW), rows [fy-(R+6), +PH) inside the image
+        if (!(fxf >= (float)(R + 9) && fxf <= (float)(cols - 4 * S5_PW + R + 6) && fyf >= (float)(R + 6) && fyf <= (float)(rows - S5_PH + R + 6))) return false;
+        X0 = ((int)fxf - (R + 6)) & ~3; Y0 = (int)fyf - (R + 6);
         srcOff = (size_t)img * A.imgStrideBytes + (size_t)Y0 * pitch + X0;
         return true;
     };
@@ -867,7 +948,7 @@ __global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Arg
         const float centerx = __fsub_rn(cIx, 6.f), centery = __fsub_rn(cIy, 6.f);      // (13 - 1) * 0.5f
         const float fpx = floorf(centerx), fpy = floorf(centery);
         const int dx = (int)fpx - X0, dy = (int)fpy - Y0;
-        if (!(dx >= 0 && dx <= 14 && dy >= 0 && dy <= 10)) {      // window left the staged patch (also NaN)
+        if (!(dx >= 0 && dx <= S5Geom<R>::DXMAX && dy >= 0 && dy <= S5Geom<R>::DYMAX)) {      // window left the staged patch (also NaN)
             if (place_patch()) stage = true; else to_generic();
             continue;
         }
@@ -911,6 +992,11 @@ __global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Arg
                     const int ii = r - 3;
                     const double py = (double)(ii - S5_WIN);
                     const double* mrow = sMask + ii * 11;
+                    // x * k is exact in double for k in {0, +-1, +-2, +-4}; then fma(x, k, y) == x*k + y with its single
+                    // rounding, so the reference's "gxx*px + gxy*py" (two products, one sum) needs one multiply less
+                    // wherever px (compile time) or py (per row, warp-uniform) is such a k: 87 % of the window.
+                    const int apy = abs(ii - S5_WIN);
+                    const bool pyExact = apy != 3 && apy != 5;
 #pragma unroll
                     for (int j = 0; j < 11; j++) {
                         const double m = mrow[j];
@@ -920,9 +1006,15 @@ __global__ void __launch_bounds__(S5_THREADS, 2) bird_subpix5_kernel(const S5Arg
                         const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
                         const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
                         const double px = (double)(j - S5_WIN);
+                        constexpr int dummy = 0; (void)dummy;
+                        const bool pxExact = (j - S5_WIN) != 3 && (j - S5_WIN) != -3 && (j - S5_WIN) != 5 && (j - S5_WIN) != -5;
                         sa = __dadd_rn(sa, gxx); sb = __dadd_rn(sb, gxy); sc = __dadd_rn(sc, gyy);
-                        sbb1 = __dadd_rn(sbb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
-                        sbb2 = __dadd_rn(sbb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
+                        double t1, t2;
+                        if (pxExact) { t1 = __fma_rn(gxx, px, __dmul_rn(gxy, py)); t2 = __fma_rn(gxy, px, __dmul_rn(gyy, py)); }
+                        else if (pyExact) { t1 = __fma_rn(gxy, py, __dmul_rn(gxx, px)); t2 = __fma_rn(gyy, py, __dmul_rn(gxy, px)); }
+                        else { t1 = __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)); t2 = __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)); }
+                        sbb1 = __dadd_rn(sbb1, t1);
+                        sbb2 = __dadd_rn(sbb2, t2);
                     }
                 }
 #pragma unroll
@@ -1091,42 +1183,62 @@ __global__ void __launch_bounds__(128) bird_blur_kernel(const uint8_t* __restric
 
 // computeOrbDescriptors (orb.cpp, WTA_K 2): one warp per keypoint, one descriptor byte per lane; the keypoint's angle is
 // taken as given, its position is cvRound(pt / layerScale) on the blurred layer.
+constexpr int BD_R = 19, BD_ROWS = 2 * BD_R + 1, BD_WORDS = 11;      // descriptor window: 39 rows x 44 bytes
+
 __global__ void __launch_bounds__(256) bird_describe_kernel(BirdGeom g, const uint8_t* __restrict__ blur, const orbb200_kp_t* __restrict__ kps,
                                                             const int32_t* __restrict__ counts, uint8_t* __restrict__ desc)
 {
     __shared__ float sPX[16 * 32], sPY[16 * 32];
+    __shared__ unsigned sDescPatch[8][BD_ROWS * BD_WORDS];
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 512; i += blockDim.x) {
         const int o = (i & 15) * 32 + (i >> 4);
         sPX[o] = (float)c_patX[i]; sPY[o] = (float)c_patY[i];
     }
     __syncthreads();
-    const int gk = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
-    if (gk >= counts[img]) return;
-    const orbb200_kp_t kp = kps[(size_t)img * g.kpPerImg + gk];
-    const BirdLevel L = g.lv[kp.octave];
-    constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);
-    const float ang = __fmul_rn(kp.angle, factorPI);
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);                    // == host cosf/sinf for all but ~1e-8 of inputs
-    const float a = (float)cd, b = (float)sd;
-    const int cx = __float2int_rn(__fmul_rn(kp.x, L.invScale)), cy = __float2int_rn(__fmul_rn(kp.y, L.invScale));
-    const uint8_t* bc = blur + (size_t)img * g.planeBytes + L.off + (ptrdiff_t)cy * L.pitch + cx;
-    int val = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int t[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int idx = (2 * k + e) * 32 + lane;
-            const float px = sPX[idx], py = sPY[idx];
-            const int xx = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
-            const int yy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
-            t[e] = bc[yy * L.pitch + xx];
+    // every CTA pays for the pattern table above, so a CTA walks over many keypoints of its image (the grid is a few CTAs
+    // per image, not one per eight keypoints: 72 k CTAs, most of them past the image's count, cost 0.6 ms per 128 images)
+    const int nk = min(counts[img], g.kpPerImg);
+    for (int gk = blockIdx.x * (blockDim.x >> 5) + (tid >> 5); gk < nk; gk += gridDim.x * (blockDim.x >> 5)) {
+        const orbb200_kp_t kp = kps[(size_t)img * g.kpPerImg + gk];
+        const BirdLevel L = g.lv[kp.octave];
+        constexpr float factorPI = (float)(3.14159265358979323846 / 180.0);
+        const float ang = __fmul_rn(kp.angle, factorPI);
+        double sd, cd;
+        sincos((double)ang, &sd, &cd);                    // == host cosf/sinf for all but ~1e-8 of inputs
+        const float a = (float)cd, b = (float)sd;
+        const int cx = __float2int_rn(__fmul_rn(kp.x, L.invScale)), cy = __float2int_rn(__fmul_rn(kp.y, L.invScale));
+        // The rotated pattern stays within 19 pixels of the centre (max radius 18.4): the warp first copies that 39-row window of
+        // the blurred level into shared memory with aligned word loads (11 words per row from the column rounded down to 4; the
+        // planes carry a 32-pixel margin, so the window is always inside the allocation), then every lane gathers its 16 bytes
+        // from there.  512 scattered byte loads from global memory per keypoint were 3.4 ns per keypoint; this is the same
+        // staging idea as the front camera's describe_kernel (which uses a TMA box).
+        unsigned* patch = sDescPatch[tid >> 5];
+        const int X0 = (cx - BD_R) & ~3, dxc = cx - X0;
+        const uint8_t* win = blur + (size_t)img * g.planeBytes + L.off + (ptrdiff_t)(cy - BD_R) * L.pitch + X0;
+        for (int i = lane; i < BD_ROWS * BD_WORDS; i += 32) {
+            const int r = i / BD_WORDS, w = i - r * BD_WORDS;
+            patch[i] = __ldg(reinterpret_cast<const unsigned*>(win + (size_t)r * L.pitch) + w);
         }
-        val |= (t[0] < t[1]) << k;
+        __syncwarp();
+        const uint8_t* bc = reinterpret_cast<const uint8_t*>(patch) + BD_R * (BD_WORDS * 4) + dxc;
+        int val = 0;
+    #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int t[2];
+    #pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int idx = (2 * k + e) * 32 + lane;
+                const float px = sPX[idx], py = sPY[idx];
+                const int xx = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.f)) - 0x4B400000;
+                const int yy = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.f)) - 0x4B400000;
+                t[e] = bc[yy * (BD_WORDS * 4) + xx];
+            }
+            val |= (t[0] < t[1]) << k;
+        }
+        desc[((size_t)img * g.kpPerImg + gk) * 32 + lane] = (uint8_t)val;
+        __syncwarp();                       // the next keypoint's window overwrites this warp's patch
     }
-    desc[((size_t)img * g.kpPerImg + gk) * 32 + lane] = (uint8_t)val;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1264,6 +1376,11 @@ int upload_images(Ctx& c, BirdPlan* p, const uint8_t* const* imgs, const uint8_t
 void enqueue_pyramid(Ctx& c, BirdPlan* p, int n, bool withMask, int nLevels)
 {
     const BirdGeom& g = p->g;
+    if (n >= 8 && !withMask) {              // batches: one CTA builds an image's whole pyramid
+        bird_pyramid_kernel<<<n, 1024, 0, c.stream>>>(p->d_pyr, g.planeBytes, g, p->d_tab, nLevels);
+        c.launches++;
+        return;
+    }
     for (int l = 1; l < nLevels; l++) {
         const BirdLevel& D = g.lv[l];
         dim3 grid((D.w + 127) / 128, D.h, n);
@@ -1289,13 +1406,23 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
                       p->d_candCount, n);
     const size_t smem = (size_t)BV_SORT_CAP * 12;      // keys + responses + two u16 stopper lists
-    if (smem > 48 * 1024 && smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel, SMEM_BIRD_SELECT)) {
+    if (smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel, SMEM_BIRD_SELECT)) {
         c.err = "bird_select_kernel: shared memory";
         return ORBB200_ERR_CUDA;
     }
     const uint8_t* mask = maskMode == 1 ? p->d_mask : maskMode == 2 ? p->d_maskShared : nullptr;
-    bird_select_kernel<<<dim3(BV_LEVELS, n), SEL_THREADS, smem, c.stream>>>(g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount,
-                                                                          p->d_lvlKp, p->d_lvlCount, c.d_status);
+    struct Tier { int key, n; };
+    const Tier tiers[3] = {{2048, 2048}, {8192, 5120}, {BV_SORT_CAP, BV_SORT_CAP}};
+    for (int t = 0; t < 3; t++) {
+        // levels that can reach this tier at all (candCap is the NMS bound w*h/4 of a level; levels shrink with their index)
+        int nl = BV_LEVELS;
+        if (t > 0) { nl = 0; while (nl < BV_LEVELS && g.lv[nl].candCap > tiers[t - 1].n) nl++; }
+        if (nl == 0) break;
+        bird_select_kernel<<<dim3(n, nl), SEL_THREADS, (size_t)tiers[t].key * 4 + (size_t)tiers[t].n * 8, c.stream>>>(
+            g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount, c.d_status,
+            tiers[t].key, tiers[t].n, t ? tiers[t - 1].key : 0, t ? tiers[t - 1].n : 0);
+        if (t < 2) c.launches++;
+    }
     c.launches++;
     bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
     c.launches++;
@@ -1355,8 +1482,10 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
             S.workInts = workInts;
         }
         cudaMemsetAsync(S.d_work5, 0, workInts * sizeof(int), c.stream);
-        const size_t smem = sizeof(unsigned) * S5_THREADS * S5_STRIDE;
-        if (smem > ensure_max_dynamic_smem(c.device, (const void*)bird_subpix5_kernel, SMEM_BIRD_SUBPIX)) { c.err = "bird_subpix5_kernel: shared memory"; return ORBB200_ERR_CUDA; }
+        const bool wide = c.subpixCtasPerSm <= 2;       // reach 5, two CTAs per SM; otherwise reach 3, three CTAs per SM
+        const size_t smem = sizeof(unsigned) * S5_THREADS * (wide ? S5Geom<5>::STRIDE : S5Geom<3>::STRIDE);
+        const void* kfn = wide ? (const void*)bird_subpix5_kernel<5, 2> : (const void*)bird_subpix5_kernel<3, 3>;
+        if (smem > ensure_max_dynamic_smem(c.device, kfn, wide ? SMEM_BIRD_SUBPIX : SMEM_BIRD_SUBPIX3)) { c.err = "bird_subpix5_kernel: shared memory"; return ORBB200_ERR_CUDA; }
         const long long slots = (long long)n * g.kpPerImg;
         const int grid = std::max(1, (int)std::min<long long>((long long)sms * c.subpixCtasPerSm, (slots + S5_THREADS - 1) / S5_THREADS));
         int* heads = S.d_work5;                      // [phases]
@@ -1371,7 +1500,8 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
             A.listInCount = ph == 0 ? nullptr : outCounts + (ph - 1);
             A.head = heads + ph;
             A.listOut = p->d_list[ph & 1]; A.listOutCount = outCounts + ph;
-            bird_subpix5_kernel<<<grid, S5_THREADS, smem, c.stream>>>(A);
+            if (wide) bird_subpix5_kernel<5, 2><<<grid, S5_THREADS, smem, c.stream>>>(A);
+            else bird_subpix5_kernel<3, 3><<<grid, S5_THREADS, smem, c.stream>>>(A);
             c.launches++;
         }
         bird_subpix_thread_kernel<<<std::min(sms, std::max(n, 1) * 4), SP_THREADS, 0, c.stream>>>(
@@ -1409,7 +1539,7 @@ int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels)
     for (int l = 0; l < nLevels; l++) { maxW = std::max(maxW, g.lv[l].w); maxH = std::max(maxH, g.lv[l].h); }
     bird_blur_kernel<<<dim3((maxW + 127) / 128, (maxH + 15) / 16, n * BV_LEVELS), 128, 0, c.stream>>>(p->d_pyr, p->d_blur, g.planeBytes, g, gk, nLevels);
     c.launches++;
-    bird_describe_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_blur, p->d_kps2, p->d_counts2, p->d_desc);
+    bird_describe_kernel<<<dim3(n >= 8 ? 12 : (g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_blur, p->d_kps2, p->d_counts2, p->d_desc);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;

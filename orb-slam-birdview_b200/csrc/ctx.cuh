@@ -37,7 +37,7 @@ struct WinJob;
 // "what I asked for" lets a second context on the same GPU lower the first one's limit.  Each kernel that may need
 // more than 48 KB is instead raised ONCE per device to the device's opt-in maximum; the record is process-wide.
 // Returns that maximum (bytes) or 0 after a CUDA error.  slot: one small integer per kernel instantiation.
-enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_SLOTS };
+enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_SLOTS };
 inline size_t ensure_max_dynamic_smem(int device, const void* kernel, int slot)
 {
     static std::mutex mu;
@@ -86,9 +86,12 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // side branch of the extraction graph (blur runs beside FAST + octree)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t streamBird = nullptr;       // the birdview front-end of the batched frame step runs beside the front-camera extraction
+    cudaEvent_t evBirdFork = nullptr, evBirdJoin = nullptr;
+    bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)
     std::string err;
     long long launches = 0;
-    int subpixCtasPerSm = 2;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS)
+    int subpixCtasPerSm = 3;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS: 1-2 reach-5 patches, 3 reach-3)
 
     // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)
     int nfeatures = 0;

@@ -2,6 +2,7 @@
 inputs.  Bar: bit-exact keypoints (coordinates, octave, response, angle), descriptors, match indices and
 Hamming distances.  Descriptor tolerance per BASELINE.json north_star: bit-exact wherever the angle agrees
 within 1e-4 rad, mismatch rate <= 0.1 % (we expect and assert 0 on these inputs and report the rate)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -329,9 +330,37 @@ def test_matchers_vs_committed_golden(pkg):
 
 
 def test_stereo_step_device_matches_host_calls(pkg):
-    """The batched device path used by bench.py == per-call host API == oracle."""
+    """The batched C2 step with caller-made queries (orbb200_stereo_step_device / _host) == oracle."""
+    ctx = pkg.Context(2000, 1.2, 8, 20, 7, 1241, 376, 6)
+    L = ctx._L
+    n, nq, w, h = 3, 600, 1241, 376
+    imgs = np.stack([im for i in range(n) for im in (synth.synth_frame(h, w, 4242 + i), synth.shift_frame(synth.synth_frame(h, w, 4242 + i), -7, 0))])
+    orc = oracle.Extractor(2000, 1.2, 8, 20, 7)
+    ref = [orc(im) for im in imgs]
+    qs = [synth.projection_queries(ref[2 * i][0], ref[2 * i][1], w, h, nq, 99 + i) for i in range(n)]
+    q = {k: np.ascontiguousarray(np.stack([x[k] for x in qs])) for k in qs[0]}
+    S = pkg.ProjQueries()
+    S.q_valid, S.q_u, S.q_v, S.q_uR = (q[k].ctypes.data for k in ("valid", "u", "v", "uR"))
+    S.q_level, S.q_viewcos, S.q_desc, S.q_obs_pos = (q[k].ctypes.data for k in ("level", "viewcos", "desc", "obs_pos"))
+    cap = ctx.max_keypoints
+    kps, desc, cnt = np.zeros((2 * n, cap), pkg.KP_DTYPE), np.zeros((2 * n, cap, 32), np.uint8), np.zeros(2 * n, np.int32)
+    bi, bd, nm = np.zeros((n, nq), np.int32), np.zeros((n, nq), np.int32), np.zeros(n, np.int32)
+    ctx.check(L.orbb200_stereo_step_host(ctx._h, imgs.ctypes.data, n, w, h, w, C.byref(S), nq, 1.0, 0.8, 0.0, 0.0, 64.0 / w, 48.0 / h,
+                                         kps.ctypes.data, desc.ctypes.data, cap, cnt.ctypes.data, bi.ctypes.data, bd.ctypes.data, nm.ctypes.data), "stereo_step_host")
+    ctx.sync()
+    for i in range(n):
+        kl, dl = ref[2 * i]
+        F = oracle.Frame(kl, dl, np.float32(0), np.float32(0), np.float32(64.0 / w), np.float32(48.0 / h))
+        n0, bi0, bd0, _ = oracle.search_by_projection(F, orc.scale_factors(), q["valid"][i], q["u"][i], q["v"][i], q["uR"][i], q["level"][i],
+                                                      q["viewcos"][i], q["desc"][i], q["obs_pos"][i], None, 1.0, 0.8)
+        assert kps[2 * i][:cnt[2 * i]].tobytes() == kl.tobytes() and np.array_equal(desc[2 * i][:len(kl)], dl)
+        assert int(nm[i]) == n0 and n0 > 0 and np.array_equal(bi[i], bi0) and np.array_equal(bd[i][bi0 >= 0], bd0[bi0 >= 0])
+
+
+def test_bench_steps_match_oracle(pkg):
+    """What bench.py times (orbb200_frame_step_device / _host on both workloads, full-size frames) == oracle, frame by frame."""
     bench = pytest.importorskip("bench")
-    res = bench.parity_check(n_frames=3, nq=600, w=1241, h=376, nfeatures=2000)
+    res = bench.parity_check(n_frames=3)
     assert res["ok"], res
 
 
