@@ -44,7 +44,7 @@ typedef struct orbb200_frame orbb200_frame;
 int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFactor, int nlevels,
                    int iniThFAST, int minThFAST, int max_w, int max_h, int max_batch);
 void orbb200_destroy(orbb200_ctx* ctx);
-const char* orbb200_last_error(const orbb200_ctx* ctx);   /* ctx may be NULL: last create() error */
+const char* orbb200_last_error(const orbb200_ctx* ctx);   /* ctx may be NULL: last create() error of the calling thread */
 int orbb200_sync(orbb200_ctx* ctx);
 /* cudaStream_t of the context, as void* (for callers that enqueue their own work around ours) */
 void* orbb200_stream(orbb200_ctx* ctx);

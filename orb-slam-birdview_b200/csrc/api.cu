@@ -31,7 +31,8 @@ struct orbb200_map {
 
 namespace orbb200 {
 
-static std::string g_create_err;
+// last orbb200_create() failure of THIS host thread (Tracking, LocalMapping and LoopClosing each create their own contexts)
+static thread_local std::string g_create_err;
 static std::mutex g_create_mu;
 
 static inline int cvRoundF(float v) { return (int)lrintf(v); }

@@ -891,3 +891,79 @@ def test_frame_step_vs_oracle(pkg):
     # an unchained call forgets the carried frame
     out = step(seq["imgs"][0:4], seq["bird_imgs"][0:2], poses[0:2], chain=False)
     assert out["bird_nmatches"][0] == 0
+
+
+def test_three_host_threads_three_contexts(pkg):
+    """The reference calls the front-end from three threads at once (Tracking: extraction + projection searches; LocalMapping:
+    SearchForTriangulation, src/LocalMapping.cc:278; LoopClosing: SearchByBoW, src/LoopClosing.cc:265), one ORBextractor /
+    ORBmatcher each.  Three host threads with their own context on ONE GPU, running concurrently for a few hundred calls, must
+    each reproduce the oracle exactly."""
+    import threading
+    imgs = [synth.synth_frame(240, 320, 900 + i) for i in range(4)]
+    orc = oracle.Extractor(500, 1.2, 8, 20, 7)
+    want_ex = [orc(im) for im in imgs]
+    t = cases.triangulation_case(800, 800, 620, 188, 61, n_nodes=40)
+    want_tri = oracle.search_for_triangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], t["fv1"], t["fv2"],
+                                               t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"], False, True)
+    b = cases.bow_case(800, 800, 620, 188, 81, n_nodes=40)
+    O2 = oracle.Frame(b["k2"], b["d2"], b["grid"]["min_x"], b["grid"]["min_y"], b["grid"]["inv_w"], b["grid"]["inv_h"])
+    want_bow = oracle.search_by_bow(b["d1"], b["k1"]["angle"], b["valid1"], O2, b["valid2"], b["fv1"], b["fv2"], 0.75, True, False)
+    errors, start = [], threading.Barrier(3)
+    reps = 60
+
+    def tracking():
+        try:
+            ex = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_size=(320, 240))
+            start.wait()
+            for r in range(reps):
+                k, d = ex(imgs[r % 4])
+                k0, d0 = want_ex[r % 4]
+                assert k.tobytes() == k0.tobytes() and np.array_equal(d, d0), f"extract rep {r}"
+        except Exception as e:            # noqa: BLE001
+            errors.append(("tracking", repr(e)))
+
+    def local_mapping():
+        try:
+            ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+            m = pkg.ORBmatcher(ctx, 0.6, True)
+            start.wait()
+            for r in range(reps):
+                n, pairs = m.SearchForTriangulation(t["k1"], t["d1"], t["uR1"], t["has1"], t["k2"], t["d2"], t["uR2"], t["has2"], t["fv1"], t["fv2"],
+                                                    t["F12"], t["ex"], t["ey"], t["sf2"], t["sigma2"], False)
+                assert n == want_tri[0] and np.array_equal(pairs, want_tri[1]), f"triangulation rep {r}"
+        except Exception as e:            # noqa: BLE001
+            errors.append(("local_mapping", repr(e)))
+
+    def loop_closing():
+        try:
+            ctx = pkg.Context(2000, 1.2, 8, 20, 7, 64, 64)
+            F2 = pkg.Frame(ctx, b["k2"], b["d2"], b["grid"]["min_x"], b["grid"]["min_y"], b["grid"]["inv_w"], b["grid"]["inv_h"])
+            m = pkg.ORBmatcher(ctx, 0.75, True)
+            start.wait()
+            for r in range(reps):
+                nm, out = m.SearchByBoW(b["d1"], b["k1"]["angle"], b["valid1"], F2, b["fv1"], b["fv2"], b["valid2"], False)
+                assert nm == want_bow[0] and np.array_equal(out, want_bow[1]), f"bow rep {r}"
+        except Exception as e:            # noqa: BLE001
+            errors.append(("loop_closing", repr(e)))
+
+    threads = [threading.Thread(target=f) for f in (tracking, local_mapping, loop_closing)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    assert want_tri[0] > 0 and want_bow[0] > 0
+
+
+def test_two_contexts_different_feature_budgets(pkg):
+    """the dynamic shared-memory opt-in is per (device, kernel); a second context with a smaller node table must not
+    lower the first one's limit."""
+    img = synth.synth_frame(376, 1241, 31)
+    big = pkg.ORBextractor(8000, 1.2, 8, 20, 7, max_size=(1241, 376))
+    k1, d1 = big(img)
+    small = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_size=(1241, 376))
+    small(img)
+    k2, d2 = big(img)
+    assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    k0, d0 = oracle.Extractor(8000, 1.2, 8, 20, 7)(img)
+    assert k1.tobytes() == k0.tobytes() and np.array_equal(d1, d0)
