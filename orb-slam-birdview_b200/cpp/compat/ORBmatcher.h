@@ -1,32 +1,51 @@
-// Stand-in for the reference's include/ORBmatcher.h: the class declaration (include/ORBmatcher.h:38-120) reduced to the
-// methods ../ORBmatcher_b200.cc defines.  Inside the reference tree its own header declares them (and the rest).
+// Stand-in for the reference's include/ORBmatcher.h: the same class declaration (include/ORBmatcher.h:38-120 -- the signatures
+// ARE the drop-in contract) over the compat object model.  Inside the reference tree its own header is used.
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
 
+#include <set>
+#include <utility>
 #include <vector>
 
-#include "Frame.h"
-#include "KeyFrame.h"
 #include "MapPoint.h"
+#include "KeyFrame.h"
+#include "Frame.h"
 
 namespace ORB_SLAM2
 {
+using std::pair;
+using std::vector;
 
 class ORBmatcher
 {
 public:
-    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+    ORBmatcher(float nnratio=0.6, bool checkOri=true);
 
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
 
-    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th=3);
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th);
+
+    int SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint*> &vpMapPointMatches);
+    int SearchByBoW(KeyFrame *pKF1, KeyFrame* pKF2, std::vector<MapPoint*> &vpMatches12);
+
+    int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize=10);
 
     int SearchForTriangulation(KeyFrame *pKF1, KeyFrame* pKF2, cv::Mat F12,
-                               std::vector<std::pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo);
+                               std::vector<pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo);
 
-    int BirdviewMatch(const Frame &F1, const Frame &F2, std::vector<int> &vnMatches12, int windowSize = 10);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint *> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th);
 
-    int SearchByMatchBird(Frame &CurrentFrame, const Frame &LastFrame, const int windowSize = 10);
+    int Fuse(KeyFrame* pKF, const vector<MapPoint *> &vpMapPoints, const float th=3.0);
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint);
+
+    int BirdviewMatch(Frame &F1, Frame &F2, vector<int> &vnMatches12, vector<cv::Point2f> &vPrevMatched, int windowSize=10);
+    int BirdviewMatch(const Frame &F1, const Frame &F2, vector<int> &vnMatches12, int windowSize = 10);
+    int SearchByProjectionBird(Frame &F, const std::vector<MapPointBird*> &vpMapPointsBird, const float r=4);
+    int SearchByMatchBird(Frame &CurrentFrame, const Frame &LastFrame, const int windowSize=10);
+    int SearchByMatchBird(KeyFrame *pKF, Frame &F, std::vector<MapPointBird*> &vpMapPointMatchesBird, const float r=10);
 
 public:
     static const int TH_LOW;
@@ -34,6 +53,10 @@ public:
     static const int HISTO_LENGTH;
 
 protected:
+    bool CheckDistEpipolarLine(const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const cv::Mat &F12, const KeyFrame *pKF);
+    float RadiusByViewingCos(const float &viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3);
+
     float mfNNratio;
     bool mbCheckOrientation;
 };

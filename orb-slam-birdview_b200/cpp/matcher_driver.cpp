@@ -19,8 +19,6 @@
 
 using namespace ORB_SLAM2;
 
-float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mfGridElementWidthInvBirdview, Frame::mfGridElementHeightInvBirdview;
-float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
 static std::vector<unsigned char> buf;
 static size_t off = 0;
@@ -98,6 +96,7 @@ int main(int argc, char** argv)
     const unsigned char* d2 = take<unsigned char>((size_t)n2 * 32);
     Cur.mDescriptorsBird = rows32(d2, n2);
     Cur.mvpMapPointsBird.assign(n2, static_cast<MapPointBird*>(NULL));
+    Last.mvScaleFactors = F.mvScaleFactors; Cur.mvScaleFactors = F.mvScaleFactors;
     ORBmatcher matcherBird(nnratioBird, true);                  // Tracking.cc:325-326: new ORBmatcher(0.99,true)
     std::vector<int> vnMatches12;
     const int nmBird = matcherBird.BirdviewMatch(Last, Cur, vnMatches12, window);
@@ -139,10 +138,11 @@ int main(int argc, char** argv)
         const float* ls2 = take<float>(8);
         KF2.mvScaleFactors.assign(sf2, sf2 + 8);
         KF2.mvLevelSigma2.assign(ls2, ls2 + 8);
-        KF1.Ow = cv::Mat(3, 1, CV_32F); KF2.tcw = cv::Mat(3, 1, CV_32F); KF2.Rcw = cv::Mat(3, 3, CV_32F);
+        KF1.mvScaleFactors = KF2.mvScaleFactors;
+        KF1.Ow = cv::Mat(3, 1, CV_32F); KF1.Tcw = cv::Mat::eye(4, 4, CV_32F); KF2.Tcw = cv::Mat::eye(4, 4, CV_32F);
         cv::Mat F12(3, 3, CV_32F);
-        for (int i = 0; i < 3; i++) { KF1.Ow.at<float>(i) = tf[4 + i]; KF2.tcw.at<float>(i) = tf[7 + i]; }
-        for (int i = 0; i < 9; i++) { KF2.Rcw.at<float>(i / 3, i % 3) = tf[10 + i]; F12.at<float>(i / 3, i % 3) = tf[19 + i]; }
+        for (int i = 0; i < 3; i++) { KF1.Ow.at<float>(i) = tf[4 + i]; KF2.Tcw.at<float>(i, 3) = tf[7 + i]; }
+        for (int i = 0; i < 9; i++) { KF2.Tcw.at<float>(i / 3, i % 3) = tf[10 + i]; F12.at<float>(i / 3, i % 3) = tf[19 + i]; }
         ORBmatcher matcherTri(0.6, true);                       // LocalMapping.cc:225: ORBmatcher matcher(0.6,false) uses checkOri false; true exercises the histogram
         nTri = matcherTri.SearchForTriangulation(&KF1, &KF2, F12, vMatchedIndices, onlyStereo != 0);
     }
