@@ -475,10 +475,32 @@ class GpuArm:
         ctx = self.ctxs[ci]
         ctx.check(self.L.orbb200_frame_step_device(ctx._h, C.byref(P), C.byref(I), C.byref(O)), "frame_step_device")
 
-    def step_host(self, full, p, ci=0):
-        P, I, O = self._io(full, p, ci, True)
+    def step_host(self, full, p, ci=0, sub=None):
+        """one host-buffer call; sub = (s, S): frames [s*B/S, (s+1)*B/S) of the batch only (a step fed as S smaller calls)"""
+        P, I, O = self._io(full, p, ci, True) if sub is None else self._io_sub(full, p, ci, *sub)
         ctx = self.ctxs[ci]
         ctx.check(self.L.orbb200_frame_step_host(ctx._h, C.byref(P), C.byref(I), C.byref(O)), "frame_step_host")
+
+    def _io_sub(self, full, p, ci, s, S):
+        """structs of sub-batch s of S: the same host buffers as the whole-batch call, offset to the sub-batch's frames"""
+        key = (full, p, ci, "sub", s, S)
+        if key in self._structs:
+            return self._structs[key]
+        assert not full and self.B % S == 0
+        pk = self.pkg
+        P0, I0, O0 = self._io(full, p, ci, True)
+        n = self.B // S
+        f0 = s * n
+        P, I, O = self._params(full, p, ci), pk.FrameStepInputs(), pk.FrameStepOutputs()
+        P.n_frames = n
+        src, o = self.h_in[p], self.h_out[ci]
+        I.imgs = src["imgs"][2 * f0:].data_ptr()
+        I.poses = src["poses"].data_ptr() + f0 * C.sizeof(pk.CameraPose)
+        O.kps, O.desc, O.counts = o["kps"][2 * f0:].data_ptr(), o["desc"][2 * f0:].data_ptr(), o["counts"][2 * f0:].data_ptr()
+        O.map_best_idx, O.map_best_dist, O.map_nmatches = o["bi"][f0:].data_ptr(), o["bd"][f0:].data_ptr(), o["nm"][f0:].data_ptr()
+        O.cap, O.bird_cap = self.cap, self.bcap
+        self._structs[key] = (P, I, O)
+        return self._structs[key]
 
     def h2d_bytes(self, full):
         i = self.h_in[0]
@@ -656,23 +678,26 @@ def leg_stages(arm, full, K):
     return ms, n
 
 
-def leg_e2e(arm, full, K, Wm, NE, barrier):
-    """K steps through the host-buffer C-ABI call, NE contexts in flight; wall clock around the region; returns seconds"""
+def leg_e2e(arm, full, K, Wm, NE, barrier, S=1):
+    """K steps through the host-buffer C-ABI call, NE contexts in flight; wall clock around the region; returns seconds.
+    S > 1: a step's batch is handed over as S calls of B/S frames each (what a caller does to overlap its uploads with the
+    device work from the first frame on: the un-overlapped first upload and last download of the timed region shrink S-fold)."""
     torch, P = arm.torch, arm.P
-    for s in range(max(P * NE, 2 * NE)):       # pre-warm: plans + staging buffers of every (input batch, context) pair
-        arm.step_host(full, s % P, s % NE)
+    sub = (lambda s: None) if S == 1 else (lambda s: (s, S))
+    for j in range(max(P * NE, 2 * NE) * S):   # pre-warm: plans + staging buffers of every (input batch, context) pair
+        arm.step_host(full, (j // S) % P, j % NE, sub(j % S))
     arm.sync()
-    for s in range(Wm):
-        arm.step_host(full, s % P, s % NE)
+    for j in range(Wm * S):
+        arm.step_host(full, (j // S) % P, j % NE, sub(j % S))
     arm.sync()
     barrier()
     t0 = time.perf_counter()
-    for s in range(K):
-        ci = s % NE
-        if s >= NE:
-            arm.ctxs[ci].sync()          # results of step s-NE are on the host: consume before reuse
+    for j in range(K * S):
+        ci = j % NE
+        if j >= NE:
+            arm.ctxs[ci].sync()          # results of call j-NE are on the host: consume before reuse
             _ = int(arm.h_out[ci]["nm"][0])
-        arm.step_host(full, s % P, ci)
+        arm.step_host(full, (j // S) % P, ci, sub(j % S))
     arm.sync()
     _ = int(arm.h_out[0]["nm"][0])
     torch.cuda.synchronize()
@@ -864,6 +889,7 @@ def run_ours(args):
     host_bind = bind_near_gpu(local, not args.no_numa_bind)
     B, P = args.frames_per_step, args.pools
     NE = max(2, args.e2e_contexts)
+    SUB = args.e2e_calls_per_step if args.e2e_calls_per_step > 0 and B % max(args.e2e_calls_per_step, 1) == 0 else 1
     arm = GpuArm(local, B, P, n_ctx=NE, with_bird=not args.headline_only)
     arm.setup_data(100000 * rank + 2000)
     K, Wm = args.steps, max(args.warmup, 3)
@@ -893,9 +919,9 @@ def run_ours(args):
     if world > 1 and not args.no_e2e:
         # the same leg with rank 0 alone on the host side: numerator of the end-to-end scaling efficiency
         if rank == 0:
-            e2e_solo_s = leg_e2e(arm, False, K, Wm, NE, lambda: torch.cuda.synchronize())
+            e2e_solo_s = leg_e2e(arm, False, K, Wm, NE, lambda: torch.cuda.synchronize(), SUB)
         barrier()
-    e2e_s = leg_e2e(arm, False, K, Wm, NE, barrier) if not args.no_e2e else float("nan")
+    e2e_s = leg_e2e(arm, False, K, Wm, NE, barrier, SUB) if not args.no_e2e else float("nan")
     h2d_conc = h2d_rate(arm, barrier)
     # ---- C3_full: the north-star frame ----
     full = None
@@ -1010,7 +1036,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": config_dict(B, P),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": arm.h2d_bytes(False), "d2h_bytes_per_step": arm.d2h_bytes(False),
-                "ms_per_step": e2e_ms / K, "contexts_in_flight": NE, "h2d_copy_gbs_measured": h2d_gbs, "host_binding": host_bind},
+                "ms_per_step": e2e_ms / K, "contexts_in_flight": NE, "calls_per_step": SUB, "frames_per_call": B // SUB, "h2d_copy_gbs_measured": h2d_gbs, "host_binding": host_bind},
         "e2e_h2d_gbs_all_ranks_at_once_min_rank": h2d_conc_min, "e2e_h2d_gbs_all_ranks_at_once_sum": h2d_conc_sum,
         "e2e_scaling_efficiency": (e2e_value / world) / (B * K / e2e_solo_s) if e2e_solo_s else (1.0 if world == 1 else None),
         "e2e_solo_rank0_frames_per_s": (B * K / e2e_solo_s) if e2e_solo_s else None,
@@ -1135,7 +1161,8 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true", help="skip C1 / C4 / C5 / per-frame legs")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
     ap.add_argument("--device-contexts", type=int, default=2, help="contexts (streams) the device-resident leg alternates its steps over")
-    ap.add_argument("--e2e-contexts", type=int, default=3, help="contexts (streams) the host-buffer leg keeps in flight")
+    ap.add_argument("--e2e-contexts", type=int, default=6, help="contexts (streams) the host-buffer leg keeps in flight")
+    ap.add_argument("--e2e-calls-per-step", type=int, default=4, help="the C2 host-buffer leg hands a step's batch over as this many calls (frames_per_step must be a multiple)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the CPUs nearest its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()

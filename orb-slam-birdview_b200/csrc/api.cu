@@ -441,7 +441,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
-    if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(3, atoi(e)));
+    if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(4, atoi(e)));
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
     c.scale.resize(nlevels); c.sigma2.resize(nlevels); c.invScale.resize(nlevels); c.invSigma2.resize(nlevels); c.quota.resize(nlevels);
@@ -928,7 +928,7 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     J.th = th; J.nnratio = nnratio; J.mbf = mbf;
     float* dsf = A.take<float>(MAX_LEVELS);
     cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream);
-    J.scaleFactors = dsf;
+    J.scaleFactors = dsf; J.nLevels = c.nlevels;
     J.q_valid = Q.dev_queries ? Q.valid : upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
     if (Q.level && Q.dev_queries) J.q_level = Q.level;
     else if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
@@ -1190,7 +1190,7 @@ int orbb200_search_for_triangulation(orbb200_ctx* ctx,
     J.item_e2 = (const int32_t*)up(ie2.data(), 4 * (size_t)nItems); J.nItems = nItems;
     J.F12 = (const float*)up(F12, 36); J.ex = ex; J.ey = ey;
     J.scaleFactors2 = (const float*)up(scale_factors2, 4 * (size_t)c.nlevels); J.levelSigma2_2 = (const float*)up(level_sigma2_2, 4 * (size_t)c.nlevels);
-    J.onlyStereo = only_stereo; J.checkOri = check_ori;
+    J.onlyStereo = only_stereo; J.checkOri = check_ori; J.nLevels2 = c.nlevels;
     J.match12 = A.take<int32_t>(std::max(n1, 1)); J.pairs = A.take<int32_t>(2 * (size_t)std::max(n1, 1)); J.npairs = A.take<int32_t>(1);
     launch_triangulation(c, J);
     ORBB200_CUDA_OK(c, cudaGetLastError());
@@ -1376,7 +1376,7 @@ int orbb200_stereo_step_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t i
             f.minX = min_x; f.minY = min_y; f.invW = inv_w; f.invH = inv_h;
             WinJob& J = hJ[i];
             memset(&J, 0, sizeof(J));
-            J.frame = key.dF + i; J.nq = nq; J.mode = WM_PROJ; J.kpCap = kpi; J.th = th; J.nnratio = nnratio; J.scaleFactors = dsf;
+            J.frame = key.dF + i; J.nq = nq; J.mode = WM_PROJ; J.kpCap = kpi; J.th = th; J.nnratio = nnratio; J.scaleFactors = dsf; J.nLevels = c.nlevels;
             const size_t o = (size_t)i * nq;
             J.q_valid = d_queries->q_valid ? d_queries->q_valid + o : nullptr;
             J.q_x = d_queries->q_u + o; J.q_y = d_queries->q_v + o; J.q_aux = d_queries->q_uR + o; J.q_level = d_queries->q_level + o;
@@ -1555,7 +1555,7 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
             WinJob J;
             memset(&J, 0, sizeof(J));
             const size_t o = (size_t)i * mapN;
-            J.frame = key.dF + i; J.nq = mapN; J.mode = WM_PROJ; J.kpCap = kpi; J.th = p->th; J.nnratio = p->nnratio; J.scaleFactors = dsf;
+            J.frame = key.dF + i; J.nq = mapN; J.mode = WM_PROJ; J.kpCap = kpi; J.th = p->th; J.nnratio = p->nnratio; J.scaleFactors = dsf; J.nLevels = c.nlevels;
             J.q_valid = key.inView + o; J.q_x = key.u + o; J.q_y = key.v + o; J.q_aux = key.uR + o; J.q_level = key.level + o; J.q_viewcos = key.viewcos + o;
             J.q_desc = p->map->d_desc;             // the map points' representative descriptors, shared by every frame
             J.scratch = A.take<int>(win_scratch_ints(kpi, mapN));
@@ -1574,7 +1574,7 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
             memset(&J, 0, sizeof(J));
             const size_t qo = (size_t)i * bk;
             J.frame = key.dF + n + i; J.nq = bk; J.mode = WM_BIRD; J.levelMode = 0; J.checkOri = p->bird_check_ori; J.kpCap = bk;
-            J.th = (float)p->bird_window; J.nnratio = p->bird_nnratio; J.scaleFactors = dsf;
+            J.th = (float)p->bird_window; J.nnratio = p->bird_nnratio; J.scaleFactors = dsf; J.nLevels = c.nlevels;
             J.q_valid = bv.d_qvalid + qo; J.q_x = bv.d_qx + qo; J.q_y = bv.d_qy + qo; J.q_level = bv.d_qlevel + qo; J.q_angle = bv.d_qangle + qo;
             J.q_desc = i == 0 ? bv.d_carryDesc : bv.d_desc + (size_t)(i - 1) * bk * 32;
             J.scratch = A.take<int>(win_scratch_ints(bk, bk));

@@ -833,9 +833,16 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const ui
 //   * corners need between 2 and 40 iterations, so a lane keeps a corner for at most `budget` iterations per turn and then
 //     queues it for the next launch ("phase"): the tail of a launch is at most `budget` iterations long, and the lanes of a
 //     warp stay in step.  ceil(maxIters / budget) launches finish every corner.
+#ifndef ORBB200_S5_UNROLL
+#define ORBB200_S5_UNROLL 1
+#endif
+constexpr int S5_UNROLL = ORBB200_S5_UNROLL;     // rows of the 14-row sample loop per unrolled body
 constexpr int S5_THREADS = 128;
 constexpr int S5_WIN = 5;                           // half window
-constexpr int S5_BUDGET = 8;
+#ifndef ORBB200_S5_BUDGET
+#define ORBB200_S5_BUDGET 8
+#endif
+constexpr int S5_BUDGET = ORBB200_S5_BUDGET;
 // patch geometry for a reach of R pixels around the point it was placed on: rows [fy-(R+6), +2R+14), columns from
 // fx-(R+6) rounded down to a word, 2R+14 (+3 for the rounding) bytes wide.  R = 5: 7 words x 24 rows, 86 KB per CTA, two CTAs
 // per SM; R = 3: 6 x 20, 62 KB, three CTAs per SM (12 warps: more latency hiding for a few more re-placements).
@@ -968,7 +975,7 @@ __global__ void __launch_bounds__(S5_THREADS, MINB) bird_subpix5_kernel(const S5
         for (int j = 0; j < 13; j++) { wm2[j] = 0.f; wm1[j] = 0.f; }
 #pragma unroll
         for (int j = 0; j < 14; j++) top[j] = 0.f;
-#pragma unroll 1
+#pragma unroll S5_UNROLL
         for (int r = 0; r < 14; r++, rowp += S5_PW) {
             {   // source row r: 14 bytes starting at patch byte column dx
                 const unsigned w0 = rowp[0], w1 = rowp[1], w2 = rowp[2], w3 = rowp[3], w4 = rowp[4];
@@ -1482,10 +1489,11 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
             S.workInts = workInts;
         }
         cudaMemsetAsync(S.d_work5, 0, workInts * sizeof(int), c.stream);
-        const bool wide = c.subpixCtasPerSm <= 2;       // reach 5, two CTAs per SM; otherwise reach 3, three CTAs per SM
-        const size_t smem = sizeof(unsigned) * S5_THREADS * (wide ? S5Geom<5>::STRIDE : S5Geom<3>::STRIDE);
-        const void* kfn = wide ? (const void*)bird_subpix5_kernel<5, 2> : (const void*)bird_subpix5_kernel<3, 3>;
-        if (smem > ensure_max_dynamic_smem(c.device, kfn, wide ? SMEM_BIRD_SUBPIX : SMEM_BIRD_SUBPIX3)) { c.err = "bird_subpix5_kernel: shared memory"; return ORBB200_ERR_CUDA; }
+        // reach of the staged patch: 5 (two CTAs per SM), 3 (three) or 2 (four CTAs per SM at 125 registers: 16 resident warps)
+        const int ctas = c.subpixCtasPerSm;
+        const size_t smem = sizeof(unsigned) * S5_THREADS * (ctas <= 2 ? S5Geom<5>::STRIDE : ctas == 3 ? S5Geom<3>::STRIDE : S5Geom<2>::STRIDE);
+        const void* kfn = ctas <= 2 ? (const void*)bird_subpix5_kernel<5, 2> : ctas == 3 ? (const void*)bird_subpix5_kernel<3, 3> : (const void*)bird_subpix5_kernel<2, 4>;
+        if (smem > ensure_max_dynamic_smem(c.device, kfn, ctas <= 2 ? SMEM_BIRD_SUBPIX : ctas == 3 ? SMEM_BIRD_SUBPIX3 : SMEM_BIRD_SUBPIX2)) { c.err = "bird_subpix5_kernel: shared memory"; return ORBB200_ERR_CUDA; }
         const long long slots = (long long)n * g.kpPerImg;
         const int grid = std::max(1, (int)std::min<long long>((long long)sms * c.subpixCtasPerSm, (slots + S5_THREADS - 1) / S5_THREADS));
         int* heads = S.d_work5;                      // [phases]
@@ -1500,8 +1508,9 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
             A.listInCount = ph == 0 ? nullptr : outCounts + (ph - 1);
             A.head = heads + ph;
             A.listOut = p->d_list[ph & 1]; A.listOutCount = outCounts + ph;
-            if (wide) bird_subpix5_kernel<5, 2><<<grid, S5_THREADS, smem, c.stream>>>(A);
-            else bird_subpix5_kernel<3, 3><<<grid, S5_THREADS, smem, c.stream>>>(A);
+            if (ctas <= 2) bird_subpix5_kernel<5, 2><<<grid, S5_THREADS, smem, c.stream>>>(A);
+            else if (ctas == 3) bird_subpix5_kernel<3, 3><<<grid, S5_THREADS, smem, c.stream>>>(A);
+            else bird_subpix5_kernel<2, 4><<<grid, S5_THREADS, smem, c.stream>>>(A);
             c.launches++;
         }
         bird_subpix_thread_kernel<<<std::min(sms, std::max(n, 1) * 4), SP_THREADS, 0, c.stream>>>(

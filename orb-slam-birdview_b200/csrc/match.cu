@@ -319,6 +319,7 @@ __device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
     W.x = J.q_x[q]; W.y = J.q_y[q];
     if (mode == WM_PROJ) {
         const int lvl = J.q_level[q];
+        if ((unsigned)lvl >= (unsigned)J.nLevels) return false;         // outside the pyramid: no scale factor to read
         float r = J.q_viewcos[q] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
         if (J.th != 1.0f) r = __fmul_rn(r, J.th);
         W.r = __fmul_rn(r, J.scaleFactors[lvl]);
@@ -326,6 +327,7 @@ __device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
         W.urCheck = true; W.urRef = J.q_aux[q]; W.urTol = W.r;
     } else if (mode == WM_PROJ_FRAME) {
         const int oct = J.q_level[q];
+        if ((unsigned)oct >= (unsigned)J.nLevels) return false;
         W.r = __fmul_rn(J.th, J.scaleFactors[oct]);
         if (J.levelMode == 1) { W.minL = oct; W.maxL = -1; }
         else if (J.levelMode == 2) { W.minL = 0; W.maxL = oct; }
@@ -376,6 +378,7 @@ __device__ __forceinline__ void static_candidates(const WinJob& J, const FrameDe
                 const float ex = __fsub_rn(W.x, kp.x), ey = __fsub_rn(W.y, kp.y);
                 float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
                 const float kpr = F.uRight ? F.uRight[idx] : -1.f;
+                if ((unsigned)kp.octave >= (unsigned)J.nLevels) return;  // keypoint outside the pyramid: no sigma to gate with
                 const float inv = J.invLevelSigma2[kp.octave];
                 if (kpr >= 0) {
                     const float er = __fsub_rn(J.q_aux[q], kpr);
@@ -647,6 +650,7 @@ __global__ void __launch_bounds__(256) triangulation_kernel(TriJob J)
         const int dist = hamming256(qa, qb, d2[0], d2[1]);
         if (dist > TH_LOW) continue;
         const orbb200_kp_t kp2 = J.kps2[idx2];
+        if ((unsigned)kp2.octave >= (unsigned)J.nLevels2) continue;       // outside the keyframe's pyramid tables
         if (!st1 && !st2) {
             const float dx = __fsub_rn(J.ex, kp2.x), dy = __fsub_rn(J.ey, kp2.y);
             if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, J.scaleFactors2[kp2.octave])) continue;

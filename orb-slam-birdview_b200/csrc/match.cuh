@@ -13,6 +13,7 @@ struct WinJob {
     int nq, mode, levelMode, checkOri, kpCap;
     float th, nnratio, mbf;
     const float* scaleFactors;
+    int nLevels;                // entries of scaleFactors / invLevelSigma2: queries and keypoints with a level outside [0, nLevels) are skipped
     const uint8_t* q_valid;     // may be null (all valid)
     const float* q_x;
     const float* q_y;
@@ -47,7 +48,7 @@ struct TriJob {
     const int32_t* fv2_idx;
     const int32_t* item_idx1; const int32_t* item_b2; const int32_t* item_e2; int nItems;
     const float* F12; float ex, ey;
-    const float* scaleFactors2; const float* levelSigma2_2;
+    const float* scaleFactors2; const float* levelSigma2_2; int nLevels2;
     int onlyStereo, checkOri;
     int32_t* match12;           // [n1]
     int32_t* pairs;             // [n1][2]
