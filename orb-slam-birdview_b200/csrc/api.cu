@@ -195,6 +195,30 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
             }
         }
     }
+    // the same cells, grouped for fast_strip_kernel: the cells of a row that the reference keeps (a prefix of the columns), split
+    // evenly into groups whose image (first iniX rounded down to 4 .. last maxX) fits the 136-pixel tile
+    std::vector<int4> groups;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        if (L.nCells == 0) continue;
+        int kept = 0;                                       // columns with iniX < maxBX - 6
+        while (kept < L.nCols && FAST_BORDER + kept * L.wCell < L.maxBX - 6) kept++;
+        if (kept == 0) continue;
+        const int gmax = std::max(1, std::min(FS_MAX_CELLS, (2 * (FS_PITCH - 3) - 9) / L.wCell));
+        const int ngr = (kept + gmax - 1) / gmax;
+        for (int i = 0; i < L.nRows; i++) {
+            const int iniY = FAST_BORDER + i * L.hCell;
+            if (iniY >= L.maxBY - 3) continue;
+            const int maxY = std::min(iniY + L.hCell + 6, L.maxBY);
+            for (int q = 0; q < ngr; q++) {
+                const int j0 = (int)((long)q * kept / ngr), j1 = (int)((long)(q + 1) * kept / ngr);     // cells [j0, j1)
+                const int x0 = FAST_BORDER + j0 * L.wCell;
+                const int x1 = std::min(FAST_BORDER + (j1 - 1) * L.wCell + L.wCell + 6, L.maxBX);
+                push_fast_group(groups, st.fastStrip, x0, iniY, x1, maxY, l, j1 - j0, L.wCell, L.off, L.pitch, L.candOff, L.candCap);
+            }
+        }
+    }
+    st.nFastGroups = (int)(groups.size() / 3);
     std::vector<int4> btiles, rtiles;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
@@ -274,6 +298,7 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     bool ok = up((void**)&st.d_xtab, xtab.data(), xtab.size() * sizeof(int2)) &&
               up((void**)&st.d_ytab, ytab.data(), ytab.size() * sizeof(int4)) &&
               up((void**)&st.d_cells, cells.data(), cells.size() * sizeof(int4)) &&
+              up((void**)&st.d_groups, groups.data(), groups.size() * sizeof(int4)) &&
               up((void**)&st.d_blurTiles, btiles.data(), btiles.size() * sizeof(int4)) &&
               up((void**)&st.d_resizeTiles, rtiles.data(), rtiles.size() * sizeof(int4)) &&
               up((void**)&st.d_dmaps, &st.dmaps, sizeof(st.dmaps)) &&
@@ -441,6 +466,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
+    c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
     if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(4, atoi(e)));
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
@@ -521,7 +547,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps); cudaFree(kv.second.d_rmaps);
+    for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_groups); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps); cudaFree(kv.second.d_rmaps);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
     if (c.evFork) cudaEventDestroy(c.evFork);

@@ -29,6 +29,9 @@ struct ShapeTables {
     std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count
     int nFastCells = 0;         // entries of d_cells (cells the reference skips at the image edge are not listed)
     FastSmem fastSmem;          // shared-memory carve of fast_cells_kernel
+    int4* d_groups = nullptr;   // the same cells as groups of up to 4 per cell row for fast_strip_kernel, 3 x int4 each
+    int nFastGroups = 0;
+    FastStripSmem fastStrip;
 };
 
 struct WinJob;
@@ -37,7 +40,7 @@ struct WinJob;
 // "what I asked for" lets a second context on the same GPU lower the first one's limit.  Each kernel that may need
 // more than 48 KB is instead raised ONCE per device to the device's opt-in maximum; the record is process-wide.
 // Returns that maximum (bytes) or 0 after a CUDA error.  slot: one small integer per kernel instantiation.
-enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
+enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_FAST_STRIP, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
 inline size_t ensure_max_dynamic_smem(int device, const void* kernel, int slot)
 {
     static std::mutex mu;
@@ -91,6 +94,7 @@ struct Ctx {
     bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)
     std::string err;
     long long launches = 0;
+    bool fastCells = false;                  // ORBB200_FAST_CELLS=1: grid FAST with one CTA per cell (fast_cells_kernel) instead of the strip form
     int subpixCtasPerSm = 3;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS: 1-2 reach-5 patches, 3 reach-3, 4 reach-2)
 
     // ORBextractor parameters and tables (src/ORBextractor.cc:410-470)

@@ -682,6 +682,215 @@ __global__ void __launch_bounds__(FT_THREADS, ORBB200_FT_MINBLK) fast_cells_kern
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Grid FAST, strip form: one CTA per GROUP of up to four horizontally adjacent cells of one cell row (the reference's cells,
+// src/ORBextractor.cc:789-829: same rectangles, same per-cell isolation, same per-cell threshold fallback).
+// fast_cells_kernel above (one CTA per 30-px cell; still used for cv::ORB's whole-level tiles of the birdview path) spends
+// 69 % of its executed instructions on integer glue (profiles/r2_summary.md: VIMNMX[3] 21 %, LDS 10 %): per-item index
+// divisions, list lookups across warp segments, per-cell setup for 900 pixels.  This form removes the glue instead of the math:
+//   * a tile is ~130 x 37 pixels; warp w owns rows w, w+4, ...: a row step is 32 adjacent pixel pairs, every ring offset is an
+//     immediate, consecutive lanes read consecutive words (no bank conflicts), no index arithmetic per item;
+//   * each warp compacts ITS rows' survivors into its own list segment (ballot + popc), runs the score network on that segment
+//     and compacts the pairs that reach the threshold in place: no barrier and no cross-warp lookup between the three steps;
+//   * cell isolation is a pair of lane masks per pixel pair (left / right neighbour belongs to the same cell), applied to the
+//     packed 3x3 maximum; the per-cell fallback (cv::FAST(minThFAST) only for cells that cv::FAST(iniThFAST) left empty) is a
+//     third mask, so the second pass runs on the lanes of the empty cells only;
+//   * the score tile is cleared once: a pair that fails the quick test at the lower threshold also failed it at the higher one
+//     and was never written.
+// Scores, maxima and candidates are identical to fast_cells_kernel's (same network, same NMS rule); tests/test_gpu_parity.py
+// compares candidate sets per level with the oracle.
+// ---------------------------------------------------------------------------------------------------
+#ifndef ORBB200_FS_MINBLK
+#define ORBB200_FS_MINBLK 6
+#endif
+constexpr int FS_THREADS = 128, FS_WARPS = FS_THREADS / 32;
+constexpr int FS_LOADS = 5;        // global words in flight per thread while the tile is filled
+constexpr int FS_ROWS = 4;         // rows per quick-test step
+
+template <int P>
+__global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
+                                                                                 int minTh, int iniTh, const int4* __restrict__ groups,
+                                                                                 uint32_t* __restrict__ cand, int32_t* __restrict__ candCount,
+                                                                                 int tileRows, int scrRows, int segCap, int clistCap)
+{
+    extern __shared__ uint32_t fsSmem[];
+    uint32_t* tile = fsSmem;                             // [tileRows][P]: word 1 + m of a row = pixels (2m, 2m+1) as u16x2 (+ bias)
+    uint32_t* scr = tile + ((tileRows * P + 3) & ~3);    // [scrRows][P]: scores, same layout, one zero row above and below (16-byte aligned)
+    uint32_t* inMask = scr + ((scrRows * P + 3) & ~3);   // per pair word: lanes inside the group's inner columns
+    uint32_t* lMask = inMask + P;                        //                lanes whose left neighbour lies in the same cell
+    uint32_t* rMask = lMask + P;                         //                lanes whose right neighbour lies in the same cell
+    uint32_t* p2Mask = rMask + P;                        //                lanes of cells the first pass left empty
+    uint32_t* cellIdx = p2Mask + P;                      //                cell of lane 0 | cell of lane 1 << 8
+    uint32_t* clist = cellIdx + P;                       // [clistCap] candidates of this group
+    uint16_t* lists = reinterpret_cast<uint16_t*>(clist + clistCap);   // [FS_WARPS][segCap] pair codes (row << 7 | pair word)
+    __shared__ int sN, sBase, sCellHit[FS_MAX_CELLS];
+
+    const int img = blockIdx.y;
+    const int4 ga = __ldg(groups + 3 * blockIdx.x);      // {x0|y0<<16, x1|y1<<16, level, cells}
+    const int4 gb = __ldg(groups + 3 * blockIdx.x + 1);  // {level byte offset, pitch, candOff, candCap}
+    const int4 gc = __ldg(groups + 3 * blockIdx.x + 2);  // {wCell, -, -, -}
+    const int x0 = ga.x & 0xffff, y0 = ga.x >> 16, x1 = ga.y & 0xffff, y1 = ga.y >> 16;
+    const int level = ga.z, nCells = ga.w, wCell = gc.x;
+    const int pitch = gb.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int xa = x0 & ~3;
+    const int th = y1 - y0, hi = th - 6;
+    const int firstIn = x0 + 3, endIn = x1 - 3;          // inner columns of the group [firstIn, endIn), level coordinates
+    if (hi <= 0 || endIn <= firstIn) return;
+    const int m0 = (firstIn - xa) >> 1, m1 = (endIn - 1 - xa) >> 1, npr = m1 - m0 + 1;
+    const int nw = (x1 - xa + 3) >> 2;                   // 32-bit words loaded per row
+
+    if (tid < FS_MAX_CELLS) sCellHit[tid] = 0;
+    if (tid == 0) sN = 0;
+    // per-pair lane masks
+    for (int i = tid; i < P; i += FS_THREADS) {
+        uint32_t in = 0, lm = 0, rm = 0, ci = 0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int x = xa + 2 * (i - 1) + e;
+            if (x >= firstIn && x < endIn) {
+                const int k = min((x - firstIn) / wCell, nCells - 1);
+                const int cs = firstIn + k * wCell, ce = min(cs + wCell, endIn);
+                const uint32_t L = 0xffffu << (16 * e);
+                in |= L;
+                if (x > cs) lm |= L;
+                if (x < ce - 1) rm |= L;
+                ci |= (uint32_t)k << (8 * e);
+            }
+        }
+        inMask[i] = in; lMask[i] = lm; rMask[i] = rm; cellIdx[i] = ci; p2Mask[i] = in;
+    }
+    for (int i = tid; i < (scrRows * P + 3) >> 2; i += FS_THREADS) reinterpret_cast<uint4*>(scr)[i] = make_uint4(0, 0, 0, 0);
+    // the group's image: 32-bit words widened to u16 pairs (+ bias), the (row, word) items flattened over the CTA and fetched
+    // FS_LOADS at a time before any is stored (one global round trip per batch instead of one per row); words next to the loaded
+    // span hold the bias so that masked lanes stay in range (see fast_cells_kernel)
+    {
+        const uint8_t* S = pyr + (size_t)img * pyrBytes + (unsigned)gb.x + (size_t)y0 * pitch + xa;
+        const uint32_t magicNw = (uint32_t)gc.y;         // 2^32 / nw + 1
+        const int total = th * nw;
+        for (int base = tid; base < total; base += FS_THREADS * FS_LOADS) {
+            uint32_t v[FS_LOADS];
+            int o[FS_LOADS];
+#pragma unroll
+            for (int j = 0; j < FS_LOADS; j++) {
+                const int i = min(base + j * FS_THREADS, total - 1);
+                const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
+                const int k = i - r * nw;
+                v[j] = *reinterpret_cast<const uint32_t*>(S + (unsigned)(r * pitch + 4 * k));
+                o[j] = r * P + 2 * k;
+            }
+#pragma unroll
+            for (int j = 0; j < FS_LOADS; j++) {         // (surplus items rewrite the last word with the same value)
+                tile[o[j] + 1] = __byte_perm(v[j], FT_BIAS, 0x5150);
+                tile[o[j] + 2] = __byte_perm(v[j], FT_BIAS, 0x5352);
+            }
+        }
+        for (int r = tid; r < th; r += FS_THREADS) {
+            uint32_t* t = tile + r * P;
+            t[0] = FT_BIAS; t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS;
+        }
+    }
+    __syncthreads();
+
+    const unsigned ltmask = (1u << lane) - 1u;
+    uint16_t* myq = lists + wid * segCap;
+    for (int pass = 0; pass < 2; pass++) {
+        const int thr = pass ? minTh : iniTh;
+        const uint32_t Tp = (uint32_t)(min(max(thr, 0), 255) + 1) * 0x00010001u;
+        const uint32_t* laneMask = pass ? p2Mask : inMask;
+
+        // ---- quick test: this warp's blocks of FS_ROWS rows, 32 pairs x FS_ROWS rows per step (one address computation; the rows
+        //      below are immediates) ----
+        int nq = 0;
+        for (int rr0 = wid * FS_ROWS; rr0 < hi; rr0 += FS_WARPS * FS_ROWS) {
+            const uint32_t* tb = tile + (rr0 + 3) * P + 1 + m0;
+            for (int c0 = 0; c0 < npr; c0 += 32) {
+                const int c = min(c0 + lane, npr - 1);              // surplus lanes repeat the last pair
+                const bool valid = c0 + lane < npr;
+                const uint32_t lm = pass ? laneMask[1 + m0 + c] : 0xffffffffu;
+                const int code0 = (rr0 << 7) | (m0 + c);
+#pragma unroll
+                for (int j = 0; j < FS_ROWS; j++) {                 // rows past hi read the words behind the tile (the score tile); not listed
+                    const uint32_t hit = fast_may_pass<P>(tb + c + j * P, Tp) & lm;
+                    const bool on = hit != 0 && valid && rr0 + j < hi;
+                    const unsigned bal = __ballot_sync(0xffffffffu, on);
+                    if (on) myq[nq + __popc(bal & ltmask)] = (uint16_t)(code0 + (j << 7));
+                    nq += __popc(bal);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- scores of this warp's survivors; the pairs that reach the threshold are compacted in place ----
+        int nk = 0;
+        for (int b = 0; b < nq; b += 32) {
+            const int code = myq[min(b + lane, nq - 1)];
+            const int rr = code >> 7, m = code & 127;
+            const uint32_t* t = tile + (rr + 3) * P + 1 + m;
+            uint32_t r[16];
+            fast_load_ring<P>(t, r);
+            uint32_t sc = fast_score_pair(t[0], r) & laneMask[1 + m];   // pixels outside the inner columns (second pass: outside the empty cells) score 0
+            scr[(rr + 1) * P + 1 + m] = sc;
+            const bool keep = ((int)(sc & 0xffffu) >= thr || (int)(sc >> 16) >= thr) && b + lane < nq;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();                                           // every lane has read its code before slots are rewritten
+            if ((bal >> lane) & 1u) myq[nk + __popc(bal & ltmask)] = (uint16_t)code;
+            nk += __popc(bal);
+        }
+        __syncthreads();                                            // all scores of the pass are in the tile
+
+        // ---- 3x3 strict-greater NMS inside the pixel's own cell + threshold (raw neighbour scores suffice) ----
+        for (int b = 0; b < nk; b += 32) {
+            if (b + lane < nk) {
+                const int code = myq[b + lane];
+                const int rr = code >> 7, m = code & 127;
+                const uint32_t* q = scr + (rr + 1) * P + 1 + m;
+                const uint32_t w = q[0];
+                const uint32_t u0 = q[-P - 1], u1 = q[-P], u2 = q[-P + 1];
+                const uint32_t c0 = q[-1], c2 = q[1];
+                const uint32_t d0 = q[P - 1], d1 = q[P], d2 = q[P + 1];
+                const uint32_t left = max3s(__funnelshift_r(u0, u1, 16), __funnelshift_r(c0, w, 16), __funnelshift_r(d0, d1, 16)) & lMask[1 + m];
+                const uint32_t right = max3s(__funnelshift_r(u1, u2, 16), __funnelshift_r(w, c2, 16), __funnelshift_r(d1, d2, 16)) & rMask[1 + m];
+                const uint32_t nb = max3s(left, right, __vmaxs2(u1, d1));
+                const uint32_t ci = cellIdx[1 + m];
+                const int ly = y0 + rr + 3;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int sv = (w >> (16 * e)) & 0xffff, nv = (nb >> (16 * e)) & 0xffff;     // masked lanes hold sv == 0
+                    if (sv >= thr && sv > nv) {
+                        const int slot = atomicAdd(&sN, 1);
+                        const int lx = xa + 2 * m + e;
+                        if (slot < clistCap) clist[slot] = (uint32_t)(lx - FAST_BORDER) | ((uint32_t)(ly - FAST_BORDER) << 12) | ((uint32_t)sv << 24);
+                        sCellHit[(ci >> (8 * e)) & 0xff] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (pass) break;
+        // cells without a corner take the second pass (reference :809-816)
+        bool again = false;
+        for (int k = 0; k < nCells; k++) again |= sCellHit[k] == 0;
+        if (!again) break;
+        for (int i = tid; i < P; i += FS_THREADS) {
+            const uint32_t ci = cellIdx[i], in = inMask[i];
+            uint32_t pm = 0;
+            if ((in & 0xffffu) && sCellHit[ci & 0xff] == 0) pm |= 0xffffu;
+            if ((in >> 16) && sCellHit[(ci >> 8) & 0xff] == 0) pm |= 0xffff0000u;
+            p2Mask[i] = pm;
+        }
+        __syncthreads();
+    }
+    const int nEmit = min(sN, clistCap);
+    if (nEmit == 0) return;
+    if (tid == 0) sBase = atomicAdd(&candCount[img * MAX_LEVELS + level], nEmit);
+    __syncthreads();
+    uint32_t* out = cand + (size_t)img * candPerImg + (unsigned)gb.z;
+    const int base = sBase, candCap = gb.w;
+    for (int i = tid; i < nEmit; i += FS_THREADS)
+        if (base + i < candCap) out[base + i] = clist[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // DistributeOctTree (reference src/ORBextractor.cc:539-763, DivideNode :481-537) as bulk passes over
 // arrays, one CTA per (image, level).  The std::list is a position-ordered node table; every pass:
 //   1. count the four children of each node that may be split (one sweep over the candidates),
@@ -1336,11 +1545,51 @@ void launch_fast_cells(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned
     c.launches++;
 }
 
+void push_fast_group(std::vector<int4>& groups, FastStripSmem& need, int x0, int y0, int x1, int y1, int level, int cells, int wCell,
+                     unsigned levelOff, int pitch, unsigned candOff, int candCap)
+{
+    groups.push_back(make_int4(x0 | (y0 << 16), x1 | (y1 << 16), level, cells));
+    groups.push_back(make_int4((int)levelOff, pitch, (int)candOff, candCap));
+    const int th = y1 - y0, hi = th - 6, xa = x0 & ~3;
+    const int nw = (x1 - xa + 3) >> 2;
+    groups.push_back(make_int4(wCell, (int)(0xffffffffu / (uint32_t)std::max(nw, 1) + 1u), 0, 0));
+    const int firstIn = x0 + 3, endIn = x1 - 3;
+    if (hi <= 0 || endIn <= firstIn) return;
+    const int npr = ((endIn - 1 - xa) >> 1) - ((firstIn - xa) >> 1) + 1;
+    int clist = 0;
+    for (int k = 0; k < cells; k++) {
+        const int wi = std::min(firstIn + (k + 1) * wCell, endIn) - (firstIn + k * wCell);
+        if (wi > 0) clist += ((wi + 1) / 2) * ((hi + 1) / 2);
+    }
+    need.tileRows = std::max(need.tileRows, th);
+    need.scrRows = std::max(need.scrRows, hi + 2);
+    // a warp owns the row blocks w, w + FS_WARPS, ...: at most ceil(blocks / FS_WARPS) * FS_ROWS rows of npr pairs
+    const int blocks = (hi + FS_ROWS - 1) / FS_ROWS;
+    need.segCap = std::max(need.segCap, ((((blocks + FS_WARPS - 1) / FS_WARPS) * FS_ROWS * npr + 1) & ~1) + 2);
+    need.clistCap = std::max(need.clistCap, clist);
+}
+
+void launch_fast_strips(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh,
+                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n)
+{
+    if (nGroups <= 0 || n <= 0) return;
+    const size_t smem = need.bytes();
+    if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)fast_strip_kernel<FS_PITCH>, SMEM_FAST_STRIP);
+    dim3 grid(nGroups, n);
+    fast_strip_kernel<FS_PITCH><<<grid, FS_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_groups, d_cand, d_candCount,
+                                                                    need.tileRows, need.scrRows, need.segCap, need.clistCap);
+    c.launches++;
+}
+
 void launch_fast(Ctx& c, int n)
 {
     const Geom& g = c.cur->g;
     const ShapeTables& st = *c.cur;
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
+    if (!c.fastCells && st.nFastGroups > 0) {
+        launch_fast_strips(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_groups, st.nFastGroups, st.fastStrip, c.d_cand, c.d_candCount, n);
+        return;
+    }
     launch_fast_cells(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, 2, st.d_cells, st.nFastCells, st.fastSmem, c.d_cand,
                       c.d_candCount, n);
 }

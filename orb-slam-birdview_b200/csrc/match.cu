@@ -76,18 +76,30 @@ __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(const uint4* __restric
     }
 }
 
+// One warp per query: lane l folds the contiguous split range [l*c, (l+1)*c) in order, then the lanes are folded pairwise with
+// the earlier range on the left -- (best, idx, second) with "first minimum wins" is an associative fold, so the result equals the
+// sequential scan over the splits (and therefore over the map descriptors) with strict '<'.
 __global__ void __launch_bounds__(256) knn2_merge_kernel(const int4* __restrict__ partial, int nq, int nsplit,
                                                          int32_t* __restrict__ bi, int32_t* __restrict__ bd, int32_t* __restrict__ sd)
 {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi >= nq) return;                                   // whole warps leave together
+    const int per = (nsplit + 31) >> 5;
     int best = 256, second = 256, idx = -1;
-    for (int s = 0; s < nsplit; s++) {
+    for (int s = lane * per, e = min(s + per, nsplit); s < e; s++) {
         const int4 p = __ldg(partial + (size_t)s * nq + qi);
         if (p.x < best) { second = min(best, p.z); best = p.x; idx = p.y; }
         else second = min(second, p.x);     // p.z >= p.x
     }
-    bi[qi] = idx; bd[qi] = best; sd[qi] = second;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                      // lane l (earlier splits) <- lane l + o (later splits)
+        const int b2 = __shfl_down_sync(0xffffffffu, best, o), s2 = __shfl_down_sync(0xffffffffu, second, o), i2 = __shfl_down_sync(0xffffffffu, idx, o);
+        if (lane + o < 32) {
+            if (b2 < best) { second = min(best, s2); best = b2; idx = i2; }
+            else second = min(second, b2);
+        }
+    }
+    if (lane == 0) { bi[qi] = idx; bd[qi] = best; sd[qi] = second; }
 }
 
 void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
@@ -97,7 +109,7 @@ void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm,
     dim3 grid(nsplit, (nq + KN_THREADS * KN_QPT - 1) / (KN_THREADS * KN_QPT));
     knn2_kernel<<<grid, KN_THREADS, 0, c.stream>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_m), nm,
                                                    mPerSplit, d_partial);
-    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, c.stream>>>(d_partial, nq, nsplit, bi, bd, sd);
+    knn2_merge_kernel<<<(nq + 7) / 8, 256, 0, c.stream>>>(d_partial, nq, nsplit, bi, bd, sd);
     c.launches += 2;
 }
 

@@ -29,6 +29,8 @@ constexpr int BL_ROWS = ORBB200_BL_ROWS;   // output rows per blur warp tile, 12
 constexpr int RS_ROWS = 32;             // output rows per resize tile (128 columns wide)
 constexpr int FT_PITCH = 49;            // u32 words per row of fast_cells_kernel's shared tiles (>= 2*ceil(68/4)+3 = 37), general case
 constexpr int FT_PITCH_SMALL = 25;      // the same for shapes whose cell images are at most 44 pixels wide (2*11+3): half the shared memory
+constexpr int FS_PITCH = 71;            // u32 words per row of fast_strip_kernel's shared tiles: 1 pad + 68 pair words (136 pixels) + 2 pads
+constexpr int FS_MAX_CELLS = 8;         // cells per group (cells are >= 30 px wide: at most 4 fit the tile)
 
 // Geometry of one pyramid level for one image shape (host-computed, passed to kernels by value).
 struct LevelGeom {
@@ -93,6 +95,17 @@ struct FastSmem {
     int pitch() const { return maxRowWords <= FT_PITCH_SMALL ? FT_PITCH_SMALL : FT_PITCH; }
     size_t bytes() const { return sizeof(uint32_t) * ((size_t)(tileWords + scrWords) * pitch() + clistCap) + sizeof(uint16_t) * 2 * (size_t)workCap; }
 };
+// Shared-memory carve of fast_strip_kernel for a set of cell groups (host-computed maxima).
+struct FastStripSmem {
+    int tileRows = 0, scrRows = 0, segCap = 0, clistCap = 0;
+    size_t bytes() const { return sizeof(uint32_t) * ((size_t)(tileRows + scrRows + 5) * FS_PITCH + 8 + clistCap) + sizeof(uint16_t) * 4 * (size_t)segCap; }
+};
+// Append one group of `cells` horizontally adjacent FAST cells (3 x int4) and grow `need`: [x0,x1) x [y0,y1) is the image of the
+// whole group in level coordinates (the first cell's iniX .. the last cell's maxX), cells are wCell wide.
+void push_fast_group(std::vector<int4>& groups, FastStripSmem& need, int x0, int y0, int x1, int y1, int level, int cells, int wCell,
+                     unsigned levelOff, int pitch, unsigned candOff, int candCap);
+void launch_fast_strips(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh,
+                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n);
 // Append one FAST cell (3 x int4) to a host cell table and grow `need`.  [x0,x1) x [y0,y1) is the cell image in level
 // coordinates (3-pixel FAST margin included); candidates are only emitted inside [ex0,ex1) x [ey0,ey1) (ex1 == 0: anywhere).
 void push_fast_cell(std::vector<int4>& cells, FastSmem& need, int x0, int y0, int x1, int y1, int level, unsigned levelOff, int pitch,

@@ -1,6 +1,9 @@
 """Turn ncu outputs into the markdown tables kept under profiles/.
   python tools/ncu_summary.py launches <launch_list.csv>          -> per-kernel share table
-  python tools/ncu_summary.py raw <report.ncu-rep> [metric ...]   -> one column per captured launch"""
+  python tools/ncu_summary.py raw <report.ncu-rep> [metric ...]   -> one column per captured launch
+  python tools/ncu_summary.py source <report.ncu-rep> <kernel name part> [min share %]
+                                                                  -> executed warp-instructions per opcode and per source line
+                                                                     (first captured launch of that kernel; needs -lineinfo + --import-source on)"""
 import csv
 import io
 import subprocess
@@ -53,5 +56,58 @@ def raw(path, metrics):
             print(f"| {short} | {units[i]} | " + " | ".join(r[i][:10] for r in data) + " |")
 
 
+def source(path, kernel, min_share=0.5):
+    from collections import Counter
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    # blocks start with a "Function Name" row; the header row follows
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Function Name"]
+    blk = next((i for i in starts if kernel in rows[i][1]), None)
+    if blk is None:
+        sys.exit(f"no kernel matching {kernel!r} in {path}")
+    end = next((i for i in starts if i > blk), len(rows))
+    while end > blk and rows[end - 1] and rows[end - 1][0] == "File Path":
+        end -= 1
+    hdr = rows[blk + 1]
+    ie, sm = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    te = hdr.index("Thread Instructions Executed")
+    ws, wi = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
+    ops, osmp, lines = Counter(), Counter(), []
+    tot = tsm = tthr = 0
+    for r in rows[blk + 2:end]:
+        if len(r) <= ie:
+            continue
+        try:
+            v = int(r[ie])
+        except ValueError:
+            continue
+        if r[0] != "":                              # a CUDA source line: aggregate of the SASS rows below it
+            lines.append((int(r[0]), v, int(r[sm] or 0), int(r[ws] or 0), int(r[wi] or 0), r[1].strip()[:96]))
+            continue
+        w = r[3].split()
+        if not w:
+            continue
+        op = (w[1] if w[0].startswith("@") else w[0]).split(".")[0]
+        ops[op] += v
+        osmp[op] += int(r[sm] or 0)
+        tot += v
+        tsm += int(r[sm] or 0)
+        tthr += int(r[te] or 0)
+    print(f"kernel `{rows[blk][1].split('(')[0]}`: {tot} warp-instructions executed, {tthr / (32.0 * tot):.3f} of the lanes active on average\n")
+    print("| opcode | share of executed warp-instructions | share of stall samples |\n|---|---|---|")
+    for op, v in ops.most_common():
+        if 100.0 * v / tot >= min_share:
+            print(f"| {op} | {100.0 * v / tot:.1f} % | {100.0 * osmp[op] / max(tsm, 1):.1f} % |")
+    print("\n| line | share of executed warp-instructions | stall samples | shared wavefronts (ideal) | source |\n|---|---|---|---|---|")
+    lt = sum(x[1] for x in lines) or 1
+    ls = sum(x[2] for x in lines) or 1
+    for ln, v, smp, w, wid, text in sorted(lines):
+        if 100.0 * v / lt >= min_share or w > 0.02 * sum(x[3] for x in lines):
+            print(f"| {ln} | {100.0 * v / lt:.1f} % | {100.0 * smp / ls:.1f} % | {w / 1e6:.1f} M ({wid / 1e6:.1f} M) | `{text}` |")
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "source":
+        source(sys.argv[2], sys.argv[3], float(sys.argv[4]) if len(sys.argv) > 4 else 0.5)
+        sys.exit(0)
     {"launches": lambda: launches(sys.argv[2]), "raw": lambda: raw(sys.argv[2], sys.argv[3:])}[sys.argv[1]]()
