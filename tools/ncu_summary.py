@@ -56,35 +56,29 @@ def raw(path, metrics):
             print(f"| {short} | {units[i]} | " + " | ".join(r[i][:10] for r in data) + " |")
 
 
-def source(path, kernel, min_share=0.5):
+def source(path, kernel, min_share=0.5, launch=0):
+    """Opcode table from the SASS view (every instruction once); line table from the CUDA view (an instruction inlined from a
+    helper is attributed to the helper's line AND to the call site's line there, so line shares are normalised by the SASS total
+    and can add up to more than 100 %)."""
     from collections import Counter
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    # blocks start with a "Function Name" row; the header row follows
-    starts = [i for i, r in enumerate(rows) if r and r[0] == "Function Name"]
-    blk = next((i for i in starts if kernel in rows[i][1]), None)
-    if blk is None:
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    mine = [i for i in starts if kernel in rows[i][1]]
+    if not mine:
         sys.exit(f"no kernel matching {kernel!r} in {path}")
+    blk = mine[min(launch, len(mine) - 1)]
     end = next((i for i in starts if i > blk), len(rows))
-    while end > blk and rows[end - 1] and rows[end - 1][0] == "File Path":
-        end -= 1
     hdr = rows[blk + 1]
-    ie, sm = hdr.index("Instructions Executed"), hdr.index("# Samples")
-    te = hdr.index("Thread Instructions Executed")
-    ws, wi = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
-    ops, osmp, lines = Counter(), Counter(), []
+    ie, sm, te, src = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed"), hdr.index("Source")
+    ops, osmp = Counter(), Counter()
     tot = tsm = tthr = 0
     for r in rows[blk + 2:end]:
-        if len(r) <= ie:
-            continue
         try:
             v = int(r[ie])
-        except ValueError:
+        except (ValueError, IndexError):
             continue
-        if r[0] != "":                              # a CUDA source line: aggregate of the SASS rows below it
-            lines.append((int(r[0]), v, int(r[sm] or 0), int(r[ws] or 0), int(r[wi] or 0), r[1].strip()[:96]))
-            continue
-        w = r[3].split()
+        w = r[src].split()
         if not w:
             continue
         op = (w[1] if w[0].startswith("@") else w[0]).split(".")[0]
@@ -98,12 +92,32 @@ def source(path, kernel, min_share=0.5):
     for op, v in ops.most_common():
         if 100.0 * v / tot >= min_share:
             print(f"| {op} | {100.0 * v / tot:.1f} % | {100.0 * osmp[op] / max(tsm, 1):.1f} % |")
-    print("\n| line | share of executed warp-instructions | stall samples | shared wavefronts (ideal) | source |\n|---|---|---|---|---|")
-    lt = sum(x[1] for x in lines) or 1
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Function Name"]
+    mine = [i for i in starts if kernel in rows[i][1] and rows[i - 1][1].endswith(".cu")]
+    if not mine:
+        return
+    blk = mine[0]
+    end = next((i for i in starts if i > blk), len(rows) + 1) - 1
+    hdr = rows[blk + 1]
+    ie, sm = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    ws, wi = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
+    lines = []
+    for r in rows[blk + 2:end]:
+        if len(r) <= ie or r[0] == "":
+            continue
+        try:
+            lines.append((int(r[0]), int(r[ie]), int(r[sm] or 0), int(r[ws] or 0), int(r[wi] or 0), r[1].strip()[:96]))
+        except ValueError:
+            continue
+    nl = max(len(mine), 1)      # the CUDA view lists the function once per captured launch? no: once per file; counts are of one launch
+    print("\n| line | warp-instructions (share of the kernel's total) | stall samples | shared wavefronts (ideal) | source |\n|---|---|---|---|---|")
     ls = sum(x[2] for x in lines) or 1
+    tw = sum(x[3] for x in lines) or 1
     for ln, v, smp, w, wid, text in sorted(lines):
-        if 100.0 * v / lt >= min_share or w > 0.02 * sum(x[3] for x in lines):
-            print(f"| {ln} | {100.0 * v / lt:.1f} % | {100.0 * smp / ls:.1f} % | {w / 1e6:.1f} M ({wid / 1e6:.1f} M) | `{text}` |")
+        if 100.0 * v / tot >= min_share or w > 0.03 * tw:
+            print(f"| {ln} | {100.0 * v / tot:.1f} % | {100.0 * smp / ls:.1f} % | {w / 1e6:.1f} M ({wid / 1e6:.1f} M) | `{text}` |")
 
 
 if __name__ == "__main__":
