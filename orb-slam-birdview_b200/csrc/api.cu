@@ -467,6 +467,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
     c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
+    c.stageUploads = std::getenv("ORBB200_NO_STAGED_UPLOAD") == nullptr;
     if (const char* e = std::getenv("ORBB200_SUBPIX_CTAS")) c.subpixCtasPerSm = std::max(1, std::min(4, atoi(e)));
     // ORBextractor::ORBextractor (reference src/ORBextractor.cc:410-446)
     c.nfeatures = nfeatures; c.scaleFactor = scaleFactor; c.nlevels = nlevels; c.iniTh = iniThFAST; c.minTh = minThFAST;
@@ -603,12 +604,46 @@ int orbb200_extract_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_b
     return run_extract(c, n);
 }
 
+// Results of small batches (the one-frame-per-call pattern of Frame::ExtractORB) come back through a pinned staging block: the
+// status word, the counts and the keypoint / descriptor rows are four asynchronous copies behind ONE synchronisation, and only the
+// n_out[i] valid records of each image are then copied into the caller's (pageable) buffers.  Copies straight into pageable memory
+// are four serialised round trips of the copy engine's bounce buffer.
+constexpr size_t STAGE_LIMIT = 8u << 20;
+constexpr size_t STAGE_H2D_OFF = 0, STAGE_D2H_OFF = 4u << 20;   // the upload of a call and its download do not share bytes
+
 int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out)
 {
     CTX_ENTER(ctx);
     if (!c.cur || n <= 0 || n > c.curN || !kps || !desc || !n_out || cap_per_img <= 0) { c.err = "download: bad argument"; return ORBB200_ERR_ARG; }
     const int kpi = c.cur->g.kpPerImg;
     const int take = std::min(cap_per_img, kpi);
+    const size_t rowK = (size_t)take * sizeof(orbb200_kp_t), rowD = (size_t)take * 32, cntB = align_up(sizeof(int32_t) * (size_t)n, 64);
+    const size_t stageBytes = 64 + cntB + (size_t)n * (rowK + rowD);
+    if (stageBytes <= STAGE_LIMIT - STAGE_D2H_OFF && ensure_scratch(c, 0, STAGE_LIMIT)) {
+        uint8_t* hs = c.h_scratch + STAGE_D2H_OFF;
+        int32_t* hStatus = reinterpret_cast<int32_t*>(hs);
+        int32_t* hCnt = reinterpret_cast<int32_t*>(hs + 64);
+        uint8_t* hK = hs + 64 + cntB;
+        uint8_t* hD = hK + (size_t)n * rowK;
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hStatus, c.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hCnt, c.d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(hK, rowK, c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t), rowK, n, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(hD, rowD, c.d_desc, (size_t)kpi * 32, rowD, n, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        if (*hStatus != 0) {
+            cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
+            c.err = "device-side overflow in octree distribution (status " + std::to_string(*hStatus) + ")";
+            return ORBB200_ERR_UNSUPPORTED;
+        }
+        for (int i = 0; i < n; i++) {
+            n_out[i] = hCnt[i];
+            if (n_out[i] > cap_per_img) { c.err = "extract: caller capacity too small"; return ORBB200_ERR_CAPACITY; }
+            const size_t m = (size_t)std::max(std::min(n_out[i], take), 0);
+            memcpy(kps + (size_t)i * cap_per_img, hK + (size_t)i * rowK, m * sizeof(orbb200_kp_t));
+            memcpy(desc + (size_t)i * cap_per_img * 32, hD + (size_t)i * rowD, m * 32);
+        }
+        return ORBB200_OK;
+    }
     ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(kps, (size_t)cap_per_img * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t),
                                          (size_t)take * sizeof(orbb200_kp_t), n, cudaMemcpyDeviceToHost, c.stream));
     ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(desc, (size_t)cap_per_img * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, n,
@@ -630,10 +665,24 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
     if (!st) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
     c.cur = st; c.curN = n;
     const Geom& g = st->g;
-    // rows go straight into level 0 of the pyramid pool (row pitch conversion by the copy engine)
-    for (int i = 0; i < n; i++) {
+    // rows go straight into level 0 of the pyramid pool (row pitch conversion by the copy engine); small batches pass through the
+    // pinned staging block (a host memcpy + a true DMA beats the copy engine's chunked bounce of pageable memory)
+    for (int i = 0; i < n; i++)
         if (!imgs[i]) { c.err = "extract: null image"; return ORBB200_ERR_ARG; }
-        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, imgs[i], stride, (size_t)w, (size_t)h,
+    const size_t imgB = (size_t)w * h;
+    // measured per call: 752x480 0.241 -> 0.223 ms, 1241x376 0.370 -> 0.252 ms staged; 1920x1080 0.458 -> 0.497 ms (the host memcpy of
+    // 2 MB costs more than the bounce saves): staged up to 1.5 MB per call
+    const bool staged = c.stageUploads && imgB * n <= (3u << 19) && ensure_scratch(c, 0, STAGE_LIMIT);
+    for (int i = 0; i < n; i++) {
+        const uint8_t* src = imgs[i];
+        size_t srcStride = stride;
+        if (staged) {
+            uint8_t* hs = c.h_scratch + STAGE_H2D_OFF + (size_t)i * imgB;
+            if (stride == (size_t)w) memcpy(hs, imgs[i], imgB);
+            else for (int y = 0; y < h; y++) memcpy(hs + (size_t)y * w, imgs[i] + (size_t)y * stride, (size_t)w);
+            src = hs; srcStride = (size_t)w;
+        }
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(c.d_pyr + (size_t)i * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, src, srcStride, (size_t)w, (size_t)h,
                                              cudaMemcpyHostToDevice, c.stream));
     }
     int rc = run_extract(c, n);

@@ -1476,7 +1476,7 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
     if (!S.d_work) ORBB200_CUDA_OK(c, cudaMalloc((void**)&S.d_work, 4 * sizeof(int)));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
-    if (winW == S5_WIN && winH == S5_WIN) {
+    if (winW == S5_WIN && winH == S5_WIN && n >= 8) {    // (fewer images: too few corners to fill the lanes, the warp-per-corner form below is 2.4x faster)
         // the reference's window: streaming form in ceil(maxIters / budget) phases + exact hand-over of the few corners
         // whose patch is not inside the image
         const int phases = (maxIters + S5_BUDGET - 1) / S5_BUDGET;

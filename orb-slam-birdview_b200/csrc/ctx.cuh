@@ -40,7 +40,7 @@ struct WinJob;
 // "what I asked for" lets a second context on the same GPU lower the first one's limit.  Each kernel that may need
 // more than 48 KB is instead raised ONCE per device to the device's opt-in maximum; the record is process-wide.
 // Returns that maximum (bytes) or 0 after a CUDA error.  slot: one small integer per kernel instantiation.
-enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_FAST_STRIP, SMEM_OCTREE, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
+enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_FAST_STRIP, SMEM_OCTREE, SMEM_OCTREE_FEW, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
 inline size_t ensure_max_dynamic_smem(int device, const void* kernel, int slot)
 {
     static std::mutex mu;
@@ -94,6 +94,7 @@ struct Ctx {
     bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)
     std::string err;
     long long launches = 0;
+    bool stageUploads = true;                // small host-API batches upload through the pinned staging block (ORBB200_NO_STAGED_UPLOAD=1: straight from the caller's memory)
     bool fastCells = false;                  // ORBB200_FAST_CELLS=1: grid FAST with one CTA per cell (fast_cells_kernel) instead of the strip form
     int subpixCtasPerSm = 3;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS: 1-2 reach-5 patches, 3 reach-3, 4 reach-2)
 

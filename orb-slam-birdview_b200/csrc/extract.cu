@@ -902,10 +902,12 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
 // (the documented tie rule).  Winner per final node: max response, first in
 // (cell row, cell col, y, x) order on ties (:744-759).
 // ---------------------------------------------------------------------------------------------------
-constexpr int OT_THREADS = 256;
+constexpr int OT_THREADS = 256;          // batches: many (image, level) CTAs in flight
+constexpr int OT_THREADS_FEW = 1024;     // one or two images: the level-0 CTA is the critical path, its sweeps are latency chains
 
 struct OtNode { short x0, y0, x1, y1; };
 
+template <int NT>
 __device__ __forceinline__ int block_scan_excl(int v, int* warpSums, int& total)
 {
     // exclusive scan across the block of one value per thread; all threads must call
@@ -919,17 +921,17 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warpSums, int& total)
     if (lane == 31) warpSums[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        int s = lane < (OT_THREADS / 32) ? warpSums[lane] : 0;
+        int s = lane < (NT / 32) ? warpSums[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += y;
         }
-        if (lane < (OT_THREADS / 32)) warpSums[lane] = s;
+        if (lane < (NT / 32)) warpSums[lane] = s;
     }
     __syncthreads();
     const int wbase = wid ? warpSums[wid - 1] : 0;
-    total = warpSums[OT_THREADS / 32 - 1];
+    total = warpSums[NT / 32 - 1];
     __syncthreads();
     return wbase + x - v;
 }
@@ -946,32 +948,33 @@ size_t octree_smem_bytes(int maxNodes)
 // single L2 request in flight, and the (image, level) CTAs with ~10^4 candidates then set the kernel's duration by
 // their ~20 dependent sweeps (measured: latency-bound, not issue-bound).
 constexpr int OT_UNROLL = 4;
-template <bool NEED_NODE, typename F>
+template <int NT, bool NEED_NODE, typename F>
 __device__ __forceinline__ void ot_sweep(const uint32_t* __restrict__ C, const uint16_t* nodeOf, int n, int tid, F f)
 {
-    for (int base = tid; base < n; base += OT_UNROLL * OT_THREADS) {
+    for (int base = tid; base < n; base += OT_UNROLL * NT) {
         uint32_t v[OT_UNROLL];
         int p[OT_UNROLL];
 #pragma unroll
         for (int k = 0; k < OT_UNROLL; k++) {
-            const int i = base + k * OT_THREADS;
+            const int i = base + k * NT;
             v[k] = i < n ? C[i] : 0u;
             p[k] = (NEED_NODE && i < n) ? (int)nodeOf[i] : 0;
         }
 #pragma unroll
         for (int k = 0; k < OT_UNROLL; k++) {
-            const int i = base + k * OT_THREADS;
+            const int i = base + k * NT;
             if (i < n) f(i, v[k], p[k]);
         }
     }
 }
 
-__global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
+template <int NT>
+__global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                             uint16_t* __restrict__ nodeOfAll, uint32_t* __restrict__ lvlKp,
                                                             int32_t* __restrict__ lvlCount, int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int warpSums[OT_THREADS / 32];
+    __shared__ int warpSums[NT / 32];
     __shared__ int sFlag;
 
     // blockIdx.y = level: the CTAs of level 0 (most candidates, longest) are dispatched first, the short ones fill the tail
@@ -1012,7 +1015,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
     const int nIni = L.nIni;
     const float hX = L.hX;
     const int regH = L.maxBY - FAST_BORDER;
-    for (int i = tid; i < nIni; i += OT_THREADS) {
+    for (int i = tid; i < nIni; i += NT) {
         OtNode nd;
         nd.x0 = (short)(int)__fmul_rn(hX, (float)i);
         nd.x1 = (short)(int)__fmul_rn(hX, (float)(i + 1));
@@ -1022,7 +1025,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         curCnt[i] = 0;
     }
     __syncthreads();
-    ot_sweep<false>(C, nodeOf, n, tid, [&](int i, uint32_t v, int) {
+    ot_sweep<NT, false>(C, nodeOf, n, tid, [&](int i, uint32_t v, int) {
         const int x = v & 0xfff;
         int r = (int)__fdiv_rn((float)x, hX);
         r = min(r, nIni - 1);
@@ -1045,7 +1048,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         }
         __syncthreads();
         total = sFlag;
-        ot_sweep<true>(C, nodeOf, n, tid, [&](int i, uint32_t, int p) { nodeOf[i] = (uint16_t)newPos[p]; });
+        ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int i, uint32_t, int p) { nodeOf[i] = (uint16_t)newPos[p]; });
         __syncthreads();
         listSize = total;
         OtNode* t = cur; cur = nxt; nxt = t;
@@ -1063,34 +1066,34 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         int nProc = 0;
         if (!sortedMode) {
             int carry = 0;
-            for (int base = 0; base < listSize; base += OT_THREADS) {
+            for (int base = 0; base < listSize; base += NT) {
                 const int p = base + tid;
                 const int f = (p < listSize && curCnt[p] > 1) ? 1 : 0;
                 int tot;
-                const int ex = block_scan_excl(f, warpSums, tot);
+                const int ex = block_scan_excl<NT>(f, warpSums, tot);
                 if (f) order[carry + ex] = p;
                 carry += tot;
             }
             nProc = carry;
         } else {
             int carry = 0;
-            for (int base = 0; base < frontNew; base += OT_THREADS) {
+            for (int base = 0; base < frontNew; base += NT) {
                 const int p = base + tid;
                 const int f = (p < frontNew && curCnt[p] > 1) ? 1 : 0;
                 int tot;
-                const int ex = block_scan_excl(f, warpSums, tot);
+                const int ex = block_scan_excl<NT>(f, warpSums, tot);
                 if (f) keys[carry + ex] = ((uint32_t)min(curCnt[p], 0xffff) << 16) | (uint32_t)(0xffff - p);
                 carry += tot;
             }
             nProc = carry;
             int S2 = 1;
             while (S2 < nProc) S2 <<= 1;
-            for (int i = nProc + tid; i < S2; i += OT_THREADS) keys[i] = 0;
+            for (int i = nProc + tid; i < S2; i += NT) keys[i] = 0;
             __syncthreads();
             // bitonic sort, descending
             for (int k = 2; k <= S2; k <<= 1) {
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < S2; i += OT_THREADS) {
+                    for (int i = tid; i < S2; i += NT) {
                         const int ixj = i ^ j;
                         if (ixj > i) {
                             const uint32_t a = keys[i], b = keys[ixj];
@@ -1101,20 +1104,20 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
                     __syncthreads();
                 }
             }
-            for (int i = tid; i < nProc; i += OT_THREADS) order[i] = 0xffff - (int)(keys[i] & 0xffff);
+            for (int i = tid; i < nProc; i += NT) order[i] = 0xffff - (int)(keys[i] & 0xffff);
         }
         __syncthreads();
 
         // ---- 2. child counts of the nodes in `order` ----
-        for (int i = tid; i < listSize; i += OT_THREADS) aux[i] = -1;
+        for (int i = tid; i < listSize; i += NT) aux[i] = -1;
         __syncthreads();
-        for (int i = tid; i < nProc; i += OT_THREADS) {
+        for (int i = tid; i < nProc; i += NT) {
             const int p = order[i];
             aux[p] = i;                       // processing rank
             cc[4 * p + 0] = 0; cc[4 * p + 1] = 0; cc[4 * p + 2] = 0; cc[4 * p + 3] = 0;
         }
         __syncthreads();
-        ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+        ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
             if (aux[p] < 0) return;
             const int x = v & 0xfff, y = (v >> 12) & 0xfff;
             const OtNode nd = cur[p];
@@ -1132,7 +1135,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
             int carryKids = 0;
             if (tid == 0) sFlag = nProc;      // first processing index at which the list reaches N (sorted mode)
             __syncthreads();
-            for (int base = 0; base < nProc; base += OT_THREADS) {
+            for (int base = 0; base < nProc; base += NT) {
                 const int i = base + tid;
                 int kids = 0;
                 if (i < nProc) {
@@ -1140,7 +1143,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
                     kids = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0);
                 }
                 int tot;
-                const int ex = block_scan_excl(kids, warpSums, tot);
+                const int ex = block_scan_excl<NT>(kids, warpSums, tot);
                 if (i < nProc) {
                     // child sequence start for this node = carryKids + ex; stash in childPos[4p] for now
                     childPos[4 * order[i]] = carryKids + ex;
@@ -1172,7 +1175,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         // ---- 4. build the new list ----
         // children: sequence index s (processing order, n1..n4) -> position nChildrenTotal-1-s
         int nToExpand = 0;
-        for (int i = tid; i < nSplit; i += OT_THREADS) {
+        for (int i = tid; i < nSplit; i += NT) {
             const int p = order[i];
             const OtNode nd = cur[p];
             const int hx = (nd.x1 - nd.x0 + 1) >> 1, hy = (nd.y1 - nd.y0 + 1) >> 1;
@@ -1193,11 +1196,11 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         // unsplit nodes keep their relative order after the children
         {
             int carry = 0;
-            for (int base = 0; base < listSize; base += OT_THREADS) {
+            for (int base = 0; base < listSize; base += NT) {
                 const int p = base + tid;
                 const int keep = (p < listSize && !(aux[p] >= 0 && aux[p] < nSplit)) ? 1 : 0;
                 int tot;
-                const int ex = block_scan_excl(keep, warpSums, tot);
+                const int ex = block_scan_excl<NT>(keep, warpSums, tot);
                 if (p < listSize) {
                     if (keep) {
                         const int np = nChildrenTotal + carry + ex;
@@ -1215,13 +1218,13 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         int nToExpandTotal;
         {
             int tot;
-            block_scan_excl(nToExpand, warpSums, tot);
+            block_scan_excl<NT>(nToExpand, warpSums, tot);
             nToExpandTotal = tot;
         }
         __syncthreads();
 
         // ---- 5. relabel candidates ----
-        ot_sweep<true>(C, nodeOf, n, tid, [&](int i, uint32_t v, int p) {
+        ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int i, uint32_t v, int p) {
             const int np = newPos[p];
             if (np >= 0) { nodeOf[i] = (uint16_t)np; return; }
             const int x = v & 0xfff, y = (v >> 12) & 0xfff;
@@ -1250,12 +1253,12 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
     uint32_t* best = reinterpret_cast<uint32_t*>(cc);          // [listSize] max response
     uint32_t* bestKey = reinterpret_cast<uint32_t*>(childPos); // [listSize] min order key among max-response keys
     uint32_t* bestVal = reinterpret_cast<uint32_t*>(newPos);   // [listSize] packed candidate
-    for (int i = tid; i < listSize; i += OT_THREADS) { best[i] = 0; bestKey[i] = 0xffffffffu; }
+    for (int i = tid; i < listSize; i += NT) { best[i] = 0; bestKey[i] = 0xffffffffu; }
     __syncthreads();
-    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) { atomicMax(&best[p], v >> 24); });
+    ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) { atomicMax(&best[p], v >> 24); });
     __syncthreads();
     const int wCell = L.wCell, hCell = L.hCell, nCols = L.nCols;
-    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+    ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
         if ((v >> 24) != best[p]) return;
         const int x = v & 0xfff, y = (v >> 12) & 0xfff;
         const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
@@ -1263,7 +1266,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
         atomicMin(&bestKey[p], key);
     });
     __syncthreads();
-    ot_sweep<true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
+    ot_sweep<NT, true>(C, nodeOf, n, tid, [&](int, uint32_t v, int p) {
         if ((v >> 24) != best[p]) return;
         const int x = v & 0xfff, y = (v >> 12) & 0xfff;
         const int cj = (x - 3) / wCell, ci = (y - 3) / hCell;
@@ -1272,7 +1275,7 @@ __global__ void __launch_bounds__(OT_THREADS) octree_kernel(Geom g, const uint32
     });
     __syncthreads();
     const int nOut = min(listSize, L.kpCap);
-    for (int i = tid; i < nOut; i += OT_THREADS) outKp[i] = bestVal[i];
+    for (int i = tid; i < nOut; i += NT) outKp[i] = bestVal[i];
     if (tid == 0) {
         lvlCount[img * MAX_LEVELS + level] = nOut;
         if (listSize > L.kpCap) atomicExch(status, 2);
@@ -1600,9 +1603,14 @@ void launch_octree(Ctx& c, int n)
     int maxNodes = 2;
     for (int l = 0; l < g.nlevels; l++) maxNodes = std::max(maxNodes, g.lv[l].maxNodes);
     const size_t smem = octree_smem_bytes(maxNodes);
-    if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel, SMEM_OCTREE);
     dim3 grid(n, g.nlevels);
-    octree_kernel<<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+    if (n <= 2) {
+        if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel<OT_THREADS_FEW>, SMEM_OCTREE_FEW);
+        octree_kernel<OT_THREADS_FEW><<<grid, OT_THREADS_FEW, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+    } else {
+        if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel<OT_THREADS>, SMEM_OCTREE);
+        octree_kernel<OT_THREADS><<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+    }
     c.launches++;
 }
 
