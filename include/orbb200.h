@@ -386,7 +386,9 @@ int orbb200_bird_set_mask(orbb200_ctx* ctx, int w, int h, int nfeatures, int max
 int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* d_in,
                               const orbb200_frame_step_outputs* d_out);
 /* Host variant (the end-to-end path): copies images and poses to the device, runs the step, copies every non-NULL output back.
- * Asynchronous: outputs are valid after orbb200_sync().  Pinned host memory lets the copies overlap other contexts' work. */
+ * Asynchronous: outputs are valid after orbb200_sync() (calls of up to 8 frames from pageable memory pass through a pinned staging
+ * block and are delivered by orbb200_sync() itself: synchronising the stream alone is not enough for them).  Pinned host memory
+ * lets the copies overlap other contexts' work. */
 int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p, const orbb200_frame_step_inputs* h_in,
                             const orbb200_frame_step_outputs* h_out);
 int orbb200_bird_results_device(orbb200_ctx* ctx, int w, int h, int nfeatures, const orbb200_kp_t** d_kps, const uint8_t** d_desc,

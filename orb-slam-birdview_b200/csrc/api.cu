@@ -563,10 +563,20 @@ void orbb200_destroy(orbb200_ctx* ctx)
 
 const char* orbb200_last_error(const orbb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
 
+// after the stream has drained: copy staged results of a small host-buffer frame step into the caller's buffers
+static void deliver_host_copies(Ctx& c)
+{
+    for (const Ctx::HostCopy& h : c.hostCopies)
+        for (size_t r = 0; r < h.rows; r++)
+            memcpy(static_cast<uint8_t*>(h.dst) + r * h.dpitch, static_cast<const uint8_t*>(h.src) + r * h.width, h.width);
+    c.hostCopies.clear();
+}
+
 int orbb200_sync(orbb200_ctx* ctx)
 {
     CTX_ENTER(ctx);
     ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    deliver_host_copies(c);
     return ORBB200_OK;
 }
 
@@ -615,6 +625,7 @@ int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t
 {
     CTX_ENTER(ctx);
     if (!c.cur || n <= 0 || n > c.curN || !kps || !desc || !n_out || cap_per_img <= 0) { c.err = "download: bad argument"; return ORBB200_ERR_ARG; }
+    if (!c.hostCopies.empty()) { ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream)); deliver_host_copies(c); }   // staged results of an earlier frame step
     const int kpi = c.cur->g.kpPerImg;
     const int take = std::min(cap_per_img, kpi);
     const size_t rowK = (size_t)take * sizeof(orbb200_kp_t), rowD = (size_t)take * 32, cntB = align_up(sizeof(int32_t) * (size_t)n, 64);
@@ -661,6 +672,7 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
 {
     CTX_ENTER(ctx);
     if (!imgs || n <= 0 || n > c.maxBatch || w <= 0 || h <= 0 || stride < (size_t)w) { c.err = "extract: bad argument"; return ORBB200_ERR_ARG; }
+    if (!c.hostCopies.empty()) { ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream)); deliver_host_copies(c); }
     const ShapeTables* st = get_shape(c, w, h);
     if (!st) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
     c.cur = st; c.curN = n;
@@ -1557,7 +1569,7 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     // matching, FP64- and latency-bound where the front extraction is integer-ALU-bound -> on a side stream beside it
     // (per-stage timing keeps everything on one stream so that a stage's events bracket its kernels alone)
     BirdStepView bv{};
-    const bool fork = hasBird && c.forkBird && !c.timing;
+    const bool fork = hasBird && (c.forkBird || n <= 8) && !c.timing;      // a few frames leave most SMs idle: the two front-ends overlap
     if (hasBird) {
         cudaStream_t main = c.stream;
         if (fork) {
@@ -1714,54 +1726,87 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
     Arena A(c.d_fstep, c.d_fstep_bytes);
     orbb200_frame_step_inputs din{};
     orbb200_frame_step_outputs dout{};
+    // One or a few frames from pageable memory (the per-frame call pattern): inputs and results pass through the pinned staging
+    // block -- a host memcpy + one DMA each way instead of a dozen serialised bounces of the copy engine; the results reach the
+    // caller's buffers in orbb200_sync().  Pinned caller buffers (the throughput path) are used directly.
+    bool staged = false;
+    if (c.stageUploads && !c.hostCopies.empty()) { ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream)); deliver_host_copies(c); }
+    {
+        const int kpi0 = c.gmax.kpPerImg;
+        const size_t inB = imgBytes * ni + birdBytes * n + sizeof(orbb200_camera_pose) * n + 1024;
+        const size_t outB = (size_t)ni * kpi0 * 60 + (size_t)n * kpi0 * 8 + 8 * Qm + (size_t)n * bk * 64 + 64 * (size_t)n + 8192;
+        if (c.stageUploads && n <= 8 && inB <= STAGE_D2H_OFF - STAGE_H2D_OFF && outB <= STAGE_LIMIT - STAGE_D2H_OFF) {
+            cudaPointerAttributes at{};
+            const bool pageable = cudaPointerGetAttributes(&at, in->imgs) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+            cudaGetLastError();
+            staged = pageable && ensure_scratch(c, 0, STAGE_LIMIT);
+        }
+    }
+    size_t hIn = STAGE_H2D_OFF, hOut = STAGE_D2H_OFF;
+    auto h2d = [&](void* dDst, const void* hSrc, size_t bytes) -> cudaError_t {
+        if (staged) {
+            uint8_t* hs = c.h_scratch + hIn;
+            hIn += align_up(bytes, 64);
+            memcpy(hs, hSrc, bytes);
+            hSrc = hs;
+        }
+        return cudaMemcpyAsync(dDst, hSrc, bytes, cudaMemcpyHostToDevice, c.stream);
+    };
+    auto d2h = [&](void* hDst, size_t dpitch, const void* dSrc, size_t spitch, size_t width, size_t rows) -> cudaError_t {
+        if (staged) {
+            uint8_t* hs = c.h_scratch + hOut;
+            hOut += align_up(width * rows, 64);
+            c.hostCopies.push_back(Ctx::HostCopy{hDst, dpitch, hs, width, rows});
+            return cudaMemcpy2DAsync(hs, width, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
+        }
+        return cudaMemcpy2DAsync(hDst, dpitch, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
+    };
     uint8_t* dImgs = A.take<uint8_t>(imgBytes * ni);
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dImgs, in->imgs, imgBytes * ni, cudaMemcpyHostToDevice, c.stream));
+    ORBB200_CUDA_OK(c, h2d(dImgs, in->imgs, imgBytes * ni));
     din.imgs = dImgs;
     if (hasBird) {
         uint8_t* dBird = A.take<uint8_t>(birdBytes * n);
-        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dBird, in->bird_imgs, birdBytes * n, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, h2d(dBird, in->bird_imgs, birdBytes * n));
         din.bird_imgs = dBird;
     }
     if (hasMap) {
         orbb200_camera_pose* dP = A.take<orbb200_camera_pose>(n);
-        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dP, in->poses, sizeof(orbb200_camera_pose) * n, cudaMemcpyHostToDevice, c.stream));
+        ORBB200_CUDA_OK(c, h2d(dP, in->poses, sizeof(orbb200_camera_pose) * n));
         din.poses = dP;
         dout.map_best_idx = A.take<int32_t>(Qm); dout.map_best_dist = A.take<int32_t>(Qm); dout.map_nmatches = A.take<int32_t>(n);
     }
     if (hasBird) { dout.bird_matches12 = A.take<int32_t>(Qb); dout.bird_nmatches = A.take<int32_t>(n); }
     rc = orbb200_frame_step_device(ctx, p, &din, &dout);
-    if (rc != ORBB200_OK) return rc;
+    if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
     const int kpi = c.cur->g.kpPerImg;
     if (out->kps || out->desc || out->u_right || out->depth) {
-        if (out->cap <= 0) { c.err = "frame_step_host: cap"; return ORBB200_ERR_ARG; }
+        if (out->cap <= 0) { c.err = "frame_step_host: cap"; c.hostCopies.clear(); return ORBB200_ERR_ARG; }
         const int take = std::min(out->cap, kpi);
-        if (out->kps) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->kps, (size_t)out->cap * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t),
-                                                           (size_t)take * sizeof(orbb200_kp_t), ni, cudaMemcpyDeviceToHost, c.stream));
-        if (out->desc) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->desc, (size_t)out->cap * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, ni, cudaMemcpyDeviceToHost, c.stream));
+        if (out->kps) ORBB200_CUDA_OK(c, d2h(out->kps, (size_t)out->cap * sizeof(orbb200_kp_t), c.d_kps, (size_t)kpi * sizeof(orbb200_kp_t), (size_t)take * sizeof(orbb200_kp_t), ni));
+        if (out->desc) ORBB200_CUDA_OK(c, d2h(out->desc, (size_t)out->cap * 32, c.d_desc, (size_t)kpi * 32, (size_t)take * 32, ni));
         // mvuRight / mvDepth live in the left images' rows of the pools (image 2i)
-        if (out->u_right && p->mb > 0.f) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->u_right, (size_t)out->cap * 4, c.d_uRight, (size_t)kpi * 8, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
-        if (out->depth && p->mb > 0.f) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->depth, (size_t)out->cap * 4, c.d_depth, (size_t)kpi * 8, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
+        if (out->u_right && p->mb > 0.f) ORBB200_CUDA_OK(c, d2h(out->u_right, (size_t)out->cap * 4, c.d_uRight, (size_t)kpi * 8, (size_t)take * 4, n));
+        if (out->depth && p->mb > 0.f) ORBB200_CUDA_OK(c, d2h(out->depth, (size_t)out->cap * 4, c.d_depth, (size_t)kpi * 8, (size_t)take * 4, n));
     }
-    if (out->counts) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->counts, c.d_counts, 4 * (size_t)ni, cudaMemcpyDeviceToHost, c.stream));
+    if (out->counts) ORBB200_CUDA_OK(c, d2h(out->counts, 4 * (size_t)ni, c.d_counts, 4 * (size_t)ni, 4 * (size_t)ni, 1));
     if (hasMap) {
-        if (out->map_best_idx) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_best_idx, dout.map_best_idx, 4 * Qm, cudaMemcpyDeviceToHost, c.stream));
-        if (out->map_best_dist) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_best_dist, dout.map_best_dist, 4 * Qm, cudaMemcpyDeviceToHost, c.stream));
-        if (out->map_nmatches) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->map_nmatches, dout.map_nmatches, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        if (out->map_best_idx) ORBB200_CUDA_OK(c, d2h(out->map_best_idx, 4 * Qm, dout.map_best_idx, 4 * Qm, 4 * Qm, 1));
+        if (out->map_best_dist) ORBB200_CUDA_OK(c, d2h(out->map_best_dist, 4 * Qm, dout.map_best_dist, 4 * Qm, 4 * Qm, 1));
+        if (out->map_nmatches) ORBB200_CUDA_OK(c, d2h(out->map_nmatches, 4 * (size_t)n, dout.map_nmatches, 4 * (size_t)n, 4 * (size_t)n, 1));
     }
     if (hasBird) {
         const orbb200_kp_t* bKps = nullptr; const uint8_t* bDesc = nullptr; const int32_t* bCnt = nullptr; int bcap = 0;
         rc = orbb200_bird_results_device(ctx, p->bird_w, p->bird_h, p->bird_nfeatures, &bKps, &bDesc, &bCnt, &bcap);
-        if (rc != ORBB200_OK) return rc;
+        if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
         if (out->bird_kps || out->bird_desc || out->bird_matches12) {
-            if (out->bird_cap <= 0) { c.err = "frame_step_host: bird_cap"; return ORBB200_ERR_ARG; }
+            if (out->bird_cap <= 0) { c.err = "frame_step_host: bird_cap"; c.hostCopies.clear(); return ORBB200_ERR_ARG; }
             const int take = std::min(out->bird_cap, bk);
-            if (out->bird_kps) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_kps, (size_t)out->bird_cap * sizeof(orbb200_kp_t), bKps, (size_t)bk * sizeof(orbb200_kp_t),
-                                                                    (size_t)take * sizeof(orbb200_kp_t), n, cudaMemcpyDeviceToHost, c.stream));
-            if (out->bird_desc) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_desc, (size_t)out->bird_cap * 32, bDesc, (size_t)bk * 32, (size_t)take * 32, n, cudaMemcpyDeviceToHost, c.stream));
-            if (out->bird_matches12) ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(out->bird_matches12, (size_t)out->bird_cap * 4, dout.bird_matches12, (size_t)bk * 4, (size_t)take * 4, n, cudaMemcpyDeviceToHost, c.stream));
+            if (out->bird_kps) ORBB200_CUDA_OK(c, d2h(out->bird_kps, (size_t)out->bird_cap * sizeof(orbb200_kp_t), bKps, (size_t)bk * sizeof(orbb200_kp_t), (size_t)take * sizeof(orbb200_kp_t), n));
+            if (out->bird_desc) ORBB200_CUDA_OK(c, d2h(out->bird_desc, (size_t)out->bird_cap * 32, bDesc, (size_t)bk * 32, (size_t)take * 32, n));
+            if (out->bird_matches12) ORBB200_CUDA_OK(c, d2h(out->bird_matches12, (size_t)out->bird_cap * 4, dout.bird_matches12, (size_t)bk * 4, (size_t)take * 4, n));
         }
-        if (out->bird_counts) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->bird_counts, bCnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
-        if (out->bird_nmatches) ORBB200_CUDA_OK(c, cudaMemcpyAsync(out->bird_nmatches, dout.bird_nmatches, 4 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        if (out->bird_counts) ORBB200_CUDA_OK(c, d2h(out->bird_counts, 4 * (size_t)n, bCnt, 4 * (size_t)n, 4 * (size_t)n, 1));
+        if (out->bird_nmatches) ORBB200_CUDA_OK(c, d2h(out->bird_nmatches, 4 * (size_t)n, dout.bird_nmatches, 4 * (size_t)n, 4 * (size_t)n, 1));
     }
     return ORBB200_OK;
 }
@@ -1772,6 +1817,7 @@ int orbb200_device_status(orbb200_ctx* ctx, int* status)
     int32_t st = 0;
     ORBB200_CUDA_OK(c, cudaMemcpyAsync(&st, c.d_status, sizeof(st), cudaMemcpyDeviceToHost, c.stream));
     ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    deliver_host_copies(c);
     if (st != 0) cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
     if (status) *status = st;
     if (st != 0) { c.err = "device-side capacity overflow (status " + std::to_string(st) + "): results of the last calls are incomplete"; return ORBB200_ERR_CAPACITY; }

@@ -155,6 +155,9 @@ struct Ctx {
     bool timing = false;
     struct Pending { int stage; cudaEvent_t e0, e1; };
     std::vector<Pending> pending;
+    // results of a small host-buffer frame step staged in pinned memory: delivered to the caller's (pageable) buffers by orbb200_sync()
+    struct HostCopy { void* dst; size_t dpitch; const void* src; size_t width, rows; };
+    std::vector<HostCopy> hostCopies;
     std::vector<cudaEvent_t> freeEvents;
     float stageMs[ORBB200_NUM_STAGES] = {};
     int stageGroups[ORBB200_NUM_STAGES] = {};
