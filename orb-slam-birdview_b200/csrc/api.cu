@@ -139,6 +139,9 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
     auto it = c.shapes.find({w, h});
     if (it != c.shapes.end()) return &it->second;
     ShapeTables st;
+    // max_w / max_h of orbb200_create size per-row tables too (the stereo row index has max_h + 2 entries per frame): a taller or
+    // wider image is refused even when its pools would fit
+    if (w > c.maxW || h > c.maxH) { c.err = "image shape exceeds the context's max_w/max_h"; return nullptr; }
     if (!build_geom(c, w, h, st.g, c.err)) return nullptr;
     const Geom& g = st.g;
     if (g.pyrBytes > c.gmax.pyrBytes || g.candPerImg > c.gmax.candPerImg + c.gmax.candPerImg / 8 || g.kpPerImg > c.gmax.kpPerImg) {

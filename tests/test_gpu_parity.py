@@ -118,6 +118,8 @@ def test_extract_edge_cases(pkg):
     _compare_extract(k2, d2, k0, d0, "tiny levels")
     with pytest.raises(pkg.OrbB200Error):
         ex(synth.synth_frame(500, 700, 1))                   # larger than the context's max size
+    with pytest.raises(pkg.OrbB200Error):
+        ex(synth.synth_frame(340, 200, 2))                   # fewer pixels, but taller than max_h: per-row tables are sized by max_h
 
 
 def test_getters_match_oracle(pkg):
