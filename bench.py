@@ -835,8 +835,30 @@ def leg_per_frame(arm, frames=12):
     for i in range(n):
         ex(seq["imgs"][2 * i])
     ex_ms = (time.perf_counter() - t0) / n * 1e3
-    return {"what": "one frame per host call, results on the host before the next call (the reference's call pattern)",
-            "north_star_frame_ms": full_ms, "north_star_frames_per_s": 1e3 / full_ms, "one_1241x376_extraction_ms": ex_ms}
+    out = {"what": "one frame per host call, results on the host before the next call (the reference's call pattern)",
+           "north_star_frame_ms": full_ms, "north_star_frames_per_s": 1e3 / full_ms, "one_1241x376_extraction_ms": ex_ms}
+    # the same through the C++ drop-in class (cpp/ORBextractor.h::operator(), as Frame::ExtractORB calls it)
+    try:
+        import tempfile
+        drv = os.path.join(ROOT, "orb-slam-birdview_b200", "cpp", "shim_driver")
+        if not os.path.exists(drv):
+            subprocess.run(["make", "-s", "-C", os.path.dirname(drv), "shim_driver"], check=True, timeout=300)
+        shim = {}
+        with tempfile.TemporaryDirectory() as d:
+            for (h, w, nf) in ((480, 752, 1000), (H, W, NFEAT)):
+                img = seq["imgs"][0] if (h, w) == (H, W) else _synth().synth_frame(h, w, 1000)
+                raw = os.path.join(d, "in.raw")
+                np.ascontiguousarray(img).tofile(raw)
+                r = subprocess.run([drv, raw, str(w), str(h), str(nf), str(INI_TH), str(MIN_TH), os.path.join(d, "out.bin")], capture_output=True, text=True,
+                                   timeout=300, env=dict(os.environ, ORBB200_SHIM_TIME="200"))
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("TIMING ")]
+                if line:
+                    shim[f"{w}x{h}"] = json.loads(line[0][7:])
+        if shim:
+            out["cpp_shim"] = shim
+    except Exception as e:      # the C++ number is a side leg: never fail the bench line for it
+        out["cpp_shim"] = {"error": repr(e)}
+    return out
 
 
 def c5_sharded_digest(torch, pkg, dist, rank, world, device, n_frames=256, w=1920, h=1080, nfeat=4000):

@@ -80,6 +80,13 @@ int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t
  * src/Frame.cc:669-776).  blurred!=0 returns the GaussianBlur'ed copy used for the descriptors. */
 int orbb200_pyramid_level(orbb200_ctx* ctx, int img_index, int level, int blurred,
                           uint8_t* dst, size_t dst_stride, int* w, int* h);
+/* The same for all levels at once: ONE device-to-host copy of the image's pyramid block into a pinned mirror owned by the
+ * context, and per level the address of pixel (0,0) inside it with its row pitch (rows keep the device layout: the
+ * reflect-101 border the reference's copyMakeBorder produces lies around every level, exactly as around the ROIs the reference
+ * keeps in mvImagePyramid).  The pointers stay valid until the next call of this function on the context.  This is what the
+ * ORBextractor shim fills mvImagePyramid with (cv::Mat headers over the mirror, no per-level copies). */
+int orbb200_pyramid_mirror(orbb200_ctx* ctx, int img_index, int blurred, const uint8_t** level_ptr /*[nlevels]*/,
+                           size_t* level_pitch /*[nlevels]*/, int* level_w /*[nlevels]*/, int* level_h /*[nlevels]*/);
 /* Debug/inspection: FAST candidates of one level as packed (x,y,response) int32 triples in region
  * coordinates, unordered.  Returns the count (or a negative status). */
 int orbb200_level_candidates(orbb200_ctx* ctx, int img_index, int level, int32_t* xyr, int cap);

@@ -8,7 +8,9 @@
 //    reference's assert()/exit(-1) style error handling (src/ORBextractor.cc:1050, src/System.cc:59-84);
 //  * the device context is created on the first call (it needs the image size); a larger image re-creates it;
 //  * mvImagePyramid is refreshed after every call because Frame::ComputeStereoMatches reads it
-//    (src/Frame.cc:669-776).  SetDownloadPyramid(false) skips that copy for monocular use.
+//    (src/Frame.cc:669-776): one device-to-host copy of the pyramid block into a pinned mirror, the levels are cv::Mat headers
+//    over it and stay valid until the next call (Frame::ComputeStereoMatches runs before it).  SetDownloadPyramid(false) skips
+//    the copy (monocular use, or ComputeStereoMatches replaced by orbb200_compute_stereo_matches).
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
@@ -76,12 +78,13 @@ public:
         }
         _keypoints.assign(kpbuf.begin(), kpbuf.begin() + n);
         if (bDownloadPyramid) {
+            // one copy of the whole pyramid block into the context's pinned mirror; mvImagePyramid[l] are headers over it (like the
+            // reference's ROIs into its bordered temporaries, src/ORBextractor.cc:1116-1128), valid until the next call
+            const uint8_t* lp[16]; size_t pitch[16]; int lw[16], lh[16];
+            check(orbb200_pyramid_mirror(ctx, 0, 0, lp, pitch, lw, lh));
             for (int l = 0; l < nlevels; l++) {
-                int w = 0, h = 0;
-                check(orbb200_pyramid_level(ctx, 0, l, 0, nullptr, 0, &w, &h));
-                if (w <= 0 || h <= 0) { mvImagePyramid[l].release(); continue; }
-                mvImagePyramid[l].create(h, w, CV_8UC1);
-                check(orbb200_pyramid_level(ctx, 0, l, 0, mvImagePyramid[l].ptr(0), mvImagePyramid[l].step, nullptr, nullptr));
+                if (!lp[l]) { mvImagePyramid[l].release(); continue; }
+                mvImagePyramid[l] = cv::Mat(lh[l], lw[l], CV_8UC1, const_cast<unsigned char*>(lp[l]), pitch[l]);
             }
         }
     }

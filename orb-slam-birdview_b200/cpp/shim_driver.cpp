@@ -4,6 +4,7 @@
 // With two more arguments it then runs the birdview block of Frame::Frame (src/Frame.cc:328-342) through
 // BirdviewExtractor.h on a second image + mask and appends those keypoints + descriptors:
 //   shim_driver ... <out.bin> <bird.raw> <bird_mask.raw> <bw> <bh>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -67,5 +68,20 @@ int main(int argc, char** argv)
     }
     fclose(o);
     printf("%d keypoints, levels %d, scale[1] %.6f\n", n, extractor.GetLevels(), extractor.GetScaleFactors()[1]);
+    // ORBB200_SHIM_TIME=N: wall time of N calls of operator() as Frame::ExtractORB makes them (pageable cv::Mat in, vectors out),
+    // with and without the mvImagePyramid refresh -- the drop-in latency bench.py reports as configs.per_frame.cpp_shim
+    if (const char* e = getenv("ORBB200_SHIM_TIME")) {
+        const int reps = atoi(e) > 0 ? atoi(e) : 100;
+        double ms[2];
+        for (int mode = 0; mode < 2; mode++) {
+            extractor.SetDownloadPyramid(mode == 0);
+            extractor(im, cv::Mat(), keys, desc);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < reps; i++) extractor(im, cv::Mat(), keys, desc);
+            ms[mode] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+        }
+        printf("TIMING {\"w\": %d, \"h\": %d, \"keypoints\": %d, \"operator_call_ms\": %.4f, \"operator_call_without_pyramid_refresh_ms\": %.4f}\n",
+               w, h, (int)keys.size(), ms[0], ms[1]);
+    }
     return 0;
 }

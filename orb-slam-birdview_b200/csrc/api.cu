@@ -125,6 +125,7 @@ bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes)
     if (host_bytes > c.h_scratch_bytes) {
         cudaStreamSynchronize(c.stream);
         if (c.h_scratch) cudaFreeHost(c.h_scratch);
+    if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
         c.h_scratch = nullptr; c.h_scratch_bytes = 0;
         const size_t nb = align_up(host_bytes + host_bytes / 4, 1 << 20);
         if (cudaMallocHost(&c.h_scratch, nb) != cudaSuccess) { c.err = "cudaMallocHost(scratch) failed"; return false; }
@@ -554,6 +555,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_groups); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps); cudaFree(kv.second.d_rmaps);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
+    if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
     if (c.evFork) cudaEventDestroy(c.evFork);
     if (c.evJoin) cudaEventDestroy(c.evJoin);
     if (c.stream2) cudaStreamDestroy(c.stream2);
@@ -741,6 +743,30 @@ int orbb200_pyramid_level(orbb200_ctx* ctx, int img_index, int level, int blurre
     const uint8_t* src = (blurred ? c.d_blur : c.d_pyr) + (size_t)img_index * g.pyrBytes + L.off;
     ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(dst, dst_stride, src, L.pitch, (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost, c.stream));
     ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return ORBB200_OK;
+}
+
+int orbb200_pyramid_mirror(orbb200_ctx* ctx, int img_index, int blurred, const uint8_t** level_ptr, size_t* level_pitch, int* level_w, int* level_h)
+{
+    CTX_ENTER(ctx);
+    if (!c.cur || img_index < 0 || img_index >= c.curN || !level_ptr || !level_pitch) { c.err = "pyramid_mirror: bad argument"; return ORBB200_ERR_ARG; }
+    const Geom& g = c.cur->g;
+    if (c.h_pyrMirrorBytes < g.pyrBytes) {
+        if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
+        c.h_pyrMirror = nullptr; c.h_pyrMirrorBytes = 0;
+        ORBB200_CUDA_OK(c, cudaMallocHost((void**)&c.h_pyrMirror, c.gmax.pyrBytes));
+        c.h_pyrMirrorBytes = c.gmax.pyrBytes;
+    }
+    const uint8_t* src = (blurred ? c.d_blur : c.d_pyr) + (size_t)img_index * g.pyrBytes;
+    ORBB200_CUDA_OK(c, cudaMemcpyAsync(c.h_pyrMirror, src, g.pyrBytes, cudaMemcpyDeviceToHost, c.stream));
+    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    for (int l = 0; l < c.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        level_ptr[l] = (L.w > 0 && L.h > 0) ? c.h_pyrMirror + L.off : nullptr;
+        level_pitch[l] = (size_t)L.pitch;
+        if (level_w) level_w[l] = L.w;
+        if (level_h) level_h[l] = L.h;
+    }
     return ORBB200_OK;
 }
 

@@ -143,6 +143,8 @@ struct Ctx {
     size_t d_scratch_bytes = 0;
     uint8_t* h_scratch = nullptr;            // pinned generic
     size_t h_scratch_bytes = 0;
+    uint8_t* h_pyrMirror = nullptr;          // pinned copy of one image's pyramid block (orbb200_pyramid_mirror)
+    size_t h_pyrMirrorBytes = 0;
     uint8_t* d_step = nullptr;               // device staging of the host step (images, queries, results)
     size_t d_step_bytes = 0;
 
