@@ -157,12 +157,26 @@ __global__ void __launch_bounds__(1024) bird_pyramid_kernel(uint8_t* __restrict_
             const int y0 = ty.x, y1 = min(y0 + 1, S.h - 1), b1 = ty.y, b0 = 256 - b1;
             const uint8_t* r0 = s + (size_t)y0 * S.pitch;
             const uint8_t* r1 = s + (size_t)y1 * S.pitch;
-            for (int x = lane; x < D.w; x += 32) {
-                const int2 tx = tab[D.tabX + x];
-                const int x0 = tx.x, x1 = min(x0 + 1, S.w - 1), a1 = tx.y, a0 = 256 - a1;
-                const uint32_t h0 = (uint32_t)(r0[x0] * a0 + r0[x1] * a1) & 0xffffu;
-                const uint32_t h1 = (uint32_t)(r1[x0] * a0 + r1[x1] * a1) & 0xffffu;
-                d[(size_t)y * D.pitch + x] = (uint8_t)min((h0 * b0 + h1 * b1 + 32768u) >> 16, 255u);
+            // four output pixels per lane and trip, every load of the four requested before the first store: source and
+            // destination live in the same allocation, so the compiler keeps loads behind earlier stores, and a lane with one pixel
+            // in flight waits out two dependent load latencies (table entry, then the four taps) per pixel
+            for (int xb = lane; xb < D.w; xb += 128) {
+                int2 tx[4];
+                uint32_t p00[4], p01[4], p10[4], p11[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) tx[k] = tab[D.tabX + min(xb + 32 * k, D.w - 1)];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x0 = tx[k].x, x1 = min(x0 + 1, S.w - 1);
+                    p00[k] = r0[x0]; p01[k] = r0[x1]; p10[k] = r1[x0]; p11[k] = r1[x1];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x = xb + 32 * k, a1 = tx[k].y, a0 = 256 - a1;
+                    const uint32_t h0 = (uint32_t)(p00[k] * a0 + p01[k] * a1) & 0xffffu;
+                    const uint32_t h1 = (uint32_t)(p10[k] * a0 + p11[k] * a1) & 0xffffu;
+                    if (x < D.w) d[(size_t)y * D.pitch + x] = (uint8_t)min((h0 * b0 + h1 * b1 + 32768u) >> 16, 255u);
+                }
             }
         }
         __syncthreads();                    // level l complete (global writes of this CTA) before level l+1 reads it
