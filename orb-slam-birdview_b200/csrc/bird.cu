@@ -289,7 +289,10 @@ __device__ void rb_heap_select(RB v, int first, int middle, int last)
 //      do not belong right of it) while the former lies before the latter; the stoppers are a property of the
 //      untouched data, so two stream compactions give both lists, a count gives the number of swaps K, and the K
 //      disjoint swaps and the returned cut point follow -- the exact element order of the sequential code. ----
-constexpr int SEL_THREADS = 256;
+#ifndef ORBB200_SEL_THREADS
+#define ORBB200_SEL_THREADS 256
+#endif
+constexpr int SEL_THREADS = ORBB200_SEL_THREADS;
 
 struct RBPar { float* r; uint32_t* p; uint16_t* A; uint16_t* B; int* sc; };   // sc: [SEL_THREADS / 32 + 4] ints of scratch
 
