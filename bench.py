@@ -1194,7 +1194,7 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true", help="skip C1 / C4 / C5 / per-frame legs")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core baseline (profiling runs)")
     ap.add_argument("--device-contexts", type=int, default=2, help="contexts (streams) the device-resident leg alternates its steps over")
-    ap.add_argument("--e2e-contexts", type=int, default=6, help="contexts (streams) the host-buffer leg keeps in flight")
+    ap.add_argument("--e2e-contexts", type=int, default=8, help="contexts (streams) the host-buffer leg keeps in flight")
     ap.add_argument("--e2e-calls-per-step", type=int, default=4, help="the C2 host-buffer leg hands a step's batch over as this many calls (frames_per_step must be a multiple)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the CPUs nearest its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
