@@ -155,6 +155,24 @@ int gate_and_level(MapPoint* pMP, const cv::Mat& p3Dw, const cv::Mat& Ow, KeyFra
         return -1;
     return pMP->PredictScale(dist3D,pKF);
 }
+
+// Pinhole projection of a camera-frame point the way the KeyFrame searches write it -- x = X * invz, u = fx * x + cx -- behind their
+// "depth must be positive" test.  The reciprocal is a float division in SearchByProjection(KeyFrame*, Scw, ...) and
+// Fuse(KeyFrame*, points, th) (:331, :859) and a double division rounded to float in Fuse(KeyFrame*, Scw, ...) and SearchBySim3
+// (:1019, :1166, :1246): both are kept, the last bit of invz decides which cell a window starts in.
+struct Pixel { float u, v, invz; };
+bool pinhole(const cv::Mat& p3Dc, float fx, float fy, float cx, float cy, bool doubleReciprocal, Pixel& px)
+{
+    const float z = p3Dc.at<float>(2);
+    if(z<0.0f)
+        return false;
+    px.invz = doubleReciprocal ? (float)(1.0/z) : 1/z;
+    const float x = p3Dc.at<float>(0)*px.invz;
+    const float y = p3Dc.at<float>(1)*px.invz;
+    px.u = fx*x+cx;
+    px.v = fy*y+cy;
+    return true;
+}
 }  // namespace
 
 // the constants and the constructor of src/ORBmatcher.cc:34-43 (this file takes that file's place)
@@ -329,16 +347,9 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapP
         if(pMP->isBad() || spAlreadyFound.count(pMP))
             continue;
         cv::Mat p3Dw = pMP->GetWorldPos();
-        cv::Mat p3Dc = S.Rcw*p3Dw+S.tcw;
-        if(p3Dc.at<float>(2)<0.0)
-            continue;
-        const float invz = 1/p3Dc.at<float>(2);
-        const float x = p3Dc.at<float>(0)*invz;
-        const float y = p3Dc.at<float>(1)*invz;
-        const float u = fx*x+cx;
-        const float v = fy*y+cy;
-        if(!pKF->IsInImage(u,v))
-            continue;
+        Pixel px;
+        if (!pinhole(S.Rcw*p3Dw+S.tcw, fx, fy, cx, cy, false, px) || !pKF->IsInImage(px.u,px.v)) continue;
+        const float u = px.u, v = px.v;
         float dist;
         const int nPredictedLevel = gate_and_level(pMP, p3Dw, S.Ow, pKF, dist);
         if (nPredictedLevel < 0) continue;
@@ -511,15 +522,9 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &
                 cv::Mat p3Dw = pMP->GetWorldPos();
                 cv::Mat p3DcA = RAw*p3Dw + tAw;
                 cv::Mat p3DcB = sRBA*p3DcA + tBA;
-                if(p3DcB.at<float>(2)<0.0)
-                    continue;
-                const float invz = 1.0/p3DcB.at<float>(2);
-                const float x = p3DcB.at<float>(0)*invz;
-                const float y = p3DcB.at<float>(1)*invz;
-                const float u = fx*x+cx;
-                const float v = fy*y+cy;
-                if(!pKFB->IsInImage(u,v))
-                    continue;
+                Pixel px;
+                if (!pinhole(p3DcB, fx, fy, cx, cy, true, px) || !pKFB->IsInImage(px.u,px.v)) continue;
+                const float u = px.u, v = px.v;
                 const float maxDistance = pMP->GetMaxDistanceInvariance();
                 const float minDistance = pMP->GetMinDistanceInvariance();
                 const float dist3D = cv::norm(p3DcB);
@@ -574,17 +579,10 @@ int ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const
         if(!pMP)
             continue;
         cv::Mat p3Dw = pMP->GetWorldPos();
-        cv::Mat p3Dc = Rcw*p3Dw + tcw;
-        if(p3Dc.at<float>(2)<0.0f)
-            continue;
-        const float invz = 1/p3Dc.at<float>(2);
-        const float x = p3Dc.at<float>(0)*invz;
-        const float y = p3Dc.at<float>(1)*invz;
-        const float u = fx*x+cx;
-        const float v = fy*y+cy;
-        if(!pKF->IsInImage(u,v))
-            continue;
-        const float ur = u-bf*invz;
+        Pixel px;
+        if (!pinhole(Rcw*p3Dw + tcw, fx, fy, cx, cy, false, px) || !pKF->IsInImage(px.u,px.v)) continue;
+        const float u = px.u, v = px.v;
+        const float ur = u-bf*px.invz;
         float dist3D;
         const int nPredictedLevel = gate_and_level(pMP, p3Dw, Ow, pKF, dist3D);
         if (nPredictedLevel < 0) continue;
@@ -648,16 +646,9 @@ int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint *> &vpPoi
         if(spAlreadyFound.count(pMP))
             continue;
         cv::Mat p3Dw = pMP->GetWorldPos();
-        cv::Mat p3Dc = S.Rcw*p3Dw+S.tcw;
-        if(p3Dc.at<float>(2)<0.0f)
-            continue;
-        const float invz = 1.0/p3Dc.at<float>(2);
-        const float x = p3Dc.at<float>(0)*invz;
-        const float y = p3Dc.at<float>(1)*invz;
-        const float u = fx*x+cx;
-        const float v = fy*y+cy;
-        if(!pKF->IsInImage(u,v))
-            continue;
+        Pixel px;
+        if (!pinhole(S.Rcw*p3Dw+S.tcw, fx, fy, cx, cy, true, px) || !pKF->IsInImage(px.u,px.v)) continue;
+        const float u = px.u, v = px.v;
         float dist3D;
         const int nPredictedLevel = gate_and_level(pMP, p3Dw, S.Ow, pKF, dist3D);
         if (nPredictedLevel < 0) continue;
