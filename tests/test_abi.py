@@ -66,9 +66,20 @@ def test_product_does_not_reference_the_oracle():
     pk = os.path.join(ROOT, "orb-slam-birdview_b200")
     for dirpath, _, files in os.walk(pk):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".cc", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "liborb_oracle" not in txt and "orb_oracle.h" not in txt, os.path.join(dirpath, f)
+                for line in txt.splitlines():
+                    code = line.split("#", 1)[0] if f == "Makefile" else line
+                    if f == "Makefile" or line.lstrip().startswith("#include"):
+                        assert "oracle" not in code, (line, os.path.join(dirpath, f))       # nothing built from or including oracle/ sources
+    # the product library holds no symbol of the oracle (the oracle-backed C ABI of oracle/abi_on_oracle.cpp is linked into the
+    # CPU test binary oracle/_ref/matcher_suite_oracle only)
+    import subprocess
+    lib = os.path.join(pk, "liborbb200.so")
+    if os.path.exists(lib):
+        syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+        assert "oracle_" not in syms
 
 
 def test_cpp_shim_compiles(pkg):
