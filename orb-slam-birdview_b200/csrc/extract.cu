@@ -702,7 +702,6 @@ __global__ void __launch_bounds__(FT_THREADS, ORBB200_FT_MINBLK) fast_cells_kern
 #ifndef ORBB200_FS_MINBLK
 #define ORBB200_FS_MINBLK 6
 #endif
-constexpr int FS_THREADS = 128, FS_WARPS = FS_THREADS / 32;
 constexpr int FS_LOADS = 5;        // global words in flight per thread while the tile is filled
 constexpr int FS_ROWS = 4;         // rows per quick-test step
 

@@ -30,6 +30,10 @@ constexpr int RS_ROWS = 32;             // output rows per resize tile (128 colu
 constexpr int FT_PITCH = 49;            // u32 words per row of fast_cells_kernel's shared tiles (>= 2*ceil(68/4)+3 = 37), general case
 constexpr int FT_PITCH_SMALL = 25;      // the same for shapes whose cell images are at most 44 pixels wide (2*11+3): half the shared memory
 constexpr int FS_PITCH = 71;            // u32 words per row of fast_strip_kernel's shared tiles: 1 pad + 68 pair words (136 pixels) + 2 pads
+#ifndef ORBB200_FS_THREADS
+#define ORBB200_FS_THREADS 128
+#endif
+constexpr int FS_THREADS = ORBB200_FS_THREADS, FS_WARPS = FS_THREADS / 32;   // threads of a fast_strip_kernel CTA
 constexpr int FS_MAX_CELLS = 8;         // cells per group (cells are >= 30 px wide: at most 4 fit the tile)
 
 // Geometry of one pyramid level for one image shape (host-computed, passed to kernels by value).
@@ -98,7 +102,7 @@ struct FastSmem {
 // Shared-memory carve of fast_strip_kernel for a set of cell groups (host-computed maxima).
 struct FastStripSmem {
     int tileRows = 0, scrRows = 0, segCap = 0, clistCap = 0;
-    size_t bytes() const { return sizeof(uint32_t) * ((size_t)(tileRows + scrRows + 5) * FS_PITCH + 8 + clistCap) + sizeof(uint16_t) * 4 * (size_t)segCap; }
+    size_t bytes() const { return sizeof(uint32_t) * ((size_t)(tileRows + scrRows + 5) * FS_PITCH + 8 + clistCap) + sizeof(uint16_t) * FS_WARPS * (size_t)segCap; }
 };
 // Append one group of `cells` horizontally adjacent FAST cells (3 x int4) and grow `need`: [x0,x1) x [y0,y1) is the image of the
 // whole group in level coordinates (the first cell's iniX .. the last cell's maxX), cells are wCell wide.
