@@ -702,8 +702,14 @@ __global__ void __launch_bounds__(FT_THREADS, ORBB200_FT_MINBLK) fast_cells_kern
 #ifndef ORBB200_FS_MINBLK
 #define ORBB200_FS_MINBLK 6
 #endif
-constexpr int FS_LOADS = 5;        // global words in flight per thread while the tile is filled
-constexpr int FS_ROWS = 4;         // rows per quick-test step
+#ifndef ORBB200_FS_LOADS
+#define ORBB200_FS_LOADS 10
+#endif
+#ifndef ORBB200_FS_ROWS
+#define ORBB200_FS_ROWS 2
+#endif
+constexpr int FS_LOADS = ORBB200_FS_LOADS;   // global words in flight per thread while the tile is filled
+constexpr int FS_ROWS = ORBB200_FS_ROWS;     // rows per quick-test step
 
 template <int P>
 __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kernel(const uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned candPerImg,
