@@ -746,6 +746,32 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
 
     if (tid < FS_MAX_CELLS) sCellHit[tid] = 0;
     if (tid == 0) sN = 0;
+    // The group's image: 32-bit words widened to u16 pairs (+ bias), the (row, word) items flattened over the CTA and requested
+    // FS_LOADS at a time before any is stored -- for the usual tile that is ALL of a thread's words in one global round trip, and
+    // the first batch is requested before the masks and the score clear below, which need no pixel.
+    const uint8_t* S = pyr + (size_t)img * pyrBytes + (unsigned)gb.x + (size_t)y0 * pitch + xa;
+    const uint32_t magicNw = (uint32_t)gc.y;             // 2^32 / nw + 1
+    const int total = th * nw;
+    uint32_t v[FS_LOADS];
+    int o[FS_LOADS];
+    auto request = [&](int base) {
+#pragma unroll
+        for (int j = 0; j < FS_LOADS; j++) {
+            const int i = min(base + j * FS_THREADS, total - 1);
+            const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
+            const int k = i - r * nw;
+            v[j] = *reinterpret_cast<const uint32_t*>(S + (unsigned)(r * pitch + 4 * k));
+            o[j] = r * P + 2 * k;
+        }
+    };
+    auto widen = [&]() {
+#pragma unroll
+        for (int j = 0; j < FS_LOADS; j++) {             // (surplus items rewrite the last word with the same value)
+            tile[o[j] + 1] = __byte_perm(v[j], FT_BIAS, 0x5150);
+            tile[o[j] + 2] = __byte_perm(v[j], FT_BIAS, 0x5352);
+        }
+    };
+    request(tid);
     // per-pair lane masks
     for (int i = tid; i < P; i += FS_THREADS) {
         uint32_t in = 0, lm = 0, rm = 0, ci = 0;
@@ -765,35 +791,13 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
         inMask[i] = in; lMask[i] = lm; rMask[i] = rm; cellIdx[i] = ci; p2Mask[i] = in;
     }
     for (int i = tid; i < (scrRows * P + 3) >> 2; i += FS_THREADS) reinterpret_cast<uint4*>(scr)[i] = make_uint4(0, 0, 0, 0);
-    // the group's image: 32-bit words widened to u16 pairs (+ bias), the (row, word) items flattened over the CTA and fetched
-    // FS_LOADS at a time before any is stored (one global round trip per batch instead of one per row); words next to the loaded
-    // span hold the bias so that masked lanes stay in range (see fast_cells_kernel)
-    {
-        const uint8_t* S = pyr + (size_t)img * pyrBytes + (unsigned)gb.x + (size_t)y0 * pitch + xa;
-        const uint32_t magicNw = (uint32_t)gc.y;         // 2^32 / nw + 1
-        const int total = th * nw;
-        for (int base = tid; base < total; base += FS_THREADS * FS_LOADS) {
-            uint32_t v[FS_LOADS];
-            int o[FS_LOADS];
-#pragma unroll
-            for (int j = 0; j < FS_LOADS; j++) {
-                const int i = min(base + j * FS_THREADS, total - 1);
-                const int r = nw == 1 ? i : (int)__umulhi((uint32_t)i, magicNw);
-                const int k = i - r * nw;
-                v[j] = *reinterpret_cast<const uint32_t*>(S + (unsigned)(r * pitch + 4 * k));
-                o[j] = r * P + 2 * k;
-            }
-#pragma unroll
-            for (int j = 0; j < FS_LOADS; j++) {         // (surplus items rewrite the last word with the same value)
-                tile[o[j] + 1] = __byte_perm(v[j], FT_BIAS, 0x5150);
-                tile[o[j] + 2] = __byte_perm(v[j], FT_BIAS, 0x5352);
-            }
-        }
-        for (int r = tid; r < th; r += FS_THREADS) {
-            uint32_t* t = tile + r * P;
-            t[0] = FT_BIAS; t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS;
-        }
+    // words next to the loaded span hold the bias so that masked lanes stay in range (see fast_cells_kernel)
+    for (int r = tid; r < th; r += FS_THREADS) {
+        uint32_t* t = tile + r * P;
+        t[0] = FT_BIAS; t[2 * nw + 1] = FT_BIAS; t[2 * nw + 2] = FT_BIAS;
     }
+    widen();
+    for (int base = tid + FS_THREADS * FS_LOADS; base < total; base += FS_THREADS * FS_LOADS) { request(base); widen(); }
     __syncthreads();
 
     const unsigned ltmask = (1u << lane) - 1u;
