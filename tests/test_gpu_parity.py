@@ -87,6 +87,17 @@ def test_extract_full_hd_4000(pkg):
     _compare_extract(k, d, k0, d0, "c5")
 
 
+def test_extract_large_image_near_the_size_limit(pkg):
+    """A 4000 x 3000 image (12 MP, the level-0 FAST region is close to the 4096-pixel coordinate limit of the packed candidates) with
+    a 12000-feature budget: 133 x 99 FAST cells on level 0, ~3300 cell groups, the octree of level 0 with ~10^5 candidates."""
+    img = synth.synth_frame(3000, 4000, 12000)
+    ex = pkg.ORBextractor(12000, 1.2, 8, 20, 7, max_size=(4000, 3000))
+    k, d = ex(img)
+    k0, d0 = oracle.Extractor(12000, 1.2, 8, 20, 7)(img)
+    assert len(k0) > 11000
+    _compare_extract(k, d, k0, d0, "12 MP")
+
+
 def test_extract_batch_independent_of_batching(pkg):
     imgs = [synth.synth_frame(376, 1241, 2000 + i) for i in range(5)]
     ex = pkg.ORBextractor(2000, 1.2, 8, 20, 7, max_size=(1241, 376), max_batch=5)
