@@ -35,7 +35,9 @@ SCENES = {
     "wide": dict(seed=13, n_points=1200, n_clutter=600, n_birds=600,                               # wide windows, loose ratios: long greedy chains
                  params={0: 6.0, 1: 0.95, 2: 30.0, 3: 20.0, 4: 20.0, 5: 6.0, 6: 12.0, 7: 10.0, 8: 25.0, 9: 0.9, 10: 0.95, 12: 0.9}),
     "tight": dict(seed=14, n_points=500, n_clutter=50, n_birds=200, params={0: 1.0, 1: 0.6, 2: 7.0, 5: 2.0, 9: 0.6}),
+    "tiny": dict(seed=15, n_points=40, n_clutter=6, n_birds=24),                                   # a few dozen features: most calls find little or nothing
 }
+SPARSE = {"tiny"}                                                                                  # scenes whose calls may legitimately come back empty
 
 
 def _have_ref_build():
@@ -74,7 +76,7 @@ def test_adapters_on_oracle_equal_unmodified_reference(name, tmp_path):
     _same(ref, ora, name)
     # the scene exercises every method: no call may come back empty
     for tag, r in ref.items():
-        assert r["ret"] > 0, f"{name}: {tag} found nothing -- the scene does not exercise it"
+        assert r["ret"] > 0 or name in SPARSE, f"{name}: {tag} found nothing -- the scene does not exercise it"
 
 
 def test_reference_output_equals_committed_golden(tmp_path):
