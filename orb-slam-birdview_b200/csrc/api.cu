@@ -125,7 +125,6 @@ bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes)
     if (host_bytes > c.h_scratch_bytes) {
         cudaStreamSynchronize(c.stream);
         if (c.h_scratch) cudaFreeHost(c.h_scratch);
-    if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
         c.h_scratch = nullptr; c.h_scratch_bytes = 0;
         const size_t nb = align_up(host_bytes + host_bytes / 4, 1 << 20);
         if (cudaMallocHost(&c.h_scratch, nb) != cudaSuccess) { c.err = "cudaMallocHost(scratch) failed"; return false; }
@@ -223,6 +222,13 @@ const ShapeTables* get_shape(Ctx& c, int w, int h)
         }
     }
     st.nFastGroups = (int)(groups.size() / 3);
+    {   // groups are level-major: first group of each level
+        int gi = 0;
+        for (int l = 0; l <= g.nlevels; l++) {
+            while (gi < st.nFastGroups && groups[3 * (size_t)gi].z < l) gi++;
+            st.fastGroupBase[l] = gi;
+        }
+    }
     std::vector<int4> btiles, rtiles;
     for (int l = 0; l < g.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
@@ -349,49 +355,89 @@ void drain_stage_events(Ctx& c)
 // fork == true: the blur (FMA pipe + memory bound; only the descriptors need it) runs on a second stream beside
 // FAST + octree (integer-ALU bound) and joins before the descriptor kernel.  In a captured graph this becomes
 // two parallel branches.  With per-stage timing the stages run back to back on one stream.
-static void enqueue_extract_kernels(Ctx& c, int n, bool fork)
+//
+// One or two images (the drop-in's one-frame-per-call pattern) are latency bound: seven dependent resize launches, then FAST, the
+// octree (one CTA per level) and the descriptors.  Grid FAST reads no border pixel and level 0 needs no resize, so for them FAST +
+// octree of level 0 -- the longest of the per-level CTAs -- run on a third branch beside the resize chain; the other levels follow
+// the chain, the border fill + blur take the second branch, and the descriptor kernel joins all three.  Within a branch the
+// kernels are programmatic dependent launches (see pdl_wait): a successor's CTAs are resident and past their prologue when the
+// predecessor's last CTA retires.
+static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* hs = nullptr)
 {
+    const Geom& g = c.cur->g;
+    const HostMirror* mirror = hs ? &hs->mirror : nullptr;
+    launch_clear_counters(c, n);
+    if (hs) launch_import_host(c, hs->imgs, hs->imgBytes, hs->rowBytes, n);
+    if (fork && n <= 2 && c.splitLevel0 && !c.fastCells && c.cur->nFastGroups > 0 && g.nlevels > 1) {
+        cudaEventRecord(c.evFork0, c.stream);
+        cudaStreamWaitEvent(c.stream3, c.evFork0, 0);
+        launch_fast_levels(c, n, 0, 1, c.stream3, false);
+        launch_octree_levels(c, n, 0, 1, c.stream3, true);
+        cudaEventRecord(c.evJoin0, c.stream3);
+        launch_resizes(c, n, c.stream);
+        cudaEventRecord(c.evFork, c.stream);
+        cudaStreamWaitEvent(c.stream2, c.evFork, 0);
+        launch_border(c, n, c.stream2, false);
+        launch_blur(c, n, c.stream2, true);
+        cudaEventRecord(c.evJoin, c.stream2);
+        launch_fast_levels(c, n, 1, g.nlevels, c.stream, true);
+        launch_octree_levels(c, n, 1, g.nlevels, c.stream, true);
+        cudaStreamWaitEvent(c.stream, c.evJoin0, 0);
+        cudaStreamWaitEvent(c.stream, c.evJoin, 0);
+        launch_describe(c, n, false, mirror);
+        return;
+    }
     { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
     if (fork) {
         cudaEventRecord(c.evFork, c.stream);
         cudaStreamWaitEvent(c.stream2, c.evFork, 0);
         launch_blur(c, n, c.stream2);
         cudaEventRecord(c.evJoin, c.stream2);
-        launch_fast(c, n);
+        launch_fast(c, n, true);
         launch_octree(c, n);
         cudaStreamWaitEvent(c.stream, c.evJoin, 0);
-        launch_describe(c, n);
+        launch_describe(c, n, false, mirror);
         return;
     }
     { StageTimer t(c, 2); launch_fast(c, n); }
     { StageTimer t(c, 3); launch_blur(c, n, c.stream); }
     { StageTimer t(c, 4); launch_octree(c, n); }
-    { StageTimer t(c, 5); launch_describe(c, n); }
+    { StageTimer t(c, 5); launch_describe(c, n, false, mirror); }
 }
 
 // The ~20 launches of one extraction are captured once per (shape, image count) into a CUDA graph and replayed:
 // for single frames (the real-time use of the drop-in) the CPU launch cost is a large part of the latency.
 // Per-stage timing needs events between the kernels, so it uses the plain launches.
-static int run_extract(Ctx& c, int n)
+//
+// hs != nullptr (a small host call): the images are in the pinned staging block and the results are wanted in its mirror half; the
+// upload (import_host_kernel) and the delivery (describe_kernel's second set of stores) are then part of the same graph, keyed
+// separately and re-captured if the staging block has moved.
+static int run_extract(Ctx& c, int n, const HostStage* hs = nullptr)
 {
     c.stereoValid = false;
     if (c.timing || !c.useGraphs) {
-        enqueue_extract_kernels(c, n, !c.timing && c.forkBlur);
+        enqueue_extract_kernels(c, n, !c.timing && c.forkBlur, hs);
         ORBB200_CUDA_OK(c, cudaGetLastError());
         return ORBB200_OK;
     }
     ShapeTables* st = const_cast<ShapeTables*>(c.cur);
-    auto it = st->graphs.find(n);
+    const int key = hs ? n + 65536 : n;
+    auto it = st->graphs.find(key);
+    if (it != st->graphs.end() && hs && it->second.stage != hs->imgs) {       // the pinned block was reallocated since the capture
+        cudaGraphExecDestroy(it->second.exec);
+        st->graphs.erase(it);
+        it = st->graphs.end();
+    }
     if (it == st->graphs.end()) {
         // warm the lazily configured kernel attributes outside the capture, then capture
         const long long before = c.launches;
-        enqueue_extract_kernels(c, n, c.forkBlur);
+        enqueue_extract_kernels(c, n, c.forkBlur, hs);
         ORBB200_CUDA_OK(c, cudaGetLastError());
         const long long perRun = c.launches - before;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         ORBB200_CUDA_OK(c, cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_extract_kernels(c, n, c.forkBlur);
+        enqueue_extract_kernels(c, n, c.forkBlur, hs);
         c.launches -= perRun;                      // the capture pass enqueues nothing
         cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
         if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
@@ -401,7 +447,7 @@ static int run_extract(Ctx& c, int n)
             c.useGraphs = false;
             return ORBB200_OK;                     // the warm-up run above already produced this call's result
         }
-        st->graphs[n] = {exec, perRun};
+        st->graphs[key] = {exec, perRun, hs ? hs->imgs : nullptr};
         return ORBB200_OK;                         // ditto
     }
     ORBB200_CUDA_OK(c, cudaGraphLaunch(it->second.exec, c.stream));
@@ -464,11 +510,18 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evFork0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evJoin0, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.streamBird, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evBirdFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evBirdJoin, cudaEventDisableTiming) != cudaSuccess)
         return fail("cudaStreamCreate failed", ORBB200_ERR_CUDA);
     c.forkBlur = std::getenv("ORBB200_SERIAL") == nullptr;
+    c.pdl = std::getenv("ORBB200_NO_PDL") == nullptr;
+    c.splitLevel0 = std::getenv("ORBB200_NO_SPLIT") == nullptr;
+    c.octreeSmemCand = std::getenv("ORBB200_NO_OCTREE_SMEM") == nullptr;
+    c.hostGraph = std::getenv("ORBB200_NO_HOST_GRAPH") == nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
     c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
     c.stageUploads = std::getenv("ORBB200_NO_STAGED_UPLOAD") == nullptr;
@@ -559,6 +612,9 @@ void orbb200_destroy(orbb200_ctx* ctx)
     if (c.evFork) cudaEventDestroy(c.evFork);
     if (c.evJoin) cudaEventDestroy(c.evJoin);
     if (c.stream2) cudaStreamDestroy(c.stream2);
+    if (c.evFork0) cudaEventDestroy(c.evFork0);
+    if (c.evJoin0) cudaEventDestroy(c.evJoin0);
+    if (c.stream3) cudaStreamDestroy(c.stream3);
     if (c.evBirdFork) cudaEventDestroy(c.evBirdFork);
     if (c.evBirdJoin) cudaEventDestroy(c.evBirdJoin);
     if (c.streamBird) cudaStreamDestroy(c.streamBird);
@@ -690,6 +746,44 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
     // measured per call: 752x480 0.241 -> 0.223 ms, 1241x376 0.370 -> 0.252 ms staged; 1920x1080 0.458 -> 0.497 ms (the host memcpy of
     // 2 MB costs more than the bounce saves): staged up to 1.5 MB per call
     const bool staged = c.stageUploads && imgB * n <= (3u << 19) && ensure_scratch(c, 0, STAGE_LIMIT);
+    // One or two staged images whose results fit the mirror half of the block: ONE graph launch does the upload (the first kernel
+    // reads the pinned rows over PCIe), the extraction and the delivery (the last kernel also stores into the pinned mirror) --
+    // no copy-engine operation on either side.  Measured per call (752x480 / 1241x376): 0.195 / 0.199 -> see DESIGN.md section 5.
+    const int rowB = (w + 15) & ~15;
+    const int kpi = g.kpPerImg;
+    const size_t cntB = align_up(sizeof(int32_t) * (size_t)n, 64);
+    if (staged && c.hostGraph && n <= 2 && (size_t)rowB * h * n <= STAGE_D2H_OFF && 64 + cntB + (size_t)n * kpi * 60 <= STAGE_LIMIT - STAGE_D2H_OFF && kps &&
+        desc && n_out && cap_per_img > 0) {
+        HostStage hs;
+        hs.imgs = c.h_scratch + STAGE_H2D_OFF; hs.imgBytes = (size_t)rowB * h; hs.rowBytes = rowB;
+        uint8_t* hm = c.h_scratch + STAGE_D2H_OFF;
+        hs.mirror.status = reinterpret_cast<int32_t*>(hm);
+        hs.mirror.counts = reinterpret_cast<int32_t*>(hm + 64);
+        hs.mirror.kps = reinterpret_cast<orbb200_kp_t*>(hm + 64 + cntB);
+        hs.mirror.desc = hm + 64 + cntB + (size_t)n * kpi * sizeof(orbb200_kp_t);
+        hs.mirror.d_status = c.d_status;
+        for (int i = 0; i < n; i++) {
+            uint8_t* dst = c.h_scratch + STAGE_H2D_OFF + (size_t)i * hs.imgBytes;
+            if (stride == (size_t)w && rowB == w) memcpy(dst, imgs[i], imgB);
+            else for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * rowB, imgs[i] + (size_t)y * stride, (size_t)w);
+        }
+        int rc = run_extract(c, n, &hs);
+        if (rc != ORBB200_OK) return rc;
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        if (*hs.mirror.status != 0) {
+            cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
+            c.err = "device-side overflow in octree distribution (status " + std::to_string(*hs.mirror.status) + ")";
+            return ORBB200_ERR_UNSUPPORTED;
+        }
+        for (int i = 0; i < n; i++) {
+            n_out[i] = hs.mirror.counts[i];
+            if (n_out[i] > cap_per_img) { c.err = "extract: caller capacity too small"; return ORBB200_ERR_CAPACITY; }
+            const size_t m = (size_t)std::max(n_out[i], 0);
+            memcpy(kps + (size_t)i * cap_per_img, hs.mirror.kps + (size_t)i * kpi, m * sizeof(orbb200_kp_t));
+            memcpy(desc + (size_t)i * cap_per_img * 32, hs.mirror.desc + (size_t)i * kpi * 32, m * 32);
+        }
+        return ORBB200_OK;
+    }
     for (int i = 0; i < n; i++) {
         const uint8_t* src = imgs[i];
         size_t srcStride = stride;

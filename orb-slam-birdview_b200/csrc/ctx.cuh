@@ -25,12 +25,13 @@ struct ShapeTables {
     int resizeTileCount[MAX_LEVELS] = {0};
     bool resizeNarrow[MAX_LEVELS] = {false};  // taps of any 4 adjacent output columns span <= 8 source bytes (scale <= 2)
     int resizeSmemPitch[MAX_LEVELS] = {0}, resizeSmemRows[MAX_LEVELS] = {0};   // staged source window of a resize tile
-    struct GraphExec { cudaGraphExec_t exec; long long launches; };
+    struct GraphExec { cudaGraphExec_t exec; long long launches; const uint8_t* stage; };
     std::map<int, GraphExec> graphs;   // captured extraction pipeline per image count
     int nFastCells = 0;         // entries of d_cells (cells the reference skips at the image edge are not listed)
     FastSmem fastSmem;          // shared-memory carve of fast_cells_kernel
     int4* d_groups = nullptr;   // the same cells as groups of up to 4 per cell row for fast_strip_kernel, 3 x int4 each
     int nFastGroups = 0;
+    int fastGroupBase[MAX_LEVELS + 1] = {0};   // groups of level l: [fastGroupBase[l], fastGroupBase[l+1])
     FastStripSmem fastStrip;
 };
 
@@ -89,6 +90,12 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // side branch of the extraction graph (blur runs beside FAST + octree)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t stream3 = nullptr;          // one or two images: FAST + octree of level 0 beside the resize chain
+    cudaEvent_t evFork0 = nullptr, evJoin0 = nullptr;
+    bool pdl = true;                         // programmatic dependent launches inside the extraction chain (ORBB200_NO_PDL=1 turns them off)
+    bool octreeSmemCand = true;              // one or two images: a level's candidates are swept from shared memory (ORBB200_NO_OCTREE_SMEM=1: from L2)
+    bool hostGraph = true;                   // small host calls: upload and result delivery are nodes of the extraction graph (ORBB200_NO_HOST_GRAPH=1: copy-engine operations around it)
+    bool splitLevel0 = true;                 // the level-0 branch for one or two images (ORBB200_NO_SPLIT=1 turns it off)
     cudaStream_t streamBird = nullptr;       // the birdview front-end of the batched frame step runs beside the front-camera extraction
     cudaEvent_t evBirdFork = nullptr, evBirdJoin = nullptr;
     bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)

@@ -38,6 +38,20 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
     *reinterpret_cast<uint4*>(d + x16) = o;               // 128-byte pitched rows: the row padding absorbs the tail
 }
 
+// The same for a small host call: the images sit in the context's pinned staging block (rows padded to 16 bytes by the host
+// memcpy) and this kernel reads them over PCIe itself, 16 bytes per lane, so that the upload is a node of the extraction graph
+// instead of a copy-engine operation in front of it.
+__global__ void __launch_bounds__(128) import_host_kernel(const uint8_t* __restrict__ src, unsigned imgBytes, int rowVec, int nVec,
+                                                          uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned off0, int pitch)
+{
+    const int img = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    if (i >= nVec) return;
+    const int r = i / rowVec, k = i - r * rowVec;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)img * imgBytes) + i);
+    *reinterpret_cast<uint4*>(pyr + (size_t)img * pyrBytes + off0 + (size_t)r * pitch + 16 * k) = v;     // the row padding absorbs the tail
+}
+
 // ---------------------------------------------------------------------------------------------------
 // cv::resize INTER_LINEAR u8 (reference src/ORBextractor.cc:1120): level l-1 -> l.
 // 11-bit fixed-point coefficients from host-built tables; vertical pass
@@ -89,6 +103,7 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
     extern __shared__ __align__(128) uint8_t rsSmem[];
     __shared__ int4 sY[RS_ROWS];
     __shared__ __align__(8) uint64_t sBar;
+    pdl_launch_dependents();
     const int4 t = __ldg(tiles + 2 * blockIdx.x);       // {x0, y0, first staged source row, rows}
     const int4 u = __ldg(tiles + 2 * blockIdx.x + 1);   // {first staged source column, vectors per row, 2^16/vectors + 1, -}
     const int img = blockIdx.y;
@@ -102,6 +117,7 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; i++) xt[i] = __ldg(xtab + dst.xtabOff + min(x4 + i, dst.w - 1));
     if (tid < RS_ROWS) sY[tid] = __ldg(ytab + dst.ytabOff + min(y0 + tid, dst.h - 1));
+    pdl_wait();                                                           // the source level is complete
     if (srcMap != nullptr) {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sBar);
         if (tid == 0) {
@@ -205,6 +221,8 @@ __global__ void __launch_bounds__(128) border_kernel(uint8_t* __restrict__ pyr, 
 {
     const int level = blockIdx.x / BD_CHUNKS, chunk = blockIdx.x - level * BD_CHUNKS, img = blockIdx.y;
     const LevelGeom L = g.lv[level];
+    pdl_launch_dependents();
+    pdl_wait();
     if (L.w < 8 || L.h < 4) return;
     uint8_t* B = pyr + (size_t)img * pyrBytes + L.off;
     auto rx = [&](int x) { return x < 0 ? -x : (x >= L.w ? 2 * (L.w - 1) - x : x); };
@@ -269,9 +287,11 @@ __global__ void __launch_bounds__(BL_WARPS * 32) blur_kernel(const uint8_t* __re
     // warp index through a shuffle: lets the compiler treat everything derived from the tile (level, row base
     // pointers) as warp-uniform and address the loads as uniform base + 32-bit lane offset
     const int tileIdx = blockIdx.x * BL_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    pdl_launch_dependents();
     if (tileIdx >= nTiles) return;
     const int lane = threadIdx.x & 31;
     const int4 t = __ldg(tiles + tileIdx);          // {level, x0, y0, -}
+    pdl_wait();
     const LevelGeom L = g.lv[t.x];
     const int img = blockIdx.y;
     const int x = t.y + 4 * lane, y0 = t.z;
@@ -730,6 +750,7 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
     __shared__ int sN, sBase, sCellHit[FS_MAX_CELLS];
 
     const int img = blockIdx.y;
+    pdl_launch_dependents();
     const int4 ga = __ldg(groups + 3 * blockIdx.x);      // {x0|y0<<16, x1|y1<<16, level, cells}
     const int4 gb = __ldg(groups + 3 * blockIdx.x + 1);  // {level byte offset, pitch, candOff, candCap}
     const int4 gc = __ldg(groups + 3 * blockIdx.x + 2);  // {wCell, -, -, -}
@@ -771,6 +792,7 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
             tile[o[j] + 2] = __byte_perm(v[j], FT_BIAS, 0x5352);
         }
     };
+    pdl_wait();                                          // the level's pixels are final; the candidate counters are zeroed
     request(tid);
     // per-pair lane masks
     for (int i = tid; i < P; i += FS_THREADS) {
@@ -945,11 +967,12 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warpSums, int& total)
     return wbase + x - v;
 }
 
-size_t octree_smem_bytes(int maxNodes)
+size_t octree_smem_bytes(int maxNodes, int smemCand)
 {
     const int P2 = 1 << (32 - __builtin_clz(std::max(maxNodes, 2) - 1));
     // nodes A,B (8 B) + cnt A,B (4 B) + cc (16 B) + newPos (4 B) + childPos (16 B) + order (4 B) + sort keys (P2*4)
-    return (size_t)maxNodes * (8 * 2 + 4 * 2 + 16 + 4 + 16 + 4 + 4) + (size_t)P2 * 4 + 256;
+    // + the shared-memory copy of the candidates and their labels (6 B each)
+    return (size_t)maxNodes * (8 * 2 + 4 * 2 + 16 + 4 + 16 + 4 + 4) + (size_t)P2 * 4 + 256 + (size_t)smemCand * 6;
 }
 
 // One sweep over a level's candidates: the packed candidate and its node label of OT_UNROLL strided items are
@@ -980,21 +1003,27 @@ __device__ __forceinline__ void ot_sweep(const uint32_t* __restrict__ C, const u
 template <int NT>
 __global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                             uint16_t* __restrict__ nodeOfAll, uint32_t* __restrict__ lvlKp,
-                                                            int32_t* __restrict__ lvlCount, int32_t* __restrict__ status)
+                                                            int32_t* __restrict__ lvlCount, int32_t* __restrict__ status, int levelBase, int smemCand)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int warpSums[NT / 32];
     __shared__ int sFlag;
 
     // blockIdx.y = level: the CTAs of level 0 (most candidates, longest) are dispatched first, the short ones fill the tail
-    const int level = blockIdx.y, img = blockIdx.x;
+    const int level = levelBase + blockIdx.y, img = blockIdx.x;
     const LevelGeom L = g.lv[level];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int N = L.quota;
     const int maxNodes = L.maxNodes;
     int n = min(candCount[img * MAX_LEVELS + level], L.candCap);
     const uint32_t* C = cand + (size_t)img * g.candPerImg + L.candOff;
     uint16_t* nodeOf = nodeOfAll + (size_t)img * g.candPerImg + L.candOff;
+    // One or two images: a CTA has the SM to itself, and its ~20 sweeps over the candidates are the critical path of the whole
+    // extraction.  When the level's candidates fit the shared memory left over (smemCand entries), the packed candidates are copied
+    // there by the first sweep and the node labels live there from the start: every later sweep is shared-memory only.
+    const bool local = n <= smemCand;
     uint32_t* outKp = lvlKp + (size_t)img * g.kpPerImg + L.kpOff;
 
     // carve shared memory
@@ -1009,6 +1038,8 @@ __global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __re
     int* order = childPos + 4 * maxNodes;    // [maxNodes] processing order -> node position
     int* aux = order + maxNodes;             // [maxNodes] scratch (split flag / processing rank)
     uint32_t* keys = reinterpret_cast<uint32_t*>(aux + maxNodes);   // [P2] sort keys
+    uint32_t* sC = keys + P2;                                       // [smemCand] candidates (few-image launches)
+    if (local) nodeOf = reinterpret_cast<uint16_t*>(sC + smemCand); // [smemCand] node labels
 
     if (n == 0 || L.nIni <= 0 || L.nIni > maxNodes) {
         if (tid == 0) lvlCount[img * MAX_LEVELS + level] = 0;
@@ -1039,8 +1070,10 @@ __global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __re
         int r = (int)__fdiv_rn((float)x, hX);
         r = min(r, nIni - 1);
         nodeOf[i] = (uint16_t)r;
+        if (local) sC[i] = v;
         atomicAdd(&curCnt[r], 1);
     });
+    if (local) C = sC;
     __syncthreads();
     // drop empty roots (compaction in order)
     int listSize;
@@ -1301,7 +1334,8 @@ __global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __re
 #endif
 constexpr int DS_NBUF = ORBB200_DS_NBUF;
 constexpr int DS_WARPS = 8;
-constexpr int DS_KPB = 32;        // keypoints per CTA: one lane each for the scalar (atan2, sincos) part
+constexpr int DS_KPB = 32;        // keypoints per CTA in batches: one lane each for the scalar (atan2, sincos) part, four per warp
+constexpr int DS_KPB_FEW = 8;     // one or two images: one keypoint per warp, four times the CTAs (the four in a row were a latency chain)
 constexpr int DS_R = 19;          // reach of the rotated rBRIEF pattern
 constexpr int DS_PROWS = 2 * DS_R + 1;
 constexpr int DS_TPATCH = ((DS_TBOX_W * DS_TBOX_H + 127) / 128) * 128;     // bytes of one TMA box in shared memory (128-byte aligned)
@@ -1309,11 +1343,13 @@ constexpr int DS_TPATCH = ((DS_TBOX_W * DS_TBOX_H + 127) / 128) * 128;     // by
 #ifndef ORBB200_DS_MINBLK
 #define ORBB200_DS_MINBLK 8
 #endif
+template <int KPB>
 __global__ void __launch_bounds__(DS_WARPS * 32, ORBB200_DS_MINBLK) describe_kernel(Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                                                                  const uint32_t* __restrict__ lvlKp, const int32_t* __restrict__ lvlCount,
                                                                  orbb200_kp_t* __restrict__ kps, uint8_t* __restrict__ desc,
-                                                                 int32_t* __restrict__ counts, const CUtensorMap* __restrict__ maps)
+                                                                 int32_t* __restrict__ counts, const CUtensorMap* __restrict__ maps, HostMirror M)
 {
+    constexpr int DS_KPB = KPB;
     __shared__ float sPX[16 * 32], sPY[16 * 32];      // [sample within the byte][lane]: conflict-free
     __shared__ int sLevel[DS_KPB], sX[DS_KPB], sY[DS_KPB], sResp[DS_KPB], sM01[DS_KPB], sM10[DS_KPB];
     __shared__ float sA[DS_KPB], sB[DS_KPB];
@@ -1321,10 +1357,12 @@ __global__ void __launch_bounds__(DS_WARPS * 32, ORBB200_DS_MINBLK) describe_ker
     __shared__ __align__(8) uint64_t sBar[DS_WARPS][2];
     const int img = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();
     for (int i = tid; i < 512; i += blockDim.x) {
         const int o = (i & 15) * 32 + (i >> 4);
         sPX[o] = (float)c_patX[i]; sPY[o] = (float)c_patY[i];
     }
+    pdl_wait();
     // ---- phase 0: which keypoint (output order = level-major, octree list order inside a level) ----
     if (tid < DS_KPB) {
         const int gk = blockIdx.x * DS_KPB + tid;
@@ -1334,7 +1372,13 @@ __global__ void __launch_bounds__(DS_WARPS * 32, ORBB200_DS_MINBLK) describe_ker
             if (level < 0 && gk < total + c) { level = l; off = total; }
             total += c;
         }
-        if (blockIdx.x == 0 && tid == 0) counts[img] = total;
+        if (blockIdx.x == 0 && tid == 0) {
+            counts[img] = total;
+            if (M.counts) {                     // small host call: the results also go straight to the pinned mirror
+                M.counts[img] = total;
+                if (img == 0) *M.status = *M.d_status;
+            }
+        }
         sLevel[tid] = level;
         if (level >= 0) {
             const uint32_t v = lvlKp[(size_t)img * g.kpPerImg + g.lv[level].kpOff + (gk - off)];
@@ -1417,6 +1461,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, ORBB200_DS_MINBLK) describe_ker
         kp.octave = level;
         kp.class_id = -1;
         kps[(size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + tid] = kp;
+        if (M.kps) M.kps[(size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + tid] = kp;
     }
     __syncthreads();
 
@@ -1463,6 +1508,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, ORBB200_DS_MINBLK) describe_ker
             val |= (t[0] < t[1]) << k;
         }
         desc[((size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + j) * 32 + lane] = (uint8_t)val;
+        if (M.desc) M.desc[((size_t)img * g.kpPerImg + blockIdx.x * DS_KPB + j) * 32 + lane] = (uint8_t)val;
         __syncwarp();                                                        // every lane is done with this buffer
         if (DS_NBUF == 1 && lane == 0 && j + DS_WARPS < DS_KPB && sLevel[j + DS_WARPS] >= 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1482,7 +1528,7 @@ void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t strid
     c.launches++;
 }
 
-void launch_pyramid(Ctx& c, int n)
+void launch_resizes(Ctx& c, int n, cudaStream_t stream)
 {
     const Geom& g = c.cur->g;
     const ShapeTables& st = *c.cur;
@@ -1491,26 +1537,34 @@ void launch_pyramid(Ctx& c, int n)
         if (d.w <= 0 || d.h <= 0 || st.resizeTileCount[l] == 0) break;
         dim3 grid(st.resizeTileCount[l], n);
         const size_t smem = (size_t)st.resizeSmemPitch[l] * st.resizeSmemRows[l];
-        if (st.resizeNarrow[l])
-            resize_kernel<true><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                                     st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
-                                                                     st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
-        else
-            resize_kernel<false><<<grid, RS_THREADS, smem, c.stream>>>(c.d_pyr, g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab,
-                                                                      st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
-                                                                      st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
+        // level 1 follows the import kernel or an upload (a full dependency either way); levels >= 2 follow a resize_kernel
+        launch_chain(c.pdl && l > 1, st.resizeNarrow[l] ? resize_kernel<true> : resize_kernel<false>, grid, dim3(RS_THREADS), smem, stream, c.d_pyr,
+                     g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab, st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
+                     st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
         c.launches++;
     }
-    border_kernel<<<dim3(g.nlevels * BD_CHUNKS, n), 128, 0, c.stream>>>(c.d_pyr, g.pyrBytes, g);
+}
+
+// afterKernel (here and below): the previous operation on `stream` is a kernel of this chain, so the launch may be programmatic
+void launch_border(Ctx& c, int n, cudaStream_t stream, bool afterKernel)
+{
+    const Geom& g = c.cur->g;
+    launch_chain(c.pdl && afterKernel, border_kernel, dim3(g.nlevels * BD_CHUNKS, n), dim3(128), 0, stream, c.d_pyr, g.pyrBytes, g);
     c.launches++;
 }
 
-void launch_blur(Ctx& c, int n, cudaStream_t stream)
+void launch_pyramid(Ctx& c, int n)
+{
+    launch_resizes(c, n, c.stream);
+    launch_border(c, n, c.stream, c.cur->g.nlevels > 1);
+}
+
+void launch_blur(Ctx& c, int n, cudaStream_t stream, bool afterKernel)
 {
     const Geom& g = c.cur->g;
     if (c.cur->nBlurTiles == 0) return;
     dim3 grid((c.cur->nBlurTiles + BL_WARPS - 1) / BL_WARPS, n);
-    blur_kernel<<<grid, BL_WARPS * 32, 0, stream>>>(c.d_pyr, c.d_blur, g.pyrBytes, g, c.cur->d_blurTiles, c.cur->nBlurTiles);
+    launch_chain(c.pdl && afterKernel, blur_kernel, grid, dim3(BL_WARPS * 32), 0, stream, c.d_pyr, c.d_blur, g.pyrBytes, g, c.cur->d_blurTiles, c.cur->nBlurTiles);
     c.launches++;
 }
 
@@ -1582,52 +1636,93 @@ void push_fast_group(std::vector<int4>& groups, FastStripSmem& need, int x0, int
 }
 
 void launch_fast_strips(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh,
-                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n)
+                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n,
+                        cudaStream_t stream, bool pdl)
 {
     if (nGroups <= 0 || n <= 0) return;
     const size_t smem = need.bytes();
     if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)fast_strip_kernel<FS_PITCH>, SMEM_FAST_STRIP);
     dim3 grid(nGroups, n);
-    fast_strip_kernel<FS_PITCH><<<grid, FS_THREADS, smem, c.stream>>>(d_pyr, pyrBytes, candPerImg, minTh, iniTh, d_groups, d_cand, d_candCount,
-                                                                    need.tileRows, need.scrRows, need.segCap, need.clistCap);
+    launch_chain(pdl, fast_strip_kernel<FS_PITCH>, grid, dim3(FS_THREADS), smem, stream ? stream : c.stream, d_pyr, pyrBytes, candPerImg, minTh, iniTh,
+                 d_groups, d_cand, d_candCount, need.tileRows, need.scrRows, need.segCap, need.clistCap);
     c.launches++;
 }
 
-void launch_fast(Ctx& c, int n)
+// Grid FAST of levels [l0, l1).  The candidate counters must be zero (launch_fast and the few-image chain clear them first).
+void launch_fast_levels(Ctx& c, int n, int l0, int l1, cudaStream_t stream, bool afterKernel)
 {
     const Geom& g = c.cur->g;
     const ShapeTables& st = *c.cur;
+    const int g0 = st.fastGroupBase[l0], g1 = st.fastGroupBase[l1];
+    launch_fast_strips(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_groups + 3 * (size_t)g0, g1 - g0, st.fastStrip, c.d_cand, c.d_candCount, n,
+                       stream, c.pdl && afterKernel);
+}
+
+void launch_clear_counters(Ctx& c, int n)
+{
     cudaMemsetAsync(c.d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
+}
+
+void launch_fast(Ctx& c, int n, bool afterKernel)
+{
+    const Geom& g = c.cur->g;
+    const ShapeTables& st = *c.cur;
     if (!c.fastCells && st.nFastGroups > 0) {
-        launch_fast_strips(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, st.d_groups, st.nFastGroups, st.fastStrip, c.d_cand, c.d_candCount, n);
+        launch_fast_levels(c, n, 0, g.nlevels, c.stream, afterKernel);
         return;
     }
     launch_fast_cells(c, c.d_pyr, g.pyrBytes, g.candPerImg, g.minTh, g.iniTh, 2, st.d_cells, st.nFastCells, st.fastSmem, c.d_cand,
                       c.d_candCount, n);
 }
 
-void launch_octree(Ctx& c, int n)
+void launch_octree_levels(Ctx& c, int n, int l0, int l1, cudaStream_t stream, bool afterKernel)
 {
     const Geom& g = c.cur->g;
+    if (l1 <= l0) return;
     int maxNodes = 2;
     for (int l = 0; l < g.nlevels; l++) maxNodes = std::max(maxNodes, g.lv[l].maxNodes);
-    const size_t smem = octree_smem_bytes(maxNodes);
-    dim3 grid(n, g.nlevels);
+    const size_t smem = octree_smem_bytes(maxNodes, 0);
+    dim3 grid(n, l1 - l0);
+    const bool pdl = c.pdl && afterKernel;
     if (n <= 2) {
-        if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel<OT_THREADS_FEW>, SMEM_OCTREE_FEW);
-        octree_kernel<OT_THREADS_FEW><<<grid, OT_THREADS_FEW, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+        // the SM's whole opt-in shared memory: what the node tables leave holds the candidates (up to 32768 per level)
+        const size_t lim = ensure_max_dynamic_smem(c.device, (const void*)octree_kernel<OT_THREADS_FEW>, SMEM_OCTREE_FEW);
+        const int smemCand = c.octreeSmemCand && lim > smem + 1024 ? (int)std::min<size_t>(32768, ((lim - smem - 512) / 6) & ~(size_t)7) : 0;
+        launch_chain(pdl, octree_kernel<OT_THREADS_FEW>, grid, dim3(OT_THREADS_FEW), octree_smem_bytes(maxNodes, smemCand), stream, g, c.d_cand, c.d_candCount,
+                     c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status, l0, smemCand);
     } else {
         if (smem > 48 * 1024) ensure_max_dynamic_smem(c.device, (const void*)octree_kernel<OT_THREADS>, SMEM_OCTREE);
-        octree_kernel<OT_THREADS><<<grid, OT_THREADS, smem, c.stream>>>(g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount, c.d_status);
+        launch_chain(pdl, octree_kernel<OT_THREADS>, grid, dim3(OT_THREADS), smem, stream, g, c.d_cand, c.d_candCount, c.d_nodeOf, c.d_lvlKp, c.d_lvlCount,
+                     c.d_status, l0, 0);
     }
     c.launches++;
 }
 
-void launch_describe(Ctx& c, int n)
+void launch_octree(Ctx& c, int n)
+{
+    // after fast_strip_kernel on the same stream (the one-CTA-per-cell form is launched plainly, a full dependency is always right)
+    launch_octree_levels(c, n, 0, c.cur->g.nlevels, c.stream, true);
+}
+
+void launch_describe(Ctx& c, int n, bool afterKernel, const HostMirror* mirror)
 {
     const Geom& g = c.cur->g;
-    dim3 grid((g.kpPerImg + DS_KPB - 1) / DS_KPB, n);
-    describe_kernel<<<grid, DS_WARPS * 32, 0, c.stream>>>(g, c.d_pyr, c.d_blur, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.cur->d_dmaps);
+    const HostMirror M = mirror ? *mirror : HostMirror{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (n <= 2)
+        launch_chain(c.pdl && afterKernel, describe_kernel<DS_KPB_FEW>, dim3((g.kpPerImg + DS_KPB_FEW - 1) / DS_KPB_FEW, n), dim3(DS_WARPS * 32), 0, c.stream, g,
+                     c.d_pyr, c.d_blur, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.cur->d_dmaps, M);
+    else
+        launch_chain(c.pdl && afterKernel, describe_kernel<DS_KPB>, dim3((g.kpPerImg + DS_KPB - 1) / DS_KPB, n), dim3(DS_WARPS * 32), 0, c.stream, g,
+                     c.d_pyr, c.d_blur, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.cur->d_dmaps, M);
+    c.launches++;
+}
+
+// n images of rowBytes-pitched rows (a multiple of 16) in pinned host memory -> level 0 of the pyramid pool
+void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n)
+{
+    const Geom& g = c.cur->g;
+    const int rowVec = rowBytes / 16, nVec = rowVec * g.h;
+    import_host_kernel<<<dim3((nVec + 127) / 128, n), 128, 0, c.stream>>>(h_imgs, (unsigned)imgBytes, rowVec, nVec, c.d_pyr, g.pyrBytes, g.lv[0].off, g.lv[0].pitch);
     c.launches++;
 }
 

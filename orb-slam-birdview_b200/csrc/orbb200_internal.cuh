@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/orbb200.h"
@@ -109,7 +110,8 @@ struct FastStripSmem {
 void push_fast_group(std::vector<int4>& groups, FastStripSmem& need, int x0, int y0, int x1, int y1, int level, int cells, int wCell,
                      unsigned levelOff, int pitch, unsigned candOff, int candCap);
 void launch_fast_strips(Ctx& c, const uint8_t* d_pyr, unsigned pyrBytes, unsigned candPerImg, int minTh, int iniTh,
-                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n);
+                        const int4* d_groups, int nGroups, const FastStripSmem& need, uint32_t* d_cand, int32_t* d_candCount, int n,
+                        cudaStream_t stream = nullptr, bool pdl = false);
 // Append one FAST cell (3 x int4) to a host cell table and grow `need`.  [x0,x1) x [y0,y1) is the cell image in level
 // coordinates (3-pixel FAST margin included); candidates are only emitted inside [ex0,ex1) x [ey0,ey1) (ex1 == 0: anywhere).
 void push_fast_cell(std::vector<int4>& cells, FastSmem& need, int x0, int y0, int x1, int y1, int level, unsigned levelOff, int pitch,
@@ -131,14 +133,48 @@ int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t*
 int bird_step_carry(Ctx& c, const BirdStepView& v, int n);
 int bird_step_status(Ctx& c);
 
+// ---- programmatic dependent launch (PDL) ----
+// The extraction is a chain of short dependent kernels; launched with cudaLaunchAttributeProgrammaticStreamSerialization a kernel's
+// CTAs are scheduled while its predecessor drains, run their prologue (table loads, shared-memory set-up) and block in
+// griddepcontrol.wait until the predecessor grid has completed and its writes are visible.  Rule kept by every kernel launched this
+// way: nothing that another kernel of the chain writes or reads is touched before pdl_wait() (host-uploaded tables are fair game).
+// Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 // ---- kernels launchers (extract.cu) ----
+// Level ranges [l0, l1) and the stream are explicit so that, for one or two images, level 0 (no resize needed) can run FAST + octree
+// on a side branch of the graph while the other levels are still being built.
 void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);
+void launch_resizes(Ctx& c, int n, cudaStream_t stream);
+void launch_border(Ctx& c, int n, cudaStream_t stream, bool afterKernel);
 void launch_pyramid(Ctx& c, int n);
-void launch_blur(Ctx& c, int n, cudaStream_t stream);
-void launch_fast(Ctx& c, int n);
+void launch_blur(Ctx& c, int n, cudaStream_t stream, bool afterKernel = false);
+void launch_clear_counters(Ctx& c, int n);       // zeroes the per-level candidate counters: once per extraction, before any FAST launch
+void launch_fast(Ctx& c, int n, bool afterKernel = false);
+void launch_fast_levels(Ctx& c, int n, int l0, int l1, cudaStream_t stream, bool afterKernel);
 void launch_octree(Ctx& c, int n);
-void launch_describe(Ctx& c, int n);
-size_t octree_smem_bytes(int maxNodes);
+void launch_octree_levels(Ctx& c, int n, int l0, int l1, cudaStream_t stream, bool afterKernel);
+// Pinned (device-mapped) result block of a small host call: describe_kernel writes the final records there as well, so that no
+// copy-engine operation follows the graph.  All null: device pools only.
+struct HostMirror { orbb200_kp_t* kps; uint8_t* desc; int32_t* counts; int32_t* status; const int32_t* d_status; };
+// A small host call staged in pinned memory: n images of rowBytes-pitched rows in, results out through `mirror`.
+struct HostStage { const uint8_t* imgs; size_t imgBytes; int rowBytes; HostMirror mirror; };
+void launch_describe(Ctx& c, int n, bool afterKernel = false, const HostMirror* mirror = nullptr);
+void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n);
+size_t octree_smem_bytes(int maxNodes, int smemCand = 0);
 void launch_stereo(Ctx& c, int n_frames, int left0, int right0, int strideImgs, float mb, float mbf, const float* d_invScale, int32_t* d_nKept);
 
 }  // namespace orbb200
