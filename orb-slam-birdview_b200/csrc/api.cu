@@ -115,6 +115,7 @@ bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err)
 bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes)
 {
     if (dev_bytes > c.d_scratch_bytes) {
+        c.allocEpoch++;
         cudaStreamSynchronize(c.stream);
         if (c.d_scratch) cudaFree(c.d_scratch);
         c.d_scratch = nullptr; c.d_scratch_bytes = 0;
@@ -123,6 +124,7 @@ bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes)
         c.d_scratch_bytes = nb;
     }
     if (host_bytes > c.h_scratch_bytes) {
+        c.allocEpoch++;
         cudaStreamSynchronize(c.stream);
         if (c.h_scratch) cudaFreeHost(c.h_scratch);
         c.h_scratch = nullptr; c.h_scratch_bytes = 0;
@@ -420,6 +422,13 @@ static int run_extract(Ctx& c, int n, const HostStage* hs = nullptr)
         ORBB200_CUDA_OK(c, cudaGetLastError());
         return ORBB200_OK;
     }
+    {   // inside somebody else's capture (a whole frame step being recorded): the kernels become nodes of that graph
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c.stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) {
+            enqueue_extract_kernels(c, n, c.forkBlur, hs);
+            return ORBB200_OK;
+        }
+    }
     ShapeTables* st = const_cast<ShapeTables*>(c.cur);
     const int key = hs ? n + 65536 : n;
     auto it = st->graphs.find(key);
@@ -522,6 +531,8 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     c.splitLevel0 = std::getenv("ORBB200_NO_SPLIT") == nullptr;
     c.octreeSmemCand = std::getenv("ORBB200_NO_OCTREE_SMEM") == nullptr;
     c.hostGraph = std::getenv("ORBB200_NO_HOST_GRAPH") == nullptr;
+    c.frameGraph = std::getenv("ORBB200_NO_FRAME_GRAPH") == nullptr;
+    c.subpixGenericWarp = std::getenv("ORBB200_SUBPIX_GENERIC") != nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
     c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
     c.stageUploads = std::getenv("ORBB200_NO_STAGED_UPLOAD") == nullptr;
@@ -605,6 +616,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     void* ptrs[] = {c.d_pyr, c.d_blur, c.d_cand, c.d_nodeOf, c.d_candCount, c.d_lvlKp, c.d_lvlCount, c.d_kps, c.d_desc, c.d_counts, c.d_status, c.d_scratch, c.d_step,
                     c.d_uRight, c.d_depth, c.d_sad, c.d_nKept, c.d_invScale, c.d_rowStart, c.d_rowItems};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& fg : c.frameGraphs) if (fg.exec) cudaGraphExecDestroy(fg.exec);
     for (auto& kv : c.shapes) { cudaFree(kv.second.d_xtab); cudaFree(kv.second.d_ytab); cudaFree(kv.second.d_cells); cudaFree(kv.second.d_groups); cudaFree(kv.second.d_blurTiles); cudaFree(kv.second.d_resizeTiles); cudaFree(kv.second.d_dmaps); cudaFree(kv.second.d_rmaps);
                                for (auto& gk : kv.second.graphs) cudaGraphExecDestroy(gk.second.exec); }
     if (c.h_scratch) cudaFreeHost(c.h_scratch);
@@ -1191,6 +1203,7 @@ int orbb200_map_upload(orbb200_ctx* ctx, orbb200_map** map, int n, const float* 
     if (!map || n < 0 || (n > 0 && (!pos || !normal || !max_distance || !min_distance || !desc))) { c.err = "map_upload: bad argument"; return ORBB200_ERR_ARG; }
     orbb200_map* m = new orbb200_map();
     m->ctx = &c; m->n = n;
+    c.allocEpoch++;                                // a new map may reuse the address of a freed one
     const size_t k = (size_t)std::max(n, 1);
     bool ok = cudaMalloc((void**)&m->d_pos, k * 12) == cudaSuccess && cudaMalloc((void**)&m->d_normal, k * 12) == cudaSuccess &&
               cudaMalloc((void**)&m->d_maxDist, k * 4) == cudaSuccess && cudaMalloc((void**)&m->d_minDist, k * 4) == cudaSuccess &&
@@ -1730,6 +1743,7 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     for (auto& q : c.framePlans)
         if (memcmp(&q, &key, offsetof(FramePlan, dF)) == 0) { plan = &q; break; }
     if (!plan) {
+        c.allocEpoch++;
         if (c.framePlans.size() >= 16) {
             cudaStreamSynchronize(c.stream);
             for (auto& q : c.framePlans) cudaFree(q.block);
@@ -1838,6 +1852,7 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
     const size_t need = align_up(imgBytes * ni, 256) + align_up(birdBytes * n, 256) + align_up(sizeof(orbb200_camera_pose) * n, 256) + align_up(4 * Qm, 256) * 2 +
                         align_up(4 * Qb, 256) + align_up(4 * (size_t)n, 256) * 2 + 4096;
     if (need > c.d_fstep_bytes) {
+        c.allocEpoch++;
         cudaStreamSynchronize(c.stream);
         if (c.d_fstep) cudaFree(c.d_fstep);
         c.d_fstep = nullptr; c.d_fstep_bytes = 0;
@@ -1865,6 +1880,39 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
             staged = pageable && ensure_scratch(c, 0, STAGE_LIMIT);
         }
     }
+    // The staged step as one graph (see Ctx::FrameGraph): state 0 -> run eagerly, 1 -> capture + launch, 2 -> replay.
+    Ctx::FrameGraph* fg = nullptr;
+    if (staged && c.useGraphs && c.frameGraph && !c.timing) {
+        if (c.frameGraphEpoch != c.allocEpoch) {
+            ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+            for (auto& q : c.frameGraphs) if (q.exec) cudaGraphExecDestroy(q.exec);
+            c.frameGraphs.clear();
+            c.frameGraphEpoch = c.allocEpoch;
+        }
+        std::vector<uint8_t> key(sizeof(*p) + 16 + 2 * sizeof(void*));
+        memcpy(key.data(), p, sizeof(*p));
+        const uint32_t want = (out->kps ? 1u : 0u) | (out->desc ? 2u : 0u) | (out->counts ? 4u : 0u) | (out->u_right ? 8u : 0u) | (out->depth ? 16u : 0u) |
+                              (out->map_best_idx ? 32u : 0u) | (out->map_best_dist ? 64u : 0u) | (out->map_nmatches ? 128u : 0u) | (out->bird_kps ? 256u : 0u) |
+                              (out->bird_desc ? 512u : 0u) | (out->bird_counts ? 1024u : 0u) | (out->bird_matches12 ? 2048u : 0u) | (out->bird_nmatches ? 4096u : 0u);
+        const int32_t caps[3] = {(int32_t)want, out->cap, out->bird_cap};
+        memcpy(key.data() + sizeof(*p), caps, 12);
+        const void* ptrs[2] = {c.h_scratch, c.d_fstep};
+        memcpy(key.data() + sizeof(*p) + 16, ptrs, sizeof(ptrs));
+        for (auto& q : c.frameGraphs)
+            if (q.key == key) { fg = &q; break; }
+        if (!fg && c.frameGraphs.size() < 8) { c.frameGraphs.push_back(Ctx::FrameGraph{key, 0, nullptr, 0}); fg = &c.frameGraphs.back(); }
+    }
+    const bool replay = fg && fg->state == 2, capture = fg && fg->state == 1;
+    const unsigned long long epoch0 = c.allocEpoch;
+    const long long launches0 = c.launches;
+    struct CaptureGuard {      // an error return between Begin and EndCapture must not leave the stream capturing
+        cudaStream_t s; bool on;
+        ~CaptureGuard() { if (on) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); } }
+    } guard{c.stream, false};
+    if (capture) {
+        ORBB200_CUDA_OK(c, cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed));
+        guard.on = true;
+    }
     size_t hIn = STAGE_H2D_OFF, hOut = STAGE_D2H_OFF;
     auto h2d = [&](void* dDst, const void* hSrc, size_t bytes) -> cudaError_t {
         if (staged) {
@@ -1873,14 +1921,14 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
             memcpy(hs, hSrc, bytes);
             hSrc = hs;
         }
-        return cudaMemcpyAsync(dDst, hSrc, bytes, cudaMemcpyHostToDevice, c.stream);
+        return replay ? cudaSuccess : cudaMemcpyAsync(dDst, hSrc, bytes, cudaMemcpyHostToDevice, c.stream);
     };
     auto d2h = [&](void* hDst, size_t dpitch, const void* dSrc, size_t spitch, size_t width, size_t rows) -> cudaError_t {
         if (staged) {
             uint8_t* hs = c.h_scratch + hOut;
             hOut += align_up(width * rows, 64);
             c.hostCopies.push_back(Ctx::HostCopy{hDst, dpitch, hs, width, rows});
-            return cudaMemcpy2DAsync(hs, width, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
+            return replay ? cudaSuccess : cudaMemcpy2DAsync(hs, width, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
         }
         return cudaMemcpy2DAsync(hDst, dpitch, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
     };
@@ -1899,8 +1947,14 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         dout.map_best_idx = A.take<int32_t>(Qm); dout.map_best_dist = A.take<int32_t>(Qm); dout.map_nmatches = A.take<int32_t>(n);
     }
     if (hasBird) { dout.bird_matches12 = A.take<int32_t>(Qb); dout.bird_nmatches = A.take<int32_t>(n); }
-    rc = orbb200_frame_step_device(ctx, p, &din, &dout);
-    if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
+    if (replay) {                                   // host-side state the enqueueing path leaves behind
+        const ShapeTables* st = get_shape(c, p->w, p->h);
+        if (!st) { c.hostCopies.clear(); return ORBB200_ERR_UNSUPPORTED; }
+        c.cur = st; c.curN = ni; c.stereoValid = p->mb > 0.f;
+    } else {
+        rc = orbb200_frame_step_device(ctx, p, &din, &dout);
+        if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
+    }
     const int kpi = c.cur->g.kpPerImg;
     if (out->kps || out->desc || out->u_right || out->depth) {
         if (out->cap <= 0) { c.err = "frame_step_host: cap"; c.hostCopies.clear(); return ORBB200_ERR_ARG; }
@@ -1930,6 +1984,30 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         }
         if (out->bird_counts) ORBB200_CUDA_OK(c, d2h(out->bird_counts, 4 * (size_t)n, bCnt, 4 * (size_t)n, 4 * (size_t)n, 1));
         if (out->bird_nmatches) ORBB200_CUDA_OK(c, d2h(out->bird_nmatches, 4 * (size_t)n, dout.bird_nmatches, 4 * (size_t)n, 4 * (size_t)n, 1));
+    }
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        guard.on = false;
+        cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+        if (e == cudaSuccess && c.allocEpoch == epoch0) e = cudaGraphInstantiate(&exec, graph, 0);
+        else if (e == cudaSuccess) e = cudaErrorUnknown;       // something was (re)allocated while recording: the recording is not trusted
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess || !exec) {                       // nothing has run yet: do this call eagerly and never try this key again
+            cudaGetLastError();
+            fg->state = -1;
+            c.launches = launches0;
+            c.hostCopies.clear();
+            return orbb200_frame_step_host(ctx, p, in, out);
+        }
+        fg->exec = exec; fg->launches = c.launches - launches0; fg->state = 2;
+        ORBB200_CUDA_OK(c, cudaGraphLaunch(exec, c.stream));
+    } else if (replay) {
+        ORBB200_CUDA_OK(c, cudaGraphLaunch(fg->exec, c.stream));
+        c.launches += fg->launches;
+    } else if (fg && fg->state == 0) {
+        // plans, pools and kernel attributes exist now; record the next call -- unless this one had to allocate (then once more)
+        if (c.allocEpoch == epoch0) fg->state = 1;
     }
     return ORBB200_OK;
 }

@@ -292,13 +292,16 @@ __device__ void rb_heap_select(RB v, int first, int middle, int last)
 #ifndef ORBB200_SEL_THREADS
 #define ORBB200_SEL_THREADS 256
 #endif
-constexpr int SEL_THREADS = ORBB200_SEL_THREADS;
+constexpr int SEL_THREADS = ORBB200_SEL_THREADS;       // batches: many (image, level) CTAs in flight
+constexpr int SEL_THREADS_FEW = 1024;                  // one or two images: the level-0 CTA is the critical path of the whole frame
 
-struct RBPar { float* r; uint32_t* p; uint16_t* A; uint16_t* B; int* sc; };   // sc: [SEL_THREADS / 32 + 4] ints of scratch
+struct RBPar { float* r; uint32_t* p; uint16_t* A; uint16_t* B; int* sc; };   // sc: [NT / 32 + 4] ints of scratch
 
 // exclusive block scan of one int per thread (all threads call); total returned through sc
+template <int NT>
 __device__ __forceinline__ int rb_block_scan(int v, int* sc, int& total)
 {
+    constexpr int SEL_THREADS = NT;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int x = v;
 #pragma unroll
@@ -326,8 +329,10 @@ __device__ __forceinline__ int rb_block_scan(int v, int* sc, int& total)
 
 // ge == false: std::__unguarded_partition(lo, hi, pivot value pv) with comp = greater  -> cut
 // ge == true : std::partition(lo, hi, response >= pv)                                   -> first element of the false group
+template <int NT>
 __device__ int rb_partition_block(RBPar v, int lo, int hi, float pv, bool ge)
 {
+    constexpr int SEL_THREADS = NT;
     const int tid = threadIdx.x;
     const int len = hi - lo;
     if (len <= 0) return lo;
@@ -341,7 +346,7 @@ __device__ int rb_partition_block(RBPar v, int lo, int hi, float pv, bool ge)
         cnt += (int)isL + ((int)isR << 16);
     }
     int total;
-    const int base = rb_block_scan(cnt, v.sc, total);
+    const int base = rb_block_scan<NT>(cnt, v.sc, total);
     const int nL = total & 0xffff, nR = total >> 16;
     int kL = base & 0xffff, kR = base >> 16;
     for (int i = b; i < e; i++) {
@@ -376,6 +381,7 @@ __device__ int rb_partition_block(RBPar v, int lo, int hi, float pv, bool ge)
 }
 
 // KeyPointsFilter::retainBest, all threads of the CTA call; returns the new count
+template <int NT>
 __device__ int rb_retain_best_block(RBPar v, int n, int n_points)
 {
     if (!(n_points >= 0 && n > n_points)) return n;
@@ -397,12 +403,12 @@ __device__ int rb_retain_best_block(RBPar v, int n, int n_points)
         const int mid = first + (last - first) / 2;
         if (tid == 0) rb_move_median_to_first(s, first, first + 1, mid, last - 1);
         __syncthreads();
-        const int cut = rb_partition_block(v, first + 1, last, v.r[first], false);
+        const int cut = rb_partition_block<NT>(v, first + 1, last, v.r[first], false);
         if (cut <= nth) first = cut; else last = cut;
     }
     if (!done && tid == 0) rb_insertion_sort(s, first, last);
     __syncthreads();
-    return rb_partition_block(v, n_points, n, v.r[n_points - 1], true);
+    return rb_partition_block<NT>(v, n_points, n, v.r[n_points - 1], true);
 }
 
 // HarrisResponses (orb.cpp), blockSize 7, k 0.04
@@ -427,7 +433,8 @@ __device__ float bird_harris(const uint8_t* img, int pitch, int x0, int y0)
 
 // Per (image, level): FAST corners -> mask filter -> row-major order (cv::FAST's) -> retainBest(2 * quota) on the FAST
 // score -> Harris responses -> retainBest(quota) (orb.cpp computeKeyPoints).  Writes the level's survivors in order.
-__global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ mpyr,
+template <int NT>
+__global__ void __launch_bounds__(NT) bird_select_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ mpyr,
                                                                   unsigned maskPlaneBytes,      // 0: one mask pyramid for every image
                                                                   const uint32_t* __restrict__ cand, const int32_t* __restrict__ candCount,
                                                                   float4* __restrict__ lvlKp, int32_t* __restrict__ lvlCount,
@@ -438,6 +445,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
     // The kernel is a chain of block-wide steps (latency-bound), so residency matters: it is launched in tiers of growing
     // shared memory -- 24 KB (levels of <= 2048 corners, 9 CTAs per SM), 72 KB (<= 5120, three per SM; a 400x400 level 0 holds
     // 3-5 k), 196 KB (the NMS bound) -- and a CTA returns at once when its level belongs to another tier.
+    constexpr int SEL_THREADS = NT;
     extern __shared__ uint32_t selSmem[];
     uint32_t* key = selSmem;                                              // [capKey]
     float* resp = reinterpret_cast<float*>(selSmem + capKey);             // [capN]
@@ -491,11 +499,11 @@ __global__ void __launch_bounds__(SEL_THREADS) bird_select_kernel(BirdGeom g, co
     for (int i = tid; i < n; i += SEL_THREADS) resp[i] = (float)(key[i] & 0xffu);
     __syncthreads();
     RBPar v{resp, key, stopA, stopB, sScratch};
-    n = rb_retain_best_block(v, n, 2 * L.quota);
+    n = rb_retain_best_block<NT>(v, n, 2 * L.quota);
     const uint8_t* I = pyr + (size_t)img * g.planeBytes + L.off;
     for (int i = tid; i < n; i += SEL_THREADS) resp[i] = bird_harris(I, L.pitch, (int)((key[i] >> 8) & 0xfff), (int)(key[i] >> 20));
     __syncthreads();
-    n = rb_retain_best_block(v, n, L.quota);
+    n = rb_retain_best_block<NT>(v, n, L.quota);
     if (n > L.kpCap) {
         if (tid == 0) atomicExch(status, 4);
         n = L.kpCap;
@@ -691,6 +699,101 @@ __global__ void __launch_bounds__(SP_WARPS * 32) bird_subpix_kernel(const uint8_
         if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) break;
     } while (++iter < maxIters && err > eps);
     if (fabsf(__fsub_rn(cIx, cTx)) > winW || fabsf(__fsub_rn(cIy, cTy)) > winH) { cIx = cTx; cIy = cTy; }
+    if (lane == 0) { P[0] = cIx; P[1] = cIy; }
+}
+
+// The same for the reference's 5x5 half-window (Frame.cc:337), every trip count a constant: the six rounds of window samples and the
+// four rounds of gradient products are unrolled, so a round's loads and conversion chains overlap the others' instead of queueing
+// behind them.  One or two images leave most warp slots empty, the kernel's duration is (iterations of the slowest corner) x
+// (latency of one iteration), and that latency is what this form cuts; a window that touches the image border takes the generic
+// sampler, with the same arithmetic.
+__global__ void __launch_bounds__(SP_WARPS * 32) bird_subpix_warp5_kernel(const uint8_t* __restrict__ imgs, size_t imgStrideBytes, int pitch, int cols,
+                                                                          int rows, float* __restrict__ pts, size_t ptsPerImg,
+                                                                          const int32_t* __restrict__ counts, int nFixed, const double* __restrict__ winMaskD,
+                                                                          int maxIters, double eps)
+{
+    constexpr int WIN = 5, WW = 2 * WIN + 1, BW = WW + 2, NWIN = WW * WW, NSAMP = BW * BW;
+    __shared__ float sBuf[SP_WARPS][NSAMP + 7];
+    __shared__ double sG[SP_WARPS][5][NWIN];            // gxx, gxy, gyy, (gxx*px + gxy*py), (gxy*px + gyy*py)
+    __shared__ double sMask[NWIN];
+    const int img = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < NWIN) sMask[threadIdx.x] = winMaskD[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * SP_WARPS + wid;
+    const int n = counts ? counts[img] : nFixed;
+    if (i >= n) return;
+    const uint8_t* src = imgs + (size_t)img * imgStrideBytes;
+    float* P = pts + (size_t)img * ptsPerImg * 2 + 2 * (size_t)i;
+    float* buf = sBuf[wid];
+    const float cTx = P[0], cTy = P[1];
+    float cIx = cTx, cIy = cTy;
+    int iter = 0;
+    double err = 0;
+    do {
+        {   // getRectSubPix_8u32f, window (BW, BW) around (cIx, cIy)
+            const float centerx = __fsub_rn(cIx, (float)(BW - 1) * 0.5f), centery = __fsub_rn(cIy, (float)(BW - 1) * 0.5f);
+            const int ipx = (int)floorf(centerx), ipy = (int)floorf(centery);
+            if (0 <= ipx && ipx + BW < cols && 0 <= ipy && ipy + BW < rows) {
+                float a = __fsub_rn(centerx, (float)ipx);
+                const float b = __fsub_rn(centery, (float)ipy);
+                a = fmaxf(a, 0.0001f);
+                const float b1 = __fsub_rn(1.f, b), b2 = b;
+                const float a12 = __fmul_rn(a, b1), a22 = __fmul_rn(a, b);
+                const float oma = __fsub_rn(1.f, a);
+                const double s = __ddiv_rn(__dsub_rn(1.0, (double)a), (double)a);
+                const uint8_t* p0 = src + (ptrdiff_t)ipy * pitch + ipx;
+#pragma unroll
+                for (int r = 0; r < (NSAMP + 31) / 32; r++) {
+                    const int e = min(r * 32 + lane, NSAMP - 1);               // (surplus lanes of the last round redo the last sample)
+                    const int ii = e / BW, j = e - ii * BW;
+                    const uint8_t* p = p0 + ii * pitch + j;
+                    const float q0 = (float)p[0], q1 = (float)p[1], r0 = (float)p[pitch], r1 = (float)p[pitch + 1];
+                    const float t = __fadd_rn(__fmul_rn(a12, q1), __fmul_rn(a22, r1));
+                    const float tp = __fadd_rn(__fmul_rn(a12, q0), __fmul_rn(a22, r0));
+                    const float prev = j == 0 ? __fmul_rn(oma, __fadd_rn(__fmul_rn(b1, q0), __fmul_rn(b2, r0))) : (float)__dmul_rn((double)tp, s);
+                    buf[e] = __fadd_rn(prev, t);
+                }
+            } else {
+                bird_get_rect_sub_pix_warp(src, pitch, cols, rows, buf, BW, BW, cIx, cIy, lane);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < (NWIN + 31) / 32; r++) {
+            const int k = min(r * 32 + lane, NWIN - 1);
+            const int ii = k / WW, j = k - ii * WW;
+            const float* subpix = buf + (ii + 1) * BW + 1;
+            const double py = (double)(ii - WIN), px = (double)(j - WIN);
+            const double m = sMask[k];
+            const double tgx = (double)__fsub_rn(subpix[j + 1], subpix[j - 1]);
+            const double tgy = (double)__fsub_rn(subpix[j + BW], subpix[j - BW]);
+            const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m);
+            const double gxy = __dmul_rn(__dmul_rn(tgx, tgy), m);
+            const double gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+            sG[wid][0][k] = gxx; sG[wid][1][k] = gxy; sG[wid][2][k] = gyy;
+            sG[wid][3][k] = __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py));
+            sG[wid][4][k] = __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py));
+        }
+        __syncwarp();
+        double acc = 0;
+        if (lane < 5) {
+            const double* g = sG[wid][lane];
+#pragma unroll
+            for (int k = 0; k < NWIN; k++) acc = __dadd_rn(acc, g[k]);
+        }
+        const double a = __shfl_sync(0xffffffffu, acc, 0), b = __shfl_sync(0xffffffffu, acc, 1), c = __shfl_sync(0xffffffffu, acc, 2);
+        const double bb1 = __shfl_sync(0xffffffffu, acc, 3), bb2 = __shfl_sync(0xffffffffu, acc, 4);
+        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = __ddiv_rn(1.0, det);
+        const float nx = (float)__dsub_rn(__dadd_rn((double)cIx, __dmul_rn(__dmul_rn(c, scale), bb1)), __dmul_rn(__dmul_rn(b, scale), bb2));
+        const float ny = (float)__dadd_rn(__dsub_rn((double)cIy, __dmul_rn(__dmul_rn(b, scale), bb1)), __dmul_rn(__dmul_rn(a, scale), bb2));
+        const float dx = __fsub_rn(nx, cIx), dy = __fsub_rn(ny, cIy);
+        err = (double)__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        cIx = nx; cIy = ny;
+        if (cIx < 0 || cIx >= cols || cIy < 0 || cIy >= rows) break;
+    } while (++iter < maxIters && err > eps);
+    if (fabsf(__fsub_rn(cIx, cTx)) > WIN || fabsf(__fsub_rn(cIy, cTy)) > WIN) { cIx = cTx; cIy = cTy; }
     if (lane == 0) { P[0] = cIx; P[1] = cIy; }
 }
 
@@ -1337,6 +1440,7 @@ BirdPlan* get_plan(Ctx& c, int w, int h, int nfeatures, int batch)
     auto it = S.plans.find(key);
     BirdPlan* p = it == S.plans.end() ? nullptr : it->second;
     if (p && p->batch >= batch) return p;
+    c.allocEpoch++;
     if (p) { cudaStreamSynchronize(c.stream); free_plan(p); S.plans.erase(key); }
     p = new BirdPlan();
     BirdGeom& g = p->g;
@@ -1461,11 +1565,23 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
                       p->d_candCount, n);
     const size_t smem = (size_t)BV_SORT_CAP * 12;      // keys + responses + two u16 stopper lists
-    if (smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel, SMEM_BIRD_SELECT)) {
+    if (smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel<SEL_THREADS>, SMEM_BIRD_SELECT) ||
+        smem > ensure_max_dynamic_smem(c.device, (const void*)bird_select_kernel<SEL_THREADS_FEW>, SMEM_BIRD_SELECT_FEW)) {
         c.err = "bird_select_kernel: shared memory";
         return ORBB200_ERR_CUDA;
     }
     const uint8_t* mask = maskMode == 1 ? p->d_mask : maskMode == 2 ? p->d_maskShared : nullptr;
+    if (n <= 2) {
+        // one or two images: every level at once, one 1024-thread CTA each with the largest carve (an SM per level is there for the
+        // taking; the tiers below would run one after the other, and level 0's sort and partitions are 4x shorter per thread)
+        bird_select_kernel<SEL_THREADS_FEW><<<dim3(n, BV_LEVELS), SEL_THREADS_FEW, smem, c.stream>>>(
+            g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount, c.d_status, BV_SORT_CAP, BV_SORT_CAP, 0, 0);
+        c.launches++;
+        bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
+        c.launches++;
+        ORBB200_CUDA_OK(c, cudaGetLastError());
+        return ORBB200_OK;
+    }
     struct Tier { int key, n; };
     const Tier tiers[3] = {{2048, 2048}, {8192, 5120}, {BV_SORT_CAP, BV_SORT_CAP}};
     for (int t = 0; t < 3; t++) {
@@ -1473,7 +1589,7 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
         int nl = BV_LEVELS;
         if (t > 0) { nl = 0; while (nl < BV_LEVELS && g.lv[nl].candCap > tiers[t - 1].n) nl++; }
         if (nl == 0) break;
-        bird_select_kernel<<<dim3(n, nl), SEL_THREADS, (size_t)tiers[t].key * 4 + (size_t)tiers[t].n * 8, c.stream>>>(
+        bird_select_kernel<SEL_THREADS><<<dim3(n, nl), SEL_THREADS, (size_t)tiers[t].key * 4 + (size_t)tiers[t].n * 8, c.stream>>>(
             g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount, c.d_status,
             tiers[t].key, tiers[t].n, t ? tiers[t - 1].key : 0, t ? tiers[t - 1].n : 0);
         if (t < 2) c.launches++;
@@ -1571,6 +1687,9 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
             p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, g.kpPerImg, n, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps, S.d_work,
             nullptr, nullptr);
     }
+    else if (winW == S5_WIN && winH == S5_WIN && !c.subpixGenericWarp)
+        bird_subpix_warp5_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
+            p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, S.d_winMaskD, maxIters, eps);
     else
         bird_subpix_kernel<<<dim3((g.kpPerImg + SP_WARPS - 1) / SP_WARPS, n), SP_WARPS * 32, 0, c.stream>>>(
             p->d_pyr + L0.off, g.planeBytes, L0.pitch, g.w, g.h, p->d_pts, (size_t)g.kpPerImg, d_counts, nFixed, S.d_winMask, winW, winH, maxIters, eps);
@@ -1640,6 +1759,7 @@ int download(Ctx& c, BirdPlan* p, int n, const orbb200_kp_t* d_kps, const int32_
 static int ensure_step_buffers(Ctx& c, BirdPlan* p)
 {
     if (p->d_qx) return ORBB200_OK;
+    c.allocEpoch++;
     const size_t Q = ((size_t)p->batch + 1) * p->g.kpPerImg;
     const size_t K = (size_t)p->g.kpPerImg;
     const bool ok = cudaMalloc((void**)&p->d_qx, Q * 4) == cudaSuccess && cudaMalloc((void**)&p->d_qy, Q * 4) == cudaSuccess &&
@@ -1657,6 +1777,7 @@ int bird_set_mask(Ctx& c, int w, int h, int nfeatures, int batch, const uint8_t*
     BirdPlan* p = get_plan(c, w, h, nfeatures, std::max(batch, 1));
     if (!p) return ORBB200_ERR_CUDA;
     const BirdGeom& g = p->g;
+    c.allocEpoch++;                             // captured frame steps hold the mask pointer (or its absence)
     if (!mask) {
         if (p->d_maskShared) { cudaStreamSynchronize(c.stream); cudaFree(p->d_maskShared); p->d_maskShared = nullptr; }
         return ORBB200_OK;

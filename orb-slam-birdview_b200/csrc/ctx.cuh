@@ -41,7 +41,7 @@ struct WinJob;
 // "what I asked for" lets a second context on the same GPU lower the first one's limit.  Each kernel that may need
 // more than 48 KB is instead raised ONCE per device to the device's opt-in maximum; the record is process-wide.
 // Returns that maximum (bytes) or 0 after a CUDA error.  slot: one small integer per kernel instantiation.
-enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_FAST_STRIP, SMEM_OCTREE, SMEM_OCTREE_FEW, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
+enum SmemSlot { SMEM_FAST = 0, SMEM_FAST_SMALL, SMEM_FAST_STRIP, SMEM_OCTREE, SMEM_OCTREE_FEW, SMEM_WINDOW_MATCH, SMEM_BIRD_SELECT, SMEM_BIRD_SELECT_FEW, SMEM_BIRD_SUBPIX, SMEM_BIRD_SUBPIX3, SMEM_BIRD_SUBPIX2, SMEM_SLOTS };
 inline size_t ensure_max_dynamic_smem(int device, const void* kernel, int slot)
 {
     static std::mutex mu;
@@ -157,6 +157,15 @@ struct Ctx {
 
     std::vector<StepPlan> plans;
     std::vector<FramePlan> framePlans;
+    // Small host frame steps (the one-frame-per-call pattern) replayed as ONE graph: uploads from the pinned staging block, both
+    // front-ends, matching, downloads into the staging block.  A key's first call runs eagerly (it creates plans and pools), the
+    // second is captured, later ones are a single cudaGraphLaunch.  allocEpoch counts every reallocation of something a captured
+    // node may point to (staging blocks, birdview plans and masks, local maps, frame plans): a change drops all captured steps.
+    struct FrameGraph { std::vector<uint8_t> key; int state; cudaGraphExec_t exec; long long launches; };
+    std::vector<FrameGraph> frameGraphs;
+    unsigned long long allocEpoch = 0, frameGraphEpoch = 0;
+    bool subpixGenericWarp = false;          // ORBB200_SUBPIX_GENERIC=1: the generic warp-per-corner cornerSubPix also for the 5x5 window (A/B)
+    bool frameGraph = true;                  // ORBB200_NO_FRAME_GRAPH=1 turns the replay off
     uint8_t* d_fstep = nullptr;              // device staging of the host frame step
     size_t d_fstep_bytes = 0;
 

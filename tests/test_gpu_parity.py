@@ -906,6 +906,44 @@ def test_frame_step_vs_oracle(pkg):
     assert out["bird_nmatches"][0] == 0
 
 
+def test_frame_step_one_frame_per_call_replayed_graph(pkg):
+    """The drop-in pattern: ONE frame per orbb200_frame_step_host call from pageable memory, chained.  The first calls of a
+    parameter set run eagerly, the next one is recorded into a CUDA graph (uploads, both front-ends, matching, downloads) and
+    later ones replay it: every call, whichever way it ran, must equal the oracle -- keypoints, descriptors, mvuRight / mvDepth
+    bits, SearchLocalPoints and BirdviewMatch results."""
+    w, h, bw, bh, nfeat, bnf, nmap = 620, 188, 200, 200, 1000, 600, 1500
+    seq = synth.northstar_sequence(7, 23, w=w, h=h, bird=(bw, bh), vehicle=(40, 60))
+    orc = oracle.Extractor(nfeat, 1.2, 8, 20, 7)
+    mp = synth.northstar_map(seq, lambda im: orc(im), nmap, 3)
+    ctx = pkg.Context(nfeat, 1.2, 8, 20, 7, w, h, 2)
+    M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+    step = pkg.FrameStep(ctx, w, h, M, mb=0.537, mbf=386.1448, th=1.0, nnratio=0.8, bird_size=(bw, bh), bird_nfeatures=bnf,
+                         bird_mask=seq["bird_mask"], bird_window=15, bird_nnratio=0.99)
+    poses = [pkg.CameraPose.make(**p) for p in seq["poses"]]
+    prev = None
+    launches = []
+    for i in range(7):
+        before = ctx.launches
+        out = step(seq["imgs"][2 * i:2 * i + 2], seq["bird_imgs"][i:i + 1], poses[i:i + 1], chain=i > 0)
+        launches.append(ctx.launches - before)
+        (r,), prev = _oracle_frame_step(seq, mp, [i], nfeat, bnf, w, h, bw, bh, 1.0, 0.8, 15, 0.99, prev)
+        nl, nr = out["counts"][0], out["counts"][1]
+        assert out["kps"][0][:nl].tobytes() == r["kl"].tobytes() and out["kps"][1][:nr].tobytes() == r["kr"].tobytes(), i
+        assert np.array_equal(out["desc"][0][:nl], r["dl"]) and np.array_equal(out["desc"][1][:nr], r["dr"]), i
+        assert np.array_equal(out["u_right"][0][:nl].view(np.uint32), r["ur"].view(np.uint32)), i
+        assert np.array_equal(out["depth"][0][:nl].view(np.uint32), r["dep"].view(np.uint32)), i
+        assert out["map_nmatches"][0] == r["nm"] and np.array_equal(out["map_best_idx"][0], r["bi"]), i
+        assert np.array_equal(out["map_best_dist"][0][r["bi"] >= 0], r["bd"][r["bi"] >= 0]), i
+        nb = out["bird_counts"][0]
+        assert out["bird_kps"][0][:nb].tobytes() == r["bk"].tobytes() and np.array_equal(out["bird_desc"][0][:nb], r["bdsc"]), i
+        if r["m12"] is None:
+            assert out["bird_nmatches"][0] == 0
+        else:
+            assert out["bird_nmatches"][0] == r["nbm"] and np.array_equal(out["bird_matches12"][0][:len(r["m12"])], r["m12"]), i
+    # eager, recorded and replayed calls enqueue the same kernels
+    assert len(set(launches[1:])) == 1 and launches[1] > 30, launches
+
+
 def test_three_host_threads_three_contexts(pkg):
     """The reference calls the front-end from three threads at once (Tracking: extraction + projection searches; LocalMapping:
     SearchForTriangulation, src/LocalMapping.cc:278; LoopClosing: SearchByBoW, src/LoopClosing.cc:265), one ORBextractor /

@@ -31,3 +31,40 @@ with tempfile.TemporaryDirectory() as d:
             r = subprocess.run([drv, raw, str(w), str(h), str(nf), "20", "7", os.path.join(d, "out.bin")], capture_output=True, text=True, env=env)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("TIMING ")]
             print(json.dumps({"shape": f"{w}x{h}", "knobs": v, **(json.loads(line[0][7:]) if line else {"error": r.stderr[-300:]})}), flush=True)
+
+# ---- the whole north-star frame, one frame per call (what bench.py reports as configs.per_frame.north_star_frame_ms) ----
+if os.environ.get("ORBB200_PROBE_FRAME", "1") != "0":
+    import time
+    probe = r'''
+import os, sys, time, json
+import numpy as np
+sys.path.insert(0, %r)
+import orb_slam_birdview_b200 as pkg
+from importlib import import_module
+synth = import_module("orb_slam_birdview_b200.synth")
+W, H, BW, BH = 1241, 376, 400, 400
+seq = synth.northstar_sequence(24, 5, w=W, h=H, bird=(BW, BH))
+ex = pkg.ORBextractor(2000, 1.2, 8, 20, 7, max_size=(W, H))
+mp = synth.northstar_map(seq, lambda im: ex(im), 3000, 12)
+ctx = pkg.Context(2000, 1.2, 8, 20, 7, W, H, 2)
+M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+step = pkg.FrameStep(ctx, W, H, M, mb=0.537, mbf=386.1448, th=1.0, nnratio=0.8, bird_size=(BW, BH), bird_nfeatures=2000,
+                     bird_mask=seq["bird_mask"], bird_window=15, bird_nnratio=0.99)
+poses = [pkg.CameraPose.make(**p) for p in seq["poses"]]
+n = len(poses)
+for i in range(6):
+    step(seq["imgs"][2 * i:2 * i + 2], seq["bird_imgs"][i:i + 1], poses[i:i + 1], chain=i > 0)
+t0 = time.perf_counter()
+for i in range(6, n):
+    step(seq["imgs"][2 * i:2 * i + 2], seq["bird_imgs"][i:i + 1], poses[i:i + 1], chain=True)
+ms = (time.perf_counter() - t0) / (n - 6) * 1e3
+print(json.dumps({"north_star_frame_ms": round(ms, 4)}))
+''' % ROOT
+    for v in variants:
+        env = dict(os.environ)
+        for kv in filter(None, v.split(",")):
+            k, _, val = kv.partition("=")
+            env[k] = val
+        r = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=env)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        print(json.dumps({"shape": "north-star frame", "knobs": v, **(json.loads(line[-1]) if line else {"error": r.stderr[-400:]})}), flush=True)
