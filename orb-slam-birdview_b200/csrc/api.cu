@@ -1709,7 +1709,9 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     if (hasBird) {
         cudaStream_t main = c.stream;
         if (fork) {
-            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, main));
+            // (the host variant records the event itself, right behind the birdview upload: the birdview front-end -- the longer
+            // of the two -- then starts while the front images are still on their way)
+            if (!c.birdForkRecorded) ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, main));
             ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.streamBird, c.evBirdFork, 0));
             c.stream = c.streamBird;
         }
@@ -1933,13 +1935,15 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         return cudaMemcpy2DAsync(hDst, dpitch, dSrc, spitch, width, rows, cudaMemcpyDeviceToHost, c.stream);
     };
     uint8_t* dImgs = A.take<uint8_t>(imgBytes * ni);
-    ORBB200_CUDA_OK(c, h2d(dImgs, in->imgs, imgBytes * ni));
-    din.imgs = dImgs;
-    if (hasBird) {
+    struct ForkFlag { bool& f; ~ForkFlag() { f = false; } } forkFlag{c.birdForkRecorded};
+    if (hasBird) {                                  // the birdview image first: see orbb200_frame_step_device
         uint8_t* dBird = A.take<uint8_t>(birdBytes * n);
         ORBB200_CUDA_OK(c, h2d(dBird, in->bird_imgs, birdBytes * n));
         din.bird_imgs = dBird;
+        if (!replay) { ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, c.stream)); c.birdForkRecorded = true; }
     }
+    ORBB200_CUDA_OK(c, h2d(dImgs, in->imgs, imgBytes * ni));
+    din.imgs = dImgs;
     if (hasMap) {
         orbb200_camera_pose* dP = A.take<orbb200_camera_pose>(n);
         ORBB200_CUDA_OK(c, h2d(dP, in->poses, sizeof(orbb200_camera_pose) * n));
