@@ -856,6 +856,18 @@ def leg_per_frame(arm, frames=12):
                     shim[f"{w}x{h}"] = json.loads(line[0][7:])
         if shim:
             out["cpp_shim"] = shim
+        # the same frame step and the same extraction from C++ with no interpreter in the loop (tools/ubench/*.cu, built by
+        # __graft_entry__.build()): wall ms per call and the device chain alone (CUDA events)
+        cpp = {}
+        for name, args in (("frame_timeline", ["100"]), ("call_timeline", ["752", "480", "1000", "200"]), ("call_timeline", ["1241", "376", "2000", "200"])):
+            exe = os.path.join(ROOT, "tools", "ubench", name)
+            if os.path.exists(exe):
+                r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                if line:
+                    cpp[name if name == "frame_timeline" else f"{name}_{args[0]}x{args[1]}"] = json.loads(line[-1])
+        if cpp:
+            out["cpp_c_abi"] = cpp
     except Exception as e:      # the C++ number is a side leg: never fail the bench line for it
         out["cpp_shim"] = {"error": repr(e)}
     return out

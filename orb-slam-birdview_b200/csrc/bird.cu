@@ -1006,9 +1006,12 @@ __global__ void __launch_bounds__(SP_THREADS) bird_subpix_thread_kernel(const ui
 //     queues it for the next launch ("phase"): the tail of a launch is at most `budget` iterations long, and the lanes of a
 //     warp stay in step.  ceil(maxIters / budget) launches finish every corner.
 #ifndef ORBB200_S5_UNROLL
-#define ORBB200_S5_UNROLL 1
+#define ORBB200_S5_UNROLL 2
 #endif
-constexpr int S5_UNROLL = ORBB200_S5_UNROLL;     // rows of the 14-row sample loop per unrolled body
+// rows of the 14-row sample loop per unrolled body.  Two: the top / cur source rows swap roles instead of being copied (14 moves
+// per row less), 11 KB of loop body; measured per 128 images: 1 -> 2.08 ms, 2 -> 1.94, 3 -> 1.94, 7 -> 2.19, 14 -> 2.39 (the body
+// outgrows the instruction cache)
+constexpr int S5_UNROLL = ORBB200_S5_UNROLL;
 constexpr int S5_THREADS = 128;
 constexpr int S5_WIN = 5;                           // half window
 #ifndef ORBB200_S5_BUDGET
@@ -1623,7 +1626,7 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
         return ORBB200_ERR_CUDA;
     }
     const uint8_t* mask = maskMode == 1 ? p->d_mask : maskMode == 2 ? p->d_maskShared : nullptr;
-    if (n <= 2) {
+    if (n <= 2 && !c.selectTiers) {
         // one or two images: every level at once, one 1024-thread CTA each with the largest carve (an SM per level is there for the
         // taking; the tiers below would run one after the other, and level 0's sort and partitions are 4x shorter per thread)
         bird_select_kernel<SEL_THREADS_FEW><<<dim3(n, BV_LEVELS), SEL_THREADS_FEW, smem, c.stream>>>(

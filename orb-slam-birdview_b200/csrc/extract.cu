@@ -1128,25 +1128,40 @@ __global__ void __launch_bounds__(NT) octree_kernel(Geom g, const uint32_t* __re
                 carry += tot;
             }
             nProc = carry;
-            int S2 = 1;
-            while (S2 < nProc) S2 <<= 1;
-            for (int i = nProc + tid; i < S2; i += NT) keys[i] = 0;
-            __syncthreads();
-            // bitonic sort, descending
-            for (int k = 2; k <= S2; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < S2; i += NT) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const uint32_t a = keys[i], b = keys[ixj];
-                            const bool desc = (i & k) == 0;
-                            if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
+            if (NT == OT_THREADS_FEW) {
+                // one or two images: the CTA is alone on its SM and the ~50 barrier-separated steps of a sorting network are the
+                // cost.  The keys are unique (they carry the position), so a key's place in the descending order is the number of
+                // larger keys: every thread counts that for its key over the whole list (broadcast reads), no barrier in between.
+                for (int i = nProc + tid; i < ((nProc + 3) & ~3); i += NT) keys[i] = 0;
+                __syncthreads();
+                for (int i = tid; i < nProc; i += NT) {
+                    const uint32_t mine = keys[i];
+                    int rank = 0;
+                    for (int j = 0; j < nProc; j += 4)
+                        rank += (keys[j] > mine) + (keys[j + 1] > mine) + (keys[j + 2] > mine) + (keys[j + 3] > mine);
+                    order[rank] = 0xffff - (int)(mine & 0xffff);
                 }
+            } else {
+                int S2 = 1;
+                while (S2 < nProc) S2 <<= 1;
+                for (int i = nProc + tid; i < S2; i += NT) keys[i] = 0;
+                __syncthreads();
+                // bitonic sort, descending
+                for (int k = 2; k <= S2; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int i = tid; i < S2; i += NT) {
+                            const int ixj = i ^ j;
+                            if (ixj > i) {
+                                const uint32_t a = keys[i], b = keys[ixj];
+                                const bool desc = (i & k) == 0;
+                                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int i = tid; i < nProc; i += NT) order[i] = 0xffff - (int)(keys[i] & 0xffff);
             }
-            for (int i = tid; i < nProc; i += NT) order[i] = 0xffff - (int)(keys[i] & 0xffff);
         }
         __syncthreads();
 
