@@ -534,6 +534,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     c.frameGraph = std::getenv("ORBB200_NO_FRAME_GRAPH") == nullptr;
     c.subpixGenericWarp = std::getenv("ORBB200_SUBPIX_GENERIC") != nullptr;
     c.selectTiers = std::getenv("ORBB200_SELECT_TIERS") != nullptr;
+    c.stageMatch = std::getenv("ORBB200_NO_STAGED_MATCH") == nullptr;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
     c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
     c.stageUploads = std::getenv("ORBB200_NO_STAGED_UPLOAD") == nullptr;
@@ -1132,50 +1133,79 @@ int run_window_job(Ctx& c, const orbb200_frame* F, const QueryHost& Q, int mode,
     const int nq = Q.nq, kpCap = std::max(F->cap, 1);
     const size_t need = (size_t)nq * (32 + 4 * 8 + 2 + 4 * 3) + (size_t)kpCap * (1 + 4) + (size_t)Q.n_cand * 4 + win_scratch_ints(kpCap, nq) * 4 +
                         80 * 256 + sizeof(WinJob);
+    if (!c.hostCopies.empty()) { ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream)); deliver_host_copies(c); }   // staged results of an earlier frame step
     if (!ensure_scratch(c, need, 0)) return ORBB200_ERR_CUDA;
     Arena A(c.d_scratch, c.d_scratch_bytes);
+    // Every host array of the call is first allocated back to back at the head of the device arena and mirrored at the same offset
+    // of the pinned staging block: ONE copy uploads them all (descriptor, the query arrays, the per-keypoint flags), and the
+    // outputs -- also back to back -- come home in ONE copy.  A matcher call used to be a dozen pageable-memory copies, each a
+    // synchronous bounce through the driver, around 70 us of kernels.
+    const size_t upBound = (size_t)nq * (32 + 4 * 8 + 2) + (size_t)kpCap + (size_t)Q.n_cand * 4 + 24 * 256 + sizeof(WinJob);
+    const size_t outBound = (size_t)nq * 12 + (size_t)kpCap * 4 + 6 * 256;
+    const bool staged = c.stageMatch && upBound <= STAGE_D2H_OFF - STAGE_H2D_OFF && outBound <= STAGE_LIMIT - STAGE_D2H_OFF && ensure_scratch(c, 0, STAGE_LIMIT);
+    uint8_t* const hUp = staged ? c.h_scratch + STAGE_H2D_OFF : nullptr;
+    auto up = [&](const void* src, size_t bytes) -> void* {
+        uint8_t* d = A.take<uint8_t>(bytes);
+        if (staged) memcpy(hUp + (d - c.d_scratch), src, bytes);
+        else cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c.stream);
+        return d;
+    };
     WinJob J{};
-    auto upF = [&](const float* src) -> const float* {
-        if (!src || Q.dev_queries) return src;
-        float* d = A.take<float>(nq);
-        cudaMemcpyAsync(d, src, sizeof(float) * nq, cudaMemcpyHostToDevice, c.stream);
-        return d;
-    };
-    auto upB = [&](const uint8_t* src, size_t n) -> const uint8_t* {
-        if (!src) return nullptr;
-        uint8_t* d = A.take<uint8_t>(n);
-        cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, c.stream);
-        return d;
-    };
+    auto upF = [&](const float* src) -> const float* { return (!src || Q.dev_queries) ? src : static_cast<const float*>(up(src, sizeof(float) * nq)); };
+    auto upB = [&](const uint8_t* src, size_t n) -> const uint8_t* { return src ? static_cast<const uint8_t*>(up(src, n)) : nullptr; };
+    auto upI = [&](const int32_t* src, size_t n) -> const int32_t* { return src ? static_cast<const int32_t*>(up(src, 4 * n)) : nullptr; };
     J.frame = F->d_self; J.nq = nq; J.mode = mode; J.levelMode = levelMode; J.checkOri = checkOri; J.kpCap = kpCap;
     J.th = th; J.nnratio = nnratio; J.mbf = mbf;
-    float* dsf = A.take<float>(MAX_LEVELS);
-    cudaMemcpyAsync(dsf, c.scale.data(), sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream);
-    J.scaleFactors = dsf; J.nLevels = c.nlevels;
+    WinJob* dJ = A.take<WinJob>(1);                    // filled last (it holds the output pointers), uploaded with the rest
+    float sf[MAX_LEVELS] = {};
+    std::copy(c.scale.begin(), c.scale.begin() + c.nlevels, sf);
+    J.scaleFactors = static_cast<const float*>(up(sf, sizeof(sf))); J.nLevels = c.nlevels;
     J.q_valid = Q.dev_queries ? Q.valid : upB(Q.valid, nq); J.q_x = upF(Q.x); J.q_y = upF(Q.y); J.q_aux = upF(Q.aux);
-    if (Q.level && Q.dev_queries) J.q_level = Q.level;
-    else if (Q.level) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.level, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_level = d; }
+    J.q_level = (Q.level && Q.dev_queries) ? Q.level : upI(Q.level, nq);
     J.q_viewcos = upF(Q.viewcos); J.q_angle = upF(Q.angle); J.q_r = upF(Q.r);
-    if (Q.maxlevel) { int32_t* d = A.take<int32_t>(nq); cudaMemcpyAsync(d, Q.maxlevel, 4 * (size_t)nq, cudaMemcpyHostToDevice, c.stream); J.q_maxlevel = d; }
-    if (Q.cand_idx && Q.n_cand > 0) { int32_t* d = A.take<int32_t>(Q.n_cand); cudaMemcpyAsync(d, Q.cand_idx, 4 * (size_t)Q.n_cand, cudaMemcpyHostToDevice, c.stream); J.cand_idx = d; }
-    if (Q.inv_sigma2) { float* d = A.take<float>(MAX_LEVELS); cudaMemcpyAsync(d, Q.inv_sigma2, sizeof(float) * c.nlevels, cudaMemcpyHostToDevice, c.stream); J.invLevelSigma2 = d; }
+    J.q_maxlevel = upI(Q.maxlevel, nq);
+    if (Q.cand_idx && Q.n_cand > 0) J.cand_idx = upI(Q.cand_idx, Q.n_cand);
+    if (Q.inv_sigma2) {
+        float is2[MAX_LEVELS] = {};
+        std::copy(Q.inv_sigma2, Q.inv_sigma2 + c.nlevels, is2);
+        J.invLevelSigma2 = static_cast<const float*>(up(is2, sizeof(is2)));
+    }
     J.accTh = Q.acc_th; J.flags = Q.flags;
     J.q_desc = Q.dev_queries ? Q.desc : upB(Q.desc, (size_t)nq * 32); J.q_obs_pos = upB(Q.obs_pos, nq); J.kp_blocked = upB(Q.kp_blocked, F->cap);
-    J.scratch = A.take<int>(win_scratch_ints(kpCap, nq));
-    J.out_best_idx = A.take<int32_t>(nq); J.out_best_dist = A.take<int32_t>(nq);
+    const size_t upEnd = A.off;
+    J.out_best_idx = A.take<int32_t>(nq);              // outputs back to back: one download
+    const size_t outBegin = reinterpret_cast<uint8_t*>(J.out_best_idx) - c.d_scratch;
+    J.out_best_dist = A.take<int32_t>(nq);
     J.out_per_kp = A.take<int32_t>(kpCap); J.out_per_query = A.take<int32_t>(nq);
     J.out_nmatches = A.take<int32_t>(1);
-    WinJob* dJ = A.take<WinJob>(1);
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, &J, sizeof(J), cudaMemcpyHostToDevice, c.stream));
+    const size_t outEnd = A.off;
+    J.scratch = A.take<int>(win_scratch_ints(kpCap, nq));
+    if (staged) {
+        const size_t jOff = reinterpret_cast<uint8_t*>(dJ) - c.d_scratch;
+        memcpy(hUp + jOff, &J, sizeof(J));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(c.d_scratch + jOff, hUp + jOff, upEnd - jOff, cudaMemcpyHostToDevice, c.stream));
+    } else {
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(dJ, &J, sizeof(J), cudaMemcpyHostToDevice, c.stream));
+    }
     launch_window_match(c, dJ, 1, nq, kpCap);
     ORBB200_CUDA_OK(c, cudaGetLastError());
-    if (h_best_idx) cudaMemcpyAsync(h_best_idx, J.out_best_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
-    if (h_best_dist) cudaMemcpyAsync(h_best_dist, J.out_best_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
-    if (h_per_kp && F->cap > 0) cudaMemcpyAsync(h_per_kp, J.out_per_kp, 4 * (size_t)F->cap, cudaMemcpyDeviceToHost, c.stream);
-    if (h_per_query) cudaMemcpyAsync(h_per_query, J.out_per_query, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
     int32_t nm = 0;
-    cudaMemcpyAsync(&nm, J.out_nmatches, 4, cudaMemcpyDeviceToHost, c.stream);
-    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (staged) {
+        uint8_t* hOut = c.h_scratch + STAGE_D2H_OFF;
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hOut, c.d_scratch + outBegin, outEnd - outBegin, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        auto home = [&](void* dst, const void* dsrc, size_t bytes) { if (dst && bytes) memcpy(dst, hOut + (static_cast<const uint8_t*>(dsrc) - (c.d_scratch + outBegin)), bytes); };
+        home(h_best_idx, J.out_best_idx, 4 * (size_t)nq); home(h_best_dist, J.out_best_dist, 4 * (size_t)nq);
+        home(h_per_kp, J.out_per_kp, 4 * (size_t)std::max(F->cap, 0)); home(h_per_query, J.out_per_query, 4 * (size_t)nq);
+        home(&nm, J.out_nmatches, 4);
+    } else {
+        if (h_best_idx) cudaMemcpyAsync(h_best_idx, J.out_best_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+        if (h_best_dist) cudaMemcpyAsync(h_best_dist, J.out_best_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+        if (h_per_kp && F->cap > 0) cudaMemcpyAsync(h_per_kp, J.out_per_kp, 4 * (size_t)F->cap, cudaMemcpyDeviceToHost, c.stream);
+        if (h_per_query) cudaMemcpyAsync(h_per_query, J.out_per_query, 4 * (size_t)nq, cudaMemcpyDeviceToHost, c.stream);
+        cudaMemcpyAsync(&nm, J.out_nmatches, 4, cudaMemcpyDeviceToHost, c.stream);
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    }
     if (h_nmatches) *h_nmatches = nm;
     return ORBB200_OK;
 }
