@@ -520,6 +520,9 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c.stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evFork4, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evJoin4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evFork0, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evJoin0, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.streamBird, cudaStreamNonBlocking) != cudaSuccess ||
@@ -629,6 +632,9 @@ void orbb200_destroy(orbb200_ctx* ctx)
     if (c.evFork0) cudaEventDestroy(c.evFork0);
     if (c.evJoin0) cudaEventDestroy(c.evJoin0);
     if (c.stream3) cudaStreamDestroy(c.stream3);
+    if (c.evFork4) cudaEventDestroy(c.evFork4);
+    if (c.evJoin4) cudaEventDestroy(c.evJoin4);
+    if (c.stream4) cudaStreamDestroy(c.stream4);
     if (c.evBirdFork) cudaEventDestroy(c.evBirdFork);
     if (c.evBirdJoin) cudaEventDestroy(c.evBirdJoin);
     if (c.streamBird) cudaStreamDestroy(c.streamBird);

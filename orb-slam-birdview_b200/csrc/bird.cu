@@ -1611,10 +1611,37 @@ void enqueue_pyramid(Ctx& c, BirdPlan* p, int n, bool withMask, int nLevels)
 
 // maskMode: 0 none; 1 one mask per image in p->d_mask level 0 (its pyramid is built here); 2 the shared mask pyramid of
 // orbb200_bird_set_mask (p->d_maskShared, already built)
-int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode)
+void enqueue_blur(Ctx& c, BirdPlan* p, int n, int nLevels, cudaStream_t stream)
+{
+    const BirdGeom& g = p->g;
+    GaussK gk;
+    {   // cv::getGaussianKernel(7, 2, CV_32F)
+        double sum = 0;
+        for (int i = 0; i < 7; i++) { const double x = i - 3.0; gk.k[i] = (float)std::exp(-0.5 / 4.0 * x * x); sum += gk.k[i]; }
+        sum = 1. / sum;
+        for (int i = 0; i < 7; i++) gk.k[i] = (float)(gk.k[i] * sum);
+    }
+    int maxW = 1, maxH = 1;
+    for (int l = 0; l < nLevels; l++) { maxW = std::max(maxW, g.lv[l].w); maxH = std::max(maxH, g.lv[l].h); }
+    bird_blur_kernel<<<dim3((((maxW + 3) / 4) * ((maxH + 15) / 16) + 127) / 128, 1, n * BV_LEVELS), 128, 0, stream>>>(p->d_pyr, p->d_blur, g.planeBytes, g, gk, nLevels);
+    c.launches++;
+}
+
+// forkBlur: the caller will run enqueue_compute on the same pyramid (detect + cornerSubPix + compute in one call).  For one or two
+// images the blurred pyramid -- which only compute's descriptors read and which depends on nothing but the pyramid -- is then
+// built on a side stream beside FAST, retainBest and cornerSubPix instead of after them.
+int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nullptr)
 {
     const BirdGeom& g = p->g;
     { StageTimer t(c, 9); enqueue_pyramid(c, p, n, maskMode == 1, BV_LEVELS); }
+    if (forkBlur) *forkBlur = false;
+    if (forkBlur && n <= 2 && !c.timing && c.stream4) {
+        cudaEventRecord(c.evFork4, c.stream);
+        cudaStreamWaitEvent(c.stream4, c.evFork4, 0);
+        enqueue_blur(c, p, n, BV_LEVELS, c.stream4);
+        cudaEventRecord(c.evJoin4, c.stream4);
+        *forkBlur = true;                            // the caller hands this to enqueue_compute, which joins the side stream
+    }
     StageTimer t(c, 10);
     cudaMemsetAsync(p->d_candCount, 0, sizeof(int32_t) * MAX_LEVELS * n, c.stream);
     launch_fast_cells(c, p->d_pyr, g.planeBytes, g.candPerImg, BV_FAST_TH, BV_FAST_TH, 1, p->d_cells, p->nCells, p->need, p->d_cand,
@@ -1754,22 +1781,16 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
 }
 
 // d_kps/d_counts -> filtered into d_kps2/d_counts2, descriptors in d_desc
-int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels)
+int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels, bool blurForked = false)
 {
     const BirdGeom& g = p->g;
     bird_filter_kernel<<<n, 256, 0, c.stream>>>(g, p->d_kps, p->d_counts, p->d_kps2, p->d_counts2);
     c.launches++;
-    GaussK gk;
-    {   // cv::getGaussianKernel(7, 2, CV_32F)
-        double sum = 0;
-        for (int i = 0; i < 7; i++) { const double x = i - 3.0; gk.k[i] = (float)std::exp(-0.5 / 4.0 * x * x); sum += gk.k[i]; }
-        sum = 1. / sum;
-        for (int i = 0; i < 7; i++) gk.k[i] = (float)(gk.k[i] * sum);
+    if (blurForked) {                               // enqueue_detect started it on the side stream
+        cudaStreamWaitEvent(c.stream, c.evJoin4, 0);
+    } else {
+        enqueue_blur(c, p, n, nLevels, c.stream);
     }
-    int maxW = 1, maxH = 1;
-    for (int l = 0; l < nLevels; l++) { maxW = std::max(maxW, g.lv[l].w); maxH = std::max(maxH, g.lv[l].h); }
-    bird_blur_kernel<<<dim3((((maxW + 3) / 4) * ((maxH + 15) / 16) + 127) / 128, 1, n * BV_LEVELS), 128, 0, c.stream>>>(p->d_pyr, p->d_blur, g.planeBytes, g, gk, nLevels);
-    c.launches++;
     bird_describe_kernel<<<dim3(n >= 8 ? 12 : (g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_blur, p->d_kps2, p->d_counts2, p->d_desc);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
@@ -1868,7 +1889,8 @@ int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t*
         bird_import_kernel<<<dim3(g.h, n), 128, 0, c.stream>>>(d_imgs, imgBytes, stride, p->d_pyr, g.planeBytes, g.lv[0]);
         c.launches++;
     }
-    rc = enqueue_detect(c, p, n, p->d_maskShared ? 2 : 0);
+    bool blurForked = false;
+    rc = enqueue_detect(c, p, n, p->d_maskShared ? 2 : 0, &blurForked);
     if (rc != ORBB200_OK) return rc;
     {
         StageTimer t(c, 11);
@@ -1883,7 +1905,7 @@ int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t*
     }
     {
         StageTimer t(c, 12);
-        rc = enqueue_compute(c, p, n, BV_LEVELS);
+        rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked);
         if (rc != ORBB200_OK) return rc;
         bird_queries_kernel<<<dim3((g.kpPerImg + 255) / 256, n + 1), 256, 0, c.stream>>>(p->d_kps2, p->d_counts2, p->d_carryKps, p->d_carryCount, g.kpPerImg,
                                                                                         p->d_qx, p->d_qy, p->d_qangle, p->d_qlevel, p->d_qvalid);
@@ -2014,7 +2036,8 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     if (!p) return ORBB200_ERR_CUDA;
     const BirdGeom& g = p->g;
     int rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
-    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0);
+    bool blurForked = false;
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0, &blurForked);
     if (rc != ORBB200_OK) return rc;
     // cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001))   (src/Frame.cc:335-336)
     bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
@@ -2025,7 +2048,7 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     }
     bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 1);
     c.launches++;
-    rc = enqueue_compute(c, p, n, BV_LEVELS);
+    rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked);
     if (rc != ORBB200_OK) return rc;
     return download(c, p, n, p->d_kps2, p->d_counts2, kps, desc, cap_per_img, n_out);
 }

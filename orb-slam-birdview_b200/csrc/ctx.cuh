@@ -90,6 +90,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // side branch of the extraction graph (blur runs beside FAST + octree)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t stream4 = nullptr;          // one or two birdview images: the blurred pyramid beside FAST + retainBest + cornerSubPix
+    cudaEvent_t evFork4 = nullptr, evJoin4 = nullptr;
     cudaStream_t stream3 = nullptr;          // one or two images: FAST + octree of level 0 beside the resize chain
     cudaEvent_t evFork0 = nullptr, evJoin0 = nullptr;
     bool pdl = true;                         // programmatic dependent launches inside the extraction chain (ORBB200_NO_PDL=1 turns them off)
