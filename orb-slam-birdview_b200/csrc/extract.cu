@@ -934,7 +934,10 @@ __global__ void __launch_bounds__(FS_THREADS, ORBB200_FS_MINBLK) fast_strip_kern
 // (cell row, cell col, y, x) order on ties (:744-759).
 // ---------------------------------------------------------------------------------------------------
 constexpr int OT_THREADS = 256;          // batches: many (image, level) CTAs in flight
-constexpr int OT_THREADS_FEW = 1024;     // one or two images: the level-0 CTA is the critical path, its sweeps are latency chains
+#ifndef ORBB200_OT_FEW
+#define ORBB200_OT_FEW 1024
+#endif
+constexpr int OT_THREADS_FEW = ORBB200_OT_FEW;     // one or two images: the level-0 CTA is the critical path, its sweeps are latency chains
 
 struct OtNode { short x0, y0, x1, y1; };
 
