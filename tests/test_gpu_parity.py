@@ -68,6 +68,25 @@ def test_extract_vs_oracle(pkg, name, h, w, nf, ini, mn, seed):
     assert k.tobytes() == k2.tobytes() and np.array_equal(d, d2)
 
 
+def test_small_host_calls_one_graph_paths(pkg):
+    """One or two images per host call run as one graph whose first kernel reads the pinned staging rows and whose last kernel
+    writes the pinned result mirror.  Rows of the caller's images need not be contiguous (a cv::Mat ROI) and widths need not be
+    multiples of 16 (the staging pads them): strided views, two images per call, an odd width, the same context reused across
+    shapes -- all byte-exact against the oracle, also on the replayed graph."""
+    orc = oracle.Extractor(700, 1.2, 8, 20, 7)
+    ex = pkg.ORBextractor(700, 1.2, 8, 20, 7, max_size=(640, 400), max_batch=2)
+    for (h, w, seed) in ((300, 437, 31), (400, 640, 32), (300, 437, 33)):
+        big = [synth.synth_frame(h + 10, w + 23, seed + 10 * i) for i in range(2)]
+        views = [b[5:5 + h, 11:11 + w] for b in big]                  # stride = w + 23
+        want = [orc(np.ascontiguousarray(v)) for v in views]
+        for rep in range(3):                                          # warm-up, capture, replay
+            ks, ds, ns = ex.extract_batch(views)
+            for i, (k0, d0) in enumerate(want):
+                _compare_extract(ks[i, :ns[i]], ds[i, :ns[i]], k0, d0, f"{w}x{h} strided pair, call {rep}")
+            k, d = ex(views[1])
+            _compare_extract(k, d, want[1][0], want[1][1], f"{w}x{h} strided single, call {rep}")
+
+
 @pytest.mark.parametrize("name", ["c1_752x480", "bird_400x400", "small_320x240"])
 def test_extract_vs_committed_golden(pkg, name):
     g = np.load(os.path.join(GOLDEN, f"extract_{name}.npz"))
