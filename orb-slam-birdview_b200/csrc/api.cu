@@ -1939,7 +1939,15 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         memcpy(key.data() + sizeof(*p) + 16, ptrs, sizeof(ptrs));
         for (auto& q : c.frameGraphs)
             if (q.key == key) { fg = &q; break; }
-        if (!fg && c.frameGraphs.size() < 8) { c.frameGraphs.push_back(Ctx::FrameGraph{key, 0, nullptr, 0}); fg = &c.frameGraphs.back(); }
+        if (!fg) {
+            if (c.frameGraphs.size() >= 8) {            // more parameter sets than slots: start over rather than run the newcomers eagerly for ever
+                ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+                for (auto& q : c.frameGraphs) if (q.exec) cudaGraphExecDestroy(q.exec);
+                c.frameGraphs.clear();
+            }
+            c.frameGraphs.push_back(Ctx::FrameGraph{key, 0, nullptr, 0});
+            fg = &c.frameGraphs.back();
+        }
     }
     const bool replay = fg && fg->state == 2, capture = fg && fg->state == 1;
     const unsigned long long epoch0 = c.allocEpoch;

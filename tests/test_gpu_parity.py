@@ -963,6 +963,58 @@ def test_frame_step_one_frame_per_call_replayed_graph(pkg):
     assert len(set(launches[1:])) == 1 and launches[1] > 30, launches
 
 
+def test_frame_step_replay_survives_reallocation(pkg):
+    """A recorded frame step holds device and pinned pointers.  Replacing the local map, changing the birdview mask and growing
+    the staging blocks (a larger matcher call, a batch of two) between replayed calls must drop the recording, not replay it on
+    stale pointers: every call still equals the oracle."""
+    w, h, bw, bh, nfeat, bnf, nmap = 620, 188, 200, 200, 1000, 600, 1500
+    seq = synth.northstar_sequence(12, 29, w=w, h=h, bird=(bw, bh), vehicle=(40, 60))
+    orc = oracle.Extractor(nfeat, 1.2, 8, 20, 7)
+    mp = synth.northstar_map(seq, lambda im: orc(im), nmap, 3)
+    mp2 = synth.northstar_map(seq, lambda im: orc(im), nmap, 4)
+    mask2 = seq["bird_mask"].copy()
+    mask2[:40, :] = 0
+    ctx = pkg.Context(nfeat, 1.2, 8, 20, 7, w, h, 4)
+    poses = [pkg.CameraPose.make(**p) for p in seq["poses"]]
+
+    def check(step, i, m, mask, prev):
+        out = step(seq["imgs"][2 * i:2 * i + 2], seq["bird_imgs"][i:i + 1], poses[i:i + 1], chain=prev is not None)
+        s2 = dict(seq, bird_mask=mask)
+        (r,), prev = _oracle_frame_step(s2, m, [i], nfeat, bnf, w, h, bw, bh, 1.0, 0.8, 15, 0.99, prev)
+        nl, nb = out["counts"][0], out["bird_counts"][0]
+        assert out["kps"][0][:nl].tobytes() == r["kl"].tobytes() and np.array_equal(out["desc"][0][:nl], r["dl"]), i
+        assert out["map_nmatches"][0] == r["nm"] and np.array_equal(out["map_best_idx"][0], r["bi"]), i
+        assert out["bird_kps"][0][:nb].tobytes() == r["bk"].tobytes() and np.array_equal(out["bird_desc"][0][:nb], r["bdsc"]), i
+        if r["m12"] is not None:
+            assert out["bird_nmatches"][0] == r["nbm"] and np.array_equal(out["bird_matches12"][0][:len(r["m12"])], r["m12"]), i
+        return prev
+
+    def make(m, mask):
+        M = pkg.LocalMap(ctx, m["pos"], m["normal"], m["max_distance"], m["min_distance"], m["desc"])
+        return M, pkg.FrameStep(ctx, w, h, M, mb=0.537, mbf=386.1448, th=1.0, nnratio=0.8, bird_size=(bw, bh), bird_nfeatures=bnf,
+                                bird_mask=mask, bird_window=15, bird_nnratio=0.99)
+    M, step = make(mp, seq["bird_mask"])
+    prev = None
+    for i in range(5):                                # eager, eager, recorded, replayed, replayed
+        prev = check(step, i, mp, seq["bird_mask"], prev)
+    # a large matcher call grows the scratch blocks; a two-frame step uses other plans
+    k, d = orc(seq["imgs"][0])
+    F = pkg.Frame(ctx, k, d, 0.0, 0.0, 64.0 / w, 48.0 / h)
+    nq = 60000
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, len(k), nq)
+    pkg.ORBmatcher(ctx, 0.8).SearchByProjection(F, np.ones(nq, np.uint8), k["x"][idx], k["y"][idx], np.full(nq, -1, np.float32),
+                                                k["octave"][idx].astype(np.int32), np.full(nq, 0.9, np.float32), d[idx].copy())
+    for i in range(5, 8):
+        prev = check(step, i, mp, seq["bird_mask"], prev)
+    # new map (the old one freed: its addresses may be handed out again) and a new mask
+    del step, M
+    M, step = make(mp2, mask2)
+    prev = None
+    for i in range(8, 12):
+        prev = check(step, i, mp2, mask2, prev)
+
+
 def test_three_host_threads_three_contexts(pkg):
     """The reference calls the front-end from three threads at once (Tracking: extraction + projection searches; LocalMapping:
     SearchForTriangulation, src/LocalMapping.cc:278; LoopClosing: SearchByBoW, src/LoopClosing.cc:265), one ORBextractor /
