@@ -908,7 +908,7 @@ int orbb200_level_candidates(orbb200_ctx* ctx, int img_index, int level, int32_t
 static int knn2_splits(int nq, int nm)
 {
     // enough CTAs for ~2 waves of 148 SMs x 4 resident CTAs, at least 64 map descriptors per split
-    const int qtiles = (nq + 511) / 512;
+    const int qtiles = (nq + 128 * knn2_queries_per_thread(nq, nm) - 1) / (128 * knn2_queries_per_thread(nq, nm));
     int s = std::max(1, (148 * 8) / std::max(qtiles, 1));
     s = std::min(s, std::max(1, nm / 64));
     return s;

@@ -20,13 +20,17 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 // so that the first minimum in index order wins, exactly like a sequential scan with strict '<'.
 // ---------------------------------------------------------------------------------------------------
 constexpr int KN_THREADS = 128;
-constexpr int KN_QPT = 4;
+constexpr int KN_QPT = 4;        // queries per thread when there is enough work to fill the GPU with it
 constexpr int KN_MT = 128;       // map descriptors per shared-memory tile
 
+// KN_QPT queries per thread amortise a shared-memory broadcast over four distances; small problems (2k x 2k: 7 us of POPC work) do not
+// fill 148 SMs that way and run with one query per thread instead -- four times the CTAs, a quarter of the chain per thread.
+template <int KN_QPT>
 __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ m, int nm,
                                                           int mPerSplit, int4* __restrict__ partial)
 {
     __shared__ uint4 sM[2][KN_MT][2];
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int split = blockIdx.x;
     const int mBeg = split * mPerSplit, mEnd = min(nm, mBeg + mPerSplit);
@@ -83,6 +87,7 @@ __global__ void __launch_bounds__(256) knn2_merge_kernel(const int4* __restrict_
                                                          int32_t* __restrict__ bi, int32_t* __restrict__ bd, int32_t* __restrict__ sd)
 {
     const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_wait();                                             // launched programmatically behind knn2_kernel
     if (qi >= nq) return;                                   // whole warps leave together
     const int per = (nsplit + 31) >> 5;
     int best = 256, second = 256, idx = -1;
@@ -102,14 +107,20 @@ __global__ void __launch_bounds__(256) knn2_merge_kernel(const int4* __restrict_
     if (lane == 0) { bi[qi] = idx; bd[qi] = best; sd[qi] = second; }
 }
 
+// one query per thread below ~64 M descriptor pairs (see knn2_kernel)
+int knn2_queries_per_thread(int nq, int nm) { return (long long)nq * nm < (64ll << 20) ? 1 : KN_QPT; }
+
 void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
                  int32_t* bi, int32_t* bd, int32_t* sd)
 {
     const int mPerSplit = (nm + nsplit - 1) / nsplit;
-    dim3 grid(nsplit, (nq + KN_THREADS * KN_QPT - 1) / (KN_THREADS * KN_QPT));
-    knn2_kernel<<<grid, KN_THREADS, 0, c.stream>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_m), nm,
-                                                   mPerSplit, d_partial);
-    knn2_merge_kernel<<<(nq + 7) / 8, 256, 0, c.stream>>>(d_partial, nq, nsplit, bi, bd, sd);
+    const int qpt = knn2_queries_per_thread(nq, nm);
+    dim3 grid(nsplit, (nq + KN_THREADS * qpt - 1) / (KN_THREADS * qpt));
+    if (qpt == 1)
+        knn2_kernel<1><<<grid, KN_THREADS, 0, c.stream>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_m), nm, mPerSplit, d_partial);
+    else
+        knn2_kernel<KN_QPT><<<grid, KN_THREADS, 0, c.stream>>>(reinterpret_cast<const uint4*>(d_q), nq, reinterpret_cast<const uint4*>(d_m), nm, mPerSplit, d_partial);
+    launch_chain(c.pdl, knn2_merge_kernel, dim3((nq + 7) / 8), dim3(256), 0, c.stream, (const int4*)d_partial, nq, nsplit, bi, bd, sd);
     c.launches += 2;
 }
 

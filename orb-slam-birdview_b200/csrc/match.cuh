@@ -55,6 +55,7 @@ struct TriJob {
     int32_t* npairs;
 };
 
+int knn2_queries_per_thread(int nq, int nm);
 void launch_knn2(Ctx& c, const uint8_t* d_q, int nq, const uint8_t* d_m, int nm, int nsplit, int4* d_partial,
                  int32_t* bi, int32_t* bd, int32_t* sd);
 void launch_popc_peak(Ctx& c, uint32_t* d_out, int blocks, int iters);
