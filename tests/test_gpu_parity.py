@@ -815,6 +815,29 @@ def test_bird_retain_best_ties(pkg):
     assert _same_kps(a, b) and len(b) > 100
 
 
+def test_bird_retain_best_dense_and_tall(pkg):
+    """The row-major ordering of a level's corners has two forms (counting sort by row when the row cursors fit the level's
+    shared-memory carve, bitonic network otherwise) and the selection three shared-memory tiers in batches plus the one-launch form
+    for one or two images: a noise image whose level 0 holds several thousand corners (largest tier) and a tall, sparse one (more
+    rows than the smallest tier has cursor slots), each alone and in a batch of three."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    rng = np.random.default_rng(12)
+    dense = np.repeat(np.repeat(rng.integers(0, 256, (150, 150)).astype(np.uint8), 2, 0), 2, 1)          # 300 x 300, 2 x 2 noise blocks
+    tall = np.full((2304, 128), 100, np.uint8)                                                             # a narrow noise strip: ~800 corners on 2304 rows
+    tall[:, 60:68] = np.repeat(np.repeat(rng.integers(0, 256, (1152, 4)).astype(np.uint8), 2, 0), 2, 1)
+    for img, nf in ((dense, 2000), (tall, 400)):
+        want_k, want_d = oracle.bird_extract(img, None, nf)
+        assert len(want_k) > 100
+        B = pkg.BirdviewORB(ctx, nf)
+        k, d = B(img, None)
+        assert _same_kps(k, want_k) and np.array_equal(d, want_d)
+        ks, ds = B.extract_batch([img, img.copy(), img.copy()], None)
+        for i in range(3):
+            assert _same_kps(ks[i], want_k) and np.array_equal(ds[i], want_d), i
+    n0 = len(oracle.bird_detect(dense, None, 100000))
+    assert n0 > 5120, n0                                                                                  # the dense case really is in the last tier
+
+
 def test_bird_edge_cases(pkg):
     """No corners, everything masked, images too small for the 31-pixel edge threshold, strided input, empty inputs."""
     ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
