@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "orb-slam-birdview_b200", "liborbb200.so")
 WATCH = ["UTMALDG", "UTMASTG", "SYNCS", "VIMNMX3", "VIMNMX", "IDP", "POPC", "PRMT", "SHF", "DMUL", "DADD", "DFMA", "F2F", "LDGSTS", "REDUX", "VOTE",
-         "ATOMS", "ATOMG", "RED", "BAR", "HMMA", "UTCHMMA"]
+         "ATOMS", "ATOMG", "RED", "BAR", "ACQBULK", "PREEXIT", "HMMA", "UTCHMMA"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 arch = sorted(set(re.findall(r"arch = (sm_\w+)", sass)))
@@ -29,7 +29,7 @@ for line in sass.splitlines():
 demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
 print(f"{os.path.relpath(LIB, ROOT)}: {len(kernels)} kernels, cubin architectures {arch}")
 print("static SASS instruction counts per kernel (cuobjdump -sass); only the watched mnemonics that occur are listed")
-print("UTMALDG = cp.async.bulk.tensor (TMA load), SYNCS = mbarrier, VIMNMX3 = three-input packed min/max, IDP = dp2a/dp4a, no HMMA/UTC*MMA: nothing on this path is a matrix product\n")
+print("UTMALDG = cp.async.bulk.tensor (TMA load), SYNCS = mbarrier, ACQBULK / PREEXIT = griddepcontrol.wait / .launch_dependents (programmatic dependent launch), VIMNMX3 = three-input packed min/max, IDP = dp2a/dp4a, no HMMA/UTC*MMA: nothing on this path is a matrix product\n")
 for mangled, name in zip(kernels, demangle):
     c = kernels[mangled]
     short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "")).replace("void ", "").replace("orbb200::", "")
