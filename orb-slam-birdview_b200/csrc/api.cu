@@ -1738,38 +1738,19 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     const bool hasMap = p->map && p->map->n > 0, hasBird = p->bird_w > 0, stereo = p->mb > 0.f;
     if (!in || !out || !in->imgs || (hasBird && !in->bird_imgs) || (hasMap && (!in->poses || !out->map_best_idx || !out->map_best_dist || !out->map_nmatches)) ||
         (hasBird && (!out->bird_matches12 || !out->bird_nmatches))) { c.err = "frame_step: missing input or output array"; return ORBB200_ERR_ARG; }
-    // birdview front-end + the query arrays of BirdviewMatch(previous, current): independent of the front camera until the
-    // matching, FP64- and latency-bound where the front extraction is integer-ALU-bound -> on a side stream beside it
-    // (per-stage timing keeps everything on one stream so that a stage's events bracket its kernels alone)
+    // birdview front-end + the query arrays of BirdviewMatch(previous, current): independent of the front camera, FP64- and
+    // latency-bound where the front extraction is integer-ALU-bound -> on a side stream beside it, TOGETHER WITH ITS OWN MATCHING
+    // (grid of the birdview frame + the BirdviewMatch job): the two paths only meet at the end of the step.  (Per-stage timing keeps
+    // everything on one stream so that a stage's events bracket its kernels alone.)
     BirdStepView bv{};
-    const bool fork = hasBird && (c.forkBird || n <= 8) && !c.timing;      // a few frames leave most SMs idle: the two front-ends overlap
-    if (hasBird) {
-        cudaStream_t main = c.stream;
-        if (fork) {
-            // (the host variant records the event itself, right behind the birdview upload: the birdview front-end -- the longer
-            // of the two -- then starts while the front images are still on their way)
-            if (!c.birdForkRecorded) ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, main));
-            ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.streamBird, c.evBirdFork, 0));
-            c.stream = c.streamBird;
-        }
-        rc = bird_step_enqueue(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, in->bird_imgs, (size_t)p->bird_h * p->bird_stride, p->bird_stride,
-                               p->chain != 0, &bv);
-        if (fork) {
-            cudaEventRecord(c.evBirdJoin, c.streamBird);
-            c.stream = main;
-        }
+    const bool fork = hasBird && (c.forkBird || n <= 8) && !c.timing;      // a few frames leave most SMs idle: the two paths overlap
+    if (hasBird) {                                  // the plan's pools (no launch yet): the frame plan below points into them
+        rc = bird_step_view(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, &bv);
         if (rc != ORBB200_OK) return rc;
     }
-    // front camera: both images of every frame in one extraction, then the stereo matcher on its pools
-    rc = orbb200_extract_device(ctx, in->imgs, (size_t)p->h * p->stride, 2 * n, p->w, p->h, p->stride);
-    if (rc != ORBB200_OK) return rc;
-    if (stereo) {
-        StageTimer t(c, 8);
-        launch_stereo(c, n, 0, 1, 2, p->mb, p->mbf, c.d_invScale, c.d_nKept);
-        c.stereoValid = true;
-    }
-    if (fork) ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0));
-    const int kpi = c.cur->g.kpPerImg, mapN = hasMap ? p->map->n : 0;
+    const ShapeTables* shape = get_shape(c, p->w, p->h);
+    if (!shape) return c.err.find("exceeds") != std::string::npos ? ORBB200_ERR_ARG : ORBB200_ERR_UNSUPPORTED;
+    const int kpi = shape->g.kpPerImg, mapN = hasMap ? p->map->n : 0;
     FramePlan key{};
     key.n = n; key.kpi = kpi; key.birdKpi = hasBird ? bv.kpPerImg : 0; key.mapN = mapN; key.stereo = stereo ? 1 : 0; key.birdWindow = p->bird_window;
     key.birdOri = p->bird_check_ori; key.hasBird = hasBird ? 1 : 0; key.th = p->th; key.nnratio = p->nnratio; key.minX = p->min_x; key.minY = p->min_y;
@@ -1855,6 +1836,36 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
         c.framePlans.push_back(key);
         plan = &c.framePlans.back();
     }
+    const int nFrontJobs = hasMap ? n : 0, nBirdJobs = plan->nJobs - nFrontJobs, birdKpi = plan->birdKpi;
+    if (hasBird) {
+        cudaStream_t main = c.stream;
+        struct Restore { cudaStream_t& s; cudaStream_t v; ~Restore() { s = v; } } restore{c.stream, main};
+        if (fork) {
+            // (the host variant records the event itself, right behind the birdview upload: the birdview path -- the longer of the
+            // two -- then starts while the front images are still on their way)
+            if (!c.birdForkRecorded) ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdFork, main));
+            ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.streamBird, c.evBirdFork, 0));
+            c.stream = c.streamBird;
+        }
+        rc = bird_step_enqueue(c, p->bird_w, p->bird_h, p->bird_nfeatures, n, in->bird_imgs, (size_t)p->bird_h * p->bird_stride, p->bird_stride,
+                               p->chain != 0, &bv);
+        if (rc != ORBB200_OK) return rc;
+        if (fork) {
+            launch_grid_build(c, plan->dF + n, n);
+            if (nBirdJobs > 0) launch_window_match(c, plan->dJ + nFrontJobs, nBirdJobs, birdKpi, birdKpi);
+            rc = bird_step_carry(c, bv, n);
+            if (rc != ORBB200_OK) return rc;
+            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdJoin, c.streamBird));
+        }
+    }
+    // front camera: both images of every frame in one extraction, then the stereo matcher on its pools
+    rc = orbb200_extract_device(ctx, in->imgs, (size_t)p->h * p->stride, 2 * n, p->w, p->h, p->stride);
+    if (rc != ORBB200_OK) return rc;
+    if (stereo) {
+        StageTimer t(c, 8);
+        launch_stereo(c, n, 0, 1, 2, p->mb, p->mbf, c.d_invScale, c.d_nKept);
+        c.stereoValid = true;
+    }
     if (hasMap) {                                  // Frame::isInFrustum for every (frame, map point)
         StageTimer t(c, 13);
         FrustumJob J{};
@@ -1863,11 +1874,17 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
         J.inView = plan->inView; J.u = plan->u; J.v = plan->v; J.uR = plan->uR; J.level = plan->level; J.viewcos = plan->viewcos; J.count = plan->count;
         launch_frustum(c, J);
     }
-    { StageTimer t(c, 6); launch_grid_build(c, plan->dF, plan->nFrames); }
-    if (plan->nJobs > 0) { StageTimer t(c, 7); launch_window_match(c, plan->dJ, plan->nJobs, plan->maxNq, plan->maxKpCap); }
-    if (hasBird) {
-        rc = bird_step_carry(c, bv, n);
-        if (rc != ORBB200_OK) return rc;
+    if (fork) {                                    // the birdview frames were matched on their own stream
+        launch_grid_build(c, plan->dF, n);
+        if (nFrontJobs > 0) launch_window_match(c, plan->dJ, nFrontJobs, std::max(mapN, 1), kpi);
+        ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0));
+    } else {
+        { StageTimer t(c, 6); launch_grid_build(c, plan->dF, plan->nFrames); }
+        if (plan->nJobs > 0) { StageTimer t(c, 7); launch_window_match(c, plan->dJ, plan->nJobs, plan->maxNq, plan->maxKpCap); }
+        if (hasBird) {
+            rc = bird_step_carry(c, bv, n);
+            if (rc != ORBB200_OK) return rc;
+        }
     }
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;

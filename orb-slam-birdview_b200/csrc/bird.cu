@@ -1876,6 +1876,25 @@ int bird_set_mask(Ctx& c, int w, int h, int nfeatures, int batch, const uint8_t*
 
 // cv::ORB detect(mask) + cornerSubPix(5,5; 40; 1e-3) + compute on n device-resident images, everything enqueued on the
 // context's stream; then the query arrays of the frame-to-frame birdview matching.  chain == false forgets the carried frame.
+static void fill_step_view(BirdPlan* p, BirdStepView* out)
+{
+    out->d_kps = p->d_kps2; out->d_desc = p->d_desc; out->d_counts = p->d_counts2; out->kpPerImg = p->g.kpPerImg;
+    out->d_qx = p->d_qx; out->d_qy = p->d_qy; out->d_qangle = p->d_qangle; out->d_qlevel = p->d_qlevel; out->d_qvalid = p->d_qvalid;
+    out->d_carryDesc = p->d_carryDesc;
+    out->plan = p;
+}
+
+// the pools a step of n images will use (allocated on first use), without enqueueing anything
+int bird_step_view(Ctx& c, int w, int h, int nfeatures, int n, BirdStepView* out)
+{
+    BirdPlan* p = get_plan(c, w, h, nfeatures, n);
+    if (!p) return ORBB200_ERR_CUDA;
+    const int rc = ensure_step_buffers(c, p);
+    if (rc != ORBB200_OK) return rc;
+    fill_step_view(p, out);
+    return ORBB200_OK;
+}
+
 int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t* d_imgs, size_t imgBytes, size_t stride, bool chain, BirdStepView* out)
 {
     BirdPlan* p = get_plan(c, w, h, nfeatures, n);
@@ -1912,10 +1931,7 @@ int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t*
         c.launches++;
     }
     ORBB200_CUDA_OK(c, cudaGetLastError());
-    out->d_kps = p->d_kps2; out->d_desc = p->d_desc; out->d_counts = p->d_counts2; out->kpPerImg = g.kpPerImg;
-    out->d_qx = p->d_qx; out->d_qy = p->d_qy; out->d_qangle = p->d_qangle; out->d_qlevel = p->d_qlevel; out->d_qvalid = p->d_qvalid;
-    out->d_carryDesc = p->d_carryDesc;
-    out->plan = p;
+    fill_step_view(p, out);
     return ORBB200_OK;
 }
 

@@ -129,6 +129,7 @@ struct BirdStepView {
     void* plan;
 };
 int bird_set_mask(Ctx& c, int w, int h, int nfeatures, int batch, const uint8_t* mask, size_t stride);
+int bird_step_view(Ctx& c, int w, int h, int nfeatures, int n, BirdStepView* out);
 int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t* d_imgs, size_t imgBytes, size_t stride, bool chain, BirdStepView* out);
 int bird_step_carry(Ctx& c, const BirdStepView& v, int n);
 int bird_step_status(Ctx& c);

@@ -87,6 +87,23 @@ def test_small_host_calls_one_graph_paths(pkg):
             _compare_extract(k, d, want[1][0], want[1][1], f"{w}x{h} strided single, call {rep}")
 
 
+def test_replayed_extraction_graph_on_a_changing_sequence(pkg):
+    """The replayed one-call graph (programmatic dependent launches, three branches, pinned mirror) on 24 different frames in a
+    row: nothing of frame k-1 may leak into frame k (a kernel that started before its predecessor had finished would read the
+    previous frame's pyramid, candidates or counters)."""
+    h, w = 188, 620
+    canvas = synth.synth_frame(h, w + 24 * 7 + 8, 4711)
+    orc = oracle.Extractor(800, 1.2, 8, 20, 7)
+    ex = pkg.ORBextractor(800, 1.2, 8, 20, 7, max_size=(w, h), max_batch=2)
+    for i in range(24):
+        img = np.ascontiguousarray(canvas[:, 7 * i:7 * i + w])
+        if i % 5 == 4:
+            img = np.ascontiguousarray(img[::-1])                     # a very different frame in between
+        k0, d0 = orc(img)
+        k, d = ex(img)
+        _compare_extract(k, d, k0, d0, f"frame {i}")
+
+
 @pytest.mark.parametrize("name", ["c1_752x480", "bird_400x400", "small_320x240"])
 def test_extract_vs_committed_golden(pkg, name):
     g = np.load(os.path.join(GOLDEN, f"extract_{name}.npz"))
