@@ -380,7 +380,9 @@ static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* h
         cudaEventRecord(c.evFork, c.stream);
         cudaStreamWaitEvent(c.stream2, c.evFork, 0);
         launch_border(c, n, c.stream2, false);
-        launch_blur(c, n, c.stream2, true);
+        // a full dependency, not a programmatic one: the border bytes share cache lines with pixels that FAST CTAs on the other branch
+        // may have pulled into an SM's L1 before border_kernel wrote them; only a kernel boundary is documented to drop such lines
+        launch_blur(c, n, c.stream2, false);
         cudaEventRecord(c.evJoin, c.stream2);
         launch_fast_levels(c, n, 1, g.nlevels, c.stream, true);
         launch_octree_levels(c, n, 1, g.nlevels, c.stream, true);

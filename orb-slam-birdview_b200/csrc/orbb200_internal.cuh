@@ -139,6 +139,10 @@ int bird_step_status(Ctx& c);
 // CTAs are scheduled while its predecessor drains, run their prologue (table loads, shared-memory set-up) and block in
 // griddepcontrol.wait until the predecessor grid has completed and its writes are visible.  Rule kept by every kernel launched this
 // way: nothing that another kernel of the chain writes or reads is touched before pdl_wait() (host-uploaded tables are fair game).
+// Second rule, learnt the hard way (profiles/r2c_summary.md): a programmatic edge is only used where every buffer the successor reads was
+// written ONCE, before anybody in the chain read it (pyramid levels, candidate slots, partial results).  Buffers that one kernel reads and
+// a later one partly rewrites (the birdview corner arrays through cornerSubPix, the border bytes next to pixels) keep full dependencies:
+// an SM's L1 may still hold the older line, and only a kernel boundary is documented to drop it.
 // Without the attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
