@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(NT) bird_select_kernel(BirdGeom g, const uint8
 // keypoint, output order = level-major, retainBest order inside a level.
 __global__ void __launch_bounds__(256) bird_finish_kernel(BirdGeom g, const uint8_t* __restrict__ pyr, const float4* __restrict__ lvlKp,
                                                           const int32_t* __restrict__ lvlCount, orbb200_kp_t* __restrict__ kps,
-                                                          int32_t* __restrict__ counts)
+                                                          int32_t* __restrict__ counts, float* __restrict__ pts)      // pts != nullptr: also the (x, y) list cornerSubPix refines
 {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
     const int gk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(256) bird_finish_kernel(BirdGeom g, const uint
         kp.octave = level;
         kp.class_id = -1;
         kps[(size_t)img * g.kpPerImg + gk] = kp;
+        if (pts) { pts[2 * ((size_t)img * g.kpPerImg + gk)] = kp.x; pts[2 * ((size_t)img * g.kpPerImg + gk) + 1] = kp.y; }
     }
 }
 
@@ -1279,13 +1280,18 @@ __global__ void __launch_bounds__(256) bird_queries_kernel(const orbb200_kp_t* _
 
 // ORB::compute on provided keypoints: KeyPointsFilter::runByImageBorder(kps, image size, 31) keeping the order, then a
 // stable regrouping by octave when the input is not sorted by level (orb.cpp detectAndCompute).  One CTA per image.
-__global__ void __launch_bounds__(256) bird_filter_kernel(BirdGeom g, const orbb200_kp_t* __restrict__ in, const int32_t* __restrict__ inCount,
-                                                          orbb200_kp_t* __restrict__ out, int32_t* __restrict__ outCount)
+// pts != nullptr: the keypoints' positions are taken from the refined (x, y) list (the fused pipelines skip the copy back into `in`).
+// NT: 256 in batches (one CTA per image, many images), 1024 for one or two images (the lone CTA's chunk loops are the latency).
+template <int NT>
+__global__ void __launch_bounds__(NT) bird_filter_kernel(BirdGeom g, const orbb200_kp_t* __restrict__ in, const int32_t* __restrict__ inCount,
+                                                         orbb200_kp_t* __restrict__ out, int32_t* __restrict__ outCount, const float* __restrict__ pts)
 {
-    __shared__ int sBase[BV_LEVELS + 1], sWarp[8], sSorted;
+    __shared__ int sBase[BV_LEVELS + 1], sWarp[NT / 32], sSorted;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = min(inCount[img], g.kpPerImg);
     const orbb200_kp_t* K = in + (size_t)img * g.kpPerImg;
+    const float* PT = pts ? pts + 2 * (size_t)img * g.kpPerImg : nullptr;
+    auto load = [&](int i) { orbb200_kp_t k = K[i]; if (PT) { k.x = PT[2 * i]; k.y = PT[2 * i + 1]; } return k; };
     orbb200_kp_t* O = out + (size_t)img * g.kpPerImg;
     auto keep = [&](const orbb200_kp_t& k) {
         if (g.h <= BV_EDGE * 2 || g.w <= BV_EDGE * 2) return false;
@@ -1295,13 +1301,13 @@ __global__ void __launch_bounds__(256) bird_filter_kernel(BirdGeom g, const orbb
     // sortedByLevel?
     if (tid == 0) sSorted = 1;
     __syncthreads();
-    for (int i = tid + 1; i < n; i += 256) if (K[i].octave < K[i - 1].octave) sSorted = 0;
+    for (int i = tid + 1; i < n; i += NT) if (K[i].octave < K[i - 1].octave) sSorted = 0;
     __syncthreads();
     const bool sorted = sSorted != 0;
     // pass 1: per-level counts of kept keypoints (one level "all" when already sorted)
     if (tid <= BV_LEVELS) sBase[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += 256) if (keep(K[i])) atomicAdd(&sBase[sorted ? 0 : K[i].octave], 1);
+    for (int i = tid; i < n; i += NT) { const orbb200_kp_t k = load(i); if (keep(k)) atomicAdd(&sBase[sorted ? 0 : k.octave], 1); }
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -1312,16 +1318,16 @@ __global__ void __launch_bounds__(256) bird_filter_kernel(BirdGeom g, const orbb
     // pass 2: stable scatter, chunks of 256 in order
     for (int l = 0; l < (sorted ? 1 : BV_LEVELS); l++) {
         int base = sBase[l];
-        for (int c0 = 0; c0 < n; c0 += 256) {
+        for (int c0 = 0; c0 < n; c0 += NT) {
             const int i = c0 + tid;
             orbb200_kp_t k;
             bool f = false;
-            if (i < n) { k = K[i]; f = keep(k) && (sorted || k.octave == l); }
+            if (i < n) { k = load(i); f = keep(k) && (sorted || k.octave == l); }
             const unsigned bal = __ballot_sync(0xffffffffu, f);
             if (lane == 0) sWarp[wid] = __popc(bal);
             __syncthreads();
             int before = 0, totalc = 0;
-            for (int w = 0; w < 8; w++) { if (w < wid) before += sWarp[w]; totalc += sWarp[w]; }
+            for (int w = 0; w < NT / 32; w++) { if (w < wid) before += sWarp[w]; totalc += sWarp[w]; }
             if (f) O[base + before + __popc(bal & ((1u << lane) - 1u))] = k;
             base += totalc;
             __syncthreads();
@@ -1630,7 +1636,7 @@ void enqueue_blur(Ctx& c, BirdPlan* p, int n, int nLevels, cudaStream_t stream)
 // forkBlur: the caller will run enqueue_compute on the same pyramid (detect + cornerSubPix + compute in one call).  For one or two
 // images the blurred pyramid -- which only compute's descriptors read and which depends on nothing but the pyramid -- is then
 // built on a side stream beside FAST, retainBest and cornerSubPix instead of after them.
-int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nullptr)
+int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nullptr, float* ptsOut = nullptr)
 {
     const BirdGeom& g = p->g;
     { StageTimer t(c, 9); enqueue_pyramid(c, p, n, maskMode == 1, BV_LEVELS); }
@@ -1659,7 +1665,7 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nu
         bird_select_kernel<SEL_THREADS_FEW><<<dim3(n, BV_LEVELS), SEL_THREADS_FEW, smem, c.stream>>>(
             g, p->d_pyr, mask, maskMode == 1 ? g.planeBytes : 0u, p->d_cand, p->d_candCount, p->d_lvlKp, p->d_lvlCount, c.d_status, BV_SORT_CAP, BV_SORT_CAP, 0, 0);
         c.launches++;
-        bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
+        bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts, ptsOut);
         c.launches++;
         ORBB200_CUDA_OK(c, cudaGetLastError());
         return ORBB200_OK;
@@ -1677,7 +1683,7 @@ int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nu
         if (t < 2) c.launches++;
     }
     c.launches++;
-    bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts);
+    bird_finish_kernel<<<dim3((g.kpPerImg + 7) / 8, n), 256, 0, c.stream>>>(g, p->d_pyr, p->d_lvlKp, p->d_lvlCount, p->d_kps, p->d_counts, ptsOut);
     c.launches++;
     ORBB200_CUDA_OK(c, cudaGetLastError());
     return ORBB200_OK;
@@ -1781,10 +1787,11 @@ int enqueue_subpix(Ctx& c, BirdPlan* p, int n, const int32_t* d_counts, int nFix
 }
 
 // d_kps/d_counts -> filtered into d_kps2/d_counts2, descriptors in d_desc
-int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels, bool blurForked = false)
+int enqueue_compute(Ctx& c, BirdPlan* p, int n, int nLevels, bool blurForked = false, const float* refinedPts = nullptr)
 {
     const BirdGeom& g = p->g;
-    bird_filter_kernel<<<n, 256, 0, c.stream>>>(g, p->d_kps, p->d_counts, p->d_kps2, p->d_counts2);
+    if (n <= 2) bird_filter_kernel<1024><<<n, 1024, 0, c.stream>>>(g, p->d_kps, p->d_counts, p->d_kps2, p->d_counts2, refinedPts);
+    else bird_filter_kernel<256><<<n, 256, 0, c.stream>>>(g, p->d_kps, p->d_counts, p->d_kps2, p->d_counts2, refinedPts);
     c.launches++;
     if (blurForked) {                               // enqueue_detect started it on the side stream
         cudaStreamWaitEvent(c.stream, c.evJoin4, 0);
@@ -1909,22 +1916,19 @@ int bird_step_enqueue(Ctx& c, int w, int h, int nfeatures, int n, const uint8_t*
         c.launches++;
     }
     bool blurForked = false;
-    rc = enqueue_detect(c, p, n, p->d_maskShared ? 2 : 0, &blurForked);
+    // (the detector writes the (x, y) list cornerSubPix refines, and compute's border filter reads the refined list: no copies between)
+    rc = enqueue_detect(c, p, n, p->d_maskShared ? 2 : 0, &blurForked, p->d_pts);
     if (rc != ORBB200_OK) return rc;
     {
         StageTimer t(c, 11);
-        bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
-        c.launches++;
         if (g.w >= 15 && g.h >= 15) {
             rc = enqueue_subpix(c, p, n, p->d_counts, 0, 5, 5, 40, 0.001);
             if (rc != ORBB200_OK) return rc;
         }
-        bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 1);
-        c.launches++;
     }
     {
         StageTimer t(c, 12);
-        rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked);
+        rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked, p->d_pts);
         if (rc != ORBB200_OK) return rc;
         bird_queries_kernel<<<dim3((g.kpPerImg + 255) / 256, n + 1), 256, 0, c.stream>>>(p->d_kps2, p->d_counts2, p->d_carryKps, p->d_carryCount, g.kpPerImg,
                                                                                         p->d_qx, p->d_qy, p->d_qangle, p->d_qlevel, p->d_qvalid);
@@ -2053,18 +2057,14 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     const BirdGeom& g = p->g;
     int rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
     bool blurForked = false;
-    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0, &blurForked);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0, &blurForked, p->d_pts);
     if (rc != ORBB200_OK) return rc;
     // cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001))   (src/Frame.cc:335-336)
-    bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 0);
-    c.launches++;
     if (g.w >= 15 && g.h >= 15) {
         rc = enqueue_subpix(c, p, n, p->d_counts, 0, 5, 5, 40, 0.001);
         if (rc != ORBB200_OK) return rc;
     }
-    bird_kps_to_pts_kernel<<<dim3((g.kpPerImg + 255) / 256, n), 256, 0, c.stream>>>(p->d_kps, p->d_pts, g.kpPerImg, p->d_counts, 1);
-    c.launches++;
-    rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked);
+    rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked, p->d_pts);
     if (rc != ORBB200_OK) return rc;
     return download(c, p, n, p->d_kps2, p->d_counts2, kps, desc, cap_per_img, n_out);
 }
