@@ -167,6 +167,7 @@ struct Ctx {
     struct FrameGraph { std::vector<uint8_t> key; int state; cudaGraphExec_t exec; long long launches; };
     std::vector<FrameGraph> frameGraphs;
     unsigned long long allocEpoch = 0, frameGraphEpoch = 0;
+    bool warpCands = true;                   // small matcher jobs scan their windows with one warp per query (ORBB200_NO_WARP_CANDS=1: one thread per query)
     bool stageMatch = true;                  // matcher calls upload / download through the pinned staging block in one copy each (ORBB200_NO_STAGED_MATCH=1: array by array)
     bool selectTiers = false;                // ORBB200_SELECT_TIERS=1: the tiered 256-thread retainBest launches also for one or two images (A/B)
     bool subpixGenericWarp = false;          // ORBB200_SUBPIX_GENERIC=1: the generic warp-per-corner cornerSubPix also for the 5x5 window (A/B)

@@ -370,6 +370,33 @@ __device__ __forceinline__ bool query_window(const WinJob& J, int q, Window& W)
     return true;
 }
 
+// The filters of a window candidate that depend neither on the loop-carried state nor on the descriptor (the modes without
+// "distance" semantics): blocked keypoints, the stereo-consistency test, Fuse's reprojection gate.
+__device__ __forceinline__ bool keypoint_passes(const WinJob& J, const FrameDev& F, int q, const Window& W, int mode, int idx, float kx, float ky, int octave)
+{
+    if (J.kp_blocked && J.kp_blocked[idx]) return false;
+    if (W.urCheck && F.uRight) {
+        const float ur = F.uRight[idx];
+        if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return false;
+    }
+    if (mode == WM_BEST && (J.flags & WF_CHI2)) {
+        // reprojection gate of Fuse (:913-936): 7.8 with a stereo observation, 5.99 without
+        const float ex = __fsub_rn(W.x, kx), ey = __fsub_rn(W.y, ky);
+        float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+        const float kpr = F.uRight ? F.uRight[idx] : -1.f;
+        if ((unsigned)octave >= (unsigned)J.nLevels) return false;  // keypoint outside the pyramid: no sigma to gate with
+        const float inv = J.invLevelSigma2[octave];
+        if (kpr >= 0) {
+            const float er = __fsub_rn(J.q_aux[q], kpr);
+            e2 = __fadd_rn(e2, __fmul_rn(er, er));
+            if ((double)__fmul_rn(e2, inv) > 7.8) return false;
+        } else {
+            if ((double)__fmul_rn(e2, inv) > 5.99) return false;
+        }
+    }
+    return true;
+}
+
 // Enumerate, in the reference's scan order, the candidates of query q that pass every filter which does not
 // depend on the loop-carried state, with their Hamming distance: visit(idx, dist, octave).
 template <class Visit>
@@ -390,28 +417,7 @@ __device__ __forceinline__ void static_candidates(const WinJob& J, const FrameDe
     }
     const bool distSem = is_dist_sem(mode);
     scan_window(F, W.x, W.y, W.r, W.minL, W.maxL, [&](int idx, const orbb200_kp_t& kp) {
-        if (!distSem) {
-            if (J.kp_blocked && J.kp_blocked[idx]) return;
-            if (W.urCheck && F.uRight) {
-                const float ur = F.uRight[idx];
-                if (ur > 0 && fabsf(__fsub_rn(W.urRef, ur)) > W.urTol) return;
-            }
-            if (mode == WM_BEST && (J.flags & WF_CHI2)) {
-                // reprojection gate of Fuse (:913-936): 7.8 with a stereo observation, 5.99 without
-                const float ex = __fsub_rn(W.x, kp.x), ey = __fsub_rn(W.y, kp.y);
-                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-                const float kpr = F.uRight ? F.uRight[idx] : -1.f;
-                if ((unsigned)kp.octave >= (unsigned)J.nLevels) return;  // keypoint outside the pyramid: no sigma to gate with
-                const float inv = J.invLevelSigma2[kp.octave];
-                if (kpr >= 0) {
-                    const float er = __fsub_rn(J.q_aux[q], kpr);
-                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
-                    if ((double)__fmul_rn(e2, inv) > 7.8) return;
-                } else {
-                    if ((double)__fmul_rn(e2, inv) > 5.99) return;
-                }
-            }
-        }
+        if (!distSem && !keypoint_passes(J, F, q, W, mode, idx, kp.x, kp.y, kp.octave)) return;
         const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
         visit(idx, hamming256(qa, qb, kd[0], kd[1]), kp.octave);
     });
@@ -438,6 +444,94 @@ __global__ void __launch_bounds__(WC_THREADS) window_cands_kernel(const WinJob* 
         });
     }
     ccount[q] = n;
+}
+
+// The same phase for a few calls (one frame per call: a few thousand queries on an otherwise idle GPU), ONE WARP per query.  A
+// thread-per-query scan is a chain of dependent L2 round trips -- cell bounds, items two at a time, per-keypoint flags, a 32-byte
+// descriptor per surviving item -- and the slowest thread sets the kernel's duration (40 us for 3000 map points).  Here the lanes take
+// 32 consecutive items of a column slice at once: one round trip for the items, one for the flags, one for the descriptors, and a
+// ballot appends the survivors in scan order (the list is the one the thread-per-query kernel writes).
+constexpr int WCW_WARPS = 8;
+
+__global__ void __launch_bounds__(WCW_WARPS * 32) window_cands_warp_kernel(const WinJob* __restrict__ jobs)
+{
+    const WinJob J = jobs[blockIdx.y];
+    const int q = blockIdx.x * WCW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= J.nq) return;                                  // whole warps leave together
+    const FrameDev F = *J.frame;
+    int* ccount = J.scratch + 2 * J.kpCap + 6 * J.nq;
+    int2* clist = reinterpret_cast<int2*>(J.scratch + win_clist_offset(J.kpCap, J.nq)) + (size_t)q * WM_LISTCAP;
+    const unsigned ltmask = (1u << lane) - 1u;
+    Window W;
+    int n = -1;     // skipped query
+    if (query_window(J, q, W)) {                            // (warp-uniform: every lane evaluates the same query)
+        n = 0;
+        const int mode = J.mode;
+        const uint4* qd = reinterpret_cast<const uint4*>(J.q_desc) + 2 * (size_t)q;
+        const uint4 qa = __ldg(qd), qb = __ldg(qd + 1);
+        auto append = [&](bool pass, int idx, int level) {
+            int d = 0;
+            if (pass) {
+                const uint4* kd = reinterpret_cast<const uint4*>(F.desc) + 2 * (size_t)idx;
+                d = hamming256(qa, qb, kd[0], kd[1]);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            const int pos = n + __popc(bal & ltmask);
+            if (pass && pos < WM_LISTCAP) clist[pos] = make_int2(idx, d | (level << 16));
+            n += __popc(bal);
+        };
+        if (is_bow(mode)) {
+            const int p0 = J.q_level[q], p1 = J.q_maxlevel[q];
+            for (int pb = p0; pb < p1; pb += 32) {
+                const int p = pb + lane;
+                const int idx = p < p1 ? J.cand_idx[p] : 0;
+                const bool pass = p < p1 && !(J.kp_blocked && J.kp_blocked[idx]);
+                append(pass, idx, 0);
+            }
+        } else {
+            // Frame::GetFeaturesInArea[Birdview] (reference src/Frame.cc:494-547, 891-944), as in scan_window
+            const float x = W.x, y = W.y, r = W.r;
+            const int minLevel = W.minL, maxLevel = W.maxL;
+            const bool distSem = is_dist_sem(mode);
+            const float fx = __fsub_rn(x, F.minX), fy = __fsub_rn(y, F.minY);
+            const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(fx, r), F.invW)));
+            const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(fx, r), F.invW)));
+            const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(fy, r), F.invH)));
+            const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(fy, r), F.invH)));
+            if (nMinCellX < GRID_COLS && nMaxCellX >= 0 && nMinCellY < GRID_ROWS && nMaxCellY >= 0) {
+                const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+                // the slice bounds of every column of the window in one round trip (lane = column; windows wider than 32 columns loop)
+                for (int ixb = nMinCellX; ixb <= nMaxCellX; ixb += 32) {
+                    const int myIx = ixb + lane;
+                    int myB = 0, myE = 0;
+                    if (myIx <= nMaxCellX) { myB = F.cellStart[myIx * GRID_ROWS + nMinCellY]; myE = F.cellStart[myIx * GRID_ROWS + nMaxCellY + 1]; }
+                    const int ncol = min(32, nMaxCellX - ixb + 1);
+                    for (int cidx = 0; cidx < ncol; cidx++) {
+                        const int b = __shfl_sync(0xffffffffu, myB, cidx), e = __shfl_sync(0xffffffffu, myE, cidx);
+                        for (int kb = b; kb < e; kb += 32) {
+                            const int k = kb + lane;
+                            bool pass = k < e;
+                            int idx = 0, octave = 0;
+                            if (pass) {
+                                const int4 it = F.cellKp[k];
+                                const float kx = __int_as_float(it.x), ky = __int_as_float(it.y);
+                                octave = it.z; idx = it.w;
+                                if (bCheckLevels) {
+                                    if (octave < minLevel) pass = false;
+                                    if (maxLevel >= 0 && octave > maxLevel) pass = false;
+                                }
+                                const float dx = __fsub_rn(kx, x), dy = __fsub_rn(ky, y);
+                                if (!(fabsf(dx) < r && fabsf(dy) < r)) pass = false;
+                                if (pass && !distSem && !keypoint_passes(J, F, q, W, mode, idx, kx, ky, octave)) pass = false;
+                            }
+                            append(pass, idx, octave);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) ccount[q] = n;
 }
 
 __global__ void __launch_bounds__(WM_THREADS) window_match_kernel(const WinJob* __restrict__ jobs, int smemInts)
@@ -629,8 +723,12 @@ void launch_window_match(Ctx& c, const WinJob* d_jobs, int njobs, int maxNq, int
     if (smem > WM_SMEM_MAX) smem = 0;
     if (smem > 48 * 1024 && smem > ensure_max_dynamic_smem(c.device, (const void*)window_match_kernel, SMEM_WINDOW_MATCH)) smem = 0;
     if (maxNq > 0) {
-        dim3 grid((maxNq + WC_THREADS - 1) / WC_THREADS, njobs);
-        window_cands_kernel<<<grid, WC_THREADS, 0, c.stream>>>(d_jobs);
+        if (c.warpCands && (long long)maxNq * njobs <= 32768) {     // a few calls: one warp per query (see window_cands_warp_kernel)
+            window_cands_warp_kernel<<<dim3((maxNq + WCW_WARPS - 1) / WCW_WARPS, njobs), WCW_WARPS * 32, 0, c.stream>>>(d_jobs);
+        } else {
+            dim3 grid((maxNq + WC_THREADS - 1) / WC_THREADS, njobs);
+            window_cands_kernel<<<grid, WC_THREADS, 0, c.stream>>>(d_jobs);
+        }
         c.launches++;
     }
     window_match_kernel<<<njobs, WM_THREADS, smem, c.stream>>>(d_jobs, (int)(smem / sizeof(int)));
