@@ -165,9 +165,14 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
     __shared__ int sCnt[GRID_CELLS];
     __shared__ int warpTot[32];
     __shared__ int sTotal;                  // keypoints that fell inside the grid (<= n: PosInGrid rejects the rest)
+    // the per-cell item lists are put in order by insertion sorts: chains of dependent reads and writes, in shared memory when the
+    // frame's keypoints fit (they do for every extractor budget in use), in the global list otherwise
+    constexpr int GB_SMEM_ITEMS = 6144;
+    __shared__ int sItems[GB_SMEM_ITEMS];
     const FrameDev F = frames[blockIdx.x];
     const int n = frame_count(F);
     const int tid = threadIdx.x;
+    int* const items = n <= GB_SMEM_ITEMS ? sItems : F.cellItems;
     for (int i = tid; i < GRID_CELLS; i += 1024) sCnt[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
@@ -199,17 +204,17 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         const int cid = grid_cell_of(F, F.kps[i]);
-        if (cid >= 0) F.cellItems[atomicAdd(&sCnt[cid], 1)] = i;
+        if (cid >= 0) items[atomicAdd(&sCnt[cid], 1)] = i;
     }
     __syncthreads();
     // restore ascending index order inside each cell (lists are a few items long)
     for (int cidx = tid; cidx < GRID_CELLS; cidx += 1024) {
-        const int b = F.cellStart[cidx], e = sCnt[cidx];
+        const int e = sCnt[cidx], b = cidx ? sCnt[cidx - 1] : 0;      // after the scatter sCnt[c] is the end of cell c = the start of cell c + 1
         for (int i = b + 1; i < e; i++) {
-            const int key = F.cellItems[i];
+            const int key = items[i];
             int j = i - 1;
-            while (j >= b && F.cellItems[j] > key) { F.cellItems[j + 1] = F.cellItems[j]; j--; }
-            F.cellItems[j + 1] = key;
+            while (j >= b && items[j] > key) { items[j + 1] = items[j]; j--; }
+            items[j + 1] = key;
         }
     }
     __syncthreads();
@@ -217,7 +222,8 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const FrameDev* __rest
     // (only the sTotal items the CSR holds: cellItems beyond them is unwritten memory)
     const int nItems = sTotal;
     for (int k = tid; k < nItems; k += 1024) {
-        const int idx = F.cellItems[k];
+        const int idx = items[k];
+        if (items != F.cellItems) F.cellItems[k] = idx;
         const orbb200_kp_t kp = F.kps[idx];
         F.cellKp[k] = make_int4(__float_as_int(kp.x), __float_as_int(kp.y), kp.octave, idx);
     }
