@@ -385,6 +385,9 @@ static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* h
         launch_blur(c, n, c.stream2, false);
         cudaEventRecord(c.evJoin, c.stream2);
         launch_fast_levels(c, n, 1, g.nlevels, c.stream, true);
+        if (std::getenv("ORBB200_OCTREE_PER_LEVEL")) {       // profiling aid: one launch per level (per-level durations under ncu)
+            for (int l = 1; l < g.nlevels; l++) launch_octree_levels(c, n, l, l + 1, c.stream, false);
+        } else
         launch_octree_levels(c, n, 1, g.nlevels, c.stream, true);
         cudaStreamWaitEvent(c.stream, c.evJoin0, 0);
         cudaStreamWaitEvent(c.stream, c.evJoin, 0);
