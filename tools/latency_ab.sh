@@ -9,7 +9,10 @@ for k in "" "ORBB200_NO_HOST_GRAPH=1" "ORBB200_NO_PDL=1" "ORBB200_NO_SPLIT=1" "O
     echo "{\"probe\": \"call_timeline\", \"knobs\": \"$k\", \"result\": $(env $k tools/ubench/call_timeline $shape $R)}"
   done
 done
-for k in "" "ORBB200_NO_FRAME_GRAPH=1" "ORBB200_SELECT_TIERS=1" "ORBB200_SUBPIX_GENERIC=1" \
-         "ORBB200_NO_FRAME_GRAPH=1 ORBB200_SELECT_TIERS=1 ORBB200_SUBPIX_GENERIC=1 ORBB200_NO_HOST_GRAPH=1 ORBB200_NO_PDL=1 ORBB200_NO_SPLIT=1 ORBB200_NO_OCTREE_SMEM=1"; do
+for k in "" "ORBB200_NO_FRAME_GRAPH=1" "ORBB200_SELECT_TIERS=1" "ORBB200_SUBPIX_GENERIC=1" "ORBB200_NO_WARP_CANDS=1" \
+         "ORBB200_NO_FRAME_GRAPH=1 ORBB200_SELECT_TIERS=1 ORBB200_SUBPIX_GENERIC=1 ORBB200_NO_WARP_CANDS=1 ORBB200_NO_HOST_GRAPH=1 ORBB200_NO_PDL=1 ORBB200_NO_SPLIT=1 ORBB200_NO_OCTREE_SMEM=1"; do
   echo "{\"probe\": \"frame_timeline\", \"knobs\": \"$k\", \"result\": $(env $k tools/ubench/frame_timeline $R)}"
+done
+for k in "" "ORBB200_NO_WARP_CANDS=1" "ORBB200_NO_STAGED_MATCH=1" "ORBB200_NO_WARP_CANDS=1 ORBB200_NO_STAGED_MATCH=1"; do
+  echo "{\"probe\": \"matcher_latency\", \"knobs\": \"$k\", \"result\": $(env $k python tools/matcher_latency.py $R | tail -1)}"
 done
