@@ -1234,16 +1234,6 @@ __global__ void __launch_bounds__(S5_THREADS, MINB) bird_subpix5_kernel(const S5
     }
 }
 
-__global__ void bird_kps_to_pts_kernel(const orbb200_kp_t* __restrict__ kps, float* __restrict__ pts, int kpPerImg, const int32_t* __restrict__ counts,
-                                       int toKps)
-{
-    const int img = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counts[img]) return;
-    orbb200_kp_t* k = const_cast<orbb200_kp_t*>(kps) + (size_t)img * kpPerImg + i;
-    float* p = pts + ((size_t)img * kpPerImg + i) * 2;
-    if (toKps) { k->x = p[0]; k->y = p[1]; } else { p[0] = k->x; p[1] = k->y; }
-}
-
 // n device-resident images (rows of `stride` bytes, image i at imgs + i*imgBytes) into level 0 of the planes
 __global__ void __launch_bounds__(128) bird_import_kernel(const uint8_t* __restrict__ imgs, size_t imgBytes, size_t stride, uint8_t* __restrict__ pyr,
                                                           unsigned planeBytes, BirdLevel L0)
