@@ -87,6 +87,10 @@ int orbb200_pyramid_level(orbb200_ctx* ctx, int img_index, int level, int blurre
  * ORBextractor shim fills mvImagePyramid with (cv::Mat headers over the mirror, no per-level copies). */
 int orbb200_pyramid_mirror(orbb200_ctx* ctx, int img_index, int blurred, const uint8_t** level_ptr /*[nlevels]*/,
                            size_t* level_pitch /*[nlevels]*/, int* level_w /*[nlevels]*/, int* level_h /*[nlevels]*/);
+/* mvImagePyramid without a copy: after orbb200_set_pyramid_mirror(ctx, 1), an orbb200_extract of one or two staged images also stores
+ * image 0's levels into the pinned mirror from the kernels that produce them, and the next orbb200_pyramid_mirror(ctx, 0, 0, ...) returns
+ * the level pointers without copying or synchronising (include/ORBextractor.h:85, read by Frame::ComputeStereoMatches). */
+int orbb200_set_pyramid_mirror(orbb200_ctx* ctx, int enable);
 /* Debug/inspection: FAST candidates of one level as packed (x,y,response) int32 triples in region
  * coordinates, unordered.  Returns the count (or a negative status). */
 int orbb200_level_candidates(orbb200_ctx* ctx, int img_index, int level, int32_t* xyr, int cap);

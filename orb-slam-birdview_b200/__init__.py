@@ -58,6 +58,7 @@ _SIGNATURES = {
     "orbb200_download_results": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "orbb200_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "orbb200_pyramid_mirror": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbb200_set_pyramid_mirror": (_i, [_vp, _i]),
     "orbb200_level_candidates": (_i, [_vp, _i, _i, _vp, _i]),
     "orbb200_hamming_knn2": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "orbb200_distinctive_descriptors": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

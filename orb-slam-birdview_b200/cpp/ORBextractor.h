@@ -67,6 +67,7 @@ public:
         kpbuf.resize(cap);
         descbuf.resize((size_t)cap * 32);
         int n = 0;
+        if (bDownloadPyramid != bMirrorSet) { check(orbb200_set_pyramid_mirror(ctx, bDownloadPyramid ? 1 : 0)); bMirrorSet = bDownloadPyramid; }
         check(orbb200_extract(ctx, image.ptr(0), image.cols, image.rows, image.step,
                               reinterpret_cast<orbb200_kp_t*>(kpbuf.data()), descbuf.data(), cap, &n));
         if (n == 0)
@@ -130,6 +131,7 @@ protected:
             fprintf(stderr, "ORBextractor (orbb200): %s\n", orbb200_last_error(nullptr));
             exit(-1);
         }
+        bMirrorSet = false;
     }
     void check(int rc) { if (rc != ORBB200_OK) die(orbb200_last_error(ctx)); }
     void die(const char* what) { fprintf(stderr, "ORBextractor (orbb200): %s\n", what); abort(); }
@@ -148,6 +150,7 @@ protected:
     orbb200_ctx* ctx = nullptr;
     int ctxW = 0, ctxH = 0, device = 0;
     bool bDownloadPyramid = true;
+    bool bMirrorSet = false;         // what the context was last told (orbb200_set_pyramid_mirror); a new context starts with "off"
     std::vector<cv::KeyPoint> kpbuf;
     std::vector<unsigned char> descbuf;
 };

@@ -369,14 +369,15 @@ static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* h
     const Geom& g = c.cur->g;
     const HostMirror* mirror = hs ? &hs->mirror : nullptr;
     launch_clear_counters(c, n);
-    if (hs) launch_import_host(c, hs->imgs, hs->imgBytes, hs->rowBytes, n);
+    uint8_t* hostPyr = hs ? hs->hostPyr : nullptr;
+    if (hs) launch_import_host(c, hs->imgs, hs->imgBytes, hs->rowBytes, n, hostPyr);
     if (fork && n <= 2 && c.splitLevel0 && !c.fastCells && c.cur->nFastGroups > 0 && g.nlevels > 1) {
         cudaEventRecord(c.evFork0, c.stream);
         cudaStreamWaitEvent(c.stream3, c.evFork0, 0);
         launch_fast_levels(c, n, 0, 1, c.stream3, false);
         launch_octree_levels(c, n, 0, 1, c.stream3, true);
         cudaEventRecord(c.evJoin0, c.stream3);
-        launch_resizes(c, n, c.stream);
+        launch_resizes(c, n, c.stream, hostPyr);
         cudaEventRecord(c.evFork, c.stream);
         cudaStreamWaitEvent(c.stream2, c.evFork, 0);
         launch_border(c, n, c.stream2, false);
@@ -394,7 +395,7 @@ static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* h
         launch_describe(c, n, false, mirror);
         return;
     }
-    { StageTimer t(c, 1); launch_pyramid(c, n); }   // includes the border fill
+    { StageTimer t(c, 1); launch_pyramid(c, n, hostPyr); }   // includes the border fill
     if (fork) {
         cudaEventRecord(c.evFork, c.stream);
         cudaStreamWaitEvent(c.stream2, c.evFork, 0);
@@ -422,6 +423,7 @@ static void enqueue_extract_kernels(Ctx& c, int n, bool fork, const HostStage* h
 static int run_extract(Ctx& c, int n, const HostStage* hs = nullptr)
 {
     c.stereoValid = false;
+    c.pyrMirrorFresh = nullptr;
     if (c.timing || !c.useGraphs) {
         enqueue_extract_kernels(c, n, !c.timing && c.forkBlur, hs);
         ORBB200_CUDA_OK(c, cudaGetLastError());
@@ -435,7 +437,7 @@ static int run_extract(Ctx& c, int n, const HostStage* hs = nullptr)
         }
     }
     ShapeTables* st = const_cast<ShapeTables*>(c.cur);
-    const int key = hs ? n + 65536 : n;
+    const int key = hs ? n + 65536 + (hs->hostPyr ? 131072 : 0) : n;
     auto it = st->graphs.find(key);
     if (it != st->graphs.end() && hs && it->second.stage != hs->imgs) {       // the pinned block was reallocated since the capture
         cudaGraphExecDestroy(it->second.exec);
@@ -788,6 +790,21 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
         hs.mirror.kps = reinterpret_cast<orbb200_kp_t*>(hm + 64 + cntB);
         hs.mirror.desc = hm + 64 + cntB + (size_t)n * kpi * sizeof(orbb200_kp_t);
         hs.mirror.d_status = c.d_status;
+        hs.hostPyr = nullptr;
+        if (c.mirrorPyramid) {                      // the drop-in's mvImagePyramid: image 0's levels straight into the pinned mirror
+            if (c.h_pyrMirrorBytes < c.gmax.pyrBytes) {
+                c.allocEpoch++;
+                ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+                if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
+                c.h_pyrMirror = nullptr; c.h_pyrMirrorBytes = 0;
+                ORBB200_CUDA_OK(c, cudaMallocHost((void**)&c.h_pyrMirror, c.gmax.pyrBytes));
+                c.h_pyrMirrorBytes = c.gmax.pyrBytes;
+                for (auto& kv : c.shapes)           // recordings that point at the old mirror
+                    for (auto it = kv.second.graphs.begin(); it != kv.second.graphs.end();)
+                        if (it->first >= 65536 + 131072) { cudaGraphExecDestroy(it->second.exec); it = kv.second.graphs.erase(it); } else ++it;
+            }
+            hs.hostPyr = c.h_pyrMirror;
+        }
         for (int i = 0; i < n; i++) {
             uint8_t* dst = c.h_scratch + STAGE_H2D_OFF + (size_t)i * hs.imgBytes;
             if (stride == (size_t)w && rowB == w) memcpy(dst, imgs[i], imgB);
@@ -796,6 +813,7 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
         int rc = run_extract(c, n, &hs);
         if (rc != ORBB200_OK) return rc;
         ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        if (hs.hostPyr) c.pyrMirrorFresh = c.cur;
         if (*hs.mirror.status != 0) {
             cudaMemsetAsync(c.d_status, 0, sizeof(int32_t), c.stream);
             c.err = "device-side overflow in octree distribution (status " + std::to_string(*hs.mirror.status) + ")";
@@ -872,14 +890,19 @@ int orbb200_pyramid_mirror(orbb200_ctx* ctx, int img_index, int blurred, const u
     if (!c.cur || img_index < 0 || img_index >= c.curN || !level_ptr || !level_pitch) { c.err = "pyramid_mirror: bad argument"; return ORBB200_ERR_ARG; }
     const Geom& g = c.cur->g;
     if (c.h_pyrMirrorBytes < g.pyrBytes) {
+        c.allocEpoch++;
         if (c.h_pyrMirror) cudaFreeHost(c.h_pyrMirror);
         c.h_pyrMirror = nullptr; c.h_pyrMirrorBytes = 0;
+        c.pyrMirrorFresh = nullptr;
         ORBB200_CUDA_OK(c, cudaMallocHost((void**)&c.h_pyrMirror, c.gmax.pyrBytes));
         c.h_pyrMirrorBytes = c.gmax.pyrBytes;
     }
-    const uint8_t* src = (blurred ? c.d_blur : c.d_pyr) + (size_t)img_index * g.pyrBytes;
-    ORBB200_CUDA_OK(c, cudaMemcpyAsync(c.h_pyrMirror, src, g.pyrBytes, cudaMemcpyDeviceToHost, c.stream));
-    ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    if (!(c.pyrMirrorFresh == c.cur && img_index == 0 && !blurred)) {       // (else the extraction's kernels have already written it: orbb200_set_pyramid_mirror)
+        const uint8_t* src = (blurred ? c.d_blur : c.d_pyr) + (size_t)img_index * g.pyrBytes;
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(c.h_pyrMirror, src, g.pyrBytes, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        c.pyrMirrorFresh = nullptr;
+    }
     for (int l = 0; l < c.nlevels; l++) {
         const LevelGeom& L = g.lv[l];
         level_ptr[l] = (L.w > 0 && L.h > 0) ? c.h_pyrMirror + L.off : nullptr;
@@ -887,6 +910,13 @@ int orbb200_pyramid_mirror(orbb200_ctx* ctx, int img_index, int blurred, const u
         if (level_w) level_w[l] = L.w;
         if (level_h) level_h[l] = L.h;
     }
+    return ORBB200_OK;
+}
+
+int orbb200_set_pyramid_mirror(orbb200_ctx* ctx, int enable)
+{
+    CTX_ENTER(ctx);
+    c.mirrorPyramid = enable != 0;
     return ORBB200_OK;
 }
 

@@ -155,6 +155,8 @@ struct Ctx {
     size_t h_scratch_bytes = 0;
     uint8_t* h_pyrMirror = nullptr;          // pinned copy of one image's pyramid block (orbb200_pyramid_mirror)
     size_t h_pyrMirrorBytes = 0;
+    bool mirrorPyramid = false;              // orbb200_set_pyramid_mirror: small host calls also deliver image 0's pyramid to the pinned mirror
+    const ShapeTables* pyrMirrorFresh = nullptr;   // shape of the extraction whose pyramid the mirror currently holds (null: stale)
     uint8_t* d_step = nullptr;               // device staging of the host step (images, queries, results)
     size_t d_step_bytes = 0;
 

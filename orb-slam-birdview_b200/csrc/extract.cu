@@ -41,8 +41,10 @@ __global__ void __launch_bounds__(256) import_kernel(const uint8_t* __restrict__
 // The same for a small host call: the images sit in the context's pinned staging block (rows padded to 16 bytes by the host
 // memcpy) and this kernel reads them over PCIe itself, 16 bytes per lane, so that the upload is a node of the extraction graph
 // instead of a copy-engine operation in front of it.
+// hostPyr != nullptr: image 0's levels are also stored into a pinned mirror of its pyramid block (the drop-in's mvImagePyramid), by the
+// kernels that produce them: posted 16-byte / 4-byte stores over PCIe beside the device stores, no copy afterwards.
 __global__ void __launch_bounds__(128) import_host_kernel(const uint8_t* __restrict__ src, unsigned imgBytes, int rowVec, int nVec,
-                                                          uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned off0, int pitch)
+                                                          uint8_t* __restrict__ pyr, unsigned pyrBytes, unsigned off0, int pitch, uint8_t* __restrict__ hostPyr)
 {
     const int img = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_launch_dependents();
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(128) import_host_kernel(const uint8_t* __restr
     const int r = i / rowVec, k = i - r * rowVec;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)img * imgBytes) + i);
     *reinterpret_cast<uint4*>(pyr + (size_t)img * pyrBytes + off0 + (size_t)r * pitch + 16 * k) = v;     // the row padding absorbs the tail
+    if (hostPyr && img == 0) *reinterpret_cast<uint4*>(hostPyr + off0 + (size_t)r * pitch + 16 * k) = v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -93,7 +96,7 @@ template <bool NARROW>
 __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict__ pyr, unsigned pyrBytes, LevelGeom src, LevelGeom dst,
                                                             const int2* __restrict__ xtab, const int4* __restrict__ ytab,
                                                             const int4* __restrict__ tiles, int nTiles, int smemPitch, int smemRows,
-                                                            const CUtensorMap* __restrict__ srcMap)
+                                                            const CUtensorMap* __restrict__ srcMap, uint8_t* __restrict__ hostPyr)
 {
     // The source footprint of the tile is staged in shared memory, so the interpolation reads never wait on global
     // memory: one TMA box (cp.async.bulk.tensor.3d of smemPitch x smemRows bytes from the source level, its first column
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
     const int tid = threadIdx.x;
     const uint8_t* S = pyr + (size_t)img * pyrBytes + src.off;
     uint8_t* D = pyr + (size_t)img * pyrBytes + dst.off;
+    uint8_t* HD = (hostPyr && img == 0) ? hostPyr + dst.off : nullptr;      // pinned mirror of image 0's pyramid block (see import_host_kernel)
     const int x4 = x0 + 4 * (tid & 31);
     int2 xt[4];
 #pragma unroll
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(RS_THREADS) resize_kernel(uint8_t* __restrict_
         for (int i = 0; i < 4; i++) v[i] = (__umulhi(bz, ha[i]) + __umulhi(bw, hb[i]) + 2u) >> 2;     // <= 255
         const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         *reinterpret_cast<uint32_t*>(D + doff) = out;                     // row padding absorbs the tail
+        if (HD) *reinterpret_cast<uint32_t*>(HD + doff) = out;
         doff += (unsigned)dst.pitch;
     }
 }
@@ -1546,7 +1551,7 @@ void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t strid
     c.launches++;
 }
 
-void launch_resizes(Ctx& c, int n, cudaStream_t stream)
+void launch_resizes(Ctx& c, int n, cudaStream_t stream, uint8_t* hostPyr)
 {
     const Geom& g = c.cur->g;
     const ShapeTables& st = *c.cur;
@@ -1558,7 +1563,7 @@ void launch_resizes(Ctx& c, int n, cudaStream_t stream)
         // level 1 follows the import kernel or an upload (a full dependency either way); levels >= 2 follow a resize_kernel
         launch_chain(c.pdl && l > 1, st.resizeNarrow[l] ? resize_kernel<true> : resize_kernel<false>, grid, dim3(RS_THREADS), smem, stream, c.d_pyr,
                      g.pyrBytes, g.lv[l - 1], d, st.d_xtab, st.d_ytab, st.d_resizeTiles + 2 * st.resizeTileBase[l], st.resizeTileCount[l],
-                     st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr);
+                     st.resizeSmemPitch[l], st.resizeSmemRows[l], st.resizeMapOk[l] ? st.d_rmaps + l : nullptr, hostPyr);
         c.launches++;
     }
 }
@@ -1571,9 +1576,9 @@ void launch_border(Ctx& c, int n, cudaStream_t stream, bool afterKernel)
     c.launches++;
 }
 
-void launch_pyramid(Ctx& c, int n)
+void launch_pyramid(Ctx& c, int n, uint8_t* hostPyr)
 {
-    launch_resizes(c, n, c.stream);
+    launch_resizes(c, n, c.stream, hostPyr);
     launch_border(c, n, c.stream, c.cur->g.nlevels > 1);
 }
 
@@ -1736,11 +1741,11 @@ void launch_describe(Ctx& c, int n, bool afterKernel, const HostMirror* mirror)
 }
 
 // n images of rowBytes-pitched rows (a multiple of 16) in pinned host memory -> level 0 of the pyramid pool
-void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n)
+void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n, uint8_t* hostPyr)
 {
     const Geom& g = c.cur->g;
     const int rowVec = rowBytes / 16, nVec = rowVec * g.h;
-    import_host_kernel<<<dim3((nVec + 127) / 128, n), 128, 0, c.stream>>>(h_imgs, (unsigned)imgBytes, rowVec, nVec, c.d_pyr, g.pyrBytes, g.lv[0].off, g.lv[0].pitch);
+    import_host_kernel<<<dim3((nVec + 127) / 128, n), 128, 0, c.stream>>>(h_imgs, (unsigned)imgBytes, rowVec, nVec, c.d_pyr, g.pyrBytes, g.lv[0].off, g.lv[0].pitch, hostPyr);
     c.launches++;
 }
 

@@ -163,9 +163,9 @@ inline cudaError_t launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 grid, d
 // Level ranges [l0, l1) and the stream are explicit so that, for one or two images, level 0 (no resize needed) can run FAST + octree
 // on a side branch of the graph while the other levels are still being built.
 void launch_import(Ctx& c, const uint8_t* d_imgs, size_t img_bytes, size_t stride, int n);
-void launch_resizes(Ctx& c, int n, cudaStream_t stream);
+void launch_resizes(Ctx& c, int n, cudaStream_t stream, uint8_t* hostPyr = nullptr);
 void launch_border(Ctx& c, int n, cudaStream_t stream, bool afterKernel);
-void launch_pyramid(Ctx& c, int n);
+void launch_pyramid(Ctx& c, int n, uint8_t* hostPyr = nullptr);
 void launch_blur(Ctx& c, int n, cudaStream_t stream, bool afterKernel = false);
 void launch_clear_counters(Ctx& c, int n);       // zeroes the per-level candidate counters: once per extraction, before any FAST launch
 void launch_fast(Ctx& c, int n, bool afterKernel = false);
@@ -176,9 +176,9 @@ void launch_octree_levels(Ctx& c, int n, int l0, int l1, cudaStream_t stream, bo
 // copy-engine operation follows the graph.  All null: device pools only.
 struct HostMirror { orbb200_kp_t* kps; uint8_t* desc; int32_t* counts; int32_t* status; const int32_t* d_status; };
 // A small host call staged in pinned memory: n images of rowBytes-pitched rows in, results out through `mirror`.
-struct HostStage { const uint8_t* imgs; size_t imgBytes; int rowBytes; HostMirror mirror; };
+struct HostStage { const uint8_t* imgs; size_t imgBytes; int rowBytes; HostMirror mirror; uint8_t* hostPyr; };   // hostPyr: pinned mirror of image 0's pyramid block or null
 void launch_describe(Ctx& c, int n, bool afterKernel = false, const HostMirror* mirror = nullptr);
-void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n);
+void launch_import_host(Ctx& c, const uint8_t* h_imgs, size_t imgBytes, int rowBytes, int n, uint8_t* hostPyr = nullptr);
 size_t octree_smem_bytes(int maxNodes, int smemCand = 0);
 void launch_stereo(Ctx& c, int n_frames, int left0, int right0, int strideImgs, float mb, float mbf, const float* d_invScale, int32_t* d_nKept);
 
