@@ -34,6 +34,19 @@ int main(int argc, char** argv)
     const int pw = extractor.mvImagePyramid[1].cols, ph = extractor.mvImagePyramid[1].rows;
     fwrite(&pw, 4, 1, o); fwrite(&ph, 4, 1, o);
     for (int y = 0; y < ph; y++) fwrite(extractor.mvImagePyramid[1].ptr(y), 1, pw, o);
+    // ORBB200_SHIM_DUMP_PYRAMID=<file>: every level of mvImagePyramid as {w, h, rows} (the pinned mirror the extraction's kernels fill)
+    if (const char* pf = getenv("ORBB200_SHIM_DUMP_PYRAMID")) {
+        FILE* po = fopen(pf, "wb");
+        const int nl = (int)extractor.mvImagePyramid.size();
+        fwrite(&nl, 4, 1, po);
+        for (int l = 0; l < nl; l++) {
+            const cv::Mat& m = extractor.mvImagePyramid[l];
+            const int lw = m.cols, lh = m.rows;
+            fwrite(&lw, 4, 1, po); fwrite(&lh, 4, 1, po);
+            for (int y = 0; y < lh; y++) fwrite(m.ptr(y), 1, lw, po);
+        }
+        fclose(po);
+    }
     if (argc >= 12) {
         const int bw = atoi(argv[10]), bh = atoi(argv[11]);
         std::vector<unsigned char> bimg((size_t)bw * bh), bmask((size_t)bw * bh);

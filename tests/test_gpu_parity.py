@@ -435,6 +435,24 @@ def test_cpp_shim(pkg, tmp_path):
     pw, ph = np.frombuffer(buf, np.int32, 2, off)
     lvl1 = np.frombuffer(buf, np.uint8, pw * ph, off + 8).reshape(ph, pw)
     assert np.array_equal(lvl1, orc.level_image(1))          # mvImagePyramid[1]
+    # every level of mvImagePyramid (written into the pinned mirror by the extraction's own kernels), also for a width that is not a
+    # multiple of 16 (the staged rows are padded) and after a second call on the same extractor
+    for (h, w, nf, seed) in ((480, 752, 1000, 1000), (376, 1241, 2000, 5)):
+        im = synth.synth_frame(h, w, seed)
+        im.tofile(raw)
+        pyr = tmp_path / "pyr.bin"
+        subprocess.run([drv, str(raw), str(w), str(h), str(nf), "20", "7", str(out)], check=True, timeout=120,
+                       env=dict(os.environ, ORBB200_SHIM_DUMP_PYRAMID=str(pyr)))
+        pb = open(pyr, "rb").read()
+        o2 = oracle.Extractor(nf, 1.2, 8, 20, 7)
+        o2(im)
+        nl, pos = int(np.frombuffer(pb, np.int32, 1)[0]), 4
+        assert nl == 8
+        for lvl in range(nl):
+            lw, lh = (int(v) for v in np.frombuffer(pb, np.int32, 2, pos))
+            got = np.frombuffer(pb, np.uint8, lw * lh, pos + 8).reshape(lh, lw)
+            pos += 8 + lw * lh
+            assert np.array_equal(got, o2.level_image(lvl)), (w, h, lvl)
 
 
 def test_cpp_matcher_shim(pkg, tmp_path):
