@@ -471,6 +471,15 @@ static int run_extract(Ctx& c, int n, const HostStage* hs = nullptr)
     return ORBB200_OK;
 }
 
+// after the stream has drained: copy staged results of a small host-buffer frame step into the caller's buffers
+void deliver_host_copies(Ctx& c)
+{
+    for (const Ctx::HostCopy& h : c.hostCopies)
+        for (size_t r = 0; r < h.rows; r++)
+            memcpy(static_cast<uint8_t*>(h.dst) + r * h.dpitch, static_cast<const uint8_t*>(h.src) + r * h.width, h.width);
+    c.hostCopies.clear();
+}
+
 static int check_status(Ctx& c)
 {
     int32_t st = 0;
@@ -652,14 +661,6 @@ void orbb200_destroy(orbb200_ctx* ctx)
 
 const char* orbb200_last_error(const orbb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
 
-// after the stream has drained: copy staged results of a small host-buffer frame step into the caller's buffers
-static void deliver_host_copies(Ctx& c)
-{
-    for (const Ctx::HostCopy& h : c.hostCopies)
-        for (size_t r = 0; r < h.rows; r++)
-            memcpy(static_cast<uint8_t*>(h.dst) + r * h.dpitch, static_cast<const uint8_t*>(h.src) + r * h.width, h.width);
-    c.hostCopies.clear();
-}
 
 int orbb200_sync(orbb200_ctx* ctx)
 {
@@ -707,8 +708,6 @@ int orbb200_extract_device(orbb200_ctx* ctx, const uint8_t* d_imgs, size_t img_b
 // status word, the counts and the keypoint / descriptor rows are four asynchronous copies behind ONE synchronisation, and only the
 // n_out[i] valid records of each image are then copied into the caller's (pageable) buffers.  Copies straight into pageable memory
 // are four serialised round trips of the copy engine's bounce buffer.
-constexpr size_t STAGE_LIMIT = 8u << 20;
-constexpr size_t STAGE_H2D_OFF = 0, STAGE_D2H_OFF = 4u << 20;   // the upload of a call and its download do not share bytes
 
 int orbb200_download_results(orbb200_ctx* ctx, int n, orbb200_kp_t* kps, uint8_t* desc, int cap_per_img, int* n_out)
 {

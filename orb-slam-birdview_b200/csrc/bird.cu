@@ -72,6 +72,8 @@ struct BirdPlan {
     float* d_qx = nullptr; float* d_qy = nullptr; float* d_qangle = nullptr; int32_t* d_qlevel = nullptr; uint8_t* d_qvalid = nullptr;   // [batch+1][kpPerImg]
     orbb200_kp_t* d_carryKps = nullptr; uint8_t* d_carryDesc = nullptr; int32_t* d_carryCount = nullptr;
     bool carryValid = false;
+    std::vector<uint8_t> hostMask;   // packed copy of the mask whose pyramid image 0's slot of d_mask holds (orbb200_bird_extract of one image)
+    bool maskCacheValid = false;
 };
 
 struct BirdState {
@@ -1573,6 +1575,7 @@ int upload_images(Ctx& c, BirdPlan* p, const uint8_t* const* imgs, const uint8_t
 {
     const BirdGeom& g = p->g;
     const BirdLevel& L0 = g.lv[0];
+    if (masks) p->maskCacheValid = false;           // image 0's mask slot is about to hold something else (see orbb200_bird_extract_batch)
     for (int i = 0; i < n; i++) {
         ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_pyr + (size_t)i * g.planeBytes + L0.off, L0.pitch, imgs[i], stride, g.w, g.h,
                                              cudaMemcpyHostToDevice, c.stream));
@@ -1626,10 +1629,10 @@ void enqueue_blur(Ctx& c, BirdPlan* p, int n, int nLevels, cudaStream_t stream)
 // forkBlur: the caller will run enqueue_compute on the same pyramid (detect + cornerSubPix + compute in one call).  For one or two
 // images the blurred pyramid -- which only compute's descriptors read and which depends on nothing but the pyramid -- is then
 // built on a side stream beside FAST, retainBest and cornerSubPix instead of after them.
-int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nullptr, float* ptsOut = nullptr)
+int enqueue_detect(Ctx& c, BirdPlan* p, int n, int maskMode, bool* forkBlur = nullptr, float* ptsOut = nullptr, bool maskPyramidCached = false)
 {
     const BirdGeom& g = p->g;
-    { StageTimer t(c, 9); enqueue_pyramid(c, p, n, maskMode == 1, BV_LEVELS); }
+    { StageTimer t(c, 9); enqueue_pyramid(c, p, n, maskMode == 1 && !maskPyramidCached, BV_LEVELS); }
     if (forkBlur) *forkBlur = false;
     if (forkBlur && n <= 2 && !c.timing && c.stream4) {
         cudaEventRecord(c.evFork4, c.stream);
@@ -2045,9 +2048,39 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     BirdPlan* p = get_plan(c, w, h, nfeatures, n);
     if (!p) return ORBB200_ERR_CUDA;
     const BirdGeom& g = p->g;
-    int rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
+    if (!c.hostCopies.empty()) { ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream)); deliver_host_copies(c); }   // staged results of an earlier frame step
+    int rc = ORBB200_OK;
+    // One image per call (the birdview block of Frame::Frame, src/Frame.cc:328-342): the image goes through the pinned staging block (a
+    // host memcpy + a true DMA instead of the copy engine's synchronous bounce of pageable memory), the results come back through it
+    // in one synchronisation, and the mask -- the vehicle mask, the same for every frame -- is compared with the copy kept from the last
+    // call: when equal its upload and the seven resize + threshold launches of its pyramid are skipped.
+    const BirdLevel& L0 = g.lv[0];
+    const size_t imgB = (size_t)w * h, outB = 128 + (size_t)g.kpPerImg * 60;
+    const bool staged = c.stageUploads && n == 1 && imgB * 2 <= STAGE_D2H_OFF - STAGE_H2D_OFF && outB <= STAGE_LIMIT - STAGE_D2H_OFF && ensure_scratch(c, 0, STAGE_LIMIT);
+    bool maskCached = false;
+    if (staged) {
+        uint8_t* hs = c.h_scratch + STAGE_H2D_OFF;
+        for (int y = 0; y < h; y++) memcpy(hs + (size_t)y * w, imgs[0] + (size_t)y * stride, (size_t)w);
+        ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_pyr + L0.off, L0.pitch, hs, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, c.stream));
+        if (masks) {
+            maskCached = p->maskCacheValid && p->hostMask.size() == imgB;
+            for (int y = 0; maskCached && y < h; y++) maskCached = memcmp(p->hostMask.data() + (size_t)y * w, masks[0] + (size_t)y * mask_stride, (size_t)w) == 0;
+            if (!maskCached) {
+                p->hostMask.resize(imgB);
+                uint8_t* hm = hs + imgB;
+                for (int y = 0; y < h; y++) {
+                    memcpy(hm + (size_t)y * w, masks[0] + (size_t)y * mask_stride, (size_t)w);
+                    memcpy(p->hostMask.data() + (size_t)y * w, masks[0] + (size_t)y * mask_stride, (size_t)w);
+                }
+                ORBB200_CUDA_OK(c, cudaMemcpy2DAsync(p->d_mask + L0.off, L0.pitch, hm, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, c.stream));
+                p->maskCacheValid = true;
+            }
+        }
+    } else {
+        rc = upload_images(c, p, imgs, masks, n, stride, mask_stride);
+    }
     bool blurForked = false;
-    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0, &blurForked, p->d_pts);
+    if (rc == ORBB200_OK) rc = enqueue_detect(c, p, n, masks != nullptr ? 1 : 0, &blurForked, p->d_pts, maskCached);
     if (rc != ORBB200_OK) return rc;
     // cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + MAX_ITER, 40, 0.001))   (src/Frame.cc:335-336)
     if (g.w >= 15 && g.h >= 15) {
@@ -2056,6 +2089,25 @@ int orbb200_bird_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, con
     }
     rc = enqueue_compute(c, p, n, BV_LEVELS, blurForked, p->d_pts);
     if (rc != ORBB200_OK) return rc;
+    if (staged) {
+        uint8_t* ho = c.h_scratch + STAGE_D2H_OFF;
+        int32_t* hStatus = reinterpret_cast<int32_t*>(ho);
+        int32_t* hCnt = reinterpret_cast<int32_t*>(ho + 64);
+        uint8_t* hK = ho + 128;
+        uint8_t* hD = hK + (size_t)g.kpPerImg * sizeof(orbb200_kp_t);
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hStatus, c.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hCnt, p->d_counts2, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hK, p->d_kps2, (size_t)g.kpPerImg * sizeof(orbb200_kp_t), cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaMemcpyAsync(hD, p->d_desc, (size_t)g.kpPerImg * 32, cudaMemcpyDeviceToHost, c.stream));
+        ORBB200_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+        if (*hStatus != 0) return check_bird_status(c);       // reads, reports and clears the flag
+        const int m = *hCnt;
+        if (m > cap_per_img) { c.err = "bird: output capacity too small"; return ORBB200_ERR_CAPACITY; }
+        memcpy(kps, hK, (size_t)std::max(m, 0) * sizeof(orbb200_kp_t));
+        memcpy(desc, hD, (size_t)std::max(m, 0) * 32);
+        n_out[0] = m;
+        return ORBB200_OK;
+    }
     return download(c, p, n, p->d_kps2, p->d_counts2, kps, desc, cap_per_img, n_out);
 }
 

@@ -200,6 +200,10 @@ struct StageTimer {
 void drain_stage_events(Ctx& c);
 
 bool ensure_scratch(Ctx& c, size_t dev_bytes, size_t host_bytes);
+// The pinned staging block of small host calls: uploads in the lower half, the result mirror in the upper half.
+constexpr size_t STAGE_LIMIT = 8u << 20;
+constexpr size_t STAGE_H2D_OFF = 0, STAGE_D2H_OFF = 4u << 20;   // the upload of a call and its download do not share bytes
+void deliver_host_copies(Ctx& c);      // staged results of an earlier frame step -> the caller's buffers (the stream must have drained)
 const ShapeTables* get_shape(Ctx& c, int w, int h);   // nullptr + c.err on failure
 bool build_geom(const Ctx& c, int w, int h, Geom& g, std::string& err);
 

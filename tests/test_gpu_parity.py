@@ -873,6 +873,27 @@ def test_bird_retain_best_dense_and_tall(pkg):
     assert n0 > 5120, n0                                                                                  # the dense case really is in the last tier
 
 
+def test_bird_single_call_mask_cache(pkg):
+    """One image per call keeps the last mask's pyramid on the device and skips its upload when the next call brings the same mask:
+    same mask, changed mask, no mask, a detect() call in between (it rewrites the mask slot), a strided mask -- each equal to the oracle."""
+    ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
+    B = pkg.BirdviewORB(ctx, 800)
+    imgs = [cases.birdview_case(240, 40 + i)[0] for i in range(6)]
+    mask_a = cases.birdview_case(240, 40)[1]
+    mask_b = mask_a.copy()
+    mask_b[:60, :] = 0
+    wide = np.zeros((240, 300), np.uint8)
+    wide[:, :240] = mask_b
+    seq = [(0, mask_a), (1, mask_a), (2, mask_b), (3, mask_b), (4, None), (5, mask_b), (0, wide[:, :240]), (1, mask_a)]
+    for step, (i, m) in enumerate(seq):
+        k, d = B(imgs[i], m)
+        k0, d0 = oracle.bird_extract(imgs[i], None if m is None else np.ascontiguousarray(m), 800)
+        assert _same_kps(k, k0) and np.array_equal(d, d0), step
+        if step == 4:
+            det = B.detect(imgs[2], mask_a)                  # another entry point writes image 0's mask slot
+            assert _same_kps(det, oracle.bird_detect(imgs[2], mask_a, 800))
+
+
 def test_bird_edge_cases(pkg):
     """No corners, everything masked, images too small for the 31-pixel edge threshold, strided input, empty inputs."""
     ctx = pkg.Context(1000, 1.2, 8, 20, 7, 64, 64)
