@@ -555,6 +555,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
     c.selectTiers = std::getenv("ORBB200_SELECT_TIERS") != nullptr;
     c.stageMatch = std::getenv("ORBB200_NO_STAGED_MATCH") == nullptr;
     c.warpCands = std::getenv("ORBB200_NO_WARP_CANDS") == nullptr;
+    if (const char* e = std::getenv("ORBB200_STAGE_MAX_KB")) c.stageMaxBytes = (size_t)std::max(0, atoi(e)) << 10;
     c.forkBird = std::getenv("ORBB200_FORK_BIRD") != nullptr;      // measured: beside the front extraction it is 3 % SLOWER than after it (6.86 vs 6.65 ms per 128 frames)
     c.fastCells = std::getenv("ORBB200_FAST_CELLS") != nullptr;
     c.stageUploads = std::getenv("ORBB200_NO_STAGED_UPLOAD") == nullptr;
@@ -772,7 +773,7 @@ int orbb200_extract_batch(orbb200_ctx* ctx, const uint8_t* const* imgs, int n, i
     const size_t imgB = (size_t)w * h;
     // measured per call: 752x480 0.241 -> 0.223 ms, 1241x376 0.370 -> 0.252 ms staged; 1920x1080 0.458 -> 0.497 ms (the host memcpy of
     // 2 MB costs more than the bounce saves): staged up to 1.5 MB per call
-    const bool staged = c.stageUploads && imgB * n <= (3u << 19) && ensure_scratch(c, 0, STAGE_LIMIT);
+    const bool staged = c.stageUploads && imgB * n <= c.stageMaxBytes && ensure_scratch(c, 0, STAGE_LIMIT);
     // One or two staged images whose results fit the mirror half of the block: ONE graph launch does the upload (the first kernel
     // reads the pinned rows over PCIe), the extraction and the delivery (the last kernel also stores into the pinned mirror) --
     // no copy-engine operation on either side.  Measured per call (752x480 / 1241x376): 0.195 / 0.199 -> see DESIGN.md section 5.

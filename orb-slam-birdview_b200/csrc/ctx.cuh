@@ -104,6 +104,7 @@ struct Ctx {
     bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)
     std::string err;
     long long launches = 0;
+    size_t stageMaxBytes = 3u << 19;         // largest host call (bytes of images) that goes through the pinned staging block (ORBB200_STAGE_MAX_KB)
     bool stageUploads = true;                // small host-API batches upload through the pinned staging block (ORBB200_NO_STAGED_UPLOAD=1: straight from the caller's memory)
     bool fastCells = false;                  // ORBB200_FAST_CELLS=1: grid FAST with one CTA per cell (fast_cells_kernel) instead of the strip form
     int subpixCtasPerSm = 3;                 // resident CTAs per SM of bird_subpix5_kernel (tuning knob, ORBB200_SUBPIX_CTAS: 1-2 reach-5 patches, 3 reach-3, 4 reach-2)
