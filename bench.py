@@ -593,7 +593,18 @@ def dist_setup(args):
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local)
-        dist_.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # stdout carries ONE JSON line: NCCL prints its version banner (and, with NCCL_DEBUG=INFO, its log) to file descriptor 1 when
+        # the communicator is created, so descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist_.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         dist = dist_
     return rank, world, local, dist
 
