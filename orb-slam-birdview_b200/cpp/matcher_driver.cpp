@@ -10,6 +10,7 @@
 //          int32 nmBird; int32 vnMatches12[n1]; int32 nmSearchByMatchBird; int32 bird_mp_of_kp2[n2] (LastFrame keypoint index or -1);
 //          int32 DescriptorDistance(desc1[0], desc2[0]); int32 nTri (-1: no keyframe section); int32 pairs[nTri][2]
 // optional keyframe section of case.bin: see the reader below
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -101,6 +102,22 @@ int main(int argc, char** argv)
     std::vector<int> vnMatches12;
     const int nmBird = matcherBird.BirdviewMatch(Last, Cur, vnMatches12, window);
     const int nmSBM = matcherBird.SearchByMatchBird(Cur, Last, window);
+
+    // ORBB200_MATCHER_TIME=N: wall time per call of the two per-frame searches through the adapters and the objects (the frame's device
+    // copy is cached by content after the first call, as Tracking's three to five searches on one Frame find it)
+    if (const char* e = getenv("ORBB200_MATCHER_TIME")) {
+        const int reps = atoi(e) > 0 ? atoi(e) : 100;
+        const std::vector<MapPoint*> initial = [&] { std::vector<MapPoint*> v(nF, static_cast<MapPoint*>(NULL)); for (int i = 0; i < nF; i++) if (kpObs[i] >= 0) v[i] = &existing[i]; return v; }();
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t0 = now();
+        for (int r = 0; r < reps; r++) { F.mvpMapPoints = initial; matcher.SearchByProjection(F, vpLocalMapPoints, th); }
+        const double msProj = (now() - t0) / reps;
+        t0 = now();
+        for (int r = 0; r < reps; r++) matcherBird.BirdviewMatch(Last, Cur, vnMatches12, window);
+        const double msBird = (now() - t0) / reps;
+        printf("TIMING {\"keypoints\": %d, \"map_points\": %d, \"SearchByProjection_ms\": %.4f, \"bird_keypoints\": %d, \"BirdviewMatch_ms\": %.4f}\n",
+               nF, nq, msProj, n2, msBird);
+    }
 
     // ---- two keyframes: LocalMapping::CreateNewMapPoints -> matcher.SearchForTriangulation(mpCurrentKeyFrame, pKF2, F12, vMatchedIndices, false)
     std::vector<std::pair<size_t, size_t> > vMatchedIndices;
