@@ -537,6 +537,7 @@ int orbb200_create(orbb200_ctx** out, int device, int nfeatures, float scaleFact
         cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c.stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.evBirdCarry, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evFork4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evJoin4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.evFork0, cudaEventDisableTiming) != cudaSuccess ||
@@ -650,6 +651,7 @@ void orbb200_destroy(orbb200_ctx* ctx)
     if (c.evFork0) cudaEventDestroy(c.evFork0);
     if (c.evJoin0) cudaEventDestroy(c.evJoin0);
     if (c.stream3) cudaStreamDestroy(c.stream3);
+    if (c.evBirdCarry) cudaEventDestroy(c.evBirdCarry);
     if (c.evFork4) cudaEventDestroy(c.evFork4);
     if (c.evJoin4) cudaEventDestroy(c.evJoin4);
     if (c.stream4) cudaStreamDestroy(c.stream4);
@@ -1889,9 +1891,10 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
         if (fork) {
             launch_grid_build(c, plan->dF + n, n);
             if (nBirdJobs > 0) launch_window_match(c, plan->dJ + nFrontJobs, nBirdJobs, birdKpi, birdKpi);
-            rc = bird_step_carry(c, bv, n);
+            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdJoin, c.streamBird));        // the birdview results are complete here
+            rc = bird_step_carry(c, bv, n);                                          // (only the next step needs these copies)
             if (rc != ORBB200_OK) return rc;
-            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdJoin, c.streamBird));
+            ORBB200_CUDA_OK(c, cudaEventRecord(c.evBirdCarry, c.streamBird));
         }
     }
     // front camera: both images of every frame in one extraction, then the stereo matcher on its pools
@@ -1913,7 +1916,13 @@ int orbb200_frame_step_device(orbb200_ctx* ctx, const orbb200_frame_step_params*
     if (fork) {                                    // the birdview frames were matched on their own stream
         launch_grid_build(c, plan->dF, n);
         if (nFrontJobs > 0) launch_window_match(c, plan->dJ, nFrontJobs, std::max(mapN, 1), kpi);
-        ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0));
+        // The host variant joins later: its front-camera downloads go ahead of the wait for the (longer) birdview path, and the carry
+        // copies are only waited for at the very end.  Everybody else gets a fully joined stream back.
+        if (c.deferBirdJoin) c.birdJoinPending = true;
+        else {
+            ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0));
+            ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdCarry, 0));
+        }
     } else {
         { StageTimer t(c, 6); launch_grid_build(c, plan->dF, plan->nFrames); }
         if (plan->nJobs > 0) { StageTimer t(c, 7); launch_window_match(c, plan->dJ, plan->nJobs, plan->maxNq, plan->maxKpCap); }
@@ -2049,14 +2058,29 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         dout.map_best_idx = A.take<int32_t>(Qm); dout.map_best_dist = A.take<int32_t>(Qm); dout.map_nmatches = A.take<int32_t>(n);
     }
     if (hasBird) { dout.bird_matches12 = A.take<int32_t>(Qb); dout.bird_nmatches = A.take<int32_t>(n); }
+    struct JoinFlags { bool& d; bool& pnd; ~JoinFlags() { d = false; pnd = false; } } joinFlags{c.deferBirdJoin, c.birdJoinPending};
     if (replay) {                                   // host-side state the enqueueing path leaves behind
         const ShapeTables* st = get_shape(c, p->w, p->h);
         if (!st) { c.hostCopies.clear(); return ORBB200_ERR_UNSUPPORTED; }
         c.cur = st; c.curN = ni; c.stereoValid = p->mb > 0.f;
     } else {
+        c.deferBirdJoin = true;
         rc = orbb200_frame_step_device(ctx, p, &din, &dout);
-        if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
+        c.deferBirdJoin = false;
+        if (rc != ORBB200_OK) {
+            if (c.birdJoinPending) { cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0); cudaStreamWaitEvent(c.stream, c.evBirdCarry, 0); }
+            c.hostCopies.clear();
+            return rc;
+        }
     }
+    // join the birdview path (deferred by orbb200_frame_step_device on request): before the first birdview download, and the carry
+    // copies before the call is over
+    auto join_bird = [&]() -> cudaError_t {
+        if (!c.birdJoinPending) return cudaSuccess;
+        c.birdJoinPending = false;
+        return cudaStreamWaitEvent(c.stream, c.evBirdJoin, 0);
+    };
+    const bool carryPending = c.birdJoinPending;
     const int kpi = c.cur->g.kpPerImg;
     if (out->kps || out->desc || out->u_right || out->depth) {
         if (out->cap <= 0) { c.err = "frame_step_host: cap"; c.hostCopies.clear(); return ORBB200_ERR_ARG; }
@@ -2074,9 +2098,10 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         if (out->map_nmatches) ORBB200_CUDA_OK(c, d2h(out->map_nmatches, 4 * (size_t)n, dout.map_nmatches, 4 * (size_t)n, 4 * (size_t)n, 1));
     }
     if (hasBird) {
+        ORBB200_CUDA_OK(c, join_bird());
         const orbb200_kp_t* bKps = nullptr; const uint8_t* bDesc = nullptr; const int32_t* bCnt = nullptr; int bcap = 0;
         rc = orbb200_bird_results_device(ctx, p->bird_w, p->bird_h, p->bird_nfeatures, &bKps, &bDesc, &bCnt, &bcap);
-        if (rc != ORBB200_OK) { c.hostCopies.clear(); return rc; }
+        if (rc != ORBB200_OK) { if (carryPending) cudaStreamWaitEvent(c.stream, c.evBirdCarry, 0); c.hostCopies.clear(); return rc; }
         if (out->bird_kps || out->bird_desc || out->bird_matches12) {
             if (out->bird_cap <= 0) { c.err = "frame_step_host: bird_cap"; c.hostCopies.clear(); return ORBB200_ERR_ARG; }
             const int take = std::min(out->bird_cap, bk);
@@ -2087,6 +2112,8 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         if (out->bird_counts) ORBB200_CUDA_OK(c, d2h(out->bird_counts, 4 * (size_t)n, bCnt, 4 * (size_t)n, 4 * (size_t)n, 1));
         if (out->bird_nmatches) ORBB200_CUDA_OK(c, d2h(out->bird_nmatches, 4 * (size_t)n, dout.bird_nmatches, 4 * (size_t)n, 4 * (size_t)n, 1));
     }
+    ORBB200_CUDA_OK(c, join_bird());
+    if (carryPending) ORBB200_CUDA_OK(c, cudaStreamWaitEvent(c.stream, c.evBirdCarry, 0));
     if (capture) {
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;

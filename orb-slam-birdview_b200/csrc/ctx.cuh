@@ -100,6 +100,8 @@ struct Ctx {
     bool splitLevel0 = true;                 // the level-0 branch for one or two images (ORBB200_NO_SPLIT=1 turns it off)
     cudaStream_t streamBird = nullptr;       // the birdview front-end of the batched frame step runs beside the front-camera extraction
     cudaEvent_t evBirdFork = nullptr, evBirdJoin = nullptr;
+    cudaEvent_t evBirdCarry = nullptr;       // the carry copies behind the birdview matching (only the next step needs them)
+    bool deferBirdJoin = false, birdJoinPending = false;   // orbb200_frame_step_host joins the birdview stream itself, behind its front-camera downloads
     bool birdForkRecorded = false;           // orbb200_frame_step_host has recorded evBirdFork behind the birdview upload
     bool forkBird = false;                   // ORBB200_FORK_BIRD=1 turns it on (measured slower: the GPU is already full)
     std::string err;
