@@ -2119,6 +2119,7 @@ int orbb200_frame_step_host(orbb200_ctx* ctx, const orbb200_frame_step_params* p
         cudaGraphExec_t exec = nullptr;
         guard.on = false;
         cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+        if (e == cudaSuccess && std::getenv("ORBB200_TEST_CAPTURE_FAIL")) e = cudaErrorUnknown;      // (test hook: exercises the fall-back below)
         if (e == cudaSuccess && c.allocEpoch == epoch0) e = cudaGraphInstantiate(&exec, graph, 0);
         else if (e == cudaSuccess) e = cudaErrorUnknown;       // something was (re)allocated while recording: the recording is not trusted
         if (graph) cudaGraphDestroy(graph);

@@ -1042,6 +1042,31 @@ def test_frame_step_one_frame_per_call_replayed_graph(pkg):
     assert len(set(launches[1:])) == 1 and launches[1] > 30, launches
 
 
+def test_frame_step_recording_failure_falls_back(pkg, monkeypatch):
+    """When the recording of a frame step cannot be turned into a graph, the call that tried runs eagerly instead (nothing has
+    executed at that point) and the parameter set is never recorded again: results stay equal to the oracle call after call."""
+    monkeypatch.setenv("ORBB200_TEST_CAPTURE_FAIL", "1")
+    w, h, bw, bh, nfeat, bnf, nmap = 620, 188, 200, 200, 1000, 600, 1500
+    seq = synth.northstar_sequence(6, 31, w=w, h=h, bird=(bw, bh), vehicle=(40, 60))
+    orc = oracle.Extractor(nfeat, 1.2, 8, 20, 7)
+    mp = synth.northstar_map(seq, lambda im: orc(im), nmap, 3)
+    ctx = pkg.Context(nfeat, 1.2, 8, 20, 7, w, h, 2)
+    M = pkg.LocalMap(ctx, mp["pos"], mp["normal"], mp["max_distance"], mp["min_distance"], mp["desc"])
+    step = pkg.FrameStep(ctx, w, h, M, mb=0.537, mbf=386.1448, th=1.0, nnratio=0.8, bird_size=(bw, bh), bird_nfeatures=bnf,
+                         bird_mask=seq["bird_mask"], bird_window=15, bird_nnratio=0.99)
+    poses = [pkg.CameraPose.make(**p) for p in seq["poses"]]
+    prev = None
+    for i in range(6):
+        out = step(seq["imgs"][2 * i:2 * i + 2], seq["bird_imgs"][i:i + 1], poses[i:i + 1], chain=i > 0)
+        (r,), prev = _oracle_frame_step(seq, mp, [i], nfeat, bnf, w, h, bw, bh, 1.0, 0.8, 15, 0.99, prev)
+        nl, nb = out["counts"][0], out["bird_counts"][0]
+        assert out["kps"][0][:nl].tobytes() == r["kl"].tobytes() and np.array_equal(out["desc"][0][:nl], r["dl"]), i
+        assert out["map_nmatches"][0] == r["nm"] and np.array_equal(out["map_best_idx"][0], r["bi"]), i
+        assert out["bird_kps"][0][:nb].tobytes() == r["bk"].tobytes() and np.array_equal(out["bird_desc"][0][:nb], r["bdsc"]), i
+        if r["m12"] is not None:
+            assert out["bird_nmatches"][0] == r["nbm"] and np.array_equal(out["bird_matches12"][0][:len(r["m12"])], r["m12"]), i
+
+
 def test_frame_step_replay_survives_reallocation(pkg):
     """A recorded frame step holds device and pinned pointers.  Replacing the local map, changing the birdview mask and growing
     the staging blocks (a larger matcher call, a batch of two) between replayed calls must drop the recording, not replay it on
