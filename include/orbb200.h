@@ -414,7 +414,7 @@ int orbb200_device_status(orbb200_ctx* ctx, int* status);
 #define ORBB200_NUM_STAGES 16
 int orbb200_stage_timing(orbb200_ctx* ctx, int enable);
 /* Synchronises, then returns accumulated milliseconds and launch-group counts per stage; reset!=0 clears. */
-int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[9]*/, int32_t* groups /*[9]*/, int reset);
+int orbb200_stage_times(orbb200_ctx* ctx, float* ms /*[ORBB200_NUM_STAGES]*/, int32_t* groups /*[ORBB200_NUM_STAGES]*/, int reset);
 /* Measured POPC issue rate of this device in G popc/s (denominator of the matching roofline). */
 double orbb200_measure_popc_peak(orbb200_ctx* ctx);
 
