@@ -870,7 +870,8 @@ def leg_per_frame(arm, frames=12):
         # the same frame step and the same extraction from C++ with no interpreter in the loop (tools/ubench/*.cu, built by
         # __graft_entry__.build()): wall ms per call and the device chain alone (CUDA events)
         cpp = {}
-        for name, args in (("frame_timeline", ["100"]), ("call_timeline", ["752", "480", "1000", "200"]), ("call_timeline", ["1241", "376", "2000", "200"])):
+        for name, args in (("frame_timeline", ["100"]), ("call_timeline", ["752", "480", "1000", "200"]), ("call_timeline", ["1241", "376", "2000", "200"]),
+                           ("concurrent_calls", ["1241", "376", "2000", "200"])):
             exe = os.path.join(ROOT, "tools", "ubench", name)
             if os.path.exists(exe):
                 r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
