@@ -90,6 +90,19 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def host_cpu_model():
+    """CPU model of the box the CPU arm runs on (core count and model go into the line)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    import platform
+    return platform.processor() or platform.machine()
+
+
 def make_pool(B, seed, extract):
     """One input batch: a B-frame sequence (front L/R + birdview + poses) and its local map."""
     synth = _synth()
@@ -1131,7 +1144,7 @@ def cpu_baseline(seq, with_full, target_s=12.0):
                "sample": f"{n} stereo frames of the C2 workload on {cores} host threads ({dt:.1f} s); 1 thread: {1.0 / t1:.2f} frames/s; "
                          + ("ORBextractor = the reference's own src/ORBextractor.cc compiled unmodified (oracle/_ref; its OpenCV primitives are the "
                             "cv2-pinned scalar restatements), isInFrustum + SearchByProjection = oracle port" if cpu.use_ref else "oracle port"),
-               "single_thread_value": 1.0 / t1, "native_build": cpu.native,
+               "single_thread_value": 1.0 / t1, "native_build": cpu.native, "cpu_model": host_cpu_model(),
                "per_stage": cpu_stage_report(seq["imgs"][0], 1e3 * cores / (2 * n / dt))}
         if with_full:
             t1f = one.run(seq, [1], full=True)[0]
@@ -1196,7 +1209,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config_dict(B, P),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "cpu_model": host_cpu_model(),
                          "sample": f"{F} stereo frames per step on {cores} host threads (persistent pool, per-thread extractors), native_build={cpu.native}; "
                                    "ORBextractor = the reference's own source compiled unmodified (oracle/_ref), matcher = oracle port"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
