@@ -10,6 +10,10 @@
 #include <thread>
 #include <vector>
 
+#include <cstring>
+
+#include <cuda_runtime.h>
+
 #include "orbb200.h"
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -18,6 +22,9 @@ int main(int argc, char** argv)
 {
     const int w = argc > 1 ? atoi(argv[1]) : 1241, h = argc > 2 ? atoi(argv[2]) : 376, nf = argc > 3 ? atoi(argv[3]) : 2000;
     const int reps = argc > 4 ? atoi(argv[4]) : 300;
+    // "dev": the image is already on the device and the results stay there (orbb200_extract_device + orbb200_sync): the same kernels
+    // without the host side of the call -- tells whether the threads are held up by the device chain or by the copies around it
+    const bool dev = argc > 5 && !strcmp(argv[5], "dev");
     const int maxT = 8;
     // one image per thread (different content: no two threads do the same work)
     std::vector<std::vector<uint8_t>> imgs(maxT, std::vector<uint8_t>((size_t)w * h));
@@ -34,8 +41,14 @@ int main(int argc, char** argv)
     for (int t = 0; t < maxT; t++)
         if (orbb200_create(&ctx[t], 0, nf, 1.2f, 8, 20, 7, w, h, 2) != 0) { fprintf(stderr, "create: %s\n", orbb200_last_error(nullptr)); return 1; }
     const int cap = orbb200_max_keypoints(ctx[0]);
+    std::vector<uint8_t*> dimg(maxT, nullptr);
+    if (dev)
+        for (int t = 0; t < maxT; t++) {
+            cudaMalloc(&dimg[t], imgs[t].size());
+            cudaMemcpy(dimg[t], imgs[t].data(), imgs[t].size(), cudaMemcpyHostToDevice);
+        }
     std::vector<int> first(maxT, -1);
-    printf("{\"w\": %d, \"h\": %d, \"nfeatures\": %d, \"calls_per_thread\": %d, \"threads\": {", w, h, nf, reps);
+    printf("{\"w\": %d, \"h\": %d, \"nfeatures\": %d, \"calls_per_thread\": %d, \"mode\": \"%s\", \"threads\": {", w, h, nf, reps, dev ? "device-resident" : "host");
     bool ok = true;
     for (int T = 1, k = 0; T <= maxT; T *= 2, k++) {
         std::atomic<int> ready{0}, bad{0};
@@ -51,10 +64,15 @@ int main(int argc, char** argv)
                 for (int i = 0; i < 5; i++)
                     if (orbb200_extract(ctx[t], imgs[t].data(), w, h, w, kps.data(), desc.data(), cap, &n) != 0) bad++;
                 if (first[t] < 0) first[t] = n;
+                for (int i = 0; dev && i < 5; i++) { orbb200_extract_device(ctx[t], dimg[t], imgs[t].size(), 1, w, h, w); orbb200_sync(ctx[t]); }
                 ready++;
                 while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
                 const double s0 = now_ms();
                 for (int i = 0; i < reps; i++) {
+                    if (dev) {
+                        if (orbb200_extract_device(ctx[t], dimg[t], imgs[t].size(), 1, w, h, w) != 0 || orbb200_sync(ctx[t]) != 0) bad++;
+                        continue;
+                    }
                     if (orbb200_extract(ctx[t], imgs[t].data(), w, h, w, kps.data(), desc.data(), cap, &n) != 0) bad++;
                     if (n != first[t]) bad++;                   // the same image gives the same keypoints whatever runs beside it
                 }
