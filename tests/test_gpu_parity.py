@@ -1181,6 +1181,40 @@ def test_three_host_threads_three_contexts(pkg):
     assert want_tri[0] > 0 and want_bow[0] > 0
 
 
+def test_eight_extraction_threads_match_oracle(pkg):
+    """The drop-in call from many threads (the reference extracts L and R on two threads, src/Frame.cc:124-127; tools/ubench/
+    concurrent_calls.cu measures 1-8): eight host threads, one extractor (= one context) each on ONE GPU, every thread calls
+    operator() on one image per call -- the one-graph staged path, eight graphs replayed concurrently -- and every result of every
+    call must be the oracle's, byte for byte."""
+    import threading
+    shapes = [(240, 320, 500), (188, 620, 800)]
+    imgs = {sh: [synth.synth_frame(sh[0], sh[1], 1300 + 10 * k + i) for i in range(3)] for k, sh in enumerate(shapes)}
+    want = {sh: [oracle.Extractor(sh[2], 1.2, 8, 20, 7)(im) for im in imgs[sh]] for sh in shapes}
+    T, reps = 8, 30
+    errors, start = [], threading.Barrier(T)
+
+    def worker(t):
+        try:
+            sh = shapes[t % 2]
+            ex = pkg.ORBextractor(sh[2], 1.2, 8, 20, 7, max_size=(sh[1], sh[0]))
+            start.wait()
+            for r in range(reps):
+                i = (r + t) % 3
+                k, d = ex(imgs[sh][i])
+                k0, d0 = want[sh][i]
+                assert k.tobytes() == k0.tobytes() and np.array_equal(d, d0), f"thread {t} rep {r}"
+        except Exception as e:            # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    assert all(len(k0) > 100 for sh in shapes for k0, _ in want[sh])
+
+
 def test_two_contexts_different_feature_budgets(pkg):
     """the dynamic shared-memory opt-in is per (device, kernel); a second context with a smaller node table must not
     lower the first one's limit."""
