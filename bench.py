@@ -597,7 +597,22 @@ def parity_check(n_frames=3, device=0):
     return res
 
 
+RANK_PLACEMENT = "packed"      # how dist_setup mapped the local ranks to GPUs (goes into the JSON line)
+
+
+def place_rank(local, world, ndev):
+    """Which GPU a local rank uses when fewer ranks than GPUs run on the box.  Pinned host-to-device copies are capped per group of
+    four GPUs of an 8-GPU box (~116-128 GB/s for GPUs 0-3, the same for 4-7; one or two copying ranks per group lose nothing, four get
+    29 GB/s each instead of 55: profiles/r2f_n4_placement.json), and the end-to-end leg is bound by exactly those copies -- so the ranks
+    alternate between the two halves: 0, 4, 1, 5, ...  With as many ranks as visible GPUs (or ORBB200_RANK_PLACEMENT=packed) rank i
+    uses GPU i."""
+    if os.environ.get("ORBB200_RANK_PLACEMENT", "") == "packed" or world < 2 or ndev < 4 or ndev % 2 or world >= ndev:
+        return local, "packed"
+    return (local // 2) + (local % 2) * (ndev // 2), "spread over the two halves of the box (host-I/O groups)"
+
+
 def dist_setup(args):
+    global RANK_PLACEMENT
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -605,6 +620,7 @@ def dist_setup(args):
     if world > 1:
         import torch
         import torch.distributed as dist_
+        local, RANK_PLACEMENT = place_rank(local, world, torch.cuda.device_count() if args.impl == "ours" else 0)
         torch.cuda.set_device(local)
         # stdout carries ONE JSON line: NCCL prints its version banner (and, with NCCL_DEBUG=INFO, its log) to file descriptor 1 when
         # the communicator is created, so descriptor 1 points at stderr while that happens
@@ -1112,6 +1128,7 @@ def run_ours(args):
         "e2e_solo_rank0_frames_per_s": (B * K / e2e_solo_s) if e2e_solo_s else None,
         "host_memcpy_gbs_all_cores": {"value": host_gbs[0], "threads": host_gbs[1]} if host_gbs else None,
         "gpu_launches": int(launches),
+        "rank_placement": {"how": RANK_PLACEMENT, "rank0_gpu": int(local), "visible_gpus": int(torch.cuda.device_count())},
         "clocks": clocks,
         "roofline": roofline,
         "stage_ms_per_step": {STAGES[i]: float(st_ms[i] / K) for i in range(9)},
