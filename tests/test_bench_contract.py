@@ -27,3 +27,21 @@ def test_reference_arm_line():
     import bench
     assert d["config"] == bench.config_dict(128, 3)
     assert d["gpu_launches"] == 0
+
+
+def test_rank_placement_is_a_distinct_gpu_per_rank(monkeypatch):
+    """bench.place_rank: fewer ranks than GPUs are spread over the two halves of the box (0, 4, 1, 5, ...), every rank gets its own GPU,
+    as many ranks as GPUs (or ORBB200_RANK_PLACEMENT=packed) is the identity."""
+    import bench
+    monkeypatch.delenv("ORBB200_RANK_PLACEMENT", raising=False)
+    for ndev in (2, 4, 8, 16):
+        for world in range(1, ndev + 1):
+            gpus = [bench.place_rank(l, world, ndev)[0] for l in range(world)]
+            assert len(set(gpus)) == world and all(0 <= g < ndev for g in gpus), (ndev, world, gpus)
+            if world == ndev or world == 1 or ndev < 4:
+                assert gpus == list(range(world))
+    assert [bench.place_rank(l, 4, 8)[0] for l in range(4)] == [0, 4, 1, 5]
+    assert [bench.place_rank(l, 2, 8)[0] for l in range(2)] == [0, 4]
+    assert bench.place_rank(3, 4, 7) == (3, "packed")                # odd GPU counts: no halves
+    monkeypatch.setenv("ORBB200_RANK_PLACEMENT", "packed")
+    assert [bench.place_rank(l, 4, 8)[0] for l in range(4)] == [0, 1, 2, 3]
